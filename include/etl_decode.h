@@ -1,0 +1,332 @@
+/*
+ * etl_decode.h — C ABI of the B200 batched pgoutput (CDC) decode engine.
+ *
+ * This is the drop-in boundary for supabase/etl's streaming-replication hot path. The reference
+ * has no FFI seam at the decoder; the entry points below are what a Rust shim in `crates/etl`
+ * binds in place of:
+ *
+ *   reference interface replaced                                   | entry point here
+ *   ---------------------------------------------------------------+-----------------------------
+ *   EventsStream::poll_next  (crates/etl/src/replication/stream.rs:291-306): one parsed message
+ *     per poll → raw CopyData bodies appended to a pinned staging buffer              | etl_stage_*
+ *   SchemaStore / SharedTableCache lookups done per message
+ *     (crates/etl/src/replication/apply.rs:2062-2079, :3324-3357)                   | etl_dec_put_table_schema
+ *   ApplyLoop::handle_replication_message → handle_logical_replication_message →
+ *     handle_{begin,commit,relation,insert,update,delete,truncate}_message
+ *     (apply.rs:1687-2248) + conversions::event::parse_event_from_*_message
+ *     (crates/etl/src/conversions/event.rs:276-543) + parse_cell_from_postgres_text
+ *     (crates/etl/src/conversions/text.rs:28-173) for a whole batch at once          | etl_dec_decode
+ *   Vec<Event> handed to ApplyLoopState::add_event_to_batch (apply.rs:433-439)        | etl_dec_batch_* accessors
+ *
+ * Conventions: every function returns 0 on success and a non-zero
+ * `etl_status` on infrastructure failure (CUDA, allocation, bad arguments). DATA errors are not
+ * return codes: they are reported as `first_error` inside a successfully returned batch whose
+ * records [0, first_error.record_index) are valid — mirroring apply.rs:1595-1599 where earlier
+ * events stay in the batch and the failing message returns Err. One ctx per apply loop; calls on
+ * one ctx are not re-entrant. All integers are host (little-endian) order. No torch / C++ types
+ * cross this boundary.
+ */
+#ifndef ETL_DECODE_H
+#define ETL_DECODE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ETL_DECODE_ABI_VERSION 1u
+
+/* ---------------------------------------------------------------- status codes */
+typedef enum etl_status {
+  ETL_OK = 0,
+  ETL_ERR_INVALID_ARG = 1,
+  ETL_ERR_CUDA = 2,
+  ETL_ERR_ALLOC = 3,
+  ETL_ERR_NO_DEVICE = 4,
+  ETL_ERR_INTERNAL = 5,
+} etl_status;
+
+/* ---------------------------------------------------------------- record kinds
+ * rec_kind is the pgoutput tag byte of the frame (XLogData 'w' frames), or 'k' for a primary
+ * keepalive frame. Grammar: SURVEY.md Appendix B. */
+enum {
+  ETL_REC_BEGIN = 'B',
+  ETL_REC_COMMIT = 'C',
+  ETL_REC_ORIGIN = 'O',
+  ETL_REC_RELATION = 'R',
+  ETL_REC_TYPE = 'Y',
+  ETL_REC_INSERT = 'I',
+  ETL_REC_UPDATE = 'U',
+  ETL_REC_DELETE = 'D',
+  ETL_REC_TRUNCATE = 'T',
+  ETL_REC_MESSAGE = 'M',
+  ETL_REC_KEEPALIVE = 'k',
+};
+
+/* rec_flags bits */
+enum {
+  ETL_RF_OLD_FULL = 0x01,    /* 'O' image present: OldTableRow::Full   (event.rs:445-448) */
+  ETL_RF_OLD_KEY = 0x02,     /* 'K' image present: OldTableRow::Key    (event.rs:441-444) */
+  ETL_RF_NEW_PARTIAL = 0x04, /* UpdatedTableRow::Partial               (event.rs:662-667) */
+  ETL_RF_DDL_MESSAGE = 0x08, /* 'M' whose prefix is supabase_etl_ddl   (event.rs:31)      */
+  ETL_RF_EVENT = 0x80,       /* the reference emits an Event for this frame               */
+};
+
+/* ---------------------------------------------------------------- cell tags = Cell variants
+ * crates/etl/src/types/cell.rs:38-76, in declaration order. */
+enum {
+  ETL_CELL_NULL = 0,
+  ETL_CELL_BOOL = 1,        /* val = 0|1 */
+  ETL_CELL_STRING = 2,      /* val = byte offset into the staged stream, aux = byte length (zero copy) */
+  ETL_CELL_I16 = 3,         /* val = sign-extended value */
+  ETL_CELL_I32 = 4,
+  ETL_CELL_U32 = 5,
+  ETL_CELL_I64 = 6,
+  ETL_CELL_F32 = 7,         /* val = IEEE-754 bits (low 32) */
+  ETL_CELL_F64 = 8,         /* val = IEEE-754 bits */
+  ETL_CELL_NUMERIC = 9,     /* val = heap offset of etl_numeric_hdr, aux = number of base-10000 digits */
+  ETL_CELL_DATE = 10,       /* val = days since 1970-01-01 (signed) */
+  ETL_CELL_TIME = 11,       /* val = seconds since midnight, aux = nanoseconds (>= 1e9 only for :60 leap second) */
+  ETL_CELL_TIMESTAMP = 12,  /* val = seconds since 1970-01-01T00:00:00 (naive), aux = nanoseconds */
+  ETL_CELL_TIMESTAMPTZ = 13,/* val = UTC seconds since the unix epoch, aux = nanoseconds */
+  ETL_CELL_UUID = 14,       /* val = heap offset of 16 big-endian bytes */
+  ETL_CELL_JSON = 15,       /* val = stream byte offset, aux = byte length of the VALIDATED json text */
+  ETL_CELL_BYTES = 16,      /* val = heap offset of decoded bytes, aux = length */
+  ETL_CELL_ARRAY = 17,      /* val = heap offset of etl_array_hdr, aux = element count */
+  ETL_CELL_MISSING = 254,   /* unresolved UnchangedToast → PartialTableRow missing index (event.rs:641-656) */
+};
+
+/* column decode classes derived from the type oid exactly as text.rs:28-173 dispatches */
+enum {
+  ETL_K_BOOL = 1, ETL_K_STRING = 2, ETL_K_I16 = 3, ETL_K_I32 = 4, ETL_K_U32 = 5, ETL_K_I64 = 6,
+  ETL_K_F32 = 7, ETL_K_F64 = 8, ETL_K_NUMERIC = 9, ETL_K_DATE = 10, ETL_K_TIME = 11,
+  ETL_K_TIMESTAMP = 12, ETL_K_TIMESTAMPTZ = 13, ETL_K_UUID = 14, ETL_K_JSON = 15, ETL_K_BYTES = 16,
+  ETL_K_ARRAY = 0x20, /* ETL_K_ARRAY | element kind */
+};
+
+/* numeric heap entry: header followed by `aux` little-endian int16 base-10000 digits.
+ * crates/etl/src/conversions/numeric.rs:67-88 */
+typedef struct etl_numeric_hdr {
+  uint8_t kind;   /* 0 value, 1 NaN, 2 +Infinity, 3 -Infinity */
+  uint8_t sign;   /* 0 positive, 1 negative */
+  int16_t weight;
+  uint16_t scale;
+  uint16_t _pad;
+} etl_numeric_hdr;
+
+/* array heap entry: header followed by n_elems etl_array_elem (8-byte aligned). Element payloads
+ * (unescaped strings, numerics, bytes, uuids) live in the heap at elem.val. text.rs:184-249 */
+typedef struct etl_array_hdr {
+  uint8_t elem_kind; /* ETL_K_* of the element type */
+  uint8_t _pad[3];
+  uint32_t n_elems;
+} etl_array_hdr;
+typedef struct etl_array_elem {
+  uint64_t val;
+  uint32_t aux;
+  uint8_t tag;   /* ETL_CELL_* (ETL_CELL_NULL for a NULL element) */
+  uint8_t _pad[3];
+} etl_array_elem;
+
+/* ---------------------------------------------------------------- data-error descriptions
+ * (ErrorKind, description) pairs the path can raise. crates/etl/src/error.rs */
+typedef enum etl_error_kind {
+  ETL_EK_NONE = 0,
+  ETL_EK_CONVERSION_ERROR = 1,
+  ETL_EK_INVALID_DATA = 2,
+  ETL_EK_DESERIALIZATION_ERROR = 3,
+  ETL_EK_INVALID_STATE = 4,
+  ETL_EK_VALIDATION_ERROR = 5,
+  ETL_EK_CORRUPTED_TABLE_SCHEMA = 6,
+  ETL_EK_MISSING_TABLE_SCHEMA = 7,
+  ETL_EK_SOURCE_ERROR = 8, /* malformed frame: the third-party parser returns io::Error */
+} etl_error_kind;
+
+typedef enum etl_error_code {
+  ETL_E_NONE = 0,
+  ETL_E_UTF8 = 1,               /* ConversionError  "UTF-8 conversion failed"            error.rs:480-489 */
+  ETL_E_PARSE_INT = 2,          /* ConversionError  "Integer parsing failed"             error.rs:510    */
+  ETL_E_PARSE_FLOAT = 3,        /* ConversionError  "Float parsing failed"               error.rs:525    */
+  ETL_E_DATETIME = 4,           /* ConversionError  "Datetime parsing failed"            error.rs:878    */
+  ETL_E_NUMERIC = 5,            /* ConversionError  "Numeric parsing failed"             error.rs:893    */
+  ETL_E_UUID = 6,               /* InvalidData      "UUID parsing failed"                error.rs:863    */
+  ETL_E_JSON = 7,               /* DeserializationError "JSON deserialization failed"    error.rs:456-463 */
+  ETL_E_BOOL = 8,               /* InvalidData      "Invalid boolean value"              bool.rs:17      */
+  ETL_E_BYTEA = 9,              /* ConversionError  "Bytea hex string conversion failed" hex.rs:12-29    */
+  ETL_E_BINARY_FORMAT = 10,     /* ConversionError  "Binary format not supported in tuple data" event.rs:976 */
+  ETL_E_NOT_NULL = 11,          /* InvalidData      "Required column missing from tuple" event.rs:947-955 */
+  ETL_E_FIELD_COUNT = 12,       /* ConversionError  "Tuple data field count does not match schema" event.rs:556,608 */
+  ETL_E_FULL_ROW_MISSING = 13,  /* ConversionError  "Tuple missing source value for full row image" event.rs:568 */
+  ETL_E_KEY_NO_COLUMNS = 14,    /* ConversionError  "Replica-identity tuple missing key columns" event.rs:890 */
+  ETL_E_KEY_SHAPE = 15,         /* ConversionError  "Replica-identity tuple shape does not match schema" event.rs:907 */
+  ETL_E_KEY_MISSING_VALUE = 16, /* ConversionError  "Replica-identity tuple missing source value" event.rs:803,847 */
+  ETL_E_TX_STATE = 17,          /* InvalidState     "Invalid transaction state"          apply.rs:1955,2018,2098,... */
+  ETL_E_COMMIT_LSN = 18,        /* ValidationError  "Invalid commit LSN"                 apply.rs:1960-1969 */
+  ETL_E_MISSING_TABLE_STATE = 19,/* InvalidState    "Missing shared table state"         apply.rs:3328-3337 */
+  ETL_E_ARRAY_SHORT = 20,       /* ConversionError  "Array input too short"              text.rs:190 */
+  ETL_E_ARRAY_BRACES = 21,      /* ConversionError  "Array input missing braces"         text.rs:194 */
+  ETL_E_UNKNOWN_COLUMNS = 22,   /* CorruptedTableSchema "Received columns during replication that are not in the stored table schema" error.rs:960-975 */
+  ETL_E_MISSING_TABLE_SCHEMA = 23,/* MissingTableSchema  stored TableSchema absent for a Relation (apply.rs:2062-2072) */
+  ETL_E_MALFORMED_FRAME = 24,   /* SourceError: truncated frame / unknown tag (postgres-replication parse error) */
+  ETL_E__COUNT
+} etl_error_code;
+
+typedef struct etl_first_error {
+  uint64_t record_index; /* UINT64_MAX when the batch decoded cleanly */
+  uint32_t seq;          /* evaluation step inside the record (old tuple cells, then new tuple cells) */
+  uint32_t code;         /* etl_error_code */
+  uint32_t kind;         /* etl_error_kind */
+  uint32_t _pad;
+} etl_first_error;
+
+/* ---------------------------------------------------------------- schema catalogue
+ * ColumnSchema — crates/etl-postgres/src/types/schema.rs:165-179 */
+typedef struct etl_column_schema {
+  const char* name;        /* UTF-8, NUL terminated */
+  uint32_t type_oid;
+  int32_t modifier;
+  int32_t ordinal_position;
+  int32_t primary_key_ordinal_position; /* -1 = not part of the primary key */
+  uint8_t nullable;
+  uint8_t _pad[7];
+} etl_column_schema;
+
+/* stream state carried between batches — ApplyLoopState {remote_final_lsn, next_tx_ordinal}
+ * apply.rs:600-626 */
+typedef struct etl_stream_state {
+  uint64_t final_lsn;       /* valid when in_tx != 0 */
+  uint64_t next_tx_ordinal;
+  uint8_t in_tx;            /* remote_final_lsn.is_some() */
+  uint8_t _pad[7];
+} etl_stream_state;
+
+/* ---------------------------------------------------------------- staging
+ * The stager is the replacement for the per-message parse in EventsStream: each CopyData body
+ * (what `copy_both_simple::<Bytes>` yields, crates/etl/src/replication/client.rs:1098-1099) is
+ * appended as 'd' + int32(len+4, big-endian) + body into one pinned host buffer. While appending
+ * it records, for free, (a) sparse anchors: anchors[k] = offset of the first frame that starts at
+ * or after k*anchor_stride (len if none), and (b) the offsets of Relation frames. */
+typedef struct etl_stager etl_stager;
+int etl_stage_create(uint64_t capacity_bytes, uint32_t anchor_stride, etl_stager** out);
+void etl_stage_destroy(etl_stager*);
+void etl_stage_reset(etl_stager*);
+int etl_stage_append(etl_stager*, const uint8_t* copydata_body, uint32_t body_len);
+/* adopt an already framed stream (bench/tests): walks it once on the host to build the indexes */
+int etl_stage_append_framed(etl_stager*, const uint8_t* framed, uint64_t len);
+
+typedef struct etl_dec_input {
+  const uint8_t* host_buf;       /* framed stream in host memory (pinned if from the stager) */
+  const uint8_t* dev_buf;        /* optional: same bytes already resident in HBM (NULL → library copies) */
+  uint64_t len;
+  const uint64_t* anchors;       /* host array, n_anchors entries, see etl_stager */
+  uint64_t n_anchors;
+  uint32_t anchor_stride;
+  uint32_t _pad;
+  const uint64_t* relation_offsets; /* host array: frame offsets of every 'R' frame, ascending */
+  uint64_t n_relations;
+  etl_stream_state carry_in;
+} etl_dec_input;
+int etl_stage_view(const etl_stager*, etl_dec_input* out);
+
+/* ---------------------------------------------------------------- decoder */
+typedef struct etl_dec_ctx etl_dec_ctx;
+typedef struct etl_dec_batch etl_dec_batch;
+
+int etl_dec_create(int device_id, etl_dec_ctx** out);
+void etl_dec_destroy(etl_dec_ctx*);
+const char* etl_dec_last_error(const etl_dec_ctx*);
+uint32_t etl_dec_abi_version(void);
+
+/* store (or replace) the TableSchema the SchemaStore would return for table_id */
+int etl_dec_put_table_schema(etl_dec_ctx*, uint32_t table_id, uint64_t snapshot_id,
+                             const etl_column_schema* cols, uint32_t n_cols);
+/* forget replicated-schema state (new connection: Postgres re-sends Relation messages) */
+int etl_dec_reset_relations(etl_dec_ctx*);
+
+/* flags for etl_dec_decode */
+enum {
+  ETL_DECODE_RESULTS_TO_HOST = 0x1, /* copy result planes to pinned host memory before returning */
+  ETL_DECODE_SEAM_DEFER = 0x2,      /* multi-GPU shard: carry_in unknown, run only the local scan;
+                                       caller exchanges etl_dec_seam and calls etl_dec_decode_finish */
+};
+
+/* per-shard seam summary exchanged with ONE all-gather across the GPUs of a box */
+typedef struct etl_dec_seam {
+  uint64_t n_records;
+  uint64_t n_cells;
+  uint64_t heap_bytes;
+  uint64_t lsn;        /* final_lsn of the last Begin in the shard (valid if has_begin) */
+  uint64_t ord;        /* has_begin: next_tx_ordinal at shard end; else ordinal consumers in shard */
+  uint8_t has_begin;
+  uint8_t closed;      /* a Commit follows the last Begin (or any Commit when !has_begin) */
+  uint8_t _pad[6];
+} etl_dec_seam;
+
+int etl_dec_decode(etl_dec_ctx*, const etl_dec_input*, uint32_t flags, etl_dec_batch** out);
+/* multi-GPU two-phase form */
+int etl_dec_decode_begin(etl_dec_ctx*, const etl_dec_input*, uint32_t flags, etl_dec_seam* seam_out);
+int etl_dec_decode_finish(etl_dec_ctx*, const etl_stream_state* carry_in, uint64_t record_index_base,
+                          etl_dec_batch** out);
+void etl_dec_batch_free(etl_dec_batch*);
+
+/* result planes. *_dev pointers are device memory owned by the batch; *_host are valid only when
+ * ETL_DECODE_RESULTS_TO_HOST was set. All arrays are in stream order. */
+typedef struct etl_dec_planes {
+  uint64_t n_records;
+  uint64_t n_cells;
+  uint64_t heap_bytes;
+  /* record plane (n_records entries; rec_cell_base has n_records + 1) */
+  const uint64_t* rec_off;
+  const uint8_t* rec_kind;
+  const uint8_t* rec_flags;
+  const uint32_t* rec_rel;       /* relation id (R/I/U/D), relation count (T) */
+  const int32_t* rec_schema;     /* schema version index (see etl_dec_batch_schema), -1 if none */
+  const uint64_t* rec_start_lsn;
+  const uint64_t* rec_commit_lsn;
+  const uint64_t* rec_tx_ordinal;
+  const uint64_t* rec_cell_base;
+  /* cell plane */
+  const uint8_t* cell_tag;
+  const uint64_t* cell_val;
+  const uint32_t* cell_aux;
+  /* heap */
+  const uint8_t* heap;
+} etl_dec_planes;
+
+typedef struct etl_dec_summary {
+  etl_first_error first_error;
+  etl_stream_state carry_out;
+  uint64_t insert_bytes;  /* ETL_BYTES_PROCESSED_TOTAL{insert}: calculate_tuple_bytes event.rs:260-270 */
+  uint64_t update_bytes;
+  uint64_t delete_bytes;
+  uint64_t n_events;      /* frames with ETL_RF_EVENT */
+  uint32_t n_schemas;     /* schema versions referenced by rec_schema */
+  uint32_t gpu_launches;  /* kernels launched for this batch */
+  float kernel_ms;        /* CUDA-event time of the kernel sequence (resident input → resident output) */
+  float h2d_ms, d2h_ms;
+  uint32_t _pad;
+} etl_dec_summary;
+
+int etl_dec_batch_planes(const etl_dec_batch*, int host, etl_dec_planes* out);
+int etl_dec_batch_summary(const etl_dec_batch*, etl_dec_summary* out);
+
+/* replicated schema version i: what ReplicatedTableSchema exposes to events (schema.rs:651-900) */
+typedef struct etl_dec_schema_info {
+  uint32_t table_id;
+  uint32_t n_cols;          /* replicated columns */
+  uint32_t n_identity;
+  uint32_t _pad;
+  uint64_t snapshot_id;
+  uint64_t effective_off;   /* stream offset of the Relation frame that installed it (0 = carried in) */
+  const uint8_t* col_kind;  /* n_cols ETL_K_* */
+  const uint8_t* col_flags; /* bit0 nullable, bit1 identity */
+  const int32_t* col_index; /* index into the stored TableSchema's column list */
+} etl_dec_schema_info;
+int etl_dec_batch_schema(const etl_dec_batch*, uint32_t index, etl_dec_schema_info* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ETL_DECODE_H */

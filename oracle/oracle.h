@@ -1,0 +1,86 @@
+/*
+ * oracle.h — CPU oracle for the pgoutput decode path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this. The product (etl_b200/, libetl_decode.so) never links or calls it.
+ *
+ * Parity status: the reference (Rust) cannot be built in this image (no cargo/rustc, un-vendored
+ * crates), so this is a restatement ("port"). It is pinned against every known-answer test the
+ * reference holds for the path (tests/test_oracle_reference_vectors.py quotes them with
+ * file:line). Behaviour that lives in third-party crates absent from /root/reference and is not
+ * covered by an in-tree reference test is marked "parity unpinned" where it is implemented
+ * (chrono leniency, uuid alternate spellings, serde_json depth limit, pgoutput Begin/Commit/
+ * Relation/Insert/Truncate layouts which follow the PostgreSQL protocol documentation).
+ */
+#ifndef ETL_ORACLE_H
+#define ETL_ORACLE_H
+
+#include "../include/etl_decode.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_ctx orc_ctx;
+
+typedef struct orc_schema {
+  uint32_t table_id;
+  uint32_t n_cols;
+  uint32_t n_identity;
+  uint32_t _pad;
+  uint64_t snapshot_id;
+  uint64_t effective_off;
+  uint8_t* col_kind;
+  uint8_t* col_flags;
+  int32_t* col_index;
+} orc_schema;
+
+typedef struct orc_batch {
+  uint64_t n_records, n_cells, heap_bytes;
+  uint64_t* rec_off;
+  uint8_t* rec_kind;
+  uint8_t* rec_flags;
+  uint32_t* rec_rel;
+  int32_t* rec_schema;
+  uint64_t* rec_start_lsn;
+  uint64_t* rec_commit_lsn;
+  uint64_t* rec_tx_ordinal;
+  uint64_t* rec_cell_base; /* n_records + 1 */
+  uint8_t* cell_tag;
+  uint64_t* cell_val;
+  uint32_t* cell_aux;
+  uint8_t* heap;
+  etl_first_error first_error;
+  etl_stream_state carry_out;
+  uint64_t insert_bytes, update_bytes, delete_bytes, n_events;
+  uint32_t n_schemas;
+  uint32_t _pad;
+  orc_schema* schemas;
+  /* capacities (internal) */
+  uint64_t cap_records, cap_cells, cap_heap, cap_schemas;
+} orc_batch;
+
+orc_ctx* orc_create(void);
+void orc_destroy(orc_ctx*);
+int orc_put_table_schema(orc_ctx*, uint32_t table_id, uint64_t snapshot_id,
+                         const etl_column_schema* cols, uint32_t n_cols);
+void orc_reset_relations(orc_ctx*);
+/* decode a framed stream; `out` is zero-initialised by the callee and must be released with
+ * orc_batch_free. Returns 0; data errors are in out->first_error. */
+int orc_decode(orc_ctx*, const uint8_t* buf, uint64_t len, const etl_stream_state* carry_in,
+               orc_batch* out);
+void orc_batch_free(orc_batch*);
+
+/* text.rs:28 parse_cell_from_postgres_text for one value. heap receives numeric/bytes/uuid/array
+ * payloads (offsets in val are relative to heap). Returns etl_error_code (0 = ok). */
+uint32_t orc_parse_cell(uint32_t type_oid, const uint8_t* text, uint32_t len, uint8_t* tag,
+                        uint64_t* val, uint32_t* aux, uint8_t* heap, uint32_t heap_cap,
+                        uint32_t* heap_len);
+/* type oid → ETL_K_* exactly as text.rs:28-173 + utils.rs:7-16 dispatch */
+uint32_t orc_kind_for_oid(uint32_t type_oid);
+uint32_t orc_error_kind(uint32_t code);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
