@@ -1,0 +1,524 @@
+// cell_parsers.cuh — device-side Postgres text → typed Cell parsers (sm_100a).
+//
+// Each parser is the GPU counterpart of one arm of parse_cell_from_postgres_text
+// (crates/etl/src/conversions/text.rs:28-173) and takes the cell's bytes through a generic pointer
+// (shared-memory tile window or global memory for oversize frames).  Integer / byte arithmetic
+// only; results must be bit-identical to the reference (the CPU oracle checks that in tests/).
+#pragma once
+#include <stdint.h>
+
+#include "etl_decode.h"
+
+namespace etl {
+
+struct CellOut {
+  uint64_t val;
+  uint32_t aux;
+  uint32_t tag;
+};
+
+// bump allocator over the frame's pre-sized heap slice
+struct HeapCursor {
+  uint8_t* heap;   // batch heap base (global)
+  uint64_t pos;    // next free byte (8-aligned)
+  __device__ __forceinline__ uint64_t alloc(uint32_t nbytes) {
+    uint64_t off = pos;
+    pos += (uint64_t)((nbytes + 7u) & ~7u);
+    return off;
+  }
+};
+
+__device__ __forceinline__ bool is_digit(uint32_t c) { return (c - '0') <= 9u; }
+__device__ __forceinline__ uint32_t lower(uint32_t c) { return (c - 'A') <= 25u ? c + 32u : c; }
+__device__ __forceinline__ int hexval(uint32_t c) {
+  if ((c - '0') <= 9u) return (int)(c - '0');
+  c = lower(c);
+  if ((c - 'a') <= 5u) return (int)(c - 'a' + 10);
+  return -1;
+}
+__device__ __forceinline__ bool ieq(const uint8_t* s, uint32_t n, const char* lit, uint32_t m) {
+  if (n != m) return false;
+  for (uint32_t i = 0; i < n; i++)
+    if (lower(s[i]) != (uint32_t)(uint8_t)lit[i]) return false;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// UTF-8 validation (core::str::from_utf8, event.rs:972).  Position-local formulation: byte i is
+// checked against its three predecessors, so any chunking of a cell gives the same verdict; the
+// block-cooperative path for large cells uses the same function on 16-byte chunks.
+__device__ __forceinline__ bool utf8_step_bad(uint32_t b, uint32_t p1, uint32_t p2, uint32_t p3) {
+  bool must_cont = (p1 >= 0xC0u) || (p2 >= 0xE0u) || (p3 >= 0xF0u);
+  bool is_cont = (b & 0xC0u) == 0x80u;
+  if (must_cont != is_cont) return true;
+  if (p1 >= 0xC0u) {  // b is the first continuation byte of a sequence: range restrictions
+    if (p1 < 0xC2u) return true;                  // overlong 2-byte
+    if (p1 == 0xE0u && b < 0xA0u) return true;    // overlong 3-byte
+    if (p1 == 0xEDu && b >= 0xA0u) return true;   // surrogates
+    if (p1 == 0xF0u && b < 0x90u) return true;    // overlong 4-byte
+    if (p1 == 0xF4u && b >= 0x90u) return true;   // > U+10FFFF
+    if (p1 > 0xF4u) return true;
+  }
+  return false;
+}
+// validate bytes [lo, hi) of a cell of n bytes (lo..hi chunk; predecessors read from the cell)
+__device__ __forceinline__ bool utf8_chunk_valid(const uint8_t* s, uint32_t n, uint32_t lo, uint32_t hi) {
+  uint32_t p1 = lo >= 1 ? s[lo - 1] : 0, p2 = lo >= 2 ? s[lo - 2] : 0, p3 = lo >= 3 ? s[lo - 3] : 0;
+  bool bad = false;
+  for (uint32_t i = lo; i < hi; i++) {
+    uint32_t b = s[i];
+    bad |= utf8_step_bad(b, p1, p2, p3);
+    p3 = p2; p2 = p1; p1 = b;
+  }
+  if (hi == n) bad |= (p1 >= 0xC0u) || (p2 >= 0xE0u) || (p3 >= 0xF0u);  // truncated tail sequence
+  return !bad;
+}
+__device__ __forceinline__ bool utf8_valid(const uint8_t* s, uint32_t n) {
+  // ASCII fast path per byte; multi-byte handled by the local rule
+  uint32_t p1 = 0, p2 = 0, p3 = 0;
+  bool bad = false;
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t b = s[i];
+    if ((b | p1 | p2 | p3) >= 0x80u) bad |= utf8_step_bad(b, p1, p2, p3);
+    p3 = p2; p2 = p1; p1 = b;
+  }
+  bad |= (p1 >= 0xC0u) || (p2 >= 0xE0u) || (p3 >= 0xF0u);
+  return !bad;
+}
+
+// Unicode White_Space (char::is_whitespace) byte length at s, 0 if none. Input is valid UTF-8.
+__device__ __forceinline__ uint32_t ws_len(const uint8_t* s, uint32_t n) {
+  if (n == 0) return 0;
+  uint32_t b = s[0];
+  if (b == ' ' || (b - 9u) <= 4u) return 1;
+  if (b < 0xC2u) return 0;
+  if (b == 0xC2u && n >= 2 && (s[1] == 0x85 || s[1] == 0xA0)) return 2;
+  if (n >= 3) {
+    uint32_t c1 = s[1], c2 = s[2];
+    if (b == 0xE1u && c1 == 0x9A && c2 == 0x80) return 3;
+    if (b == 0xE2u && c1 == 0x80 && ((c2 - 0x80u) <= 0x0Au || c2 == 0xA8 || c2 == 0xA9 || c2 == 0xAF)) return 3;
+    if (b == 0xE2u && c1 == 0x81 && c2 == 0x9F) return 3;
+    if (b == 0xE3u && c1 == 0x80 && c2 == 0x80) return 3;
+  }
+  return 0;
+}
+struct Cur {
+  const uint8_t* s;
+  uint32_t n;
+  __device__ __forceinline__ void trim_start() {
+    uint32_t w;
+    while ((w = ws_len(s, n)) != 0) { s += w; n -= w; }
+  }
+  __device__ __forceinline__ bool lit(uint32_t ch) {
+    if (n < 1 || s[0] != ch) return false;
+    s++; n--; return true;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// integers: Rust FromStr (text.rs:49-60,159-161)
+__device__ __forceinline__ uint32_t parse_int(const uint8_t* s, uint32_t n, bool is_signed, uint64_t pos_limit,
+                                              uint64_t neg_limit, int64_t* out) {
+  if (n == 0) return ETL_E_PARSE_INT;
+  bool neg = false;
+  uint32_t i = 0;
+  uint32_t c0 = s[0];
+  if (c0 == '+') i = 1;
+  else if (c0 == '-') { if (!is_signed) return ETL_E_PARSE_INT; neg = true; i = 1; }
+  if (i == n) return ETL_E_PARSE_INT;
+  uint64_t limit = neg ? neg_limit : pos_limit;
+  uint64_t acc = 0;
+  for (; i < n; i++) {
+    uint32_t d = (uint32_t)s[i] - '0';
+    if (d > 9u) return ETL_E_PARSE_INT;
+    if (acc > (limit - d) / 10u) return ETL_E_PARSE_INT;
+    acc = acc * 10u + d;
+  }
+  *out = neg ? (int64_t)(0ull - acc) : (int64_t)acc;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// chrono 0.4 parse_from_str (formats etl-postgres/src/types/time.rs:7-21)
+__device__ __forceinline__ bool scan_number(Cur& c, uint32_t minw, uint32_t maxw, int64_t* out) {
+  uint32_t k = 0;
+  int64_t v = 0;
+  while (k < c.n && k < maxw && is_digit(c.s[k])) {
+    int d = c.s[k] - '0';
+    if (v > (INT64_MAX - d) / 10) return false;
+    v = v * 10 + d;
+    k++;
+  }
+  if (k < minw) return false;
+  c.s += k; c.n -= k; *out = v;
+  return true;
+}
+__device__ __forceinline__ bool num_field(Cur& c, uint32_t width, bool is_signed, int64_t* out) {
+  c.trim_start();
+  if (is_signed && c.n > 0 && c.s[0] == '-') {
+    c.s++; c.n--;
+    int64_t v;
+    if (!scan_number(c, 1, 0xFFFFFFFFu, &v)) return false;
+    *out = -v; return true;
+  }
+  if (is_signed && c.n > 0 && c.s[0] == '+') {
+    c.s++; c.n--;
+    return scan_number(c, 1, 0xFFFFFFFFu, out);
+  }
+  return scan_number(c, 1, width, out);
+}
+__device__ __forceinline__ int64_t days_from_civil(int64_t y, int64_t m, int64_t d) {
+  y -= m <= 2;
+  int64_t era = (y >= 0 ? y : y - 399) / 400;
+  int64_t yoe = y - era * 400;
+  int64_t doy = (153 * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1;
+  int64_t doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+  return era * 146097 + doe - 719468;
+}
+__device__ __forceinline__ bool parse_date_part(Cur& c, int64_t* days) {
+  int64_t y, m, d;
+  if (!num_field(c, 4, true, &y)) return false;
+  if (y < INT32_MIN || y > INT32_MAX) return false;
+  if (!c.lit('-')) return false;
+  if (!num_field(c, 2, false, &m) || m < 1 || m > 12) return false;
+  if (!c.lit('-')) return false;
+  if (!num_field(c, 2, false, &d) || d < 1 || d > 31) return false;
+  if (y < -262143 || y > 262142) return false;
+  int dim = (m == 2) ? (((y % 4 == 0 && y % 100 != 0) || y % 400 == 0) ? 29 : 28)
+                     : ((m == 4 || m == 6 || m == 9 || m == 11) ? 30 : 31);
+  if (d > dim) return false;
+  *days = days_from_civil(y, m, d);
+  return true;
+}
+__device__ __forceinline__ bool parse_time_part(Cur& c, int64_t* secs, uint32_t* nanos) {
+  int64_t h, mi, se;
+  if (!num_field(c, 2, false, &h) || h > 23) return false;
+  if (!c.lit(':')) return false;
+  if (!num_field(c, 2, false, &mi) || mi > 59) return false;
+  if (!c.lit(':')) return false;
+  if (!num_field(c, 2, false, &se) || se > 60) return false;
+  uint32_t ns = 0;
+  if (c.n > 0 && c.s[0] == '.') {
+    c.s++; c.n--;
+    uint32_t before = c.n;
+    int64_t v;
+    if (!scan_number(c, 1, 9, &v)) return false;
+    uint32_t consumed = before - c.n;
+    for (uint32_t k = consumed; k < 9; k++) v *= 10;
+    while (c.n > 0 && is_digit(c.s[0])) { c.s++; c.n--; }
+    ns = (uint32_t)v;
+  }
+  if (se == 60) { se = 59; ns += 1000000000u; }
+  *secs = h * 3600 + mi * 60 + se;
+  *nanos = ns;
+  return true;
+}
+__device__ __forceinline__ bool parse_tz(Cur& c, bool allow_zulu, bool allow_missing_minutes, int32_t* off) {
+  c.trim_start();
+  if (allow_zulu && c.n > 0 && (c.s[0] == 'Z' || c.s[0] == 'z')) { c.s++; c.n--; *off = 0; return true; }
+  if (c.n == 0) return false;
+  bool neg;
+  if (c.s[0] == '+') { neg = false; c.s++; c.n--; }
+  else if (c.s[0] == '-') { neg = true; c.s++; c.n--; }
+  else if (c.n >= 3 && c.s[0] == 0xE2 && c.s[1] == 0x88 && c.s[2] == 0x92) { neg = true; c.s += 3; c.n -= 3; }
+  else return false;
+  if (c.n < 2 || !is_digit(c.s[0]) || !is_digit(c.s[1])) return false;
+  int32_t hours = (c.s[0] - '0') * 10 + (c.s[1] - '0');
+  c.s += 2; c.n -= 2;
+  for (;;) {
+    if (c.n > 0 && c.s[0] == ':') { c.s++; c.n--; continue; }
+    uint32_t w = ws_len(c.s, c.n);
+    if (w) { c.s += w; c.n -= w; continue; }
+    break;
+  }
+  int32_t minutes;
+  if (c.n >= 2) {
+    uint32_t m1 = c.s[0], m2 = c.s[1];
+    if ((m1 - '0') <= 5u && is_digit(m2)) minutes = (int32_t)((m1 - '0') * 10 + (m2 - '0'));
+    else return false;
+  } else if (allow_missing_minutes) minutes = 0;
+  else return false;
+  if (c.n >= 2) { c.s += 2; c.n -= 2; }
+  else if (c.n != 0) return false;
+  int32_t secs = hours * 3600 + minutes * 60;
+  *off = neg ? -secs : secs;
+  return true;
+}
+__device__ __forceinline__ bool parse_ts_prefix(Cur& c, int64_t* days, int64_t* secs, uint32_t* ns) {
+  if (!parse_date_part(c, days)) return false;
+  c.trim_start();
+  return parse_time_part(c, secs, ns);
+}
+__device__ __noinline__ bool parse_timestamptz_fmt(const uint8_t* s, uint32_t n, bool permissive, CellOut& o) {
+  Cur c{s, n};
+  int64_t days, secs;
+  uint32_t ns;
+  int32_t off;
+  if (!parse_ts_prefix(c, &days, &secs, &ns)) return false;
+  if (!parse_tz(c, permissive, permissive, &off)) return false;
+  if (c.n != 0) return false;
+  if (off <= -86400 || off >= 86400) return false;
+  int64_t utc = days * 86400 + secs - off;
+  const int64_t lo = -8334601228800LL;  // days_from_civil(-262143,1,1)*86400
+  const int64_t hi = 8210266876800LL;   // (days_from_civil(262142,12,31)+1)*86400
+  if (utc < lo || utc >= hi) return false;
+  o.tag = ETL_CELL_TIMESTAMPTZ; o.val = (uint64_t)utc; o.aux = ns;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// numeric.rs:99-472.  Two passes over the text: grammar + shape, then base-10000 grouping straight
+// into the heap slice (no temporaries).
+__device__ __noinline__ uint32_t parse_numeric(const uint8_t* s, uint32_t n, HeapCursor& hc, CellOut& o) {
+  Cur c{s, n};
+  c.trim_start();
+  if (c.n == 0) return ETL_E_NUMERIC;
+  bool neg = false, explicit_sign = false;
+  if (c.s[0] == '+') { explicit_sign = true; c.s++; c.n--; }
+  else if (c.s[0] == '-') { neg = true; explicit_sign = true; c.s++; c.n--; }
+  etl_numeric_hdr hdr;
+  hdr.kind = 0; hdr.sign = 0; hdr.weight = 0; hdr.scale = 0; hdr._pad = 0;
+  const uint8_t* p = c.s;
+  uint32_t rem = c.n;
+  if (!(rem > 0 && (is_digit(p[0]) || p[0] == '.'))) {
+    uint32_t e = rem;
+    for (;;) {  // trim_end by Unicode whitespace
+      bool trimmed = false;
+      for (uint32_t w = 1; w <= 3 && w <= e; w++)
+        if (ws_len(p + e - w, w) == w) { e -= w; trimmed = true; break; }
+      if (!trimmed) break;
+    }
+    if (ieq(p, e, "nan", 3)) { if (explicit_sign) return ETL_E_NUMERIC; hdr.kind = 1; }
+    else if (ieq(p, e, "infinity", 8) || ieq(p, e, "inf", 3)) hdr.kind = neg ? 3 : 2;
+    else return ETL_E_NUMERIC;
+    uint64_t off = hc.alloc(8);
+    *reinterpret_cast<etl_numeric_hdr*>(hc.heap + off) = hdr;
+    o.tag = ETL_CELL_NUMERIC; o.val = off; o.aux = 0;
+    return 0;
+  }
+  // pass 1: grammar (numeric.rs:285-401)
+  uint32_t i = 0, ndec = 0;
+  bool have_dp = false;
+  int64_t dweight = -1, dscale = 0;
+  if (p[0] == '.') { have_dp = true; i = 1; }
+  if (!(i < rem && is_digit(p[i]))) return ETL_E_NUMERIC;
+  uint32_t mant_begin = 0, mant_end;
+  while (i < rem) {
+    uint32_t ch = p[i];
+    if (is_digit(ch)) { i++; ndec++; if (!have_dp) dweight++; else dscale++; }
+    else if (ch == '.') {
+      if (have_dp) return ETL_E_NUMERIC;
+      have_dp = true; i++;
+      if (i < rem && p[i] == '_') return ETL_E_NUMERIC;
+    } else if (ch == '_') {
+      i++;
+      if (!(i < rem && is_digit(p[i]))) return ETL_E_NUMERIC;
+    } else break;
+  }
+  mant_end = i;
+  if (i < rem && (p[i] == 'e' || p[i] == 'E')) {
+    i++;
+    int64_t exponent = 0;
+    bool eneg = false;
+    if (i < rem && p[i] == '+') i++;
+    else if (i < rem && p[i] == '-') { eneg = true; i++; }
+    if (!(i < rem && is_digit(p[i]))) return ETL_E_NUMERIC;
+    while (i < rem) {
+      uint32_t ch = p[i];
+      if (is_digit(ch)) {
+        i++; exponent = exponent * 10 + (int64_t)(ch - '0');
+        if (exponent > 2147483647LL / 2) return ETL_E_NUMERIC;
+      } else if (ch == '_') {
+        i++;
+        if (!(i < rem && is_digit(p[i]))) return ETL_E_NUMERIC;
+      } else break;
+    }
+    if (eneg) exponent = -exponent;
+    dweight += exponent;
+    dscale = (dscale - exponent) < 0 ? 0 : (dscale - exponent);
+  }
+  { Cur t{p + i, rem - i}; t.trim_start(); if (t.n != 0) return ETL_E_NUMERIC; }
+  if (dscale > 16383) return ETL_E_NUMERIC;
+  hdr.scale = (uint16_t)dscale;
+  // pass 2: convert_to_base_10000 (numeric.rs:409-472)
+  int64_t weight = dweight >= 0 ? (dweight + 4) / 4 - 1 : -((-dweight - 1) / 4 + 1);
+  int64_t offset = (weight + 1) * 4 - (dweight + 1);
+  uint32_t ndig = (uint32_t)(((int64_t)ndec + offset + 3) / 4);
+  uint64_t off = hc.alloc(8 + 2 * ndig);
+  int16_t* dg = reinterpret_cast<int16_t*>(hc.heap + off + 8);
+  uint32_t lead = 0, written = 0, last_nz = 0;
+  bool seen_nz = false;
+  int v = 0;
+  uint32_t pos_in_group = (uint32_t)offset;  // leading pad zeros
+  for (uint32_t k = mant_begin; k < mant_end; k++) {
+    uint32_t ch = p[k];
+    if (!is_digit(ch)) continue;
+    v = v * 10 + (int)(ch - '0');
+    if (++pos_in_group == 4) {
+      if (!seen_nz) { if (v == 0) lead++; else { seen_nz = true; dg[0] = (int16_t)v; written = 1; last_nz = 1; } }
+      else { dg[written++] = (int16_t)v; if (v) last_nz = written; }
+      v = 0; pos_in_group = 0;
+    }
+  }
+  if (pos_in_group != 0) {
+    for (; pos_in_group < 4; pos_in_group++) v *= 10;
+    if (!seen_nz) { if (v == 0) lead++; else { seen_nz = true; dg[0] = (int16_t)v; written = 1; last_nz = 1; } }
+    else { dg[written++] = (int16_t)v; if (v) last_nz = written; }
+  }
+  uint32_t nd = 0;
+  if (seen_nz) {
+    int64_t fw = weight - (int64_t)lead;
+    if (fw < -32768 || fw > 32767) return ETL_E_NUMERIC;
+    hdr.sign = neg ? 1 : 0;
+    hdr.weight = (int16_t)fw;
+    nd = last_nz;
+  }
+  *reinterpret_cast<etl_numeric_hdr*>(hc.heap + off) = hdr;
+  o.tag = ETL_CELL_NUMERIC; o.val = off; o.aux = nd;
+  return 0;
+}
+// heap bytes reserved for a numeric cell of n text bytes (upper bound on 8 + 2*ndigits, 8-aligned)
+__device__ __forceinline__ uint32_t numeric_heap_bound(uint32_t n) { return (8u + 2u * (n / 4u + 2u) + 7u) & ~7u; }
+
+// ------------------------------------------------------------------------------------------------
+// hex.rs:11-37
+__device__ __noinline__ uint32_t parse_bytea(const uint8_t* s, uint32_t n, HeapCursor& hc, CellOut& o) {
+  if (n < 2 || s[0] != '\\' || s[1] != 'x') return ETL_E_BYTEA;
+  s += 2; n -= 2;
+  if (n & 1u) return ETL_E_BYTEA;
+  uint64_t off = hc.alloc(n / 2);
+  uint8_t* d = hc.heap + off;
+  for (uint32_t i = 0; i < n; i += 2) {
+    int a, b;
+    if (s[i] == '+') { b = hexval(s[i + 1]); if (b < 0) return ETL_E_PARSE_INT; d[i >> 1] = (uint8_t)b; continue; }
+    a = hexval(s[i]); b = hexval(s[i + 1]);
+    if ((a | b) < 0) return ETL_E_PARSE_INT;
+    d[i >> 1] = (uint8_t)(a * 16 + b);
+  }
+  o.tag = ETL_CELL_BYTES; o.val = off; o.aux = n / 2;
+  return 0;
+}
+__device__ __forceinline__ uint32_t bytea_heap_bound(uint32_t n) { return n >= 2 ? (((n - 2u) / 2u + 7u) & ~7u) : 0u; }
+
+// uuid 1.x Uuid::parse_str (text.rs:141-149)
+__device__ __noinline__ uint32_t parse_uuid(const uint8_t* s, uint32_t n, HeapCursor& hc, CellOut& o) {
+  uint8_t out[16];
+  if (n == 38 && s[0] == '{' && s[37] == '}') { s++; n = 36; }
+  else if (n == 45 && s[0] == 'u' && s[1] == 'r' && s[2] == 'n' && s[3] == ':' && s[4] == 'u' && s[5] == 'u' &&
+           s[6] == 'i' && s[7] == 'd' && s[8] == ':') { s += 9; n = 36; }
+  if (n == 32) {
+    for (int i = 0; i < 16; i++) {
+      int a = hexval(s[2 * i]), b = hexval(s[2 * i + 1]);
+      if ((a | b) < 0) return ETL_E_UUID;
+      out[i] = (uint8_t)(a * 16 + b);
+    }
+  } else if (n == 36) {
+    if (s[8] != '-' || s[13] != '-' || s[18] != '-' || s[23] != '-') return ETL_E_UUID;
+    int k = 0;
+    for (int i = 0; i < 36;) {
+      if (i == 8 || i == 13 || i == 18 || i == 23) { i++; continue; }
+      int a = hexval(s[i]), b = hexval(s[i + 1]);
+      if ((a | b) < 0) return ETL_E_UUID;
+      out[k++] = (uint8_t)(a * 16 + b);
+      i += 2;
+    }
+  } else return ETL_E_UUID;
+  uint64_t off = hc.alloc(16);
+  for (int i = 0; i < 16; i++) hc.heap[off + i] = out[i];
+  o.tag = ETL_CELL_UUID; o.val = off; o.aux = 16;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// serde_json::from_str::<Value> acceptance (text.rs:150-153): iterative validator with an explicit
+// container stack (1 bit per level, 128 levels = serde_json's recursion limit).
+__device__ __noinline__ bool json_valid(const uint8_t* s, uint32_t n) {
+  uint32_t stack[4] = {0, 0, 0, 0};  // bit = 1 → object, 0 → array
+  int depth = 0;
+  uint32_t i = 0;
+  // state: 0 expect value, 1 after value, 2 expect key or '}', 3 expect key, 4 expect ':', 5 expect value or ']'
+  int st = 0;
+  for (;;) {
+    while (i < n && (s[i] == ' ' || s[i] == '\t' || s[i] == '\n' || s[i] == '\r')) i++;
+    if (st == 1 && depth == 0) return i == n;
+    if (i >= n) return false;
+    uint32_t ch = s[i];
+    if (st == 1) {
+      bool is_obj = (stack[(depth - 1) >> 5] >> ((depth - 1) & 31)) & 1u;
+      if (ch == ',') { i++; st = is_obj ? 3 : 0; continue; }
+      if (ch == (is_obj ? '}' : ']')) { i++; depth--; st = 1; continue; }
+      return false;
+    }
+    if (st == 4) { if (ch != ':') return false; i++; st = 0; continue; }
+    if (st == 2 || st == 3) {
+      if (st == 2 && ch == '}') { i++; depth--; st = 1; continue; }
+      if (ch != '"') return false;
+      // fallthrough to string parse, then expect ':'
+    } else if (st == 5) {
+      if (ch == ']') { i++; depth--; st = 1; continue; }
+      st = 0;
+    }
+    if (ch == '"') {
+      i++;
+      for (;;) {
+        if (i >= n) return false;
+        uint32_t c = s[i];
+        if (c == '"') { i++; break; }
+        if (c < 0x20u) return false;
+        if (c == '\\') {
+          i++;
+          if (i >= n) return false;
+          uint32_t e = s[i++];
+          if (e == 'u') {
+            if (i + 4 > n) return false;
+            uint32_t u = 0;
+            for (int k = 0; k < 4; k++) { int h = hexval(s[i + k]); if (h < 0) return false; u = u * 16 + (uint32_t)h; }
+            i += 4;
+            if (u >= 0xDC00u && u <= 0xDFFFu) return false;
+            if (u >= 0xD800u && u <= 0xDBFFu) {
+              if (i + 6 > n || s[i] != '\\' || s[i + 1] != 'u') return false;
+              i += 2;
+              uint32_t u2 = 0;
+              for (int k = 0; k < 4; k++) { int h = hexval(s[i + k]); if (h < 0) return false; u2 = u2 * 16 + (uint32_t)h; }
+              i += 4;
+              if (u2 < 0xDC00u || u2 > 0xDFFFu) return false;
+            }
+          } else if (!(e == '"' || e == '\\' || e == '/' || e == 'b' || e == 'f' || e == 'n' || e == 'r' || e == 't')) return false;
+          continue;
+        }
+        i++;
+      }
+      st = (st == 2 || st == 3) ? 4 : 1;
+      continue;
+    }
+    // st == 0 here: a value
+    if (ch == '{' || ch == '[') {
+      if (depth >= 127) return false;  // remaining_depth reaches 0 on the 128th nested container
+      if (ch == '{') stack[depth >> 5] |= (1u << (depth & 31)); else stack[depth >> 5] &= ~(1u << (depth & 31));
+      depth++; i++;
+      st = (ch == '{') ? 2 : 5;
+      continue;
+    }
+    if (ch == 't') { if (i + 4 > n || s[i + 1] != 'r' || s[i + 2] != 'u' || s[i + 3] != 'e') return false; i += 4; st = 1; continue; }
+    if (ch == 'f') { if (i + 5 > n || s[i + 1] != 'a' || s[i + 2] != 'l' || s[i + 3] != 's' || s[i + 4] != 'e') return false; i += 5; st = 1; continue; }
+    if (ch == 'n') { if (i + 4 > n || s[i + 1] != 'u' || s[i + 2] != 'l' || s[i + 3] != 'l') return false; i += 4; st = 1; continue; }
+    if (ch == '-' || is_digit(ch)) {
+      if (ch == '-') { i++; if (i >= n) return false; }
+      if (s[i] == '0') { i++; if (i < n && is_digit(s[i])) return false; }
+      else if ((uint32_t)(s[i] - '1') <= 8u) { while (i < n && is_digit(s[i])) i++; }
+      else return false;
+      if (i < n && s[i] == '.') { i++; if (!(i < n && is_digit(s[i]))) return false; while (i < n && is_digit(s[i])) i++; }
+      if (i < n && (s[i] == 'e' || s[i] == 'E')) {
+        i++;
+        if (i < n && (s[i] == '+' || s[i] == '-')) i++;
+        if (!(i < n && is_digit(s[i]))) return false;
+        while (i < n && is_digit(s[i])) i++;
+      }
+      st = 1;
+      continue;
+    }
+    return false;
+  }
+}
+
+}  // namespace etl

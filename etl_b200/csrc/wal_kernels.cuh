@@ -1,0 +1,799 @@
+// wal_kernels.cuh — sm_100a kernels of the batched pgoutput decode path.
+//
+//   k_index   (pass A)  one thread per anchor segment walks the 'd'+len32 frame chain from global
+//                       memory (only frame heads are touched), classifies frames and reduces a
+//                       per-tile summary {records, cells, heap bytes, stream-state transformer}.
+//   k_scan    (pass B)  single-block exclusive scan of the per-group summaries (the state
+//                       transformer is associative, so commit_lsn / tx_ordinal become a scan).
+//   k_emit    (pass C)  one CTA per 32 KiB tile: coalesced 16-byte loads stage the tile in shared
+//                       memory, segment walkers rebuild the frame list there, then thread-per-frame
+//                       parsing of TupleData cells writes the record / cell / heap planes; large
+//                       text cells are validated block-cooperatively.
+//
+// Reference semantics: apply.rs:1687-2248 (state machine), event.rs:376-979 (tuples → rows),
+// text.rs:28-173 (cells).  HBM-bound integer/byte work — no tensor cores.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cell_parsers.cuh"
+
+namespace etl {
+
+constexpr int kTileBytes = 32768;      // nominal tile = kTileBytes of stream (frames that START inside it)
+constexpr int kTileCap = 40960;        // shared-memory window; bytes past it are read from global
+constexpr int kEmitThreads = 256;
+constexpr int kMaxTileFrames = 2048;   // > kTileBytes/23 + segments
+constexpr int kIndexThreads = 256;
+constexpr int kBigCell = 512;          // text cells at least this long are validated cooperatively
+constexpr int kBigQueue = 128;
+
+// ---- stream-state transformer (apply.rs:600-626, 1927-2006) + counters; associative under fold()
+struct Summ {
+  uint64_t lsn;      // final_lsn of the last Begin (valid if HAS_B)
+  uint64_t ord;      // HAS_B: next ordinal after the span; else number of ordinal consumers in the span
+  uint64_t n_cells;
+  uint64_t heap;
+  uint32_t n_rec;
+  uint32_t flags;    // 1 HAS_B, 2 CLOSED (a Commit follows the last Begin / any Commit if no Begin)
+};
+constexpr uint32_t S_HAS_B = 1, S_CLOSED = 2;
+
+__host__ __device__ __forceinline__ Summ summ_identity() { return Summ{0, 0, 0, 0, 0, 0}; }
+__host__ __device__ __forceinline__ Summ fold(const Summ& a, const Summ& b) {
+  Summ r;
+  r.n_rec = a.n_rec + b.n_rec;
+  r.n_cells = a.n_cells + b.n_cells;
+  r.heap = a.heap + b.heap;
+  if (b.flags & S_HAS_B) { r.flags = b.flags; r.lsn = b.lsn; r.ord = b.ord; }
+  else {
+    r.flags = (a.flags & S_HAS_B) | ((b.flags & S_CLOSED) ? S_CLOSED : (a.flags & S_CLOSED));
+    r.lsn = a.lsn;
+    r.ord = a.ord + b.ord;
+  }
+  return r;
+}
+
+struct DevSchema {
+  uint32_t table_id;
+  uint32_t n_cols;
+  uint32_t n_ident;
+  uint32_t col_base;      // into col_kind / col_flags
+  uint64_t effective_off; // stream offset from which this version applies
+  uint32_t batch_index;   // index reported in rec_schema
+  uint32_t has_heap;      // any numeric / bytea / uuid / array column
+};
+
+struct DecodeParams {
+  const uint8_t* buf;
+  uint64_t len;
+  const uint64_t* anchors;   // n_anchors + 1 entries (last = len)
+  uint32_t n_anchors;
+  uint32_t anchor_stride;
+  uint32_t segs_per_tile;
+  uint32_t n_tiles;
+  uint32_t tiles_per_group;  // tiles folded per k_index CTA
+  uint32_t n_groups;
+  const DevSchema* schemas;  // sorted by (table_id, effective_off)
+  uint32_t n_schemas;
+  const uint8_t* col_kind;
+  const uint8_t* col_flags;  // bit0 nullable, bit1 identity
+  // pass A outputs
+  uint32_t* seg_frames;      // frames starting in each segment
+  Summ* tile_summ;           // per tile
+  Summ* group_summ;          // per group of tiles
+  Summ* group_prefix;        // exclusive prefix per group (pass B)
+  Summ* total;               // [0] = fold of everything (shard seam summary)
+  // carry-in (known when pass C runs)
+  Summ carry;
+  uint64_t record_index_base;  // global index of this shard's first record (multi-GPU)
+  // outputs
+  uint64_t* rec_off; uint8_t* rec_kind; uint8_t* rec_flags; uint32_t* rec_rel; int32_t* rec_schema;
+  uint64_t* rec_start_lsn; uint64_t* rec_commit_lsn; uint64_t* rec_tx_ordinal; uint64_t* rec_cell_base;
+  uint8_t* cell_tag; uint64_t* cell_val; uint32_t* cell_aux;
+  uint8_t* heap;
+  unsigned long long* first_error;  // atomicMin key: rec_index << 24 | seq << 6 | code
+  unsigned long long* metrics;      // [0] insert bytes [1] update bytes [2] delete bytes [3] events
+  // Relation frames rejected on the host (missing stored schema / unknown columns / malformed)
+  const uint64_t* rel_error_off; const uint32_t* rel_error_code; const uint32_t* rel_error_seq; uint32_t n_rel_errors;
+};
+
+// ---- big-endian readers on byte-addressed (unaligned) generic pointers
+__device__ __forceinline__ uint32_t be32(const uint8_t* p) {
+  return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+}
+__device__ __forceinline__ uint64_t be64(const uint8_t* p) { return ((uint64_t)be32(p) << 32) | be32(p + 4); }
+__device__ __forceinline__ uint32_t be16(const uint8_t* p) { return ((uint32_t)p[0] << 8) | (uint32_t)p[1]; }
+
+// error sequencing inside one record (same numbering as the oracle)
+constexpr uint32_t SEQ_MALFORMED = 0, SEQ_STATE = 1, SEQ_TABLE = 2, SEQ_OLD_SHAPE = 0x10000, SEQ_NEW_SHAPE = 0x20000;
+__device__ __forceinline__ uint32_t seq_old_cell(uint32_t i) { return 0x10001u + i; }
+__device__ __forceinline__ uint32_t seq_new_cell(uint32_t i) { return 0x20001u + i; }
+__device__ __forceinline__ void report_error(const DecodeParams& P, uint64_t rec_index, uint32_t seq, uint32_t code) {
+  unsigned long long key = ((unsigned long long)rec_index << 24) | ((unsigned long long)(seq & 0x3FFFFu) << 6) | (code & 63u);
+  atomicMin(P.first_error, key);
+}
+
+// schema version for (table_id, frame offset): last entry with that table and effective_off <= off
+__device__ __forceinline__ const DevSchema* find_schema(const DecodeParams& P, uint32_t table_id, uint64_t off) {
+  int lo = 0, hi = (int)P.n_schemas;  // upper_bound on (table_id, off)
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    const DevSchema& s = P.schemas[mid];
+    bool le = (s.table_id < table_id) || (s.table_id == table_id && s.effective_off <= off);
+    if (le) lo = mid + 1; else hi = mid;
+  }
+  if (lo == 0) return nullptr;
+  const DevSchema* s = &P.schemas[lo - 1];
+  return s->table_id == table_id ? s : nullptr;
+}
+
+// ---- frame head: everything the index pass and the emit pass agree on
+struct FrameHead {
+  uint32_t flen;       // CopyData length field (counts itself)
+  uint32_t kind;       // pgoutput tag, 'k' for keepalive, 0 when malformed at the frame level
+  uint32_t rel;        // relation id (R/I/U/D), relation count (T)
+  uint32_t old_tag;    // 'O' | 'K' | 0 for U/D
+  bool malformed;
+};
+// p points at the frame's 'd'; avail = bytes from p to the end of the stream
+__device__ __forceinline__ FrameHead read_head(const uint8_t* p, uint64_t avail) {
+  FrameHead h;
+  h.kind = 0; h.rel = 0; h.old_tag = 0; h.malformed = true; h.flen = 4;
+  if (avail < 5 || p[0] != 'd') { h.flen = (uint32_t)(avail > 0 ? avail - 1 : 0); return h; }
+  uint32_t flen = be32(p + 1);
+  if (flen < 4 || 1ull + flen > avail) { h.flen = (uint32_t)(avail - 1); return h; }  // chain ends here
+  h.flen = flen;
+  uint32_t blen = flen - 4;
+  if (blen < 1) return h;
+  uint32_t t = p[5];
+  if (t == 'k') { if (blen < 18) return h; h.kind = 'k'; h.malformed = false; return h; }
+  if (t != 'w' || blen < 26) return h;
+  uint32_t tag = p[30];
+  uint32_t mlen = blen - 26;  // message bytes after the tag
+  h.kind = tag;
+  switch (tag) {
+    case 'B': if (mlen < 20) return h; break;
+    case 'C': if (mlen < 25) return h; break;
+    case 'R': case 'I': case 'U': case 'D':
+      if (mlen < 5) return h;
+      h.rel = be32(p + 31);
+      if (tag == 'U' || tag == 'D') { uint32_t tt = p[35]; if (tt == 'O' || tt == 'K') h.old_tag = tt; }
+      break;
+    case 'T': {
+      if (mlen < 5) return h;
+      int32_t n = (int32_t)be32(p + 31);
+      if (n > 0 && (uint64_t)n * 4 > (uint64_t)mlen - 5) return h;
+      h.rel = n > 0 ? (uint32_t)n : 0u;
+      break;
+    }
+    case 'O': case 'Y': case 'M': break;
+    default: return h;  // unknown tag
+  }
+  h.malformed = false;
+  return h;
+}
+
+// output cells of a frame (depends only on kind / old tag / schema — never on the tuple contents)
+__device__ __forceinline__ uint32_t frame_out_cells(const FrameHead& h, const DevSchema* s) {
+  switch (h.kind) {
+    case 'B': return 2;
+    case 'C': return 3;
+    case 'T': return 1 + h.rel;
+    case 'I': return s ? s->n_cols : 0;
+    case 'U': return s ? (s->n_cols + (h.old_tag == 'O' ? s->n_cols : (h.old_tag == 'K' ? s->n_ident : 0))) : 0;
+    case 'D': return s ? (h.old_tag == 'O' ? s->n_cols : (h.old_tag == 'K' ? s->n_ident : 0)) : 0;
+    default: return 0;
+  }
+}
+__device__ __forceinline__ Summ frame_state_elem(const FrameHead& h, const uint8_t* p) {
+  Summ e = summ_identity();
+  e.n_rec = 1;
+  if (h.malformed) return e;
+  switch (h.kind) {
+    case 'B': e.flags = S_HAS_B; e.lsn = be64(p + 31); e.ord = 1; break;
+    case 'C': e.flags = S_CLOSED; e.ord = 1; break;
+    case 'R': case 'I': case 'U': case 'D': case 'T': e.ord = 1; break;
+    default: break;
+  }
+  return e;
+}
+
+// heap bytes a text cell of `kind` and length n may need (upper bound; identical in passes A and C)
+__device__ __forceinline__ uint32_t cell_heap_bound(uint32_t kind, uint32_t n) {
+  switch (kind) {
+    case ETL_K_NUMERIC: return numeric_heap_bound(n);
+    case ETL_K_BYTES: return bytea_heap_bound(n);
+    case ETL_K_UUID: return 16;
+    default: return 0;
+  }
+}
+
+// Walk one TupleData, calling f(col_index, tag, value_ptr, len) per cell. Returns bytes consumed
+// or 0 if the tuple runs past `end` / has an unknown cell tag (malformed frame).
+template <typename F>
+__device__ __forceinline__ uint32_t walk_tuple(const uint8_t* p, const uint8_t* end, int32_t* ncols_out, F&& f) {
+  if (p + 2 > end) return 0;
+  int32_t n = (int32_t)(int16_t)be16(p);
+  if (n < 0) n = 0;
+  *ncols_out = n;
+  const uint8_t* q = p + 2;
+  for (int32_t i = 0; i < n; i++) {
+    if (q + 1 > end) return 0;
+    uint32_t tag = *q++;
+    if (tag == 'n' || tag == 'u') { f(i, tag, q, 0u); continue; }
+    if (tag != 't' && tag != 'b') return 0;
+    if (q + 4 > end) return 0;
+    int32_t l = (int32_t)be32(q);
+    q += 4;
+    if (l < 0 || (uint64_t)l > (uint64_t)(end - q)) return 0;
+    f(i, tag, q, (uint32_t)l);
+    q += l;
+  }
+  return (uint32_t)(q - p);
+}
+
+// heap bytes reserved for a DML frame = sum of cell_heap_bound over its text cells, mapped to
+// columns positionally (dense key tuples: k-th cell → k-th identity column).  An upper bound on
+// what the emit pass allocates; both passes call this same function so prefixes agree exactly.
+__device__ __noinline__ uint32_t frame_heap_bytes(const DecodeParams& P, const FrameHead& h, const DevSchema* s,
+                                                  const uint8_t* p) {
+  if (!s || !s->has_heap) return 0;
+  const uint8_t* end = p + 1 + h.flen;
+  const uint8_t* kinds = P.col_kind + s->col_base;
+  const uint8_t* flags = P.col_flags + s->col_base;
+  const uint32_t n_cols = s->n_cols, n_ident = s->n_ident;
+  uint32_t total = 0;
+  const uint8_t* q = p + 36;  // first tuple (after 'N' / 'O' / 'K' marker at p[35])
+  const int n_tuples = (h.kind == 'U' && h.old_tag) ? 2 : 1;
+  if (h.kind == 'U' && !h.old_tag && p[35] != 'N') return 0;
+  for (int t = 0; t < n_tuples; t++) {
+    if (q + 2 > end) return total;
+    const bool dense_key = (t == 0) && (h.kind != 'I') && h.old_tag == 'K' && (uint32_t)(int32_t)(int16_t)be16(q) == n_ident;
+    uint32_t cmap = 0;
+    int32_t nc;
+    uint32_t used = walk_tuple(q, end, &nc, [&](int32_t i, uint32_t tag, const uint8_t*, uint32_t len) {
+      uint32_t col = (uint32_t)i;
+      if (dense_key) { while (cmap < n_cols && !(flags[cmap] & 2)) cmap++; col = cmap++; }
+      if (tag == 't' && col < n_cols) total += cell_heap_bound(kinds[col], len);
+    });
+    if (!used) return total;
+    q += used;
+    if (t == 0 && n_tuples == 2) { if (q >= end || *q != 'N') return total; q++; }
+  }
+  return total;
+}
+
+// structure of a DML message body (what LogicalReplicationMessage::parse would reject) + Σ text lengths
+__device__ __noinline__ bool dml_structure_ok(const FrameHead& h, const uint8_t* p, unsigned long long* tbytes) {
+  const uint8_t* end = p + 1 + h.flen;
+  const uint8_t* t = p + 35;
+  unsigned long long tb = 0;
+  int32_t nc;
+  auto count = [&](int32_t, uint32_t tag, const uint8_t*, uint32_t l) { if (tag == 't' || tag == 'b') tb += l; };
+  if (t >= end) return false;
+  uint32_t tt = *t++;
+  if (h.kind == 'I') { if (tt != 'N') return false; }
+  else if (h.kind == 'U') {
+    if (tt == 'O' || tt == 'K') {
+      uint32_t used = walk_tuple(t, end, &nc, count);
+      if (!used) return false;
+      t += used;
+      if (t >= end || *t != 'N') return false;
+      t++;
+    } else if (tt != 'N') return false;
+  } else if (tt != 'O' && tt != 'K') return false;
+  if (!walk_tuple(t, end, &nc, count)) return false;
+  *tbytes = tb;
+  return true;
+}
+__device__ __forceinline__ const uint8_t* cstr_end(const uint8_t* q, const uint8_t* end) {
+  while (q < end && *q) q++;
+  return q < end ? q + 1 : nullptr;
+}
+
+// ================================================================================================
+// pass A: index.  grid = n_groups, block = tiles_per_group * segs_per_tile threads.
+__global__ void __launch_bounds__(kIndexThreads) k_index(DecodeParams P) {
+  const uint32_t spt = P.segs_per_tile;
+  const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+  Summ acc = summ_identity();
+  uint32_t nframes = 0;
+  if (seg < P.n_anchors) {
+    uint64_t pos = P.anchors[seg];
+    const uint64_t stop = P.anchors[seg + 1];
+    while (pos < stop) {
+      const uint8_t* p = P.buf + pos;
+      FrameHead h = read_head(p, P.len - pos);
+      Summ e = frame_state_elem(h, p);
+      if (!h.malformed) {
+        const DevSchema* s = nullptr;
+        if (h.kind == 'I' || h.kind == 'U' || h.kind == 'D') s = find_schema(P, h.rel, pos);
+        e.n_cells = frame_out_cells(h, s);
+        if (s && s->has_heap) e.heap = frame_heap_bytes(P, h, s, p);
+      }
+      acc = fold(acc, e);
+      nframes++;
+      pos += 1ull + h.flen;
+    }
+    P.seg_frames[seg] = nframes;
+  }
+  // fold across the segments of each tile, then across the tiles of the group (ordered shuffles)
+  // generic ordered fold over the block through shared memory (blockDim <= 256)
+  __shared__ Summ sh[kIndexThreads];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  // per-tile fold by the first lane of each tile
+  const uint32_t tile_in_block = threadIdx.x / spt;
+  if (threadIdx.x % spt == 0) {
+    Summ t = summ_identity();
+    for (uint32_t k = 0; k < spt && threadIdx.x + k < blockDim.x; k++) t = fold(t, sh[threadIdx.x + k]);
+    uint32_t tile = blockIdx.x * P.tiles_per_group + tile_in_block;
+    if (tile < P.n_tiles) P.tile_summ[tile] = t;
+    sh[threadIdx.x] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Summ g = summ_identity();
+    for (uint32_t k = 0; k < P.tiles_per_group; k++) g = fold(g, sh[k * spt]);
+    P.group_summ[blockIdx.x] = g;
+  }
+}
+
+// ================================================================================================
+// pass B: exclusive scan of group summaries (single CTA; n_groups is len / (tiles_per_group*32 KiB))
+__global__ void __launch_bounds__(512) k_scan(DecodeParams P) {
+  __shared__ Summ sh[512];
+  const uint32_t n = P.n_groups;
+  const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
+  const uint32_t lo = threadIdx.x * per, hi = min(lo + per, n);
+  Summ acc = summ_identity();
+  for (uint32_t i = lo; i < hi; i++) acc = fold(acc, P.group_summ[i]);
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over 1024 partials with the non-commutative fold
+  for (uint32_t d = 1; d < blockDim.x; d <<= 1) {
+    Summ v = sh[threadIdx.x];
+    if (threadIdx.x >= d) v = fold(sh[threadIdx.x - d], v);
+    __syncthreads();
+    sh[threadIdx.x] = v;
+    __syncthreads();
+  }
+  Summ run = threadIdx.x ? sh[threadIdx.x - 1] : summ_identity();
+  for (uint32_t i = lo; i < hi; i++) {
+    P.group_prefix[i] = run;
+    run = fold(run, P.group_summ[i]);
+  }
+  if (threadIdx.x == blockDim.x - 1) P.total[0] = sh[blockDim.x - 1];
+}
+
+// ================================================================================================
+// pass C: emit
+struct BigCell {
+  const uint8_t* ptr;
+  uint32_t len;
+  uint32_t seq;
+  uint64_t rec_index;
+};
+
+struct EmitShared {
+  alignas(16) uint8_t tile[kTileCap];
+  uint32_t foff[kMaxTileFrames];
+  uint32_t seg_base[132];
+  Summ warp_summ[kEmitThreads / 32];
+  Summ chunk_carry;
+  BigCell big[kBigQueue];
+  uint32_t n_big;
+  unsigned long long metrics[4];
+};
+
+// inclusive block scan of Summ (ordered), returns exclusive prefix within the block and the block total
+__device__ __forceinline__ Summ shfl_up_summ(const Summ& v, int d) {
+  Summ r;
+  r.lsn = __shfl_up_sync(0xffffffffu, v.lsn, d);
+  r.ord = __shfl_up_sync(0xffffffffu, v.ord, d);
+  r.n_cells = __shfl_up_sync(0xffffffffu, v.n_cells, d);
+  r.heap = __shfl_up_sync(0xffffffffu, v.heap, d);
+  r.n_rec = __shfl_up_sync(0xffffffffu, v.n_rec, d);
+  r.flags = __shfl_up_sync(0xffffffffu, v.flags, d);
+  return r;
+}
+__device__ __forceinline__ Summ block_exclusive_scan(const Summ& mine, Summ* warp_summ, Summ* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  Summ inc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    Summ up = shfl_up_summ(inc, d);
+    if (lane >= d) inc = fold(up, inc);
+  }
+  if (lane == 31) warp_summ[wid] = inc;
+  __syncthreads();
+  Summ wpre = summ_identity();
+  for (int w = 0; w < wid; w++) wpre = fold(wpre, warp_summ[w]);
+  Summ tot = summ_identity();
+  for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot = fold(tot, warp_summ[w]);
+  *total = tot;
+  Summ excl = shfl_up_summ(inc, 1);
+  if (lane == 0) excl = summ_identity();
+  __syncthreads();
+  return fold(wpre, excl);
+}
+
+struct CellSink {
+  const DecodeParams& P;
+  uint64_t base;  // first output cell of the frame
+  __device__ __forceinline__ void put(uint32_t i, const CellOut& c) const {
+    P.cell_tag[base + i] = (uint8_t)c.tag; P.cell_val[base + i] = c.val; P.cell_aux[base + i] = c.aux;
+  }
+  __device__ __forceinline__ void put(uint32_t i, uint32_t tag, uint64_t val, uint32_t aux) const {
+    P.cell_tag[base + i] = (uint8_t)tag; P.cell_val[base + i] = val; P.cell_aux[base + i] = aux;
+  }
+  __device__ __forceinline__ CellOut get(uint32_t i) const {
+    CellOut c; c.tag = P.cell_tag[base + i]; c.val = P.cell_val[base + i]; c.aux = P.cell_aux[base + i]; return c;
+  }
+};
+
+// text.rs:28-173 dispatch for one 't' cell. `soff` = absolute stream offset of the value bytes.
+__device__ __forceinline__ uint32_t parse_text_cell(uint32_t kind, const uint8_t* s, uint32_t n, uint64_t soff,
+                                                    HeapCursor& hc, CellOut& o, bool defer_utf8) {
+  o.aux = 0;
+  if (!defer_utf8 && !utf8_valid(s, n)) return ETL_E_UTF8;  // event.rs:972
+  int64_t iv;
+  uint32_t e;
+  switch (kind) {
+    case ETL_K_STRING: o.tag = ETL_CELL_STRING; o.val = soff; o.aux = n; return 0;
+    case ETL_K_I32: e = parse_int(s, n, true, 2147483647ull, 2147483648ull, &iv); o.tag = ETL_CELL_I32; o.val = (uint64_t)iv; return e;
+    case ETL_K_I64: e = parse_int(s, n, true, 9223372036854775807ull, 9223372036854775808ull, &iv); o.tag = ETL_CELL_I64; o.val = (uint64_t)iv; return e;
+    case ETL_K_I16: e = parse_int(s, n, true, 32767ull, 32768ull, &iv); o.tag = ETL_CELL_I16; o.val = (uint64_t)iv; return e;
+    case ETL_K_U32: e = parse_int(s, n, false, 4294967295ull, 0ull, &iv); o.tag = ETL_CELL_U32; o.val = (uint64_t)iv; return e;
+    case ETL_K_BOOL:
+      if (n == 1 && (s[0] == 't' || s[0] == 'f')) { o.tag = ETL_CELL_BOOL; o.val = s[0] == 't'; return 0; }
+      return ETL_E_BOOL;
+    case ETL_K_NUMERIC: return parse_numeric(s, n, hc, o);
+    case ETL_K_TIMESTAMPTZ:
+      if (parse_timestamptz_fmt(s, n, true, o)) return 0;   // text.rs:111 %#z
+      if (parse_timestamptz_fmt(s, n, false, o)) return 0;  // text.rs:113 %:z
+      return ETL_E_DATETIME;
+    case ETL_K_JSON:
+      if (!json_valid(s, n)) return ETL_E_JSON;
+      o.tag = ETL_CELL_JSON; o.val = soff; o.aux = n; return 0;
+    case ETL_K_DATE: {
+      Cur c{s, n}; int64_t days;
+      if (!parse_date_part(c, &days) || c.n != 0) return ETL_E_DATETIME;
+      o.tag = ETL_CELL_DATE; o.val = (uint64_t)days; return 0;
+    }
+    case ETL_K_TIME: {
+      Cur c{s, n}; int64_t secs; uint32_t ns;
+      if (!parse_time_part(c, &secs, &ns) || c.n != 0) return ETL_E_DATETIME;
+      o.tag = ETL_CELL_TIME; o.val = (uint64_t)secs; o.aux = ns; return 0;
+    }
+    case ETL_K_TIMESTAMP: {
+      Cur c{s, n}; int64_t days, secs; uint32_t ns;
+      if (!parse_ts_prefix(c, &days, &secs, &ns) || c.n != 0) return ETL_E_DATETIME;
+      o.tag = ETL_CELL_TIMESTAMP; o.val = (uint64_t)(days * 86400 + secs); o.aux = ns; return 0;
+    }
+    case ETL_K_UUID: return parse_uuid(s, n, hc, o);
+    case ETL_K_BYTES: return parse_bytea(s, n, hc, o);
+    default: return ETL_E_MALFORMED_FRAME;  // unsupported decode class: rejected on the host before launch
+  }
+}
+
+struct FrameCtx {
+  const DecodeParams& P;
+  EmitShared& sh;
+  uint64_t rec_index;     // global record index (for error keys)
+  uint64_t frame_off;     // absolute stream offset of the frame
+  const uint8_t* fp;      // frame bytes (shared window or global)
+  const uint8_t* kinds;
+  const uint8_t* flags;
+  HeapCursor hc;
+};
+
+// convert_tuple_data_to_cell (event.rs:934-979). returns 0 present, 1 missing, 2 error (reported)
+__device__ __forceinline__ int convert_cell(FrameCtx& fc, uint32_t col, uint32_t tag, const uint8_t* v, uint32_t len,
+                                            const CellOut* old_value, CellOut& out, uint32_t seq, uint32_t missing_code) {
+  uint32_t code = 0;
+  if (tag == 'n') {
+    if (fc.flags[col] & 1) { out.tag = ETL_CELL_NULL; out.val = 0; out.aux = 0; return 0; }
+    code = ETL_E_NOT_NULL;
+  } else if (tag == 'u') {
+    if (old_value) { out = *old_value; return 0; }
+    if (!missing_code) return 1;
+    code = missing_code;
+  } else if (tag == 't') {
+    uint32_t kind = fc.kinds[col];
+    bool defer = (kind == ETL_K_STRING) && len >= (uint32_t)kBigCell;
+    if (defer) {  // large text: verdict comes from the block-cooperative validator
+      uint32_t slot = atomicAdd(&fc.sh.n_big, 1u);
+      if (slot < (uint32_t)kBigQueue) { fc.sh.big[slot] = BigCell{v, len, seq, fc.rec_index}; }
+      else defer = false;  // queue full: validate inline
+    }
+    uint64_t soff = fc.frame_off + (uint64_t)(v - fc.fp);
+    code = parse_text_cell(kind, v, len, soff, fc.hc, out, defer);
+    if (!code) return 0;
+  } else code = ETL_E_BINARY_FORMAT;
+  report_error(fc.P, fc.rec_index, seq, code);
+  return 2;
+}
+
+// one DML frame: event.rs:376-523 (+ :550-919)
+__device__ __noinline__ void emit_dml(FrameCtx& fc, const FrameHead& h, const DevSchema* s, const CellSink& sink) {
+  const uint8_t* p = fc.fp;
+  const uint8_t* end = p + 1 + h.flen;
+  const uint32_t n_cols = s->n_cols, n_ident = s->n_ident;
+  const uint8_t* q = p + 35;
+  uint32_t n_old = 0;
+  // ---- old image
+  if (h.kind != 'I' && h.old_tag) {
+    const uint8_t* t = q + 1;
+    int32_t nc = (int32_t)(int16_t)be16(t);
+    if (nc < 0) nc = 0;
+    if (h.old_tag == 'K') {                               // normalize_key_tuple_to_row event.rs:879-919
+      if (n_ident == 0) { report_error(fc.P, fc.rec_index, SEQ_OLD_SHAPE, ETL_E_KEY_NO_COLUMNS); return; }
+      bool dense = (uint32_t)nc == n_ident, fullw = (uint32_t)nc == n_cols;
+      if (!dense && !fullw) { report_error(fc.P, fc.rec_index, SEQ_OLD_SHAPE, ETL_E_KEY_SHAPE); return; }
+      uint32_t k = 0, cmap = 0;
+      bool failed = false;
+      uint32_t used = walk_tuple(t, end, &nc, [&](int32_t i, uint32_t tag, const uint8_t* v, uint32_t len) {
+        if (failed) return;
+        uint32_t col;
+        if (dense) { while (cmap < n_cols && !(fc.flags[cmap] & 2)) cmap++; col = cmap++; }
+        else { col = (uint32_t)i; if (!(fc.flags[col] & 2)) return; }
+        CellOut c;
+        int r = convert_cell(fc, col, tag, v, len, nullptr, c, seq_old_cell((uint32_t)i), ETL_E_KEY_MISSING_VALUE);
+        if (r) { failed = true; return; }
+        sink.put(k++, c);
+      });
+      if (failed) return;
+      q = t + used;
+      n_old = n_ident;
+    } else {                                              // convert_tuple_to_row event.rs:550-583
+      if ((uint32_t)nc != n_cols) { report_error(fc.P, fc.rec_index, SEQ_OLD_SHAPE, ETL_E_FIELD_COUNT); return; }
+      bool failed = false;
+      uint32_t used = walk_tuple(t, end, &nc, [&](int32_t i, uint32_t tag, const uint8_t* v, uint32_t len) {
+        if (failed) return;
+        CellOut c;
+        int r = convert_cell(fc, (uint32_t)i, tag, v, len, nullptr, c, seq_old_cell((uint32_t)i), ETL_E_FULL_ROW_MISSING);
+        if (r) { failed = true; return; }
+        sink.put((uint32_t)i, c);
+      });
+      if (failed) return;
+      q = t + used;
+      n_old = n_cols;
+    }
+  }
+  if (h.kind == 'D') return;
+  // ---- new tuple
+  q++;  // 'N'
+  int32_t nc = (int32_t)(int16_t)be16(q);
+  if (nc < 0) nc = 0;
+  if ((uint32_t)nc != n_cols) { report_error(fc.P, fc.rec_index, SEQ_NEW_SHAPE, ETL_E_FIELD_COUNT); return; }
+  bool failed = false, partial = false;
+  uint32_t key_i = 0;
+  const bool is_update = h.kind == 'U';
+  walk_tuple(q, end, &nc, [&](int32_t i, uint32_t tag, const uint8_t* v, uint32_t len) {
+    if (failed) return;
+    CellOut c, oldv;
+    const CellOut* oldp = nullptr;
+    if (is_update) {                                      // OldRowResolver event.rs:722-762
+      bool is_ident = fc.flags[i] & 2;
+      if (h.old_tag == 'O') { if (tag == 'u') { oldv = sink.get((uint32_t)i); oldp = &oldv; } }
+      else if (h.old_tag == 'K' && is_ident) { if (tag == 'u') { oldv = sink.get(key_i); oldp = &oldv; } key_i++; }
+    }
+    int r = convert_cell(fc, (uint32_t)i, tag, v, len, oldp, c, seq_new_cell((uint32_t)i), is_update ? 0u : (uint32_t)ETL_E_FULL_ROW_MISSING);
+    if (r == 2) { failed = true; return; }
+    if (r == 1) { partial = true; c.tag = ETL_CELL_MISSING; c.val = 0; c.aux = 0; }
+    sink.put(n_old + (uint32_t)i, c);
+  });
+  if (partial) fc.P.rec_flags[fc.rec_index - fc.P.record_index_base] |= ETL_RF_NEW_PARTIAL;
+}
+
+__global__ void __launch_bounds__(kEmitThreads, 2) k_emit(DecodeParams P) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  EmitShared& sh = *reinterpret_cast<EmitShared*>(smem_raw);
+  const uint32_t spt = P.segs_per_tile;
+  for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+    const uint32_t seg0 = tile * spt;
+    const uint32_t seg1 = min(seg0 + spt, P.n_anchors);
+    const uint64_t t_begin = P.anchors[seg0];
+    const uint64_t t_end = P.anchors[seg1];
+    __syncthreads();  // previous tile fully consumed
+    if (threadIdx.x == 0) {
+      // exclusive prefix of this tile: carry ⊕ group prefix ⊕ earlier tiles of the group
+      uint32_t g = tile / P.tiles_per_group;
+      Summ pre = fold(P.carry, P.group_prefix[g]);
+      for (uint32_t t = g * P.tiles_per_group; t < tile; t++) pre = fold(pre, P.tile_summ[t]);
+      sh.chunk_carry = pre;
+      sh.n_big = 0;
+      sh.metrics[0] = sh.metrics[1] = sh.metrics[2] = sh.metrics[3] = 0;
+      uint32_t b = 0;
+      for (uint32_t s = seg0; s < seg1; s++) { sh.seg_base[s - seg0] = b; b += P.seg_frames[s]; }
+      sh.seg_base[seg1 - seg0] = b;
+    }
+    if (t_end <= t_begin) { __syncthreads(); continue; }
+    // ---- stage the tile: coalesced 16-byte loads (window starts at the 16-byte boundary below t_begin)
+    const uint64_t win0 = t_begin & ~15ull;
+    const uint32_t lead = (uint32_t)(t_begin - win0);
+    const uint64_t want = (t_end - win0 + 15ull) & ~15ull;
+    uint64_t wb = want;
+    const uint64_t to_end = ((uint64_t)(P.len - win0) + 15ull) & ~15ull;
+    if (to_end < wb) wb = to_end;
+    if ((uint64_t)kTileCap < wb) wb = (uint64_t)kTileCap;
+    const uint32_t win_bytes = (uint32_t)wb;
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(P.buf + win0);
+      uint4* dst = reinterpret_cast<uint4*>(sh.tile);
+      for (uint32_t i = threadIdx.x; i < win_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const uint32_t n_frames = sh.seg_base[seg1 - seg0];
+    // ---- frame list: one walker thread per segment, in shared memory
+    if (threadIdx.x < seg1 - seg0) {
+      uint64_t pos = P.anchors[seg0 + threadIdx.x];
+      const uint64_t stop = P.anchors[seg0 + threadIdx.x + 1];
+      uint32_t k = sh.seg_base[threadIdx.x];
+      while (pos < stop && k < (uint32_t)kMaxTileFrames) {
+        uint32_t rel = (uint32_t)(pos - win0);
+        uint32_t flen;
+        if (rel + 5 <= win_bytes) {
+          const uint8_t* p = sh.tile + rel;
+          uint64_t avail = P.len - pos;
+          if (p[0] != 'd' || avail < 5) flen = (uint32_t)(avail > 0 ? avail - 1 : 0);
+          else { flen = be32(p + 1); if (flen < 4 || 1ull + flen > avail) flen = (uint32_t)(avail - 1); }
+        } else {
+          FrameHead hh = read_head(P.buf + pos, P.len - pos);
+          flen = hh.flen;
+        }
+        sh.foff[k++] = (uint32_t)(pos - t_begin);
+        pos += 1ull + flen;
+      }
+    }
+    __syncthreads();
+    // ---- frames in chunks of blockDim: classify → ordered scan → emit
+    for (uint32_t c0 = 0; c0 < n_frames; c0 += blockDim.x) {
+      const uint32_t f = c0 + threadIdx.x;
+      const bool active = f < n_frames;
+      FrameHead h;
+      h.malformed = true; h.kind = 0; h.flen = 0; h.rel = 0; h.old_tag = 0;
+      Summ e = summ_identity();
+      const uint8_t* fp = nullptr;
+      uint64_t foff_abs = 0;
+      const DevSchema* s = nullptr;
+      if (active) {
+        foff_abs = t_begin + sh.foff[f];
+        const uint32_t rel = lead + sh.foff[f];
+        // head from global if it may straddle the window; body pointer decided after flen is known
+        const uint8_t* gp = P.buf + foff_abs;
+        const bool head_in = rel + 40 <= win_bytes;
+        h = read_head(head_in ? sh.tile + rel : gp, P.len - foff_abs);
+        fp = (rel + 1ull + h.flen <= win_bytes) ? sh.tile + rel : gp;
+        e = frame_state_elem(h, fp);
+        if (!h.malformed) {
+          if (h.kind == 'I' || h.kind == 'U' || h.kind == 'D') s = find_schema(P, h.rel, foff_abs);
+          e.n_cells = frame_out_cells(h, s);
+          if (s && s->has_heap) e.heap = frame_heap_bytes(P, h, s, fp);
+        }
+      }
+      Summ chunk_total;
+      Summ pre = block_exclusive_scan(e, sh.warp_summ, &chunk_total);
+      const Summ carry = sh.chunk_carry;
+      pre = fold(carry, pre);
+      __syncthreads();
+      if (threadIdx.x == 0) sh.chunk_carry = fold(carry, chunk_total);
+      if (active) {
+        const uint64_t ridx = pre.n_rec;             // index within this shard
+        const uint64_t gidx = P.record_index_base + ridx;
+        const bool in_tx = (pre.flags & S_HAS_B) && !(pre.flags & S_CLOSED);
+        uint64_t commit_lsn = 0, ordinal = 0, start_lsn = 0;
+        uint32_t rflags = 0;
+        int32_t rschema = -1;
+        uint32_t rrel = h.rel;
+        const CellSink sink{P, pre.n_cells};
+        bool ok = true;
+        unsigned long long tb = 0;
+        bool wellformed = !h.malformed;
+        if (wellformed && (h.kind == 'I' || h.kind == 'U' || h.kind == 'D')) wellformed = dml_structure_ok(h, fp, &tb);
+        if (wellformed && h.kind == 'O') wellformed = (h.flen >= 4 + 26 + 8) && cstr_end(fp + 39, fp + 1 + h.flen) != nullptr;
+        if (wellformed && h.kind == 'Y') {
+          const uint8_t* fe = fp + 1 + h.flen;
+          const uint8_t* q1 = (h.flen >= 4 + 26 + 4) ? cstr_end(fp + 35, fe) : nullptr;
+          wellformed = q1 != nullptr && cstr_end(q1, fe) != nullptr;
+        }
+        if (!wellformed) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; }
+        else if (h.kind == 'k') { start_lsn = be64(fp + 6); rrel = fp[22]; }
+        else {
+          start_lsn = be64(fp + 6);                   // wal_start apply.rs:1700
+          const uint8_t* m = fp + 31;                 // message body after the tag
+          switch (h.kind) {
+            case 'B':                                 // apply.rs:1927-1943
+              commit_lsn = be64(m); ordinal = 0; rflags = ETL_RF_EVENT;
+              sink.put(0, ETL_CELL_I64, be64(m + 8), 0);
+              sink.put(1, ETL_CELL_U32, be32(m + 16), 0);
+              break;
+            case 'C': {                               // apply.rs:1946-2006
+              if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; break; }
+              uint64_t cl = be64(m + 1);
+              if (cl != pre.lsn) { report_error(P, gidx, SEQ_STATE, ETL_E_COMMIT_LSN); ok = false; break; }
+              commit_lsn = cl; ordinal = pre.ord; rflags = ETL_RF_EVENT;
+              sink.put(0, ETL_CELL_I32, (uint64_t)(int64_t)(int8_t)m[0], 0);
+              sink.put(1, ETL_CELL_I64, be64(m + 9), 0);
+              sink.put(2, ETL_CELL_I64, be64(m + 17), 0);
+              break;
+            }
+            case 'R':                                 // apply.rs:2012-2089 (masks are built on the host)
+              for (uint32_t k = 0; k < P.n_rel_errors; k++)     // Relation frames the host could not turn into masks
+                if (P.rel_error_off[k] == foff_abs) { report_error(P, gidx, P.rel_error_seq[k], P.rel_error_code[k]); ok = false; }
+              if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; break; }
+              commit_lsn = pre.lsn; ordinal = pre.ord; rflags = ETL_RF_EVENT;
+              { const DevSchema* rs = find_schema(P, h.rel, foff_abs); if (rs && rs->effective_off == foff_abs) rschema = (int32_t)rs->batch_index; }
+              break;
+            case 'I': case 'U': case 'D': {           // apply.rs:2092-2203
+              if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; break; }
+              commit_lsn = pre.lsn; ordinal = pre.ord;
+              if (!s) { report_error(P, gidx, SEQ_TABLE, ETL_E_MISSING_TABLE_STATE); ok = false; break; }
+              rschema = (int32_t)s->batch_index; rflags = ETL_RF_EVENT;
+              if (h.old_tag == 'O') rflags |= ETL_RF_OLD_FULL; else if (h.old_tag == 'K') rflags |= ETL_RF_OLD_KEY;
+              break;
+            }
+            case 'T': {                               // apply.rs:2206-2248
+              if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; break; }
+              commit_lsn = pre.lsn; ordinal = pre.ord;
+              sink.put(0, ETL_CELL_I32, (uint64_t)(int64_t)(int8_t)m[4], 0);
+              for (uint32_t i = 0; i < h.rel; i++) {
+                uint32_t rid = be32(m + 5 + 4 * i);
+                const DevSchema* ts = find_schema(P, rid, foff_abs);
+                if (!ts) { report_error(P, gidx, SEQ_TABLE, ETL_E_MISSING_TABLE_STATE); ok = false; break; }
+                sink.put(1 + i, ETL_CELL_U32, rid, ts->batch_index);
+              }
+              if (h.rel > 0) rflags = ETL_RF_EVENT;
+              break;
+            }
+            case 'M': {                               // apply.rs:1808-1924
+              // flags i8, lsn u64, prefix cstr, len i32, content — structure checked here
+              const uint8_t* end = fp + 1 + h.flen;
+              const uint8_t* q = m + 9;
+              const char* ddl = "supabase_etl_ddl";
+              bool is_ddl = true; uint32_t k = 0; bool term = false;
+              if (q > end) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; break; }
+              for (; q + k < end; k++) { uint32_t ch = q[k]; if (!ch) { term = true; break; } if (k >= 16 || ch != (uint32_t)(uint8_t)ddl[k]) is_ddl = false; }
+              if (!term || !utf8_valid(q, k)) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; break; }
+              is_ddl = is_ddl && k == 16;
+              const uint8_t* cq = q + k + 1;
+              if (cq + 4 > end) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; break; }
+              int32_t cl = (int32_t)be32(cq);
+              if (cl < 0 || (uint64_t)cl > (uint64_t)(end - cq - 4)) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; break; }
+              if (is_ddl) { rflags |= ETL_RF_DDL_MESSAGE; if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; } }
+              break;
+            }
+            default: break;                           // Origin / Type: structure only
+          }
+        }
+        P.rec_off[ridx] = foff_abs; P.rec_kind[ridx] = (uint8_t)h.kind; P.rec_flags[ridx] = (uint8_t)rflags;
+        P.rec_rel[ridx] = rrel; P.rec_schema[ridx] = rschema; P.rec_start_lsn[ridx] = start_lsn;
+        P.rec_commit_lsn[ridx] = commit_lsn; P.rec_tx_ordinal[ridx] = ordinal; P.rec_cell_base[ridx] = pre.n_cells;
+        if (ok && (rflags & ETL_RF_EVENT)) atomicAdd(&sh.metrics[3], 1ull);
+        if (ok && s && (h.kind == 'I' || h.kind == 'U' || h.kind == 'D')) {
+          FrameCtx fc{P, sh, gidx, foff_abs, fp, P.col_kind + s->col_base, P.col_flags + s->col_base, HeapCursor{P.heap, pre.heap}};
+          emit_dml(fc, h, s, sink);
+          atomicAdd(&sh.metrics[h.kind == 'I' ? 0 : (h.kind == 'U' ? 1 : 2)], tb);
+        }
+      }
+      __syncthreads();
+    }
+    // ---- large text cells: block-cooperative UTF-8 validation, 16-byte chunks per thread
+    __syncthreads();
+    const uint32_t nb = min(sh.n_big, (uint32_t)kBigQueue);
+    for (uint32_t b = 0; b < nb; b++) {
+      const BigCell bc = sh.big[b];
+      bool bad = false;
+      for (uint32_t lo = threadIdx.x * 32u; lo < bc.len; lo += blockDim.x * 32u) {
+        uint32_t hi = min(lo + 32u, bc.len);
+        bad |= !utf8_chunk_valid(bc.ptr, bc.len, lo, hi);
+      }
+      if (__syncthreads_or(bad) && threadIdx.x == 0) report_error(P, bc.rec_index, bc.seq, ETL_E_UTF8);
+    }
+    if (threadIdx.x < 4 && sh.metrics[threadIdx.x]) atomicAdd(&P.metrics[threadIdx.x], sh.metrics[threadIdx.x]);
+  }
+}
+
+}  // namespace etl

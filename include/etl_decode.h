@@ -221,6 +221,7 @@ typedef struct etl_dec_input {
   const uint8_t* dev_buf;        /* optional: same bytes already resident in HBM (NULL → library copies) */
   uint64_t len;
   const uint64_t* anchors;       /* host array, n_anchors entries, see etl_stager */
+  const uint64_t* dev_anchors;   /* optional: n_anchors + 1 entries resident in HBM, last entry = len */
   uint64_t n_anchors;
   uint32_t anchor_stride;
   uint32_t _pad;
@@ -235,6 +236,9 @@ typedef struct etl_dec_ctx etl_dec_ctx;
 typedef struct etl_dec_batch etl_dec_batch;
 
 int etl_dec_create(int device_id, etl_dec_ctx** out);
+/* run on the caller's CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream);
+ * default: a private stream created by etl_dec_create */
+int etl_dec_set_stream(etl_dec_ctx*, void* cuda_stream);
 void etl_dec_destroy(etl_dec_ctx*);
 const char* etl_dec_last_error(const etl_dec_ctx*);
 uint32_t etl_dec_abi_version(void);
@@ -271,8 +275,9 @@ int etl_dec_decode_finish(etl_dec_ctx*, const etl_stream_state* carry_in, uint64
                           etl_dec_batch** out);
 void etl_dec_batch_free(etl_dec_batch*);
 
-/* result planes. *_dev pointers are device memory owned by the batch; *_host are valid only when
- * ETL_DECODE_RESULTS_TO_HOST was set. All arrays are in stream order. */
+/* result planes. Device planes are owned by the batch. Host planes exist only when
+ * ETL_DECODE_RESULTS_TO_HOST was set; they live in a pinned buffer cached on the ctx and stay
+ * valid until the next decode on the same ctx. All arrays are in stream order. */
 typedef struct etl_dec_planes {
   uint64_t n_records;
   uint64_t n_cells;
@@ -306,7 +311,10 @@ typedef struct etl_dec_summary {
   uint32_t gpu_launches;  /* kernels launched for this batch */
   float kernel_ms;        /* CUDA-event time of the kernel sequence (resident input → resident output) */
   float h2d_ms, d2h_ms;
-  uint32_t _pad;
+  float index_ms;         /* k_index + k_scan */
+  float emit_ms;          /* k_emit (the dominant kernel) */
+  uint32_t _pad[3];
+  uint64_t h2d_bytes, d2h_bytes; /* bytes copied host→device / device→host for this batch */
 } etl_dec_summary;
 
 int etl_dec_batch_planes(const etl_dec_batch*, int host, etl_dec_planes* out);

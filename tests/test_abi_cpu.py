@@ -1,0 +1,82 @@
+"""CPU-side checks of the C ABI: the library loads, exports every symbol include/etl_decode.h
+declares, the stager indexes frames correctly, and the decode path refuses to run without a GPU
+(no CPU fallback).  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from etl_b200 import abi, pgoutput as pg, workloads as wl
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = abi.load()
+    header = open(os.path.join(ROOT, "include", "etl_decode.h")).read()
+    declared = set(re.findall(r"\b(etl_(?:dec|stage)_[a-z_]+)\s*\(", header))
+    assert declared == set(abi.EXPORTS), declared ^ set(abi.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.etl_dec_abi_version() == 1
+
+
+def test_struct_layouts_match_header_sizes():
+    # sizes the C compiler gives (x86-64 SysV): guards against silent ABI drift in the bindings
+    assert C.sizeof(abi.ColumnSchema) == 32
+    assert C.sizeof(abi.StreamState) == 24
+    assert C.sizeof(abi.FirstError) == 24
+    assert C.sizeof(abi.DecInput) == 96
+    assert C.sizeof(abi.Seam) == 48
+    assert C.sizeof(abi.Planes) == 128
+    assert C.sizeof(abi.Summary) == 136
+    assert C.sizeof(abi.SchemaInfo) == 56
+
+
+@pytest.mark.parametrize("stride", [256, 2048, 32768])
+def test_stager_anchor_index_matches_definition(stride):
+    from etl_b200.decoder import Stager
+    w = wl.make("c5", 0.0005, n_segments=2)
+    stream, stats = w.generate()
+    st = Stager(stream.nbytes, stride)
+    st.append_framed(stream)
+    v = st.view()
+    anchors = np.ctypeslib.as_array(C.cast(v.anchors, abi.u64p), shape=(int(v.n_anchors),)).copy()
+    rels = np.ctypeslib.as_array(C.cast(v.relation_offsets, abi.u64p), shape=(int(v.n_relations),)).copy()
+    raw = stream.tobytes()
+    assert anchors.tolist() == pg.build_anchors(raw, stride)
+    assert rels.tolist() == pg.scan_relation_offsets(raw)
+    assert v.len == len(raw) and v.anchor_stride == stride
+    assert np.array_equal(st.host_array(), stream)
+    st.close()
+
+
+def test_stager_append_bodies_equals_framed():
+    from etl_b200.decoder import Stager
+    w = pg.StreamWriter()
+    w.emit(pg.begin(5, 6, 7))
+    w.emit(pg.relation(9, "public", "t", "d", [(1, "id", 20, -1)]))
+    w.emit_keepalive()
+    w.emit(pg.commit(0, 5, 13, 8))
+    raw = w.bytes()
+    st = Stager(1 << 16, 256)
+    pos = 0
+    while pos < len(raw):
+        n = int.from_bytes(raw[pos + 1:pos + 5], "big")
+        st.append(raw[pos + 5:pos + 1 + n])
+        pos += 1 + n
+    assert st.host_array().tobytes() == raw
+    v = st.view()
+    assert v.n_relations == 1 and v.n_anchors == -(-len(raw) // 256)
+    st.close()
+
+
+def test_decoder_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from etl_b200.decoder import Decoder, DecodeError
+    with pytest.raises(DecodeError):
+        Decoder(0)
