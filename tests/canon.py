@@ -177,7 +177,10 @@ def assert_planes_equal(got, want, stream: bytes, check_heap_contents: bool = Tr
             b = decode_cell(int(wt[i]), int(wv[i]), int(wa[i]), stream, wh)
             if a != b:
                 raise AssertionError(f"var cell {i} (tag {wt[i]}) differs: got {a} want {b}")
-    # schema versions
+    # schema versions (the host installs every Relation of the batch up front; after a data error
+    # only the records before it are specified, so versions are compared for clean batches only)
+    if want.first_error[0] is not None:
+        return
     assert len(got.schemas) == len(want.schemas), (len(got.schemas), len(want.schemas))
     for i, (a, b) in enumerate(zip(got.schemas, want.schemas)):
         assert (a.table_id, a.n_cols, a.n_identity, a.effective_off) == (b.table_id, b.n_cols, b.n_identity, b.effective_off), f"schema {i}"
