@@ -573,11 +573,13 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
   b->schemas = std::move(ctx->pending_schemas);
 
   // ---- one device block for all planes
-  const uint64_t nr = T.n_rec, nc = T.n_cells, nh = T.heap;
+  bool any_heap = false;
+  for (const RelVersion& v : b->schemas) for (uint8_t k : v.kind) any_heap = any_heap || kind_has_heap(k);
+  // upper bound on Σ cell_heap_bound: numeric ≤ n/2+19, bytea ≤ n/2+7, uuid = 16 per decoded text cell
+  const uint64_t nr = T.n_rec, nc = T.n_cells, nh = any_heap ? (P.len / 2 + 24 * T.n_cells + 256) : 0;
   auto al = [](uint64_t x) { return (x + 255) & ~255ull; };
-  uint64_t o_off = 0, cur = 0;
+  uint64_t cur = 0;
   auto take = [&](uint64_t bytes) { uint64_t o = cur; cur += al(bytes); return o; };
-  (void)o_off;
   const uint64_t f_rec_off = take(nr * 8), f_kind = take(nr), f_flags = take(nr), f_rel = take(nr * 4), f_schema = take(nr * 4),
                  f_start = take(nr * 8), f_commit = take(nr * 8), f_ord = take(nr * 8), f_cbase = take((nr + 1) * 8),
                  f_tag = take(nc), f_val = take(nc * 8), f_aux = take(nc * 4), f_heap = take(nh);
@@ -597,6 +599,7 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
   P.rec_commit_lsn = (uint64_t*)b->dev.rec_commit_lsn; P.rec_tx_ordinal = (uint64_t*)b->dev.rec_tx_ordinal;
   P.rec_cell_base = (uint64_t*)b->dev.rec_cell_base; P.cell_tag = (uint8_t*)b->dev.cell_tag; P.cell_val = (uint64_t*)b->dev.cell_val;
   P.cell_aux = (uint32_t*)b->dev.cell_aux; P.heap = (uint8_t*)b->dev.heap;
+  P.heap_top = ctx->d_scalars.p + 5; P.heap_cap = nh;
   P.record_index_base = record_index_base;
   Summ carry = summ_identity();
   etl_stream_state cin{};
@@ -606,9 +609,8 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
   P.carry = carry;
 
   // ---- pass C
-  ctx->h_scalars[0] = ~0ull; ctx->h_scalars[1] = ctx->h_scalars[2] = ctx->h_scalars[3] = ctx->h_scalars[4] = 0;
-  CK(cudaMemcpyAsync(ctx->d_scalars.p, ctx->h_scalars, 5 * 8, cudaMemcpyHostToDevice, st));
-  if (nh) CK(cudaMemsetAsync((void*)b->dev.heap, 0, nh, st));  // reserved-but-unused heap bytes read as zero
+  ctx->h_scalars[0] = ~0ull; ctx->h_scalars[1] = ctx->h_scalars[2] = ctx->h_scalars[3] = ctx->h_scalars[4] = ctx->h_scalars[5] = 0;
+  CK(cudaMemcpyAsync(ctx->d_scalars.p, ctx->h_scalars, 6 * 8, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(ctx->ev[3], st));
   if (P.n_tiles) {
     int sms = 148;
@@ -620,7 +622,11 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
   }
   CK(cudaMemcpyAsync((void*)(b->dev.rec_cell_base + nr), &ctx->h_total->n_cells, 8, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(ctx->ev[4], st));
-  CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars.p, 5 * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars.p, 6 * 8, cudaMemcpyDeviceToHost, st));
+  uint64_t heap_used = nh;
+  if (nh) { CK(cudaStreamSynchronize(st)); heap_used = std::min<uint64_t>(nh, ctx->h_scalars[5]); }
+  const uint64_t copy_bytes = f_heap + heap_used;
+  b->dev.heap_bytes = heap_used;
   if (ctx->pending_flags & ETL_DECODE_RESULTS_TO_HOST) {
     if (ctx->h_result_cap < b->block_bytes) {
       if (ctx->h_result) cudaFreeHost(ctx->h_result);
@@ -630,8 +636,9 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
       ctx->h_result_cap = want;
     }
     b->host_block = ctx->h_result;
-    CK(cudaMemcpyAsync(b->host_block, b->dev_block, cur, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(b->host_block, b->dev_block, copy_bytes, cudaMemcpyDeviceToHost, st));
     fill(b->host, (uint8_t*)b->host_block);
+    b->host.heap_bytes = heap_used;
     b->has_host = true;
   }
   CK(cudaEventRecord(ctx->ev[5], st));
@@ -647,7 +654,7 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
   S.index_ms = ctx->pending_index_ms; S.emit_ms = emit_ms;
   S.h2d_ms = ctx->pending_h2d_ms; S.d2h_ms = d2h_ms;
   S.h2d_bytes = ctx->pending_h2d_bytes;
-  S.d2h_bytes = 5 * 8 + sizeof(Summ) + ((ctx->pending_flags & ETL_DECODE_RESULTS_TO_HOST) ? cur : 0);
+  S.d2h_bytes = 5 * 8 + sizeof(Summ) + ((ctx->pending_flags & ETL_DECODE_RESULTS_TO_HOST) ? copy_bytes : 0);
   S.gpu_launches = ctx->launches;
   S.n_schemas = (uint32_t)b->schemas.size();
   unsigned long long key = ctx->h_scalars[0];

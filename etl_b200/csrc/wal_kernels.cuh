@@ -21,7 +21,7 @@
 namespace etl {
 
 constexpr int kTileBytes = 32768;      // nominal tile = kTileBytes of stream (frames that START inside it)
-constexpr int kTileCap = 40960;        // shared-memory window; bytes past it are read from global
+constexpr int kTileCap = 36864;        // shared-memory window; bytes past it are read from global
 constexpr int kEmitThreads = 256;
 constexpr int kMaxTileFrames = 2048;   // > kTileBytes/23 + segments
 constexpr int kIndexThreads = 256;
@@ -92,6 +92,8 @@ struct DecodeParams {
   uint64_t* rec_start_lsn; uint64_t* rec_commit_lsn; uint64_t* rec_tx_ordinal; uint64_t* rec_cell_base;
   uint8_t* cell_tag; uint64_t* cell_val; uint32_t* cell_aux;
   uint8_t* heap;
+  unsigned long long* heap_top;     // bump pointer: rounds of the emit pass reserve their heap bytes here
+  uint64_t heap_cap;                // 0 when no schema of the batch has a heap-kind column
   unsigned long long* first_error;  // atomicMin key: rec_index << 24 | seq << 6 | code
   unsigned long long* metrics;      // [0] insert bytes [1] update bytes [2] delete bytes [3] events
   // Relation frames rejected on the host (missing stored schema / unknown columns / malformed)
@@ -310,7 +312,6 @@ __global__ void __launch_bounds__(kIndexThreads) k_index(DecodeParams P) {
         const DevSchema* s = nullptr;
         if (h.kind == 'I' || h.kind == 'U' || h.kind == 'D') s = find_schema(P, h.rel, pos);
         e.n_cells = frame_out_cells(h, s);
-        if (s && s->has_heap) e.heap = frame_heap_bytes(P, h, s, p);
       }
       acc = fold(acc, e);
       nframes++;
@@ -368,26 +369,50 @@ __global__ void __launch_bounds__(512) k_scan(DecodeParams P) {
 }
 
 // ================================================================================================
-// pass C: emit
-struct BigCell {
+// pass C: emit.  Per 32 KiB tile:
+//   1. stage the tile in shared memory (coalesced 16-byte loads)
+//   2. frame list (one walker thread per anchor segment)
+//   3. per 256-frame chunk: classify heads → ordered block scan (record index, cell base, heap base,
+//      stream state) → record plane; Begin/Commit/Truncate cells
+//   4. DML frames: thread-per-frame WALKERS follow the TupleData chain and emit one 16-byte
+//      descriptor per text cell into a shared batch (NULL / unchanged-TOAST cells are resolved by
+//      the walker itself); then thread-per-CELL parsing of the batch (all lanes busy even for
+//      100-column rows); long text goes to a queue that warps validate with 16-byte loads.
+struct CellDesc {
+  uint32_t rel;       // offset of the cell's tag byte inside its frame
+  uint32_t meta;      // frame slot (8) | kind (8) | is_new (1) | wire index (15); 0xFFFFFFFF = empty
+  uint32_t dest_rel;  // output cell index relative to the tile's first cell
+  uint32_t heap_off;  // filled by the parse phase: offset inside this round's heap reservation
+};
+struct WideText {
   const uint8_t* ptr;
   uint32_t len;
   uint32_t seq;
-  uint64_t rec_index;
+  uint32_t rec_local;
 };
 
+constexpr int kDescCap = 1024;
+constexpr int kWideCap = 128;
+constexpr int kWideLen = 96;   // text cells at least this long are validated warp-cooperatively
+constexpr uint32_t kCellUnresolved = 253;  // internal: unchanged-TOAST cell awaiting its old value
+
 struct EmitShared {
-  alignas(16) uint8_t tile[kTileCap];
-  uint32_t foff[kMaxTileFrames];
+  alignas(16) uint8_t tile[kTileCap + 32];
+  uint16_t foff[kMaxTileFrames];   // frame starts relative to the tile start (< 32 KiB)
+  CellDesc desc[kDescCap];
+  const uint8_t* fi_base[kEmitThreads];   // per chunk slot: frame bytes (window or global)
+  uint64_t fi_off[kEmitThreads];          // absolute stream offset of the frame
+  uint32_t fi_rec[kEmitThreads];          // shard-local record index
+  WideText wide[kWideCap];
   uint32_t seg_base[132];
   Summ warp_summ[kEmitThreads / 32];
   Summ chunk_carry;
-  BigCell big[kBigQueue];
-  uint32_t n_big;
+  uint32_t n_desc, n_wide, wide_next;
+  uint32_t scan_u32[kEmitThreads / 32];
+  unsigned long long round_heap_base;
   unsigned long long metrics[4];
 };
 
-// inclusive block scan of Summ (ordered), returns exclusive prefix within the block and the block total
 __device__ __forceinline__ Summ shfl_up_summ(const Summ& v, int d) {
   Summ r;
   r.lsn = __shfl_up_sync(0xffffffffu, v.lsn, d);
@@ -398,6 +423,7 @@ __device__ __forceinline__ Summ shfl_up_summ(const Summ& v, int d) {
   r.flags = __shfl_up_sync(0xffffffffu, v.flags, d);
   return r;
 }
+// ordered exclusive scan of one Summ per thread; *total = fold of the whole block
 __device__ __forceinline__ Summ block_exclusive_scan(const Summ& mine, Summ* warp_summ, Summ* total) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   Summ inc = mine;
@@ -419,25 +445,42 @@ __device__ __forceinline__ Summ block_exclusive_scan(const Summ& mine, Summ* war
   return fold(wpre, excl);
 }
 
-struct CellSink {
-  const DecodeParams& P;
-  uint64_t base;  // first output cell of the frame
-  __device__ __forceinline__ void put(uint32_t i, const CellOut& c) const {
-    P.cell_tag[base + i] = (uint8_t)c.tag; P.cell_val[base + i] = c.val; P.cell_aux[base + i] = c.aux;
-  }
-  __device__ __forceinline__ void put(uint32_t i, uint32_t tag, uint64_t val, uint32_t aux) const {
-    P.cell_tag[base + i] = (uint8_t)tag; P.cell_val[base + i] = val; P.cell_aux[base + i] = aux;
-  }
-  __device__ __forceinline__ CellOut get(uint32_t i) const {
-    CellOut c; c.tag = P.cell_tag[base + i]; c.val = P.cell_val[base + i]; c.aux = P.cell_aux[base + i]; return c;
-  }
-};
+// unaligned little-endian 8-byte load built from aligned 32-bit words (works on the shared window
+// and on global memory; may touch up to 3 bytes before and 11 after p — buffers are padded)
+__device__ __forceinline__ uint64_t ld64u(const uint8_t* p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+  const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+  const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+  return ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
+}
+// cell header at p: tag byte + big-endian length
+__device__ __forceinline__ void cell_header(const uint8_t* p, uint32_t* tag, uint32_t* len) {
+  const uint64_t x = ld64u(p);
+  *tag = (uint32_t)(x & 0xFFu);
+  *len = __byte_perm((uint32_t)(x >> 8), 0, 0x0123);
+}
 
-// text.rs:28-173 dispatch for one 't' cell. `soff` = absolute stream offset of the value bytes.
+// UTF-8 check of a short/medium cell with word loads: all-ASCII words pass immediately
+__device__ __forceinline__ bool utf8_valid_fast(const uint8_t* s, uint32_t n) {
+  uint32_t hi = 0;
+  uint32_t i = 0;
+  for (; i + 8 <= n; i += 8) { uint64_t x = ld64u(s + i); hi |= (uint32_t)(x >> 32) | (uint32_t)x; }
+  if (i < n) {
+    uint64_t x = ld64u(s + i);
+    uint32_t r = n - i;  // 1..7 valid bytes
+    x &= (r >= 8) ? ~0ull : ((1ull << (8 * r)) - 1ull);
+    hi |= (uint32_t)(x >> 32) | (uint32_t)x;
+  }
+  if (!(hi & 0x80808080u)) return true;
+  return utf8_valid(s, n);
+}
+
+// text.rs:28-173 dispatch for one text cell whose bytes are known to be valid UTF-8 unless
+// `check_utf8`. `soff` = absolute stream offset of the value bytes.
 __device__ __forceinline__ uint32_t parse_text_cell(uint32_t kind, const uint8_t* s, uint32_t n, uint64_t soff,
-                                                    HeapCursor& hc, CellOut& o, bool defer_utf8) {
+                                                    HeapCursor& hc, CellOut& o) {
   o.aux = 0;
-  if (!defer_utf8 && !utf8_valid(s, n)) return ETL_E_UTF8;  // event.rs:972
   int64_t iv;
   uint32_t e;
   switch (kind) {
@@ -478,120 +521,156 @@ __device__ __forceinline__ uint32_t parse_text_cell(uint32_t kind, const uint8_t
   }
 }
 
-struct FrameCtx {
-  const DecodeParams& P;
-  EmitShared& sh;
-  uint64_t rec_index;     // global record index (for error keys)
-  uint64_t frame_off;     // absolute stream offset of the frame
-  const uint8_t* fp;      // frame bytes (shared window or global)
+// ---- walker: one thread follows the TupleData chain(s) of one DML frame (event.rs:376-919)
+enum : uint8_t { W_OLD_HDR = 0, W_OLD_CELLS = 1, W_NEW_HDR = 2, W_NEW_CELLS = 3, W_DONE = 4 };
+struct Walker {
+  const uint8_t* base;   // frame start
+  const uint8_t* p;      // next byte to read
+  const uint8_t* end;    // frame end
   const uint8_t* kinds;
   const uint8_t* flags;
-  HeapCursor hc;
+  uint64_t rec_index;    // global record index (error keys)
+  uint32_t rec_local;
+  uint32_t n_cols, n_ident;
+  uint32_t cell0;        // first output cell of the frame, relative to the tile's cell base
+  int32_t remaining;     // wire cells left in the current tuple
+  uint32_t wire_i, cmap, k_out, key_i, n_old;
+  uint8_t kind, old_tag, stage;
+  bool dense, partial, has_unresolved;
+  bool emit;             // false after the first data error: keep checking structure only, because a
+                         // malformed frame (parser error) outranks every conversion error of the record
 };
-
-// convert_tuple_data_to_cell (event.rs:934-979). returns 0 present, 1 missing, 2 error (reported)
-__device__ __forceinline__ int convert_cell(FrameCtx& fc, uint32_t col, uint32_t tag, const uint8_t* v, uint32_t len,
-                                            const CellOut* old_value, CellOut& out, uint32_t seq, uint32_t missing_code) {
-  uint32_t code = 0;
-  if (tag == 'n') {
-    if (fc.flags[col] & 1) { out.tag = ETL_CELL_NULL; out.val = 0; out.aux = 0; return 0; }
-    code = ETL_E_NOT_NULL;
-  } else if (tag == 'u') {
-    if (old_value) { out = *old_value; return 0; }
-    if (!missing_code) return 1;
-    code = missing_code;
-  } else if (tag == 't') {
-    uint32_t kind = fc.kinds[col];
-    bool defer = (kind == ETL_K_STRING) && len >= (uint32_t)kBigCell;
-    if (defer) {  // large text: verdict comes from the block-cooperative validator
-      uint32_t slot = atomicAdd(&fc.sh.n_big, 1u);
-      if (slot < (uint32_t)kBigQueue) { fc.sh.big[slot] = BigCell{v, len, seq, fc.rec_index}; }
-      else defer = false;  // queue full: validate inline
-    }
-    uint64_t soff = fc.frame_off + (uint64_t)(v - fc.fp);
-    code = parse_text_cell(kind, v, len, soff, fc.hc, out, defer);
-    if (!code) return 0;
-  } else code = ETL_E_BINARY_FORMAT;
-  report_error(fc.P, fc.rec_index, seq, code);
-  return 2;
+__device__ __forceinline__ void walker_data_error(const DecodeParams& P, Walker& w, uint32_t seq, uint32_t code) {
+  report_error(P, w.rec_index, seq, code);
+  w.emit = false;
+}
+__device__ __forceinline__ void walker_malformed(const DecodeParams& P, Walker& w) {
+  report_error(P, w.rec_index, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME);
+  w.stage = W_DONE;
+}
+__device__ __forceinline__ void put_cell(const DecodeParams& P, uint64_t idx, uint32_t tag, uint64_t val, uint32_t aux) {
+  P.cell_tag[idx] = (uint8_t)tag; P.cell_val[idx] = val; P.cell_aux[idx] = aux;
 }
 
-// one DML frame: event.rs:376-523 (+ :550-919)
-__device__ __noinline__ void emit_dml(FrameCtx& fc, const FrameHead& h, const DevSchema* s, const CellSink& sink) {
-  const uint8_t* p = fc.fp;
-  const uint8_t* end = p + 1 + h.flen;
-  const uint32_t n_cols = s->n_cols, n_ident = s->n_ident;
-  const uint8_t* q = p + 35;
-  uint32_t n_old = 0;
-  // ---- old image
-  if (h.kind != 'I' && h.old_tag) {
-    const uint8_t* t = q + 1;
-    int32_t nc = (int32_t)(int16_t)be16(t);
-    if (nc < 0) nc = 0;
-    if (h.old_tag == 'K') {                               // normalize_key_tuple_to_row event.rs:879-919
-      if (n_ident == 0) { report_error(fc.P, fc.rec_index, SEQ_OLD_SHAPE, ETL_E_KEY_NO_COLUMNS); return; }
-      bool dense = (uint32_t)nc == n_ident, fullw = (uint32_t)nc == n_cols;
-      if (!dense && !fullw) { report_error(fc.P, fc.rec_index, SEQ_OLD_SHAPE, ETL_E_KEY_SHAPE); return; }
-      uint32_t k = 0, cmap = 0;
-      bool failed = false;
-      uint32_t used = walk_tuple(t, end, &nc, [&](int32_t i, uint32_t tag, const uint8_t* v, uint32_t len) {
-        if (failed) return;
-        uint32_t col;
-        if (dense) { while (cmap < n_cols && !(fc.flags[cmap] & 2)) cmap++; col = cmap++; }
-        else { col = (uint32_t)i; if (!(fc.flags[col] & 2)) return; }
-        CellOut c;
-        int r = convert_cell(fc, col, tag, v, len, nullptr, c, seq_old_cell((uint32_t)i), ETL_E_KEY_MISSING_VALUE);
-        if (r) { failed = true; return; }
-        sink.put(k++, c);
-      });
-      if (failed) return;
-      q = t + used;
-      n_old = n_ident;
-    } else {                                              // convert_tuple_to_row event.rs:550-583
-      if ((uint32_t)nc != n_cols) { report_error(fc.P, fc.rec_index, SEQ_OLD_SHAPE, ETL_E_FIELD_COUNT); return; }
-      bool failed = false;
-      uint32_t used = walk_tuple(t, end, &nc, [&](int32_t i, uint32_t tag, const uint8_t* v, uint32_t len) {
-        if (failed) return;
-        CellOut c;
-        int r = convert_cell(fc, (uint32_t)i, tag, v, len, nullptr, c, seq_old_cell((uint32_t)i), ETL_E_FULL_ROW_MISSING);
-        if (r) { failed = true; return; }
-        sink.put((uint32_t)i, c);
-      });
-      if (failed) return;
-      q = t + used;
-      n_old = n_cols;
+// advance the walker by at most `quota` text cells, writing descriptors to d[0..quota); returns count
+__device__ __noinline__ uint32_t walker_run(const DecodeParams& P, Walker& w, uint32_t slot, uint64_t tile_cell0,
+                                            CellDesc* d, uint32_t quota, unsigned long long* tbytes) {
+  uint32_t n = 0;
+  while (w.stage != W_DONE && n < quota) {
+    if (w.stage == W_OLD_HDR || w.stage == W_NEW_HDR) {
+      const bool is_new = w.stage == W_NEW_HDR;
+      if (is_new) {
+        if (w.p >= w.end || *w.p != 'N') { walker_malformed(P, w); break; }
+        w.p++;
+      }
+      if (w.p + 2 > w.end) { walker_malformed(P, w); break; }
+      int32_t nc = (int32_t)(int16_t)be16(w.p);
+      if (nc < 0) nc = 0;
+      w.p += 2;
+      w.remaining = nc; w.wire_i = 0; w.cmap = 0; w.k_out = 0;
+      if (!is_new) {
+        if (w.old_tag == 'K') {                     // normalize_key_tuple_to_row event.rs:879-919
+          w.n_old = w.n_ident;
+          w.dense = (uint32_t)nc == w.n_ident;
+          if (w.emit) {
+            if (w.n_ident == 0) walker_data_error(P, w, SEQ_OLD_SHAPE, ETL_E_KEY_NO_COLUMNS);
+            else if (!w.dense && (uint32_t)nc != w.n_cols) walker_data_error(P, w, SEQ_OLD_SHAPE, ETL_E_KEY_SHAPE);
+          }
+        } else {                                    // convert_tuple_to_row event.rs:550-583
+          w.n_old = w.n_cols;
+          if (w.emit && (uint32_t)nc != w.n_cols) walker_data_error(P, w, SEQ_OLD_SHAPE, ETL_E_FIELD_COUNT);
+        }
+        w.stage = W_OLD_CELLS;
+      } else {
+        if (w.emit && (uint32_t)nc != w.n_cols) walker_data_error(P, w, SEQ_NEW_SHAPE, ETL_E_FIELD_COUNT);
+        w.stage = W_NEW_CELLS;
+      }
+      continue;
+    }
+    // ---- cells of the current tuple
+    if (w.remaining == 0) {
+      w.stage = (w.stage == W_OLD_CELLS && w.kind != 'D') ? W_NEW_HDR : W_DONE;
+      continue;
+    }
+    if (w.p >= w.end) { walker_malformed(P, w); break; }
+    uint32_t tag, len;
+    cell_header(w.p, &tag, &len);
+    const uint32_t rel = (uint32_t)(w.p - w.base);
+    const bool has_body = tag == 't' || tag == 'b';
+    if (!has_body && tag != 'n' && tag != 'u') { walker_malformed(P, w); break; }
+    if (has_body) {
+      if (w.p + 5 > w.end || (int32_t)len < 0 || (uint64_t)len > (uint64_t)(w.end - w.p - 5)) { walker_malformed(P, w); break; }
+      *tbytes += len;
+      w.p += 5 + (uint64_t)len;
+    } else w.p += 1;
+    const uint32_t i = w.wire_i++;
+    w.remaining--;
+    if (!w.emit) continue;                          // structure-only after a data error
+    const bool is_new = w.stage == W_NEW_CELLS;
+    uint32_t col = i, dest;
+    if (!is_new && w.old_tag == 'K') {
+      if (w.dense) { while (w.cmap < w.n_cols && !(w.flags[w.cmap] & 2)) w.cmap++; col = w.cmap++; }
+      else if (!(w.flags[i] & 2)) continue;         // full-width key: non-identity entries are not decoded
+      dest = w.cell0 + w.k_out++;
+    } else dest = w.cell0 + (is_new ? w.n_old : 0u) + i;
+    const uint32_t seq = is_new ? seq_new_cell(i) : seq_old_cell(i);
+    const uint32_t cflags = w.flags[col];
+    const bool resolver_key = is_new && w.kind == 'U' && w.old_tag == 'K' && (cflags & 2);
+    if (tag == 'n') {                               // convert_tuple_data_to_cell event.rs:941-957
+      if (resolver_key) w.key_i++;
+      if (cflags & 1) put_cell(P, tile_cell0 + dest, ETL_CELL_NULL, 0, 0);
+      else walker_data_error(P, w, seq, ETL_E_NOT_NULL);
+      continue;
+    }
+    if (tag == 'u') {                               // event.rs:958-970 + OldRowResolver :722-762
+      if (is_new && w.kind == 'U') {
+        uint32_t src = 0xFFFFFFFFu;
+        if (w.old_tag == 'O') src = w.cell0 + i;
+        else if (resolver_key) src = w.cell0 + w.key_i++;
+        if (src != 0xFFFFFFFFu) { put_cell(P, tile_cell0 + dest, kCellUnresolved, tile_cell0 + src, 0); w.has_unresolved = true; }
+        else { put_cell(P, tile_cell0 + dest, ETL_CELL_MISSING, 0, 0); w.partial = true; }
+      } else walker_data_error(P, w, seq, (!is_new && w.old_tag == 'K') ? ETL_E_KEY_MISSING_VALUE : ETL_E_FULL_ROW_MISSING);
+      continue;
+    }
+    if (resolver_key) w.key_i++;
+    if (tag == 'b') { walker_data_error(P, w, seq, ETL_E_BINARY_FORMAT); continue; }
+    const uint32_t kind = w.kinds[col];
+    CellDesc& cd = d[n++];
+    cd.rel = rel;
+    cd.meta = (slot << 24) | (kind << 16) | ((is_new ? 1u : 0u) << 15) | (i & 0x7FFFu);
+    cd.dest_rel = dest;
+    cd.heap_off = 0;
+  }
+  return n;
+}
+
+// warp-cooperative UTF-8 validation of one long text cell: 16-byte aligned chunks per lane, an
+// all-ASCII chunk costs one load + one test; a chunk with high bits is checked with the
+// position-local rule over [lo, hi+3) so the following chunk never has to look back.
+__device__ __forceinline__ bool utf8_wide_warp_bad(const uint8_t* ptr, uint32_t len, int lane) {
+  bool bad = false;
+  const uintptr_t a0 = reinterpret_cast<uintptr_t>(ptr);
+  const uint32_t headn = min(len, (uint32_t)((16u - (uint32_t)(a0 & 15u)) & 15u));
+  if (lane == 0 && headn) bad |= !utf8_chunk_valid(ptr, len, 0, min(headn + 3u, len));
+  const uint32_t nchunks = (len - headn) / 16u;
+  const uint4* body = reinterpret_cast<const uint4*>(ptr + headn);
+  for (uint32_t c = lane; c < nchunks; c += 32) {
+    const uint4 x = body[c];
+    if ((x.x | x.y | x.z | x.w) & 0x80808080u) {
+      const uint32_t lo = headn + c * 16u;
+      bad |= !utf8_chunk_valid(ptr, len, lo, min(lo + 19u, len));
     }
   }
-  if (h.kind == 'D') return;
-  // ---- new tuple
-  q++;  // 'N'
-  int32_t nc = (int32_t)(int16_t)be16(q);
-  if (nc < 0) nc = 0;
-  if ((uint32_t)nc != n_cols) { report_error(fc.P, fc.rec_index, SEQ_NEW_SHAPE, ETL_E_FIELD_COUNT); return; }
-  bool failed = false, partial = false;
-  uint32_t key_i = 0;
-  const bool is_update = h.kind == 'U';
-  walk_tuple(q, end, &nc, [&](int32_t i, uint32_t tag, const uint8_t* v, uint32_t len) {
-    if (failed) return;
-    CellOut c, oldv;
-    const CellOut* oldp = nullptr;
-    if (is_update) {                                      // OldRowResolver event.rs:722-762
-      bool is_ident = fc.flags[i] & 2;
-      if (h.old_tag == 'O') { if (tag == 'u') { oldv = sink.get((uint32_t)i); oldp = &oldv; } }
-      else if (h.old_tag == 'K' && is_ident) { if (tag == 'u') { oldv = sink.get(key_i); oldp = &oldv; } key_i++; }
-    }
-    int r = convert_cell(fc, (uint32_t)i, tag, v, len, oldp, c, seq_new_cell((uint32_t)i), is_update ? 0u : (uint32_t)ETL_E_FULL_ROW_MISSING);
-    if (r == 2) { failed = true; return; }
-    if (r == 1) { partial = true; c.tag = ETL_CELL_MISSING; c.val = 0; c.aux = 0; }
-    sink.put(n_old + (uint32_t)i, c);
-  });
-  if (partial) fc.P.rec_flags[fc.rec_index - fc.P.record_index_base] |= ETL_RF_NEW_PARTIAL;
+  const uint32_t tail0 = headn + nchunks * 16u;
+  if (lane == 31 && tail0 < len) bad |= !utf8_chunk_valid(ptr, len, tail0, len);
+  return __any_sync(0xffffffffu, bad);
 }
 
-__global__ void __launch_bounds__(kEmitThreads, 2) k_emit(DecodeParams P) {
+__global__ void __launch_bounds__(kEmitThreads, 3) k_emit(DecodeParams P) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   EmitShared& sh = *reinterpret_cast<EmitShared*>(smem_raw);
   const uint32_t spt = P.segs_per_tile;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
     const uint32_t seg0 = tile * spt;
     const uint32_t seg1 = min(seg0 + spt, P.n_anchors);
@@ -599,23 +678,20 @@ __global__ void __launch_bounds__(kEmitThreads, 2) k_emit(DecodeParams P) {
     const uint64_t t_end = P.anchors[seg1];
     __syncthreads();  // previous tile fully consumed
     if (threadIdx.x == 0) {
-      // exclusive prefix of this tile: carry ⊕ group prefix ⊕ earlier tiles of the group
       uint32_t g = tile / P.tiles_per_group;
       Summ pre = fold(P.carry, P.group_prefix[g]);
       for (uint32_t t = g * P.tiles_per_group; t < tile; t++) pre = fold(pre, P.tile_summ[t]);
       sh.chunk_carry = pre;
-      sh.n_big = 0;
       sh.metrics[0] = sh.metrics[1] = sh.metrics[2] = sh.metrics[3] = 0;
       uint32_t b = 0;
       for (uint32_t s = seg0; s < seg1; s++) { sh.seg_base[s - seg0] = b; b += P.seg_frames[s]; }
       sh.seg_base[seg1 - seg0] = b;
     }
     if (t_end <= t_begin) { __syncthreads(); continue; }
-    // ---- stage the tile: coalesced 16-byte loads (window starts at the 16-byte boundary below t_begin)
+    // ---- 1. stage the tile
     const uint64_t win0 = t_begin & ~15ull;
     const uint32_t lead = (uint32_t)(t_begin - win0);
-    const uint64_t want = (t_end - win0 + 15ull) & ~15ull;
-    uint64_t wb = want;
+    uint64_t wb = (t_end - win0 + 15ull) & ~15ull;
     const uint64_t to_end = ((uint64_t)(P.len - win0) + 15ull) & ~15ull;
     if (to_end < wb) wb = to_end;
     if ((uint64_t)kTileCap < wb) wb = (uint64_t)kTileCap;
@@ -626,8 +702,10 @@ __global__ void __launch_bounds__(kEmitThreads, 2) k_emit(DecodeParams P) {
       for (uint32_t i = threadIdx.x; i < win_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
     }
     __syncthreads();
-    const uint32_t n_frames = sh.seg_base[seg1 - seg0];
-    // ---- frame list: one walker thread per segment, in shared memory
+    const Summ tile_pre = sh.chunk_carry;           // exclusive prefix of the tile
+    const uint64_t tile_cell0 = tile_pre.n_cells;
+    const uint32_t n_frames = min(sh.seg_base[seg1 - seg0], (uint32_t)kMaxTileFrames);
+    // ---- 2. frame list
     if (threadIdx.x < seg1 - seg0) {
       uint64_t pos = P.anchors[seg0 + threadIdx.x];
       const uint64_t stop = P.anchors[seg0 + threadIdx.x + 1];
@@ -640,16 +718,13 @@ __global__ void __launch_bounds__(kEmitThreads, 2) k_emit(DecodeParams P) {
           uint64_t avail = P.len - pos;
           if (p[0] != 'd' || avail < 5) flen = (uint32_t)(avail > 0 ? avail - 1 : 0);
           else { flen = be32(p + 1); if (flen < 4 || 1ull + flen > avail) flen = (uint32_t)(avail - 1); }
-        } else {
-          FrameHead hh = read_head(P.buf + pos, P.len - pos);
-          flen = hh.flen;
-        }
-        sh.foff[k++] = (uint32_t)(pos - t_begin);
+        } else flen = read_head(P.buf + pos, P.len - pos).flen;
+        sh.foff[k++] = (uint16_t)(pos - t_begin);
         pos += 1ull + flen;
       }
     }
     __syncthreads();
-    // ---- frames in chunks of blockDim: classify → ordered scan → emit
+    // ---- 3/4. chunks of 256 frames
     for (uint32_t c0 = 0; c0 < n_frames; c0 += blockDim.x) {
       const uint32_t f = c0 + threadIdx.x;
       const bool active = f < n_frames;
@@ -662,42 +737,46 @@ __global__ void __launch_bounds__(kEmitThreads, 2) k_emit(DecodeParams P) {
       if (active) {
         foff_abs = t_begin + sh.foff[f];
         const uint32_t rel = lead + sh.foff[f];
-        // head from global if it may straddle the window; body pointer decided after flen is known
         const uint8_t* gp = P.buf + foff_abs;
-        const bool head_in = rel + 40 <= win_bytes;
-        h = read_head(head_in ? sh.tile + rel : gp, P.len - foff_abs);
+        h = read_head((rel + 40 <= win_bytes) ? sh.tile + rel : gp, P.len - foff_abs);
         fp = (rel + 1ull + h.flen <= win_bytes) ? sh.tile + rel : gp;
         e = frame_state_elem(h, fp);
         if (!h.malformed) {
           if (h.kind == 'I' || h.kind == 'U' || h.kind == 'D') s = find_schema(P, h.rel, foff_abs);
           e.n_cells = frame_out_cells(h, s);
-          if (s && s->has_heap) e.heap = frame_heap_bytes(P, h, s, fp);
         }
       }
+      if (threadIdx.x == 0) { sh.n_desc = 0; sh.n_wide = 0; sh.wide_next = 0; }
       Summ chunk_total;
       Summ pre = block_exclusive_scan(e, sh.warp_summ, &chunk_total);
       const Summ carry = sh.chunk_carry;
       pre = fold(carry, pre);
       __syncthreads();
       if (threadIdx.x == 0) sh.chunk_carry = fold(carry, chunk_total);
+      Walker w;
+      w.stage = W_DONE; w.has_unresolved = false; w.partial = false;
+      unsigned long long tb = 0;
       if (active) {
-        const uint64_t ridx = pre.n_rec;             // index within this shard
+        const uint64_t ridx = pre.n_rec;
         const uint64_t gidx = P.record_index_base + ridx;
         const bool in_tx = (pre.flags & S_HAS_B) && !(pre.flags & S_CLOSED);
         uint64_t commit_lsn = 0, ordinal = 0, start_lsn = 0;
         uint32_t rflags = 0;
         int32_t rschema = -1;
         uint32_t rrel = h.rel;
-        const CellSink sink{P, pre.n_cells};
         bool ok = true;
-        unsigned long long tb = 0;
         bool wellformed = !h.malformed;
-        if (wellformed && (h.kind == 'I' || h.kind == 'U' || h.kind == 'D')) wellformed = dml_structure_ok(h, fp, &tb);
         if (wellformed && h.kind == 'O') wellformed = (h.flen >= 4 + 26 + 8) && cstr_end(fp + 39, fp + 1 + h.flen) != nullptr;
         if (wellformed && h.kind == 'Y') {
           const uint8_t* fe = fp + 1 + h.flen;
           const uint8_t* q1 = (h.flen >= 4 + 26 + 4) ? cstr_end(fp + 35, fe) : nullptr;
           wellformed = q1 != nullptr && cstr_end(q1, fe) != nullptr;
+        }
+        if (wellformed && (h.kind == 'I' || h.kind == 'U' || h.kind == 'D')) {
+          const uint32_t tt = (h.flen >= 4 + 26 + 5) ? fp[35] : 0u;  // tuple marker
+          if (h.kind == 'I') wellformed = tt == 'N';
+          else if (h.kind == 'U') wellformed = tt == 'N' || tt == 'O' || tt == 'K';
+          else wellformed = tt == 'O' || tt == 'K';
         }
         if (!wellformed) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; }
         else if (h.kind == 'k') { start_lsn = be64(fp + 6); rrel = fp[22]; }
@@ -707,30 +786,35 @@ __global__ void __launch_bounds__(kEmitThreads, 2) k_emit(DecodeParams P) {
           switch (h.kind) {
             case 'B':                                 // apply.rs:1927-1943
               commit_lsn = be64(m); ordinal = 0; rflags = ETL_RF_EVENT;
-              sink.put(0, ETL_CELL_I64, be64(m + 8), 0);
-              sink.put(1, ETL_CELL_U32, be32(m + 16), 0);
+              put_cell(P, pre.n_cells, ETL_CELL_I64, be64(m + 8), 0);
+              put_cell(P, pre.n_cells + 1, ETL_CELL_U32, be32(m + 16), 0);
               break;
             case 'C': {                               // apply.rs:1946-2006
               if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; break; }
               uint64_t cl = be64(m + 1);
               if (cl != pre.lsn) { report_error(P, gidx, SEQ_STATE, ETL_E_COMMIT_LSN); ok = false; break; }
               commit_lsn = cl; ordinal = pre.ord; rflags = ETL_RF_EVENT;
-              sink.put(0, ETL_CELL_I32, (uint64_t)(int64_t)(int8_t)m[0], 0);
-              sink.put(1, ETL_CELL_I64, be64(m + 9), 0);
-              sink.put(2, ETL_CELL_I64, be64(m + 17), 0);
+              put_cell(P, pre.n_cells, ETL_CELL_I32, (uint64_t)(int64_t)(int8_t)m[0], 0);
+              put_cell(P, pre.n_cells + 1, ETL_CELL_I64, be64(m + 9), 0);
+              put_cell(P, pre.n_cells + 2, ETL_CELL_I64, be64(m + 17), 0);
               break;
             }
             case 'R':                                 // apply.rs:2012-2089 (masks are built on the host)
-              for (uint32_t k = 0; k < P.n_rel_errors; k++)     // Relation frames the host could not turn into masks
+              for (uint32_t k = 0; k < P.n_rel_errors; k++)
                 if (P.rel_error_off[k] == foff_abs) { report_error(P, gidx, P.rel_error_seq[k], P.rel_error_code[k]); ok = false; }
               if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; break; }
               commit_lsn = pre.lsn; ordinal = pre.ord; rflags = ETL_RF_EVENT;
               { const DevSchema* rs = find_schema(P, h.rel, foff_abs); if (rs && rs->effective_off == foff_abs) rschema = (int32_t)rs->batch_index; }
               break;
             case 'I': case 'U': case 'D': {           // apply.rs:2092-2203
-              if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; break; }
+              // the tuple structure is validated by the walker (a malformed frame outranks state errors)
+              if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); }
               commit_lsn = pre.lsn; ordinal = pre.ord;
-              if (!s) { report_error(P, gidx, SEQ_TABLE, ETL_E_MISSING_TABLE_STATE); ok = false; break; }
+              if (!s) {                             // no schema to walk with: structure check only
+                unsigned long long ignored;
+                if (!dml_structure_ok(h, fp, &ignored)) report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME);
+                report_error(P, gidx, SEQ_TABLE, ETL_E_MISSING_TABLE_STATE); ok = false; break;
+              }
               rschema = (int32_t)s->batch_index; rflags = ETL_RF_EVENT;
               if (h.old_tag == 'O') rflags |= ETL_RF_OLD_FULL; else if (h.old_tag == 'K') rflags |= ETL_RF_OLD_KEY;
               break;
@@ -738,18 +822,17 @@ __global__ void __launch_bounds__(kEmitThreads, 2) k_emit(DecodeParams P) {
             case 'T': {                               // apply.rs:2206-2248
               if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; break; }
               commit_lsn = pre.lsn; ordinal = pre.ord;
-              sink.put(0, ETL_CELL_I32, (uint64_t)(int64_t)(int8_t)m[4], 0);
+              put_cell(P, pre.n_cells, ETL_CELL_I32, (uint64_t)(int64_t)(int8_t)m[4], 0);
               for (uint32_t i = 0; i < h.rel; i++) {
                 uint32_t rid = be32(m + 5 + 4 * i);
                 const DevSchema* ts = find_schema(P, rid, foff_abs);
                 if (!ts) { report_error(P, gidx, SEQ_TABLE, ETL_E_MISSING_TABLE_STATE); ok = false; break; }
-                sink.put(1 + i, ETL_CELL_U32, rid, ts->batch_index);
+                put_cell(P, pre.n_cells + 1 + i, ETL_CELL_U32, rid, ts->batch_index);
               }
               if (h.rel > 0) rflags = ETL_RF_EVENT;
               break;
             }
             case 'M': {                               // apply.rs:1808-1924
-              // flags i8, lsn u64, prefix cstr, len i32, content — structure checked here
               const uint8_t* end = fp + 1 + h.flen;
               const uint8_t* q = m + 9;
               const char* ddl = "supabase_etl_ddl";
@@ -772,28 +855,124 @@ __global__ void __launch_bounds__(kEmitThreads, 2) k_emit(DecodeParams P) {
         P.rec_rel[ridx] = rrel; P.rec_schema[ridx] = rschema; P.rec_start_lsn[ridx] = start_lsn;
         P.rec_commit_lsn[ridx] = commit_lsn; P.rec_tx_ordinal[ridx] = ordinal; P.rec_cell_base[ridx] = pre.n_cells;
         if (ok && (rflags & ETL_RF_EVENT)) atomicAdd(&sh.metrics[3], 1ull);
+        sh.fi_base[threadIdx.x] = fp; sh.fi_off[threadIdx.x] = foff_abs; sh.fi_rec[threadIdx.x] = (uint32_t)ridx;
         if (ok && s && (h.kind == 'I' || h.kind == 'U' || h.kind == 'D')) {
-          FrameCtx fc{P, sh, gidx, foff_abs, fp, P.col_kind + s->col_base, P.col_flags + s->col_base, HeapCursor{P.heap, pre.heap}};
-          emit_dml(fc, h, s, sink);
-          atomicAdd(&sh.metrics[h.kind == 'I' ? 0 : (h.kind == 'U' ? 1 : 2)], tb);
+          w.base = fp; w.end = fp + 1 + h.flen; w.p = fp + 36;
+          w.kinds = P.col_kind + s->col_base; w.flags = P.col_flags + s->col_base;
+          w.rec_index = gidx; w.rec_local = (uint32_t)ridx; w.n_cols = s->n_cols; w.n_ident = s->n_ident;
+          w.cell0 = (uint32_t)(pre.n_cells - tile_cell0); w.emit = true;
+          w.remaining = 0; w.wire_i = 0; w.cmap = 0; w.k_out = 0; w.key_i = 0; w.n_old = 0;
+          w.kind = (uint8_t)h.kind; w.old_tag = (uint8_t)h.old_tag;
+          w.dense = false; w.partial = false; w.has_unresolved = false;
+          if (h.kind != 'I' && h.old_tag) { w.stage = W_OLD_HDR; w.p = fp + 36; }  // old image first
+          else { w.stage = W_NEW_HDR; w.p = fp + 35; }                             // 'N' marker, then the new tuple
         }
+      }
+      // ---- walker rounds
+      const uint32_t n_walkers = __syncthreads_count(w.stage != W_DONE);
+      if (n_walkers) {
+        uint32_t quota = (uint32_t)kDescCap / n_walkers;
+        if (quota > 255) quota = 255;
+        for (;;) {
+          if (w.stage != W_DONE) {
+            const uint32_t slot0 = atomicAdd(&sh.n_desc, quota);
+            const uint32_t got = walker_run(P, w, threadIdx.x, tile_cell0, sh.desc + slot0, quota, &tb);
+            for (uint32_t k = got; k < quota; k++) sh.desc[slot0 + k].meta = 0xFFFFFFFFu;
+          }
+          __syncthreads();
+          const uint32_t nd = sh.n_desc;
+          // ---- heap reservation for this round: Σ bounds of the batch's heap-kind cells, one global
+          //      atomicAdd per round (placement inside the heap is unspecified; cells carry offsets)
+          if (P.heap_cap) {
+            uint32_t mine = 0;
+            for (uint32_t di = threadIdx.x; di < nd; di += blockDim.x) {
+              const CellDesc cd = sh.desc[di];
+              if (cd.meta == 0xFFFFFFFFu) continue;
+              const uint32_t kind = (cd.meta >> 16) & 0xFFu;
+              if (kind != ETL_K_NUMERIC && kind != ETL_K_BYTES && kind != ETL_K_UUID) continue;
+              uint32_t tag, len;
+              cell_header(sh.fi_base[cd.meta >> 24] + cd.rel, &tag, &len);
+              sh.desc[di].heap_off = mine;          // thread-local running offset, rebased below
+              mine += cell_heap_bound(kind, len);
+            }
+            uint32_t inc = mine;
+#pragma unroll
+            for (int d2 = 1; d2 < 32; d2 <<= 1) { uint32_t up = __shfl_up_sync(0xffffffffu, inc, d2); if (lane >= d2) inc += up; }
+            if (lane == 31) sh.scan_u32[wid] = inc;
+            __syncthreads();
+            uint32_t wpre = 0, total = 0;
+            for (int k = 0; k < (int)(blockDim.x >> 5); k++) { if (k < wid) wpre += sh.scan_u32[k]; total += sh.scan_u32[k]; }
+            if (threadIdx.x == 0) sh.round_heap_base = total ? atomicAdd(P.heap_top, (unsigned long long)total) : 0ull;
+            const uint32_t my_base = wpre + inc - mine;
+            for (uint32_t di = threadIdx.x; di < nd; di += blockDim.x) {
+              const uint32_t kind = (sh.desc[di].meta >> 16) & 0xFFu;
+              if (sh.desc[di].meta != 0xFFFFFFFFu && (kind == ETL_K_NUMERIC || kind == ETL_K_BYTES || kind == ETL_K_UUID)) sh.desc[di].heap_off += my_base;
+            }
+            __syncthreads();
+          }
+          const unsigned long long round_heap = sh.round_heap_base;
+          // ---- thread-per-cell parsing of the batch
+          for (uint32_t di = threadIdx.x; di < nd; di += blockDim.x) {
+            const CellDesc cd = sh.desc[di];
+            if (cd.meta == 0xFFFFFFFFu) continue;
+            const uint32_t slot = cd.meta >> 24, kind = (cd.meta >> 16) & 0xFFu, wi = cd.meta & 0x7FFFu;
+            const uint32_t seq = ((cd.meta >> 15) & 1u) ? seq_new_cell(wi) : seq_old_cell(wi);
+            const uint8_t* cp = sh.fi_base[slot] + cd.rel;
+            uint32_t tag, len;
+            cell_header(cp, &tag, &len);
+            const uint8_t* v = cp + 5;
+            const uint64_t soff = sh.fi_off[slot] + cd.rel + 5;
+            CellOut o;
+            uint32_t code = 0;
+            if (kind == ETL_K_STRING && len >= (uint32_t)kWideLen) {
+              const uint32_t ws = atomicAdd(&sh.n_wide, 1u);
+              if (ws < (uint32_t)kWideCap) sh.wide[ws] = WideText{v, len, seq, sh.fi_rec[slot]};
+              else if (!utf8_valid(v, len)) code = ETL_E_UTF8;
+              o.tag = ETL_CELL_STRING; o.val = soff; o.aux = len;
+            } else if (!utf8_valid_fast(v, len)) code = ETL_E_UTF8;         // event.rs:972
+            else {
+              HeapCursor hc{P.heap, round_heap + cd.heap_off};
+              if (hc.pos + cell_heap_bound(kind, len) > P.heap_cap && cell_heap_bound(kind, len)) code = ETL_E_MALFORMED_FRAME;  // cannot happen: cap is an upper bound
+              else code = parse_text_cell(kind, v, len, soff, hc, o);
+            }
+            if (code) report_error(P, P.record_index_base + sh.fi_rec[slot], seq, code);
+            else put_cell(P, tile_cell0 + cd.dest_rel, o.tag, o.val, o.aux);
+          }
+          __syncthreads();
+          // ---- long text: one warp per cell
+          const uint32_t nw = min(sh.n_wide, (uint32_t)kWideCap);
+          for (;;) {
+            uint32_t wi = 0;
+            if (lane == 0) wi = atomicAdd(&sh.wide_next, 1u);
+            wi = __shfl_sync(0xffffffffu, wi, 0);
+            if (wi >= nw) break;
+            const WideText wt = sh.wide[wi];
+            if (utf8_wide_warp_bad(wt.ptr, wt.len, lane) && lane == 0)
+              report_error(P, P.record_index_base + wt.rec_local, wt.seq, ETL_E_UTF8);
+          }
+          __syncthreads();
+          if (threadIdx.x == 0) { sh.n_desc = 0; sh.n_wide = 0; sh.wide_next = 0; }
+          if (!__syncthreads_or(w.stage != W_DONE)) break;
+        }
+      }
+      // ---- per-frame epilogue: unchanged-TOAST values copied from the old image; Partial flag; metrics
+      if (active && (h.kind == 'I' || h.kind == 'U' || h.kind == 'D') && s) {
+        if (w.has_unresolved) {
+          const uint64_t c0n = tile_cell0 + w.cell0 + w.n_old;
+          for (uint32_t i = 0; i < w.n_cols; i++)
+            if (P.cell_tag[c0n + i] == kCellUnresolved) {
+              const uint64_t src = P.cell_val[c0n + i];
+              put_cell(P, c0n + i, P.cell_tag[src], P.cell_val[src], P.cell_aux[src]);
+            }
+        }
+        if (w.partial) P.rec_flags[w.rec_local] |= ETL_RF_NEW_PARTIAL;
+        atomicAdd(&sh.metrics[h.kind == 'I' ? 0 : (h.kind == 'U' ? 1 : 2)], tb);
       }
       __syncthreads();
     }
-    // ---- large text cells: block-cooperative UTF-8 validation, 16-byte chunks per thread
-    __syncthreads();
-    const uint32_t nb = min(sh.n_big, (uint32_t)kBigQueue);
-    for (uint32_t b = 0; b < nb; b++) {
-      const BigCell bc = sh.big[b];
-      bool bad = false;
-      for (uint32_t lo = threadIdx.x * 32u; lo < bc.len; lo += blockDim.x * 32u) {
-        uint32_t hi = min(lo + 32u, bc.len);
-        bad |= !utf8_chunk_valid(bc.ptr, bc.len, lo, hi);
-      }
-      if (__syncthreads_or(bad) && threadIdx.x == 0) report_error(P, bc.rec_index, bc.seq, ETL_E_UTF8);
-    }
     if (threadIdx.x < 4 && sh.metrics[threadIdx.x]) atomicAdd(&P.metrics[threadIdx.x], sh.metrics[threadIdx.x]);
   }
+  (void)wid;
 }
 
 }  // namespace etl
