@@ -184,7 +184,7 @@ struct etl_dec_ctx {
   DevBuf<uint8_t> d_stream;
   DevBuf<uint64_t> d_anchors;
   DevBuf<uint32_t> d_seg_frames;
-  DevBuf<Summ> d_tile_summ, d_group_summ, d_group_prefix, d_total;
+  DevBuf<Summ> d_tile_summ, d_group_summ, d_group_prefix, d_total, d_tile_prefix;
   DevBuf<DevSchema> d_schemas;
   DevBuf<uint8_t> d_col_kind, d_col_flags;
   DevBuf<unsigned long long> d_scalars;  // [0] first_error key, [1..4] metrics
@@ -321,7 +321,7 @@ void etl_dec_destroy(etl_dec_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ctx->d_stream.release(); ctx->d_anchors.release(); ctx->d_seg_frames.release(); ctx->d_tile_summ.release();
-  ctx->d_group_summ.release(); ctx->d_group_prefix.release(); ctx->d_total.release(); ctx->d_schemas.release();
+  ctx->d_group_summ.release(); ctx->d_group_prefix.release(); ctx->d_tile_prefix.release(); ctx->d_total.release(); ctx->d_schemas.release();
   ctx->d_col_kind.release(); ctx->d_col_flags.release(); ctx->d_scalars.release(); ctx->d_rel_err_off.release();
   ctx->d_rel_err_code.release(); ctx->d_rel_err_seq.release();
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
@@ -527,7 +527,8 @@ int etl_dec_decode_begin(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t fla
   P.n_rel_errors = (uint32_t)rel_err_off.size();
   CK(ctx->d_seg_frames.ensure(P.n_anchors + 1)); CK(ctx->d_tile_summ.ensure(P.n_tiles + 1));
   CK(ctx->d_group_summ.ensure(P.n_groups + 1)); CK(ctx->d_group_prefix.ensure(P.n_groups + 1)); CK(ctx->d_total.ensure(1));
-  CK(ctx->d_scalars.ensure(8));
+  CK(ctx->d_scalars.ensure(8)); CK(ctx->d_tile_prefix.ensure(P.n_tiles + 1));
+  P.tile_prefix = ctx->d_tile_prefix.p; P.tile_counter = (unsigned int*)(ctx->d_scalars.p + 6);
   P.seg_frames = ctx->d_seg_frames.p; P.tile_summ = ctx->d_tile_summ.p; P.group_summ = ctx->d_group_summ.p;
   P.group_prefix = ctx->d_group_prefix.p; P.total = ctx->d_total.p;
   P.first_error = ctx->d_scalars.p; P.metrics = ctx->d_scalars.p + 1;
@@ -537,7 +538,8 @@ int etl_dec_decode_begin(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t fla
   if (P.n_groups) {
     k_index<<<P.n_groups, P.tiles_per_group * P.segs_per_tile, 0, st>>>(P);
     k_scan<<<1, 512, 0, st>>>(P);
-    ctx->launches += 2;
+    k_tile_prefix<<<(P.n_tiles + 255) / 256, 256, 0, st>>>(P);
+    ctx->launches += 3;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->h_total, P.total, sizeof(Summ), cudaMemcpyDeviceToHost, st));
   } else *ctx->h_total = summ_identity();
@@ -609,13 +611,13 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
   P.carry = carry;
 
   // ---- pass C
-  ctx->h_scalars[0] = ~0ull; ctx->h_scalars[1] = ctx->h_scalars[2] = ctx->h_scalars[3] = ctx->h_scalars[4] = ctx->h_scalars[5] = 0;
-  CK(cudaMemcpyAsync(ctx->d_scalars.p, ctx->h_scalars, 6 * 8, cudaMemcpyHostToDevice, st));
+  ctx->h_scalars[0] = ~0ull; ctx->h_scalars[1] = ctx->h_scalars[2] = ctx->h_scalars[3] = ctx->h_scalars[4] = ctx->h_scalars[5] = ctx->h_scalars[6] = 0;
+  CK(cudaMemcpyAsync(ctx->d_scalars.p, ctx->h_scalars, 7 * 8, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(ctx->ev[3], st));
   if (P.n_tiles) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    uint32_t grid = std::min<uint32_t>(P.n_tiles, (uint32_t)sms * 8);
+    uint32_t grid = std::min<uint32_t>(P.n_tiles, (uint32_t)sms * 3);
     k_emit<<<grid, kEmitThreads, sizeof(EmitShared), st>>>(P);
     ctx->launches += 1;
     CK(cudaGetLastError());

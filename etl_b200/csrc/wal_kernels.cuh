@@ -84,6 +84,8 @@ struct DecodeParams {
   Summ* group_summ;          // per group of tiles
   Summ* group_prefix;        // exclusive prefix per group (pass B)
   Summ* total;               // [0] = fold of everything (shard seam summary)
+  Summ* tile_prefix;         // exclusive prefix per tile (pass B2), carry not included
+  unsigned int* tile_counter;  // dynamic tile scheduler of the emit pass
   // carry-in (known when pass C runs)
   Summ carry;
   uint64_t record_index_base;  // global index of this shard's first record (multi-GPU)
@@ -341,6 +343,16 @@ __global__ void __launch_bounds__(kIndexThreads) k_index(DecodeParams P) {
   }
 }
 
+// pass B2: per-tile exclusive prefix = group prefix ⊕ earlier tiles of the group (thread per tile)
+__global__ void __launch_bounds__(256) k_tile_prefix(DecodeParams P) {
+  const uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tile >= P.n_tiles) return;
+  const uint32_t g = tile / P.tiles_per_group;
+  Summ pre = P.group_prefix[g];
+  for (uint32_t t = g * P.tiles_per_group; t < tile; t++) pre = fold(pre, P.tile_summ[t]);
+  P.tile_prefix[tile] = pre;
+}
+
 // ================================================================================================
 // pass B: exclusive scan of group summaries (single CTA; n_groups is len / (tiles_per_group*32 KiB))
 __global__ void __launch_bounds__(512) k_scan(DecodeParams P) {
@@ -369,20 +381,21 @@ __global__ void __launch_bounds__(512) k_scan(DecodeParams P) {
 }
 
 // ================================================================================================
-// pass C: emit.  Per 32 KiB tile:
+// pass C: emit.  Persistent CTAs pull 32 KiB tiles from a global counter.  Per tile:
 //   1. stage the tile in shared memory (coalesced 16-byte loads)
-//   2. frame list (one walker thread per anchor segment)
-//   3. per 256-frame chunk: classify heads → ordered block scan (record index, cell base, heap base,
-//      stream state) → record plane; Begin/Commit/Truncate cells
-//   4. DML frames: thread-per-frame WALKERS follow the TupleData chain and emit one 16-byte
-//      descriptor per text cell into a shared batch (NULL / unchanged-TOAST cells are resolved by
-//      the walker itself); then thread-per-CELL parsing of the batch (all lanes busy even for
-//      100-column rows); long text goes to a queue that warps validate with 16-byte loads.
+//   2. frame list (one walker thread per anchor segment, in shared memory)
+//   3. per 256-frame chunk: classify heads → four u32 warp-shuffle scans (cells, ordinal consumers,
+//      last Begin, last Commit) give every frame its cell base and stream state → record plane
+//   4. DML frames: register-resident thread-per-frame WALKERS follow the TupleData chain and emit a
+//      16-byte descriptor per text cell into a shared batch (NULL / unchanged-TOAST cells are
+//      resolved by the walker); the batch is counting-sorted by decode class so warps run one
+//      parser at a time; thread-per-CELL parsing; long text is validated by a warp (≥ 96 B) or by
+//      the whole CTA (≥ 2 KiB) with 16-byte loads.
 struct CellDesc {
-  uint32_t rel;       // offset of the cell's tag byte inside its frame
-  uint32_t meta;      // frame slot (8) | kind (8) | is_new (1) | wire index (15); 0xFFFFFFFF = empty
+  uint32_t toff;      // offset of the value bytes relative to the tile start
+  uint32_t len;       // value length
   uint32_t dest_rel;  // output cell index relative to the tile's first cell
-  uint32_t heap_off;  // filled by the parse phase: offset inside this round's heap reservation
+  uint32_t meta;      // frame slot (8) | kind (8) | is_new (1) | wire index (15); 0xFFFFFFFF = empty
 };
 struct WideText {
   const uint8_t* ptr;
@@ -392,58 +405,36 @@ struct WideText {
 };
 
 constexpr int kDescCap = 1024;
+constexpr int kDescPerThread = kDescCap / kEmitThreads;
 constexpr int kWideCap = 128;
-constexpr int kWideLen = 96;   // text cells at least this long are validated warp-cooperatively
+constexpr int kBigCap = 16;
+constexpr int kWideLen = 96;     // text cells at least this long are validated by a warp
+constexpr int kBigLen = 2048;    // ... and these by the whole CTA
 constexpr uint32_t kCellUnresolved = 253;  // internal: unchanged-TOAST cell awaiting its old value
 
 struct EmitShared {
   alignas(16) uint8_t tile[kTileCap + 32];
-  uint16_t foff[kMaxTileFrames];   // frame starts relative to the tile start (< 32 KiB)
+  uint16_t foff[kMaxTileFrames];            // frame starts relative to the tile start (< 32 KiB)
   CellDesc desc[kDescCap];
-  const uint8_t* fi_base[kEmitThreads];   // per chunk slot: frame bytes (window or global)
-  uint64_t fi_off[kEmitThreads];          // absolute stream offset of the frame
-  uint32_t fi_rec[kEmitThreads];          // shard-local record index
+  uint16_t perm[kDescCap];                  // descriptor order after the counting sort by kind
+  const uint8_t* fi_base[kEmitThreads];     // per chunk slot: frame bytes (window or global)
+  uint64_t fi_off[kEmitThreads];            // absolute stream offset of the frame
+  uint64_t b_lsn[kEmitThreads];             // Begin frames of the chunk: final_lsn
+  uint32_t b_cons[kEmitThreads];            // ... and inclusive ordinal-consumer count
+  uint32_t fi_rec[kEmitThreads];            // shard-local record index
   WideText wide[kWideCap];
+  WideText big[kBigCap];
   uint32_t seg_base[132];
-  Summ warp_summ[kEmitThreads / 32];
-  Summ chunk_carry;
-  uint32_t n_desc, n_wide, wide_next;
-  uint32_t scan_u32[kEmitThreads / 32];
+  uint32_t ws_cells[kEmitThreads / 32], ws_cons[kEmitThreads / 32];
+  int32_t ws_b[kEmitThreads / 32], ws_c[kEmitThreads / 32];
+  uint32_t hist[32], kstart[32];
+  uint32_t carry_cells, carry_cons, carry_b_cons;
+  int32_t carry_b, carry_c;
+  uint64_t carry_b_lsn;
+  uint32_t n_desc, n_wide, wide_next, n_big, n_sorted, round_heap_need, round_heap_used, tile_idx;
   unsigned long long round_heap_base;
   unsigned long long metrics[4];
 };
-
-__device__ __forceinline__ Summ shfl_up_summ(const Summ& v, int d) {
-  Summ r;
-  r.lsn = __shfl_up_sync(0xffffffffu, v.lsn, d);
-  r.ord = __shfl_up_sync(0xffffffffu, v.ord, d);
-  r.n_cells = __shfl_up_sync(0xffffffffu, v.n_cells, d);
-  r.heap = __shfl_up_sync(0xffffffffu, v.heap, d);
-  r.n_rec = __shfl_up_sync(0xffffffffu, v.n_rec, d);
-  r.flags = __shfl_up_sync(0xffffffffu, v.flags, d);
-  return r;
-}
-// ordered exclusive scan of one Summ per thread; *total = fold of the whole block
-__device__ __forceinline__ Summ block_exclusive_scan(const Summ& mine, Summ* warp_summ, Summ* total) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  Summ inc = mine;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    Summ up = shfl_up_summ(inc, d);
-    if (lane >= d) inc = fold(up, inc);
-  }
-  if (lane == 31) warp_summ[wid] = inc;
-  __syncthreads();
-  Summ wpre = summ_identity();
-  for (int w = 0; w < wid; w++) wpre = fold(wpre, warp_summ[w]);
-  Summ tot = summ_identity();
-  for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot = fold(tot, warp_summ[w]);
-  *total = tot;
-  Summ excl = shfl_up_summ(inc, 1);
-  if (lane == 0) excl = summ_identity();
-  __syncthreads();
-  return fold(wpre, excl);
-}
 
 // unaligned little-endian 8-byte load built from aligned 32-bit words (works on the shared window
 // and on global memory; may touch up to 3 bytes before and 11 after p — buffers are padded)
@@ -454,12 +445,8 @@ __device__ __forceinline__ uint64_t ld64u(const uint8_t* p) {
   const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
   return ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
 }
-// cell header at p: tag byte + big-endian length
-__device__ __forceinline__ void cell_header(const uint8_t* p, uint32_t* tag, uint32_t* len) {
-  const uint64_t x = ld64u(p);
-  *tag = (uint32_t)(x & 0xFFu);
-  *len = __byte_perm((uint32_t)(x >> 8), 0, 0x0123);
-}
+__device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+__device__ __forceinline__ uint64_t bswap64(uint64_t v) { return ((uint64_t)bswap32((uint32_t)v) << 32) | bswap32((uint32_t)(v >> 32)); }
 
 // UTF-8 check of a short/medium cell with word loads: all-ASCII words pass immediately
 __device__ __forceinline__ bool utf8_valid_fast(const uint8_t* s, uint32_t n) {
@@ -468,16 +455,15 @@ __device__ __forceinline__ bool utf8_valid_fast(const uint8_t* s, uint32_t n) {
   for (; i + 8 <= n; i += 8) { uint64_t x = ld64u(s + i); hi |= (uint32_t)(x >> 32) | (uint32_t)x; }
   if (i < n) {
     uint64_t x = ld64u(s + i);
-    uint32_t r = n - i;  // 1..7 valid bytes
-    x &= (r >= 8) ? ~0ull : ((1ull << (8 * r)) - 1ull);
+    x &= (1ull << (8 * (n - i))) - 1ull;  // 1..7 valid bytes
     hi |= (uint32_t)(x >> 32) | (uint32_t)x;
   }
   if (!(hi & 0x80808080u)) return true;
   return utf8_valid(s, n);
 }
 
-// text.rs:28-173 dispatch for one text cell whose bytes are known to be valid UTF-8 unless
-// `check_utf8`. `soff` = absolute stream offset of the value bytes.
+// text.rs:28-173 dispatch for one text cell (bytes already UTF-8 validated). `soff` = absolute
+// stream offset of the value bytes.
 __device__ __forceinline__ uint32_t parse_text_cell(uint32_t kind, const uint8_t* s, uint32_t n, uint64_t soff,
                                                     HeapCursor& hc, CellOut& o) {
   o.aux = 0;
@@ -522,7 +508,7 @@ __device__ __forceinline__ uint32_t parse_text_cell(uint32_t kind, const uint8_t
 }
 
 // ---- walker: one thread follows the TupleData chain(s) of one DML frame (event.rs:376-919)
-enum : uint8_t { W_OLD_HDR = 0, W_OLD_CELLS = 1, W_NEW_HDR = 2, W_NEW_CELLS = 3, W_DONE = 4 };
+enum : uint32_t { W_OLD_HDR = 0, W_OLD_CELLS = 1, W_NEW_HDR = 2, W_NEW_CELLS = 3, W_DONE = 4 };
 struct Walker {
   const uint8_t* base;   // frame start
   const uint8_t* p;      // next byte to read
@@ -530,40 +516,34 @@ struct Walker {
   const uint8_t* kinds;
   const uint8_t* flags;
   uint64_t rec_index;    // global record index (error keys)
-  uint32_t rec_local;
+  uint32_t toff0;        // offset of the frame start relative to the tile start
   uint32_t n_cols, n_ident;
   uint32_t cell0;        // first output cell of the frame, relative to the tile's cell base
   int32_t remaining;     // wire cells left in the current tuple
   uint32_t wire_i, cmap, k_out, key_i, n_old;
-  uint8_t kind, old_tag, stage;
+  uint32_t kind, old_tag, stage;
   bool dense, partial, has_unresolved;
   bool emit;             // false after the first data error: keep checking structure only, because a
                          // malformed frame (parser error) outranks every conversion error of the record
 };
-__device__ __forceinline__ void walker_data_error(const DecodeParams& P, Walker& w, uint32_t seq, uint32_t code) {
-  report_error(P, w.rec_index, seq, code);
-  w.emit = false;
-}
-__device__ __forceinline__ void walker_malformed(const DecodeParams& P, Walker& w) {
-  report_error(P, w.rec_index, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME);
-  w.stage = W_DONE;
-}
 __device__ __forceinline__ void put_cell(const DecodeParams& P, uint64_t idx, uint32_t tag, uint64_t val, uint32_t aux) {
   P.cell_tag[idx] = (uint8_t)tag; P.cell_val[idx] = val; P.cell_aux[idx] = aux;
 }
+#define W_DATA_ERROR(seq_, code_) do { report_error(P, w.rec_index, (seq_), (code_)); w.emit = false; } while (0)
+#define W_MALFORMED() do { report_error(P, w.rec_index, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); w.stage = W_DONE; } while (0)
 
 // advance the walker by at most `quota` text cells, writing descriptors to d[0..quota); returns count
-__device__ __noinline__ uint32_t walker_run(const DecodeParams& P, Walker& w, uint32_t slot, uint64_t tile_cell0,
-                                            CellDesc* d, uint32_t quota, unsigned long long* tbytes) {
+__device__ __forceinline__ uint32_t walker_run(const DecodeParams& P, Walker& w, uint32_t slot, uint64_t tile_cell0,
+                                               CellDesc* d, uint32_t quota, unsigned long long& tbytes) {
   uint32_t n = 0;
   while (w.stage != W_DONE && n < quota) {
     if (w.stage == W_OLD_HDR || w.stage == W_NEW_HDR) {
       const bool is_new = w.stage == W_NEW_HDR;
       if (is_new) {
-        if (w.p >= w.end || *w.p != 'N') { walker_malformed(P, w); break; }
+        if (w.p >= w.end || *w.p != 'N') { W_MALFORMED(); break; }
         w.p++;
       }
-      if (w.p + 2 > w.end) { walker_malformed(P, w); break; }
+      if (w.p + 2 > w.end) { W_MALFORMED(); break; }
       int32_t nc = (int32_t)(int16_t)be16(w.p);
       if (nc < 0) nc = 0;
       w.p += 2;
@@ -573,34 +553,34 @@ __device__ __noinline__ uint32_t walker_run(const DecodeParams& P, Walker& w, ui
           w.n_old = w.n_ident;
           w.dense = (uint32_t)nc == w.n_ident;
           if (w.emit) {
-            if (w.n_ident == 0) walker_data_error(P, w, SEQ_OLD_SHAPE, ETL_E_KEY_NO_COLUMNS);
-            else if (!w.dense && (uint32_t)nc != w.n_cols) walker_data_error(P, w, SEQ_OLD_SHAPE, ETL_E_KEY_SHAPE);
+            if (w.n_ident == 0) W_DATA_ERROR(SEQ_OLD_SHAPE, ETL_E_KEY_NO_COLUMNS);
+            else if (!w.dense && (uint32_t)nc != w.n_cols) W_DATA_ERROR(SEQ_OLD_SHAPE, ETL_E_KEY_SHAPE);
           }
         } else {                                    // convert_tuple_to_row event.rs:550-583
           w.n_old = w.n_cols;
-          if (w.emit && (uint32_t)nc != w.n_cols) walker_data_error(P, w, SEQ_OLD_SHAPE, ETL_E_FIELD_COUNT);
+          if (w.emit && (uint32_t)nc != w.n_cols) W_DATA_ERROR(SEQ_OLD_SHAPE, ETL_E_FIELD_COUNT);
         }
         w.stage = W_OLD_CELLS;
       } else {
-        if (w.emit && (uint32_t)nc != w.n_cols) walker_data_error(P, w, SEQ_NEW_SHAPE, ETL_E_FIELD_COUNT);
+        if (w.emit && (uint32_t)nc != w.n_cols) W_DATA_ERROR(SEQ_NEW_SHAPE, ETL_E_FIELD_COUNT);
         w.stage = W_NEW_CELLS;
       }
       continue;
     }
-    // ---- cells of the current tuple
     if (w.remaining == 0) {
       w.stage = (w.stage == W_OLD_CELLS && w.kind != 'D') ? W_NEW_HDR : W_DONE;
       continue;
     }
-    if (w.p >= w.end) { walker_malformed(P, w); break; }
-    uint32_t tag, len;
-    cell_header(w.p, &tag, &len);
-    const uint32_t rel = (uint32_t)(w.p - w.base);
+    if (w.p >= w.end) { W_MALFORMED(); break; }
+    const uint64_t x = ld64u(w.p);
+    const uint32_t tag = (uint32_t)(x & 0xFFu);
+    const uint32_t len = bswap32((uint32_t)(x >> 8));
+    const uint32_t vrel = (uint32_t)(w.p - w.base) + 5u;   // value offset inside the frame
     const bool has_body = tag == 't' || tag == 'b';
-    if (!has_body && tag != 'n' && tag != 'u') { walker_malformed(P, w); break; }
+    if (!has_body && tag != 'n' && tag != 'u') { W_MALFORMED(); break; }
     if (has_body) {
-      if (w.p + 5 > w.end || (int32_t)len < 0 || (uint64_t)len > (uint64_t)(w.end - w.p - 5)) { walker_malformed(P, w); break; }
-      *tbytes += len;
+      if (w.p + 5 > w.end || (int32_t)len < 0 || (uint64_t)len > (uint64_t)(w.end - w.p - 5)) { W_MALFORMED(); break; }
+      tbytes += len;
       w.p += 5 + (uint64_t)len;
     } else w.p += 1;
     const uint32_t i = w.wire_i++;
@@ -616,10 +596,19 @@ __device__ __noinline__ uint32_t walker_run(const DecodeParams& P, Walker& w, ui
     const uint32_t seq = is_new ? seq_new_cell(i) : seq_old_cell(i);
     const uint32_t cflags = w.flags[col];
     const bool resolver_key = is_new && w.kind == 'U' && w.old_tag == 'K' && (cflags & 2);
+    if (tag == 't') {
+      if (resolver_key) w.key_i++;
+      CellDesc& cd = d[n++];
+      cd.toff = w.toff0 + vrel;
+      cd.len = len;
+      cd.dest_rel = dest;
+      cd.meta = (slot << 24) | ((uint32_t)w.kinds[col] << 16) | ((is_new ? 1u : 0u) << 15) | (i & 0x7FFFu);
+      continue;
+    }
     if (tag == 'n') {                               // convert_tuple_data_to_cell event.rs:941-957
       if (resolver_key) w.key_i++;
       if (cflags & 1) put_cell(P, tile_cell0 + dest, ETL_CELL_NULL, 0, 0);
-      else walker_data_error(P, w, seq, ETL_E_NOT_NULL);
+      else W_DATA_ERROR(seq, ETL_E_NOT_NULL);
       continue;
     }
     if (tag == 'u') {                               // event.rs:958-970 + OldRowResolver :722-762
@@ -629,32 +618,38 @@ __device__ __noinline__ uint32_t walker_run(const DecodeParams& P, Walker& w, ui
         else if (resolver_key) src = w.cell0 + w.key_i++;
         if (src != 0xFFFFFFFFu) { put_cell(P, tile_cell0 + dest, kCellUnresolved, tile_cell0 + src, 0); w.has_unresolved = true; }
         else { put_cell(P, tile_cell0 + dest, ETL_CELL_MISSING, 0, 0); w.partial = true; }
-      } else walker_data_error(P, w, seq, (!is_new && w.old_tag == 'K') ? ETL_E_KEY_MISSING_VALUE : ETL_E_FULL_ROW_MISSING);
+      } else W_DATA_ERROR(seq, (!is_new && w.old_tag == 'K') ? ETL_E_KEY_MISSING_VALUE : ETL_E_FULL_ROW_MISSING);
       continue;
     }
     if (resolver_key) w.key_i++;
-    if (tag == 'b') { walker_data_error(P, w, seq, ETL_E_BINARY_FORMAT); continue; }
-    const uint32_t kind = w.kinds[col];
-    CellDesc& cd = d[n++];
-    cd.rel = rel;
-    cd.meta = (slot << 24) | (kind << 16) | ((is_new ? 1u : 0u) << 15) | (i & 0x7FFFu);
-    cd.dest_rel = dest;
-    cd.heap_off = 0;
+    W_DATA_ERROR(seq, ETL_E_BINARY_FORMAT);         // 'b'
   }
   return n;
 }
 
-// warp-cooperative UTF-8 validation of one long text cell: 16-byte aligned chunks per lane, an
-// all-ASCII chunk costs one load + one test; a chunk with high bits is checked with the
-// position-local rule over [lo, hi+3) so the following chunk never has to look back.
-__device__ __forceinline__ bool utf8_wide_warp_bad(const uint8_t* ptr, uint32_t len, int lane) {
+// UTF-8 validation of one long text cell by `nthreads` cooperating threads (a warp or the CTA):
+// 16-byte aligned chunks, 4 independent loads in flight per thread; an all-ASCII chunk costs one
+// load + one test; a chunk with high bits is checked with the position-local rule over [lo, hi+3)
+// so the following chunk never has to look back.
+__device__ __forceinline__ bool utf8_wide_bad(const uint8_t* ptr, uint32_t len, uint32_t t, uint32_t nthreads) {
   bool bad = false;
   const uintptr_t a0 = reinterpret_cast<uintptr_t>(ptr);
   const uint32_t headn = min(len, (uint32_t)((16u - (uint32_t)(a0 & 15u)) & 15u));
-  if (lane == 0 && headn) bad |= !utf8_chunk_valid(ptr, len, 0, min(headn + 3u, len));
+  if (t == 0 && headn) bad |= !utf8_chunk_valid(ptr, len, 0, min(headn + 3u, len));
   const uint32_t nchunks = (len - headn) / 16u;
   const uint4* body = reinterpret_cast<const uint4*>(ptr + headn);
-  for (uint32_t c = lane; c < nchunks; c += 32) {
+  uint32_t c = t;
+  for (; c + 3 * nthreads < nchunks; c += 4 * nthreads) {
+    const uint4 x0 = body[c], x1 = body[c + nthreads], x2 = body[c + 2 * nthreads], x3 = body[c + 3 * nthreads];
+    const uint32_t h0 = (x0.x | x0.y | x0.z | x0.w), h1 = (x1.x | x1.y | x1.z | x1.w), h2 = (x2.x | x2.y | x2.z | x2.w), h3 = (x3.x | x3.y | x3.z | x3.w);
+    if ((h0 | h1 | h2 | h3) & 0x80808080u) {
+      if (h0 & 0x80808080u) { const uint32_t lo = headn + c * 16u; bad |= !utf8_chunk_valid(ptr, len, lo, min(lo + 19u, len)); }
+      if (h1 & 0x80808080u) { const uint32_t lo = headn + (c + nthreads) * 16u; bad |= !utf8_chunk_valid(ptr, len, lo, min(lo + 19u, len)); }
+      if (h2 & 0x80808080u) { const uint32_t lo = headn + (c + 2 * nthreads) * 16u; bad |= !utf8_chunk_valid(ptr, len, lo, min(lo + 19u, len)); }
+      if (h3 & 0x80808080u) { const uint32_t lo = headn + (c + 3 * nthreads) * 16u; bad |= !utf8_chunk_valid(ptr, len, lo, min(lo + 19u, len)); }
+    }
+  }
+  for (; c < nchunks; c += nthreads) {
     const uint4 x = body[c];
     if ((x.x | x.y | x.z | x.w) & 0x80808080u) {
       const uint32_t lo = headn + c * 16u;
@@ -662,8 +657,19 @@ __device__ __forceinline__ bool utf8_wide_warp_bad(const uint8_t* ptr, uint32_t 
     }
   }
   const uint32_t tail0 = headn + nchunks * 16u;
-  if (lane == 31 && tail0 < len) bad |= !utf8_chunk_valid(ptr, len, tail0, len);
-  return __any_sync(0xffffffffu, bad);
+  if (t == nthreads - 1 && tail0 < len) bad |= !utf8_chunk_valid(ptr, len, tail0, len);
+  return bad;
+}
+
+__device__ __forceinline__ uint32_t warp_incl_sum(uint32_t v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += u; }
+  return v;
+}
+__device__ __forceinline__ int32_t warp_incl_max(int32_t v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { int32_t u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v = max(v, u); }
+  return v;
 }
 
 __global__ void __launch_bounds__(kEmitThreads, 3) k_emit(DecodeParams P) {
@@ -671,23 +677,38 @@ __global__ void __launch_bounds__(kEmitThreads, 3) k_emit(DecodeParams P) {
   EmitShared& sh = *reinterpret_cast<EmitShared*>(smem_raw);
   const uint32_t spt = P.segs_per_tile;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+  constexpr int kWarps = kEmitThreads / 32;
+  for (;;) {
+    __syncthreads();  // previous tile fully consumed
+    if (threadIdx.x == 0) sh.tile_idx = atomicAdd(P.tile_counter, 1u);
+    __syncthreads();
+    const uint32_t tile = sh.tile_idx;
+    if (tile >= P.n_tiles) break;
     const uint32_t seg0 = tile * spt;
     const uint32_t seg1 = min(seg0 + spt, P.n_anchors);
     const uint64_t t_begin = P.anchors[seg0];
     const uint64_t t_end = P.anchors[seg1];
-    __syncthreads();  // previous tile fully consumed
-    if (threadIdx.x == 0) {
-      uint32_t g = tile / P.tiles_per_group;
-      Summ pre = fold(P.carry, P.group_prefix[g]);
-      for (uint32_t t = g * P.tiles_per_group; t < tile; t++) pre = fold(pre, P.tile_summ[t]);
-      sh.chunk_carry = pre;
-      sh.metrics[0] = sh.metrics[1] = sh.metrics[2] = sh.metrics[3] = 0;
-      uint32_t b = 0;
-      for (uint32_t s = seg0; s < seg1; s++) { sh.seg_base[s - seg0] = b; b += P.seg_frames[s]; }
-      sh.seg_base[seg1 - seg0] = b;
+    if (t_end <= t_begin) continue;
+    // frames per segment → exclusive bases (warp 0)
+    if (wid == 0) {
+      uint32_t tot = 0;
+      for (uint32_t s0 = 0; s0 < seg1 - seg0; s0 += 32) {
+        const uint32_t si = s0 + lane;
+        const uint32_t cnt = si < seg1 - seg0 ? P.seg_frames[seg0 + si] : 0u;
+        const uint32_t inc = warp_incl_sum(cnt, lane);
+        if (si < seg1 - seg0) sh.seg_base[si] = tot + inc - cnt;
+        tot += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      if (lane == 0) {
+        sh.seg_base[seg1 - seg0] = tot;
+        sh.carry_cells = 0; sh.carry_cons = 0; sh.carry_b = -1; sh.carry_c = -1; sh.carry_b_lsn = 0; sh.carry_b_cons = 0;
+        sh.metrics[0] = sh.metrics[1] = sh.metrics[2] = sh.metrics[3] = 0;
+      }
     }
-    if (t_end <= t_begin) { __syncthreads(); continue; }
+    const Summ tile_pre = fold(P.carry, P.tile_prefix[tile]);
+    const uint64_t tile_cell0 = tile_pre.n_cells;
+    const uint64_t tile_rec0 = tile_pre.n_rec;
+    const bool in_tx0 = (tile_pre.flags & S_HAS_B) && !(tile_pre.flags & S_CLOSED);
     // ---- 1. stage the tile
     const uint64_t win0 = t_begin & ~15ull;
     const uint32_t lead = (uint32_t)(t_begin - win0);
@@ -702,8 +723,6 @@ __global__ void __launch_bounds__(kEmitThreads, 3) k_emit(DecodeParams P) {
       for (uint32_t i = threadIdx.x; i < win_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
     }
     __syncthreads();
-    const Summ tile_pre = sh.chunk_carry;           // exclusive prefix of the tile
-    const uint64_t tile_cell0 = tile_pre.n_cells;
     const uint32_t n_frames = min(sh.seg_base[seg1 - seg0], (uint32_t)kMaxTileFrames);
     // ---- 2. frame list
     if (threadIdx.x < seg1 - seg0) {
@@ -711,13 +730,13 @@ __global__ void __launch_bounds__(kEmitThreads, 3) k_emit(DecodeParams P) {
       const uint64_t stop = P.anchors[seg0 + threadIdx.x + 1];
       uint32_t k = sh.seg_base[threadIdx.x];
       while (pos < stop && k < (uint32_t)kMaxTileFrames) {
-        uint32_t rel = (uint32_t)(pos - win0);
+        const uint32_t rel = (uint32_t)(pos - win0);
         uint32_t flen;
-        if (rel + 5 <= win_bytes) {
-          const uint8_t* p = sh.tile + rel;
-          uint64_t avail = P.len - pos;
-          if (p[0] != 'd' || avail < 5) flen = (uint32_t)(avail > 0 ? avail - 1 : 0);
-          else { flen = be32(p + 1); if (flen < 4 || 1ull + flen > avail) flen = (uint32_t)(avail - 1); }
+        if (rel + 8 <= win_bytes) {
+          const uint64_t x = ld64u(sh.tile + rel);
+          const uint64_t avail = P.len - pos;
+          flen = bswap32((uint32_t)(x >> 8));
+          if ((x & 0xFFu) != 'd' || avail < 5 || flen < 4 || 1ull + flen > avail) flen = (uint32_t)(avail > 0 ? avail - 1 : 0);
         } else flen = read_head(P.buf + pos, P.len - pos).flen;
         sh.foff[k++] = (uint16_t)(pos - t_begin);
         pos += 1ull + flen;
@@ -730,36 +749,79 @@ __global__ void __launch_bounds__(kEmitThreads, 3) k_emit(DecodeParams P) {
       const bool active = f < n_frames;
       FrameHead h;
       h.malformed = true; h.kind = 0; h.flen = 0; h.rel = 0; h.old_tag = 0;
-      Summ e = summ_identity();
       const uint8_t* fp = nullptr;
       uint64_t foff_abs = 0;
+      uint32_t toff0 = 0;
       const DevSchema* s = nullptr;
+      uint32_t my_cells = 0, my_cons = 0;
+      uint64_t my_lsn = 0;
+      bool isB = false, isC = false;
       if (active) {
-        foff_abs = t_begin + sh.foff[f];
-        const uint32_t rel = lead + sh.foff[f];
+        toff0 = sh.foff[f];
+        foff_abs = t_begin + toff0;
+        const uint32_t rel = lead + toff0;
         const uint8_t* gp = P.buf + foff_abs;
         h = read_head((rel + 40 <= win_bytes) ? sh.tile + rel : gp, P.len - foff_abs);
-        fp = (rel + 1ull + h.flen <= win_bytes) ? sh.tile + rel : gp;
-        e = frame_state_elem(h, fp);
+        fp = (rel + 1ull + h.flen + 16 <= win_bytes) ? sh.tile + rel : gp;
         if (!h.malformed) {
           if (h.kind == 'I' || h.kind == 'U' || h.kind == 'D') s = find_schema(P, h.rel, foff_abs);
-          e.n_cells = frame_out_cells(h, s);
+          my_cells = frame_out_cells(h, s);
+          isB = h.kind == 'B'; isC = h.kind == 'C';
+          my_cons = (isB || isC || h.kind == 'R' || h.kind == 'I' || h.kind == 'U' || h.kind == 'D' || h.kind == 'T') ? 1u : 0u;
+          if (isB) my_lsn = be64(fp + 31);
         }
       }
-      if (threadIdx.x == 0) { sh.n_desc = 0; sh.n_wide = 0; sh.wide_next = 0; }
-      Summ chunk_total;
-      Summ pre = block_exclusive_scan(e, sh.warp_summ, &chunk_total);
-      const Summ carry = sh.chunk_carry;
-      pre = fold(carry, pre);
+      if (threadIdx.x == 0) { sh.n_desc = 0; sh.n_wide = 0; sh.wide_next = 0; sh.n_big = 0; }
+      // ---- four warp scans + cross-warp combine
+      const uint32_t inc_cells = warp_incl_sum(my_cells, lane);
+      const uint32_t inc_cons = warp_incl_sum(my_cons, lane);
+      const int32_t inc_b = warp_incl_max(isB ? (int32_t)f : -1, lane);
+      const int32_t inc_c = warp_incl_max(isC ? (int32_t)f : -1, lane);
+      if (lane == 31) { sh.ws_cells[wid] = inc_cells; sh.ws_cons[wid] = inc_cons; sh.ws_b[wid] = inc_b; sh.ws_c[wid] = inc_c; }
       __syncthreads();
-      if (threadIdx.x == 0) sh.chunk_carry = fold(carry, chunk_total);
+      uint32_t pre_cells = sh.carry_cells, pre_cons = sh.carry_cons;
+      int32_t pre_b = sh.carry_b, pre_c = sh.carry_c;
+      uint32_t tot_cells = pre_cells, tot_cons = pre_cons;
+      int32_t tot_b = pre_b, tot_c = pre_c;
+#pragma unroll
+      for (int k = 0; k < kWarps; k++) {
+        if (k < wid) { pre_cells += sh.ws_cells[k]; pre_cons += sh.ws_cons[k]; pre_b = max(pre_b, sh.ws_b[k]); pre_c = max(pre_c, sh.ws_c[k]); }
+        tot_cells += sh.ws_cells[k]; tot_cons += sh.ws_cons[k]; tot_b = max(tot_b, sh.ws_b[k]); tot_c = max(tot_c, sh.ws_c[k]);
+      }
+      const uint32_t cells_excl = pre_cells + inc_cells - my_cells;   // tile-relative first output cell
+      const uint32_t cons_incl = pre_cons + inc_cons;
+      const uint32_t cons_excl = cons_incl - my_cons;
+      int32_t eb = __shfl_up_sync(0xffffffffu, inc_b, 1), ec = __shfl_up_sync(0xffffffffu, inc_c, 1);
+      if (lane == 0) { eb = -1; ec = -1; }
+      const int32_t last_b = max(pre_b, eb), last_c = max(pre_c, ec);  // last Begin / Commit strictly before f
+      if (isB) { sh.b_lsn[threadIdx.x] = my_lsn; sh.b_cons[threadIdx.x] = cons_incl; }
+      const uint64_t old_carry_b_lsn = sh.carry_b_lsn;
+      const uint32_t old_carry_b_cons = sh.carry_b_cons;
+      __syncthreads();
+      // stream state seen by this frame (apply.rs:600-626, 1927-2006)
+      bool in_tx; uint64_t st_lsn; uint64_t st_ord;
+      if (last_b >= 0) {
+        const bool in_chunk = last_b >= (int32_t)c0;
+        st_lsn = in_chunk ? sh.b_lsn[last_b - (int32_t)c0] : old_carry_b_lsn;
+        const uint32_t bc = in_chunk ? sh.b_cons[last_b - (int32_t)c0] : old_carry_b_cons;
+        st_ord = (uint64_t)(cons_excl - bc) + 1ull;
+        in_tx = last_b > last_c;
+      } else {
+        st_lsn = tile_pre.lsn; st_ord = tile_pre.ord + cons_excl; in_tx = (last_c >= 0) ? false : in_tx0;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        sh.carry_cells = tot_cells; sh.carry_cons = tot_cons;
+        if (tot_b >= (int32_t)c0) { sh.carry_b_lsn = sh.b_lsn[tot_b - (int32_t)c0]; sh.carry_b_cons = sh.b_cons[tot_b - (int32_t)c0]; }
+        sh.carry_b = tot_b; sh.carry_c = tot_c;
+      }
       Walker w;
-      w.stage = W_DONE; w.has_unresolved = false; w.partial = false;
+      w.stage = W_DONE; w.has_unresolved = false; w.partial = false; w.n_cols = 0; w.n_old = 0; w.cell0 = 0;
       unsigned long long tb = 0;
+      const uint64_t my_cell0 = tile_cell0 + cells_excl;
       if (active) {
-        const uint64_t ridx = pre.n_rec;
+        const uint64_t ridx = tile_rec0 + f;
         const uint64_t gidx = P.record_index_base + ridx;
-        const bool in_tx = (pre.flags & S_HAS_B) && !(pre.flags & S_CLOSED);
         uint64_t commit_lsn = 0, ordinal = 0, start_lsn = 0;
         uint32_t rflags = 0;
         int32_t rschema = -1;
@@ -773,7 +835,7 @@ __global__ void __launch_bounds__(kEmitThreads, 3) k_emit(DecodeParams P) {
           wellformed = q1 != nullptr && cstr_end(q1, fe) != nullptr;
         }
         if (wellformed && (h.kind == 'I' || h.kind == 'U' || h.kind == 'D')) {
-          const uint32_t tt = (h.flen >= 4 + 26 + 5) ? fp[35] : 0u;  // tuple marker
+          const uint32_t tt = fp[35];  // tuple marker (mlen >= 5 is guaranteed by read_head)
           if (h.kind == 'I') wellformed = tt == 'N';
           else if (h.kind == 'U') wellformed = tt == 'N' || tt == 'O' || tt == 'K';
           else wellformed = tt == 'O' || tt == 'K';
@@ -781,36 +843,36 @@ __global__ void __launch_bounds__(kEmitThreads, 3) k_emit(DecodeParams P) {
         if (!wellformed) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; }
         else if (h.kind == 'k') { start_lsn = be64(fp + 6); rrel = fp[22]; }
         else {
-          start_lsn = be64(fp + 6);                   // wal_start apply.rs:1700
-          const uint8_t* m = fp + 31;                 // message body after the tag
+          start_lsn = bswap64(ld64u(fp + 6));          // wal_start apply.rs:1700
+          const uint8_t* m = fp + 31;                  // message body after the tag
           switch (h.kind) {
-            case 'B':                                 // apply.rs:1927-1943
-              commit_lsn = be64(m); ordinal = 0; rflags = ETL_RF_EVENT;
-              put_cell(P, pre.n_cells, ETL_CELL_I64, be64(m + 8), 0);
-              put_cell(P, pre.n_cells + 1, ETL_CELL_U32, be32(m + 16), 0);
+            case 'B':                                  // apply.rs:1927-1943
+              commit_lsn = my_lsn; ordinal = 0; rflags = ETL_RF_EVENT;
+              put_cell(P, my_cell0, ETL_CELL_I64, be64(m + 8), 0);
+              put_cell(P, my_cell0 + 1, ETL_CELL_U32, be32(m + 16), 0);
               break;
-            case 'C': {                               // apply.rs:1946-2006
+            case 'C': {                                // apply.rs:1946-2006
               if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; break; }
-              uint64_t cl = be64(m + 1);
-              if (cl != pre.lsn) { report_error(P, gidx, SEQ_STATE, ETL_E_COMMIT_LSN); ok = false; break; }
-              commit_lsn = cl; ordinal = pre.ord; rflags = ETL_RF_EVENT;
-              put_cell(P, pre.n_cells, ETL_CELL_I32, (uint64_t)(int64_t)(int8_t)m[0], 0);
-              put_cell(P, pre.n_cells + 1, ETL_CELL_I64, be64(m + 9), 0);
-              put_cell(P, pre.n_cells + 2, ETL_CELL_I64, be64(m + 17), 0);
+              const uint64_t cl = be64(m + 1);
+              if (cl != st_lsn) { report_error(P, gidx, SEQ_STATE, ETL_E_COMMIT_LSN); ok = false; break; }
+              commit_lsn = cl; ordinal = st_ord; rflags = ETL_RF_EVENT;
+              put_cell(P, my_cell0, ETL_CELL_I32, (uint64_t)(int64_t)(int8_t)m[0], 0);
+              put_cell(P, my_cell0 + 1, ETL_CELL_I64, be64(m + 9), 0);
+              put_cell(P, my_cell0 + 2, ETL_CELL_I64, be64(m + 17), 0);
               break;
             }
-            case 'R':                                 // apply.rs:2012-2089 (masks are built on the host)
+            case 'R':                                  // apply.rs:2012-2089 (masks are built on the host)
               for (uint32_t k = 0; k < P.n_rel_errors; k++)
                 if (P.rel_error_off[k] == foff_abs) { report_error(P, gidx, P.rel_error_seq[k], P.rel_error_code[k]); ok = false; }
               if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; break; }
-              commit_lsn = pre.lsn; ordinal = pre.ord; rflags = ETL_RF_EVENT;
+              commit_lsn = st_lsn; ordinal = st_ord; rflags = ETL_RF_EVENT;
               { const DevSchema* rs = find_schema(P, h.rel, foff_abs); if (rs && rs->effective_off == foff_abs) rschema = (int32_t)rs->batch_index; }
               break;
-            case 'I': case 'U': case 'D': {           // apply.rs:2092-2203
+            case 'I': case 'U': case 'D': {            // apply.rs:2092-2203
               // the tuple structure is validated by the walker (a malformed frame outranks state errors)
-              if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); }
-              commit_lsn = pre.lsn; ordinal = pre.ord;
-              if (!s) {                             // no schema to walk with: structure check only
+              if (!in_tx) report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE);
+              commit_lsn = st_lsn; ordinal = st_ord;
+              if (!s) {                                // no schema to walk with: structure check only
                 unsigned long long ignored;
                 if (!dml_structure_ok(h, fp, &ignored)) report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME);
                 report_error(P, gidx, SEQ_TABLE, ETL_E_MISSING_TABLE_STATE); ok = false; break;
@@ -819,20 +881,20 @@ __global__ void __launch_bounds__(kEmitThreads, 3) k_emit(DecodeParams P) {
               if (h.old_tag == 'O') rflags |= ETL_RF_OLD_FULL; else if (h.old_tag == 'K') rflags |= ETL_RF_OLD_KEY;
               break;
             }
-            case 'T': {                               // apply.rs:2206-2248
+            case 'T': {                                // apply.rs:2206-2248
               if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; break; }
-              commit_lsn = pre.lsn; ordinal = pre.ord;
-              put_cell(P, pre.n_cells, ETL_CELL_I32, (uint64_t)(int64_t)(int8_t)m[4], 0);
+              commit_lsn = st_lsn; ordinal = st_ord;
+              put_cell(P, my_cell0, ETL_CELL_I32, (uint64_t)(int64_t)(int8_t)m[4], 0);
               for (uint32_t i = 0; i < h.rel; i++) {
-                uint32_t rid = be32(m + 5 + 4 * i);
+                const uint32_t rid = be32(m + 5 + 4 * i);
                 const DevSchema* ts = find_schema(P, rid, foff_abs);
                 if (!ts) { report_error(P, gidx, SEQ_TABLE, ETL_E_MISSING_TABLE_STATE); ok = false; break; }
-                put_cell(P, pre.n_cells + 1 + i, ETL_CELL_U32, rid, ts->batch_index);
+                put_cell(P, my_cell0 + 1 + i, ETL_CELL_U32, rid, ts->batch_index);
               }
               if (h.rel > 0) rflags = ETL_RF_EVENT;
               break;
             }
-            case 'M': {                               // apply.rs:1808-1924
+            case 'M': {                                // apply.rs:1808-1924
               const uint8_t* end = fp + 1 + h.flen;
               const uint8_t* q = m + 9;
               const char* ddl = "supabase_etl_ddl";
@@ -843,27 +905,26 @@ __global__ void __launch_bounds__(kEmitThreads, 3) k_emit(DecodeParams P) {
               is_ddl = is_ddl && k == 16;
               const uint8_t* cq = q + k + 1;
               if (cq + 4 > end) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; break; }
-              int32_t cl = (int32_t)be32(cq);
+              const int32_t cl = (int32_t)be32(cq);
               if (cl < 0 || (uint64_t)cl > (uint64_t)(end - cq - 4)) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; break; }
               if (is_ddl) { rflags |= ETL_RF_DDL_MESSAGE; if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; } }
               break;
             }
-            default: break;                           // Origin / Type: structure only
+            default: break;                            // Origin / Type: structure only
           }
         }
         P.rec_off[ridx] = foff_abs; P.rec_kind[ridx] = (uint8_t)h.kind; P.rec_flags[ridx] = (uint8_t)rflags;
         P.rec_rel[ridx] = rrel; P.rec_schema[ridx] = rschema; P.rec_start_lsn[ridx] = start_lsn;
-        P.rec_commit_lsn[ridx] = commit_lsn; P.rec_tx_ordinal[ridx] = ordinal; P.rec_cell_base[ridx] = pre.n_cells;
+        P.rec_commit_lsn[ridx] = commit_lsn; P.rec_tx_ordinal[ridx] = ordinal; P.rec_cell_base[ridx] = my_cell0;
         if (ok && (rflags & ETL_RF_EVENT)) atomicAdd(&sh.metrics[3], 1ull);
         sh.fi_base[threadIdx.x] = fp; sh.fi_off[threadIdx.x] = foff_abs; sh.fi_rec[threadIdx.x] = (uint32_t)ridx;
         if (ok && s && (h.kind == 'I' || h.kind == 'U' || h.kind == 'D')) {
-          w.base = fp; w.end = fp + 1 + h.flen; w.p = fp + 36;
+          w.base = fp; w.end = fp + 1 + h.flen;
           w.kinds = P.col_kind + s->col_base; w.flags = P.col_flags + s->col_base;
-          w.rec_index = gidx; w.rec_local = (uint32_t)ridx; w.n_cols = s->n_cols; w.n_ident = s->n_ident;
-          w.cell0 = (uint32_t)(pre.n_cells - tile_cell0); w.emit = true;
+          w.rec_index = gidx; w.toff0 = toff0; w.n_cols = s->n_cols; w.n_ident = s->n_ident;
+          w.cell0 = cells_excl; w.emit = true;
           w.remaining = 0; w.wire_i = 0; w.cmap = 0; w.k_out = 0; w.key_i = 0; w.n_old = 0;
-          w.kind = (uint8_t)h.kind; w.old_tag = (uint8_t)h.old_tag;
-          w.dense = false; w.partial = false; w.has_unresolved = false;
+          w.kind = h.kind; w.old_tag = h.old_tag; w.dense = false;
           if (h.kind != 'I' && h.old_tag) { w.stage = W_OLD_HDR; w.p = fp + 36; }  // old image first
           else { w.stage = W_NEW_HDR; w.p = fp + 35; }                             // 'N' marker, then the new tuple
         }
@@ -873,73 +934,91 @@ __global__ void __launch_bounds__(kEmitThreads, 3) k_emit(DecodeParams P) {
       if (n_walkers) {
         uint32_t quota = (uint32_t)kDescCap / n_walkers;
         if (quota > 255) quota = 255;
+        const uint32_t win_rel = win_bytes - lead;    // tile-relative end of the shared window
         for (;;) {
+          if (threadIdx.x < 32) sh.hist[threadIdx.x] = 0;
+          if (threadIdx.x == 0) { sh.round_heap_need = 0; sh.round_heap_used = 0; }
           if (w.stage != W_DONE) {
             const uint32_t slot0 = atomicAdd(&sh.n_desc, quota);
-            const uint32_t got = walker_run(P, w, threadIdx.x, tile_cell0, sh.desc + slot0, quota, &tb);
+            const uint32_t got = walker_run(P, w, threadIdx.x, tile_cell0, sh.desc + slot0, quota, tb);
             for (uint32_t k = got; k < quota; k++) sh.desc[slot0 + k].meta = 0xFFFFFFFFu;
           }
           __syncthreads();
           const uint32_t nd = sh.n_desc;
-          // ---- heap reservation for this round: Σ bounds of the batch's heap-kind cells, one global
-          //      atomicAdd per round (placement inside the heap is unspecified; cells carry offsets)
-          if (P.heap_cap) {
-            uint32_t mine = 0;
-            for (uint32_t di = threadIdx.x; di < nd; di += blockDim.x) {
-              const CellDesc cd = sh.desc[di];
-              if (cd.meta == 0xFFFFFFFFu) continue;
-              const uint32_t kind = (cd.meta >> 16) & 0xFFu;
-              if (kind != ETL_K_NUMERIC && kind != ETL_K_BYTES && kind != ETL_K_UUID) continue;
-              uint32_t tag, len;
-              cell_header(sh.fi_base[cd.meta >> 24] + cd.rel, &tag, &len);
-              sh.desc[di].heap_off = mine;          // thread-local running offset, rebased below
-              mine += cell_heap_bound(kind, len);
-            }
-            uint32_t inc = mine;
+          // ---- counting sort of the batch by decode class (+ heap need of the round)
+          uint32_t rank[kDescPerThread];
+          uint32_t need = 0;
 #pragma unroll
-            for (int d2 = 1; d2 < 32; d2 <<= 1) { uint32_t up = __shfl_up_sync(0xffffffffu, inc, d2); if (lane >= d2) inc += up; }
-            if (lane == 31) sh.scan_u32[wid] = inc;
-            __syncthreads();
-            uint32_t wpre = 0, total = 0;
-            for (int k = 0; k < (int)(blockDim.x >> 5); k++) { if (k < wid) wpre += sh.scan_u32[k]; total += sh.scan_u32[k]; }
-            if (threadIdx.x == 0) sh.round_heap_base = total ? atomicAdd(P.heap_top, (unsigned long long)total) : 0ull;
-            const uint32_t my_base = wpre + inc - mine;
-            for (uint32_t di = threadIdx.x; di < nd; di += blockDim.x) {
-              const uint32_t kind = (sh.desc[di].meta >> 16) & 0xFFu;
-              if (sh.desc[di].meta != 0xFFFFFFFFu && (kind == ETL_K_NUMERIC || kind == ETL_K_BYTES || kind == ETL_K_UUID)) sh.desc[di].heap_off += my_base;
+          for (int k = 0; k < kDescPerThread; k++) {
+            const uint32_t di = threadIdx.x + k * kEmitThreads;
+            rank[k] = 0xFFFFFFFFu;
+            if (di < nd) {
+              const uint32_t meta = sh.desc[di].meta;
+              if (meta != 0xFFFFFFFFu) {
+                const uint32_t kind = (meta >> 16) & 31u;
+                rank[k] = atomicAdd(&sh.hist[kind], 1u);
+                need += cell_heap_bound(kind, sh.desc[di].len);
+              }
             }
-            __syncthreads();
           }
+          if (P.heap_cap && need) atomicAdd(&sh.round_heap_need, need);
+          __syncthreads();
+          if (threadIdx.x < 32) {
+            const uint32_t cnt = sh.hist[threadIdx.x];
+            const uint32_t inc = warp_incl_sum(cnt, lane);
+            sh.kstart[threadIdx.x] = inc - cnt;
+            if (threadIdx.x == 31) sh.n_sorted = inc;
+            if (threadIdx.x == 0 && sh.round_heap_need) sh.round_heap_base = atomicAdd(P.heap_top, (unsigned long long)sh.round_heap_need);
+          }
+          __syncthreads();
+#pragma unroll
+          for (int k = 0; k < kDescPerThread; k++) {
+            const uint32_t di = threadIdx.x + k * kEmitThreads;
+            if (rank[k] != 0xFFFFFFFFu) sh.perm[sh.kstart[(sh.desc[di].meta >> 16) & 31u] + rank[k]] = (uint16_t)di;
+          }
+          __syncthreads();
+          const uint32_t ns = sh.n_sorted;
           const unsigned long long round_heap = sh.round_heap_base;
-          // ---- thread-per-cell parsing of the batch
-          for (uint32_t di = threadIdx.x; di < nd; di += blockDim.x) {
-            const CellDesc cd = sh.desc[di];
-            if (cd.meta == 0xFFFFFFFFu) continue;
+          // ---- thread-per-cell parsing, kind-sorted
+          for (uint32_t j = threadIdx.x; j < ns; j += blockDim.x) {
+            const CellDesc cd = sh.desc[sh.perm[j]];
             const uint32_t slot = cd.meta >> 24, kind = (cd.meta >> 16) & 0xFFu, wi = cd.meta & 0x7FFFu;
             const uint32_t seq = ((cd.meta >> 15) & 1u) ? seq_new_cell(wi) : seq_old_cell(wi);
-            const uint8_t* cp = sh.fi_base[slot] + cd.rel;
-            uint32_t tag, len;
-            cell_header(cp, &tag, &len);
-            const uint8_t* v = cp + 5;
-            const uint64_t soff = sh.fi_off[slot] + cd.rel + 5;
+            const uint32_t len = cd.len;
+            const uint8_t* v = ((uint64_t)cd.toff + len + 16 <= win_rel) ? sh.tile + lead + cd.toff : P.buf + t_begin + cd.toff;
+            const uint64_t soff = t_begin + cd.toff;
             CellOut o;
             uint32_t code = 0;
             if (kind == ETL_K_STRING && len >= (uint32_t)kWideLen) {
-              const uint32_t ws = atomicAdd(&sh.n_wide, 1u);
-              if (ws < (uint32_t)kWideCap) sh.wide[ws] = WideText{v, len, seq, sh.fi_rec[slot]};
-              else if (!utf8_valid(v, len)) code = ETL_E_UTF8;
+              bool queued = false;
+              if (len >= (uint32_t)kBigLen) {
+                const uint32_t bs = atomicAdd(&sh.n_big, 1u);
+                if (bs < (uint32_t)kBigCap) { sh.big[bs] = WideText{v, len, seq, sh.fi_rec[slot]}; queued = true; }
+              }
+              if (!queued) {
+                const uint32_t ws = atomicAdd(&sh.n_wide, 1u);
+                if (ws < (uint32_t)kWideCap) { sh.wide[ws] = WideText{v, len, seq, sh.fi_rec[slot]}; queued = true; }
+              }
+              if (!queued && !utf8_valid(v, len)) code = ETL_E_UTF8;
               o.tag = ETL_CELL_STRING; o.val = soff; o.aux = len;
             } else if (!utf8_valid_fast(v, len)) code = ETL_E_UTF8;         // event.rs:972
             else {
-              HeapCursor hc{P.heap, round_heap + cd.heap_off};
-              if (hc.pos + cell_heap_bound(kind, len) > P.heap_cap && cell_heap_bound(kind, len)) code = ETL_E_MALFORMED_FRAME;  // cannot happen: cap is an upper bound
-              else code = parse_text_cell(kind, v, len, soff, hc, o);
+              const uint32_t hb = cell_heap_bound(kind, len);
+              HeapCursor hc{P.heap, 0};
+              if (hb) hc.pos = round_heap + atomicAdd(&sh.round_heap_used, hb);
+              code = parse_text_cell(kind, v, len, soff, hc, o);
             }
             if (code) report_error(P, P.record_index_base + sh.fi_rec[slot], seq, code);
             else put_cell(P, tile_cell0 + cd.dest_rel, o.tag, o.val, o.aux);
           }
           __syncthreads();
-          // ---- long text: one warp per cell
+          // ---- long text: the whole CTA per very large cell, then one warp per cell
+          const uint32_t nbig = min(sh.n_big, (uint32_t)kBigCap);
+          for (uint32_t b = 0; b < nbig; b++) {
+            const WideText wt = sh.big[b];
+            const bool bad = utf8_wide_bad(wt.ptr, wt.len, threadIdx.x, blockDim.x);
+            if (__syncthreads_or(bad) && threadIdx.x == 0) report_error(P, P.record_index_base + wt.rec_local, wt.seq, ETL_E_UTF8);
+          }
           const uint32_t nw = min(sh.n_wide, (uint32_t)kWideCap);
           for (;;) {
             uint32_t wi = 0;
@@ -947,16 +1026,16 @@ __global__ void __launch_bounds__(kEmitThreads, 3) k_emit(DecodeParams P) {
             wi = __shfl_sync(0xffffffffu, wi, 0);
             if (wi >= nw) break;
             const WideText wt = sh.wide[wi];
-            if (utf8_wide_warp_bad(wt.ptr, wt.len, lane) && lane == 0)
-              report_error(P, P.record_index_base + wt.rec_local, wt.seq, ETL_E_UTF8);
+            const bool bad = utf8_wide_bad(wt.ptr, wt.len, (uint32_t)lane, 32u);
+            if (__any_sync(0xffffffffu, bad) && lane == 0) report_error(P, P.record_index_base + wt.rec_local, wt.seq, ETL_E_UTF8);
           }
           __syncthreads();
-          if (threadIdx.x == 0) { sh.n_desc = 0; sh.n_wide = 0; sh.wide_next = 0; }
+          if (threadIdx.x == 0) { sh.n_desc = 0; sh.n_wide = 0; sh.wide_next = 0; sh.n_big = 0; }
           if (!__syncthreads_or(w.stage != W_DONE)) break;
         }
       }
       // ---- per-frame epilogue: unchanged-TOAST values copied from the old image; Partial flag; metrics
-      if (active && (h.kind == 'I' || h.kind == 'U' || h.kind == 'D') && s) {
+      if (active && s && (h.kind == 'I' || h.kind == 'U' || h.kind == 'D')) {
         if (w.has_unresolved) {
           const uint64_t c0n = tile_cell0 + w.cell0 + w.n_old;
           for (uint32_t i = 0; i < w.n_cols; i++)
@@ -965,14 +1044,15 @@ __global__ void __launch_bounds__(kEmitThreads, 3) k_emit(DecodeParams P) {
               put_cell(P, c0n + i, P.cell_tag[src], P.cell_val[src], P.cell_aux[src]);
             }
         }
-        if (w.partial) P.rec_flags[w.rec_local] |= ETL_RF_NEW_PARTIAL;
-        atomicAdd(&sh.metrics[h.kind == 'I' ? 0 : (h.kind == 'U' ? 1 : 2)], tb);
+        if (w.partial) P.rec_flags[tile_rec0 + f] |= ETL_RF_NEW_PARTIAL;
+        if (tb) atomicAdd(&sh.metrics[h.kind == 'I' ? 0 : (h.kind == 'U' ? 1 : 2)], tb);
       }
       __syncthreads();
     }
     if (threadIdx.x < 4 && sh.metrics[threadIdx.x]) atomicAdd(&P.metrics[threadIdx.x], sh.metrics[threadIdx.x]);
   }
-  (void)wid;
 }
+#undef W_DATA_ERROR
+#undef W_MALFORMED
 
 }  // namespace etl
