@@ -16,7 +16,8 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 
-DECODE_LIB = os.path.join(PKG, "libetl_decode.so")
+# ETL_LIB_SUFFIX / ETL_NVCC_DEFS: build and load an experimental variant (kernel geometry sweeps)
+DECODE_LIB = os.path.join(PKG, "libetl_decode%s.so" % os.environ.get("ETL_LIB_SUFFIX", ""))
 WALGEN_LIB = os.path.join(PKG, "libwalgen.so")
 
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -46,7 +47,7 @@ def build_decode(force: bool = False, verbose: bool = False) -> str:
     srcs = decode_sources() + [os.path.join(INCLUDE, "etl_decode.h")]
     if force or _stale(DECODE_LIB, srcs):
         cu = [s for s in srcs if s.endswith((".cu", ".cpp"))]
-        cmd = [_nvcc()] + NVCC_ARCH + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-shared", "-o", DECODE_LIB] + cu + ["-lcudart"]
+        cmd = [_nvcc()] + NVCC_ARCH + NVCC_FLAGS + os.environ.get("ETL_NVCC_DEFS", "").split() + ["-I", INCLUDE, "-I", CSRC, "-shared", "-o", DECODE_LIB] + cu + ["-lcudart"]
         res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         log = os.path.join(PKG, "build_decode.log")
         with open(log, "w") as f:

@@ -521,4 +521,331 @@ __device__ __noinline__ bool json_valid(const uint8_t* s, uint32_t n) {
   }
 }
 
+
+// ================================================================================================
+// Warp-synchronous fast paths.  Independent thread scheduling does not reconverge a warp after
+// loops that exit through break / return, so the hot parsers are written as loops whose trip is
+// voted with __any_sync(mask, ...) (one convergence point per iteration) or as loop-free SWAR
+// code.  `mask` = lanes of the warp that execute the same parser together.  Anything outside the
+// spellings Postgres itself emits falls back to the exact (divergent, rare) parsers above.
+
+__device__ __forceinline__ uint64_t ldu64(const uint8_t* p) {  // unaligned LE load from aligned words
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+  const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+  const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+  return ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
+}
+// 8 ASCII digits (first char in the low byte) → value; valid only if swar_all_digits(x)
+__device__ __forceinline__ uint32_t swar_parse8(uint64_t x) {
+  x -= 0x3030303030303030ull;
+  x = (x * 10ull) + (x >> 8);
+  return (uint32_t)((((x & 0x000000FF000000FFull) * 0x000F424000000064ull) +
+                     (((x >> 16) & 0x000000FF000000FFull) * 0x0000271000000001ull)) >> 32);
+}
+__device__ __forceinline__ bool swar_all_digits(uint64_t x) {
+  return (((x + 0x4646464646464646ull) | (x - 0x3030303030303030ull)) & 0x8080808080808080ull) == 0ull;
+}
+__device__ __forceinline__ uint64_t pow10_u64(uint32_t k) {  // k in 0..8
+  const uint64_t t[9] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull};
+  return t[k];
+}
+
+// Rust FromStr for integers (text.rs:49-60,159-161), 8 digits per step.
+__device__ __forceinline__ uint32_t parse_int_sync(unsigned mask, const uint8_t* s, uint32_t n, bool is_signed,
+                                                   uint64_t pos_limit, uint64_t neg_limit, int64_t* out) {
+  bool bad = n == 0;
+  bool neg = false;
+  uint32_t i = 0;
+  if (n) {
+    const uint32_t c0 = s[0];
+    if (c0 == '+') i = 1;
+    else if (c0 == '-') { if (!is_signed) bad = true; neg = true; i = 1; }
+    if (i == n) bad = true;
+  }
+  uint64_t acc = 0;
+  bool ovf = false;
+  while (__any_sync(mask, !bad && i < n)) {
+    if (!bad && i < n) {
+      const uint32_t k = min(8u, n - i);
+      uint64_t x = ldu64(s + i);
+      // keep the k chars in the high bytes, pad the low bytes with '0' (leading zeros)
+      if (k < 8) x = (x << (8u * (8u - k))) | (0x3030303030303030ull >> (8u * k));
+      if (!swar_all_digits(x)) bad = true;
+      else {
+        const uint64_t p10 = pow10_u64(k);
+        const uint64_t hi = __umul64hi(acc, p10);
+        const uint64_t lo = acc * p10;
+        const uint64_t v = (uint64_t)swar_parse8(x);
+        const uint64_t sum = lo + v;
+        if (hi != 0 || sum < lo) ovf = true;
+        acc = sum;
+        i += k;
+      }
+    }
+  }
+  if (bad || ovf || acc > (neg ? neg_limit : pos_limit)) return ETL_E_PARSE_INT;
+  *out = neg ? (int64_t)(0ull - acc) : (int64_t)acc;
+  return 0;
+}
+
+// "YYYY-MM-DD HH:MM:SS" at s[0..19) → days / seconds of day; false unless it is exactly that shape
+__device__ __forceinline__ bool fast_ymd_hms(const uint8_t* s, int64_t* days, int64_t* sod) {
+  const uint64_t a = ldu64(s), b = ldu64(s + 8);
+  const uint32_t c = (uint32_t)ldu64(s + 16);
+  // separators: s[4]='-' s[7]='-' s[10]=' ' s[13]=':' s[16]=':'
+  if (((a >> 32) & 0xFFu) != '-' || ((a >> 56) & 0xFFu) != '-' || ((b >> 16) & 0xFFu) != ' ' || ((b >> 40) & 0xFFu) != ':' || (c & 0xFFu) != ':') return false;
+  // digits: replace separators by '0' and test all 19 positions
+  const uint64_t da = (a & 0x00FFFF00FFFFFFFFull) | 0x3000003000000000ull;
+  const uint64_t db = (b & 0xFFFF00FFFF00FFFFull) | 0x0000300000300000ull;
+  const uint64_t dc = ((uint64_t)(c & 0x00FFFF00u) | 0x30000030u) | 0x3030303000000000ull;
+  if (!swar_all_digits(da) || !swar_all_digits(db) || !swar_all_digits(dc)) return false;
+  const uint32_t y = ((uint32_t)(a & 0xF)) * 1000 + ((uint32_t)(a >> 8) & 0xF) * 100 + ((uint32_t)(a >> 16) & 0xF) * 10 + ((uint32_t)(a >> 24) & 0xF);
+  const uint32_t mo = ((uint32_t)(a >> 40) & 0xF) * 10 + ((uint32_t)(a >> 48) & 0xF);
+  const uint32_t d = ((uint32_t)b & 0xF) * 10 + ((uint32_t)(b >> 8) & 0xF);
+  const uint32_t hh = ((uint32_t)(b >> 24) & 0xF) * 10 + ((uint32_t)(b >> 32) & 0xF);
+  const uint32_t mi = ((uint32_t)(b >> 48) & 0xF) * 10 + ((uint32_t)(b >> 56) & 0xF);
+  const uint32_t ss = ((c >> 8) & 0xF) * 10 + ((c >> 16) & 0xF);
+  if (mo < 1 || mo > 12 || d < 1 || hh > 23 || mi > 59 || ss > 59) return false;  // :60 → exact path
+  const uint32_t dim = (mo == 2) ? (((y % 4 == 0 && y % 100 != 0) || y % 400 == 0) ? 29u : 28u)
+                                 : ((mo == 4 || mo == 6 || mo == 9 || mo == 11) ? 30u : 31u);
+  if (d > dim) return false;
+  *days = days_from_civil((int64_t)y, (int64_t)mo, (int64_t)d);
+  *sod = (int64_t)(hh * 3600u + mi * 60u + ss);
+  return true;
+}
+// optional ".f{1,9}" at s[i..): returns nanoseconds and advances i; false on ".": exact path decides
+__device__ __forceinline__ bool fast_fraction(const uint8_t* s, uint32_t n, uint32_t* i, uint32_t* ns) {
+  *ns = 0;
+  if (*i >= n || s[*i] != '.') return true;
+  uint32_t k = *i + 1, v = 0, nd = 0;
+  while (k < n && nd < 9 && is_digit(s[k])) { v = v * 10 + (s[k] - '0'); k++; nd++; }
+  if (nd == 0 || (k < n && is_digit(s[k]))) return false;   // ≥ 10 digits → exact path (drops extras)
+  for (; nd < 9; nd++) v *= 10;
+  *ns = v; *i = k;
+  return true;
+}
+// timestamptz in the spellings the pinned session produces ("…+00", "…+HH", "…+HH:MM", "…+HHMM")
+__device__ __forceinline__ bool fast_timestamptz(const uint8_t* s, uint32_t n, CellOut& o) {
+  if (n < 22) return false;
+  int64_t days, sod;
+  if (!fast_ymd_hms(s, &days, &sod)) return false;
+  uint32_t i = 19, ns;
+  if (!fast_fraction(s, n, &i, &ns)) return false;
+  if (i + 3 > n) return false;
+  const uint32_t sg = s[i];
+  if (sg != '+' && sg != '-') return false;
+  if (!is_digit(s[i + 1]) || !is_digit(s[i + 2])) return false;
+  int32_t off = (int32_t)((s[i + 1] - '0') * 10 + (s[i + 2] - '0')) * 3600;
+  i += 3;
+  if (i < n) {
+    if (s[i] == ':') i++;
+    if (i + 2 != n || !is_digit(s[i]) || !is_digit(s[i + 1]) || s[i] > '5') return false;
+    off += (int32_t)((s[i] - '0') * 10 + (s[i + 1] - '0')) * 60;
+  }
+  if (off >= 86400) return false;
+  if (sg == '-') off = -off;
+  o.tag = ETL_CELL_TIMESTAMPTZ; o.val = (uint64_t)(days * 86400 + sod - off); o.aux = ns;
+  return true;
+}
+__device__ __forceinline__ bool fast_timestamp(const uint8_t* s, uint32_t n, CellOut& o) {
+  if (n < 19) return false;
+  int64_t days, sod;
+  if (!fast_ymd_hms(s, &days, &sod)) return false;
+  uint32_t i = 19, ns;
+  if (!fast_fraction(s, n, &i, &ns) || i != n) return false;
+  o.tag = ETL_CELL_TIMESTAMP; o.val = (uint64_t)(days * 86400 + sod); o.aux = ns;
+  return true;
+}
+
+// numeric: [+-]digits[.digits] (what Postgres emits) with warp-synchronous loops; everything else
+// (NaN, Infinity, exponents, '_' separators, whitespace) goes to parse_numeric.
+__device__ __forceinline__ uint32_t parse_numeric_sync(unsigned mask, const uint8_t* s, uint32_t n, HeapCursor& hc, CellOut& o) {
+  bool simple = n > 0 && n <= 4096;
+  uint32_t i0 = 0;
+  bool neg = false;
+  if (simple) { const uint32_t c0 = s[0]; if (c0 == '-') { neg = true; i0 = 1; } else if (c0 == '+') i0 = 1; }
+  // pass 1: shape
+  uint32_t nint = 0, nfrac = 0, ndot = 0;
+  uint32_t i = i0;
+  while (__any_sync(mask, simple && i < n)) {
+    if (simple && i < n) {
+      const uint32_t k = min(8u, n - i);
+      uint64_t x = ldu64(s + i);
+      for (uint32_t j = 0; j < k; j++, x >>= 8) {
+        const uint32_t ch = (uint32_t)x & 0xFFu;
+        if (is_digit(ch)) { if (ndot) nfrac++; else nint++; }
+        else if (ch == '.') ndot++;
+        else simple = false;
+      }
+      i += k;
+    }
+  }
+  simple = simple && ndot <= 1 && (nint + nfrac) > 0;
+  uint32_t code = 0xFFFFFFFFu;   // sentinel: not handled by the fast path
+  // numeric.rs:409-472 on the digit string D = int digits ++ frac digits
+  const uint32_t ndec = nint + nfrac;
+  const int64_t dweight = (int64_t)nint - 1;
+  const int64_t weight = dweight >= 0 ? (dweight + 4) / 4 - 1 : -1;   // nint == 0 → dweight = -1 → weight -1
+  const uint32_t offset = (uint32_t)((weight + 1) * 4 - (dweight + 1));
+  const uint32_t ndig = simple ? (ndec + offset + 3u) / 4u : 0u;
+  uint64_t off = 0;
+  int16_t* dg = nullptr;
+  if (simple) { off = hc.alloc(8 + 2 * ndig); dg = reinterpret_cast<int16_t*>(hc.heap + off + 8); }
+  const uint8_t* dp = s + i0;                       // digit j lives at dp[j] (j < nint) or dp[j+1]
+  uint32_t lead = 0, written = 0, last_nz = 0;
+  bool seen_nz = false;
+  uint32_t g = 0;
+  while (__any_sync(mask, g < ndig)) {                // every lane of `mask` votes; non-simple lanes have ndig = 0
+    if (g < ndig) {
+      uint32_t v = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int32_t j = (int32_t)(g * 4u + (uint32_t)k) - (int32_t)offset;
+        uint32_t d = 0;
+        if (j >= 0 && (uint32_t)j < ndec) d = (uint32_t)dp[(uint32_t)j + (((uint32_t)j >= nint) ? ndot : 0u)] - '0';
+        v = v * 10u + d;
+      }
+      if (!seen_nz) { if (v == 0) lead++; else { seen_nz = true; dg[0] = (int16_t)v; written = 1; last_nz = 1; } }
+      else { dg[written++] = (int16_t)v; if (v) last_nz = written; }
+      g++;
+    }
+  }
+  if (simple) {
+    etl_numeric_hdr hdr;
+    hdr.kind = 0; hdr.sign = 0; hdr.weight = 0; hdr.scale = (uint16_t)nfrac; hdr._pad = 0;
+    uint32_t nd = 0;
+    code = 0;
+    if (nfrac > 16383u) code = ETL_E_NUMERIC;
+    else if (seen_nz) {
+      const int64_t fw = weight - (int64_t)lead;
+      if (fw < -32768 || fw > 32767) code = ETL_E_NUMERIC;
+      hdr.sign = neg ? 1 : 0; hdr.weight = (int16_t)fw; nd = last_nz;
+    }
+    *reinterpret_cast<etl_numeric_hdr*>(hc.heap + off) = hdr;
+    o.tag = ETL_CELL_NUMERIC; o.val = off; o.aux = nd;
+  }
+  if (code == 0xFFFFFFFFu) code = parse_numeric(s, n, hc, o);
+  return code;
+}
+
+// serde_json acceptance as a flat byte-at-a-time DFA (one convergence point per byte).
+struct JsonState {
+  uint32_t st;        // see J_* below
+  uint32_t depth;
+  uint32_t stack[4];  // bit per level: 1 object, 0 array
+  uint32_t aux;       // literal tail / hex accumulator
+  uint32_t hexn;      // hex digits still expected
+  bool key;           // the string being read is an object key
+  bool low_sur;       // the \u escape being read must be a low surrogate
+};
+enum : uint32_t { J_VALUE = 0, J_AFTER, J_KEY_OR_CLOSE, J_KEY, J_COLON, J_VALUE_OR_CLOSE, J_STR, J_ESC, J_HEX, J_SUR_BS, J_SUR_U,
+                  J_MINUS, J_ZERO, J_INT, J_DOT, J_FRAC, J_E, J_ESIGN, J_EXP, J_LIT, J_BAD };
+__device__ __forceinline__ bool json_top(const JsonState& S) { return (S.stack[(S.depth - 1) >> 5] >> ((S.depth - 1) & 31)) & 1u; }
+// returns true if the byte was consumed (numbers end on a delimiter that must be re-examined)
+__device__ __forceinline__ bool json_step(JsonState& S, uint32_t c) {
+  const bool ws = c == ' ' || c == '\t' || c == '\n' || c == '\r';
+  switch (S.st) {
+    case J_STR:
+      if (c == '"') S.st = S.key ? J_COLON : J_AFTER;
+      else if (c == '\\') S.st = J_ESC;
+      else if (c < 0x20u) S.st = J_BAD;
+      return true;
+    case J_ESC:
+      if (c == 'u') { S.st = J_HEX; S.hexn = 4; S.aux = 0; }
+      else if (c == '"' || c == '\\' || c == '/' || c == 'b' || c == 'f' || c == 'n' || c == 'r' || c == 't') S.st = S.low_sur ? J_BAD : J_STR;
+      else S.st = J_BAD;
+      return true;
+    case J_HEX: {
+      const int h = hexval(c);
+      if (h < 0) { S.st = J_BAD; return true; }
+      S.aux = S.aux * 16u + (uint32_t)h;
+      if (--S.hexn == 0) {
+        const uint32_t u = S.aux;
+        if (S.low_sur) { S.st = (u >= 0xDC00u && u <= 0xDFFFu) ? J_STR : J_BAD; S.low_sur = false; }
+        else if (u >= 0xDC00u && u <= 0xDFFFu) S.st = J_BAD;
+        else if (u >= 0xD800u && u <= 0xDBFFu) S.st = J_SUR_BS;
+        else S.st = J_STR;
+      }
+      return true;
+    }
+    case J_SUR_BS: S.st = (c == '\\') ? J_SUR_U : J_BAD; return true;
+    case J_SUR_U: if (c == 'u') { S.st = J_HEX; S.hexn = 4; S.aux = 0; S.low_sur = true; } else S.st = J_BAD; return true;
+    case J_LIT:
+      if (c != (S.aux & 0xFFu)) S.st = J_BAD;
+      else { S.aux >>= 8; if (!S.aux) S.st = J_AFTER; }
+      return true;
+    case J_MINUS: S.st = (c == '0') ? J_ZERO : ((c - '1') <= 8u ? J_INT : J_BAD); return true;
+    case J_ZERO:
+      if (c == '.') { S.st = J_DOT; return true; }
+      if (c == 'e' || c == 'E') { S.st = J_E; return true; }
+      if (is_digit(c)) { S.st = J_BAD; return true; }
+      S.st = J_AFTER; return false;
+    case J_INT:
+      if (is_digit(c)) return true;
+      if (c == '.') { S.st = J_DOT; return true; }
+      if (c == 'e' || c == 'E') { S.st = J_E; return true; }
+      S.st = J_AFTER; return false;
+    case J_DOT: S.st = is_digit(c) ? J_FRAC : J_BAD; return true;
+    case J_FRAC:
+      if (is_digit(c)) return true;
+      if (c == 'e' || c == 'E') { S.st = J_E; return true; }
+      S.st = J_AFTER; return false;
+    case J_E: S.st = (c == '+' || c == '-') ? J_ESIGN : (is_digit(c) ? J_EXP : J_BAD); return true;
+    case J_ESIGN: S.st = is_digit(c) ? J_EXP : J_BAD; return true;
+    case J_EXP:
+      if (is_digit(c)) return true;
+      S.st = J_AFTER; return false;
+    case J_AFTER:
+      if (ws) return true;
+      if (S.depth == 0) { S.st = J_BAD; return true; }
+      if (c == ',') { S.st = json_top(S) ? J_KEY : J_VALUE; return true; }
+      if (c == (json_top(S) ? '}' : ']')) { S.depth--; return true; }
+      S.st = J_BAD; return true;
+    case J_COLON:
+      if (ws) return true;
+      S.st = (c == ':') ? J_VALUE : J_BAD; return true;
+    case J_KEY_OR_CLOSE: case J_KEY:
+      if (ws) return true;
+      if (S.st == J_KEY_OR_CLOSE && c == '}') { S.depth--; S.st = J_AFTER; return true; }
+      if (c == '"') { S.st = J_STR; S.key = true; S.low_sur = false; } else S.st = J_BAD;
+      return true;
+    case J_VALUE_OR_CLOSE:
+      if (ws) return true;
+      if (c == ']') { S.depth--; S.st = J_AFTER; return true; }
+      S.st = J_VALUE;
+      // fallthrough
+    case J_VALUE:
+      if (ws) return true;
+      if (c == '"') { S.st = J_STR; S.key = false; S.low_sur = false; return true; }
+      if (c == '{' || c == '[') {
+        if (S.depth >= 127u) { S.st = J_BAD; return true; }
+        if (c == '{') S.stack[S.depth >> 5] |= (1u << (S.depth & 31)); else S.stack[S.depth >> 5] &= ~(1u << (S.depth & 31));
+        S.depth++;
+        S.st = (c == '{') ? J_KEY_OR_CLOSE : J_VALUE_OR_CLOSE;
+        return true;
+      }
+      if (c == 't') { S.st = J_LIT; S.aux = 'r' | ('u' << 8) | ('e' << 16); return true; }
+      if (c == 'f') { S.st = J_LIT; S.aux = 'a' | ('l' << 8) | ('s' << 16) | ((uint32_t)'e' << 24); return true; }
+      if (c == 'n') { S.st = J_LIT; S.aux = 'u' | ('l' << 8) | ('l' << 16); return true; }
+      if (c == '-') { S.st = J_MINUS; return true; }
+      if (c == '0') { S.st = J_ZERO; return true; }
+      if ((c - '1') <= 8u) { S.st = J_INT; return true; }
+      S.st = J_BAD; return true;
+    default: return true;
+  }
+}
+__device__ __forceinline__ bool json_valid_sync(unsigned mask, const uint8_t* s, uint32_t n) {
+  JsonState S;
+  S.st = J_VALUE; S.depth = 0; S.stack[0] = S.stack[1] = S.stack[2] = S.stack[3] = 0; S.aux = 0; S.hexn = 0; S.key = false; S.low_sur = false;
+  uint32_t i = 0;
+  while (__any_sync(mask, i < n && S.st != J_BAD)) {
+    if (i < n && S.st != J_BAD) {
+      if (json_step(S, s[i])) i++;
+    }
+  }
+  if (S.st == J_BAD || S.depth != 0) return false;
+  return S.st == J_AFTER || S.st == J_ZERO || S.st == J_INT || S.st == J_FRAC || S.st == J_EXP;
+}
+
 }  // namespace etl

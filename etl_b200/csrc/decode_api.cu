@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -184,9 +185,13 @@ struct etl_dec_ctx {
   DevBuf<uint8_t> d_stream;
   DevBuf<uint64_t> d_anchors;
   DevBuf<uint32_t> d_seg_frames;
-  DevBuf<Summ> d_tile_summ, d_group_summ, d_group_prefix, d_total, d_tile_prefix;
+  DevBuf<Summ> d_tile_summ, d_group_summ, d_group_prefix, d_total, d_tile_prefix, d_seg_summ;
+  DevBuf<uint32_t> d_schema_by_batch;
   DevBuf<DevSchema> d_schemas;
   DevBuf<uint8_t> d_col_kind, d_col_flags;
+  DevBuf<BigSpan> d_big_spans;
+  DevBuf<unsigned long long> d_phase;    // optional per-phase cycle totals (ETL_PHASE_TIMING=1)
+  unsigned long long h_phase[16] = {0};
   DevBuf<unsigned long long> d_scalars;  // [0] first_error key, [1..4] metrics
   DevBuf<uint64_t> d_rel_err_off;
   DevBuf<uint32_t> d_rel_err_code, d_rel_err_seq;
@@ -299,8 +304,7 @@ int etl_dec_create(int device_id, etl_dec_ctx** out) {
   ctx->own_stream = true;
   for (auto& e : ctx->ev) cudaEventCreate(&e);
   cudaHostAlloc((void**)&ctx->h_total, sizeof(Summ), cudaHostAllocDefault);
-  cudaHostAlloc((void**)&ctx->h_scalars, 8 * sizeof(unsigned long long), cudaHostAllocDefault);
-  cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitShared));
+  cudaHostAlloc((void**)&ctx->h_scalars, 16 * sizeof(unsigned long long), cudaHostAllocDefault);
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
     uint64_t thr = UINT64_MAX;
@@ -321,7 +325,7 @@ void etl_dec_destroy(etl_dec_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ctx->d_stream.release(); ctx->d_anchors.release(); ctx->d_seg_frames.release(); ctx->d_tile_summ.release();
-  ctx->d_group_summ.release(); ctx->d_group_prefix.release(); ctx->d_tile_prefix.release(); ctx->d_total.release(); ctx->d_schemas.release();
+  ctx->d_group_summ.release(); ctx->d_group_prefix.release(); ctx->d_tile_prefix.release(); ctx->d_big_spans.release(); ctx->d_seg_summ.release(); ctx->d_schema_by_batch.release(); ctx->d_total.release(); ctx->d_schemas.release();
   ctx->d_col_kind.release(); ctx->d_col_flags.release(); ctx->d_scalars.release(); ctx->d_rel_err_off.release();
   ctx->d_rel_err_code.release(); ctx->d_rel_err_seq.release();
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
@@ -527,8 +531,20 @@ int etl_dec_decode_begin(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t fla
   P.n_rel_errors = (uint32_t)rel_err_off.size();
   CK(ctx->d_seg_frames.ensure(P.n_anchors + 1)); CK(ctx->d_tile_summ.ensure(P.n_tiles + 1));
   CK(ctx->d_group_summ.ensure(P.n_groups + 1)); CK(ctx->d_group_prefix.ensure(P.n_groups + 1)); CK(ctx->d_total.ensure(1));
-  CK(ctx->d_scalars.ensure(8)); CK(ctx->d_tile_prefix.ensure(P.n_tiles + 1));
+  CK(ctx->d_scalars.ensure(16)); CK(ctx->d_tile_prefix.ensure(P.n_tiles + 1));
+  CK(ctx->d_seg_summ.ensure(P.n_anchors + 1)); P.seg_summ = ctx->d_seg_summ.p;
+  {
+    std::vector<uint32_t> sbb(ds.size() + 1, 0);
+    for (uint32_t i = 0; i < ds.size(); i++) sbb[ds[i].batch_index] = i;
+    CK(ctx->d_schema_by_batch.ensure(sbb.size()));
+    CK(cudaMemcpyAsync(ctx->d_schema_by_batch.p, sbb.data(), sbb.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // sbb is a local
+    P.schema_by_batch = ctx->d_schema_by_batch.p;
+  }
   P.tile_prefix = ctx->d_tile_prefix.p; P.tile_counter = (unsigned int*)(ctx->d_scalars.p + 6);
+  P.big_cap = (uint32_t)std::min<uint64_t>(in->len / 2048 + 4096, 1u << 30);
+  CK(ctx->d_big_spans.ensure(P.big_cap));
+  P.big_spans = ctx->d_big_spans.p; P.big_count = (unsigned int*)(ctx->d_scalars.p + 7);
   P.seg_frames = ctx->d_seg_frames.p; P.tile_summ = ctx->d_tile_summ.p; P.group_summ = ctx->d_group_summ.p;
   P.group_prefix = ctx->d_group_prefix.p; P.total = ctx->d_total.p;
   P.first_error = ctx->d_scalars.p; P.metrics = ctx->d_scalars.p + 1;
@@ -611,15 +627,23 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
   P.carry = carry;
 
   // ---- pass C
-  ctx->h_scalars[0] = ~0ull; ctx->h_scalars[1] = ctx->h_scalars[2] = ctx->h_scalars[3] = ctx->h_scalars[4] = ctx->h_scalars[5] = ctx->h_scalars[6] = 0;
-  CK(cudaMemcpyAsync(ctx->d_scalars.p, ctx->h_scalars, 7 * 8, cudaMemcpyHostToDevice, st));
+  ctx->h_scalars[0] = ~0ull; ctx->h_scalars[1] = ctx->h_scalars[2] = ctx->h_scalars[3] = ctx->h_scalars[4] = ctx->h_scalars[5] = ctx->h_scalars[6] = ctx->h_scalars[7] = 0;
+  CK(cudaMemcpyAsync(ctx->d_scalars.p, ctx->h_scalars, 8 * 8, cudaMemcpyHostToDevice, st));
+  P.phase_cycles = nullptr;
+  if (getenv("ETL_PHASE_TIMING")) {
+    CK(ctx->d_phase.ensure(16));
+    CK(cudaMemsetAsync(ctx->d_phase.p, 0, 16 * 8, st));
+    P.phase_cycles = ctx->d_phase.p;
+  }
   CK(cudaEventRecord(ctx->ev[3], st));
   if (P.n_tiles) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    uint32_t grid = std::min<uint32_t>(P.n_tiles, (uint32_t)sms * 3);
-    k_emit<<<grid, kEmitThreads, sizeof(EmitShared), st>>>(P);
-    ctx->launches += 1;
+    P.n_records = nr;
+    k_frames<<<(P.n_anchors + 255) / 256, 256, 0, st>>>(P);
+    if (nr) k_walk<<<(uint32_t)((nr + kWalkThreads - 1) / kWalkThreads), kWalkThreads, 0, st>>>(P);
+    k_utf8_spans<<<sms * 6, 256, 0, st>>>(P);
+    ctx->launches += nr ? 3 : 2;
     CK(cudaGetLastError());
   }
   CK(cudaMemcpyAsync((void*)(b->dev.rec_cell_base + nr), &ctx->h_total->n_cells, 8, cudaMemcpyHostToDevice, st));
@@ -646,6 +670,14 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
   CK(cudaEventRecord(ctx->ev[5], st));
   CK(cudaStreamSynchronize(st));
 
+  if (P.phase_cycles) {
+    cudaMemcpy(ctx->h_phase, ctx->d_phase.p, 16 * 8, cudaMemcpyDeviceToHost);
+    unsigned long long tot = 0;
+    for (int i = 0; i < 13; i++) tot += ctx->h_phase[i];
+    fprintf(stderr, "[etl phase cycles of thread 0, %% of %llu]:", tot);
+    for (int i = 0; i < 13; i++) fprintf(stderr, " p%d=%.1f", i, 100.0 * ctx->h_phase[i] / (tot ? tot : 1));
+    fprintf(stderr, "\n");
+  }
   // ---- summary
   etl_dec_summary& S = b->summary;
   memset(&S, 0, sizeof S);

@@ -5,10 +5,14 @@
 //                       per-tile summary {records, cells, heap bytes, stream-state transformer}.
 //   k_scan    (pass B)  single-block exclusive scan of the per-group summaries (the state
 //                       transformer is associative, so commit_lsn / tx_ordinal become a scan).
-//   k_emit    (pass C)  one CTA per 32 KiB tile: coalesced 16-byte loads stage the tile in shared
-//                       memory, segment walkers rebuild the frame list there, then thread-per-frame
-//                       parsing of TupleData cells writes the record / cell / heap planes; large
-//                       text cells are validated block-cooperatively.
+//   k_frames  (pass C1) one thread per anchor segment replays its frames with the segment's exclusive
+//                       prefix (record index, cell base, stream state) and writes the record plane —
+//                       the apply loop's per-message state machine, serial inside 2 KiB, parallel across.
+//   k_walk    (pass C2) one thread per DML record; each CTA first groups its 256 records by frame
+//                       shape (schema, op, old-image kind) so a warp walks structurally identical
+//                       tuples in lockstep: cell i of every lane is the same column → the same parser.
+//   k_utf8_spans (C3)   TOAST-sized text is not validated by its owning thread: it is queued and
+//                       streamed here with 16-byte coalesced loads at HBM speed.
 //
 // Reference semantics: apply.rs:1687-2248 (state machine), event.rs:376-979 (tuples → rows),
 // text.rs:28-173 (cells).  HBM-bound integer/byte work — no tensor cores.
@@ -20,10 +24,13 @@
 
 namespace etl {
 
-constexpr int kTileBytes = 32768;      // nominal tile = kTileBytes of stream (frames that START inside it)
-constexpr int kTileCap = 36864;        // shared-memory window; bytes past it are read from global
-constexpr int kEmitThreads = 256;
-constexpr int kMaxTileFrames = 2048;   // > kTileBytes/23 + segments
+#ifndef ETL_TILE_BYTES
+#define ETL_TILE_BYTES 32768
+#endif
+constexpr int kTileBytes = ETL_TILE_BYTES;       // nominal tile = kTileBytes of stream (frames that START inside it)
+constexpr int kTileCap = ETL_TILE_BYTES + 4096;        // shared-memory window; bytes past it are read from global
+constexpr int kWalkThreads = 256;
+constexpr int kMaxTileFrames = ETL_TILE_BYTES / 16;   // > kTileBytes/23 + segments
 constexpr int kIndexThreads = 256;
 constexpr int kBigCell = 512;          // text cells at least this long are validated cooperatively
 constexpr int kBigQueue = 128;
@@ -64,6 +71,15 @@ struct DevSchema {
   uint32_t has_heap;      // any numeric / bytea / uuid / array column
 };
 
+struct BigSpan {
+  uint64_t cell_off;   // stream offset of the cell's first byte
+  uint64_t span_off;   // stream offset of the first byte this span validates
+  uint32_t span_len;   // bytes to validate (position-local rule: looks back 3 bytes inside the cell)
+  uint32_t cell_len;
+  uint32_t seq;
+  uint32_t rec_local;
+};
+
 struct DecodeParams {
   const uint8_t* buf;
   uint64_t len;
@@ -80,15 +96,21 @@ struct DecodeParams {
   const uint8_t* col_flags;  // bit0 nullable, bit1 identity
   // pass A outputs
   uint32_t* seg_frames;      // frames starting in each segment
+  Summ* seg_summ;            // per segment: summary (pass A) → exclusive prefix (pass B2), carry not included
   Summ* tile_summ;           // per tile
   Summ* group_summ;          // per group of tiles
   Summ* group_prefix;        // exclusive prefix per group (pass B)
   Summ* total;               // [0] = fold of everything (shard seam summary)
   Summ* tile_prefix;         // exclusive prefix per tile (pass B2), carry not included
   unsigned int* tile_counter;  // dynamic tile scheduler of the emit pass
+  unsigned long long* phase_cycles;  // optional (profiling): per-phase clock64 totals of thread 0
+  // out-of-window remainders of very long text cells, validated by k_utf8_spans at full bandwidth
+  struct BigSpan* big_spans; unsigned int* big_count; uint32_t big_cap;
   // carry-in (known when pass C runs)
   Summ carry;
   uint64_t record_index_base;  // global index of this shard's first record (multi-GPU)
+  uint64_t n_records;          // records of this shard (known after pass B)
+  const uint32_t* schema_by_batch;  // batch schema index → position in `schemas`
   // outputs
   uint64_t* rec_off; uint8_t* rec_kind; uint8_t* rec_flags; uint32_t* rec_rel; int32_t* rec_schema;
   uint64_t* rec_start_lsn; uint64_t* rec_commit_lsn; uint64_t* rec_tx_ordinal; uint64_t* rec_cell_base;
@@ -320,6 +342,7 @@ __global__ void __launch_bounds__(kIndexThreads) k_index(DecodeParams P) {
       pos += 1ull + h.flen;
     }
     P.seg_frames[seg] = nframes;
+    P.seg_summ[seg] = acc;
   }
   // fold across the segments of each tile, then across the tiles of the group (ordered shuffles)
   // generic ordered fold over the block through shared memory (blockDim <= 256)
@@ -351,6 +374,9 @@ __global__ void __launch_bounds__(256) k_tile_prefix(DecodeParams P) {
   Summ pre = P.group_prefix[g];
   for (uint32_t t = g * P.tiles_per_group; t < tile; t++) pre = fold(pre, P.tile_summ[t]);
   P.tile_prefix[tile] = pre;
+  // per-segment exclusive prefixes inside the tile (in place)
+  const uint32_t s0 = tile * P.segs_per_tile, s1 = min(s0 + P.segs_per_tile, P.n_anchors);
+  for (uint32_t sgm = s0; sgm < s1; sgm++) { const Summ e = P.seg_summ[sgm]; P.seg_summ[sgm] = pre; pre = fold(pre, e); }
 }
 
 // ================================================================================================
@@ -381,61 +407,7 @@ __global__ void __launch_bounds__(512) k_scan(DecodeParams P) {
 }
 
 // ================================================================================================
-// pass C: emit.  Persistent CTAs pull 32 KiB tiles from a global counter.  Per tile:
-//   1. stage the tile in shared memory (coalesced 16-byte loads)
-//   2. frame list (one walker thread per anchor segment, in shared memory)
-//   3. per 256-frame chunk: classify heads → four u32 warp-shuffle scans (cells, ordinal consumers,
-//      last Begin, last Commit) give every frame its cell base and stream state → record plane
-//   4. DML frames: register-resident thread-per-frame WALKERS follow the TupleData chain and emit a
-//      16-byte descriptor per text cell into a shared batch (NULL / unchanged-TOAST cells are
-//      resolved by the walker); the batch is counting-sorted by decode class so warps run one
-//      parser at a time; thread-per-CELL parsing; long text is validated by a warp (≥ 96 B) or by
-//      the whole CTA (≥ 2 KiB) with 16-byte loads.
-struct CellDesc {
-  uint32_t toff;      // offset of the value bytes relative to the tile start
-  uint32_t len;       // value length
-  uint32_t dest_rel;  // output cell index relative to the tile's first cell
-  uint32_t meta;      // frame slot (8) | kind (8) | is_new (1) | wire index (15); 0xFFFFFFFF = empty
-};
-struct WideText {
-  const uint8_t* ptr;
-  uint32_t len;
-  uint32_t seq;
-  uint32_t rec_local;
-};
-
-constexpr int kDescCap = 1024;
-constexpr int kDescPerThread = kDescCap / kEmitThreads;
-constexpr int kWideCap = 128;
-constexpr int kBigCap = 16;
-constexpr int kWideLen = 96;     // text cells at least this long are validated by a warp
-constexpr int kBigLen = 2048;    // ... and these by the whole CTA
-constexpr uint32_t kCellUnresolved = 253;  // internal: unchanged-TOAST cell awaiting its old value
-
-struct EmitShared {
-  alignas(16) uint8_t tile[kTileCap + 32];
-  uint16_t foff[kMaxTileFrames];            // frame starts relative to the tile start (< 32 KiB)
-  CellDesc desc[kDescCap];
-  uint16_t perm[kDescCap];                  // descriptor order after the counting sort by kind
-  const uint8_t* fi_base[kEmitThreads];     // per chunk slot: frame bytes (window or global)
-  uint64_t fi_off[kEmitThreads];            // absolute stream offset of the frame
-  uint64_t b_lsn[kEmitThreads];             // Begin frames of the chunk: final_lsn
-  uint32_t b_cons[kEmitThreads];            // ... and inclusive ordinal-consumer count
-  uint32_t fi_rec[kEmitThreads];            // shard-local record index
-  WideText wide[kWideCap];
-  WideText big[kBigCap];
-  uint32_t seg_base[132];
-  uint32_t ws_cells[kEmitThreads / 32], ws_cons[kEmitThreads / 32];
-  int32_t ws_b[kEmitThreads / 32], ws_c[kEmitThreads / 32];
-  uint32_t hist[32], kstart[32];
-  uint32_t carry_cells, carry_cons, carry_b_cons;
-  int32_t carry_b, carry_c;
-  uint64_t carry_b_lsn;
-  uint32_t n_desc, n_wide, wide_next, n_big, n_sorted, round_heap_need, round_heap_used, tile_idx;
-  unsigned long long round_heap_base;
-  unsigned long long metrics[4];
-};
-
+// helpers shared by the pass C kernels
 // unaligned little-endian 8-byte load built from aligned 32-bit words (works on the shared window
 // and on global memory; may touch up to 3 bytes before and 11 after p — buffers are padded)
 __device__ __forceinline__ uint64_t ld64u(const uint8_t* p) {
@@ -507,47 +479,241 @@ __device__ __forceinline__ uint32_t parse_text_cell(uint32_t kind, const uint8_t
   }
 }
 
-// ---- walker: one thread follows the TupleData chain(s) of one DML frame (event.rs:376-919)
-enum : uint32_t { W_OLD_HDR = 0, W_OLD_CELLS = 1, W_NEW_HDR = 2, W_NEW_CELLS = 3, W_DONE = 4 };
-struct Walker {
-  const uint8_t* base;   // frame start
-  const uint8_t* p;      // next byte to read
-  const uint8_t* end;    // frame end
-  const uint8_t* kinds;
-  const uint8_t* flags;
-  uint64_t rec_index;    // global record index (error keys)
-  uint32_t toff0;        // offset of the frame start relative to the tile start
-  uint32_t n_cols, n_ident;
-  uint32_t cell0;        // first output cell of the frame, relative to the tile's cell base
-  int32_t remaining;     // wire cells left in the current tuple
-  uint32_t wire_i, cmap, k_out, key_i, n_old;
-  uint32_t kind, old_tag, stage;
-  bool dense, partial, has_unresolved;
-  bool emit;             // false after the first data error: keep checking structure only, because a
-                         // malformed frame (parser error) outranks every conversion error of the record
-};
 __device__ __forceinline__ void put_cell(const DecodeParams& P, uint64_t idx, uint32_t tag, uint64_t val, uint32_t aux) {
   P.cell_tag[idx] = (uint8_t)tag; P.cell_val[idx] = val; P.cell_aux[idx] = aux;
 }
-#define W_DATA_ERROR(seq_, code_) do { report_error(P, w.rec_index, (seq_), (code_)); w.emit = false; } while (0)
-#define W_MALFORMED() do { report_error(P, w.rec_index, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); w.stage = W_DONE; } while (0)
+constexpr int kWideLen = 96;     // text cells at least this long are validated with 16-byte loads
+constexpr int kBigLen = 2048;    // ... and these are queued for k_utf8_spans
+// UTF-8 validation of bytes [lo, hi) of one text cell by `nthreads` cooperating threads (a warp, a
+// CTA, or a CTA of k_utf8_spans): 16-byte aligned chunks, 4 independent loads in flight per thread.
+// An all-ASCII chunk costs one load + one test; a chunk with high bits is checked with the
+// position-local rule over [clo, chi+3) so the following chunk never has to look back; the first 16
+// bytes of the range are always checked with look-back (a range may start in the middle of a cell).
+__device__ __forceinline__ bool utf8_range_bad(const uint8_t* cell, uint32_t cell_len, uint32_t lo, uint32_t hi, uint32_t t, uint32_t nthreads) {
+  bool bad = false;
+  if (hi <= lo) return false;
+  const uintptr_t a0 = reinterpret_cast<uintptr_t>(cell + lo);
+  const uint32_t headn = min(hi - lo, (uint32_t)((16u - (uint32_t)(a0 & 15u)) & 15u));
+  if (t == 0) bad |= !utf8_chunk_valid(cell, cell_len, lo, min(lo + headn + 19u, hi));
+  const uint32_t body0 = lo + headn;
+  const uint32_t nchunks = (hi - body0) / 16u;
+  const uint4* body = reinterpret_cast<const uint4*>(cell + body0);
+  uint32_t c = t;
+  for (; c + 3 * nthreads < nchunks; c += 4 * nthreads) {
+    const uint4 x0 = body[c], x1 = body[c + nthreads], x2 = body[c + 2 * nthreads], x3 = body[c + 3 * nthreads];
+    const uint32_t h0 = (x0.x | x0.y | x0.z | x0.w), h1 = (x1.x | x1.y | x1.z | x1.w), h2 = (x2.x | x2.y | x2.z | x2.w), h3 = (x3.x | x3.y | x3.z | x3.w);
+    if ((h0 | h1 | h2 | h3) & 0x80808080u) {
+      if (h0 & 0x80808080u) { const uint32_t cl = body0 + c * 16u; bad |= !utf8_chunk_valid(cell, cell_len, cl, min(cl + 19u, hi)); }
+      if (h1 & 0x80808080u) { const uint32_t cl = body0 + (c + nthreads) * 16u; bad |= !utf8_chunk_valid(cell, cell_len, cl, min(cl + 19u, hi)); }
+      if (h2 & 0x80808080u) { const uint32_t cl = body0 + (c + 2 * nthreads) * 16u; bad |= !utf8_chunk_valid(cell, cell_len, cl, min(cl + 19u, hi)); }
+      if (h3 & 0x80808080u) { const uint32_t cl = body0 + (c + 3 * nthreads) * 16u; bad |= !utf8_chunk_valid(cell, cell_len, cl, min(cl + 19u, hi)); }
+    }
+  }
+  for (; c < nchunks; c += nthreads) {
+    const uint4 x = body[c];
+    if ((x.x | x.y | x.z | x.w) & 0x80808080u) {
+      const uint32_t cl = body0 + c * 16u;
+      bad |= !utf8_chunk_valid(cell, cell_len, cl, min(cl + 19u, hi));
+    }
+  }
+  const uint32_t tail0 = body0 + nchunks * 16u;
+  if (t == nthreads - 1 && tail0 < hi) bad |= !utf8_chunk_valid(cell, cell_len, tail0, hi);
+  return bad;
+}
+__device__ __forceinline__ bool utf8_wide_bad(const uint8_t* ptr, uint32_t len, uint32_t t, uint32_t nthreads) {
+  return utf8_range_bad(ptr, len, 0, len, t, nthreads);
+}
 
-// advance the walker by at most `quota` text cells, writing descriptors to d[0..quota); returns count
-__device__ __forceinline__ uint32_t walker_run(const DecodeParams& P, Walker& w, uint32_t slot, uint64_t tile_cell0,
-                                               CellDesc* d, uint32_t quota, unsigned long long& tbytes) {
-  uint32_t n = 0;
-  while (w.stage != W_DONE && n < quota) {
+// streams the out-of-window remainders of very long text cells: one CTA per span, 64 bytes in
+// flight per thread.  HBM-bound: 16 bytes loaded per 3 instructions per lane.
+__global__ void __launch_bounds__(256) k_utf8_spans(DecodeParams P) {
+  const uint32_t n = min(*P.big_count, P.big_cap);
+  for (uint32_t e = blockIdx.x; e < n; e += gridDim.x) {
+    const BigSpan sp = P.big_spans[e];
+    const uint32_t lo = (uint32_t)(sp.span_off - sp.cell_off);
+    const bool bad = utf8_range_bad(P.buf + sp.cell_off, sp.cell_len, lo, lo + sp.span_len, threadIdx.x, blockDim.x);
+    if (__syncthreads_or(bad) && threadIdx.x == 0) report_error(P, P.record_index_base + sp.rec_local, sp.seq, ETL_E_UTF8);
+  }
+}
+
+__device__ __forceinline__ uint32_t warp_incl_sum(uint32_t v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += u; }
+  return v;
+}
+__device__ __forceinline__ int32_t warp_incl_max(int32_t v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { int32_t u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v = max(v, u); }
+  return v;
+}
+
+// ================================================================================================
+// pass C1: records.  Thread per anchor segment; frames of a segment are replayed in order with the
+// running stream state (apply.rs:600-626, 1687-2248), exactly like the reference's apply loop but
+// for ~2 KiB of stream per thread.
+__global__ void __launch_bounds__(256) k_frames(DecodeParams P) {
+  const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t events = 0;
+  if (seg < P.n_anchors) {
+    Summ st = fold(P.carry, P.seg_summ[seg]);
+    uint64_t pos = P.anchors[seg];
+    const uint64_t stop = P.anchors[seg + 1];
+    while (pos < stop) {
+      const uint8_t* fp = P.buf + pos;
+      const FrameHead h = read_head(fp, P.len - pos);
+      const uint64_t ridx = st.n_rec;
+      const uint64_t gidx = P.record_index_base + ridx;
+      const uint64_t my_cell0 = st.n_cells;
+      const bool in_tx = (st.flags & S_HAS_B) && !(st.flags & S_CLOSED);
+      const DevSchema* s = nullptr;
+      Summ e = frame_state_elem(h, fp);
+      if (!h.malformed) {
+        if (h.kind == 'I' || h.kind == 'U' || h.kind == 'D') s = find_schema(P, h.rel, pos);
+        e.n_cells = frame_out_cells(h, s);
+      }
+      uint64_t commit_lsn = 0, ordinal = 0, start_lsn = 0;
+      uint32_t rflags = 0;
+      int32_t rschema = -1;
+      uint32_t rrel = h.rel;
+      bool ok = true;
+      bool wellformed = !h.malformed;
+      if (wellformed && h.kind == 'O') wellformed = (h.flen >= 4 + 26 + 8) && cstr_end(fp + 39, fp + 1 + h.flen) != nullptr;
+      if (wellformed && h.kind == 'Y') {
+        const uint8_t* fe = fp + 1 + h.flen;
+        const uint8_t* q1 = (h.flen >= 4 + 26 + 4) ? cstr_end(fp + 35, fe) : nullptr;
+        wellformed = q1 != nullptr && cstr_end(q1, fe) != nullptr;
+      }
+      if (wellformed && (h.kind == 'I' || h.kind == 'U' || h.kind == 'D')) {
+        const uint32_t tt = fp[35];  // tuple marker (mlen >= 5 is guaranteed by read_head)
+        if (h.kind == 'I') wellformed = tt == 'N';
+        else if (h.kind == 'U') wellformed = tt == 'N' || tt == 'O' || tt == 'K';
+        else wellformed = tt == 'O' || tt == 'K';
+      }
+      if (!wellformed) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; }
+      else if (h.kind == 'k') { start_lsn = be64(fp + 6); rrel = fp[22]; }
+      else {
+        start_lsn = be64(fp + 6);                      // wal_start apply.rs:1700
+        const uint8_t* m = fp + 31;                    // message body after the tag
+        switch (h.kind) {
+          case 'B':                                    // apply.rs:1927-1943
+            commit_lsn = be64(m); ordinal = 0; rflags = ETL_RF_EVENT;
+            put_cell(P, my_cell0, ETL_CELL_I64, be64(m + 8), 0);
+            put_cell(P, my_cell0 + 1, ETL_CELL_U32, be32(m + 16), 0);
+            break;
+          case 'C': {                                  // apply.rs:1946-2006
+            if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; break; }
+            const uint64_t cl = be64(m + 1);
+            if (cl != st.lsn) { report_error(P, gidx, SEQ_STATE, ETL_E_COMMIT_LSN); ok = false; break; }
+            commit_lsn = cl; ordinal = st.ord; rflags = ETL_RF_EVENT;
+            put_cell(P, my_cell0, ETL_CELL_I32, (uint64_t)(int64_t)(int8_t)m[0], 0);
+            put_cell(P, my_cell0 + 1, ETL_CELL_I64, be64(m + 9), 0);
+            put_cell(P, my_cell0 + 2, ETL_CELL_I64, be64(m + 17), 0);
+            break;
+          }
+          case 'R':                                    // apply.rs:2012-2089 (masks are built on the host)
+            for (uint32_t k = 0; k < P.n_rel_errors; k++)
+              if (P.rel_error_off[k] == pos) { report_error(P, gidx, P.rel_error_seq[k], P.rel_error_code[k]); ok = false; }
+            if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; break; }
+            commit_lsn = st.lsn; ordinal = st.ord; rflags = ETL_RF_EVENT;
+            { const DevSchema* rs = find_schema(P, h.rel, pos); if (rs && rs->effective_off == pos) rschema = (int32_t)rs->batch_index; }
+            break;
+          case 'I': case 'U': case 'D': {              // apply.rs:2092-2203
+            // the tuple structure is validated by k_walk (a malformed frame outranks state errors)
+            if (!in_tx) report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE);
+            commit_lsn = st.lsn; ordinal = st.ord;
+            if (!s) {                                  // no schema to walk with: structure check only
+              unsigned long long ignored;
+              if (!dml_structure_ok(h, fp, &ignored)) report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME);
+              report_error(P, gidx, SEQ_TABLE, ETL_E_MISSING_TABLE_STATE); ok = false; break;
+            }
+            rschema = (int32_t)s->batch_index; rflags = ETL_RF_EVENT;
+            if (h.old_tag == 'O') rflags |= ETL_RF_OLD_FULL; else if (h.old_tag == 'K') rflags |= ETL_RF_OLD_KEY;
+            break;
+          }
+          case 'T': {                                  // apply.rs:2206-2248
+            if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; break; }
+            commit_lsn = st.lsn; ordinal = st.ord;
+            put_cell(P, my_cell0, ETL_CELL_I32, (uint64_t)(int64_t)(int8_t)m[4], 0);
+            for (uint32_t i = 0; i < h.rel; i++) {
+              const uint32_t rid = be32(m + 5 + 4 * i);
+              const DevSchema* ts = find_schema(P, rid, pos);
+              if (!ts) { report_error(P, gidx, SEQ_TABLE, ETL_E_MISSING_TABLE_STATE); ok = false; break; }
+              put_cell(P, my_cell0 + 1 + i, ETL_CELL_U32, rid, ts->batch_index);
+            }
+            if (h.rel > 0) rflags = ETL_RF_EVENT;
+            break;
+          }
+          case 'M': {                                  // apply.rs:1808-1924
+            const uint8_t* end = fp + 1 + h.flen;
+            const uint8_t* q = m + 9;
+            const char* ddl = "supabase_etl_ddl";
+            bool is_ddl = true; uint32_t k = 0; bool term = false;
+            if (q > end) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; break; }
+            for (; q + k < end; k++) { uint32_t ch = q[k]; if (!ch) { term = true; break; } if (k >= 16 || ch != (uint32_t)(uint8_t)ddl[k]) is_ddl = false; }
+            if (!term || !utf8_valid(q, k)) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; break; }
+            is_ddl = is_ddl && k == 16;
+            const uint8_t* cq = q + k + 1;
+            if (cq + 4 > end) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; break; }
+            const int32_t cl = (int32_t)be32(cq);
+            if (cl < 0 || (uint64_t)cl > (uint64_t)(end - cq - 4)) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; break; }
+            if (is_ddl) { rflags |= ETL_RF_DDL_MESSAGE; if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; } }
+            break;
+          }
+          default: break;                              // Origin / Type: structure only
+        }
+      }
+      // a record k_walk must not touch keeps schema = -1 only when it failed before conversion
+      if (!ok && (h.kind == 'I' || h.kind == 'U' || h.kind == 'D')) rschema = -1;
+      P.rec_off[ridx] = pos; P.rec_kind[ridx] = (uint8_t)h.kind; P.rec_flags[ridx] = (uint8_t)rflags;
+      P.rec_rel[ridx] = rrel; P.rec_schema[ridx] = rschema; P.rec_start_lsn[ridx] = start_lsn;
+      P.rec_commit_lsn[ridx] = commit_lsn; P.rec_tx_ordinal[ridx] = ordinal; P.rec_cell_base[ridx] = my_cell0;
+      if (ok && (rflags & ETL_RF_EVENT)) events++;
+      st = fold(st, e);
+      pos += 1ull + h.flen;
+    }
+  }
+  // events: warp reduce, one atomic per warp
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) events += __shfl_down_sync(0xffffffffu, events, d);
+  if ((threadIdx.x & 31) == 0 && events) atomicAdd(&P.metrics[3], (unsigned long long)events);
+}
+
+// ================================================================================================
+// pass C2: tuples.  Thread per DML record (event.rs:376-919 + text.rs:28-173).
+struct Wk {
+  const uint8_t* base;   // frame start (global)
+  uint32_t pos, end;     // frame-relative: next byte to read / frame end
+  uint32_t col_base, n_cols, n_ident;
+  uint64_t cell0;        // first output cell of the record
+  uint32_t rec_local;
+  uint32_t remaining, wire_i, cmap, k_out, key_i, n_old;
+  uint32_t kind, old_tag, stage;
+  uint32_t tb;           // Σ text lengths (calculate_tuple_bytes event.rs:260-270)
+  bool dense, partial;
+  bool emit;             // false after the first data error: structure-only walk (a malformed frame,
+                         // i.e. a parser error in the reference, outranks every conversion error)
+};
+enum : uint32_t { W_OLD_HDR = 0, W_OLD_CELLS = 1, W_NEW_HDR = 2, W_NEW_CELLS = 3, W_DONE = 4 };
+struct TextCell { const uint8_t* v; uint32_t len, kind, seq; uint64_t dest; };
+#define W_DATA_ERROR(seq_, code_) do { report_error(P, P.record_index_base + w.rec_local, (seq_), (code_)); w.emit = false; } while (0)
+#define W_MALFORMED() do { report_error(P, P.record_index_base + w.rec_local, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); w.stage = W_DONE; } while (0)
+
+// one step: a tuple header or ONE wire cell. Returns true when a text cell must be parsed (tc filled).
+__device__ __forceinline__ bool wk_step(const DecodeParams& P, Wk& w, TextCell& tc) {
+  do {
     if (w.stage == W_OLD_HDR || w.stage == W_NEW_HDR) {
       const bool is_new = w.stage == W_NEW_HDR;
+      if ((uint64_t)w.pos + (is_new ? 3u : 2u) > w.end) { W_MALFORMED(); break; }
+      const uint64_t x = ld64u(w.base + w.pos);
+      uint32_t hdr = (uint32_t)x;
       if (is_new) {
-        if (w.p >= w.end || *w.p != 'N') { W_MALFORMED(); break; }
-        w.p++;
+        if ((hdr & 0xFFu) != 'N') { W_MALFORMED(); break; }
+        hdr >>= 8; w.pos++;
       }
-      if (w.p + 2 > w.end) { W_MALFORMED(); break; }
-      int32_t nc = (int32_t)(int16_t)be16(w.p);
+      int32_t nc = (int32_t)(int16_t)(((hdr & 0xFFu) << 8) | ((hdr >> 8) & 0xFFu));
       if (nc < 0) nc = 0;
-      w.p += 2;
-      w.remaining = nc; w.wire_i = 0; w.cmap = 0; w.k_out = 0;
+      w.pos += 2;
+      w.remaining = (uint32_t)nc; w.wire_i = 0; w.cmap = 0; w.k_out = 0;
       if (!is_new) {
         if (w.old_tag == 'K') {                     // normalize_key_tuple_to_row event.rs:879-919
           w.n_old = w.n_ident;
@@ -565,492 +731,218 @@ __device__ __forceinline__ uint32_t walker_run(const DecodeParams& P, Walker& w,
         if (w.emit && (uint32_t)nc != w.n_cols) W_DATA_ERROR(SEQ_NEW_SHAPE, ETL_E_FIELD_COUNT);
         w.stage = W_NEW_CELLS;
       }
-      continue;
+      break;
     }
     if (w.remaining == 0) {
       w.stage = (w.stage == W_OLD_CELLS && w.kind != 'D') ? W_NEW_HDR : W_DONE;
-      continue;
+      break;
     }
-    if (w.p >= w.end) { W_MALFORMED(); break; }
-    const uint64_t x = ld64u(w.p);
+    if (w.pos >= w.end) { W_MALFORMED(); break; }
+    const uint64_t x = ld64u(w.base + w.pos);
     const uint32_t tag = (uint32_t)(x & 0xFFu);
     const uint32_t len = bswap32((uint32_t)(x >> 8));
-    const uint32_t vrel = (uint32_t)(w.p - w.base) + 5u;   // value offset inside the frame
-    const bool has_body = tag == 't' || tag == 'b';
-    if (!has_body && tag != 'n' && tag != 'u') { W_MALFORMED(); break; }
-    if (has_body) {
-      if (w.p + 5 > w.end || (int32_t)len < 0 || (uint64_t)len > (uint64_t)(w.end - w.p - 5)) { W_MALFORMED(); break; }
-      tbytes += len;
-      w.p += 5 + (uint64_t)len;
-    } else w.p += 1;
+    const uint32_t voff = w.pos + 5u;
+    if (tag == 't' || tag == 'b') {
+      if ((uint64_t)w.pos + 5 > w.end || (int32_t)len < 0 || (uint64_t)len > (uint64_t)(w.end - w.pos - 5)) { W_MALFORMED(); break; }
+      w.tb += len;
+      w.pos += 5u + len;
+    } else if (tag == 'n' || tag == 'u') w.pos += 1;
+    else { W_MALFORMED(); break; }
     const uint32_t i = w.wire_i++;
     w.remaining--;
-    if (!w.emit) continue;                          // structure-only after a data error
+    if (!w.emit) break;                             // structure-only after a data error
     const bool is_new = w.stage == W_NEW_CELLS;
-    uint32_t col = i, dest;
+    const uint8_t* flags = P.col_flags + w.col_base;
+    uint32_t col = i;
+    uint64_t dest;
     if (!is_new && w.old_tag == 'K') {
-      if (w.dense) { while (w.cmap < w.n_cols && !(w.flags[w.cmap] & 2)) w.cmap++; col = w.cmap++; }
-      else if (!(w.flags[i] & 2)) continue;         // full-width key: non-identity entries are not decoded
+      if (w.dense) { while (w.cmap < w.n_cols && !(flags[w.cmap] & 2)) w.cmap++; col = w.cmap++; }
+      else if (!(flags[i] & 2)) break;              // full-width key: non-identity entries are not decoded
       dest = w.cell0 + w.k_out++;
     } else dest = w.cell0 + (is_new ? w.n_old : 0u) + i;
     const uint32_t seq = is_new ? seq_new_cell(i) : seq_old_cell(i);
-    const uint32_t cflags = w.flags[col];
+    const bool need_flags = tag != 't' || (is_new && w.kind == 'U' && w.old_tag == 'K');
+    const uint32_t cflags = need_flags ? (uint32_t)flags[col] : 0u;
     const bool resolver_key = is_new && w.kind == 'U' && w.old_tag == 'K' && (cflags & 2);
     if (tag == 't') {
       if (resolver_key) w.key_i++;
-      CellDesc& cd = d[n++];
-      cd.toff = w.toff0 + vrel;
-      cd.len = len;
-      cd.dest_rel = dest;
-      cd.meta = (slot << 24) | ((uint32_t)w.kinds[col] << 16) | ((is_new ? 1u : 0u) << 15) | (i & 0x7FFFu);
-      continue;
+      tc.v = w.base + voff; tc.len = len; tc.kind = P.col_kind[w.col_base + col]; tc.seq = seq; tc.dest = dest;
+      return true;
     }
     if (tag == 'n') {                               // convert_tuple_data_to_cell event.rs:941-957
       if (resolver_key) w.key_i++;
-      if (cflags & 1) put_cell(P, tile_cell0 + dest, ETL_CELL_NULL, 0, 0);
+      if (cflags & 1) put_cell(P, dest, ETL_CELL_NULL, 0, 0);
       else W_DATA_ERROR(seq, ETL_E_NOT_NULL);
-      continue;
+      break;
     }
     if (tag == 'u') {                               // event.rs:958-970 + OldRowResolver :722-762
       if (is_new && w.kind == 'U') {
-        uint32_t src = 0xFFFFFFFFu;
+        uint64_t src = ~0ull;
         if (w.old_tag == 'O') src = w.cell0 + i;
         else if (resolver_key) src = w.cell0 + w.key_i++;
-        if (src != 0xFFFFFFFFu) { put_cell(P, tile_cell0 + dest, kCellUnresolved, tile_cell0 + src, 0); w.has_unresolved = true; }
-        else { put_cell(P, tile_cell0 + dest, ETL_CELL_MISSING, 0, 0); w.partial = true; }
+        if (src != ~0ull) put_cell(P, dest, P.cell_tag[src], P.cell_val[src], P.cell_aux[src]);  // written earlier by this thread
+        else { put_cell(P, dest, ETL_CELL_MISSING, 0, 0); w.partial = true; }
       } else W_DATA_ERROR(seq, (!is_new && w.old_tag == 'K') ? ETL_E_KEY_MISSING_VALUE : ETL_E_FULL_ROW_MISSING);
-      continue;
+      break;
     }
     if (resolver_key) w.key_i++;
     W_DATA_ERROR(seq, ETL_E_BINARY_FORMAT);         // 'b'
-  }
-  return n;
+  } while (0);
+  return false;
 }
 
-// UTF-8 validation of one long text cell by `nthreads` cooperating threads (a warp or the CTA):
-// 16-byte aligned chunks, 4 independent loads in flight per thread; an all-ASCII chunk costs one
-// load + one test; a chunk with high bits is checked with the position-local rule over [lo, hi+3)
-// so the following chunk never has to look back.
-__device__ __forceinline__ bool utf8_wide_bad(const uint8_t* ptr, uint32_t len, uint32_t t, uint32_t nthreads) {
-  bool bad = false;
-  const uintptr_t a0 = reinterpret_cast<uintptr_t>(ptr);
-  const uint32_t headn = min(len, (uint32_t)((16u - (uint32_t)(a0 & 15u)) & 15u));
-  if (t == 0 && headn) bad |= !utf8_chunk_valid(ptr, len, 0, min(headn + 3u, len));
-  const uint32_t nchunks = (len - headn) / 16u;
-  const uint4* body = reinterpret_cast<const uint4*>(ptr + headn);
-  uint32_t c = t;
-  for (; c + 3 * nthreads < nchunks; c += 4 * nthreads) {
-    const uint4 x0 = body[c], x1 = body[c + nthreads], x2 = body[c + 2 * nthreads], x3 = body[c + 3 * nthreads];
-    const uint32_t h0 = (x0.x | x0.y | x0.z | x0.w), h1 = (x1.x | x1.y | x1.z | x1.w), h2 = (x2.x | x2.y | x2.z | x2.w), h3 = (x3.x | x3.y | x3.z | x3.w);
-    if ((h0 | h1 | h2 | h3) & 0x80808080u) {
-      if (h0 & 0x80808080u) { const uint32_t lo = headn + c * 16u; bad |= !utf8_chunk_valid(ptr, len, lo, min(lo + 19u, len)); }
-      if (h1 & 0x80808080u) { const uint32_t lo = headn + (c + nthreads) * 16u; bad |= !utf8_chunk_valid(ptr, len, lo, min(lo + 19u, len)); }
-      if (h2 & 0x80808080u) { const uint32_t lo = headn + (c + 2 * nthreads) * 16u; bad |= !utf8_chunk_valid(ptr, len, lo, min(lo + 19u, len)); }
-      if (h3 & 0x80808080u) { const uint32_t lo = headn + (c + 3 * nthreads) * 16u; bad |= !utf8_chunk_valid(ptr, len, lo, min(lo + 19u, len)); }
+struct WalkShared {
+  uint32_t dict_key[64];
+  uint32_t dict_cnt[64];
+  uint32_t dict_start[64];
+  uint32_t n_keys;
+  uint32_t order[kWalkThreads];
+};
+
+__global__ void __launch_bounds__(kWalkThreads, 2) k_walk(DecodeParams P) {
+  __shared__ WalkShared sh;
+  const int lane = threadIdx.x & 31;
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // ---- 1. group the CTA's records by frame shape so that warps walk look-alike tuples
+  uint32_t key = 0xFFFFFFFFu;
+  if (r < P.n_records) {
+    const uint32_t kind = P.rec_kind[r];
+    const int32_t sc = P.rec_schema[r];
+    if ((kind == 'I' || kind == 'U' || kind == 'D') && sc >= 0) key = ((uint32_t)sc << 4) | ((kind == 'I') ? 0u : (kind == 'U' ? 4u : 8u)) | (P.rec_flags[r] & 3u);
+  }
+  if (threadIdx.x < 64) { sh.dict_key[threadIdx.x] = 0xFFFFFFFFu; sh.dict_cnt[threadIdx.x] = 0; }
+  if (threadIdx.x == 0) sh.n_keys = 0;
+  __syncthreads();
+  // dictionary of distinct keys (open addressing, 64 slots; overflow → slot 63 is shared = no grouping for the excess)
+  uint32_t slot = 63;
+  if (key != 0xFFFFFFFFu) {
+    uint32_t hsh = (key * 2654435761u) >> 26;
+    for (uint32_t probe = 0; probe < 63; probe++) {
+      const uint32_t sl = (hsh + probe) % 63u;
+      const uint32_t prev = atomicCAS(&sh.dict_key[sl], 0xFFFFFFFFu, key);
+      if (prev == 0xFFFFFFFFu || prev == key) { slot = sl; break; }
     }
   }
-  for (; c < nchunks; c += nthreads) {
-    const uint4 x = body[c];
-    if ((x.x | x.y | x.z | x.w) & 0x80808080u) {
-      const uint32_t lo = headn + c * 16u;
-      bad |= !utf8_chunk_valid(ptr, len, lo, min(lo + 19u, len));
-    }
+  const uint32_t my_rank = (key != 0xFFFFFFFFu) ? atomicAdd(&sh.dict_cnt[slot], 1u) : 0u;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const uint32_t c0 = sh.dict_cnt[threadIdx.x], c1 = sh.dict_cnt[threadIdx.x + 32];
+    const uint32_t i0 = warp_incl_sum(c0, lane);
+    const uint32_t t0 = __shfl_sync(0xffffffffu, i0, 31);
+    const uint32_t i1 = warp_incl_sum(c1, lane);
+    sh.dict_start[threadIdx.x] = i0 - c0;
+    sh.dict_start[threadIdx.x + 32] = t0 + i1 - c1;
+    if (threadIdx.x == 31) sh.n_keys = t0 + i1;     // number of DML records in the CTA
   }
-  const uint32_t tail0 = headn + nchunks * 16u;
-  if (t == nthreads - 1 && tail0 < len) bad |= !utf8_chunk_valid(ptr, len, tail0, len);
-  return bad;
-}
-
-__device__ __forceinline__ uint32_t warp_incl_sum(uint32_t v, int lane) {
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += u; }
-  return v;
-}
-__device__ __forceinline__ int32_t warp_incl_max(int32_t v, int lane) {
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) { int32_t u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v = max(v, u); }
-  return v;
-}
-
-__global__ void __launch_bounds__(kEmitThreads, 3) k_emit(DecodeParams P) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  EmitShared& sh = *reinterpret_cast<EmitShared*>(smem_raw);
-  const uint32_t spt = P.segs_per_tile;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  constexpr int kWarps = kEmitThreads / 32;
+  __syncthreads();
+  if (key != 0xFFFFFFFFu) sh.order[sh.dict_start[slot] + my_rank] = threadIdx.x;
+  __syncthreads();
+  const uint32_t n_dml = sh.n_keys;
+  // ---- 2. thread t walks the t-th record of the grouped order
+  Wk w;
+  w.stage = W_DONE; w.tb = 0; w.partial = false; w.kind = 0; w.rec_local = 0;
+  if (threadIdx.x < n_dml) {
+    const uint64_t rr = (uint64_t)blockIdx.x * blockDim.x + sh.order[threadIdx.x];
+    const uint64_t off = P.rec_off[rr];
+    const uint8_t* fp = P.buf + off;
+    const DevSchema& s = P.schemas[P.schema_by_batch[P.rec_schema[rr]]];
+    const uint32_t flen = bswap32((uint32_t)(ld64u(fp) >> 8));
+    w.base = fp; w.end = 1u + flen;
+    w.col_base = s.col_base; w.n_cols = s.n_cols; w.n_ident = s.n_ident;
+    w.cell0 = P.rec_cell_base[rr]; w.rec_local = (uint32_t)rr; w.emit = true;
+    w.remaining = 0; w.wire_i = 0; w.cmap = 0; w.k_out = 0; w.key_i = 0; w.n_old = 0;
+    w.kind = P.rec_kind[rr];
+    const uint32_t rf = P.rec_flags[rr];
+    w.old_tag = (rf & ETL_RF_OLD_FULL) ? 'O' : ((rf & ETL_RF_OLD_KEY) ? 'K' : 0u);
+    w.dense = false;
+    if (w.kind != 'I' && w.old_tag) { w.stage = W_OLD_HDR; w.pos = 36u; }   // old image first
+    else { w.stage = W_NEW_HDR; w.pos = 35u; }                              // 'N' marker, then the new tuple
+  }
+  // warp-synchronous stepping: all lanes take one step (header or cell) per iteration
   for (;;) {
-    __syncthreads();  // previous tile fully consumed
-    if (threadIdx.x == 0) sh.tile_idx = atomicAdd(P.tile_counter, 1u);
-    __syncthreads();
-    const uint32_t tile = sh.tile_idx;
-    if (tile >= P.n_tiles) break;
-    const uint32_t seg0 = tile * spt;
-    const uint32_t seg1 = min(seg0 + spt, P.n_anchors);
-    const uint64_t t_begin = P.anchors[seg0];
-    const uint64_t t_end = P.anchors[seg1];
-    if (t_end <= t_begin) continue;
-    // frames per segment → exclusive bases (warp 0)
-    if (wid == 0) {
-      uint32_t tot = 0;
-      for (uint32_t s0 = 0; s0 < seg1 - seg0; s0 += 32) {
-        const uint32_t si = s0 + lane;
-        const uint32_t cnt = si < seg1 - seg0 ? P.seg_frames[seg0 + si] : 0u;
-        const uint32_t inc = warp_incl_sum(cnt, lane);
-        if (si < seg1 - seg0) sh.seg_base[si] = tot + inc - cnt;
-        tot += __shfl_sync(0xffffffffu, inc, 31);
+    const bool act = w.stage != W_DONE;
+    if (!__any_sync(0xffffffffu, act)) break;
+    TextCell tc;
+    tc.v = nullptr; tc.len = 0; tc.kind = 0; tc.seq = 0; tc.dest = 0;
+    const bool is_text = act && wk_step(P, w, tc);
+    // ---- text cell: UTF-8 (event.rs:972) then the per-kind parser (text.rs:28-173)
+    CellOut o;
+    o.tag = 0; o.val = 0; o.aux = 0;
+    uint32_t code = 0;
+    bool do_parse = false;
+    const uint64_t soff = (uint64_t)(tc.v - P.buf);
+    if (is_text) {
+      if (tc.kind == ETL_K_STRING) {
+        o.tag = ETL_CELL_STRING; o.val = soff; o.aux = tc.len;
+        if (tc.len >= (uint32_t)kBigLen) {             // TOAST-sized: queue for the streaming validator
+          const uint32_t pieces = (tc.len + (256u << 10) - 1u) / (256u << 10);
+          const uint32_t at = atomicAdd(P.big_count, pieces);
+          if (at + pieces <= P.big_cap) {
+            for (uint32_t k = 0; k < pieces; k++) {
+              BigSpan sp;
+              sp.cell_off = soff; sp.span_off = soff + (uint64_t)k * (256u << 10);
+              sp.span_len = min(tc.len - k * (256u << 10), 256u << 10); sp.cell_len = tc.len; sp.seq = tc.seq; sp.rec_local = w.rec_local;
+              P.big_spans[at + k] = sp;
+            }
+          } else if (utf8_range_bad(tc.v, tc.len, 0, tc.len, 0, 1)) code = ETL_E_UTF8;
+        } else if (tc.len >= (uint32_t)kWideLen) { if (utf8_range_bad(tc.v, tc.len, 0, tc.len, 0, 1)) code = ETL_E_UTF8; }
+        else if (!utf8_valid_fast(tc.v, tc.len)) code = ETL_E_UTF8;
+      } else if (!utf8_valid_fast(tc.v, tc.len)) code = ETL_E_UTF8;
+      else do_parse = true;
+    }
+    __syncwarp();
+    const unsigned pm = __ballot_sync(0xffffffffu, do_parse);
+    if (do_parse) {
+      const unsigned mask = __match_any_sync(pm, tc.kind);
+      const uint32_t hb = cell_heap_bound(tc.kind, tc.len);
+      HeapCursor hc{P.heap, 0};
+      const bool heap_kind = tc.kind == ETL_K_NUMERIC || tc.kind == ETL_K_BYTES || tc.kind == ETL_K_UUID;  // uniform over `mask`
+      if (heap_kind) {                                 // warp-aggregated bump allocation
+        const unsigned below = mask & ((1u << lane) - 1u);
+        uint32_t mine_off = 0, total = 0;
+        for (unsigned mm = mask; mm; mm &= mm - 1) {   // lanes of `mask` run this loop together
+          const int src = __ffs(mm) - 1;
+          const uint32_t v = __shfl_sync(mask, hb, src);
+          if ((below >> src) & 1u) mine_off += v;
+          total += v;
+        }
+        unsigned long long base = 0;
+        const int leader = __ffs(mask) - 1;
+        if (lane == leader) base = atomicAdd(P.heap_top, (unsigned long long)total);
+        base = __shfl_sync(mask, base, leader);
+        hc.pos = base + mine_off;
       }
-      if (lane == 0) {
-        sh.seg_base[seg1 - seg0] = tot;
-        sh.carry_cells = 0; sh.carry_cons = 0; sh.carry_b = -1; sh.carry_c = -1; sh.carry_b_lsn = 0; sh.carry_b_cons = 0;
-        sh.metrics[0] = sh.metrics[1] = sh.metrics[2] = sh.metrics[3] = 0;
+      int64_t iv = 0;
+      switch (tc.kind) {
+        case ETL_K_I32: code = parse_int_sync(mask, tc.v, tc.len, true, 2147483647ull, 2147483648ull, &iv); o.tag = ETL_CELL_I32; o.val = (uint64_t)iv; break;
+        case ETL_K_I64: code = parse_int_sync(mask, tc.v, tc.len, true, 9223372036854775807ull, 9223372036854775808ull, &iv); o.tag = ETL_CELL_I64; o.val = (uint64_t)iv; break;
+        case ETL_K_I16: code = parse_int_sync(mask, tc.v, tc.len, true, 32767ull, 32768ull, &iv); o.tag = ETL_CELL_I16; o.val = (uint64_t)iv; break;
+        case ETL_K_U32: code = parse_int_sync(mask, tc.v, tc.len, false, 4294967295ull, 0ull, &iv); o.tag = ETL_CELL_U32; o.val = (uint64_t)iv; break;
+        case ETL_K_NUMERIC: code = parse_numeric_sync(mask, tc.v, tc.len, hc, o); break;
+        case ETL_K_JSON:
+          if (json_valid_sync(mask, tc.v, tc.len)) { o.tag = ETL_CELL_JSON; o.val = soff; o.aux = tc.len; } else code = ETL_E_JSON;
+          break;
+        case ETL_K_TIMESTAMPTZ:
+          if (!fast_timestamptz(tc.v, tc.len, o)) code = parse_text_cell(tc.kind, tc.v, tc.len, soff, hc, o);
+          break;
+        case ETL_K_TIMESTAMP:
+          if (!fast_timestamp(tc.v, tc.len, o)) code = parse_text_cell(tc.kind, tc.v, tc.len, soff, hc, o);
+          break;
+        default: code = parse_text_cell(tc.kind, tc.v, tc.len, soff, hc, o); break;
       }
     }
-    const Summ tile_pre = fold(P.carry, P.tile_prefix[tile]);
-    const uint64_t tile_cell0 = tile_pre.n_cells;
-    const uint64_t tile_rec0 = tile_pre.n_rec;
-    const bool in_tx0 = (tile_pre.flags & S_HAS_B) && !(tile_pre.flags & S_CLOSED);
-    // ---- 1. stage the tile
-    const uint64_t win0 = t_begin & ~15ull;
-    const uint32_t lead = (uint32_t)(t_begin - win0);
-    uint64_t wb = (t_end - win0 + 15ull) & ~15ull;
-    const uint64_t to_end = ((uint64_t)(P.len - win0) + 15ull) & ~15ull;
-    if (to_end < wb) wb = to_end;
-    if ((uint64_t)kTileCap < wb) wb = (uint64_t)kTileCap;
-    const uint32_t win_bytes = (uint32_t)wb;
-    {
-      const uint4* src = reinterpret_cast<const uint4*>(P.buf + win0);
-      uint4* dst = reinterpret_cast<uint4*>(sh.tile);
-      for (uint32_t i = threadIdx.x; i < win_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    if (is_text) {
+      if (code) { report_error(P, P.record_index_base + w.rec_local, tc.seq, code); w.emit = false; }
+      else put_cell(P, tc.dest, o.tag, o.val, o.aux);
     }
-    __syncthreads();
-    const uint32_t n_frames = min(sh.seg_base[seg1 - seg0], (uint32_t)kMaxTileFrames);
-    // ---- 2. frame list
-    if (threadIdx.x < seg1 - seg0) {
-      uint64_t pos = P.anchors[seg0 + threadIdx.x];
-      const uint64_t stop = P.anchors[seg0 + threadIdx.x + 1];
-      uint32_t k = sh.seg_base[threadIdx.x];
-      while (pos < stop && k < (uint32_t)kMaxTileFrames) {
-        const uint32_t rel = (uint32_t)(pos - win0);
-        uint32_t flen;
-        if (rel + 8 <= win_bytes) {
-          const uint64_t x = ld64u(sh.tile + rel);
-          const uint64_t avail = P.len - pos;
-          flen = bswap32((uint32_t)(x >> 8));
-          if ((x & 0xFFu) != 'd' || avail < 5 || flen < 4 || 1ull + flen > avail) flen = (uint32_t)(avail > 0 ? avail - 1 : 0);
-        } else flen = read_head(P.buf + pos, P.len - pos).flen;
-        sh.foff[k++] = (uint16_t)(pos - t_begin);
-        pos += 1ull + flen;
-      }
-    }
-    __syncthreads();
-    // ---- 3/4. chunks of 256 frames
-    for (uint32_t c0 = 0; c0 < n_frames; c0 += blockDim.x) {
-      const uint32_t f = c0 + threadIdx.x;
-      const bool active = f < n_frames;
-      FrameHead h;
-      h.malformed = true; h.kind = 0; h.flen = 0; h.rel = 0; h.old_tag = 0;
-      const uint8_t* fp = nullptr;
-      uint64_t foff_abs = 0;
-      uint32_t toff0 = 0;
-      const DevSchema* s = nullptr;
-      uint32_t my_cells = 0, my_cons = 0;
-      uint64_t my_lsn = 0;
-      bool isB = false, isC = false;
-      if (active) {
-        toff0 = sh.foff[f];
-        foff_abs = t_begin + toff0;
-        const uint32_t rel = lead + toff0;
-        const uint8_t* gp = P.buf + foff_abs;
-        h = read_head((rel + 40 <= win_bytes) ? sh.tile + rel : gp, P.len - foff_abs);
-        fp = (rel + 1ull + h.flen + 16 <= win_bytes) ? sh.tile + rel : gp;
-        if (!h.malformed) {
-          if (h.kind == 'I' || h.kind == 'U' || h.kind == 'D') s = find_schema(P, h.rel, foff_abs);
-          my_cells = frame_out_cells(h, s);
-          isB = h.kind == 'B'; isC = h.kind == 'C';
-          my_cons = (isB || isC || h.kind == 'R' || h.kind == 'I' || h.kind == 'U' || h.kind == 'D' || h.kind == 'T') ? 1u : 0u;
-          if (isB) my_lsn = be64(fp + 31);
-        }
-      }
-      if (threadIdx.x == 0) { sh.n_desc = 0; sh.n_wide = 0; sh.wide_next = 0; sh.n_big = 0; }
-      // ---- four warp scans + cross-warp combine
-      const uint32_t inc_cells = warp_incl_sum(my_cells, lane);
-      const uint32_t inc_cons = warp_incl_sum(my_cons, lane);
-      const int32_t inc_b = warp_incl_max(isB ? (int32_t)f : -1, lane);
-      const int32_t inc_c = warp_incl_max(isC ? (int32_t)f : -1, lane);
-      if (lane == 31) { sh.ws_cells[wid] = inc_cells; sh.ws_cons[wid] = inc_cons; sh.ws_b[wid] = inc_b; sh.ws_c[wid] = inc_c; }
-      __syncthreads();
-      uint32_t pre_cells = sh.carry_cells, pre_cons = sh.carry_cons;
-      int32_t pre_b = sh.carry_b, pre_c = sh.carry_c;
-      uint32_t tot_cells = pre_cells, tot_cons = pre_cons;
-      int32_t tot_b = pre_b, tot_c = pre_c;
-#pragma unroll
-      for (int k = 0; k < kWarps; k++) {
-        if (k < wid) { pre_cells += sh.ws_cells[k]; pre_cons += sh.ws_cons[k]; pre_b = max(pre_b, sh.ws_b[k]); pre_c = max(pre_c, sh.ws_c[k]); }
-        tot_cells += sh.ws_cells[k]; tot_cons += sh.ws_cons[k]; tot_b = max(tot_b, sh.ws_b[k]); tot_c = max(tot_c, sh.ws_c[k]);
-      }
-      const uint32_t cells_excl = pre_cells + inc_cells - my_cells;   // tile-relative first output cell
-      const uint32_t cons_incl = pre_cons + inc_cons;
-      const uint32_t cons_excl = cons_incl - my_cons;
-      int32_t eb = __shfl_up_sync(0xffffffffu, inc_b, 1), ec = __shfl_up_sync(0xffffffffu, inc_c, 1);
-      if (lane == 0) { eb = -1; ec = -1; }
-      const int32_t last_b = max(pre_b, eb), last_c = max(pre_c, ec);  // last Begin / Commit strictly before f
-      if (isB) { sh.b_lsn[threadIdx.x] = my_lsn; sh.b_cons[threadIdx.x] = cons_incl; }
-      const uint64_t old_carry_b_lsn = sh.carry_b_lsn;
-      const uint32_t old_carry_b_cons = sh.carry_b_cons;
-      __syncthreads();
-      // stream state seen by this frame (apply.rs:600-626, 1927-2006)
-      bool in_tx; uint64_t st_lsn; uint64_t st_ord;
-      if (last_b >= 0) {
-        const bool in_chunk = last_b >= (int32_t)c0;
-        st_lsn = in_chunk ? sh.b_lsn[last_b - (int32_t)c0] : old_carry_b_lsn;
-        const uint32_t bc = in_chunk ? sh.b_cons[last_b - (int32_t)c0] : old_carry_b_cons;
-        st_ord = (uint64_t)(cons_excl - bc) + 1ull;
-        in_tx = last_b > last_c;
-      } else {
-        st_lsn = tile_pre.lsn; st_ord = tile_pre.ord + cons_excl; in_tx = (last_c >= 0) ? false : in_tx0;
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        sh.carry_cells = tot_cells; sh.carry_cons = tot_cons;
-        if (tot_b >= (int32_t)c0) { sh.carry_b_lsn = sh.b_lsn[tot_b - (int32_t)c0]; sh.carry_b_cons = sh.b_cons[tot_b - (int32_t)c0]; }
-        sh.carry_b = tot_b; sh.carry_c = tot_c;
-      }
-      Walker w;
-      w.stage = W_DONE; w.has_unresolved = false; w.partial = false; w.n_cols = 0; w.n_old = 0; w.cell0 = 0;
-      unsigned long long tb = 0;
-      const uint64_t my_cell0 = tile_cell0 + cells_excl;
-      if (active) {
-        const uint64_t ridx = tile_rec0 + f;
-        const uint64_t gidx = P.record_index_base + ridx;
-        uint64_t commit_lsn = 0, ordinal = 0, start_lsn = 0;
-        uint32_t rflags = 0;
-        int32_t rschema = -1;
-        uint32_t rrel = h.rel;
-        bool ok = true;
-        bool wellformed = !h.malformed;
-        if (wellformed && h.kind == 'O') wellformed = (h.flen >= 4 + 26 + 8) && cstr_end(fp + 39, fp + 1 + h.flen) != nullptr;
-        if (wellformed && h.kind == 'Y') {
-          const uint8_t* fe = fp + 1 + h.flen;
-          const uint8_t* q1 = (h.flen >= 4 + 26 + 4) ? cstr_end(fp + 35, fe) : nullptr;
-          wellformed = q1 != nullptr && cstr_end(q1, fe) != nullptr;
-        }
-        if (wellformed && (h.kind == 'I' || h.kind == 'U' || h.kind == 'D')) {
-          const uint32_t tt = fp[35];  // tuple marker (mlen >= 5 is guaranteed by read_head)
-          if (h.kind == 'I') wellformed = tt == 'N';
-          else if (h.kind == 'U') wellformed = tt == 'N' || tt == 'O' || tt == 'K';
-          else wellformed = tt == 'O' || tt == 'K';
-        }
-        if (!wellformed) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; }
-        else if (h.kind == 'k') { start_lsn = be64(fp + 6); rrel = fp[22]; }
-        else {
-          start_lsn = bswap64(ld64u(fp + 6));          // wal_start apply.rs:1700
-          const uint8_t* m = fp + 31;                  // message body after the tag
-          switch (h.kind) {
-            case 'B':                                  // apply.rs:1927-1943
-              commit_lsn = my_lsn; ordinal = 0; rflags = ETL_RF_EVENT;
-              put_cell(P, my_cell0, ETL_CELL_I64, be64(m + 8), 0);
-              put_cell(P, my_cell0 + 1, ETL_CELL_U32, be32(m + 16), 0);
-              break;
-            case 'C': {                                // apply.rs:1946-2006
-              if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; break; }
-              const uint64_t cl = be64(m + 1);
-              if (cl != st_lsn) { report_error(P, gidx, SEQ_STATE, ETL_E_COMMIT_LSN); ok = false; break; }
-              commit_lsn = cl; ordinal = st_ord; rflags = ETL_RF_EVENT;
-              put_cell(P, my_cell0, ETL_CELL_I32, (uint64_t)(int64_t)(int8_t)m[0], 0);
-              put_cell(P, my_cell0 + 1, ETL_CELL_I64, be64(m + 9), 0);
-              put_cell(P, my_cell0 + 2, ETL_CELL_I64, be64(m + 17), 0);
-              break;
-            }
-            case 'R':                                  // apply.rs:2012-2089 (masks are built on the host)
-              for (uint32_t k = 0; k < P.n_rel_errors; k++)
-                if (P.rel_error_off[k] == foff_abs) { report_error(P, gidx, P.rel_error_seq[k], P.rel_error_code[k]); ok = false; }
-              if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; break; }
-              commit_lsn = st_lsn; ordinal = st_ord; rflags = ETL_RF_EVENT;
-              { const DevSchema* rs = find_schema(P, h.rel, foff_abs); if (rs && rs->effective_off == foff_abs) rschema = (int32_t)rs->batch_index; }
-              break;
-            case 'I': case 'U': case 'D': {            // apply.rs:2092-2203
-              // the tuple structure is validated by the walker (a malformed frame outranks state errors)
-              if (!in_tx) report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE);
-              commit_lsn = st_lsn; ordinal = st_ord;
-              if (!s) {                                // no schema to walk with: structure check only
-                unsigned long long ignored;
-                if (!dml_structure_ok(h, fp, &ignored)) report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME);
-                report_error(P, gidx, SEQ_TABLE, ETL_E_MISSING_TABLE_STATE); ok = false; break;
-              }
-              rschema = (int32_t)s->batch_index; rflags = ETL_RF_EVENT;
-              if (h.old_tag == 'O') rflags |= ETL_RF_OLD_FULL; else if (h.old_tag == 'K') rflags |= ETL_RF_OLD_KEY;
-              break;
-            }
-            case 'T': {                                // apply.rs:2206-2248
-              if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; break; }
-              commit_lsn = st_lsn; ordinal = st_ord;
-              put_cell(P, my_cell0, ETL_CELL_I32, (uint64_t)(int64_t)(int8_t)m[4], 0);
-              for (uint32_t i = 0; i < h.rel; i++) {
-                const uint32_t rid = be32(m + 5 + 4 * i);
-                const DevSchema* ts = find_schema(P, rid, foff_abs);
-                if (!ts) { report_error(P, gidx, SEQ_TABLE, ETL_E_MISSING_TABLE_STATE); ok = false; break; }
-                put_cell(P, my_cell0 + 1 + i, ETL_CELL_U32, rid, ts->batch_index);
-              }
-              if (h.rel > 0) rflags = ETL_RF_EVENT;
-              break;
-            }
-            case 'M': {                                // apply.rs:1808-1924
-              const uint8_t* end = fp + 1 + h.flen;
-              const uint8_t* q = m + 9;
-              const char* ddl = "supabase_etl_ddl";
-              bool is_ddl = true; uint32_t k = 0; bool term = false;
-              if (q > end) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; break; }
-              for (; q + k < end; k++) { uint32_t ch = q[k]; if (!ch) { term = true; break; } if (k >= 16 || ch != (uint32_t)(uint8_t)ddl[k]) is_ddl = false; }
-              if (!term || !utf8_valid(q, k)) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; break; }
-              is_ddl = is_ddl && k == 16;
-              const uint8_t* cq = q + k + 1;
-              if (cq + 4 > end) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; break; }
-              const int32_t cl = (int32_t)be32(cq);
-              if (cl < 0 || (uint64_t)cl > (uint64_t)(end - cq - 4)) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; break; }
-              if (is_ddl) { rflags |= ETL_RF_DDL_MESSAGE; if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; } }
-              break;
-            }
-            default: break;                            // Origin / Type: structure only
-          }
-        }
-        P.rec_off[ridx] = foff_abs; P.rec_kind[ridx] = (uint8_t)h.kind; P.rec_flags[ridx] = (uint8_t)rflags;
-        P.rec_rel[ridx] = rrel; P.rec_schema[ridx] = rschema; P.rec_start_lsn[ridx] = start_lsn;
-        P.rec_commit_lsn[ridx] = commit_lsn; P.rec_tx_ordinal[ridx] = ordinal; P.rec_cell_base[ridx] = my_cell0;
-        if (ok && (rflags & ETL_RF_EVENT)) atomicAdd(&sh.metrics[3], 1ull);
-        sh.fi_base[threadIdx.x] = fp; sh.fi_off[threadIdx.x] = foff_abs; sh.fi_rec[threadIdx.x] = (uint32_t)ridx;
-        if (ok && s && (h.kind == 'I' || h.kind == 'U' || h.kind == 'D')) {
-          w.base = fp; w.end = fp + 1 + h.flen;
-          w.kinds = P.col_kind + s->col_base; w.flags = P.col_flags + s->col_base;
-          w.rec_index = gidx; w.toff0 = toff0; w.n_cols = s->n_cols; w.n_ident = s->n_ident;
-          w.cell0 = cells_excl; w.emit = true;
-          w.remaining = 0; w.wire_i = 0; w.cmap = 0; w.k_out = 0; w.key_i = 0; w.n_old = 0;
-          w.kind = h.kind; w.old_tag = h.old_tag; w.dense = false;
-          if (h.kind != 'I' && h.old_tag) { w.stage = W_OLD_HDR; w.p = fp + 36; }  // old image first
-          else { w.stage = W_NEW_HDR; w.p = fp + 35; }                             // 'N' marker, then the new tuple
-        }
-      }
-      // ---- walker rounds
-      const uint32_t n_walkers = __syncthreads_count(w.stage != W_DONE);
-      if (n_walkers) {
-        uint32_t quota = (uint32_t)kDescCap / n_walkers;
-        if (quota > 255) quota = 255;
-        const uint32_t win_rel = win_bytes - lead;    // tile-relative end of the shared window
-        for (;;) {
-          if (threadIdx.x < 32) sh.hist[threadIdx.x] = 0;
-          if (threadIdx.x == 0) { sh.round_heap_need = 0; sh.round_heap_used = 0; }
-          if (w.stage != W_DONE) {
-            const uint32_t slot0 = atomicAdd(&sh.n_desc, quota);
-            const uint32_t got = walker_run(P, w, threadIdx.x, tile_cell0, sh.desc + slot0, quota, tb);
-            for (uint32_t k = got; k < quota; k++) sh.desc[slot0 + k].meta = 0xFFFFFFFFu;
-          }
-          __syncthreads();
-          const uint32_t nd = sh.n_desc;
-          // ---- counting sort of the batch by decode class (+ heap need of the round)
-          uint32_t rank[kDescPerThread];
-          uint32_t need = 0;
-#pragma unroll
-          for (int k = 0; k < kDescPerThread; k++) {
-            const uint32_t di = threadIdx.x + k * kEmitThreads;
-            rank[k] = 0xFFFFFFFFu;
-            if (di < nd) {
-              const uint32_t meta = sh.desc[di].meta;
-              if (meta != 0xFFFFFFFFu) {
-                const uint32_t kind = (meta >> 16) & 31u;
-                rank[k] = atomicAdd(&sh.hist[kind], 1u);
-                need += cell_heap_bound(kind, sh.desc[di].len);
-              }
-            }
-          }
-          if (P.heap_cap && need) atomicAdd(&sh.round_heap_need, need);
-          __syncthreads();
-          if (threadIdx.x < 32) {
-            const uint32_t cnt = sh.hist[threadIdx.x];
-            const uint32_t inc = warp_incl_sum(cnt, lane);
-            sh.kstart[threadIdx.x] = inc - cnt;
-            if (threadIdx.x == 31) sh.n_sorted = inc;
-            if (threadIdx.x == 0 && sh.round_heap_need) sh.round_heap_base = atomicAdd(P.heap_top, (unsigned long long)sh.round_heap_need);
-          }
-          __syncthreads();
-#pragma unroll
-          for (int k = 0; k < kDescPerThread; k++) {
-            const uint32_t di = threadIdx.x + k * kEmitThreads;
-            if (rank[k] != 0xFFFFFFFFu) sh.perm[sh.kstart[(sh.desc[di].meta >> 16) & 31u] + rank[k]] = (uint16_t)di;
-          }
-          __syncthreads();
-          const uint32_t ns = sh.n_sorted;
-          const unsigned long long round_heap = sh.round_heap_base;
-          // ---- thread-per-cell parsing, kind-sorted
-          for (uint32_t j = threadIdx.x; j < ns; j += blockDim.x) {
-            const CellDesc cd = sh.desc[sh.perm[j]];
-            const uint32_t slot = cd.meta >> 24, kind = (cd.meta >> 16) & 0xFFu, wi = cd.meta & 0x7FFFu;
-            const uint32_t seq = ((cd.meta >> 15) & 1u) ? seq_new_cell(wi) : seq_old_cell(wi);
-            const uint32_t len = cd.len;
-            const uint8_t* v = ((uint64_t)cd.toff + len + 16 <= win_rel) ? sh.tile + lead + cd.toff : P.buf + t_begin + cd.toff;
-            const uint64_t soff = t_begin + cd.toff;
-            CellOut o;
-            uint32_t code = 0;
-            if (kind == ETL_K_STRING && len >= (uint32_t)kWideLen) {
-              bool queued = false;
-              if (len >= (uint32_t)kBigLen) {
-                const uint32_t bs = atomicAdd(&sh.n_big, 1u);
-                if (bs < (uint32_t)kBigCap) { sh.big[bs] = WideText{v, len, seq, sh.fi_rec[slot]}; queued = true; }
-              }
-              if (!queued) {
-                const uint32_t ws = atomicAdd(&sh.n_wide, 1u);
-                if (ws < (uint32_t)kWideCap) { sh.wide[ws] = WideText{v, len, seq, sh.fi_rec[slot]}; queued = true; }
-              }
-              if (!queued && !utf8_valid(v, len)) code = ETL_E_UTF8;
-              o.tag = ETL_CELL_STRING; o.val = soff; o.aux = len;
-            } else if (!utf8_valid_fast(v, len)) code = ETL_E_UTF8;         // event.rs:972
-            else {
-              const uint32_t hb = cell_heap_bound(kind, len);
-              HeapCursor hc{P.heap, 0};
-              if (hb) hc.pos = round_heap + atomicAdd(&sh.round_heap_used, hb);
-              code = parse_text_cell(kind, v, len, soff, hc, o);
-            }
-            if (code) report_error(P, P.record_index_base + sh.fi_rec[slot], seq, code);
-            else put_cell(P, tile_cell0 + cd.dest_rel, o.tag, o.val, o.aux);
-          }
-          __syncthreads();
-          // ---- long text: the whole CTA per very large cell, then one warp per cell
-          const uint32_t nbig = min(sh.n_big, (uint32_t)kBigCap);
-          for (uint32_t b = 0; b < nbig; b++) {
-            const WideText wt = sh.big[b];
-            const bool bad = utf8_wide_bad(wt.ptr, wt.len, threadIdx.x, blockDim.x);
-            if (__syncthreads_or(bad) && threadIdx.x == 0) report_error(P, P.record_index_base + wt.rec_local, wt.seq, ETL_E_UTF8);
-          }
-          const uint32_t nw = min(sh.n_wide, (uint32_t)kWideCap);
-          for (;;) {
-            uint32_t wi = 0;
-            if (lane == 0) wi = atomicAdd(&sh.wide_next, 1u);
-            wi = __shfl_sync(0xffffffffu, wi, 0);
-            if (wi >= nw) break;
-            const WideText wt = sh.wide[wi];
-            const bool bad = utf8_wide_bad(wt.ptr, wt.len, (uint32_t)lane, 32u);
-            if (__any_sync(0xffffffffu, bad) && lane == 0) report_error(P, P.record_index_base + wt.rec_local, wt.seq, ETL_E_UTF8);
-          }
-          __syncthreads();
-          if (threadIdx.x == 0) { sh.n_desc = 0; sh.n_wide = 0; sh.wide_next = 0; sh.n_big = 0; }
-          if (!__syncthreads_or(w.stage != W_DONE)) break;
-        }
-      }
-      // ---- per-frame epilogue: unchanged-TOAST values copied from the old image; Partial flag; metrics
-      if (active && s && (h.kind == 'I' || h.kind == 'U' || h.kind == 'D')) {
-        if (w.has_unresolved) {
-          const uint64_t c0n = tile_cell0 + w.cell0 + w.n_old;
-          for (uint32_t i = 0; i < w.n_cols; i++)
-            if (P.cell_tag[c0n + i] == kCellUnresolved) {
-              const uint64_t src = P.cell_val[c0n + i];
-              put_cell(P, c0n + i, P.cell_tag[src], P.cell_val[src], P.cell_aux[src]);
-            }
-        }
-        if (w.partial) P.rec_flags[tile_rec0 + f] |= ETL_RF_NEW_PARTIAL;
-        if (tb) atomicAdd(&sh.metrics[h.kind == 'I' ? 0 : (h.kind == 'U' ? 1 : 2)], tb);
-      }
-      __syncthreads();
-    }
-    if (threadIdx.x < 4 && sh.metrics[threadIdx.x]) atomicAdd(&P.metrics[threadIdx.x], sh.metrics[threadIdx.x]);
   }
+  // ---- 3. per-record epilogue: Partial flag; tuple-byte metrics (one atomic per warp and op kind)
+  if (w.partial) P.rec_flags[w.rec_local] |= ETL_RF_NEW_PARTIAL;
+  uint32_t tbi = w.kind == 'I' ? w.tb : 0u, tbu = w.kind == 'U' ? w.tb : 0u, tbd = w.kind == 'D' ? w.tb : 0u;
+  unsigned long long si = tbi, su = tbu, sd = tbd;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) { si += __shfl_down_sync(0xffffffffu, si, d); su += __shfl_down_sync(0xffffffffu, su, d); sd += __shfl_down_sync(0xffffffffu, sd, d); }
+  if (lane == 0) { if (si) atomicAdd(&P.metrics[0], si); if (su) atomicAdd(&P.metrics[1], su); if (sd) atomicAdd(&P.metrics[2], sd); }
 }
 #undef W_DATA_ERROR
 #undef W_MALFORMED
