@@ -237,7 +237,7 @@ def main():
         if s.first_error.record_index != 2**64 - 1:
             raise RuntimeError(f"decode reported a data error at record {s.first_error.record_index} code {s.first_error.code}")
         last.update(launches=s.gpu_launches, emit_ms=s.emit_ms, index_ms=s.index_ms, kernel_ms=s.kernel_ms,
-                    h2d=s.h2d_bytes, d2h=s.d2h_bytes, n_records=seam.n_records, n_cells=seam.n_cells)
+                    h2d=s.h2d_bytes, d2h=s.d2h_bytes, n_records=seam.n_records, n_cells=seam.n_cells, span_bytes=s.span_bytes)
         bh.free()
         return s
 
@@ -250,7 +250,7 @@ def main():
         e0.record()
         for _ in range(steps):
             s = step(resident)
-            emit.append(s.emit_ms)
+            emit.append((s.frames_ms, s.walk_ms, s.spans_ms))
             index.append(s.index_ms)
             launches += s.gpu_launches
         e1.record()
@@ -299,13 +299,23 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        algo_bytes = nbytes + 8 * (int(host_view.n_anchors) + 1)  # stream + anchor index, per launch on this rank
-        emit_avg = float(np.mean(emit_ms))
-        achieved = algo_bytes / (emit_avg * 1e-3) / 1e9
+        # algorithmic bytes: every byte of the staged stream once + the anchor index
+        algo_bytes = nbytes + 8 * (int(host_view.n_anchors) + 1)
+        km = np.mean(np.array(emit_ms, dtype=np.float64), axis=0)           # frames, walk, spans (ms, rank 0)
+        kern = {"k_index+k_scan+k_tile_prefix": float(np.mean(index_ms)), "k_frames": float(km[0]), "k_walk": float(km[1]),
+                "k_utf8_spans": float(km[2])}
+        span_bytes = int(last["span_bytes"])
+        # bytes each kernel is responsible for: k_utf8_spans streams the TOAST-sized text, k_walk everything
+        # else in the DML tuples, k_frames / k_index the frame heads (counted with k_walk's share here)
+        kbytes = {"k_utf8_spans": span_bytes, "k_walk": algo_bytes - span_bytes}
+        dominant = max(("k_walk", "k_utf8_spans"), key=lambda k: kern[k])
+        pipeline_ms = sum(kern.values())
+        emit_avg = kern[dominant]
+        achieved = kbytes[dominant] / (emit_avg * 1e-3) / 1e9
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(f"{w.name}@{args.scale:g}/{n_gpus}")
+                traffic = json.load(f).get(f"{w.name}/{dominant}")
         except Exception:
             pass
         line = {
@@ -318,10 +328,16 @@ def main():
                        "parallelism": f"byte-range shards x{n_gpus}, one seam all-gather" if n_gpus > 1 else "single GPU",
                        "anchor_stride": args.stride, "l2_policy": "inputs (>=1.25 GiB per GPU) larger than the 126 MB L2",
                        "generate_s": round(gen_s, 2)},
-            "roofline": {"bound": "hbm", "kernel": "k_emit", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": emit_avg,
-                         "index_pass_ms": float(np.mean(index_ms))},
+                         "algorithmic_bytes_per_launch": kbytes[dominant], "avg_launch_ms": emit_avg,
+                         "kernels_ms": kern,
+                         "pipeline": {"algorithmic_bytes": algo_bytes, "ms": pipeline_ms,
+                                      "achieved": algo_bytes / (pipeline_ms * 1e-3) / 1e9,
+                                      "frac": algo_bytes / (pipeline_ms * 1e-3) / 1e9 / peak},
+                         "k_utf8_spans": {"algorithmic_bytes": span_bytes,
+                                          "achieved": span_bytes / max(kern["k_utf8_spans"], 1e-6) / 1e6,
+                                          "frac": span_bytes / max(kern["k_utf8_spans"], 1e-6) / 1e6 / peak}},
             "gpu_launches": launches,
             "clocks": sampler.report(),
         }

@@ -52,7 +52,7 @@ class Summary(C.Structure):
                 ("update_bytes", C.c_uint64), ("delete_bytes", C.c_uint64), ("n_events", C.c_uint64),
                 ("n_schemas", C.c_uint32), ("gpu_launches", C.c_uint32), ("kernel_ms", C.c_float),
                 ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("index_ms", C.c_float),
-                ("emit_ms", C.c_float), ("_pad", C.c_uint32 * 3), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("emit_ms", C.c_float), ("frames_ms", C.c_float), ("walk_ms", C.c_float), ("spans_ms", C.c_float), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("span_bytes", C.c_uint64)]
 
 
 class SchemaInfo(C.Structure):
@@ -82,7 +82,11 @@ def load(build: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build_decode() if build else _build.DECODE_LIB
+    # an existing in-tree library is loaded as is (the GPU box receives the prebuilt .so; file times are
+    # not preserved by the snapshot, so no staleness check here — `python -m etl_b200.build` rebuilds)
+    path = _build.DECODE_LIB
+    if build and not os.path.exists(path):
+        path = _build.build_decode()
     if not os.path.exists(path):
         raise RuntimeError(f"{path} is missing: the CUDA decode library must be built (python -m etl_b200.build)")
     L = C.CDLL(path)

@@ -200,6 +200,7 @@ struct etl_dec_ctx {
   Summ* h_total = nullptr;               // pinned
   unsigned long long* h_scalars = nullptr;  // pinned
   cudaEvent_t ev[6]{};
+  cudaEvent_t evk[3]{};
   // pending two-phase decode
   bool pending = false;
   DecodeParams P{};
@@ -303,8 +304,10 @@ int etl_dec_create(int device_id, etl_dec_ctx** out) {
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ETL_ERR_CUDA; }
   ctx->own_stream = true;
   for (auto& e : ctx->ev) cudaEventCreate(&e);
+  for (auto& e : ctx->evk) cudaEventCreate(&e);
   cudaHostAlloc((void**)&ctx->h_total, sizeof(Summ), cudaHostAllocDefault);
   cudaHostAlloc((void**)&ctx->h_scalars, 16 * sizeof(unsigned long long), cudaHostAllocDefault);
+  cudaFuncSetAttribute(k_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkShared));
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
     uint64_t thr = UINT64_MAX;
@@ -492,7 +495,7 @@ int etl_dec_decode_begin(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t fla
   P.len = in->len;
   P.n_anchors = (uint32_t)in->n_anchors;
   P.anchor_stride = stride;
-  P.segs_per_tile = std::max<uint32_t>(1, kTileBytes / stride);
+  P.segs_per_tile = 32;  // one warp of anchor segments per tile
   P.n_tiles = (P.n_anchors + P.segs_per_tile - 1) / P.segs_per_tile;
   P.tiles_per_group = std::max<uint32_t>(1, kIndexThreads / P.segs_per_tile);
   P.n_groups = (P.n_tiles + P.tiles_per_group - 1) / P.tiles_per_group;
@@ -544,7 +547,7 @@ int etl_dec_decode_begin(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t fla
   P.tile_prefix = ctx->d_tile_prefix.p; P.tile_counter = (unsigned int*)(ctx->d_scalars.p + 6);
   P.big_cap = (uint32_t)std::min<uint64_t>(in->len / 2048 + 4096, 1u << 30);
   CK(ctx->d_big_spans.ensure(P.big_cap));
-  P.big_spans = ctx->d_big_spans.p; P.big_count = (unsigned int*)(ctx->d_scalars.p + 7);
+  P.big_spans = ctx->d_big_spans.p; P.big_count = (unsigned int*)(ctx->d_scalars.p + 7); P.span_bytes = ctx->d_scalars.p + 8;
   P.seg_frames = ctx->d_seg_frames.p; P.tile_summ = ctx->d_tile_summ.p; P.group_summ = ctx->d_group_summ.p;
   P.group_prefix = ctx->d_group_prefix.p; P.total = ctx->d_total.p;
   P.first_error = ctx->d_scalars.p; P.metrics = ctx->d_scalars.p + 1;
@@ -627,8 +630,8 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
   P.carry = carry;
 
   // ---- pass C
-  ctx->h_scalars[0] = ~0ull; ctx->h_scalars[1] = ctx->h_scalars[2] = ctx->h_scalars[3] = ctx->h_scalars[4] = ctx->h_scalars[5] = ctx->h_scalars[6] = ctx->h_scalars[7] = 0;
-  CK(cudaMemcpyAsync(ctx->d_scalars.p, ctx->h_scalars, 8 * 8, cudaMemcpyHostToDevice, st));
+  ctx->h_scalars[0] = ~0ull; ctx->h_scalars[1] = ctx->h_scalars[2] = ctx->h_scalars[3] = ctx->h_scalars[4] = ctx->h_scalars[5] = ctx->h_scalars[6] = ctx->h_scalars[7] = ctx->h_scalars[8] = 0;
+  CK(cudaMemcpyAsync(ctx->d_scalars.p, ctx->h_scalars, 9 * 8, cudaMemcpyHostToDevice, st));
   P.phase_cycles = nullptr;
   if (getenv("ETL_PHASE_TIMING")) {
     CK(ctx->d_phase.ensure(16));
@@ -641,14 +644,17 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     P.n_records = nr;
     k_frames<<<(P.n_anchors + 255) / 256, 256, 0, st>>>(P);
-    if (nr) k_walk<<<(uint32_t)((nr + kWalkThreads - 1) / kWalkThreads), kWalkThreads, 0, st>>>(P);
+    cudaEventRecord(ctx->evk[0], st);
+    if (nr) k_walk<<<(uint32_t)((nr + kWalkThreads - 1) / kWalkThreads), kWalkThreads, sizeof(WalkShared), st>>>(P);
+    cudaEventRecord(ctx->evk[1], st);
     k_utf8_spans<<<sms * 6, 256, 0, st>>>(P);
+    cudaEventRecord(ctx->evk[2], st);
     ctx->launches += nr ? 3 : 2;
     CK(cudaGetLastError());
   }
   CK(cudaMemcpyAsync((void*)(b->dev.rec_cell_base + nr), &ctx->h_total->n_cells, 8, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(ctx->ev[4], st));
-  CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars.p, 6 * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars.p, 9 * 8, cudaMemcpyDeviceToHost, st));
   uint64_t heap_used = nh;
   if (nh) { CK(cudaStreamSynchronize(st)); heap_used = std::min<uint64_t>(nh, ctx->h_scalars[5]); }
   const uint64_t copy_bytes = f_heap + heap_used;
@@ -686,8 +692,14 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
   cudaEventElapsedTime(&d2h_ms, ctx->ev[4], ctx->ev[5]);
   S.kernel_ms = ctx->pending_index_ms + emit_ms;
   S.index_ms = ctx->pending_index_ms; S.emit_ms = emit_ms;
+  if (P.n_tiles) {
+    cudaEventElapsedTime(&S.frames_ms, ctx->ev[3], ctx->evk[0]);
+    cudaEventElapsedTime(&S.walk_ms, ctx->evk[0], ctx->evk[1]);
+    cudaEventElapsedTime(&S.spans_ms, ctx->evk[1], ctx->evk[2]);
+  }
   S.h2d_ms = ctx->pending_h2d_ms; S.d2h_ms = d2h_ms;
   S.h2d_bytes = ctx->pending_h2d_bytes;
+  S.span_bytes = ctx->h_scalars[8];
   S.d2h_bytes = 5 * 8 + sizeof(Summ) + ((ctx->pending_flags & ETL_DECODE_RESULTS_TO_HOST) ? copy_bytes : 0);
   S.gpu_launches = ctx->launches;
   S.n_schemas = (uint32_t)b->schemas.size();

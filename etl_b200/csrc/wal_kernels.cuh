@@ -105,7 +105,7 @@ struct DecodeParams {
   unsigned int* tile_counter;  // dynamic tile scheduler of the emit pass
   unsigned long long* phase_cycles;  // optional (profiling): per-phase clock64 totals of thread 0
   // out-of-window remainders of very long text cells, validated by k_utf8_spans at full bandwidth
-  struct BigSpan* big_spans; unsigned int* big_count; uint32_t big_cap;
+  struct BigSpan* big_spans; unsigned int* big_count; uint32_t big_cap; unsigned long long* span_bytes;
   // carry-in (known when pass C runs)
   Summ carry;
   uint64_t record_index_base;  // global index of this shard's first record (multi-GPU)
@@ -374,9 +374,7 @@ __global__ void __launch_bounds__(256) k_tile_prefix(DecodeParams P) {
   Summ pre = P.group_prefix[g];
   for (uint32_t t = g * P.tiles_per_group; t < tile; t++) pre = fold(pre, P.tile_summ[t]);
   P.tile_prefix[tile] = pre;
-  // per-segment exclusive prefixes inside the tile (in place)
-  const uint32_t s0 = tile * P.segs_per_tile, s1 = min(s0 + P.segs_per_tile, P.n_anchors);
-  for (uint32_t sgm = s0; sgm < s1; sgm++) { const Summ e = P.seg_summ[sgm]; P.seg_summ[sgm] = pre; pre = fold(pre, e); }
+
 }
 
 // ================================================================================================
@@ -554,8 +552,30 @@ __device__ __forceinline__ int32_t warp_incl_max(int32_t v, int lane) {
 __global__ void __launch_bounds__(256) k_frames(DecodeParams P) {
   const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t events = 0;
+  // exclusive prefix of this segment: carry ⊕ tile prefix ⊕ earlier segments of the tile.  A tile is
+  // exactly one warp of segments (segs_per_tile == 32), so the last part is a warp shuffle scan.
+  Summ st;
+  {
+    const int lane = threadIdx.x & 31;
+    Summ inc = seg < P.n_anchors ? P.seg_summ[seg] : summ_identity();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      Summ up;
+      up.lsn = __shfl_up_sync(0xffffffffu, inc.lsn, d); up.ord = __shfl_up_sync(0xffffffffu, inc.ord, d);
+      up.n_cells = __shfl_up_sync(0xffffffffu, inc.n_cells, d); up.heap = 0;
+      up.n_rec = __shfl_up_sync(0xffffffffu, inc.n_rec, d); up.flags = __shfl_up_sync(0xffffffffu, inc.flags, d);
+      if (lane >= d) inc = fold(up, inc);
+    }
+    Summ ex;
+    ex.lsn = __shfl_up_sync(0xffffffffu, inc.lsn, 1); ex.ord = __shfl_up_sync(0xffffffffu, inc.ord, 1);
+    ex.n_cells = __shfl_up_sync(0xffffffffu, inc.n_cells, 1); ex.heap = 0;
+    ex.n_rec = __shfl_up_sync(0xffffffffu, inc.n_rec, 1); ex.flags = __shfl_up_sync(0xffffffffu, inc.flags, 1);
+    if (lane == 0) ex = summ_identity();
+    const uint32_t tile = seg / 32u;
+    const Summ tp = tile < P.n_tiles ? P.tile_prefix[tile] : summ_identity();
+    st = fold(fold(P.carry, tp), ex);
+  }
   if (seg < P.n_anchors) {
-    Summ st = fold(P.carry, P.seg_summ[seg]);
     uint64_t pos = P.anchors[seg];
     const uint64_t stop = P.anchors[seg + 1];
     while (pos < stop) {
@@ -680,8 +700,17 @@ __global__ void __launch_bounds__(256) k_frames(DecodeParams P) {
 
 // ================================================================================================
 // pass C2: tuples.  Thread per DML record (event.rs:376-919 + text.rs:28-173).
+#ifndef ETL_WALK_STAGE
+#define ETL_WALK_STAGE 1
+#endif
+#ifndef ETL_WALK_CTAS
+#define ETL_WALK_CTAS 2
+#endif
+constexpr int kStageBytes = ETL_WALK_STAGE ? 272 : 0;   // per-record shared window: 17 x 16 bytes (covers a 256-byte frame head at any alignment)
 struct Wk {
   const uint8_t* base;   // frame start (global)
+  const uint8_t* sbase;  // the same bytes in the warp's shared staging area (frame-relative indexing)
+  uint32_t staged;       // frame-relative end of the staged bytes
   uint32_t pos, end;     // frame-relative: next byte to read / frame end
   uint32_t col_base, n_cols, n_ident;
   uint64_t cell0;        // first output cell of the record
@@ -694,17 +723,20 @@ struct Wk {
                          // i.e. a parser error in the reference, outranks every conversion error)
 };
 enum : uint32_t { W_OLD_HDR = 0, W_OLD_CELLS = 1, W_NEW_HDR = 2, W_NEW_CELLS = 3, W_DONE = 4 };
-struct TextCell { const uint8_t* v; uint32_t len, kind, seq; uint64_t dest; };
+struct TextCell { const uint8_t* v; uint32_t len, kind, seq; uint64_t dest; uint64_t soff; };
 #define W_DATA_ERROR(seq_, code_) do { report_error(P, P.record_index_base + w.rec_local, (seq_), (code_)); w.emit = false; } while (0)
 #define W_MALFORMED() do { report_error(P, P.record_index_base + w.rec_local, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); w.stage = W_DONE; } while (0)
 
+__device__ __forceinline__ const uint8_t* wk_ptr(const Wk& w, uint32_t off, uint32_t span) {
+  return ((uint64_t)off + span <= w.staged) ? w.sbase + off : w.base + off;
+}
 // one step: a tuple header or ONE wire cell. Returns true when a text cell must be parsed (tc filled).
 __device__ __forceinline__ bool wk_step(const DecodeParams& P, Wk& w, TextCell& tc) {
   do {
     if (w.stage == W_OLD_HDR || w.stage == W_NEW_HDR) {
       const bool is_new = w.stage == W_NEW_HDR;
       if ((uint64_t)w.pos + (is_new ? 3u : 2u) > w.end) { W_MALFORMED(); break; }
-      const uint64_t x = ld64u(w.base + w.pos);
+      const uint64_t x = ld64u(wk_ptr(w, w.pos, 12));
       uint32_t hdr = (uint32_t)x;
       if (is_new) {
         if ((hdr & 0xFFu) != 'N') { W_MALFORMED(); break; }
@@ -738,7 +770,7 @@ __device__ __forceinline__ bool wk_step(const DecodeParams& P, Wk& w, TextCell& 
       break;
     }
     if (w.pos >= w.end) { W_MALFORMED(); break; }
-    const uint64_t x = ld64u(w.base + w.pos);
+    const uint64_t x = ld64u(wk_ptr(w, w.pos, 12));
     const uint32_t tag = (uint32_t)(x & 0xFFu);
     const uint32_t len = bswap32((uint32_t)(x >> 8));
     const uint32_t voff = w.pos + 5u;
@@ -766,7 +798,8 @@ __device__ __forceinline__ bool wk_step(const DecodeParams& P, Wk& w, TextCell& 
     const bool resolver_key = is_new && w.kind == 'U' && w.old_tag == 'K' && (cflags & 2);
     if (tag == 't') {
       if (resolver_key) w.key_i++;
-      tc.v = w.base + voff; tc.len = len; tc.kind = P.col_kind[w.col_base + col]; tc.seq = seq; tc.dest = dest;
+      tc.v = wk_ptr(w, voff, len + 16u); tc.len = len; tc.kind = P.col_kind[w.col_base + col]; tc.seq = seq; tc.dest = dest;
+      tc.soff = (uint64_t)(w.base - P.buf) + voff;
       return true;
     }
     if (tag == 'n') {                               // convert_tuple_data_to_cell event.rs:941-957
@@ -792,6 +825,7 @@ __device__ __forceinline__ bool wk_step(const DecodeParams& P, Wk& w, TextCell& 
 }
 
 struct WalkShared {
+  alignas(16) uint8_t stage[ETL_WALK_STAGE ? kWalkThreads * (kStageBytes + 16) : 16];
   uint32_t dict_key[64];
   uint32_t dict_cnt[64];
   uint32_t dict_start[64];
@@ -799,8 +833,9 @@ struct WalkShared {
   uint32_t order[kWalkThreads];
 };
 
-__global__ void __launch_bounds__(kWalkThreads, 2) k_walk(DecodeParams P) {
-  __shared__ WalkShared sh;
+__global__ void __launch_bounds__(kWalkThreads, ETL_WALK_CTAS) k_walk(DecodeParams P) {
+  extern __shared__ __align__(16) uint8_t walk_smem[];
+  WalkShared& sh = *reinterpret_cast<WalkShared*>(walk_smem);
   const int lane = threadIdx.x & 31;
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   // ---- 1. group the CTA's records by frame shape so that warps walk look-alike tuples
@@ -840,13 +875,15 @@ __global__ void __launch_bounds__(kWalkThreads, 2) k_walk(DecodeParams P) {
   const uint32_t n_dml = sh.n_keys;
   // ---- 2. thread t walks the t-th record of the grouped order
   Wk w;
-  w.stage = W_DONE; w.tb = 0; w.partial = false; w.kind = 0; w.rec_local = 0;
+  w.stage = W_DONE; w.tb = 0; w.partial = false; w.kind = 0; w.rec_local = 0; w.base = nullptr; w.sbase = nullptr; w.staged = 0;
+  uint32_t my_flen = 0;
   if (threadIdx.x < n_dml) {
     const uint64_t rr = (uint64_t)blockIdx.x * blockDim.x + sh.order[threadIdx.x];
     const uint64_t off = P.rec_off[rr];
     const uint8_t* fp = P.buf + off;
     const DevSchema& s = P.schemas[P.schema_by_batch[P.rec_schema[rr]]];
     const uint32_t flen = bswap32((uint32_t)(ld64u(fp) >> 8));
+    my_flen = flen;
     w.base = fp; w.end = 1u + flen;
     w.col_base = s.col_base; w.n_cols = s.n_cols; w.n_ident = s.n_ident;
     w.cell0 = P.rec_cell_base[rr]; w.rec_local = (uint32_t)rr; w.emit = true;
@@ -858,19 +895,44 @@ __global__ void __launch_bounds__(kWalkThreads, 2) k_walk(DecodeParams P) {
     if (w.kind != 'I' && w.old_tag) { w.stage = W_OLD_HDR; w.pos = 36u; }   // old image first
     else { w.stage = W_NEW_HDR; w.pos = 35u; }                              // 'N' marker, then the new tuple
   }
+  // ---- 2b. each warp copies the first 256 bytes of its 32 frames into shared memory: 32 independent
+  //          coalesced 16-byte loads in flight per lane-row, then every hop / short value is an LDS
+  if (ETL_WALK_STAGE) {
+    const int wid = threadIdx.x >> 5;
+    uint8_t* wstage = sh.stage + (size_t)wid * 32 * (kStageBytes + 16);
+    const uint64_t my_base = reinterpret_cast<uint64_t>(w.base);
+#pragma unroll 4
+    for (int f = 0; f < 32; f++) {
+      const uint64_t b = __shfl_sync(0xffffffffu, my_base, f);
+      const uint32_t fl = __shfl_sync(0xffffffffu, my_flen, f);
+      if (b && lane < kStageBytes / 16) {
+        const uint64_t a = b & ~15ull;
+        // never read past the end of the stream buffer (+64 bytes of padding are guaranteed)
+        if (a + (uint64_t)lane * 16 < reinterpret_cast<uint64_t>(P.buf) + P.len + 48)
+          reinterpret_cast<uint4*>(wstage + (size_t)f * (kStageBytes + 16))[lane] = reinterpret_cast<const uint4*>(a)[lane];
+      }
+      (void)fl;
+    }
+    __syncwarp();
+    if (w.base) {
+      const uint32_t lead = (uint32_t)(my_base & 15ull);
+      w.sbase = wstage + (size_t)lane * (kStageBytes + 16) + lead;
+      w.staged = min((uint32_t)kStageBytes - lead, 1u + my_flen);
+    }
+  }
   // warp-synchronous stepping: all lanes take one step (header or cell) per iteration
   for (;;) {
     const bool act = w.stage != W_DONE;
     if (!__any_sync(0xffffffffu, act)) break;
     TextCell tc;
-    tc.v = nullptr; tc.len = 0; tc.kind = 0; tc.seq = 0; tc.dest = 0;
+    tc.v = nullptr; tc.len = 0; tc.kind = 0; tc.seq = 0; tc.dest = 0; tc.soff = 0;
     const bool is_text = act && wk_step(P, w, tc);
     // ---- text cell: UTF-8 (event.rs:972) then the per-kind parser (text.rs:28-173)
     CellOut o;
     o.tag = 0; o.val = 0; o.aux = 0;
     uint32_t code = 0;
     bool do_parse = false;
-    const uint64_t soff = (uint64_t)(tc.v - P.buf);
+    const uint64_t soff = tc.soff;
     if (is_text) {
       if (tc.kind == ETL_K_STRING) {
         o.tag = ETL_CELL_STRING; o.val = soff; o.aux = tc.len;
@@ -878,6 +940,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2) k_walk(DecodeParams P) {
           const uint32_t pieces = (tc.len + (256u << 10) - 1u) / (256u << 10);
           const uint32_t at = atomicAdd(P.big_count, pieces);
           if (at + pieces <= P.big_cap) {
+            atomicAdd(P.span_bytes, (unsigned long long)tc.len);
             for (uint32_t k = 0; k < pieces; k++) {
               BigSpan sp;
               sp.cell_off = soff; sp.span_off = soff + (uint64_t)k * (256u << 10);

@@ -54,7 +54,7 @@ _lib = None
 def _walgen():
     global _lib
     if _lib is None:
-        L = C.CDLL(_build.build_walgen())
+        L = C.CDLL(_build.WALGEN_LIB if os.path.exists(_build.WALGEN_LIB) else _build.build_walgen())
         L.wg_generate_segment.argtypes = [C.POINTER(_Cfg), C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(_Stats)]
         L.wg_generate_segment.restype = C.c_uint64
         _lib = L

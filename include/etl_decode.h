@@ -311,10 +311,13 @@ typedef struct etl_dec_summary {
   uint32_t gpu_launches;  /* kernels launched for this batch */
   float kernel_ms;        /* CUDA-event time of the kernel sequence (resident input → resident output) */
   float h2d_ms, d2h_ms;
-  float index_ms;         /* k_index + k_scan */
-  float emit_ms;          /* k_emit (the dominant kernel) */
-  uint32_t _pad[3];
+  float index_ms;         /* pass A+B: k_index + k_scan + k_tile_prefix */
+  float emit_ms;          /* pass C: k_frames + k_walk + k_utf8_spans */
+  float frames_ms;        /* k_frames */
+  float walk_ms;          /* k_walk */
+  float spans_ms;         /* k_utf8_spans */
   uint64_t h2d_bytes, d2h_bytes; /* bytes copied host→device / device→host for this batch */
+  uint64_t span_bytes;    /* bytes of TOAST-sized text handed to k_utf8_spans (its algorithmic bytes) */
 } etl_dec_summary;
 
 int etl_dec_batch_planes(const etl_dec_batch*, int host, etl_dec_planes* out);

@@ -71,7 +71,8 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        build()
+        if not os.path.exists(_LIB_PATH):
+            build()
         L = C.CDLL(_LIB_PATH)
         L.orc_create.restype = C.c_void_p
         L.orc_destroy.argtypes = [C.c_void_p]
