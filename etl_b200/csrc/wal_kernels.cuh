@@ -701,10 +701,10 @@ __global__ void __launch_bounds__(256) k_frames(DecodeParams P) {
 // ================================================================================================
 // pass C2: tuples.  Thread per DML record (event.rs:376-919 + text.rs:28-173).
 #ifndef ETL_WALK_STAGE
-#define ETL_WALK_STAGE 1
+#define ETL_WALK_STAGE 0
 #endif
 #ifndef ETL_WALK_CTAS
-#define ETL_WALK_CTAS 2
+#define ETL_WALK_CTAS 4
 #endif
 constexpr int kStageBytes = ETL_WALK_STAGE ? 272 : 0;   // per-record shared window: 17 x 16 bytes (covers a 256-byte frame head at any alignment)
 struct Wk {
