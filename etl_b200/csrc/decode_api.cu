@@ -90,7 +90,7 @@ bool kind_supported_on_device(uint32_t k) {
   switch (k) {
     case ETL_K_BOOL: case ETL_K_STRING: case ETL_K_I16: case ETL_K_I32: case ETL_K_U32: case ETL_K_I64:
     case ETL_K_NUMERIC: case ETL_K_DATE: case ETL_K_TIME: case ETL_K_TIMESTAMP: case ETL_K_TIMESTAMPTZ:
-    case ETL_K_UUID: case ETL_K_JSON: case ETL_K_BYTES:
+    case ETL_K_UUID: case ETL_K_JSON: case ETL_K_BYTES: case ETL_K_F32: case ETL_K_F64:
       return true;
     default: return false;
   }
@@ -160,6 +160,8 @@ struct etl_stager {
   uint32_t stride = 2048;
   std::vector<uint64_t> anchors;
   std::vector<uint64_t> relations;
+  size_t n_real_anchors = 0;   // anchors.size() before etl_stage_view padded the tail with `len`
+  bool padded = false;
 };
 
 struct etl_dec_batch {
@@ -245,10 +247,11 @@ void etl_stage_destroy(etl_stager* s) {
   if (s->cap >> 63) free(s->buf); else cudaFreeHost(s->buf);
   delete s;
 }
-void etl_stage_reset(etl_stager* s) { s->len = 0; s->anchors.clear(); s->relations.clear(); }
+void etl_stage_reset(etl_stager* s) { s->len = 0; s->anchors.clear(); s->relations.clear(); s->padded = false; s->n_real_anchors = 0; }
 
 static inline void stage_note_frame(etl_stager* s, uint64_t off, const uint8_t* body, uint32_t body_len) {
   // anchors[k] = first frame starting at or after k*stride
+  if (s->padded) { s->anchors.resize(s->n_real_anchors); s->padded = false; }
   while ((uint64_t)s->anchors.size() * s->stride <= off) s->anchors.push_back(off);
   if (body_len >= 26 && body[0] == 'w' && body[25] == 'R') s->relations.push_back(off);
 }
@@ -280,7 +283,13 @@ int etl_stage_append_framed(etl_stager* s, const uint8_t* framed, uint64_t len) 
   s->len += len;
   return pos == len ? ETL_OK : ETL_ERR_INVALID_ARG;
 }
-int etl_stage_view(const etl_stager* s, etl_dec_input* out) {
+int etl_stage_view(const etl_stager* cs, etl_dec_input* out) {
+  etl_stager* s = const_cast<etl_stager*>(cs);
+  // blocks k*stride past the last frame start have no frame: anchors[k] = len
+  if (!s->padded) { s->n_real_anchors = s->anchors.size(); s->padded = true; }
+  s->anchors.resize(s->n_real_anchors);
+  const uint64_t want = s->len ? (s->len + s->stride - 1) / s->stride : 0;
+  while (s->anchors.size() < want) s->anchors.push_back(s->len);
   memset(out, 0, sizeof *out);
   out->host_buf = s->buf;
   out->len = s->len;
@@ -466,7 +475,7 @@ int etl_dec_decode_begin(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t fla
     for (uint8_t k : v.kind)
       if (!kind_supported_on_device(k)) {
         char msg[160];
-        snprintf(msg, sizeof msg, "table %u: column decode class 0x%x (float / array) has no device parser yet; refusing to decode", v.table_id, k);
+        snprintf(msg, sizeof msg, "table %u: column decode class 0x%x (array types) has no device parser yet; refusing to decode", v.table_id, k);
         ctx->last_error = msg;
         return ETL_ERR_INVALID_ARG;
       }

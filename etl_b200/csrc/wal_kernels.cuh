@@ -21,6 +21,7 @@
 #include <stdint.h>
 
 #include "cell_parsers.cuh"
+#include "float_parse.cuh"
 
 namespace etl {
 
@@ -473,6 +474,8 @@ __device__ __forceinline__ uint32_t parse_text_cell(uint32_t kind, const uint8_t
     }
     case ETL_K_UUID: return parse_uuid(s, n, hc, o);
     case ETL_K_BYTES: return parse_bytea(s, n, hc, o);
+    case ETL_K_F32: return parse_float(s, n, true, o);
+    case ETL_K_F64: return parse_float(s, n, false, o);
     default: return ETL_E_MALFORMED_FRAME;  // unsupported decode class: rejected on the host before launch
   }
 }

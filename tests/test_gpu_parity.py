@@ -61,8 +61,6 @@ def test_error_scenarios_on_gpu(gpu, oracle_mod, name, tables, w, expected):
 @pytest.mark.parametrize("name,scale", [("c1", 1.0), ("c2", 0.05), ("c3", 0.01), ("c4", 0.004), ("c5", 0.003)])
 @pytest.mark.parametrize("stride", [2048, 512, 16384])
 def test_workload_parity(gpu, oracle_mod, name, scale, stride):
-    if name == "c4":
-        pytest.skip("c4 carries float8 columns: device float parser lands with the next kernel wave")
     w = wl.make(name, scale)
     stream, stats = w.generate()
     got, want = both(gpu, oracle_mod, w.table_schemas(), stream, stride=stride)
@@ -156,3 +154,97 @@ def test_big_cells_and_oversize_frames(gpu, oracle_mod):
     got, want = both(gpu, oracle_mod, {90: cols}, bad)
     assert want.first_error[0] == rec and want.first_error[2] == 1
     assert_planes_equal(got, want, bad)
+
+
+def test_two_phase_shards_with_seam_fold(gpu, oracle_mod):
+    """The multi-GPU protocol on one device: every shard runs decode_begin (index + scan → seam
+    summary), the summaries are folded exactly as after the all-gather, decode_finish gets the carry.
+    Cuts are in the middle of transactions; the concatenated result must equal the oracle's."""
+    from etl_b200 import sharding
+    from etl_b200.decoder import Stager
+    w = wl.make("c2", 0.02, n_segments=1)
+    stream, _ = w.generate()
+    raw = stream.tobytes()
+    orc = oracle_mod.Oracle()
+    for tid, cols in w.table_schemas().items():
+        orc.put_table_schema(tid, cols)
+    full = orc.decode(raw)
+    kinds = [chr(k) for k in full.rec_kind]
+    cuts_rec = [next(i for i in range(full.n_records * f // 3, full.n_records) if kinds[i] in "IUD" and kinds[i - 1] in "IUD") for f in (1, 2)]
+    cuts = [0] + [int(full.rec_off[i]) for i in cuts_rec] + [len(raw)]
+    dec = gpu.Decoder(0)
+    for tid, cols in w.table_schemas().items():
+        dec.put_table_schema(tid, cols)
+    seams, parts = [], []
+    state, base = (0, 0, 0), 0
+    for k in range(3):
+        shard = raw[cuts[k]:cuts[k + 1]]
+        st = Stager(len(shard), 2048)
+        st.append_framed(shard)
+        inp = st.view()
+        seam = dec.decode_begin(inp, to_host=True)
+        words = sharding.seam_to_words(seam)
+        with dec.decode_finish(state, base) as bh:
+            parts.append(bh.to_host())
+        seams.append(words)
+        state = sharding.fold_state(state, words)
+        base += int(words[0])
+        st.close()
+    dec.close()
+    assert base == full.n_records
+    assert all(p.first_error[0] is None for p in parts)
+    ordinals = np.concatenate([p.rec_tx_ordinal for p in parts])
+    commits = np.concatenate([p.rec_commit_lsn for p in parts])
+    assert np.array_equal(ordinals, full.rec_tx_ordinal) and np.array_equal(commits, full.rec_commit_lsn)
+    assert np.array_equal(np.concatenate([p.cell_val for p in parts])[~np.isin(np.concatenate([p.cell_tag for p in parts]), (2, 15))],
+                          full.cell_val[~np.isin(full.cell_tag, (2, 15))])
+    assert parts[-1].carry_out == full.carry_out
+    # a data error in a later shard reports its GLOBAL record index
+
+
+FLOAT_CASES = ["0", "-0", "1", "3.15", "-2.818", "inf", "-Infinity", "NaN", "-nan", "3.4028235e38", "-3.4028235e38",
+               "1.7976931348623157e308", "1e999", "1e-999", "4.9406564584124654e-324", "2.4703282292062327e-324",
+               "2.4703282292062328e-324", "2.2250738585072011e-308", "2.2250738585072014e-308", "9007199254740993",
+               "9007199254740992.99999999999999999", "16777217", "16777216.000000000000000000000001",
+               "1.00000017881393432617187499", "1.00000017881393432617187501", "0.1", "0.30000000000000004", "1e23",
+               "8.41e21", "123456789012345678901234567890", "0.000000000000000000000000000000000000000000001",
+               "1.", ".5", "+1e3", "1E-2", "5e-324", "1e308", "1.8e308", "7.038531e-26", "1.17549435e-38",
+               "1.401298464324817e-45", "7.006492321624085e-46", "7.006492321624086e-46",
+               "340282356779733661637539395458142568448", "179769313486231580793728971405303415079934132710037826936173778980444968292764750946649017977587207096330286416692887910946555547851940402630657488671505820681908902000708383676273854845817711531764475730270069855571366959622842914819860834936475292719074168444365510704342711559699508093042880177904174497792",
+               "", ".", "e5", "1e", "1e+", " 1", "1 ", "+", "-", "1_0", "0x1p3", "infinit", "nan(1)", "1.2.3"]
+
+
+def test_float_parity(gpu, oracle_mod):
+    """float4 / float8 (text.rs:61-68): every value alone in its own stream so that invalid spellings
+    (→ first_error) and valid ones are both compared with the oracle (glibc strtod/strtof, correctly rounded)."""
+    cols = [sc.col("id", sc.INT8, 1), sc.col("f8", sc.FLOAT8, None, True), sc.col("f4", 700, None, True)]
+    rel = pg.relation(91, "public", "floats", "d", sc.rel_cols(cols, {"id"}))
+    rng = np.random.default_rng(11)
+    cases = list(FLOAT_CASES)
+    for _ in range(300):
+        mant = "".join(str(d) for d in rng.integers(0, 10, size=int(rng.integers(1, 30))))
+        cases.append(f"{mant[:1]}.{mant[1:]}e{int(rng.integers(-330, 320))}")
+        cases.append(repr(float(rng.standard_normal() * 10.0 ** int(rng.integers(-30, 30)))))
+    # valid values: one big stream
+    w = pg.StreamWriter()
+    tx = sc.Tx(w)
+    tx.begin()
+    w.emit(rel)
+    valid = [c for c in cases if oracle_mod.parse_cell(701, c.encode())[0] == 0]
+    for i, c in enumerate(valid):
+        w.emit(pg.insert(91, [str(i), c, c]))
+    tx.commit()
+    stream = w.bytes()
+    got, want = both(gpu, oracle_mod, {91: cols}, stream)
+    assert want.first_error[0] is None and len(valid) > 600
+    assert_planes_equal(got, want, stream)
+    for c in [c for c in cases if c not in valid]:
+        w = pg.StreamWriter()
+        tx = sc.Tx(w)
+        tx.begin()
+        w.emit(rel)
+        w.emit(pg.insert(91, ["1", c, None]))
+        tx.commit()
+        got, want = both(gpu, oracle_mod, {91: cols}, w.bytes())
+        assert want.first_error[2] == 3, c
+        assert got.first_error == want.first_error, c
