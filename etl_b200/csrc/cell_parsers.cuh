@@ -660,7 +660,8 @@ __device__ __forceinline__ bool fast_timestamp(const uint8_t* s, uint32_t n, Cel
 
 // numeric: [+-]digits[.digits] (what Postgres emits) with warp-synchronous loops; everything else
 // (NaN, Infinity, exponents, '_' separators, whitespace) goes to parse_numeric.
-__device__ __forceinline__ uint32_t parse_numeric_sync(unsigned mask, const uint8_t* s, uint32_t n, HeapCursor& hc, CellOut& o) {
+__device__ __forceinline__ uint32_t parse_numeric_sync(unsigned mask, const uint8_t* s, uint32_t n, uint8_t* heap, uint64_t hpos, CellOut& o) {
+  HeapCursor hc{heap, hpos};
   bool simple = n > 0 && n <= 4096;
   uint32_t i0 = 0;
   bool neg = false;
@@ -725,7 +726,12 @@ __device__ __forceinline__ uint32_t parse_numeric_sync(unsigned mask, const uint
     *reinterpret_cast<etl_numeric_hdr*>(hc.heap + off) = hdr;
     o.tag = ETL_CELL_NUMERIC; o.val = off; o.aux = nd;
   }
-  if (code == 0xFFFFFFFFu) code = parse_numeric(s, n, hc, o);
+  if (code == 0xFFFFFFFFu) {                          // own copies: `o` must not have its address taken (see k_walk)
+    HeapCursor h2{heap, hpos};
+    CellOut t; t.tag = 0; t.val = 0; t.aux = 0;
+    code = parse_numeric(s, n, h2, t);
+    o = t;
+  }
   return code;
 }
 

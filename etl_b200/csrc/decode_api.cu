@@ -87,6 +87,7 @@ uint32_t kind_for_oid(uint32_t oid) {
   return ETL_K_STRING;
 }
 bool kind_supported_on_device(uint32_t k) {
+  if (k & ETL_K_ARRAY) k &= ~(uint32_t)ETL_K_ARRAY;   // arrays: element kinds below
   switch (k) {
     case ETL_K_BOOL: case ETL_K_STRING: case ETL_K_I16: case ETL_K_I32: case ETL_K_U32: case ETL_K_I64:
     case ETL_K_NUMERIC: case ETL_K_DATE: case ETL_K_TIME: case ETL_K_TIMESTAMP: case ETL_K_TIMESTAMPTZ:
@@ -603,19 +604,17 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
   b->schemas = std::move(ctx->pending_schemas);
 
   // ---- one device block for all planes
-  bool any_heap = false;
-  for (const RelVersion& v : b->schemas) for (uint8_t k : v.kind) any_heap = any_heap || kind_has_heap(k);
-  // upper bound on Σ cell_heap_bound: numeric ≤ n/2+19, bytea ≤ n/2+7, uuid = 16 per decoded text cell
-  const uint64_t nr = T.n_rec, nc = T.n_cells, nh = any_heap ? (P.len / 2 + 24 * T.n_cells + 256) : 0;
+  bool any_heap = false, any_array = false;
+  for (const RelVersion& v : b->schemas) for (uint8_t k : v.kind) { any_heap = any_heap || kind_has_heap(k); any_array = any_array || (k & ETL_K_ARRAY); }
+  // upper bound on Σ cell_heap_bound: numeric ≤ n/2+19, bytea ≤ n/2+7, uuid = 16 per decoded text cell.
+  // Arrays reserve 16 + 44·n_elems + 1.5·len per cell: first guess 3·len, retried ×4 on overflow (≤ 48·len).
+  const uint64_t nr = T.n_rec, nc = T.n_cells;
+  uint64_t nh = any_heap ? (P.len / 2 + 24 * T.n_cells + 256) : 0;
+  nh = (nh + 15) & ~15ull;
+  const uint64_t scalar_heap = nh;
+  if (any_array) nh += 3 * P.len + 4096;
   auto al = [](uint64_t x) { return (x + 255) & ~255ull; };
-  uint64_t cur = 0;
-  auto take = [&](uint64_t bytes) { uint64_t o = cur; cur += al(bytes); return o; };
-  const uint64_t f_rec_off = take(nr * 8), f_kind = take(nr), f_flags = take(nr), f_rel = take(nr * 4), f_schema = take(nr * 4),
-                 f_start = take(nr * 8), f_commit = take(nr * 8), f_ord = take(nr * 8), f_cbase = take((nr + 1) * 8),
-                 f_tag = take(nc), f_val = take(nc * 8), f_aux = take(nc * 4), f_heap = take(nh);
-  b->block_bytes = cur ? cur : 256;
-  CK(cudaMallocAsync(&b->dev_block, b->block_bytes, st));
-  uint8_t* base = (uint8_t*)b->dev_block;
+  uint64_t f_rec_off, f_kind, f_flags, f_rel, f_schema, f_start, f_commit, f_ord, f_cbase, f_tag, f_val, f_aux, f_heap;
   auto fill = [&](etl_dec_planes& pl, uint8_t* bs) {
     pl.n_records = nr; pl.n_cells = nc; pl.heap_bytes = nh;
     pl.rec_off = (uint64_t*)(bs + f_rec_off); pl.rec_kind = bs + f_kind; pl.rec_flags = bs + f_flags;
@@ -623,13 +622,6 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
     pl.rec_commit_lsn = (uint64_t*)(bs + f_commit); pl.rec_tx_ordinal = (uint64_t*)(bs + f_ord); pl.rec_cell_base = (uint64_t*)(bs + f_cbase);
     pl.cell_tag = bs + f_tag; pl.cell_val = (uint64_t*)(bs + f_val); pl.cell_aux = (uint32_t*)(bs + f_aux); pl.heap = bs + f_heap;
   };
-  fill(b->dev, base);
-  P.rec_off = (uint64_t*)b->dev.rec_off; P.rec_kind = (uint8_t*)b->dev.rec_kind; P.rec_flags = (uint8_t*)b->dev.rec_flags;
-  P.rec_rel = (uint32_t*)b->dev.rec_rel; P.rec_schema = (int32_t*)b->dev.rec_schema; P.rec_start_lsn = (uint64_t*)b->dev.rec_start_lsn;
-  P.rec_commit_lsn = (uint64_t*)b->dev.rec_commit_lsn; P.rec_tx_ordinal = (uint64_t*)b->dev.rec_tx_ordinal;
-  P.rec_cell_base = (uint64_t*)b->dev.rec_cell_base; P.cell_tag = (uint8_t*)b->dev.cell_tag; P.cell_val = (uint64_t*)b->dev.cell_val;
-  P.cell_aux = (uint32_t*)b->dev.cell_aux; P.heap = (uint8_t*)b->dev.heap;
-  P.heap_top = ctx->d_scalars.p + 5; P.heap_cap = nh;
   P.record_index_base = record_index_base;
   Summ carry = summ_identity();
   etl_stream_state cin{};
@@ -637,35 +629,57 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
   if (cin.in_tx) { carry.flags = S_HAS_B; carry.lsn = cin.final_lsn; }
   carry.ord = cin.next_tx_ordinal;
   P.carry = carry;
-
-  // ---- pass C
-  ctx->h_scalars[0] = ~0ull; ctx->h_scalars[1] = ctx->h_scalars[2] = ctx->h_scalars[3] = ctx->h_scalars[4] = ctx->h_scalars[5] = ctx->h_scalars[6] = ctx->h_scalars[7] = ctx->h_scalars[8] = 0;
-  CK(cudaMemcpyAsync(ctx->d_scalars.p, ctx->h_scalars, 9 * 8, cudaMemcpyHostToDevice, st));
   P.phase_cycles = nullptr;
-  if (getenv("ETL_PHASE_TIMING")) {
-    CK(ctx->d_phase.ensure(16));
-    CK(cudaMemsetAsync(ctx->d_phase.p, 0, 16 * 8, st));
-    P.phase_cycles = ctx->d_phase.p;
+  uint64_t heap_used = 0;
+  for (int attempt = 0;; attempt++) {
+    uint64_t cur = 0;
+    auto take = [&](uint64_t bytes) { uint64_t o = cur; cur += al(bytes); return o; };
+    f_rec_off = take(nr * 8); f_kind = take(nr); f_flags = take(nr); f_rel = take(nr * 4); f_schema = take(nr * 4);
+    f_start = take(nr * 8); f_commit = take(nr * 8); f_ord = take(nr * 8); f_cbase = take((nr + 1) * 8);
+    f_tag = take(nc); f_val = take(nc * 8); f_aux = take(nc * 4); f_heap = take(nh);
+    b->block_bytes = cur ? cur : 256;
+    CK(cudaMallocAsync(&b->dev_block, b->block_bytes, st));
+    fill(b->dev, (uint8_t*)b->dev_block);
+    P.rec_off = (uint64_t*)b->dev.rec_off; P.rec_kind = (uint8_t*)b->dev.rec_kind; P.rec_flags = (uint8_t*)b->dev.rec_flags;
+    P.rec_rel = (uint32_t*)b->dev.rec_rel; P.rec_schema = (int32_t*)b->dev.rec_schema; P.rec_start_lsn = (uint64_t*)b->dev.rec_start_lsn;
+    P.rec_commit_lsn = (uint64_t*)b->dev.rec_commit_lsn; P.rec_tx_ordinal = (uint64_t*)b->dev.rec_tx_ordinal;
+    P.rec_cell_base = (uint64_t*)b->dev.rec_cell_base; P.cell_tag = (uint8_t*)b->dev.cell_tag; P.cell_val = (uint64_t*)b->dev.cell_val;
+    P.cell_aux = (uint32_t*)b->dev.cell_aux; P.heap = (uint8_t*)b->dev.heap;
+    P.heap_top = ctx->d_scalars.p + 5; P.heap_cap = nh;
+    P.heap_overflow = (unsigned int*)(ctx->d_scalars.p + 9);
+    P.arr_top = ctx->d_scalars.p + 10; P.arr_base = scalar_heap;
+
+    // ---- pass C
+    ctx->h_scalars[0] = ~0ull;
+    for (int i = 1; i < 11; i++) ctx->h_scalars[i] = 0;
+    CK(cudaMemcpyAsync(ctx->d_scalars.p, ctx->h_scalars, 11 * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev[3], st));
+    if (P.n_tiles) {
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+      P.n_records = nr;
+      k_frames<<<(P.n_anchors + 255) / 256, 256, 0, st>>>(P);
+      cudaEventRecord(ctx->evk[0], st);
+      if (nr) k_walk<<<(uint32_t)((nr + kWalkThreads - 1) / kWalkThreads), kWalkThreads, sizeof(WalkShared), st>>>(P);
+      cudaEventRecord(ctx->evk[1], st);
+      k_utf8_spans<<<sms * 6, 256, 0, st>>>(P);
+      cudaEventRecord(ctx->evk[2], st);
+      ctx->launches += nr ? 3 : 2;
+      CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync((void*)(b->dev.rec_cell_base + nr), &ctx->h_total->n_cells, 8, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev[4], st));
+    CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars.p, 11 * 8, cudaMemcpyDeviceToHost, st));
+    heap_used = nh;
+    if (!nh) break;
+    CK(cudaStreamSynchronize(st));
+    heap_used = std::min<uint64_t>(nh, ctx->h_scalars[10] ? scalar_heap + ctx->h_scalars[10] : ctx->h_scalars[5]);
+    if (!ctx->h_scalars[9]) break;
+    if (attempt >= 3) { ctx->last_error = "array heap reservation overflow after retries"; cudaFreeAsync(b->dev_block, st); delete b; return ETL_ERR_CUDA; }
+    CK(cudaFreeAsync(b->dev_block, st));
+    b->dev_block = nullptr;
+    nh = scalar_heap + (nh - scalar_heap) * 4;
   }
-  CK(cudaEventRecord(ctx->ev[3], st));
-  if (P.n_tiles) {
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    P.n_records = nr;
-    k_frames<<<(P.n_anchors + 255) / 256, 256, 0, st>>>(P);
-    cudaEventRecord(ctx->evk[0], st);
-    if (nr) k_walk<<<(uint32_t)((nr + kWalkThreads - 1) / kWalkThreads), kWalkThreads, sizeof(WalkShared), st>>>(P);
-    cudaEventRecord(ctx->evk[1], st);
-    k_utf8_spans<<<sms * 6, 256, 0, st>>>(P);
-    cudaEventRecord(ctx->evk[2], st);
-    ctx->launches += nr ? 3 : 2;
-    CK(cudaGetLastError());
-  }
-  CK(cudaMemcpyAsync((void*)(b->dev.rec_cell_base + nr), &ctx->h_total->n_cells, 8, cudaMemcpyHostToDevice, st));
-  CK(cudaEventRecord(ctx->ev[4], st));
-  CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars.p, 9 * 8, cudaMemcpyDeviceToHost, st));
-  uint64_t heap_used = nh;
-  if (nh) { CK(cudaStreamSynchronize(st)); heap_used = std::min<uint64_t>(nh, ctx->h_scalars[5]); }
   const uint64_t copy_bytes = f_heap + heap_used;
   b->dev.heap_bytes = heap_used;
   if (ctx->pending_flags & ETL_DECODE_RESULTS_TO_HOST) {
@@ -685,14 +699,6 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
   CK(cudaEventRecord(ctx->ev[5], st));
   CK(cudaStreamSynchronize(st));
 
-  if (P.phase_cycles) {
-    cudaMemcpy(ctx->h_phase, ctx->d_phase.p, 16 * 8, cudaMemcpyDeviceToHost);
-    unsigned long long tot = 0;
-    for (int i = 0; i < 13; i++) tot += ctx->h_phase[i];
-    fprintf(stderr, "[etl phase cycles of thread 0, %% of %llu]:", tot);
-    for (int i = 0; i < 13; i++) fprintf(stderr, " p%d=%.1f", i, 100.0 * ctx->h_phase[i] / (tot ? tot : 1));
-    fprintf(stderr, "\n");
-  }
   // ---- summary
   etl_dec_summary& S = b->summary;
   memset(&S, 0, sizeof S);

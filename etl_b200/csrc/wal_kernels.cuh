@@ -117,7 +117,10 @@ struct DecodeParams {
   uint64_t* rec_start_lsn; uint64_t* rec_commit_lsn; uint64_t* rec_tx_ordinal; uint64_t* rec_cell_base;
   uint8_t* cell_tag; uint64_t* cell_val; uint32_t* cell_aux;
   uint8_t* heap;
-  unsigned long long* heap_top;     // bump pointer: rounds of the emit pass reserve their heap bytes here
+  unsigned long long* heap_top;     // bump pointer of the heap plane
+  unsigned long long* arr_top;      // bump pointer of the array region, relative to arr_base
+  uint64_t arr_base;
+  unsigned int* heap_overflow;      // set when an array reservation did not fit (host retries with a larger heap)
   uint64_t heap_cap;                // 0 when no schema of the batch has a heap-kind column
   unsigned long long* first_error;  // atomicMin key: rec_index << 24 | seq << 6 | code
   unsigned long long* metrics;      // [0] insert bytes [1] update bytes [2] delete bytes [3] events
@@ -435,8 +438,8 @@ __device__ __forceinline__ bool utf8_valid_fast(const uint8_t* s, uint32_t n) {
 
 // text.rs:28-173 dispatch for one text cell (bytes already UTF-8 validated). `soff` = absolute
 // stream offset of the value bytes.
-__device__ __forceinline__ uint32_t parse_text_cell(uint32_t kind, const uint8_t* s, uint32_t n, uint64_t soff,
-                                                    HeapCursor& hc, CellOut& o) {
+__device__ __forceinline__ uint32_t parse_text_cell_impl(uint32_t kind, const uint8_t* s, uint32_t n, uint64_t soff,
+                                                         HeapCursor& hc, CellOut& o) {
   o.aux = 0;
   int64_t iv;
   uint32_t e;
@@ -478,6 +481,95 @@ __device__ __forceinline__ uint32_t parse_text_cell(uint32_t kind, const uint8_t
     case ETL_K_F64: return parse_float(s, n, false, o);
     default: return ETL_E_MALFORMED_FRAME;  // unsupported decode class: rejected on the host before launch
   }
+}
+
+// out-of-line entry for k_walk's cold kinds: heap position by value, so the caller's state stays in registers
+__device__ __noinline__ uint32_t parse_text_cell(uint32_t kind, const uint8_t* s, uint32_t n, uint64_t soff, uint8_t* heap,
+                                                 uint64_t hpos, CellOut& o) {
+  HeapCursor hc{heap, hpos};
+  return parse_text_cell_impl(kind, s, n, soff, hc, o);
+}
+
+// ---- arrays (text.rs:184-249): one-dimensional split — `"` toggles quoting, `\` escapes the next
+// char, `,` splits outside quotes, an unquoted case-insensitive NULL is a null element.  Elements are
+// unescaped into the heap and parsed there with the exact scalar parsers.  Thread-serial: arrays are
+// off the named hot configurations; what matters is that accept/reject and every value match.
+// Returns 0xFFFFFFFE when the heap reservation does not fit (host retries with a larger heap).
+struct ArrHeap { uint8_t* heap; unsigned long long* arr_top; uint64_t arr_base, heap_cap; };
+__device__ __noinline__ uint32_t parse_array_cell(const ArrHeap P, uint32_t ekind, const uint8_t* s, uint32_t n,
+                                                  int tz_fmt /*0 n/a, 1 %#z, 2 %:z*/, CellOut& o) {
+  if (n < 2) return ETL_E_ARRAY_SHORT;
+  if (s[0] != '{' || s[n - 1] != '}') return ETL_E_ARRAY_BRACES;
+  const uint8_t* p = s + 1;
+  const uint32_t m = n - 2;
+  // pass 1: element count
+  uint32_t ne = 0;
+  {
+    bool in_q = false, in_e = false;
+    uint32_t commas = 0;
+    for (uint32_t i = 0; i < m; i++) {
+      const uint32_t ch = p[i];
+      if (in_e) { in_e = false; continue; }
+      if (ch == '"') in_q = !in_q;
+      else if (ch == '\\') in_e = true;
+      else if (ch == ',' && !in_q) commas++;
+    }
+    ne = m ? commas + 1 : 0;
+  }
+  const uint64_t need = 16ull + 44ull * ne + (uint64_t)m + m / 2u;   // hdr + elems + unescaped text + numeric/bytes payloads
+  // arrays bump-allocate in their own region [arr_base, heap_cap) so the scalar region's bound stays exact
+  const uint64_t base = P.arr_base + atomicAdd(P.arr_top, (unsigned long long)((need + 7ull) & ~7ull));
+  if (base + need > P.heap_cap) return 0xFFFFFFFEu;
+  etl_array_hdr hdr;
+  hdr.elem_kind = (uint8_t)ekind; hdr._pad[0] = hdr._pad[1] = hdr._pad[2] = 0; hdr.n_elems = ne;
+  *reinterpret_cast<etl_array_hdr*>(P.heap + base) = hdr;
+  etl_array_elem* elems = reinterpret_cast<etl_array_elem*>(P.heap + base + 8);
+  HeapCursor hc{P.heap, base + 8 + 16ull * ne};
+  // pass 2
+  bool in_q = false, in_e = false, quoted = false;
+  uint32_t i = 0, k = 0;
+  bool done = (m == 0);
+  uint32_t err = 0;
+  while (!done && !err) {
+    const uint64_t voff = hc.pos;
+    uint8_t* val = P.heap + voff;
+    uint32_t vl = 0;
+    for (;;) {
+      if (i >= m) { done = true; break; }
+      const uint32_t ch = p[i];
+      if (in_e) { val[vl++] = (uint8_t)ch; in_e = false; i++; continue; }
+      if (ch == '"') { if (!in_q) quoted = true; in_q = !in_q; i++; continue; }
+      if (ch == '\\') { in_e = true; i++; continue; }
+      if (ch == ',' && !in_q) { i++; break; }
+      val[vl++] = (uint8_t)ch; i++;
+    }
+    hc.pos += (vl + 7u) & ~7u;
+    etl_array_elem e;
+    e.val = 0; e.aux = 0; e.tag = ETL_CELL_NULL; e._pad[0] = e._pad[1] = e._pad[2] = 0;
+    if (!(!quoted && ieq(val, vl, "null", 4))) {
+      CellOut eo;
+      eo.val = 0; eo.aux = 0; eo.tag = 0;
+      if (ekind == ETL_K_STRING) { eo.tag = ETL_CELL_STRING; eo.val = voff; eo.aux = vl; }
+      else if (ekind == ETL_K_JSON) { if (json_valid(val, vl)) { eo.tag = ETL_CELL_JSON; eo.val = voff; eo.aux = vl; } else err = ETL_E_JSON; }
+      else if (ekind == ETL_K_TIMESTAMPTZ) { if (!parse_timestamptz_fmt(val, vl, tz_fmt == 1, eo)) err = ETL_E_DATETIME; }
+      else err = parse_text_cell_impl(ekind, val, vl, voff, hc, eo);
+      e.val = eo.val; e.aux = eo.aux; e.tag = (uint8_t)eo.tag;
+    }
+    if (!err && k < ne) elems[k++] = e;
+    quoted = false;
+  }
+  if (err) return err;
+  o.tag = ETL_CELL_ARRAY; o.val = base; o.aux = ne;
+  return 0;
+}
+__device__ __noinline__ uint32_t parse_array_any(const ArrHeap P, uint32_t kind, const uint8_t* s, uint32_t n, CellOut& o) {
+  const uint32_t ek = kind & ~(uint32_t)ETL_K_ARRAY;
+  if (ek == ETL_K_TIMESTAMPTZ) {                       // text.rs:117-140: whole-array retry with the second format
+    const uint32_t e = parse_array_cell(P, ek, s, n, 1, o);
+    if (e == 0 || e == 0xFFFFFFFEu) return e;
+    return parse_array_cell(P, ek, s, n, 2, o);
+  }
+  return parse_array_cell(P, ek, s, n, 0, o);
 }
 
 __device__ __forceinline__ void put_cell(const DecodeParams& P, uint64_t idx, uint32_t tag, uint64_t val, uint32_t aux) {
@@ -703,77 +795,77 @@ __global__ void __launch_bounds__(256) k_frames(DecodeParams P) {
 
 // ================================================================================================
 // pass C2: tuples.  Thread per DML record (event.rs:376-919 + text.rs:28-173).
-#ifndef ETL_WALK_STAGE
-#define ETL_WALK_STAGE 0
-#endif
 #ifndef ETL_WALK_CTAS
 #define ETL_WALK_CTAS 4
 #endif
-constexpr int kStageBytes = ETL_WALK_STAGE ? 272 : 0;   // per-record shared window: 17 x 16 bytes (covers a 256-byte frame head at any alignment)
+// Walker state, packed: k_walk is bound by live registers (a spilled field costs an LSU wavefront per
+// access, and the first ncu pass showed 60 % of all warp instructions were local loads/stores).
 struct Wk {
   const uint8_t* base;   // frame start (global)
-  const uint8_t* sbase;  // the same bytes in the warp's shared staging area (frame-relative indexing)
-  uint32_t staged;       // frame-relative end of the staged bytes
   uint32_t pos, end;     // frame-relative: next byte to read / frame end
-  uint32_t col_base, n_cols, n_ident;
+  uint32_t col_base;
+  uint32_t nc_ni;        // n_cols | n_ident << 16   (both ≤ 32767: int16 on the wire)
   uint64_t cell0;        // first output cell of the record
   uint32_t rec_local;
-  uint32_t remaining, wire_i, cmap, k_out, key_i, n_old;
-  uint32_t kind, old_tag, stage;
+  uint32_t rem_wire;     // remaining | wire_i << 16
+  uint32_t cmap_kout;    // cmap | k_out << 16
+  uint32_t keyi_nold;    // key_i | n_old << 16
+  uint32_t bits;         // stage[0:3) kind[3:5) old[5:7) dense[7] partial[8] emit[9]
   uint32_t tb;           // Σ text lengths (calculate_tuple_bytes event.rs:260-270)
-  bool dense, partial;
-  bool emit;             // false after the first data error: structure-only walk (a malformed frame,
-                         // i.e. a parser error in the reference, outranks every conversion error)
 };
 enum : uint32_t { W_OLD_HDR = 0, W_OLD_CELLS = 1, W_NEW_HDR = 2, W_NEW_CELLS = 3, W_DONE = 4 };
-struct TextCell { const uint8_t* v; uint32_t len, kind, seq; uint64_t dest; uint64_t soff; };
-#define W_DATA_ERROR(seq_, code_) do { report_error(P, P.record_index_base + w.rec_local, (seq_), (code_)); w.emit = false; } while (0)
-#define W_MALFORMED() do { report_error(P, P.record_index_base + w.rec_local, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); w.stage = W_DONE; } while (0)
+enum : uint32_t { WK_I = 1, WK_U = 2, WK_D = 3, WO_FULL = 1, WO_KEY = 2, WB_DENSE = 1u << 7, WB_PARTIAL = 1u << 8,
+                  WB_EMIT = 1u << 9 };   // emit clears after the first data error: structure-only walk (a malformed
+                                         // frame, i.e. a parser error in the reference, outranks every conversion error)
+struct TextCell { uint32_t voff, len, kind, seq, dest; };   // voff frame-relative, dest relative to cell0
+#define W_SET_STAGE(s_) (w.bits = (w.bits & ~7u) | (s_))
+#define W_DATA_ERROR(seq_, code_) do { report_error(P, P.record_index_base + w.rec_local, (seq_), (code_)); w.bits &= ~WB_EMIT; } while (0)
+#define W_MALFORMED() do { report_error(P, P.record_index_base + w.rec_local, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); W_SET_STAGE(W_DONE); } while (0)
 
-__device__ __forceinline__ const uint8_t* wk_ptr(const Wk& w, uint32_t off, uint32_t span) {
-  return ((uint64_t)off + span <= w.staged) ? w.sbase + off : w.base + off;
-}
 // one step: a tuple header or ONE wire cell. Returns true when a text cell must be parsed (tc filled).
 __device__ __forceinline__ bool wk_step(const DecodeParams& P, Wk& w, TextCell& tc) {
+  const uint32_t stage = w.bits & 7u, kind = (w.bits >> 3) & 3u, old = (w.bits >> 5) & 3u;
+  const bool emit = (w.bits & WB_EMIT) != 0;
+  const uint32_t n_cols = w.nc_ni & 0xFFFFu, n_ident = w.nc_ni >> 16;
   do {
-    if (w.stage == W_OLD_HDR || w.stage == W_NEW_HDR) {
-      const bool is_new = w.stage == W_NEW_HDR;
+    if (stage == W_OLD_HDR || stage == W_NEW_HDR) {
+      const bool is_new = stage == W_NEW_HDR;
       if ((uint64_t)w.pos + (is_new ? 3u : 2u) > w.end) { W_MALFORMED(); break; }
-      const uint64_t x = ld64u(wk_ptr(w, w.pos, 12));
-      uint32_t hdr = (uint32_t)x;
+      uint32_t hdr = (uint32_t)ld64u(w.base + w.pos);
       if (is_new) {
         if ((hdr & 0xFFu) != 'N') { W_MALFORMED(); break; }
         hdr >>= 8; w.pos++;
       }
-      int32_t nc = (int32_t)(int16_t)(((hdr & 0xFFu) << 8) | ((hdr >> 8) & 0xFFu));
-      if (nc < 0) nc = 0;
+      int32_t nci = (int32_t)(int16_t)(((hdr & 0xFFu) << 8) | ((hdr >> 8) & 0xFFu));
+      const uint32_t nc = nci < 0 ? 0u : (uint32_t)nci;
       w.pos += 2;
-      w.remaining = (uint32_t)nc; w.wire_i = 0; w.cmap = 0; w.k_out = 0;
+      w.rem_wire = nc; w.cmap_kout = 0;
       if (!is_new) {
-        if (w.old_tag == 'K') {                     // normalize_key_tuple_to_row event.rs:879-919
-          w.n_old = w.n_ident;
-          w.dense = (uint32_t)nc == w.n_ident;
-          if (w.emit) {
-            if (w.n_ident == 0) W_DATA_ERROR(SEQ_OLD_SHAPE, ETL_E_KEY_NO_COLUMNS);
-            else if (!w.dense && (uint32_t)nc != w.n_cols) W_DATA_ERROR(SEQ_OLD_SHAPE, ETL_E_KEY_SHAPE);
+        if (old == WO_KEY) {                        // normalize_key_tuple_to_row event.rs:879-919
+          w.keyi_nold = (w.keyi_nold & 0xFFFFu) | (n_ident << 16);
+          const bool dense = nc == n_ident;
+          if (dense) w.bits |= WB_DENSE;
+          if (emit) {
+            if (n_ident == 0) W_DATA_ERROR(SEQ_OLD_SHAPE, ETL_E_KEY_NO_COLUMNS);
+            else if (!dense && nc != n_cols) W_DATA_ERROR(SEQ_OLD_SHAPE, ETL_E_KEY_SHAPE);
           }
         } else {                                    // convert_tuple_to_row event.rs:550-583
-          w.n_old = w.n_cols;
-          if (w.emit && (uint32_t)nc != w.n_cols) W_DATA_ERROR(SEQ_OLD_SHAPE, ETL_E_FIELD_COUNT);
+          w.keyi_nold = (w.keyi_nold & 0xFFFFu) | (n_cols << 16);
+          if (emit && nc != n_cols) W_DATA_ERROR(SEQ_OLD_SHAPE, ETL_E_FIELD_COUNT);
         }
-        w.stage = W_OLD_CELLS;
+        W_SET_STAGE(W_OLD_CELLS);
       } else {
-        if (w.emit && (uint32_t)nc != w.n_cols) W_DATA_ERROR(SEQ_NEW_SHAPE, ETL_E_FIELD_COUNT);
-        w.stage = W_NEW_CELLS;
+        if (emit && nc != n_cols) W_DATA_ERROR(SEQ_NEW_SHAPE, ETL_E_FIELD_COUNT);
+        W_SET_STAGE(W_NEW_CELLS);
       }
       break;
     }
-    if (w.remaining == 0) {
-      w.stage = (w.stage == W_OLD_CELLS && w.kind != 'D') ? W_NEW_HDR : W_DONE;
+    if ((w.rem_wire & 0xFFFFu) == 0) {
+      W_SET_STAGE((stage == W_OLD_CELLS && kind != WK_D) ? W_NEW_HDR : W_DONE);
       break;
     }
     if (w.pos >= w.end) { W_MALFORMED(); break; }
-    const uint64_t x = ld64u(wk_ptr(w, w.pos, 12));
+    const uint64_t x = ld64u(w.base + w.pos);
     const uint32_t tag = (uint32_t)(x & 0xFFu);
     const uint32_t len = bswap32((uint32_t)(x >> 8));
     const uint32_t voff = w.pos + 5u;
@@ -783,52 +875,55 @@ __device__ __forceinline__ bool wk_step(const DecodeParams& P, Wk& w, TextCell& 
       w.pos += 5u + len;
     } else if (tag == 'n' || tag == 'u') w.pos += 1;
     else { W_MALFORMED(); break; }
-    const uint32_t i = w.wire_i++;
-    w.remaining--;
-    if (!w.emit) break;                             // structure-only after a data error
-    const bool is_new = w.stage == W_NEW_CELLS;
+    const uint32_t i = w.rem_wire >> 16;
+    w.rem_wire += 0x10000u - 1u;                    // wire_i++, remaining--
+    if (!emit) break;                               // structure-only after a data error
+    const bool is_new = stage == W_NEW_CELLS;
     const uint8_t* flags = P.col_flags + w.col_base;
-    uint32_t col = i;
-    uint64_t dest;
-    if (!is_new && w.old_tag == 'K') {
-      if (w.dense) { while (w.cmap < w.n_cols && !(flags[w.cmap] & 2)) w.cmap++; col = w.cmap++; }
-      else if (!(flags[i] & 2)) break;              // full-width key: non-identity entries are not decoded
-      dest = w.cell0 + w.k_out++;
-    } else dest = w.cell0 + (is_new ? w.n_old : 0u) + i;
+    uint32_t col = i, dest;
+    if (!is_new && old == WO_KEY) {
+      if (w.bits & WB_DENSE) {
+        uint32_t cmap = w.cmap_kout & 0xFFFFu;
+        while (cmap < n_cols && !(flags[cmap] & 2)) cmap++;
+        col = cmap++;
+        w.cmap_kout = (w.cmap_kout & 0xFFFF0000u) | cmap;
+      } else if (!(flags[i] & 2)) break;            // full-width key: non-identity entries are not decoded
+      dest = w.cmap_kout >> 16;
+      w.cmap_kout += 0x10000u;
+    } else dest = (is_new ? (w.keyi_nold >> 16) : 0u) + i;
     const uint32_t seq = is_new ? seq_new_cell(i) : seq_old_cell(i);
-    const bool need_flags = tag != 't' || (is_new && w.kind == 'U' && w.old_tag == 'K');
+    const bool upd_key = is_new && kind == WK_U && old == WO_KEY;
+    const bool need_flags = tag != 't' || upd_key;
     const uint32_t cflags = need_flags ? (uint32_t)flags[col] : 0u;
-    const bool resolver_key = is_new && w.kind == 'U' && w.old_tag == 'K' && (cflags & 2);
+    const bool resolver_key = upd_key && (cflags & 2);
     if (tag == 't') {
-      if (resolver_key) w.key_i++;
-      tc.v = wk_ptr(w, voff, len + 16u); tc.len = len; tc.kind = P.col_kind[w.col_base + col]; tc.seq = seq; tc.dest = dest;
-      tc.soff = (uint64_t)(w.base - P.buf) + voff;
+      if (resolver_key) w.keyi_nold++;
+      tc.voff = voff; tc.len = len; tc.kind = P.col_kind[w.col_base + col]; tc.seq = seq; tc.dest = dest;
       return true;
     }
     if (tag == 'n') {                               // convert_tuple_data_to_cell event.rs:941-957
-      if (resolver_key) w.key_i++;
-      if (cflags & 1) put_cell(P, dest, ETL_CELL_NULL, 0, 0);
+      if (resolver_key) w.keyi_nold++;
+      if (cflags & 1) put_cell(P, w.cell0 + dest, ETL_CELL_NULL, 0, 0);
       else W_DATA_ERROR(seq, ETL_E_NOT_NULL);
       break;
     }
     if (tag == 'u') {                               // event.rs:958-970 + OldRowResolver :722-762
-      if (is_new && w.kind == 'U') {
+      if (is_new && kind == WK_U) {
         uint64_t src = ~0ull;
-        if (w.old_tag == 'O') src = w.cell0 + i;
-        else if (resolver_key) src = w.cell0 + w.key_i++;
-        if (src != ~0ull) put_cell(P, dest, P.cell_tag[src], P.cell_val[src], P.cell_aux[src]);  // written earlier by this thread
-        else { put_cell(P, dest, ETL_CELL_MISSING, 0, 0); w.partial = true; }
-      } else W_DATA_ERROR(seq, (!is_new && w.old_tag == 'K') ? ETL_E_KEY_MISSING_VALUE : ETL_E_FULL_ROW_MISSING);
+        if (old == WO_FULL) src = w.cell0 + i;
+        else if (resolver_key) { src = w.cell0 + (w.keyi_nold & 0xFFFFu); w.keyi_nold++; }
+        if (src != ~0ull) put_cell(P, w.cell0 + dest, P.cell_tag[src], P.cell_val[src], P.cell_aux[src]);  // written earlier by this thread
+        else { put_cell(P, w.cell0 + dest, ETL_CELL_MISSING, 0, 0); w.bits |= WB_PARTIAL; }
+      } else W_DATA_ERROR(seq, (!is_new && old == WO_KEY) ? ETL_E_KEY_MISSING_VALUE : ETL_E_FULL_ROW_MISSING);
       break;
     }
-    if (resolver_key) w.key_i++;
+    if (resolver_key) w.keyi_nold++;
     W_DATA_ERROR(seq, ETL_E_BINARY_FORMAT);         // 'b'
   } while (0);
   return false;
 }
 
 struct WalkShared {
-  alignas(16) uint8_t stage[ETL_WALK_STAGE ? kWalkThreads * (kStageBytes + 16) : 16];
   uint32_t dict_key[64];
   uint32_t dict_cnt[64];
   uint32_t dict_start[64];
@@ -878,64 +973,36 @@ __global__ void __launch_bounds__(kWalkThreads, ETL_WALK_CTAS) k_walk(DecodePara
   const uint32_t n_dml = sh.n_keys;
   // ---- 2. thread t walks the t-th record of the grouped order
   Wk w;
-  w.stage = W_DONE; w.tb = 0; w.partial = false; w.kind = 0; w.rec_local = 0; w.base = nullptr; w.sbase = nullptr; w.staged = 0;
-  uint32_t my_flen = 0;
+  w.bits = W_DONE; w.tb = 0; w.rec_local = 0; w.base = nullptr; w.pos = 0; w.end = 0; w.col_base = 0; w.nc_ni = 0; w.cell0 = 0;
+  w.rem_wire = 0; w.cmap_kout = 0; w.keyi_nold = 0;
   if (threadIdx.x < n_dml) {
     const uint64_t rr = (uint64_t)blockIdx.x * blockDim.x + sh.order[threadIdx.x];
-    const uint64_t off = P.rec_off[rr];
-    const uint8_t* fp = P.buf + off;
+    const uint8_t* fp = P.buf + P.rec_off[rr];
     const DevSchema& s = P.schemas[P.schema_by_batch[P.rec_schema[rr]]];
-    const uint32_t flen = bswap32((uint32_t)(ld64u(fp) >> 8));
-    my_flen = flen;
-    w.base = fp; w.end = 1u + flen;
-    w.col_base = s.col_base; w.n_cols = s.n_cols; w.n_ident = s.n_ident;
-    w.cell0 = P.rec_cell_base[rr]; w.rec_local = (uint32_t)rr; w.emit = true;
-    w.remaining = 0; w.wire_i = 0; w.cmap = 0; w.k_out = 0; w.key_i = 0; w.n_old = 0;
-    w.kind = P.rec_kind[rr];
-    const uint32_t rf = P.rec_flags[rr];
-    w.old_tag = (rf & ETL_RF_OLD_FULL) ? 'O' : ((rf & ETL_RF_OLD_KEY) ? 'K' : 0u);
-    w.dense = false;
-    if (w.kind != 'I' && w.old_tag) { w.stage = W_OLD_HDR; w.pos = 36u; }   // old image first
-    else { w.stage = W_NEW_HDR; w.pos = 35u; }                              // 'N' marker, then the new tuple
-  }
-  // ---- 2b. each warp copies the first 256 bytes of its 32 frames into shared memory: 32 independent
-  //          coalesced 16-byte loads in flight per lane-row, then every hop / short value is an LDS
-  if (ETL_WALK_STAGE) {
-    const int wid = threadIdx.x >> 5;
-    uint8_t* wstage = sh.stage + (size_t)wid * 32 * (kStageBytes + 16);
-    const uint64_t my_base = reinterpret_cast<uint64_t>(w.base);
-#pragma unroll 4
-    for (int f = 0; f < 32; f++) {
-      const uint64_t b = __shfl_sync(0xffffffffu, my_base, f);
-      const uint32_t fl = __shfl_sync(0xffffffffu, my_flen, f);
-      if (b && lane < kStageBytes / 16) {
-        const uint64_t a = b & ~15ull;
-        // never read past the end of the stream buffer (+64 bytes of padding are guaranteed)
-        if (a + (uint64_t)lane * 16 < reinterpret_cast<uint64_t>(P.buf) + P.len + 48)
-          reinterpret_cast<uint4*>(wstage + (size_t)f * (kStageBytes + 16))[lane] = reinterpret_cast<const uint4*>(a)[lane];
-      }
-      (void)fl;
-    }
-    __syncwarp();
-    if (w.base) {
-      const uint32_t lead = (uint32_t)(my_base & 15ull);
-      w.sbase = wstage + (size_t)lane * (kStageBytes + 16) + lead;
-      w.staged = min((uint32_t)kStageBytes - lead, 1u + my_flen);
-    }
+    w.base = fp; w.end = 1u + bswap32((uint32_t)(ld64u(fp) >> 8));
+    w.col_base = s.col_base; w.nc_ni = s.n_cols | (s.n_ident << 16);
+    w.cell0 = P.rec_cell_base[rr]; w.rec_local = (uint32_t)rr;
+    const uint32_t k = P.rec_kind[rr], rf = P.rec_flags[rr];
+    const uint32_t kc = k == 'I' ? WK_I : (k == 'U' ? WK_U : WK_D);
+    const uint32_t oc = (rf & ETL_RF_OLD_FULL) ? WO_FULL : ((rf & ETL_RF_OLD_KEY) ? WO_KEY : 0u);
+    const bool old_first = kc != WK_I && oc;        // old image first; else the 'N' marker, then the new tuple
+    w.pos = old_first ? 36u : 35u;
+    w.bits = (old_first ? W_OLD_HDR : W_NEW_HDR) | (kc << 3) | (oc << 5) | WB_EMIT;
   }
   // warp-synchronous stepping: all lanes take one step (header or cell) per iteration
   for (;;) {
-    const bool act = w.stage != W_DONE;
+    const bool act = (w.bits & 7u) != W_DONE;
     if (!__any_sync(0xffffffffu, act)) break;
     TextCell tc;
-    tc.v = nullptr; tc.len = 0; tc.kind = 0; tc.seq = 0; tc.dest = 0; tc.soff = 0;
+    tc.voff = 0; tc.len = 0; tc.kind = 0; tc.seq = 0; tc.dest = 0;
     const bool is_text = act && wk_step(P, w, tc);
+    const uint8_t* tv = w.base + tc.voff;
     // ---- text cell: UTF-8 (event.rs:972) then the per-kind parser (text.rs:28-173)
     CellOut o;
     o.tag = 0; o.val = 0; o.aux = 0;
     uint32_t code = 0;
     bool do_parse = false;
-    const uint64_t soff = tc.soff;
+    const uint64_t soff = (uint64_t)(w.base - P.buf) + tc.voff;
     if (is_text) {
       if (tc.kind == ETL_K_STRING) {
         o.tag = ETL_CELL_STRING; o.val = soff; o.aux = tc.len;
@@ -950,20 +1017,20 @@ __global__ void __launch_bounds__(kWalkThreads, ETL_WALK_CTAS) k_walk(DecodePara
               sp.span_len = min(tc.len - k * (256u << 10), 256u << 10); sp.cell_len = tc.len; sp.seq = tc.seq; sp.rec_local = w.rec_local;
               P.big_spans[at + k] = sp;
             }
-          } else if (utf8_range_bad(tc.v, tc.len, 0, tc.len, 0, 1)) code = ETL_E_UTF8;
-        } else if (tc.len >= (uint32_t)kWideLen) { if (utf8_range_bad(tc.v, tc.len, 0, tc.len, 0, 1)) code = ETL_E_UTF8; }
-        else if (!utf8_valid_fast(tc.v, tc.len)) code = ETL_E_UTF8;
-      } else if (!utf8_valid_fast(tc.v, tc.len)) code = ETL_E_UTF8;
+          } else if (utf8_range_bad(tv, tc.len, 0, tc.len, 0, 1)) code = ETL_E_UTF8;
+        } else if (tc.len >= (uint32_t)kWideLen) { if (utf8_range_bad(tv, tc.len, 0, tc.len, 0, 1)) code = ETL_E_UTF8; }
+        else if (!utf8_valid_fast(tv, tc.len)) code = ETL_E_UTF8;
+      } else if (!utf8_valid_fast(tv, tc.len)) code = ETL_E_UTF8;
       else do_parse = true;
     }
     __syncwarp();
     const unsigned pm = __ballot_sync(0xffffffffu, do_parse);
     if (do_parse) {
       const unsigned mask = __match_any_sync(pm, tc.kind);
-      const uint32_t hb = cell_heap_bound(tc.kind, tc.len);
-      HeapCursor hc{P.heap, 0};
+      uint64_t hpos = 0;
       const bool heap_kind = tc.kind == ETL_K_NUMERIC || tc.kind == ETL_K_BYTES || tc.kind == ETL_K_UUID;  // uniform over `mask`
       if (heap_kind) {                                 // warp-aggregated bump allocation
+        const uint32_t hb = cell_heap_bound(tc.kind, tc.len);
         const unsigned below = mask & ((1u << lane) - 1u);
         uint32_t mine_off = 0, total = 0;
         for (unsigned mm = mask; mm; mm &= mm - 1) {   // lanes of `mask` run this loop together
@@ -976,35 +1043,47 @@ __global__ void __launch_bounds__(kWalkThreads, ETL_WALK_CTAS) k_walk(DecodePara
         const int leader = __ffs(mask) - 1;
         if (lane == leader) base = atomicAdd(P.heap_top, (unsigned long long)total);
         base = __shfl_sync(mask, base, leader);
-        hc.pos = base + mine_off;
+        hpos = base + mine_off;
       }
+      // out-of-line parsers get their own CellOut / HeapCursor so that `o` never has its address taken
+      // (an escaped struct lives in local memory for the whole loop)
       int64_t iv = 0;
       switch (tc.kind) {
-        case ETL_K_I32: code = parse_int_sync(mask, tc.v, tc.len, true, 2147483647ull, 2147483648ull, &iv); o.tag = ETL_CELL_I32; o.val = (uint64_t)iv; break;
-        case ETL_K_I64: code = parse_int_sync(mask, tc.v, tc.len, true, 9223372036854775807ull, 9223372036854775808ull, &iv); o.tag = ETL_CELL_I64; o.val = (uint64_t)iv; break;
-        case ETL_K_I16: code = parse_int_sync(mask, tc.v, tc.len, true, 32767ull, 32768ull, &iv); o.tag = ETL_CELL_I16; o.val = (uint64_t)iv; break;
-        case ETL_K_U32: code = parse_int_sync(mask, tc.v, tc.len, false, 4294967295ull, 0ull, &iv); o.tag = ETL_CELL_U32; o.val = (uint64_t)iv; break;
-        case ETL_K_NUMERIC: code = parse_numeric_sync(mask, tc.v, tc.len, hc, o); break;
+        case ETL_K_I32: code = parse_int_sync(mask, tv, tc.len, true, 2147483647ull, 2147483648ull, &iv); o.tag = ETL_CELL_I32; o.val = (uint64_t)iv; break;
+        case ETL_K_I64: code = parse_int_sync(mask, tv, tc.len, true, 9223372036854775807ull, 9223372036854775808ull, &iv); o.tag = ETL_CELL_I64; o.val = (uint64_t)iv; break;
+        case ETL_K_I16: code = parse_int_sync(mask, tv, tc.len, true, 32767ull, 32768ull, &iv); o.tag = ETL_CELL_I16; o.val = (uint64_t)iv; break;
+        case ETL_K_U32: code = parse_int_sync(mask, tv, tc.len, false, 4294967295ull, 0ull, &iv); o.tag = ETL_CELL_U32; o.val = (uint64_t)iv; break;
+        case ETL_K_NUMERIC: code = parse_numeric_sync(mask, tv, tc.len, P.heap, hpos, o); break;
         case ETL_K_JSON:
-          if (json_valid_sync(mask, tc.v, tc.len)) { o.tag = ETL_CELL_JSON; o.val = soff; o.aux = tc.len; } else code = ETL_E_JSON;
+          if (json_valid_sync(mask, tv, tc.len)) { o.tag = ETL_CELL_JSON; o.val = soff; o.aux = tc.len; } else code = ETL_E_JSON;
           break;
         case ETL_K_TIMESTAMPTZ:
-          if (!fast_timestamptz(tc.v, tc.len, o)) code = parse_text_cell(tc.kind, tc.v, tc.len, soff, hc, o);
+          if (!fast_timestamptz(tv, tc.len, o)) { CellOut t; t.tag = 0; t.val = 0; t.aux = 0; code = parse_text_cell(tc.kind, tv, tc.len, soff, P.heap, hpos, t); o = t; }
           break;
         case ETL_K_TIMESTAMP:
-          if (!fast_timestamp(tc.v, tc.len, o)) code = parse_text_cell(tc.kind, tc.v, tc.len, soff, hc, o);
+          if (!fast_timestamp(tv, tc.len, o)) { CellOut t; t.tag = 0; t.val = 0; t.aux = 0; code = parse_text_cell(tc.kind, tv, tc.len, soff, P.heap, hpos, t); o = t; }
           break;
-        default: code = parse_text_cell(tc.kind, tc.v, tc.len, soff, hc, o); break;
+        case ETL_K_STRING: o.tag = ETL_CELL_STRING; o.val = soff; o.aux = tc.len; break;
+        default: {
+          CellOut t; t.tag = 0; t.val = 0; t.aux = 0;
+          if (tc.kind & ETL_K_ARRAY) {
+            code = parse_array_any(ArrHeap{P.heap, P.arr_top, P.arr_base, P.heap_cap}, tc.kind, tv, tc.len, t);
+            if (code == 0xFFFFFFFEu) { atomicExch(P.heap_overflow, 1u); code = 0; t.tag = ETL_CELL_NULL; }
+          } else code = parse_text_cell(tc.kind, tv, tc.len, soff, P.heap, hpos, t);
+          o = t;
+          break;
+        }
       }
     }
     if (is_text) {
-      if (code) { report_error(P, P.record_index_base + w.rec_local, tc.seq, code); w.emit = false; }
-      else put_cell(P, tc.dest, o.tag, o.val, o.aux);
+      if (code) { report_error(P, P.record_index_base + w.rec_local, tc.seq, code); w.bits &= ~WB_EMIT; }
+      else put_cell(P, w.cell0 + tc.dest, o.tag, o.val, o.aux);
     }
   }
   // ---- 3. per-record epilogue: Partial flag; tuple-byte metrics (one atomic per warp and op kind)
-  if (w.partial) P.rec_flags[w.rec_local] |= ETL_RF_NEW_PARTIAL;
-  uint32_t tbi = w.kind == 'I' ? w.tb : 0u, tbu = w.kind == 'U' ? w.tb : 0u, tbd = w.kind == 'D' ? w.tb : 0u;
+  if (w.bits & WB_PARTIAL) P.rec_flags[w.rec_local] |= ETL_RF_NEW_PARTIAL;
+  const uint32_t wkind = (w.bits >> 3) & 3u;
+  uint32_t tbi = wkind == WK_I ? w.tb : 0u, tbu = wkind == WK_U ? w.tb : 0u, tbd = wkind == WK_D ? w.tb : 0u;
   unsigned long long si = tbi, su = tbu, sd = tbd;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) { si += __shfl_down_sync(0xffffffffu, si, d); su += __shfl_down_sync(0xffffffffu, su, d); sd += __shfl_down_sync(0xffffffffu, sd, d); }
@@ -1012,5 +1091,6 @@ __global__ void __launch_bounds__(kWalkThreads, ETL_WALK_CTAS) k_walk(DecodePara
 }
 #undef W_DATA_ERROR
 #undef W_MALFORMED
+#undef W_SET_STAGE
 
 }  // namespace etl

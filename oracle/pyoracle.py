@@ -232,3 +232,8 @@ def parse_cell(type_oid: int, text: bytes):
     heap = (C.c_uint8 * cap)()
     e = L.orc_parse_cell(type_oid, text, len(text), C.byref(tag), C.byref(val), C.byref(aux), heap, cap, C.byref(hl))
     return e, tag.value, val.value, aux.value, bytes(heap[:min(hl.value, cap)])
+
+
+def kind_for_oid(type_oid: int) -> int:
+    """ETL_K_* decode class the reference's `Type` dispatch gives this oid (oracle_cells.c)."""
+    return int(lib().orc_kind_for_oid(type_oid))

@@ -248,3 +248,80 @@ def test_float_parity(gpu, oracle_mod):
         got, want = both(gpu, oracle_mod, {91: cols}, w.bytes())
         assert want.first_error[2] == 3, c
         assert got.first_error == want.first_error, c
+
+
+# ---------------------------------------------------------------------------------------------
+# arrays (text.rs:69-140 element dispatch, :184-249 the split)
+# ---------------------------------------------------------------------------------------------
+ARRAY_COLS = [  # (array type oid, valid spellings, invalid spellings)
+    (1007, ["{}", "{1,2,3}", "{NULL,5,null}", '{"7","-8"}', "{2147483647,-2147483648}"], ["{1,x}", "{2147483648}", "1,2", "{", "{1,2", "{1,,2}"]),
+    (1016, ["{9223372036854775807}", "{+5}"], ["{9223372036854775808}"]),
+    (1005, ["{1,-32768}"], ["{40000}"]),
+    (1000, ["{t,f,NULL}"], ["{true}"]),
+    (1009, ['{a,b c,"d,e","f\\"g",NULL,"NULL","",\\x}', '{"multi\\\\back","é✓"}', "{ a , b }"], []),
+    (1022, ["{1.5,-2e10,NaN,inf,NULL}"], ["{1.5,abc}"]),
+    (1021, ["{0.1,3.4028235e38}"], ["{}x"]),
+    (1231, ["{1.50,NaN,-0.0001,123456789012345678901234567890.123456789,NULL}"], ["{1.2.3}"]),
+    (1182, ["{2024-01-02,0001-01-01}"], ["{2024-13-01}"]),
+    (1183, ["{12:34:56.789,00:00:00}"], ["{25:00:00}"]),
+    (1115, ['{"2024-01-02 03:04:05.678","2000-02-29 23:59:59"}'], ['{"2024-01-02"}']),
+    (1185, ['{"2024-01-02 03:04:05+00","2024-06-01 12:00:00.5-07"}', '{"2024-01-02 03:04:05+05:30"}',
+            '{"2024-01-02 03:04:05+05:30","2024-01-02 03:04:05+00"}'], ['{"2024-01-02 03:04:05"}', '{"2024-01-02 03:04:05+5"}']),
+    (2951, ["{a0eebc99-9c0b-4ef8-bb6d-6bb9bd380a11,NULL}"], ["{zz}"]),
+    (199, ['{"{\\"a\\": [1, 2]}","null",NULL}'], ['{"{bad"}']),
+    (3807, ['{"[1,2,3]"}'], ['{"[1,"}']),
+    (1001, ['{"\\\\x0102ff",NULL}'], ['{"\\\\x0g"}', "{abc}"]),
+    (1028, ["{1,4294967295}"], ["{-1}"]),
+]
+
+
+def test_array_parity(gpu, oracle_mod):
+    """Every array element kind the reference decodes: valid spellings together in one stream, then each
+    invalid spelling alone (first_error compared).  Heap placement is unspecified; contents are compared."""
+    usable = [(oid, v, bad) for oid, v, bad in ARRAY_COLS if oracle_mod.kind_for_oid(oid) & 0x20]
+    assert len(usable) >= 12, [hex(oracle_mod.kind_for_oid(o)) for o, _, _ in ARRAY_COLS]
+    cols = [sc.col("id", sc.INT8, 1)] + [sc.col(f"a{oid}", oid, None, True) for oid, _, _ in usable]
+    rel = pg.relation(92, "public", "arrays", "d", sc.rel_cols(cols, {"id"}))
+    w = pg.StreamWriter()
+    tx = sc.Tx(w)
+    tx.begin()
+    w.emit(rel)
+    nrow = max(len(v) for _, v, _ in usable)
+    for r in range(nrow * 40):   # enough rows to overflow the first heap guess? no: to exercise many warps
+        w.emit(pg.insert(92, [str(r)] + [v[(r + j) % len(v)] for j, (_, v, _) in enumerate(usable)]))
+    tx.commit()
+    stream = w.bytes()
+    got, want = both(gpu, oracle_mod, {92: cols}, stream)
+    assert want.first_error[0] is None, want.first_error
+    assert_planes_equal(got, want, stream)
+    for j, (oid, _, bads) in enumerate(usable):
+        for bad in bads:
+            w = pg.StreamWriter()
+            tx = sc.Tx(w)
+            tx.begin()
+            w.emit(rel)
+            vals = [None] * len(usable)
+            vals[j] = bad
+            w.emit(pg.insert(92, ["1"] + vals))
+            tx.commit()
+            got, want = both(gpu, oracle_mod, {92: cols}, w.bytes())
+            assert want.first_error[0] is not None, (oid, bad)
+            assert got.first_error == want.first_error, (oid, bad, got.first_error, want.first_error)
+
+
+def test_array_heap_retry(gpu, oracle_mod):
+    """Arrays of many empty elements need far more heap than the first reservation (44 B per element):
+    the decode retries with a larger heap instead of failing or truncating."""
+    cols = [sc.col("id", sc.INT8, 1), sc.col("a", 1009, None, True)]
+    rel = pg.relation(93, "public", "wide", "d", sc.rel_cols(cols, {"id"}))
+    w = pg.StreamWriter()
+    tx = sc.Tx(w)
+    tx.begin()
+    w.emit(rel)
+    for r in range(64):
+        w.emit(pg.insert(93, [str(r), "{" + "," * 3000 + "}"]))
+    tx.commit()
+    stream = w.bytes()
+    got, want = both(gpu, oracle_mod, {93: cols}, stream)
+    assert want.first_error[0] is None
+    assert_planes_equal(got, want, stream)

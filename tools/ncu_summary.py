@@ -32,7 +32,7 @@ fname, ci = "?", None
 for r in csv.reader(io.StringIO(src)):
     if not r:
         continue
-    if r[0] == "File Name":
+    if r[0] in ("File Name", "File Path"):
         fname = os.path.basename(r[1]); continue
     if r[0] == "Line No":
         ci = {c: i for i, c in enumerate(r) if c not in ("Source",)}
