@@ -9,6 +9,7 @@
 
 #include "etl_decode.h"
 
+#include "json_tables.cuh"
 namespace etl {
 
 struct CellOut {
@@ -735,123 +736,72 @@ __device__ __forceinline__ uint32_t parse_numeric_sync(unsigned mask, const uint
   return code;
 }
 
-// serde_json acceptance as a flat byte-at-a-time DFA (one convergence point per byte).
-struct JsonState {
-  uint32_t st;        // see J_* below
-  uint32_t depth;
-  uint32_t stack[4];  // bit per level: 1 object, 0 array
-  uint32_t aux;       // literal tail / hex accumulator
-  uint32_t hexn;      // hex digits still expected
-  bool key;           // the string being read is an object key
-  bool low_sur;       // the \u escape being read must be a low surrogate
-};
-enum : uint32_t { J_VALUE = 0, J_AFTER, J_KEY_OR_CLOSE, J_KEY, J_COLON, J_VALUE_OR_CLOSE, J_STR, J_ESC, J_HEX, J_SUR_BS, J_SUR_U,
-                  J_MINUS, J_ZERO, J_INT, J_DOT, J_FRAC, J_E, J_ESIGN, J_EXP, J_LIT, J_BAD };
-__device__ __forceinline__ bool json_top(const JsonState& S) { return (S.stack[(S.depth - 1) >> 5] >> ((S.depth - 1) & 31)) & 1u; }
-// returns true if the byte was consumed (numbers end on a delimiter that must be re-examined)
-__device__ __forceinline__ bool json_step(JsonState& S, uint32_t c) {
-  const bool ws = c == ' ' || c == '\t' || c == '\n' || c == '\r';
-  switch (S.st) {
-    case J_STR:
-      if (c == '"') S.st = S.key ? J_COLON : J_AFTER;
-      else if (c == '\\') S.st = J_ESC;
-      else if (c < 0x20u) S.st = J_BAD;
-      return true;
-    case J_ESC:
-      if (c == 'u') { S.st = J_HEX; S.hexn = 4; S.aux = 0; }
-      else if (c == '"' || c == '\\' || c == '/' || c == 'b' || c == 'f' || c == 'n' || c == 'r' || c == 't') S.st = S.low_sur ? J_BAD : J_STR;
-      else S.st = J_BAD;
-      return true;
-    case J_HEX: {
-      const int h = hexval(c);
-      if (h < 0) { S.st = J_BAD; return true; }
-      S.aux = S.aux * 16u + (uint32_t)h;
-      if (--S.hexn == 0) {
-        const uint32_t u = S.aux;
-        if (S.low_sur) { S.st = (u >= 0xDC00u && u <= 0xDFFFu) ? J_STR : J_BAD; S.low_sur = false; }
-        else if (u >= 0xDC00u && u <= 0xDFFFu) S.st = J_BAD;
-        else if (u >= 0xD800u && u <= 0xDBFFu) S.st = J_SUR_BS;
-        else S.st = J_STR;
-      }
-      return true;
-    }
-    case J_SUR_BS: S.st = (c == '\\') ? J_SUR_U : J_BAD; return true;
-    case J_SUR_U: if (c == 'u') { S.st = J_HEX; S.hexn = 4; S.aux = 0; S.low_sur = true; } else S.st = J_BAD; return true;
-    case J_LIT:
-      if (c != (S.aux & 0xFFu)) S.st = J_BAD;
-      else { S.aux >>= 8; if (!S.aux) S.st = J_AFTER; }
-      return true;
-    case J_MINUS: S.st = (c == '0') ? J_ZERO : ((c - '1') <= 8u ? J_INT : J_BAD); return true;
-    case J_ZERO:
-      if (c == '.') { S.st = J_DOT; return true; }
-      if (c == 'e' || c == 'E') { S.st = J_E; return true; }
-      if (is_digit(c)) { S.st = J_BAD; return true; }
-      S.st = J_AFTER; return false;
-    case J_INT:
-      if (is_digit(c)) return true;
-      if (c == '.') { S.st = J_DOT; return true; }
-      if (c == 'e' || c == 'E') { S.st = J_E; return true; }
-      S.st = J_AFTER; return false;
-    case J_DOT: S.st = is_digit(c) ? J_FRAC : J_BAD; return true;
-    case J_FRAC:
-      if (is_digit(c)) return true;
-      if (c == 'e' || c == 'E') { S.st = J_E; return true; }
-      S.st = J_AFTER; return false;
-    case J_E: S.st = (c == '+' || c == '-') ? J_ESIGN : (is_digit(c) ? J_EXP : J_BAD); return true;
-    case J_ESIGN: S.st = is_digit(c) ? J_EXP : J_BAD; return true;
-    case J_EXP:
-      if (is_digit(c)) return true;
-      S.st = J_AFTER; return false;
-    case J_AFTER:
-      if (ws) return true;
-      if (S.depth == 0) { S.st = J_BAD; return true; }
-      if (c == ',') { S.st = json_top(S) ? J_KEY : J_VALUE; return true; }
-      if (c == (json_top(S) ? '}' : ']')) { S.depth--; return true; }
-      S.st = J_BAD; return true;
-    case J_COLON:
-      if (ws) return true;
-      S.st = (c == ':') ? J_VALUE : J_BAD; return true;
-    case J_KEY_OR_CLOSE: case J_KEY:
-      if (ws) return true;
-      if (S.st == J_KEY_OR_CLOSE && c == '}') { S.depth--; S.st = J_AFTER; return true; }
-      if (c == '"') { S.st = J_STR; S.key = true; S.low_sur = false; } else S.st = J_BAD;
-      return true;
-    case J_VALUE_OR_CLOSE:
-      if (ws) return true;
-      if (c == ']') { S.depth--; S.st = J_AFTER; return true; }
-      S.st = J_VALUE;
-      // fallthrough
-    case J_VALUE:
-      if (ws) return true;
-      if (c == '"') { S.st = J_STR; S.key = false; S.low_sur = false; return true; }
-      if (c == '{' || c == '[') {
-        if (S.depth >= 127u) { S.st = J_BAD; return true; }
-        if (c == '{') S.stack[S.depth >> 5] |= (1u << (S.depth & 31)); else S.stack[S.depth >> 5] &= ~(1u << (S.depth & 31));
-        S.depth++;
-        S.st = (c == '{') ? J_KEY_OR_CLOSE : J_VALUE_OR_CLOSE;
-        return true;
-      }
-      if (c == 't') { S.st = J_LIT; S.aux = 'r' | ('u' << 8) | ('e' << 16); return true; }
-      if (c == 'f') { S.st = J_LIT; S.aux = 'a' | ('l' << 8) | ('s' << 16) | ((uint32_t)'e' << 24); return true; }
-      if (c == 'n') { S.st = J_LIT; S.aux = 'u' | ('l' << 8) | ('l' << 16); return true; }
-      if (c == '-') { S.st = J_MINUS; return true; }
-      if (c == '0') { S.st = J_ZERO; return true; }
-      if ((c - '1') <= 8u) { S.st = J_INT; return true; }
-      S.st = J_BAD; return true;
-    default: return true;
-  }
-}
-__device__ __forceinline__ bool json_valid_sync(unsigned mask, const uint8_t* s, uint32_t n) {
-  JsonState S;
-  S.st = J_VALUE; S.depth = 0; S.stack[0] = S.stack[1] = S.stack[2] = S.stack[3] = 0; S.aux = 0; S.hexn = 0; S.key = false; S.low_sur = false;
+// serde_json acceptance, table-driven so that every lane executes the same instructions per byte
+// (a switch over the state serialises the warp: the first version spent ~225 warp instructions per
+// byte step on it).  Tables: tools/gen_json_tables.py (fuzzed against the oracle in
+// tests/test_json_tables.py); T points at the CTA's shared-memory copy of kJsonTables.
+// Every iteration consumes exactly one byte, so `i` stays uniform over the lanes of `mask`.
+__device__ __forceinline__ bool json_valid_sync(unsigned mask, const uint8_t* s, uint32_t n, const uint8_t* T) {
+  uint32_t st = JT_VALUE, depth = 0, ctx = 0 /*0 top, 1 object, 2 array*/, aux = 0, hexn = 0;
+  bool key = false, low_sur = false;
+  uint64_t lo = 0, hi = 0;                            // container stack, bit d = 1: level d is an object
+  uint64_t word = 0;
   uint32_t i = 0;
-  while (__any_sync(mask, i < n && S.st != J_BAD)) {
-    if (i < n && S.st != J_BAD) {
-      if (json_step(S, s[i])) i++;
+  while (__any_sync(mask, i < n && st != JT_BAD)) {
+    if (i < n && st != JT_BAD) {
+      if ((i & 7u) == 0) word = ldu64(s + i);
+      const uint32_t c = (uint32_t)(word >> ((i & 7u) * 8u)) & 0xFFu;
+      i++;
+      if (st - JT_ESC <= 3u) {                        // inside an escape: rare
+        if (st == JT_ESC) {
+          if (c == 'u') { st = JT_HEX; hexn = 4; aux = 0; }
+          else if (c == '"' || c == '\\' || c == '/' || c == 'b' || c == 'f' || c == 'n' || c == 'r' || c == 't') st = low_sur ? JT_BAD : JT_STR;
+          else st = JT_BAD;
+        } else if (st == JT_HEX) {
+          const int h = hexval(c);
+          if (h < 0) st = JT_BAD;
+          else {
+            aux = aux * 16u + (uint32_t)h;
+            if (--hexn == 0) {
+              if (low_sur) { st = (aux >= 0xDC00u && aux <= 0xDFFFu) ? JT_STR : JT_BAD; low_sur = false; }
+              else if (aux >= 0xDC00u && aux <= 0xDFFFu) st = JT_BAD;
+              else if (aux >= 0xD800u && aux <= 0xDBFFu) st = JT_SUR_BS;
+              else st = JT_STR;
+            }
+          }
+        } else if (st == JT_SUR_BS) st = (c == '\\') ? JT_SUR_U : JT_BAD;
+        else { if (c == 'u') { st = JT_HEX; hexn = 4; aux = 0; low_sur = true; } else st = JT_BAD; }
+      } else {
+        const uint32_t e = T[256u + st * (uint32_t)kJsonClasses + T[c]];
+        uint32_t nst = e & 31u;
+        const uint32_t act = e >> 5;
+        if (act) {                                    // brackets, commas, opening quotes
+          if (act <= JA_PUSH_ARR) {
+            if (depth >= 127u) nst = JT_BAD;
+            else {
+              const uint64_t bit = act == JA_PUSH_OBJ ? 1ull : 0ull;
+              if (depth < 64u) lo = (lo & ~(1ull << depth)) | (bit << depth);
+              else hi = (hi & ~(1ull << (depth - 64u))) | (bit << (depth - 64u));
+              depth++;
+              ctx = act == JA_PUSH_OBJ ? 1u : 2u;
+            }
+          } else if (act <= JA_POP_ARR) {
+            if (ctx != (act == JA_POP_OBJ ? 1u : 2u)) nst = JT_BAD;
+            else {
+              depth--;
+              const uint32_t p = depth - 1u;          // parent level (unused when depth == 0)
+              const uint64_t bits = p < 64u ? lo : hi;
+              ctx = depth == 0 ? 0u : (((bits >> (p & 63u)) & 1ull) ? 1u : 2u);
+            }
+          } else if (act == JA_COMMA) nst = ctx == 0 ? JT_BAD : (ctx == 1 ? JT_KEY : JT_VALUE);
+          else { key = act == JA_KEYSTR; low_sur = false; }
+        }
+        if (nst == JT_STR_END) nst = key ? JT_COLON : JT_AFTER;
+        st = nst;
+      }
     }
   }
-  if (S.st == J_BAD || S.depth != 0) return false;
-  return S.st == J_AFTER || S.st == J_ZERO || S.st == J_INT || S.st == J_FRAC || S.st == J_EXP;
+  return depth == 0 && (st == JT_AFTER || st == JT_ZERO || st == JT_INT || st == JT_FRAC || st == JT_EXP);
 }
 
 }  // namespace etl

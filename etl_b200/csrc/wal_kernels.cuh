@@ -423,6 +423,17 @@ __device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 
 __device__ __forceinline__ uint64_t bswap64(uint64_t v) { return ((uint64_t)bswap32((uint32_t)v) << 32) | bswap32((uint32_t)(v >> 32)); }
 
 // UTF-8 check of a short/medium cell with word loads: all-ASCII words pass immediately
+__device__ __forceinline__ bool has_high_bits(const uint8_t* s, uint32_t n) {
+  uint32_t hi = 0;
+  uint32_t i = 0;
+  for (; i + 8 <= n; i += 8) { uint64_t x = ld64u(s + i); hi |= (uint32_t)(x >> 32) | (uint32_t)x; }
+  if (i < n) {
+    uint64_t x = ld64u(s + i);
+    x &= (1ull << (8 * (n - i))) - 1ull;  // 1..7 valid bytes
+    hi |= (uint32_t)(x >> 32) | (uint32_t)x;
+  }
+  return (hi & 0x80808080u) != 0;
+}
 __device__ __forceinline__ bool utf8_valid_fast(const uint8_t* s, uint32_t n) {
   uint32_t hi = 0;
   uint32_t i = 0;
@@ -798,6 +809,9 @@ __global__ void __launch_bounds__(256) k_frames(DecodeParams P) {
 #ifndef ETL_WALK_CTAS
 #define ETL_WALK_CTAS 4
 #endif
+#ifndef ETL_WALK_PREFETCH
+#define ETL_WALK_PREFETCH 1
+#endif
 // Walker state, packed: k_walk is bound by live registers (a spilled field costs an LSU wavefront per
 // access, and the first ncu pass showed 60 % of all warp instructions were local loads/stores).
 struct Wk {
@@ -929,6 +943,7 @@ struct WalkShared {
   uint32_t dict_start[64];
   uint32_t n_keys;
   uint32_t order[kWalkThreads];
+  alignas(4) uint8_t json_tables[256 + 32 * kJsonClasses];   // byte classes + transitions (json_valid_sync)
 };
 
 __global__ void __launch_bounds__(kWalkThreads, ETL_WALK_CTAS) k_walk(DecodeParams P) {
@@ -945,6 +960,8 @@ __global__ void __launch_bounds__(kWalkThreads, ETL_WALK_CTAS) k_walk(DecodePara
   }
   if (threadIdx.x < 64) { sh.dict_key[threadIdx.x] = 0xFFFFFFFFu; sh.dict_cnt[threadIdx.x] = 0; }
   if (threadIdx.x == 0) sh.n_keys = 0;
+  for (uint32_t k = threadIdx.x; k < sizeof(sh.json_tables) / 4; k += blockDim.x)
+    reinterpret_cast<uint32_t*>(sh.json_tables)[k] = reinterpret_cast<const uint32_t*>(kJsonTables)[k];
   __syncthreads();
   // dictionary of distinct keys (open addressing, 64 slots; overflow → slot 63 is shared = no grouping for the excess)
   uint32_t slot = 63;
@@ -979,6 +996,11 @@ __global__ void __launch_bounds__(kWalkThreads, ETL_WALK_CTAS) k_walk(DecodePara
     const uint64_t rr = (uint64_t)blockIdx.x * blockDim.x + sh.order[threadIdx.x];
     const uint8_t* fp = P.buf + P.rec_off[rr];
     const DevSchema& s = P.schemas[P.schema_by_batch[P.rec_schema[rr]]];
+#if ETL_WALK_PREFETCH
+    // the walk is a dependent chain through the frame: put its first lines in flight together
+    if (fp + 128 < P.buf + P.len) asm volatile("prefetch.global.L2 [%0];" ::"l"(fp + 128));
+    if (fp + 256 < P.buf + P.len) asm volatile("prefetch.global.L2 [%0];" ::"l"(fp + 256));
+#endif
     w.base = fp; w.end = 1u + bswap32((uint32_t)(ld64u(fp) >> 8));
     w.col_base = s.col_base; w.nc_ni = s.n_cols | (s.n_ident << 16);
     w.cell0 = P.rec_cell_base[rr]; w.rec_local = (uint32_t)rr;
@@ -1003,27 +1025,40 @@ __global__ void __launch_bounds__(kWalkThreads, ETL_WALK_CTAS) k_walk(DecodePara
     uint32_t code = 0;
     bool do_parse = false;
     const uint64_t soff = (uint64_t)(w.base - P.buf) + tc.voff;
+    bool need_slow = false;                            // small cell with non-ASCII bytes: validated by the whole warp below
     if (is_text) {
-      if (tc.kind == ETL_K_STRING) {
-        o.tag = ETL_CELL_STRING; o.val = soff; o.aux = tc.len;
-        if (tc.len >= (uint32_t)kBigLen) {             // TOAST-sized: queue for the streaming validator
-          const uint32_t pieces = (tc.len + (256u << 10) - 1u) / (256u << 10);
-          const uint32_t at = atomicAdd(P.big_count, pieces);
-          if (at + pieces <= P.big_cap) {
-            atomicAdd(P.span_bytes, (unsigned long long)tc.len);
-            for (uint32_t k = 0; k < pieces; k++) {
-              BigSpan sp;
-              sp.cell_off = soff; sp.span_off = soff + (uint64_t)k * (256u << 10);
-              sp.span_len = min(tc.len - k * (256u << 10), 256u << 10); sp.cell_len = tc.len; sp.seq = tc.seq; sp.rec_local = w.rec_local;
-              P.big_spans[at + k] = sp;
-            }
-          } else if (utf8_range_bad(tv, tc.len, 0, tc.len, 0, 1)) code = ETL_E_UTF8;
-        } else if (tc.len >= (uint32_t)kWideLen) { if (utf8_range_bad(tv, tc.len, 0, tc.len, 0, 1)) code = ETL_E_UTF8; }
-        else if (!utf8_valid_fast(tv, tc.len)) code = ETL_E_UTF8;
-      } else if (!utf8_valid_fast(tv, tc.len)) code = ETL_E_UTF8;
-      else do_parse = true;
+      if (tc.kind == ETL_K_STRING) { o.tag = ETL_CELL_STRING; o.val = soff; o.aux = tc.len; }
+      if (tc.kind == ETL_K_STRING && tc.len >= (uint32_t)kBigLen) {   // TOAST-sized: queue for the streaming validator
+        const uint32_t pieces = (tc.len + (256u << 10) - 1u) / (256u << 10);
+        const uint32_t at = atomicAdd(P.big_count, pieces);
+        if (at + pieces <= P.big_cap) {
+          atomicAdd(P.span_bytes, (unsigned long long)tc.len);
+          for (uint32_t k = 0; k < pieces; k++) {
+            BigSpan sp;
+            sp.cell_off = soff; sp.span_off = soff + (uint64_t)k * (256u << 10);
+            sp.span_len = min(tc.len - k * (256u << 10), 256u << 10); sp.cell_len = tc.len; sp.seq = tc.seq; sp.rec_local = w.rec_local;
+            P.big_spans[at + k] = sp;
+          }
+        } else if (utf8_range_bad(tv, tc.len, 0, tc.len, 0, 1)) code = ETL_E_UTF8;
+      } else if (tc.len >= (uint32_t)kWideLen) { if (utf8_range_bad(tv, tc.len, 0, tc.len, 0, 1)) code = ETL_E_UTF8; }
+      else need_slow = has_high_bits(tv, tc.len);
     }
     __syncwarp();
+    // position-local UTF-8 rule, one byte position per lane (a lane-serial walk of a 60-byte cell would
+    // hold the other 31 lanes for ~1000 issue slots; this costs ~60 for the whole warp)
+    for (unsigned sm = __ballot_sync(0xffffffffu, need_slow); sm; sm &= sm - 1) {
+      const int src = __ffs(sm) - 1;
+      const uint8_t* cp = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(tv), src));
+      const uint32_t cn = __shfl_sync(0xffffffffu, tc.len, src);
+      bool bad = false;
+      for (uint32_t i = lane; i <= cn; i += 32) {      // position cn = a virtual ASCII terminator (catches a truncated tail)
+        const uint32_t b = i < cn ? cp[i] : 0u, p1 = i >= 1 ? cp[i - 1] : 0u, p2 = i >= 2 ? cp[i - 2] : 0u, p3 = i >= 3 ? cp[i - 3] : 0u;
+        if ((b | p1 | p2 | p3) >= 0x80u) bad |= utf8_step_bad(b, p1, p2, p3);
+      }
+      bad = __any_sync(0xffffffffu, bad);
+      if (lane == src && bad) code = ETL_E_UTF8;
+    }
+    do_parse = is_text && !code && tc.kind != ETL_K_STRING;
     const unsigned pm = __ballot_sync(0xffffffffu, do_parse);
     if (do_parse) {
       const unsigned mask = __match_any_sync(pm, tc.kind);
@@ -1055,7 +1090,7 @@ __global__ void __launch_bounds__(kWalkThreads, ETL_WALK_CTAS) k_walk(DecodePara
         case ETL_K_U32: code = parse_int_sync(mask, tv, tc.len, false, 4294967295ull, 0ull, &iv); o.tag = ETL_CELL_U32; o.val = (uint64_t)iv; break;
         case ETL_K_NUMERIC: code = parse_numeric_sync(mask, tv, tc.len, P.heap, hpos, o); break;
         case ETL_K_JSON:
-          if (json_valid_sync(mask, tv, tc.len)) { o.tag = ETL_CELL_JSON; o.val = soff; o.aux = tc.len; } else code = ETL_E_JSON;
+          if (json_valid_sync(mask, tv, tc.len, sh.json_tables)) { o.tag = ETL_CELL_JSON; o.val = soff; o.aux = tc.len; } else code = ETL_E_JSON;
           break;
         case ETL_K_TIMESTAMPTZ:
           if (!fast_timestamptz(tv, tc.len, o)) { CellOut t; t.tag = 0; t.val = 0; t.aux = 0; code = parse_text_cell(tc.kind, tv, tc.len, soff, P.heap, hpos, t); o = t; }
