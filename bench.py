@@ -160,7 +160,7 @@ def run_reference(args, rank, world):
     val = total_bytes / (secs / args.steps) / 1e9
     sample = f"{n_sample} of {w.n_segments} segments ({total_bytes / GIB:.2f} GiB) of workload {w.name}, {min(cores, n_sample)} threads"
     line = {"impl": "reference", "metric": "wal_decode_throughput", "value": val, "unit": "GB/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "events_per_s": frames / (secs / args.steps),
             "config": {"workload": f"{w.name}: {w.description}", "scale": args.scale, "sample": sample},
@@ -192,7 +192,8 @@ def main():
     # ---- this rank's byte range of the workload
     w = wl.make(args.workload, args.scale)
     S = w.n_segments
-    my_segs = list(range(rank * S // world, (rank + 1) * S // world))
+    # weak scaling: every GPU decodes a full-size shard (segments rank*S .. rank*S+S-1 of one longer stream)
+    my_segs = list(range(rank * S, (rank + 1) * S))
     cores = os.cpu_count() or 8
     t0 = time.perf_counter()
     arrays, stats = generate_segments(w, my_segs, args.gen_threads or max(1, cores // world))
@@ -202,6 +203,9 @@ def main():
     for a in arrays:
         stager.append_framed(a)
     gen_s = time.perf_counter() - t0
+    n_my_segs = len(arrays)
+    if not (rank == 0 and world == 1 and not args.no_cpu_baseline):
+        arrays = None                                 # the pinned staged copy is all the timed legs need
     host_view = stager.view()
     host_arr = stager.host_array()
 
@@ -250,7 +254,7 @@ def main():
         e0.record()
         for _ in range(steps):
             s = step(resident)
-            emit.append((s.frames_ms, s.walk_ms, s.spans_ms))
+            emit.append((s.frames_ms, s.walk_ms, s.spans_ms, s.kernel_ms))
             index.append(s.index_ms)
             launches += s.gpu_launches
         e1.record()
@@ -301,16 +305,18 @@ def main():
         peak, peak_src = measured_peak()
         # algorithmic bytes: every byte of the staged stream once + the anchor index
         algo_bytes = nbytes + 8 * (int(host_view.n_anchors) + 1)
-        km = np.mean(np.array(emit_ms, dtype=np.float64), axis=0)           # frames, walk, spans (ms, rank 0)
-        kern = {"k_index+k_scan+k_tile_prefix": float(np.mean(index_ms)), "k_frames": float(km[0]), "k_walk": float(km[1]),
-                "k_utf8_spans": float(km[2])}
+        km = np.mean(np.array(emit_ms, dtype=np.float64), axis=0)           # frames, walk, dead-segment pass, critical path (ms, rank 0)
+        kern = {"k_act*+k_index+k_scan+k_tile_prefix": float(np.mean(index_ms)), "k_frames": float(km[0]), "k_walk": float(km[1]),
+                "k_utf8_dead (side stream, overlapped)": float(km[2])}
         span_bytes = int(last["span_bytes"])
-        # bytes each kernel is responsible for: k_utf8_spans streams the TOAST-sized text, k_walk everything
-        # else in the DML tuples, k_frames / k_index the frame heads (counted with k_walk's share here)
-        kbytes = {"k_utf8_spans": span_bytes, "k_walk": algo_bytes - span_bytes}
-        dominant = max(("k_walk", "k_utf8_spans"), key=lambda k: kern[k])
-        pipeline_ms = sum(kern.values())
-        emit_avg = kern[dominant]
+        # bytes each kernel is responsible for: k_utf8_dead streams the segments without a frame start (the inside of
+        # TOAST-sized values), k_walk everything else in the DML tuples, k_frames / k_index the frame heads (counted
+        # with k_walk's share here)
+        kbytes = {"k_utf8_dead": span_bytes, "k_walk": algo_bytes - span_bytes}
+        ktime = {"k_utf8_dead": float(km[2]), "k_walk": float(km[1])}
+        dominant = max(ktime, key=lambda k: ktime[k])
+        pipeline_ms = float(km[3])                                          # index + records passes incl. the join with the side stream
+        emit_avg = ktime[dominant]
         achieved = kbytes[dominant] / (emit_avg * 1e-3) / 1e9
         traffic = None
         try:
@@ -321,11 +327,11 @@ def main():
         line = {
             "metric": "wal_decode_throughput", "value": total_bytes / (ms_per_step * 1e-3) / 1e9, "unit": "GB/s",
             "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "events_per_s": total_frames / (ms_per_step * 1e-3),
             "config": {"workload": f"{w.name}: {w.description}", "scale": args.scale, "bytes_total": int(total_bytes),
                        "msgs_total": int(total_frames), "records": int(tot[2].item()), "cells": int(tot[3].item()),
-                       "parallelism": f"byte-range shards x{n_gpus}, one seam all-gather" if n_gpus > 1 else "single GPU",
+                       "parallelism": f"{n_gpus} byte-range shards of {S} segments each (one per GPU), one seam all-gather" if n_gpus > 1 else "single GPU",
                        "anchor_stride": args.stride, "l2_policy": "inputs (>=1.25 GiB per GPU) larger than the 126 MB L2",
                        "generate_s": round(gen_s, 2)},
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -335,9 +341,10 @@ def main():
                          "pipeline": {"algorithmic_bytes": algo_bytes, "ms": pipeline_ms,
                                       "achieved": algo_bytes / (pipeline_ms * 1e-3) / 1e9,
                                       "frac": algo_bytes / (pipeline_ms * 1e-3) / 1e9 / peak},
-                         "k_utf8_spans": {"algorithmic_bytes": span_bytes,
-                                          "achieved": span_bytes / max(kern["k_utf8_spans"], 1e-6) / 1e6,
-                                          "frac": span_bytes / max(kern["k_utf8_spans"], 1e-6) / 1e6 / peak}},
+                         "k_utf8_dead": {"algorithmic_bytes": span_bytes,
+                                         "achieved": span_bytes / max(ktime["k_utf8_dead"], 1e-6) / 1e6,
+                                         "frac": span_bytes / max(ktime["k_utf8_dead"], 1e-6) / 1e6 / peak,
+                                         "note": "timed while the index/records passes run on the main stream"}},
             "gpu_launches": launches,
             "clocks": sampler.report(),
         }

@@ -74,6 +74,18 @@ __device__ __forceinline__ bool utf8_chunk_valid(const uint8_t* s, uint32_t n, u
   if (hi == n) bad |= (p1 >= 0xC0u) || (p2 >= 0xE0u) || (p3 >= 0xF0u);  // truncated tail sequence
   return !bad;
 }
+// the same over stream positions [lo, hi) with 64-bit offsets (k_utf8_lines: the "cell" is the whole stream)
+__device__ __forceinline__ bool utf8_chunk_valid_at(const uint8_t* s, uint64_t n, uint64_t lo, uint64_t hi) {
+  uint32_t p1 = lo >= 1 ? s[lo - 1] : 0, p2 = lo >= 2 ? s[lo - 2] : 0, p3 = lo >= 3 ? s[lo - 3] : 0;
+  bool bad = false;
+  for (uint64_t i = lo; i < hi; i++) {
+    uint32_t b = s[i];
+    bad |= utf8_step_bad(b, p1, p2, p3);
+    p3 = p2; p2 = p1; p1 = b;
+  }
+  if (hi == n) bad |= (p1 >= 0xC0u) || (p2 >= 0xE0u) || (p3 >= 0xF0u);
+  return !bad;
+}
 __device__ __forceinline__ bool utf8_valid(const uint8_t* s, uint32_t n) {
   // ASCII fast path per byte; multi-byte handled by the local rule
   uint32_t p1 = 0, p2 = 0, p3 = 0;

@@ -181,20 +181,20 @@ struct etl_dec_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  bool lines_launched = false;
   std::string last_error;
   std::map<uint32_t, StoredTable> tables;
   std::map<uint32_t, RelVersion> current;  // SharedTableCache Ready state (table_cache.rs:36-130)
   // scratch
   DevBuf<uint8_t> d_stream;
   DevBuf<uint64_t> d_anchors;
-  DevBuf<uint32_t> d_seg_frames;
+  DevBuf<uint32_t> d_seg_frames, d_act, d_act_blk;
   DevBuf<Summ> d_tile_summ, d_group_summ, d_group_prefix, d_total, d_tile_prefix, d_seg_summ;
   DevBuf<uint32_t> d_schema_by_batch;
   DevBuf<DevSchema> d_schemas;
   DevBuf<uint8_t> d_col_kind, d_col_flags;
-  DevBuf<BigSpan> d_big_spans;
-  DevBuf<unsigned long long> d_phase;    // optional per-phase cycle totals (ETL_PHASE_TIMING=1)
-  unsigned long long h_phase[16] = {0};
+  DevBuf<uint32_t> d_line_bad, d_dead, d_bin_count, d_bin_cursor, d_perm;
+  DevBuf<LongCell> d_long;
   DevBuf<unsigned long long> d_scalars;  // [0] first_error key, [1..4] metrics
   DevBuf<uint64_t> d_rel_err_off;
   DevBuf<uint32_t> d_rel_err_code, d_rel_err_seq;
@@ -204,6 +204,8 @@ struct etl_dec_ctx {
   unsigned long long* h_scalars = nullptr;  // pinned
   cudaEvent_t ev[6]{};
   cudaEvent_t evk[3]{};
+  cudaStream_t side = nullptr;           // k_utf8_lines runs here, underneath the index / records passes
+  cudaEvent_t ev_in = nullptr, ev_l0 = nullptr, ev_l1 = nullptr;
   // pending two-phase decode
   bool pending = false;
   DecodeParams P{};
@@ -315,6 +317,8 @@ int etl_dec_create(int device_id, etl_dec_ctx** out) {
   ctx->own_stream = true;
   for (auto& e : ctx->ev) cudaEventCreate(&e);
   for (auto& e : ctx->evk) cudaEventCreate(&e);
+  if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ETL_ERR_CUDA; }
+  cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming); cudaEventCreate(&ctx->ev_l0); cudaEventCreate(&ctx->ev_l1);
   cudaHostAlloc((void**)&ctx->h_total, sizeof(Summ), cudaHostAllocDefault);
   cudaHostAlloc((void**)&ctx->h_scalars, 16 * sizeof(unsigned long long), cudaHostAllocDefault);
   cudaFuncSetAttribute(k_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkShared));
@@ -338,13 +342,18 @@ void etl_dec_destroy(etl_dec_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ctx->d_stream.release(); ctx->d_anchors.release(); ctx->d_seg_frames.release(); ctx->d_tile_summ.release();
-  ctx->d_group_summ.release(); ctx->d_group_prefix.release(); ctx->d_tile_prefix.release(); ctx->d_big_spans.release(); ctx->d_seg_summ.release(); ctx->d_schema_by_batch.release(); ctx->d_total.release(); ctx->d_schemas.release();
+  ctx->d_group_summ.release(); ctx->d_group_prefix.release(); ctx->d_tile_prefix.release(); ctx->d_line_bad.release(); ctx->d_seg_summ.release(); ctx->d_schema_by_batch.release(); ctx->d_total.release(); ctx->d_schemas.release();
   ctx->d_col_kind.release(); ctx->d_col_flags.release(); ctx->d_scalars.release(); ctx->d_rel_err_off.release();
   ctx->d_rel_err_code.release(); ctx->d_rel_err_seq.release();
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
   if (ctx->h_total) cudaFreeHost(ctx->h_total);
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : ctx->evk) if (e) cudaEventDestroy(e);
+  if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
+  if (ctx->ev_l0) cudaEventDestroy(ctx->ev_l0);
+  if (ctx->ev_l1) cudaEventDestroy(ctx->ev_l1);
+  if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -452,6 +461,7 @@ int etl_dec_decode_begin(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t fla
   const uint32_t stride = in->anchor_stride;
   if (stride < 256 || stride > 32768 || (stride & (stride - 1))) { ctx->last_error = "anchor_stride must be a power of two in [256, 32768]"; return ETL_ERR_INVALID_ARG; }
   if (in->len && (!in->host_buf && !in->dev_buf)) { ctx->last_error = "no input buffer"; return ETL_ERR_INVALID_ARG; }
+  if (in->dev_buf && (reinterpret_cast<uintptr_t>(in->dev_buf) & 15u)) { ctx->last_error = "dev_buf must be 16-byte aligned"; return ETL_ERR_INVALID_ARG; }
   const uint64_t n_anchors_expected = in->len ? (in->len + stride - 1) / stride : 0;
   if (in->n_anchors != n_anchors_expected || (in->n_anchors && !in->anchors && !in->dev_anchors)) { ctx->last_error = "anchors: expected ceil(len/stride) entries"; return ETL_ERR_INVALID_ARG; }
   if (in->n_relations && (!in->relation_offsets || !in->host_buf)) { ctx->last_error = "relation_offsets require host_buf"; return ETL_ERR_INVALID_ARG; }
@@ -555,20 +565,44 @@ int etl_dec_decode_begin(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t fla
     P.schema_by_batch = ctx->d_schema_by_batch.p;
   }
   P.tile_prefix = ctx->d_tile_prefix.p; P.tile_counter = (unsigned int*)(ctx->d_scalars.p + 6);
-  P.big_cap = (uint32_t)std::min<uint64_t>(in->len / 2048 + 4096, 1u << 30);
-  CK(ctx->d_big_spans.ensure(P.big_cap));
-  P.big_spans = ctx->d_big_spans.p; P.big_count = (unsigned int*)(ctx->d_scalars.p + 7); P.span_bytes = ctx->d_scalars.p + 8;
+  const size_t line_words = (in->len + 4095) / 4096 + 1;
+  CK(ctx->d_line_bad.ensure(line_words)); CK(ctx->d_dead.ensure(P.n_anchors + 1));
+  P.line_bad = ctx->d_line_bad.p; P.dead = ctx->d_dead.p;
+  P.long_cap = P.n_anchors + 16;                      // a listed cell covers at least one whole segment
+  CK(ctx->d_long.ensure(P.long_cap));
+  P.long_cells = ctx->d_long.p; P.long_count = (unsigned int*)(ctx->d_scalars.p + 7);
+  CK(cudaMemsetAsync(P.line_bad, 0, line_words * 4, st));
   P.seg_frames = ctx->d_seg_frames.p; P.tile_summ = ctx->d_tile_summ.p; P.group_summ = ctx->d_group_summ.p;
   P.group_prefix = ctx->d_group_prefix.p; P.total = ctx->d_total.p;
   P.first_error = ctx->d_scalars.p; P.metrics = ctx->d_scalars.p + 1;
+  const uint32_t act_blocks = (P.n_anchors + kActThreads - 1) / kActThreads;
+  CK(ctx->d_act.ensure(P.n_anchors + 1)); CK(ctx->d_act_blk.ensure(act_blocks + 1));
+  P.act = ctx->d_act.p; P.act_blk = ctx->d_act_blk.p; P.n_act = (unsigned int*)(ctx->d_scalars.p + 12);   // [12] survives decode_finish's reset of [0..10]
   CK(cudaEventRecord(ctx->ev[1], st));
+
+  ctx->lines_launched = false;
 
   // ---- pass A + B
   if (P.n_groups) {
+    k_act_count<<<act_blocks, kActThreads, 0, st>>>(P);
+    k_act_scan<<<1, kActThreads, 0, st>>>(P, act_blocks);
+    k_act_scatter<<<act_blocks, kActThreads, 0, st>>>(P);
+    if (!getenv("ETL_DEAD_SERIAL")) {  // structure-blind UTF-8 pass over the dead segments, on the side stream underneath everything that follows
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+      CK(cudaEventRecord(ctx->ev_in, st));
+      CK(cudaStreamWaitEvent(ctx->side, ctx->ev_in, 0));
+      CK(cudaEventRecord(ctx->ev_l0, ctx->side));
+      static const int dead_ctas = getenv("ETL_DEAD_CTAS") ? atoi(getenv("ETL_DEAD_CTAS")) : 3;   // per SM (tuning knob)
+      k_utf8_dead<<<sms * dead_ctas, 256, 0, ctx->side>>>(P);
+      CK(cudaEventRecord(ctx->ev_l1, ctx->side));
+      ctx->launches += 1;
+      ctx->lines_launched = true;
+    }
     k_index<<<P.n_groups, P.tiles_per_group * P.segs_per_tile, 0, st>>>(P);
     k_scan<<<1, 512, 0, st>>>(P);
     k_tile_prefix<<<(P.n_tiles + 255) / 256, 256, 0, st>>>(P);
-    ctx->launches += 3;
+    ctx->launches += 6;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->h_total, P.total, sizeof(Summ), cudaMemcpyDeviceToHost, st));
   } else *ctx->h_total = summ_identity();
@@ -629,7 +663,6 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
   if (cin.in_tx) { carry.flags = S_HAS_B; carry.lsn = cin.final_lsn; }
   carry.ord = cin.next_tx_ordinal;
   P.carry = carry;
-  P.phase_cycles = nullptr;
   uint64_t heap_used = 0;
   for (int attempt = 0;; attempt++) {
     uint64_t cur = 0;
@@ -651,25 +684,42 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
 
     // ---- pass C
     ctx->h_scalars[0] = ~0ull;
-    for (int i = 1; i < 11; i++) ctx->h_scalars[i] = 0;
-    CK(cudaMemcpyAsync(ctx->d_scalars.p, ctx->h_scalars, 11 * 8, cudaMemcpyHostToDevice, st));
+    for (int i = 1; i < 12; i++) ctx->h_scalars[i] = 0;
+    CK(cudaMemcpyAsync(ctx->d_scalars.p, ctx->h_scalars, 12 * 8, cudaMemcpyHostToDevice, st));
+    P.n_bins = (uint32_t)std::min<size_t>(kMaxBins, std::max<size_t>(16, 16 * b->schemas.size()));
+    const size_t perm_cap = nr + 32ull * P.n_bins + 256;
+    CK(ctx->d_bin_count.ensure(kMaxBins)); CK(ctx->d_bin_cursor.ensure(kMaxBins)); CK(ctx->d_perm.ensure(perm_cap));
+    P.bin_count = ctx->d_bin_count.p; P.bin_cursor = ctx->d_bin_cursor.p; P.perm = ctx->d_perm.p;
+    P.perm_len = (unsigned int*)(ctx->d_scalars.p + 11);
+    CK(cudaMemsetAsync(P.bin_count, 0, P.n_bins * 4, st));
+    CK(cudaMemsetAsync(P.perm, 0xFF, perm_cap * 4, st));
     CK(cudaEventRecord(ctx->ev[3], st));
     if (P.n_tiles) {
-      int sms = 148;
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
       P.n_records = nr;
       k_frames<<<(P.n_anchors + 255) / 256, 256, 0, st>>>(P);
       cudaEventRecord(ctx->evk[0], st);
-      if (nr) k_walk<<<(uint32_t)((nr + kWalkThreads - 1) / kWalkThreads), kWalkThreads, sizeof(WalkShared), st>>>(P);
+      if (nr) {
+        k_bin_scan<<<1, 1024, 0, st>>>(P);
+        k_perm<<<(uint32_t)((nr + 255) / 256), 256, 0, st>>>(P);
+        k_walk<<<(uint32_t)((nr + 32ull * P.n_bins + kWalkThreads - 1) / kWalkThreads) + 64u, kWalkThreads, sizeof(WalkShared), st>>>(P);
+      }
       cudaEventRecord(ctx->evk[1], st);
-      k_utf8_spans<<<sms * 6, 256, 0, st>>>(P);
-      cudaEventRecord(ctx->evk[2], st);
-      ctx->launches += nr ? 3 : 2;
+      if (ctx->lines_launched) CK(cudaStreamWaitEvent(st, ctx->ev_l1, 0));   // join: the bitmap is complete
+      else {                                          // ETL_DEAD_SERIAL: the same pass on the main stream (tuning knob)
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        cudaEventRecord(ctx->ev_l0, st);
+        k_utf8_dead<<<sms * (getenv("ETL_DEAD_CTAS") ? atoi(getenv("ETL_DEAD_CTAS")) : 6), 256, 0, st>>>(P);
+        cudaEventRecord(ctx->ev_l1, st);
+        ctx->launches += 1;
+      }
+      if (nr) k_long_verdict<<<64, 256, 0, st>>>(P);
+      ctx->launches += nr ? 5 : 1;
       CK(cudaGetLastError());
     }
     CK(cudaMemcpyAsync((void*)(b->dev.rec_cell_base + nr), &ctx->h_total->n_cells, 8, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(ctx->ev[4], st));
-    CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars.p, 11 * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars.p, 13 * 8, cudaMemcpyDeviceToHost, st));
     heap_used = nh;
     if (!nh) break;
     CK(cudaStreamSynchronize(st));
@@ -710,11 +760,12 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
   if (P.n_tiles) {
     cudaEventElapsedTime(&S.frames_ms, ctx->ev[3], ctx->evk[0]);
     cudaEventElapsedTime(&S.walk_ms, ctx->evk[0], ctx->evk[1]);
-    cudaEventElapsedTime(&S.spans_ms, ctx->evk[1], ctx->evk[2]);
+    cudaEventElapsedTime(&S.spans_ms, ctx->ev_l0, ctx->ev_l1);   // concurrent with index / records
   }
   S.h2d_ms = ctx->pending_h2d_ms; S.d2h_ms = d2h_ms;
   S.h2d_bytes = ctx->pending_h2d_bytes;
-  S.span_bytes = ctx->h_scalars[8];
+  // bytes k_utf8_dead streamed: the dead segments (h_scalars[12] = live segment count, left by k_act_scan)
+  S.span_bytes = P.n_tiles ? std::min<uint64_t>(P.len, (uint64_t)(P.n_anchors - (uint32_t)ctx->h_scalars[12]) * P.anchor_stride) : 0;
   S.d2h_bytes = 5 * 8 + sizeof(Summ) + ((ctx->pending_flags & ETL_DECODE_RESULTS_TO_HOST) ? copy_bytes : 0);
   S.gpu_launches = ctx->launches;
   S.n_schemas = (uint32_t)b->schemas.size();

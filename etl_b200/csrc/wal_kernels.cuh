@@ -11,8 +11,14 @@
 //   k_walk    (pass C2) one thread per DML record; each CTA first groups its 256 records by frame
 //                       shape (schema, op, old-image kind) so a warp walks structurally identical
 //                       tuples in lockstep: cell i of every lane is the same column → the same parser.
-//   k_utf8_spans (C3)   TOAST-sized text is not validated by its owning thread: it is queued and
-//                       streamed here with 16-byte coalesced loads at HBM speed.
+//   k_act_*   (pass A0) compact the list of segments that contain a frame start (TOAST-heavy streams
+//                       leave most segments empty).
+//   k_utf8_dead         structure-blind UTF-8 pass over the segments WITHOUT a frame start (the inside of
+//                       TOAST-sized values) at HBM speed: one bit per 128-byte line, "some position in
+//                       this line breaks the position-local rule".  Needs no frame structure, so it runs
+//                       on a second stream underneath the latency-bound passes.
+//   k_long_verdict      after both streams join: the interior verdict of every long text cell that
+//                       k_walk listed, read from the line bitmap.
 //
 // Reference semantics: apply.rs:1687-2248 (state machine), event.rs:376-979 (tuples → rows),
 // text.rs:28-173 (cells).  HBM-bound integer/byte work — no tensor cores.
@@ -30,11 +36,14 @@ namespace etl {
 #endif
 constexpr int kTileBytes = ETL_TILE_BYTES;       // nominal tile = kTileBytes of stream (frames that START inside it)
 constexpr int kTileCap = ETL_TILE_BYTES + 4096;        // shared-memory window; bytes past it are read from global
-constexpr int kWalkThreads = 256;
-constexpr int kMaxTileFrames = ETL_TILE_BYTES / 16;   // > kTileBytes/23 + segments
+#ifndef ETL_WALK_THREADS
+#define ETL_WALK_THREADS 256
+#endif
+constexpr int kWalkThreads = ETL_WALK_THREADS;
 constexpr int kIndexThreads = 256;
-constexpr int kBigCell = 512;          // text cells at least this long are validated cooperatively
-constexpr int kBigQueue = 128;
+constexpr int kMaxBins = 4096;         // 16 frame shapes x 256 schema versions (more versions share the last bins)
+
+struct LongCell { uint32_t rec_local, seq; uint64_t l0, l1; };   // lines [l0, l1) of the stream are interior to the cell
 
 // ---- stream-state transformer (apply.rs:600-626, 1927-2006) + counters; associative under fold()
 struct Summ {
@@ -72,14 +81,6 @@ struct DevSchema {
   uint32_t has_heap;      // any numeric / bytea / uuid / array column
 };
 
-struct BigSpan {
-  uint64_t cell_off;   // stream offset of the cell's first byte
-  uint64_t span_off;   // stream offset of the first byte this span validates
-  uint32_t span_len;   // bytes to validate (position-local rule: looks back 3 bytes inside the cell)
-  uint32_t cell_len;
-  uint32_t seq;
-  uint32_t rec_local;
-};
 
 struct DecodeParams {
   const uint8_t* buf;
@@ -104,9 +105,11 @@ struct DecodeParams {
   Summ* total;               // [0] = fold of everything (shard seam summary)
   Summ* tile_prefix;         // exclusive prefix per tile (pass B2), carry not included
   unsigned int* tile_counter;  // dynamic tile scheduler of the emit pass
-  unsigned long long* phase_cycles;  // optional (profiling): per-phase clock64 totals of thread 0
-  // out-of-window remainders of very long text cells, validated by k_utf8_spans at full bandwidth
-  struct BigSpan* big_spans; unsigned int* big_count; uint32_t big_cap; unsigned long long* span_bytes;
+  // global grouping of the DML records by frame shape (k_frames counts, k_bin_scan lays out, k_perm fills)
+  uint32_t* bin_count; uint32_t* bin_cursor; uint32_t n_bins; uint32_t* perm; unsigned int* perm_len;
+  uint32_t* line_bad;               // k_utf8_dead: bit l set = line l (128 bytes) holds a UTF-8 rule violation (zeroed per batch)
+  uint32_t* dead;                   // segments without a frame start (ascending); n_dead = n_anchors - *n_act
+  struct LongCell* long_cells; unsigned int* long_count; uint32_t long_cap;   // text cells spanning whole dead segments
   // carry-in (known when pass C runs)
   Summ carry;
   uint64_t record_index_base;  // global index of this shard's first record (multi-GPU)
@@ -117,6 +120,9 @@ struct DecodeParams {
   uint64_t* rec_start_lsn; uint64_t* rec_commit_lsn; uint64_t* rec_tx_ordinal; uint64_t* rec_cell_base;
   uint8_t* cell_tag; uint64_t* cell_val; uint32_t* cell_aux;
   uint8_t* heap;
+  uint32_t* act;                    // compacted list of the segments that contain a frame start (ascending)
+  uint32_t* act_blk;                // per-1024-segment block: count, then exclusive offset
+  unsigned int* n_act;              // length of `act` (device scalar: no host round trip)
   unsigned long long* heap_top;     // bump pointer of the heap plane
   unsigned long long* arr_top;      // bump pointer of the array region, relative to arr_base
   uint64_t arr_base;
@@ -323,13 +329,74 @@ __device__ __forceinline__ const uint8_t* cstr_end(const uint8_t* q, const uint8
 }
 
 // ================================================================================================
+// pass A0: compaction.  A segment is a thread's unit of work in k_index / k_frames; a stream with large
+// values (TOAST) leaves most segments without a frame start, and a warp whose 32 segments hold three
+// live ones still issues every instruction (k_index ran at 2.9 active lanes on C5).  Listing the live
+// segments first packs them 32 to a warp.  Empty segments fold as the identity, so the scans are
+// unchanged in the compacted index space.
+constexpr int kActThreads = 1024;
+__device__ __forceinline__ bool seg_live(const DecodeParams& P, uint32_t seg) {
+  return seg < P.n_anchors && P.anchors[seg] < P.anchors[seg + 1];
+}
+__global__ void __launch_bounds__(kActThreads) k_act_count(DecodeParams P) {
+  const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = __syncthreads_count(seg_live(P, seg));
+  if (threadIdx.x == 0) P.act_blk[blockIdx.x] = (uint32_t)c;
+}
+__global__ void __launch_bounds__(kActThreads) k_act_scan(DecodeParams P, uint32_t nb) {
+  __shared__ uint32_t sh[kActThreads];
+  const uint32_t per = (nb + blockDim.x - 1) / blockDim.x;
+  const uint32_t lo = threadIdx.x * per, hi = min(lo + per, nb);
+  uint32_t acc = 0;
+  for (uint32_t i = lo; i < hi; i++) acc += P.act_blk[i];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (uint32_t d = 1; d < blockDim.x; d <<= 1) {
+    uint32_t v = sh[threadIdx.x];
+    if (threadIdx.x >= d) v += sh[threadIdx.x - d];
+    __syncthreads();
+    sh[threadIdx.x] = v;
+    __syncthreads();
+  }
+  uint32_t run = threadIdx.x ? sh[threadIdx.x - 1] : 0u;
+  for (uint32_t i = lo; i < hi; i++) { const uint32_t c = P.act_blk[i]; P.act_blk[i] = run; run += c; }
+  if (threadIdx.x == blockDim.x - 1) *P.n_act = sh[blockDim.x - 1];
+}
+__global__ void __launch_bounds__(kActThreads) k_act_scatter(DecodeParams P) {
+  __shared__ uint32_t warp_cnt[kActThreads / 32];
+  const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = seg_live(P, seg);
+  const unsigned bal = __ballot_sync(0xffffffffu, live);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) warp_cnt[wid] = __popc(bal);
+  __syncthreads();
+  uint32_t before = 0;
+  for (int k = 0; k < wid; k++) before += warp_cnt[k];
+  const uint32_t live_rank = P.act_blk[blockIdx.x] + before + __popc(bal & ((1u << lane) - 1u));   // live segments before this one
+  if (live) P.act[live_rank] = seg;
+  else if (seg < P.n_anchors) P.dead[seg - live_rank] = seg;
+}
+// compacted geometry, derived on the device
+struct ActGeom { uint32_t n_act, n_tiles, n_groups; };
+__device__ __forceinline__ ActGeom act_geom(const DecodeParams& P) {
+  ActGeom g;
+  g.n_act = *P.n_act;
+  g.n_tiles = (g.n_act + P.segs_per_tile - 1) / P.segs_per_tile;
+  g.n_groups = (g.n_tiles + P.tiles_per_group - 1) / P.tiles_per_group;
+  return g;
+}
+
+// ================================================================================================
 // pass A: index.  grid = n_groups, block = tiles_per_group * segs_per_tile threads.
 __global__ void __launch_bounds__(kIndexThreads) k_index(DecodeParams P) {
   const uint32_t spt = P.segs_per_tile;
-  const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+  const ActGeom G = act_geom(P);
+  if (blockIdx.x >= G.n_groups) return;             // the grid is sized for a stream with every segment live
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   Summ acc = summ_identity();
   uint32_t nframes = 0;
-  if (seg < P.n_anchors) {
+  if (j < G.n_act) {
+    const uint32_t seg = P.act[j];
     uint64_t pos = P.anchors[seg];
     const uint64_t stop = P.anchors[seg + 1];
     while (pos < stop) {
@@ -345,8 +412,8 @@ __global__ void __launch_bounds__(kIndexThreads) k_index(DecodeParams P) {
       nframes++;
       pos += 1ull + h.flen;
     }
-    P.seg_frames[seg] = nframes;
-    P.seg_summ[seg] = acc;
+    P.seg_frames[j] = nframes;
+    P.seg_summ[j] = acc;
   }
   // fold across the segments of each tile, then across the tiles of the group (ordered shuffles)
   // generic ordered fold over the block through shared memory (blockDim <= 256)
@@ -359,7 +426,7 @@ __global__ void __launch_bounds__(kIndexThreads) k_index(DecodeParams P) {
     Summ t = summ_identity();
     for (uint32_t k = 0; k < spt && threadIdx.x + k < blockDim.x; k++) t = fold(t, sh[threadIdx.x + k]);
     uint32_t tile = blockIdx.x * P.tiles_per_group + tile_in_block;
-    if (tile < P.n_tiles) P.tile_summ[tile] = t;
+    if (tile < G.n_tiles) P.tile_summ[tile] = t;
     sh[threadIdx.x] = t;
   }
   __syncthreads();
@@ -373,7 +440,7 @@ __global__ void __launch_bounds__(kIndexThreads) k_index(DecodeParams P) {
 // pass B2: per-tile exclusive prefix = group prefix ⊕ earlier tiles of the group (thread per tile)
 __global__ void __launch_bounds__(256) k_tile_prefix(DecodeParams P) {
   const uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tile >= P.n_tiles) return;
+  if (tile >= act_geom(P).n_tiles) return;
   const uint32_t g = tile / P.tiles_per_group;
   Summ pre = P.group_prefix[g];
   for (uint32_t t = g * P.tiles_per_group; t < tile; t++) pre = fold(pre, P.tile_summ[t]);
@@ -385,7 +452,7 @@ __global__ void __launch_bounds__(256) k_tile_prefix(DecodeParams P) {
 // pass B: exclusive scan of group summaries (single CTA; n_groups is len / (tiles_per_group*32 KiB))
 __global__ void __launch_bounds__(512) k_scan(DecodeParams P) {
   __shared__ Summ sh[512];
-  const uint32_t n = P.n_groups;
+  const uint32_t n = act_geom(P).n_groups;
   const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
   const uint32_t lo = threadIdx.x * per, hi = min(lo + per, n);
   Summ acc = summ_identity();
@@ -587,7 +654,7 @@ __device__ __forceinline__ void put_cell(const DecodeParams& P, uint64_t idx, ui
   P.cell_tag[idx] = (uint8_t)tag; P.cell_val[idx] = val; P.cell_aux[idx] = aux;
 }
 constexpr int kWideLen = 96;     // text cells at least this long are validated with 16-byte loads
-constexpr int kBigLen = 2048;    // ... and these are queued for k_utf8_spans
+constexpr int kCoopLen = 512;    // ... these by the whole warp; the part that covers whole dead segments by k_utf8_dead
 // UTF-8 validation of bytes [lo, hi) of one text cell by `nthreads` cooperating threads (a warp, a
 // CTA, or a CTA of k_utf8_spans): 16-byte aligned chunks, 4 independent loads in flight per thread.
 // An all-ASCII chunk costs one load + one test; a chunk with high bits is checked with the
@@ -598,7 +665,10 @@ __device__ __forceinline__ bool utf8_range_bad(const uint8_t* cell, uint32_t cel
   if (hi <= lo) return false;
   const uintptr_t a0 = reinterpret_cast<uintptr_t>(cell + lo);
   const uint32_t headn = min(hi - lo, (uint32_t)((16u - (uint32_t)(a0 & 15u)) & 15u));
-  if (t == 0) bad |= !utf8_chunk_valid(cell, cell_len, lo, min(lo + headn + 19u, hi));
+  if (t == 0) {                                       // head: byte-serial only when it (or its look-back) has high bits
+    const uint32_t hhi = min(lo + headn + 19u, hi), hlo = lo >= 3u ? lo - 3u : 0u;
+    if (has_high_bits(cell + hlo, hhi - hlo)) bad |= !utf8_chunk_valid(cell, cell_len, lo, hhi);
+  }
   const uint32_t body0 = lo + headn;
   const uint32_t nchunks = (hi - body0) / 16u;
   const uint4* body = reinterpret_cast<const uint4*>(cell + body0);
@@ -621,24 +691,73 @@ __device__ __forceinline__ bool utf8_range_bad(const uint8_t* cell, uint32_t cel
     }
   }
   const uint32_t tail0 = body0 + nchunks * 16u;
-  if (t == nthreads - 1 && tail0 < hi) bad |= !utf8_chunk_valid(cell, cell_len, tail0, hi);
+  if (t == nthreads - 1 && tail0 < hi) {
+    const uint32_t tlo = tail0 >= 3u ? tail0 - 3u : 0u;
+    if (has_high_bits(cell + tlo, hi - tlo)) bad |= !utf8_chunk_valid(cell, cell_len, tail0, hi);
+  }
   return bad;
 }
-__device__ __forceinline__ bool utf8_wide_bad(const uint8_t* ptr, uint32_t len, uint32_t t, uint32_t nthreads) {
-  return utf8_range_bad(ptr, len, 0, len, t, nthreads);
-}
-
-// streams the out-of-window remainders of very long text cells: one CTA per span, 64 bytes in
-// flight per thread.  HBM-bound: 16 bytes loaded per 3 instructions per lane.
-__global__ void __launch_bounds__(256) k_utf8_spans(DecodeParams P) {
-  const uint32_t n = min(*P.big_count, P.big_cap);
-  for (uint32_t e = blockIdx.x; e < n; e += gridDim.x) {
-    const BigSpan sp = P.big_spans[e];
-    const uint32_t lo = (uint32_t)(sp.span_off - sp.cell_off);
-    const bool bad = utf8_range_bad(P.buf + sp.cell_off, sp.cell_len, lo, lo + sp.span_len, threadIdx.x, blockDim.x);
-    if (__syncthreads_or(bad) && threadIdx.x == 0) report_error(P, P.record_index_base + sp.rec_local, sp.seq, ETL_E_UTF8);
+// Structure-blind UTF-8 pass.  The position-local rule (utf8_step_bad) needs only the three preceding
+// bytes, so the verdict for position i of a cell is the verdict for stream position a+i whenever the
+// three predecessors lie inside the cell.  A segment without a frame start lies inside one frame; the
+// segments that lie inside one text cell are what k_walk asks about.  One warp per dead segment, 2 KiB
+// (4 coalesced 16-byte loads per lane) per pass; the bitmap is written only where a violation is found.
+__global__ void __launch_bounds__(256) k_utf8_dead(DecodeParams P) {
+  const uint32_t n_dead = P.n_anchors - *P.n_act;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; d < n_dead; d += nwarps) {
+    const uint64_t s0 = (uint64_t)P.dead[d] * P.anchor_stride;
+    const uint64_t s1 = s0 + P.anchor_stride < P.len ? s0 + P.anchor_stride : P.len;
+    for (uint64_t base = s0; base < s1; base += 2048ull) {
+      uint4 x[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint64_t off = base + (uint64_t)(k * 32 + (int)lane) * 16ull;
+        x[k] = off < s1 ? *reinterpret_cast<const uint4*>(P.buf + off) : make_uint4(0, 0, 0, 0);   // +64 bytes of padding are readable
+      }
+      uint32_t word = 0;
+      uint32_t carry = base >= 4 ? *reinterpret_cast<const uint32_t*>(P.buf + base - 4) : 0u;   // last word before the pass
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        uint32_t pw = __shfl_up_sync(0xffffffffu, x[k].w, 1);      // the previous 16 bytes' last word
+        if (lane == 0) pw = carry;
+        carry = __shfl_sync(0xffffffffu, x[k].w, 31);
+        const uint32_t h = x[k].x | x[k].y | x[k].z | x[k].w;
+        bool bad = false;
+        if ((h & 0x80808080u) | (pw & 0x80808000u)) {             // high bits here or in the three bytes before
+          const uint64_t off = base + (uint64_t)(k * 32 + (int)lane) * 16ull;
+          if (off < s1) bad = !utf8_chunk_valid_at(P.buf, P.len, off, off + 16ull < P.len ? off + 16ull : P.len);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, bad);
+#pragma unroll
+        for (int m = 0; m < 4; m++) if ((bal >> (8 * m)) & 0xFFu) word |= 1u << (k * 4 + m);
+      }
+      // base is a multiple of min(stride, 2048): the (at most 16) bits of this pass stay inside one word
+      if (word && lane == 0) atomicOr(&P.line_bad[(base >> 7) >> 5], word << ((base >> 7) & 31u));
+    }
   }
 }
+// any flagged line in [l0, l1)?
+__device__ __forceinline__ bool lines_any_bad(const uint32_t* bm, uint64_t l0, uint64_t l1) {
+  const uint64_t w0 = l0 >> 5, w1 = (l1 - 1) >> 5;
+  for (uint64_t w = w0; w <= w1; w++) {
+    uint32_t m = 0xFFFFFFFFu;
+    if (w == w0) m &= 0xFFFFFFFFu << (l0 & 31);
+    if (w == w1 && (l1 & 31)) m &= (1u << (l1 & 31)) - 1u;
+    if (bm[w] & m) return true;
+  }
+  return false;
+}
+__global__ void __launch_bounds__(256) k_long_verdict(DecodeParams P) {
+  const uint32_t n = min(*P.long_count, P.long_cap);
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const LongCell c = P.long_cells[e];
+    if (lines_any_bad(P.line_bad, c.l0, c.l1)) report_error(P, P.record_index_base + c.rec_local, c.seq, ETL_E_UTF8);
+  }
+}
+// out of line: k_walk's registers are the scarce resource
+__device__ __noinline__ bool utf8_medium_bad(const uint8_t* cell, uint32_t len) { return utf8_range_bad(cell, len, 0, len, 0, 1); }
 
 __device__ __forceinline__ uint32_t warp_incl_sum(uint32_t v, int lane) {
 #pragma unroll
@@ -652,18 +771,73 @@ __device__ __forceinline__ int32_t warp_incl_max(int32_t v, int lane) {
 }
 
 // ================================================================================================
+// Shape bins.  A warp of k_walk is fastest when its 32 records have the same frame shape (table
+// version, operation, old-image kind): wire cell i is then the same column for every lane and one parser
+// runs for all of them.  Output positions are fixed by the scan, so records can be walked in any order:
+// k_frames histograms the shapes, k_bin_scan lays the bins out (each padded to a whole warp), k_perm
+// writes the record indices bin by bin, and k_walk thread t walks record perm[t].
+__device__ __forceinline__ uint32_t walk_bin(const DecodeParams& P, int32_t schema, uint32_t kind, uint32_t rflags) {
+  const uint32_t b = ((uint32_t)schema << 4) | (kind == 'I' ? 0u : (kind == 'U' ? 4u : 8u)) | (rflags & 3u);
+  return b < P.n_bins ? b : P.n_bins - 16u + (b & 15u);
+}
+__global__ void __launch_bounds__(1024) k_bin_scan(DecodeParams P) {
+  __shared__ uint32_t sh[1024];
+  const uint32_t per = (P.n_bins + 1023u) / 1024u;
+  const uint32_t lo = threadIdx.x * per, hi = min(lo + per, P.n_bins);
+  uint32_t acc = 0;
+  for (uint32_t i = lo; i < hi; i++) acc += (P.bin_count[i] + 31u) & ~31u;
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (uint32_t d = 1; d < 1024; d <<= 1) {
+    uint32_t v = sh[threadIdx.x];
+    if (threadIdx.x >= d) v += sh[threadIdx.x - d];
+    __syncthreads();
+    sh[threadIdx.x] = v;
+    __syncthreads();
+  }
+  uint32_t run = threadIdx.x ? sh[threadIdx.x - 1] : 0u;
+  for (uint32_t i = lo; i < hi; i++) { P.bin_cursor[i] = run; run += (P.bin_count[i] + 31u) & ~31u; }
+  if (threadIdx.x == 1023) *P.perm_len = sh[1023];
+}
+__global__ void __launch_bounds__(256) k_perm(DecodeParams P) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool dml = false;
+  uint32_t bin = 0;
+  if (r < P.n_records) {
+    const uint32_t kind = P.rec_kind[r];
+    const int32_t sc = P.rec_schema[r];
+    if ((kind == 'I' || kind == 'U' || kind == 'D') && sc >= 0) { dml = true; bin = walk_bin(P, sc, kind, P.rec_flags[r]); }
+  }
+  const unsigned vm = __ballot_sync(0xffffffffu, dml);
+  if (dml) {                                          // one atomic per bin per warp
+    const unsigned mask = __match_any_sync(vm, bin);
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&P.bin_cursor[bin], (uint32_t)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    P.perm[base + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)r;
+  }
+}
+
+// ================================================================================================
 // pass C1: records.  Thread per anchor segment; frames of a segment are replayed in order with the
 // running stream state (apply.rs:600-626, 1687-2248), exactly like the reference's apply loop but
 // for ~2 KiB of stream per thread.
 __global__ void __launch_bounds__(256) k_frames(DecodeParams P) {
-  const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+  const ActGeom G = act_geom(P);
+  if (blockIdx.x * blockDim.x >= G.n_act) return;   // grid sized for the all-live case
+  __shared__ uint32_t hist[kMaxBins];               // frame shapes of the CTA's DML records
+  for (uint32_t i = threadIdx.x; i < P.n_bins; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t events = 0;
   // exclusive prefix of this segment: carry ⊕ tile prefix ⊕ earlier segments of the tile.  A tile is
   // exactly one warp of segments (segs_per_tile == 32), so the last part is a warp shuffle scan.
   Summ st;
   {
     const int lane = threadIdx.x & 31;
-    Summ inc = seg < P.n_anchors ? P.seg_summ[seg] : summ_identity();
+    Summ inc = j < G.n_act ? P.seg_summ[j] : summ_identity();
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       Summ up;
@@ -677,11 +851,12 @@ __global__ void __launch_bounds__(256) k_frames(DecodeParams P) {
     ex.n_cells = __shfl_up_sync(0xffffffffu, inc.n_cells, 1); ex.heap = 0;
     ex.n_rec = __shfl_up_sync(0xffffffffu, inc.n_rec, 1); ex.flags = __shfl_up_sync(0xffffffffu, inc.flags, 1);
     if (lane == 0) ex = summ_identity();
-    const uint32_t tile = seg / 32u;
-    const Summ tp = tile < P.n_tiles ? P.tile_prefix[tile] : summ_identity();
+    const uint32_t tile = j / 32u;
+    const Summ tp = tile < G.n_tiles ? P.tile_prefix[tile] : summ_identity();
     st = fold(fold(P.carry, tp), ex);
   }
-  if (seg < P.n_anchors) {
+  if (j < G.n_act) {
+    const uint32_t seg = P.act[j];
     uint64_t pos = P.anchors[seg];
     const uint64_t stop = P.anchors[seg + 1];
     while (pos < stop) {
@@ -789,7 +964,10 @@ __global__ void __launch_bounds__(256) k_frames(DecodeParams P) {
         }
       }
       // a record k_walk must not touch keeps schema = -1 only when it failed before conversion
-      if (!ok && (h.kind == 'I' || h.kind == 'U' || h.kind == 'D')) rschema = -1;
+      if (h.kind == 'I' || h.kind == 'U' || h.kind == 'D') {
+        if (!ok) rschema = -1;
+        else if (rschema >= 0) atomicAdd(&hist[walk_bin(P, rschema, h.kind, rflags)], 1u);
+      }
       P.rec_off[ridx] = pos; P.rec_kind[ridx] = (uint8_t)h.kind; P.rec_flags[ridx] = (uint8_t)rflags;
       P.rec_rel[ridx] = rrel; P.rec_schema[ridx] = rschema; P.rec_start_lsn[ridx] = start_lsn;
       P.rec_commit_lsn[ridx] = commit_lsn; P.rec_tx_ordinal[ridx] = ordinal; P.rec_cell_base[ridx] = my_cell0;
@@ -802,6 +980,8 @@ __global__ void __launch_bounds__(256) k_frames(DecodeParams P) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) events += __shfl_down_sync(0xffffffffu, events, d);
   if ((threadIdx.x & 31) == 0 && events) atomicAdd(&P.metrics[3], (unsigned long long)events);
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < P.n_bins; i += blockDim.x) if (hist[i]) atomicAdd(&P.bin_count[i], hist[i]);
 }
 
 // ================================================================================================
@@ -938,62 +1118,32 @@ __device__ __forceinline__ bool wk_step(const DecodeParams& P, Wk& w, TextCell& 
 }
 
 struct WalkShared {
-  uint32_t dict_key[64];
-  uint32_t dict_cnt[64];
-  uint32_t dict_start[64];
-  uint32_t n_keys;
-  uint32_t order[kWalkThreads];
   alignas(4) uint8_t json_tables[256 + 32 * kJsonClasses];   // byte classes + transitions (json_valid_sync)
 };
 
-__global__ void __launch_bounds__(kWalkThreads, ETL_WALK_CTAS) k_walk(DecodeParams P) {
+__global__ void __launch_bounds__(kWalkThreads, ETL_WALK_CTAS * 256 / kWalkThreads) k_walk(DecodeParams P) {
   extern __shared__ __align__(16) uint8_t walk_smem[];
   WalkShared& sh = *reinterpret_cast<WalkShared*>(walk_smem);
   const int lane = threadIdx.x & 31;
-  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  // ---- 1. group the CTA's records by frame shape so that warps walk look-alike tuples
-  uint32_t key = 0xFFFFFFFFu;
-  if (r < P.n_records) {
-    const uint32_t kind = P.rec_kind[r];
-    const int32_t sc = P.rec_schema[r];
-    if ((kind == 'I' || kind == 'U' || kind == 'D') && sc >= 0) key = ((uint32_t)sc << 4) | ((kind == 'I') ? 0u : (kind == 'U' ? 4u : 8u)) | (P.rec_flags[r] & 3u);
-  }
-  if (threadIdx.x < 64) { sh.dict_key[threadIdx.x] = 0xFFFFFFFFu; sh.dict_cnt[threadIdx.x] = 0; }
-  if (threadIdx.x == 0) sh.n_keys = 0;
+  const uint32_t n_perm = *P.perm_len;
+  // chunk of the binned order for this CTA.  Bins are contiguous and differ in cost per record (an update
+  // with a full old image walks twice the cells of an insert): consecutive CTAs take chunks 1/64 of the
+  // order apart so that every SM gets the same mix.  The grid is sized for the worst-case padding.
+  const uint32_t n_chunks = (n_perm + blockDim.x - 1) / blockDim.x, cols = (n_chunks + 63u) / 64u;
+  const uint32_t chunk = (blockIdx.x & 63u) * cols + (blockIdx.x >> 6);
+  if ((blockIdx.x >> 6) >= cols || chunk >= n_chunks) return;
   for (uint32_t k = threadIdx.x; k < sizeof(sh.json_tables) / 4; k += blockDim.x)
     reinterpret_cast<uint32_t*>(sh.json_tables)[k] = reinterpret_cast<const uint32_t*>(kJsonTables)[k];
   __syncthreads();
-  // dictionary of distinct keys (open addressing, 64 slots; overflow → slot 63 is shared = no grouping for the excess)
-  uint32_t slot = 63;
-  if (key != 0xFFFFFFFFu) {
-    uint32_t hsh = (key * 2654435761u) >> 26;
-    for (uint32_t probe = 0; probe < 63; probe++) {
-      const uint32_t sl = (hsh + probe) % 63u;
-      const uint32_t prev = atomicCAS(&sh.dict_key[sl], 0xFFFFFFFFu, key);
-      if (prev == 0xFFFFFFFFu || prev == key) { slot = sl; break; }
-    }
-  }
-  const uint32_t my_rank = (key != 0xFFFFFFFFu) ? atomicAdd(&sh.dict_cnt[slot], 1u) : 0u;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const uint32_t c0 = sh.dict_cnt[threadIdx.x], c1 = sh.dict_cnt[threadIdx.x + 32];
-    const uint32_t i0 = warp_incl_sum(c0, lane);
-    const uint32_t t0 = __shfl_sync(0xffffffffu, i0, 31);
-    const uint32_t i1 = warp_incl_sum(c1, lane);
-    sh.dict_start[threadIdx.x] = i0 - c0;
-    sh.dict_start[threadIdx.x + 32] = t0 + i1 - c1;
-    if (threadIdx.x == 31) sh.n_keys = t0 + i1;     // number of DML records in the CTA
-  }
-  __syncthreads();
-  if (key != 0xFFFFFFFFu) sh.order[sh.dict_start[slot] + my_rank] = threadIdx.x;
-  __syncthreads();
-  const uint32_t n_dml = sh.n_keys;
-  // ---- 2. thread t walks the t-th record of the grouped order
+  // ---- 1. this thread's record: entry t of the shape-binned order (0xFFFFFFFF = bin padding)
+  const uint32_t t = chunk * blockDim.x + threadIdx.x;
+  const uint32_t my_rec = t < n_perm ? P.perm[t] : 0xFFFFFFFFu;
+  // ---- 2. walk it
   Wk w;
   w.bits = W_DONE; w.tb = 0; w.rec_local = 0; w.base = nullptr; w.pos = 0; w.end = 0; w.col_base = 0; w.nc_ni = 0; w.cell0 = 0;
   w.rem_wire = 0; w.cmap_kout = 0; w.keyi_nold = 0;
-  if (threadIdx.x < n_dml) {
-    const uint64_t rr = (uint64_t)blockIdx.x * blockDim.x + sh.order[threadIdx.x];
+  if (my_rec != 0xFFFFFFFFu) {
+    const uint64_t rr = my_rec;
     const uint8_t* fp = P.buf + P.rec_off[rr];
     const DevSchema& s = P.schemas[P.schema_by_batch[P.rec_schema[rr]]];
 #if ETL_WALK_PREFETCH
@@ -1026,21 +1176,23 @@ __global__ void __launch_bounds__(kWalkThreads, ETL_WALK_CTAS) k_walk(DecodePara
     bool do_parse = false;
     const uint64_t soff = (uint64_t)(w.base - P.buf) + tc.voff;
     bool need_slow = false;                            // small cell with non-ASCII bytes: validated by the whole warp below
+    uint32_t r0_hi = 0, r1_lo = 0, r1_hi = 0;          // long cell: byte ranges [0, r0_hi) and [r1_lo, r1_hi) validated by the whole warp
     if (is_text) {
       if (tc.kind == ETL_K_STRING) { o.tag = ETL_CELL_STRING; o.val = soff; o.aux = tc.len; }
-      if (tc.kind == ETL_K_STRING && tc.len >= (uint32_t)kBigLen) {   // TOAST-sized: queue for the streaming validator
-        const uint32_t pieces = (tc.len + (256u << 10) - 1u) / (256u << 10);
-        const uint32_t at = atomicAdd(P.big_count, pieces);
-        if (at + pieces <= P.big_cap) {
-          atomicAdd(P.span_bytes, (unsigned long long)tc.len);
-          for (uint32_t k = 0; k < pieces; k++) {
-            BigSpan sp;
-            sp.cell_off = soff; sp.span_off = soff + (uint64_t)k * (256u << 10);
-            sp.span_len = min(tc.len - k * (256u << 10), 256u << 10); sp.cell_len = tc.len; sp.seq = tc.seq; sp.rec_local = w.rec_local;
-            P.big_spans[at + k] = sp;
+      if (tc.len >= (uint32_t)kCoopLen) {
+        // whole segments inside the cell hold no frame start: k_utf8_dead covers them, the rest is done here
+        const uint64_t cb = soff + tc.len;
+        const uint64_t S0 = (soff + 3ull + P.anchor_stride - 1ull) & ~(uint64_t)(P.anchor_stride - 1u), S1 = cb & ~(uint64_t)(P.anchor_stride - 1u);
+        r0_hi = tc.len;
+        if (S0 < S1) {
+          const uint32_t at = atomicAdd(P.long_count, 1u);
+          if (at < P.long_cap) {
+            LongCell lc; lc.rec_local = w.rec_local; lc.seq = tc.seq; lc.l0 = S0 >> 7; lc.l1 = S1 >> 7;
+            P.long_cells[at] = lc;
+            r0_hi = (uint32_t)(S0 - soff); r1_lo = (uint32_t)(S1 - soff); r1_hi = tc.len;
           }
-        } else if (utf8_range_bad(tv, tc.len, 0, tc.len, 0, 1)) code = ETL_E_UTF8;
-      } else if (tc.len >= (uint32_t)kWideLen) { if (utf8_range_bad(tv, tc.len, 0, tc.len, 0, 1)) code = ETL_E_UTF8; }
+        }
+      } else if (tc.len >= (uint32_t)kWideLen) { if (utf8_medium_bad(tv, tc.len)) code = ETL_E_UTF8; }
       else need_slow = has_high_bits(tv, tc.len);
     }
     __syncwarp();
@@ -1057,6 +1209,16 @@ __global__ void __launch_bounds__(kWalkThreads, ETL_WALK_CTAS) k_walk(DecodePara
       }
       bad = __any_sync(0xffffffffu, bad);
       if (lane == src && bad) code = ETL_E_UTF8;
+    }
+    for (int round = 0; round < 2; round++) {
+      const uint32_t my_lo = round ? r1_lo : 0u, my_hi = round ? r1_hi : r0_hi;
+      for (unsigned sm = __ballot_sync(0xffffffffu, my_hi > my_lo); sm; sm &= sm - 1) {
+        const int src = __ffs(sm) - 1;
+        const uint8_t* cp = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(tv), src));
+        const uint32_t cn = __shfl_sync(0xffffffffu, tc.len, src), lo = __shfl_sync(0xffffffffu, my_lo, src), hi = __shfl_sync(0xffffffffu, my_hi, src);
+        const bool bad = __any_sync(0xffffffffu, utf8_range_bad(cp, cn, lo, hi, (uint32_t)lane, 32u));
+        if (lane == src && bad) code = ETL_E_UTF8;
+      }
     }
     do_parse = is_text && !code && tc.kind != ETL_K_STRING;
     const unsigned pm = __ballot_sync(0xffffffffu, do_parse);

@@ -218,7 +218,7 @@ int etl_stage_append_framed(etl_stager*, const uint8_t* framed, uint64_t len);
 
 typedef struct etl_dec_input {
   const uint8_t* host_buf;       /* framed stream in host memory (pinned if from the stager) */
-  const uint8_t* dev_buf;        /* optional: same bytes already resident in HBM (NULL → library copies) */
+  const uint8_t* dev_buf;        /* optional: same bytes already resident in HBM, 16-byte aligned (NULL → library copies) */
   uint64_t len;
   const uint64_t* anchors;       /* host array, n_anchors entries, see etl_stager */
   const uint64_t* dev_anchors;   /* optional: n_anchors + 1 entries resident in HBM, last entry = len */
@@ -315,9 +315,9 @@ typedef struct etl_dec_summary {
   float emit_ms;          /* pass C: k_frames + k_walk + k_utf8_spans */
   float frames_ms;        /* k_frames */
   float walk_ms;          /* k_walk */
-  float spans_ms;         /* k_utf8_spans */
+  float spans_ms;         /* k_utf8_lines (structure-blind UTF-8 pass; runs concurrently with index/records) */
   uint64_t h2d_bytes, d2h_bytes; /* bytes copied host→device / device→host for this batch */
-  uint64_t span_bytes;    /* bytes of TOAST-sized text handed to k_utf8_spans (its algorithmic bytes) */
+  uint64_t span_bytes;    /* bytes streamed by k_utf8_lines (= len; its algorithmic bytes) */
 } etl_dec_summary;
 
 int etl_dec_batch_planes(const etl_dec_batch*, int host, etl_dec_planes* out);

@@ -325,3 +325,60 @@ def test_array_heap_retry(gpu, oracle_mod):
     got, want = both(gpu, oracle_mod, {93: cols}, stream)
     assert want.first_error[0] is None
     assert_planes_equal(got, want, stream)
+
+
+def test_long_cell_utf8_boundaries(gpu, oracle_mod):
+    """Long text takes its interior UTF-8 verdict from the structure-blind line bitmap and its head / tail
+    from direct checks: poison bytes (and split multi-byte sequences) at every kind of position — first
+    bytes of the cell, around the first and last 128-byte line boundary, the last bytes — and valid
+    multi-byte sequences that straddle line boundaries.  Verdicts must match the oracle byte for byte."""
+    cols = [sc.col("id", sc.INT8, 1), sc.col("doc", sc.TEXT, None, True)]
+    rel = pg.relation(94, "public", "docs2", "d", sc.rel_cols(cols, {"id"}))
+    rng = np.random.default_rng(5)
+    n = 3000
+
+    def build(payload: bytes) -> bytes:
+        w = pg.StreamWriter()
+        tx = sc.Tx(w)
+        tx.begin()
+        w.emit(rel)
+        w.emit(pg.insert(94, ["1", "pad" * 7]))
+        w.emit(_raw_text_insert(94, b"2", payload))
+        tx.commit()
+        return w.bytes()
+
+    base = bytearray(rng.integers(97, 123, size=n, dtype=np.uint8).tobytes())
+    clean = build(bytes(base))
+    got, want = both(gpu, oracle_mod, {94: cols}, clean)
+    assert want.first_error[0] is None
+    assert_planes_equal(got, want, clean)
+    cell_off = clean.index(bytes(base))            # absolute stream offset of the value
+    l0 = (-(cell_off + 3)) % 128 + 3               # cell-relative offset of the first interior line
+    last_line = (cell_off + n) // 128 * 128 - cell_off
+    spots = sorted({0, 1, 2, 3, l0 - 4, l0 - 1, l0, l0 + 1, l0 + 127, l0 + 128, 1500, last_line - 1, last_line, last_line + 1, n - 4, n - 2, n - 1})
+    emoji = "🤔".encode()
+    for p in spots:
+        for kind in ("ff", "cont", "lead", "emoji"):
+            b = bytearray(base)
+            if kind == "ff":
+                b[p] = 0xFF
+            elif kind == "cont":
+                b[p] = 0x80                          # continuation byte without a lead
+            elif kind == "lead":
+                b[p] = 0xE2                          # lead byte followed by ASCII (or by the end of the cell)
+            else:
+                if p + 4 > n:
+                    continue
+                b[p:p + 4] = emoji                   # valid 4-byte sequence, possibly straddling a line boundary
+            s = build(bytes(b))
+            got, want = both(gpu, oracle_mod, {94: cols}, s)
+            assert got.first_error == want.first_error, (p, kind, got.first_error, want.first_error)
+            assert (want.first_error[0] is None) == (kind == "emoji"), (p, kind)
+
+
+def _raw_text_insert(rel_id: int, key: bytes, payload: bytes) -> bytes:
+    """Insert message whose second column carries arbitrary bytes (pg.insert encodes str as UTF-8)."""
+    import struct
+    body = b"I" + struct.pack(">I", rel_id) + b"N" + struct.pack(">H", 2)
+    body += b"t" + struct.pack(">I", len(key)) + key + b"t" + struct.pack(">I", len(payload)) + payload
+    return body
