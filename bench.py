@@ -254,7 +254,7 @@ def main():
         e0.record()
         for _ in range(steps):
             s = step(resident)
-            emit.append((s.frames_ms, s.walk_ms, s.spans_ms, s.kernel_ms))
+            emit.append((s.frames_ms, s.walk_ms, s.spans_ms, s.kernel_ms, s.cells_ms))
             index.append(s.index_ms)
             launches += s.gpu_launches
         e1.record()
@@ -306,14 +306,15 @@ def main():
         # algorithmic bytes: every byte of the staged stream once + the anchor index
         algo_bytes = nbytes + 8 * (int(host_view.n_anchors) + 1)
         km = np.mean(np.array(emit_ms, dtype=np.float64), axis=0)           # frames, walk, dead-segment pass, critical path (ms, rank 0)
-        kern = {"k_act*+k_index+k_scan+k_tile_prefix": float(np.mean(index_ms)), "k_frames": float(km[0]), "k_walk": float(km[1]),
+        kern = {"k_act*+k_index+k_scan+k_tile_prefix": float(np.mean(index_ms)), "k_frames": float(km[0]),
+                "k_bin_scan+k_perm+k_walk": float(km[1]), "k_cells+k_copy": float(km[4]),
                 "k_utf8_dead (side stream, overlapped)": float(km[2])}
         span_bytes = int(last["span_bytes"])
         # bytes each kernel is responsible for: k_utf8_dead streams the segments without a frame start (the inside of
         # TOAST-sized values), k_walk everything else in the DML tuples, k_frames / k_index the frame heads (counted
         # with k_walk's share here)
-        kbytes = {"k_utf8_dead": span_bytes, "k_walk": algo_bytes - span_bytes}
-        ktime = {"k_utf8_dead": float(km[2]), "k_walk": float(km[1])}
+        kbytes = {"k_utf8_dead": span_bytes, "k_walk": algo_bytes - span_bytes, "k_cells": algo_bytes - span_bytes}
+        ktime = {"k_utf8_dead": float(km[2]), "k_walk": float(km[1]), "k_cells": float(km[4])}
         dominant = max(ktime, key=lambda k: ktime[k])
         pipeline_ms = float(km[3])                                          # index + records passes incl. the join with the side stream
         emit_avg = ktime[dominant]

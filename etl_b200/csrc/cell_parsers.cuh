@@ -559,10 +559,9 @@ __device__ __forceinline__ uint32_t swar_parse8(uint64_t x) {
 __device__ __forceinline__ bool swar_all_digits(uint64_t x) {
   return (((x + 0x4646464646464646ull) | (x - 0x3030303030303030ull)) & 0x8080808080808080ull) == 0ull;
 }
-__device__ __forceinline__ uint64_t pow10_u64(uint32_t k) {  // k in 0..8
-  const uint64_t t[9] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull};
-  return t[k];
-}
+// a table in global memory: a local array would be re-materialised (18 stores) by every thread of k_cells
+__device__ const uint64_t kPow10[9] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull};
+__device__ __forceinline__ uint64_t pow10_u64(uint32_t k) { return kPow10[k]; }  // k in 0..8
 
 // Rust FromStr for integers (text.rs:49-60,159-161), 8 digits per step.
 __device__ __forceinline__ uint32_t parse_int_sync(unsigned mask, const uint8_t* s, uint32_t n, bool is_signed,

@@ -193,7 +193,9 @@ struct etl_dec_ctx {
   DevBuf<uint32_t> d_schema_by_batch;
   DevBuf<DevSchema> d_schemas;
   DevBuf<uint8_t> d_col_kind, d_col_flags;
-  DevBuf<uint32_t> d_line_bad, d_dead, d_bin_count, d_bin_cursor, d_perm;
+  DevBuf<uint32_t> d_line_bad, d_dead, d_bin_count, d_bin_cursor, d_perm, d_bin_start, d_bin_row_base, d_row_chunk;
+  DevBuf<CellDesc> d_desc;
+  DevBuf<CopyPair> d_copies;
   DevBuf<LongCell> d_long;
   DevBuf<unsigned long long> d_scalars;  // [0] first_error key, [1..4] metrics
   DevBuf<uint64_t> d_rel_err_off;
@@ -321,7 +323,6 @@ int etl_dec_create(int device_id, etl_dec_ctx** out) {
   cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming); cudaEventCreate(&ctx->ev_l0); cudaEventCreate(&ctx->ev_l1);
   cudaHostAlloc((void**)&ctx->h_total, sizeof(Summ), cudaHostAllocDefault);
   cudaHostAlloc((void**)&ctx->h_scalars, 16 * sizeof(unsigned long long), cudaHostAllocDefault);
-  cudaFuncSetAttribute(k_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkShared));
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
     uint64_t thr = UINT64_MAX;
@@ -614,7 +615,7 @@ int etl_dec_decode_begin(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t fla
   const Summ& T = *ctx->h_total;
   if (seam_out) {
     memset(seam_out, 0, sizeof *seam_out);
-    seam_out->n_records = T.n_rec; seam_out->n_cells = T.n_cells; seam_out->heap_bytes = T.heap;
+    seam_out->n_records = T.n_rec; seam_out->n_cells = T.n_cells; seam_out->heap_bytes = 0;
     seam_out->lsn = T.lsn; seam_out->ord = T.ord;
     seam_out->has_begin = (T.flags & S_HAS_B) ? 1 : 0; seam_out->closed = (T.flags & S_CLOSED) ? 1 : 0;
   }
@@ -691,6 +692,20 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
     CK(ctx->d_bin_count.ensure(kMaxBins)); CK(ctx->d_bin_cursor.ensure(kMaxBins)); CK(ctx->d_perm.ensure(perm_cap));
     P.bin_count = ctx->d_bin_count.p; P.bin_cursor = ctx->d_bin_cursor.p; P.perm = ctx->d_perm.p;
     P.perm_len = (unsigned int*)(ctx->d_scalars.p + 11);
+    CK(ctx->d_bin_start.ensure(kMaxBins)); CK(ctx->d_bin_row_base.ensure(kMaxBins));
+    P.bin_start = ctx->d_bin_start.p; P.bin_row_base = ctx->d_bin_row_base.p; P.n_batch_schemas = (uint32_t)b->schemas.size();
+    // descriptor rows: Σ over bins ceil(count/32)·slots(bin) ≤ slots/32 + Σ slots(bin) ≤ slots/32 + 32·Σ n_cols
+    uint64_t sum_cols = 0, max_cols = 0;
+    for (const RelVersion& v : b->schemas) { sum_cols += v.kind.size(); max_cols = std::max<uint64_t>(max_cols, v.kind.size()); }
+    uint64_t rows_cap = T.slots / 32 + 32 * sum_cols + 64;
+    if (16 * b->schemas.size() > (size_t)kMaxBins) rows_cap = ((uint64_t)nr * 2 * max_cols) / 32 + 64ull * kMaxBins / 16 * max_cols + 64;   // clamped bins take the widest schema
+    if (rows_cap >= (1ull << 31)) { ctx->last_error = "batch too large for the descriptor plane"; delete b; return ETL_ERR_INVALID_ARG; }
+    P.desc_row_cap = (uint32_t)rows_cap;
+    CK(ctx->d_desc.ensure(rows_cap * 32)); CK(ctx->d_row_chunk.ensure(rows_cap));
+    P.desc = ctx->d_desc.p; P.row_chunk = ctx->d_row_chunk.p; P.desc_rows = (unsigned int*)(ctx->d_scalars.p + 13);
+    P.copy_cap = (uint32_t)std::min<uint64_t>(nc / 2 + 16, 0xFFFFFFFFull);
+    CK(ctx->d_copies.ensure(P.copy_cap));
+    P.copies = ctx->d_copies.p; P.copy_count = (unsigned int*)(ctx->d_scalars.p + 8);
     CK(cudaMemsetAsync(P.bin_count, 0, P.n_bins * 4, st));
     CK(cudaMemsetAsync(P.perm, 0xFF, perm_cap * 4, st));
     CK(cudaEventRecord(ctx->ev[3], st));
@@ -701,8 +716,11 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
       if (nr) {
         k_bin_scan<<<1, 1024, 0, st>>>(P);
         k_perm<<<(uint32_t)((nr + 255) / 256), 256, 0, st>>>(P);
-        k_walk<<<(uint32_t)((nr + 32ull * P.n_bins + kWalkThreads - 1) / kWalkThreads) + 64u, kWalkThreads, sizeof(WalkShared), st>>>(P);
-      }
+        k_walk<<<(uint32_t)((nr + 32ull * P.n_bins + kWalkThreads - 1) / kWalkThreads) + 64u, kWalkThreads, 0, st>>>(P);
+        cudaEventRecord(ctx->evk[2], st);
+        k_cells<<<(uint32_t)((rows_cap * 32 + 255) / 256), 256, 0, st>>>(P);
+        k_copy<<<128, 256, 0, st>>>(P);
+      } else cudaEventRecord(ctx->evk[2], st);
       cudaEventRecord(ctx->evk[1], st);
       if (ctx->lines_launched) CK(cudaStreamWaitEvent(st, ctx->ev_l1, 0));   // join: the bitmap is complete
       else {                                          // ETL_DEAD_SERIAL: the same pass on the main stream (tuning knob)
@@ -714,7 +732,7 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
         ctx->launches += 1;
       }
       if (nr) k_long_verdict<<<64, 256, 0, st>>>(P);
-      ctx->launches += nr ? 5 : 1;
+      ctx->launches += nr ? 7 : 1;
       CK(cudaGetLastError());
     }
     CK(cudaMemcpyAsync((void*)(b->dev.rec_cell_base + nr), &ctx->h_total->n_cells, 8, cudaMemcpyHostToDevice, st));
@@ -759,7 +777,8 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
   S.index_ms = ctx->pending_index_ms; S.emit_ms = emit_ms;
   if (P.n_tiles) {
     cudaEventElapsedTime(&S.frames_ms, ctx->ev[3], ctx->evk[0]);
-    cudaEventElapsedTime(&S.walk_ms, ctx->evk[0], ctx->evk[1]);
+    cudaEventElapsedTime(&S.walk_ms, ctx->evk[0], ctx->evk[2]);    // k_bin_scan + k_perm + k_walk (structure)
+    cudaEventElapsedTime(&S.cells_ms, ctx->evk[2], ctx->evk[1]);   // k_cells + k_copy
     cudaEventElapsedTime(&S.spans_ms, ctx->ev_l0, ctx->ev_l1);   // concurrent with index / records
   }
   S.h2d_ms = ctx->pending_h2d_ms; S.d2h_ms = d2h_ms;

@@ -37,12 +37,17 @@ namespace etl {
 constexpr int kTileBytes = ETL_TILE_BYTES;       // nominal tile = kTileBytes of stream (frames that START inside it)
 constexpr int kTileCap = ETL_TILE_BYTES + 4096;        // shared-memory window; bytes past it are read from global
 #ifndef ETL_WALK_THREADS
-#define ETL_WALK_THREADS 256
+#define ETL_WALK_THREADS 128
 #endif
 constexpr int kWalkThreads = ETL_WALK_THREADS;
 constexpr int kIndexThreads = 256;
 constexpr int kMaxBins = 4096;         // 16 frame shapes x 256 schema versions (more versions share the last bins)
 
+// One wire cell of a DML tuple, as k_walk hands it to k_cells.  Rows of 32 descriptors = one slot (wire cell
+// index) of the 32 records a k_walk warp steps through, so a k_cells warp gets 32 cells of the same column.
+struct CellDesc { uint64_t a, b; };   // a = stream offset (40) | len[0:24) << 40;  b = dest cell (40) | kind << 40 | len[24:32) << 48
+struct CopyPair { uint64_t dest, src; };   // unchanged TOAST resolved from the old image: cell[dest] = cell[src] after k_cells
+constexpr uint32_t DK_EMPTY = 0xFFu;
 struct LongCell { uint32_t rec_local, seq; uint64_t l0, l1; };   // lines [l0, l1) of the stream are interior to the cell
 
 // ---- stream-state transformer (apply.rs:600-626, 1927-2006) + counters; associative under fold()
@@ -50,7 +55,7 @@ struct Summ {
   uint64_t lsn;      // final_lsn of the last Begin (valid if HAS_B)
   uint64_t ord;      // HAS_B: next ordinal after the span; else number of ordinal consumers in the span
   uint64_t n_cells;
-  uint64_t heap;
+  uint64_t slots;    // descriptor slots k_walk will fill (wire cells of the DML tuples, by frame shape)
   uint32_t n_rec;
   uint32_t flags;    // 1 HAS_B, 2 CLOSED (a Commit follows the last Begin / any Commit if no Begin)
 };
@@ -61,7 +66,7 @@ __host__ __device__ __forceinline__ Summ fold(const Summ& a, const Summ& b) {
   Summ r;
   r.n_rec = a.n_rec + b.n_rec;
   r.n_cells = a.n_cells + b.n_cells;
-  r.heap = a.heap + b.heap;
+  r.slots = a.slots + b.slots;
   if (b.flags & S_HAS_B) { r.flags = b.flags; r.lsn = b.lsn; r.ord = b.ord; }
   else {
     r.flags = (a.flags & S_HAS_B) | ((b.flags & S_CLOSED) ? S_CLOSED : (a.flags & S_CLOSED));
@@ -107,6 +112,9 @@ struct DecodeParams {
   unsigned int* tile_counter;  // dynamic tile scheduler of the emit pass
   // global grouping of the DML records by frame shape (k_frames counts, k_bin_scan lays out, k_perm fills)
   uint32_t* bin_count; uint32_t* bin_cursor; uint32_t n_bins; uint32_t* perm; unsigned int* perm_len;
+  uint32_t* bin_start; uint32_t* bin_row_base; uint32_t n_batch_schemas;
+  CellDesc* desc; uint32_t* row_chunk; unsigned int* desc_rows; uint32_t desc_row_cap;   // descriptor rows (32 cells each)
+  CopyPair* copies; unsigned int* copy_count; uint32_t copy_cap;
   uint32_t* line_bad;               // k_utf8_dead: bit l set = line l (128 bytes) holds a UTF-8 rule violation (zeroed per batch)
   uint32_t* dead;                   // segments without a frame start (ascending); n_dead = n_anchors - *n_act
   struct LongCell* long_cells; unsigned int* long_count; uint32_t long_cap;   // text cells spanning whole dead segments
@@ -222,6 +230,15 @@ __device__ __forceinline__ uint32_t frame_out_cells(const FrameHead& h, const De
     default: return 0;
   }
 }
+// wire-cell slots reserved for a DML frame: by shape only (a full-width key tuple has n_cols entries)
+__device__ __forceinline__ uint32_t shape_slots(uint32_t shape /*op << 2 | old flags*/, uint32_t n_cols) {
+  return ((shape >> 2) == 1u && (shape & 3u)) ? 2u * n_cols : n_cols;   // only an update with an old image has two tuples
+}
+__device__ __forceinline__ uint32_t frame_slots(const FrameHead& h, const DevSchema* s) {
+  if (!s || (h.kind != 'I' && h.kind != 'U' && h.kind != 'D')) return 0;
+  const uint32_t oldf = h.old_tag == 'O' ? 1u : (h.old_tag == 'K' ? 2u : 0u);
+  return shape_slots((h.kind == 'I' ? 0u : (h.kind == 'U' ? 4u : 8u)) | oldf, s->n_cols);
+}
 __device__ __forceinline__ Summ frame_state_elem(const FrameHead& h, const uint8_t* p) {
   Summ e = summ_identity();
   e.n_rec = 1;
@@ -267,37 +284,6 @@ __device__ __forceinline__ uint32_t walk_tuple(const uint8_t* p, const uint8_t* 
     q += l;
   }
   return (uint32_t)(q - p);
-}
-
-// heap bytes reserved for a DML frame = sum of cell_heap_bound over its text cells, mapped to
-// columns positionally (dense key tuples: k-th cell → k-th identity column).  An upper bound on
-// what the emit pass allocates; both passes call this same function so prefixes agree exactly.
-__device__ __noinline__ uint32_t frame_heap_bytes(const DecodeParams& P, const FrameHead& h, const DevSchema* s,
-                                                  const uint8_t* p) {
-  if (!s || !s->has_heap) return 0;
-  const uint8_t* end = p + 1 + h.flen;
-  const uint8_t* kinds = P.col_kind + s->col_base;
-  const uint8_t* flags = P.col_flags + s->col_base;
-  const uint32_t n_cols = s->n_cols, n_ident = s->n_ident;
-  uint32_t total = 0;
-  const uint8_t* q = p + 36;  // first tuple (after 'N' / 'O' / 'K' marker at p[35])
-  const int n_tuples = (h.kind == 'U' && h.old_tag) ? 2 : 1;
-  if (h.kind == 'U' && !h.old_tag && p[35] != 'N') return 0;
-  for (int t = 0; t < n_tuples; t++) {
-    if (q + 2 > end) return total;
-    const bool dense_key = (t == 0) && (h.kind != 'I') && h.old_tag == 'K' && (uint32_t)(int32_t)(int16_t)be16(q) == n_ident;
-    uint32_t cmap = 0;
-    int32_t nc;
-    uint32_t used = walk_tuple(q, end, &nc, [&](int32_t i, uint32_t tag, const uint8_t*, uint32_t len) {
-      uint32_t col = (uint32_t)i;
-      if (dense_key) { while (cmap < n_cols && !(flags[cmap] & 2)) cmap++; col = cmap++; }
-      if (tag == 't' && col < n_cols) total += cell_heap_bound(kinds[col], len);
-    });
-    if (!used) return total;
-    q += used;
-    if (t == 0 && n_tuples == 2) { if (q >= end || *q != 'N') return total; q++; }
-  }
-  return total;
 }
 
 // structure of a DML message body (what LogicalReplicationMessage::parse would reject) + Σ text lengths
@@ -407,6 +393,7 @@ __global__ void __launch_bounds__(kIndexThreads) k_index(DecodeParams P) {
         const DevSchema* s = nullptr;
         if (h.kind == 'I' || h.kind == 'U' || h.kind == 'D') s = find_schema(P, h.rel, pos);
         e.n_cells = frame_out_cells(h, s);
+        e.slots = frame_slots(h, s);
       }
       acc = fold(acc, e);
       nframes++;
@@ -780,24 +767,41 @@ __device__ __forceinline__ uint32_t walk_bin(const DecodeParams& P, int32_t sche
   const uint32_t b = ((uint32_t)schema << 4) | (kind == 'I' ? 0u : (kind == 'U' ? 4u : 8u)) | (rflags & 3u);
   return b < P.n_bins ? b : P.n_bins - 16u + (b & 15u);
 }
+// wire-cell slots per record of a bin (clamped bins hold several schema versions: take the widest)
+__device__ __forceinline__ uint32_t bin_slots(const DecodeParams& P, uint32_t bin) {
+  const uint32_t si = bin >> 4;
+  uint32_t n_cols = 0;
+  if (si < P.n_batch_schemas) n_cols = P.schemas[P.schema_by_batch[si]].n_cols;
+  if (bin + 16u >= P.n_bins) for (uint32_t j = si + 1; j < P.n_batch_schemas; j++) n_cols = max(n_cols, P.schemas[P.schema_by_batch[j]].n_cols);
+  return shape_slots(bin & 15u, n_cols);
+}
 __global__ void __launch_bounds__(1024) k_bin_scan(DecodeParams P) {
-  __shared__ uint32_t sh[1024];
+  __shared__ uint32_t sh[1024], shr[1024];
   const uint32_t per = (P.n_bins + 1023u) / 1024u;
   const uint32_t lo = threadIdx.x * per, hi = min(lo + per, P.n_bins);
-  uint32_t acc = 0;
-  for (uint32_t i = lo; i < hi; i++) acc += (P.bin_count[i] + 31u) & ~31u;
-  sh[threadIdx.x] = acc;
+  uint32_t acc = 0, accr = 0;
+  for (uint32_t i = lo; i < hi; i++) {
+    const uint32_t pc = (P.bin_count[i] + 31u) & ~31u;
+    acc += pc;
+    if (pc) accr += (pc >> 5) * bin_slots(P, i);
+  }
+  sh[threadIdx.x] = acc; shr[threadIdx.x] = accr;
   __syncthreads();
   for (uint32_t d = 1; d < 1024; d <<= 1) {
-    uint32_t v = sh[threadIdx.x];
-    if (threadIdx.x >= d) v += sh[threadIdx.x - d];
+    uint32_t v = sh[threadIdx.x], vr = shr[threadIdx.x];
+    if (threadIdx.x >= d) { v += sh[threadIdx.x - d]; vr += shr[threadIdx.x - d]; }
     __syncthreads();
-    sh[threadIdx.x] = v;
+    sh[threadIdx.x] = v; shr[threadIdx.x] = vr;
     __syncthreads();
   }
-  uint32_t run = threadIdx.x ? sh[threadIdx.x - 1] : 0u;
-  for (uint32_t i = lo; i < hi; i++) { P.bin_cursor[i] = run; run += (P.bin_count[i] + 31u) & ~31u; }
-  if (threadIdx.x == 1023) *P.perm_len = sh[1023];
+  uint32_t run = threadIdx.x ? sh[threadIdx.x - 1] : 0u, runr = threadIdx.x ? shr[threadIdx.x - 1] : 0u;
+  for (uint32_t i = lo; i < hi; i++) {
+    const uint32_t pc = (P.bin_count[i] + 31u) & ~31u;
+    P.bin_cursor[i] = run; P.bin_start[i] = run; P.bin_row_base[i] = runr;
+    run += pc;
+    if (pc) runr += (pc >> 5) * bin_slots(P, i);
+  }
+  if (threadIdx.x == 1023) { *P.perm_len = sh[1023]; *P.desc_rows = shr[1023]; }
 }
 __global__ void __launch_bounds__(256) k_perm(DecodeParams P) {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -842,13 +846,13 @@ __global__ void __launch_bounds__(256) k_frames(DecodeParams P) {
     for (int d = 1; d < 32; d <<= 1) {
       Summ up;
       up.lsn = __shfl_up_sync(0xffffffffu, inc.lsn, d); up.ord = __shfl_up_sync(0xffffffffu, inc.ord, d);
-      up.n_cells = __shfl_up_sync(0xffffffffu, inc.n_cells, d); up.heap = 0;
+      up.n_cells = __shfl_up_sync(0xffffffffu, inc.n_cells, d); up.slots = 0;
       up.n_rec = __shfl_up_sync(0xffffffffu, inc.n_rec, d); up.flags = __shfl_up_sync(0xffffffffu, inc.flags, d);
       if (lane >= d) inc = fold(up, inc);
     }
     Summ ex;
     ex.lsn = __shfl_up_sync(0xffffffffu, inc.lsn, 1); ex.ord = __shfl_up_sync(0xffffffffu, inc.ord, 1);
-    ex.n_cells = __shfl_up_sync(0xffffffffu, inc.n_cells, 1); ex.heap = 0;
+    ex.n_cells = __shfl_up_sync(0xffffffffu, inc.n_cells, 1); ex.slots = 0;
     ex.n_rec = __shfl_up_sync(0xffffffffu, inc.n_rec, 1); ex.flags = __shfl_up_sync(0xffffffffu, inc.flags, 1);
     if (lane == 0) ex = summ_identity();
     const uint32_t tile = j / 32u;
@@ -1011,16 +1015,18 @@ enum : uint32_t { W_OLD_HDR = 0, W_OLD_CELLS = 1, W_NEW_HDR = 2, W_NEW_CELLS = 3
 enum : uint32_t { WK_I = 1, WK_U = 2, WK_D = 3, WO_FULL = 1, WO_KEY = 2, WB_DENSE = 1u << 7, WB_PARTIAL = 1u << 8,
                   WB_EMIT = 1u << 9 };   // emit clears after the first data error: structure-only walk (a malformed
                                          // frame, i.e. a parser error in the reference, outranks every conversion error)
-struct TextCell { uint32_t voff, len, kind, seq, dest; };   // voff frame-relative, dest relative to cell0
+struct TextCell { uint32_t voff, len, kind, dest; };   // voff frame-relative, dest relative to cell0
 #define W_SET_STAGE(s_) (w.bits = (w.bits & ~7u) | (s_))
 #define W_DATA_ERROR(seq_, code_) do { report_error(P, P.record_index_base + w.rec_local, (seq_), (code_)); w.bits &= ~WB_EMIT; } while (0)
 #define W_MALFORMED() do { report_error(P, P.record_index_base + w.rec_local, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); W_SET_STAGE(W_DONE); } while (0)
 
-// one step: a tuple header or ONE wire cell. Returns true when a text cell must be parsed (tc filled).
-__device__ __forceinline__ bool wk_step(const DecodeParams& P, Wk& w, TextCell& tc) {
+// one step: a tuple header or ONE wire cell.  Returns 0 when no wire cell was consumed (header, end of a
+// tuple, malformed), 1 when one was consumed and needs no parsing, 2 when it is a text cell (tc filled).
+__device__ __forceinline__ uint32_t wk_step(const DecodeParams& P, Wk& w, TextCell& tc) {
   const uint32_t stage = w.bits & 7u, kind = (w.bits >> 3) & 3u, old = (w.bits >> 5) & 3u;
   const bool emit = (w.bits & WB_EMIT) != 0;
   const uint32_t n_cols = w.nc_ni & 0xFFFFu, n_ident = w.nc_ni >> 16;
+  uint32_t ret = 0;
   do {
     if (stage == W_OLD_HDR || stage == W_NEW_HDR) {
       const bool is_new = stage == W_NEW_HDR;
@@ -1071,6 +1077,7 @@ __device__ __forceinline__ bool wk_step(const DecodeParams& P, Wk& w, TextCell& 
     else { W_MALFORMED(); break; }
     const uint32_t i = w.rem_wire >> 16;
     w.rem_wire += 0x10000u - 1u;                    // wire_i++, remaining--
+    ret = 1;
     if (!emit) break;                               // structure-only after a data error
     const bool is_new = stage == W_NEW_CELLS;
     const uint8_t* flags = P.col_flags + w.col_base;
@@ -1092,8 +1099,8 @@ __device__ __forceinline__ bool wk_step(const DecodeParams& P, Wk& w, TextCell& 
     const bool resolver_key = upd_key && (cflags & 2);
     if (tag == 't') {
       if (resolver_key) w.keyi_nold++;
-      tc.voff = voff; tc.len = len; tc.kind = P.col_kind[w.col_base + col]; tc.seq = seq; tc.dest = dest;
-      return true;
+      tc.voff = voff; tc.len = len; tc.kind = P.col_kind[w.col_base + col]; tc.dest = dest;
+      return 2;
     }
     if (tag == 'n') {                               // convert_tuple_data_to_cell event.rs:941-957
       if (resolver_key) w.keyi_nold++;
@@ -1106,24 +1113,29 @@ __device__ __forceinline__ bool wk_step(const DecodeParams& P, Wk& w, TextCell& 
         uint64_t src = ~0ull;
         if (old == WO_FULL) src = w.cell0 + i;
         else if (resolver_key) { src = w.cell0 + (w.keyi_nold & 0xFFFFu); w.keyi_nold++; }
-        if (src != ~0ull) put_cell(P, w.cell0 + dest, P.cell_tag[src], P.cell_val[src], P.cell_aux[src]);  // written earlier by this thread
-        else { put_cell(P, w.cell0 + dest, ETL_CELL_MISSING, 0, 0); w.bits |= WB_PARTIAL; }
+        if (src != ~0ull) {                           // the old cell is produced by k_cells: copied by k_copy afterwards
+          const uint32_t at = atomicAdd(P.copy_count, 1u);
+          if (at < P.copy_cap) { CopyPair cp; cp.dest = w.cell0 + dest; cp.src = src; P.copies[at] = cp; }
+        } else { put_cell(P, w.cell0 + dest, ETL_CELL_MISSING, 0, 0); w.bits |= WB_PARTIAL; }
       } else W_DATA_ERROR(seq, (!is_new && old == WO_KEY) ? ETL_E_KEY_MISSING_VALUE : ETL_E_FULL_ROW_MISSING);
       break;
     }
     if (resolver_key) w.keyi_nold++;
     W_DATA_ERROR(seq, ETL_E_BINARY_FORMAT);         // 'b'
   } while (0);
-  return false;
+  return ret;
 }
 
-struct WalkShared {
-  alignas(4) uint8_t json_tables[256 + 32 * kJsonClasses];   // byte classes + transitions (json_valid_sync)
-};
+__device__ __forceinline__ CellDesc desc_make(uint64_t soff, uint32_t len, uint64_t dest, uint32_t kind) {
+  CellDesc d;
+  d.a = soff | ((uint64_t)(len & 0xFFFFFFu) << 40);
+  d.b = dest | ((uint64_t)kind << 40) | ((uint64_t)(len >> 24) << 48);
+  return d;
+}
 
-__global__ void __launch_bounds__(kWalkThreads, ETL_WALK_CTAS * 256 / kWalkThreads) k_walk(DecodeParams P) {
-  extern __shared__ __align__(16) uint8_t walk_smem[];
-  WalkShared& sh = *reinterpret_cast<WalkShared*>(walk_smem);
+// pass C2a: structure.  Thread t walks record perm[t] one wire cell per step and writes one descriptor per
+// step into row (row0 + slot); the 32 lanes of a warp hold records of one shape bin, so a row is one column.
+__global__ void __launch_bounds__(kWalkThreads) k_walk(DecodeParams P) {
   const int lane = threadIdx.x & 31;
   const uint32_t n_perm = *P.perm_len;
   // chunk of the binned order for this CTA.  Bins are contiguous and differ in cost per record (an update
@@ -1132,20 +1144,17 @@ __global__ void __launch_bounds__(kWalkThreads, ETL_WALK_CTAS * 256 / kWalkThrea
   const uint32_t n_chunks = (n_perm + blockDim.x - 1) / blockDim.x, cols = (n_chunks + 63u) / 64u;
   const uint32_t chunk = (blockIdx.x & 63u) * cols + (blockIdx.x >> 6);
   if ((blockIdx.x >> 6) >= cols || chunk >= n_chunks) return;
-  for (uint32_t k = threadIdx.x; k < sizeof(sh.json_tables) / 4; k += blockDim.x)
-    reinterpret_cast<uint32_t*>(sh.json_tables)[k] = reinterpret_cast<const uint32_t*>(kJsonTables)[k];
-  __syncthreads();
-  // ---- 1. this thread's record: entry t of the shape-binned order (0xFFFFFFFF = bin padding)
   const uint32_t t = chunk * blockDim.x + threadIdx.x;
-  const uint32_t my_rec = t < n_perm ? P.perm[t] : 0xFFFFFFFFu;
-  // ---- 2. walk it
+  const uint32_t my_rec = t < n_perm ? P.perm[t] : 0xFFFFFFFFu;   // 0xFFFFFFFF = bin padding
   Wk w;
   w.bits = W_DONE; w.tb = 0; w.rec_local = 0; w.base = nullptr; w.pos = 0; w.end = 0; w.col_base = 0; w.nc_ni = 0; w.cell0 = 0;
   w.rem_wire = 0; w.cmap_kout = 0; w.keyi_nold = 0;
+  uint32_t bin = 0;
   if (my_rec != 0xFFFFFFFFu) {
     const uint64_t rr = my_rec;
     const uint8_t* fp = P.buf + P.rec_off[rr];
-    const DevSchema& s = P.schemas[P.schema_by_batch[P.rec_schema[rr]]];
+    const int32_t sc = P.rec_schema[rr];
+    const DevSchema& s = P.schemas[P.schema_by_batch[sc]];
 #if ETL_WALK_PREFETCH
     // the walk is a dependent chain through the frame: put its first lines in flight together
     if (fp + 128 < P.buf + P.len) asm volatile("prefetch.global.L2 [%0];" ::"l"(fp + 128));
@@ -1155,129 +1164,44 @@ __global__ void __launch_bounds__(kWalkThreads, ETL_WALK_CTAS * 256 / kWalkThrea
     w.col_base = s.col_base; w.nc_ni = s.n_cols | (s.n_ident << 16);
     w.cell0 = P.rec_cell_base[rr]; w.rec_local = (uint32_t)rr;
     const uint32_t k = P.rec_kind[rr], rf = P.rec_flags[rr];
+    bin = walk_bin(P, sc, k, rf);
     const uint32_t kc = k == 'I' ? WK_I : (k == 'U' ? WK_U : WK_D);
     const uint32_t oc = (rf & ETL_RF_OLD_FULL) ? WO_FULL : ((rf & ETL_RF_OLD_KEY) ? WO_KEY : 0u);
     const bool old_first = kc != WK_I && oc;        // old image first; else the 'N' marker, then the new tuple
     w.pos = old_first ? 36u : 35u;
     w.bits = (old_first ? W_OLD_HDR : W_NEW_HDR) | (kc << 3) | (oc << 5) | WB_EMIT;
   }
-  // warp-synchronous stepping: all lanes take one step (header or cell) per iteration
+  // the warp's descriptor rows: all valid lanes are in the same bin
+  const unsigned vm = __ballot_sync(0xffffffffu, my_rec != 0xFFFFFFFFu);
+  if (vm == 0) return;
+  bin = __shfl_sync(0xffffffffu, bin, __ffs(vm) - 1);
+  const uint32_t bound = bin_slots(P, bin);
+  const uint32_t row0 = P.bin_row_base[bin] + ((t >> 5) - (P.bin_start[bin] >> 5)) * bound;
+  uint32_t slot = 0;
+  // warp-synchronous stepping: all lanes take one step (header or cell) per iteration; a finished lane
+  // pads its remaining slots with empty descriptors
   for (;;) {
     const bool act = (w.bits & 7u) != W_DONE;
-    if (!__any_sync(0xffffffffu, act)) break;
+    if (!__any_sync(0xffffffffu, act || slot < bound)) break;
     TextCell tc;
-    tc.voff = 0; tc.len = 0; tc.kind = 0; tc.seq = 0; tc.dest = 0;
-    const bool is_text = act && wk_step(P, w, tc);
-    const uint8_t* tv = w.base + tc.voff;
-    // ---- text cell: UTF-8 (event.rs:972) then the per-kind parser (text.rs:28-173)
-    CellOut o;
-    o.tag = 0; o.val = 0; o.aux = 0;
-    uint32_t code = 0;
-    bool do_parse = false;
-    const uint64_t soff = (uint64_t)(w.base - P.buf) + tc.voff;
-    bool need_slow = false;                            // small cell with non-ASCII bytes: validated by the whole warp below
-    uint32_t r0_hi = 0, r1_lo = 0, r1_hi = 0;          // long cell: byte ranges [0, r0_hi) and [r1_lo, r1_hi) validated by the whole warp
-    if (is_text) {
-      if (tc.kind == ETL_K_STRING) { o.tag = ETL_CELL_STRING; o.val = soff; o.aux = tc.len; }
-      if (tc.len >= (uint32_t)kCoopLen) {
-        // whole segments inside the cell hold no frame start: k_utf8_dead covers them, the rest is done here
-        const uint64_t cb = soff + tc.len;
-        const uint64_t S0 = (soff + 3ull + P.anchor_stride - 1ull) & ~(uint64_t)(P.anchor_stride - 1u), S1 = cb & ~(uint64_t)(P.anchor_stride - 1u);
-        r0_hi = tc.len;
-        if (S0 < S1) {
-          const uint32_t at = atomicAdd(P.long_count, 1u);
-          if (at < P.long_cap) {
-            LongCell lc; lc.rec_local = w.rec_local; lc.seq = tc.seq; lc.l0 = S0 >> 7; lc.l1 = S1 >> 7;
-            P.long_cells[at] = lc;
-            r0_hi = (uint32_t)(S0 - soff); r1_lo = (uint32_t)(S1 - soff); r1_hi = tc.len;
-          }
-        }
-      } else if (tc.len >= (uint32_t)kWideLen) { if (utf8_medium_bad(tv, tc.len)) code = ETL_E_UTF8; }
-      else need_slow = has_high_bits(tv, tc.len);
-    }
-    __syncwarp();
-    // position-local UTF-8 rule, one byte position per lane (a lane-serial walk of a 60-byte cell would
-    // hold the other 31 lanes for ~1000 issue slots; this costs ~60 for the whole warp)
-    for (unsigned sm = __ballot_sync(0xffffffffu, need_slow); sm; sm &= sm - 1) {
-      const int src = __ffs(sm) - 1;
-      const uint8_t* cp = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(tv), src));
-      const uint32_t cn = __shfl_sync(0xffffffffu, tc.len, src);
-      bool bad = false;
-      for (uint32_t i = lane; i <= cn; i += 32) {      // position cn = a virtual ASCII terminator (catches a truncated tail)
-        const uint32_t b = i < cn ? cp[i] : 0u, p1 = i >= 1 ? cp[i - 1] : 0u, p2 = i >= 2 ? cp[i - 2] : 0u, p3 = i >= 3 ? cp[i - 3] : 0u;
-        if ((b | p1 | p2 | p3) >= 0x80u) bad |= utf8_step_bad(b, p1, p2, p3);
+    tc.voff = 0; tc.len = 0; tc.kind = 0; tc.dest = 0;
+    const uint32_t got = act ? wk_step(P, w, tc) : (slot < bound ? 1u : 0u);
+    if (got) {
+      if (slot < bound) {
+        CellDesc d;
+        if (got == 2) d = desc_make((uint64_t)(w.base - P.buf) + tc.voff, tc.len, w.cell0 + tc.dest, tc.kind);
+        else d = desc_make(0, 0, 0, DK_EMPTY);
+        const uint32_t row = row0 + slot;
+        reinterpret_cast<uint4*>(P.desc)[(uint64_t)row * 32u + lane] = make_uint4((uint32_t)d.a, (uint32_t)(d.a >> 32), (uint32_t)d.b, (uint32_t)(d.b >> 32));
+        if (lane == 0) P.row_chunk[row] = t >> 5;
+      } else if (got == 2) {
+        // cannot happen for a well-formed shape (the reserved slots cover n_cols wire cells per tuple); a tuple
+        // that is longer than its schema already raised a field-count error and emits nothing
       }
-      bad = __any_sync(0xffffffffu, bad);
-      if (lane == src && bad) code = ETL_E_UTF8;
-    }
-    for (int round = 0; round < 2; round++) {
-      const uint32_t my_lo = round ? r1_lo : 0u, my_hi = round ? r1_hi : r0_hi;
-      for (unsigned sm = __ballot_sync(0xffffffffu, my_hi > my_lo); sm; sm &= sm - 1) {
-        const int src = __ffs(sm) - 1;
-        const uint8_t* cp = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(tv), src));
-        const uint32_t cn = __shfl_sync(0xffffffffu, tc.len, src), lo = __shfl_sync(0xffffffffu, my_lo, src), hi = __shfl_sync(0xffffffffu, my_hi, src);
-        const bool bad = __any_sync(0xffffffffu, utf8_range_bad(cp, cn, lo, hi, (uint32_t)lane, 32u));
-        if (lane == src && bad) code = ETL_E_UTF8;
-      }
-    }
-    do_parse = is_text && !code && tc.kind != ETL_K_STRING;
-    const unsigned pm = __ballot_sync(0xffffffffu, do_parse);
-    if (do_parse) {
-      const unsigned mask = __match_any_sync(pm, tc.kind);
-      uint64_t hpos = 0;
-      const bool heap_kind = tc.kind == ETL_K_NUMERIC || tc.kind == ETL_K_BYTES || tc.kind == ETL_K_UUID;  // uniform over `mask`
-      if (heap_kind) {                                 // warp-aggregated bump allocation
-        const uint32_t hb = cell_heap_bound(tc.kind, tc.len);
-        const unsigned below = mask & ((1u << lane) - 1u);
-        uint32_t mine_off = 0, total = 0;
-        for (unsigned mm = mask; mm; mm &= mm - 1) {   // lanes of `mask` run this loop together
-          const int src = __ffs(mm) - 1;
-          const uint32_t v = __shfl_sync(mask, hb, src);
-          if ((below >> src) & 1u) mine_off += v;
-          total += v;
-        }
-        unsigned long long base = 0;
-        const int leader = __ffs(mask) - 1;
-        if (lane == leader) base = atomicAdd(P.heap_top, (unsigned long long)total);
-        base = __shfl_sync(mask, base, leader);
-        hpos = base + mine_off;
-      }
-      // out-of-line parsers get their own CellOut / HeapCursor so that `o` never has its address taken
-      // (an escaped struct lives in local memory for the whole loop)
-      int64_t iv = 0;
-      switch (tc.kind) {
-        case ETL_K_I32: code = parse_int_sync(mask, tv, tc.len, true, 2147483647ull, 2147483648ull, &iv); o.tag = ETL_CELL_I32; o.val = (uint64_t)iv; break;
-        case ETL_K_I64: code = parse_int_sync(mask, tv, tc.len, true, 9223372036854775807ull, 9223372036854775808ull, &iv); o.tag = ETL_CELL_I64; o.val = (uint64_t)iv; break;
-        case ETL_K_I16: code = parse_int_sync(mask, tv, tc.len, true, 32767ull, 32768ull, &iv); o.tag = ETL_CELL_I16; o.val = (uint64_t)iv; break;
-        case ETL_K_U32: code = parse_int_sync(mask, tv, tc.len, false, 4294967295ull, 0ull, &iv); o.tag = ETL_CELL_U32; o.val = (uint64_t)iv; break;
-        case ETL_K_NUMERIC: code = parse_numeric_sync(mask, tv, tc.len, P.heap, hpos, o); break;
-        case ETL_K_JSON:
-          if (json_valid_sync(mask, tv, tc.len, sh.json_tables)) { o.tag = ETL_CELL_JSON; o.val = soff; o.aux = tc.len; } else code = ETL_E_JSON;
-          break;
-        case ETL_K_TIMESTAMPTZ:
-          if (!fast_timestamptz(tv, tc.len, o)) { CellOut t; t.tag = 0; t.val = 0; t.aux = 0; code = parse_text_cell(tc.kind, tv, tc.len, soff, P.heap, hpos, t); o = t; }
-          break;
-        case ETL_K_TIMESTAMP:
-          if (!fast_timestamp(tv, tc.len, o)) { CellOut t; t.tag = 0; t.val = 0; t.aux = 0; code = parse_text_cell(tc.kind, tv, tc.len, soff, P.heap, hpos, t); o = t; }
-          break;
-        case ETL_K_STRING: o.tag = ETL_CELL_STRING; o.val = soff; o.aux = tc.len; break;
-        default: {
-          CellOut t; t.tag = 0; t.val = 0; t.aux = 0;
-          if (tc.kind & ETL_K_ARRAY) {
-            code = parse_array_any(ArrHeap{P.heap, P.arr_top, P.arr_base, P.heap_cap}, tc.kind, tv, tc.len, t);
-            if (code == 0xFFFFFFFEu) { atomicExch(P.heap_overflow, 1u); code = 0; t.tag = ETL_CELL_NULL; }
-          } else code = parse_text_cell(tc.kind, tv, tc.len, soff, P.heap, hpos, t);
-          o = t;
-          break;
-        }
-      }
-    }
-    if (is_text) {
-      if (code) { report_error(P, P.record_index_base + w.rec_local, tc.seq, code); w.bits &= ~WB_EMIT; }
-      else put_cell(P, w.cell0 + tc.dest, o.tag, o.val, o.aux);
+      slot++;
     }
   }
-  // ---- 3. per-record epilogue: Partial flag; tuple-byte metrics (one atomic per warp and op kind)
+  // ---- per-record epilogue: Partial flag; tuple-byte metrics (one atomic per warp and op kind)
   if (w.bits & WB_PARTIAL) P.rec_flags[w.rec_local] |= ETL_RF_NEW_PARTIAL;
   const uint32_t wkind = (w.bits >> 3) & 3u;
   uint32_t tbi = wkind == WK_I ? w.tb : 0u, tbu = wkind == WK_U ? w.tb : 0u, tbd = wkind == WK_D ? w.tb : 0u;
@@ -1289,5 +1213,169 @@ __global__ void __launch_bounds__(kWalkThreads, ETL_WALK_CTAS * 256 / kWalkThrea
 #undef W_DATA_ERROR
 #undef W_MALFORMED
 #undef W_SET_STAGE
+
+// (record, evaluation step) of the cell in lane `lane` of descriptor row `row`: needed only when the cell
+// fails or is a long cell, so it is recomputed from the frame instead of travelling in every descriptor.
+// (inlined: a reference to the kernel parameter struct from an out-of-line function makes every thread copy
+// the whole struct to local memory at kernel entry)
+__device__ __forceinline__ void desc_origin(const DecodeParams& P, uint32_t row, uint32_t lane, uint32_t* rec_out, uint32_t* seq_out) {
+  const uint32_t wchunk = P.row_chunk[row];
+  const uint32_t rec = P.perm[(uint64_t)wchunk * 32u + lane];
+  const uint32_t kind = P.rec_kind[rec], rf = P.rec_flags[rec];
+  const uint32_t bin = walk_bin(P, P.rec_schema[rec], kind, rf);
+  const uint32_t slot = row - (P.bin_row_base[bin] + (wchunk - (P.bin_start[bin] >> 5)) * bin_slots(P, bin));
+  uint32_t n_old_wire = 0;
+  if (kind != 'I' && (rf & 3u)) {                     // old image present: its wire count sits right after the tag
+    const uint8_t* fp = P.buf + P.rec_off[rec];
+    const int32_t nc = (int32_t)(int16_t)(((uint32_t)fp[36] << 8) | fp[37]);
+    n_old_wire = nc < 0 ? 0u : (uint32_t)nc;
+  }
+  *rec_out = rec;
+  *seq_out = slot < n_old_wire ? seq_old_cell(slot) : seq_new_cell(slot - n_old_wire);
+}
+
+// pass C2b: cells.  One warp per descriptor row (text.rs:28-173 on 32 cells of one column): UTF-8
+// (event.rs:972), the per-kind parser, the cell plane and the heap.  No walker state: the registers go to
+// the parsers.
+struct CellsShared { alignas(4) uint8_t json_tables[256 + 32 * kJsonClasses]; };   // byte classes + transitions (json_valid_sync)
+#ifndef ETL_CELLS_CTAS
+#define ETL_CELLS_CTAS 4
+#endif
+__global__ void __launch_bounds__(256, ETL_CELLS_CTAS) k_cells(DecodeParams P) {
+  __shared__ CellsShared sh;
+  for (uint32_t k = threadIdx.x; k < sizeof(sh.json_tables) / 4; k += blockDim.x)
+    reinterpret_cast<uint32_t*>(sh.json_tables)[k] = reinterpret_cast<const uint32_t*>(kJsonTables)[k];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= *P.desc_rows) return;                   // grid sized for the host's upper bound
+  const uint4 raw = reinterpret_cast<const uint4*>(P.desc)[(uint64_t)row * 32u + lane];
+  const uint64_t da = ((uint64_t)raw.y << 32) | raw.x, db = ((uint64_t)raw.w << 32) | raw.z;
+  const uint32_t kind = (uint32_t)(db >> 40) & 0xFFu;
+  const bool is_text = kind != DK_EMPTY;
+  const uint64_t soff = da & ((1ull << 40) - 1ull), dest = db & ((1ull << 40) - 1ull);
+  const uint32_t len = (uint32_t)(da >> 40) | ((uint32_t)(db >> 48) & 0xFFu) << 24;
+  const uint8_t* tv = P.buf + soff;
+  CellOut o;
+  o.tag = 0; o.val = 0; o.aux = 0;
+  uint32_t code = 0;
+  bool need_slow = false;                            // small cell with non-ASCII bytes: validated by the whole warp below
+  uint32_t r0_hi = 0, r1_lo = 0, r1_hi = 0;          // long cell: byte ranges [0, r0_hi) and [r1_lo, r1_hi) validated by the whole warp
+  if (is_text) {
+    if (kind == ETL_K_STRING) { o.tag = ETL_CELL_STRING; o.val = soff; o.aux = len; }
+    if (len >= (uint32_t)kCoopLen) {
+      // whole segments inside the cell hold no frame start: k_utf8_dead covers them, the rest is done here
+      const uint64_t cb = soff + len;
+      const uint64_t S0 = (soff + 3ull + P.anchor_stride - 1ull) & ~(uint64_t)(P.anchor_stride - 1u), S1 = cb & ~(uint64_t)(P.anchor_stride - 1u);
+      r0_hi = len;
+      if (S0 < S1) {
+        const uint32_t at = atomicAdd(P.long_count, 1u);
+        if (at < P.long_cap) {
+          LongCell lc;
+          desc_origin(P, row, lane, &lc.rec_local, &lc.seq);
+          lc.l0 = S0 >> 7; lc.l1 = S1 >> 7;
+          P.long_cells[at] = lc;
+          r0_hi = (uint32_t)(S0 - soff); r1_lo = (uint32_t)(S1 - soff); r1_hi = len;
+        }
+      }
+    } else if (len >= (uint32_t)kWideLen) { if (utf8_medium_bad(tv, len)) code = ETL_E_UTF8; }
+    else need_slow = has_high_bits(tv, len);
+  }
+  __syncwarp();
+  // position-local UTF-8 rule, one byte position per lane (a lane-serial walk of a 60-byte cell would
+  // hold the other 31 lanes for ~1000 issue slots; this costs ~60 for the whole warp)
+  for (unsigned sm = __ballot_sync(0xffffffffu, need_slow); sm; sm &= sm - 1) {
+    const int src = __ffs(sm) - 1;
+    const uint8_t* cp = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(tv), src));
+    const uint32_t cn = __shfl_sync(0xffffffffu, len, src);
+    bool bad = false;
+    for (uint32_t i = lane; i <= cn; i += 32) {        // position cn = a virtual ASCII terminator (catches a truncated tail)
+      const uint32_t b = i < cn ? cp[i] : 0u, p1 = i >= 1 ? cp[i - 1] : 0u, p2 = i >= 2 ? cp[i - 2] : 0u, p3 = i >= 3 ? cp[i - 3] : 0u;
+      if ((b | p1 | p2 | p3) >= 0x80u) bad |= utf8_step_bad(b, p1, p2, p3);
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == src && bad) code = ETL_E_UTF8;
+  }
+  for (int round = 0; round < 2; round++) {
+    const uint32_t my_lo = round ? r1_lo : 0u, my_hi = round ? r1_hi : r0_hi;
+    for (unsigned sm = __ballot_sync(0xffffffffu, my_hi > my_lo); sm; sm &= sm - 1) {
+      const int src = __ffs(sm) - 1;
+      const uint8_t* cp = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(tv), src));
+      const uint32_t cn = __shfl_sync(0xffffffffu, len, src), lo = __shfl_sync(0xffffffffu, my_lo, src), hi = __shfl_sync(0xffffffffu, my_hi, src);
+      const bool bad = __any_sync(0xffffffffu, utf8_range_bad(cp, cn, lo, hi, (uint32_t)lane, 32u));
+      if (lane == src && bad) code = ETL_E_UTF8;
+    }
+  }
+  const bool do_parse = is_text && !code && kind != ETL_K_STRING;
+  const unsigned pm = __ballot_sync(0xffffffffu, do_parse);
+  if (do_parse) {
+    const unsigned mask = __match_any_sync(pm, kind);
+    uint64_t hpos = 0;
+    const bool heap_kind = kind == ETL_K_NUMERIC || kind == ETL_K_BYTES || kind == ETL_K_UUID;  // uniform over `mask`
+    if (heap_kind) {                                 // warp-aggregated bump allocation
+      const uint32_t hb = cell_heap_bound(kind, len);
+      const unsigned below = mask & ((1u << lane) - 1u);
+      uint32_t mine_off = 0, total = 0;
+      for (unsigned mm = mask; mm; mm &= mm - 1) {   // lanes of `mask` run this loop together
+        const int src = __ffs(mm) - 1;
+        const uint32_t v = __shfl_sync(mask, hb, src);
+        if ((below >> src) & 1u) mine_off += v;
+        total += v;
+      }
+      unsigned long long base = 0;
+      const int leader = __ffs(mask) - 1;
+      if (lane == leader) base = atomicAdd(P.heap_top, (unsigned long long)total);
+      base = __shfl_sync(mask, base, leader);
+      hpos = base + mine_off;
+    }
+    // out-of-line parsers get their own CellOut so that `o` never has its address taken
+    int64_t iv = 0;
+    switch (kind) {
+      case ETL_K_I32: case ETL_K_I64: case ETL_K_I16: case ETL_K_U32: {   // one copy of the parser, limits by kind
+        const uint64_t pos_limit = kind == ETL_K_I32 ? 2147483647ull : (kind == ETL_K_I64 ? 9223372036854775807ull : (kind == ETL_K_I16 ? 32767ull : 4294967295ull));
+        const uint64_t neg_limit = kind == ETL_K_U32 ? 0ull : pos_limit + 1ull;
+        code = parse_int_sync(mask, tv, len, kind != ETL_K_U32, pos_limit, neg_limit, &iv);
+        o.tag = kind == ETL_K_I32 ? ETL_CELL_I32 : (kind == ETL_K_I64 ? ETL_CELL_I64 : (kind == ETL_K_I16 ? ETL_CELL_I16 : ETL_CELL_U32));
+        o.val = (uint64_t)iv;
+        break;
+      }
+      case ETL_K_NUMERIC: code = parse_numeric_sync(mask, tv, len, P.heap, hpos, o); break;
+      case ETL_K_JSON:
+        if (json_valid_sync(mask, tv, len, sh.json_tables)) { o.tag = ETL_CELL_JSON; o.val = soff; o.aux = len; } else code = ETL_E_JSON;
+        break;
+      case ETL_K_TIMESTAMPTZ:
+        if (!fast_timestamptz(tv, len, o)) { CellOut t; t.tag = 0; t.val = 0; t.aux = 0; code = parse_text_cell(kind, tv, len, soff, P.heap, hpos, t); o = t; }
+        break;
+      case ETL_K_TIMESTAMP:
+        if (!fast_timestamp(tv, len, o)) { CellOut t; t.tag = 0; t.val = 0; t.aux = 0; code = parse_text_cell(kind, tv, len, soff, P.heap, hpos, t); o = t; }
+        break;
+      default: {
+        CellOut t; t.tag = 0; t.val = 0; t.aux = 0;
+        if (kind & ETL_K_ARRAY) {
+          code = parse_array_any(ArrHeap{P.heap, P.arr_top, P.arr_base, P.heap_cap}, kind, tv, len, t);
+          if (code == 0xFFFFFFFEu) { atomicExch(P.heap_overflow, 1u); code = 0; t.tag = ETL_CELL_NULL; }
+        } else code = parse_text_cell(kind, tv, len, soff, P.heap, hpos, t);
+        o = t;
+        break;
+      }
+    }
+  }
+  if (is_text) {
+    if (code) {
+      uint32_t rec, seq;
+      desc_origin(P, row, (uint32_t)lane, &rec, &seq);
+      report_error(P, P.record_index_base + rec, seq, code);
+    } else put_cell(P, dest, o.tag, o.val, o.aux);
+  }
+}
+
+// pass C2c: unchanged-TOAST cells of updates take the value k_cells produced for the old image
+__global__ void __launch_bounds__(256) k_copy(DecodeParams P) {
+  const uint32_t n = min(*P.copy_count, P.copy_cap);
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const CopyPair c = P.copies[e];
+    put_cell(P, c.dest, P.cell_tag[c.src], P.cell_val[c.src], P.cell_aux[c.src]);
+  }
+}
 
 }  // namespace etl

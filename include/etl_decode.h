@@ -311,13 +311,15 @@ typedef struct etl_dec_summary {
   uint32_t gpu_launches;  /* kernels launched for this batch */
   float kernel_ms;        /* CUDA-event time of the kernel sequence (resident input → resident output) */
   float h2d_ms, d2h_ms;
-  float index_ms;         /* pass A+B: k_index + k_scan + k_tile_prefix */
-  float emit_ms;          /* pass C: k_frames + k_walk + k_utf8_spans */
+  float index_ms;         /* pass A+B: k_act_* + k_index + k_scan + k_tile_prefix */
+  float emit_ms;          /* pass C: k_frames … k_long_verdict, incl. the join with the side stream */
   float frames_ms;        /* k_frames */
-  float walk_ms;          /* k_walk */
-  float spans_ms;         /* k_utf8_lines (structure-blind UTF-8 pass; runs concurrently with index/records) */
+  float walk_ms;          /* k_bin_scan + k_perm + k_walk (tuple structure → cell descriptors) */
+  float spans_ms;         /* k_utf8_dead (structure-blind UTF-8 pass over segments without a frame start; side stream) */
+  float cells_ms;         /* k_cells + k_copy (UTF-8, per-kind parsers, cell plane) */
+  float _pad1;
   uint64_t h2d_bytes, d2h_bytes; /* bytes copied host→device / device→host for this batch */
-  uint64_t span_bytes;    /* bytes streamed by k_utf8_lines (= len; its algorithmic bytes) */
+  uint64_t span_bytes;    /* bytes streamed by k_utf8_dead (its algorithmic bytes) */
 } etl_dec_summary;
 
 int etl_dec_batch_planes(const etl_dec_batch*, int host, etl_dec_planes* out);

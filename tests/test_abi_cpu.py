@@ -31,7 +31,7 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(abi.DecInput) == 96
     assert C.sizeof(abi.Seam) == 48
     assert C.sizeof(abi.Planes) == 128
-    assert C.sizeof(abi.Summary) == 144
+    assert C.sizeof(abi.Summary) == 152
     assert C.sizeof(abi.SchemaInfo) == 56
 
 

@@ -10,6 +10,7 @@ for r in csv.reader(io.StringIO(src)):
     if r[0] in ("File Name", "File Path"): fname = os.path.basename(r[1]); continue
     if r[0] == "Line No": ci = {c: i for i, c in enumerate(r)}; continue
     if ci is None or len(r) < 20: continue
+    if not r[0].strip(): continue            # SASS-only rows repeat the per-line totals
     a = agg[(fname, r[0])]
     try:
         a[0] += float(r[ci["# Samples"]] or 0); a[1] += float(r[ci["Instructions Executed"]] or 0); a[2] += float(r[ci["Thread Instructions Executed"]] or 0)
