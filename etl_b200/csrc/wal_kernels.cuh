@@ -477,16 +477,20 @@ __device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 
 __device__ __forceinline__ uint64_t bswap64(uint64_t v) { return ((uint64_t)bswap32((uint32_t)v) << 32) | bswap32((uint32_t)(v >> 32)); }
 
 // UTF-8 check of a short/medium cell with word loads: all-ASCII words pass immediately
+// any byte >= 0x80 in [s, s+n)?  Aligned 8-byte loads with the edges masked off (the bytes around a cell are
+// readable: frame header before, padding after) — one load per word instead of the three of ld64u.
 __device__ __forceinline__ bool has_high_bits(const uint8_t* s, uint32_t n) {
-  uint32_t hi = 0;
-  uint32_t i = 0;
-  for (; i + 8 <= n; i += 8) { uint64_t x = ld64u(s + i); hi |= (uint32_t)(x >> 32) | (uint32_t)x; }
-  if (i < n) {
-    uint64_t x = ld64u(s + i);
-    x &= (1ull << (8 * (n - i))) - 1ull;  // 1..7 valid bytes
-    hi |= (uint32_t)(x >> 32) | (uint32_t)x;
-  }
-  return (hi & 0x80808080u) != 0;
+  if (n == 0) return false;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+  const uint64_t* w = reinterpret_cast<const uint64_t*>(a & ~uintptr_t(7));
+  const uint32_t lead = (uint32_t)(a & 7u);
+  const uint32_t nw = (lead + n + 7u) >> 3;          // words touched
+  uint64_t acc = w[0] & (~0ull << (8u * lead));
+  if (nw == 1) { const uint32_t tail = lead + n; if (tail < 8u) acc &= (1ull << (8u * tail)) - 1ull; return (acc & 0x8080808080808080ull) != 0; }
+  for (uint32_t i = 1; i + 1 < nw; i++) acc |= w[i];
+  const uint32_t tail = (lead + n) & 7u;
+  acc |= tail ? (w[nw - 1] & ((1ull << (8u * tail)) - 1ull)) : w[nw - 1];
+  return (acc & 0x8080808080808080ull) != 0;
 }
 __device__ __forceinline__ bool utf8_valid_fast(const uint8_t* s, uint32_t n) {
   uint32_t hi = 0;
@@ -1237,15 +1241,10 @@ __device__ __forceinline__ void desc_origin(const DecodeParams& P, uint32_t row,
 // pass C2b: cells.  One warp per descriptor row (text.rs:28-173 on 32 cells of one column): UTF-8
 // (event.rs:972), the per-kind parser, the cell plane and the heap.  No walker state: the registers go to
 // the parsers.
-struct CellsShared { alignas(4) uint8_t json_tables[256 + 32 * kJsonClasses]; };   // byte classes + transitions (json_valid_sync)
 #ifndef ETL_CELLS_CTAS
-#define ETL_CELLS_CTAS 4
+#define ETL_CELLS_CTAS 6
 #endif
 __global__ void __launch_bounds__(256, ETL_CELLS_CTAS) k_cells(DecodeParams P) {
-  __shared__ CellsShared sh;
-  for (uint32_t k = threadIdx.x; k < sizeof(sh.json_tables) / 4; k += blockDim.x)
-    reinterpret_cast<uint32_t*>(sh.json_tables)[k] = reinterpret_cast<const uint32_t*>(kJsonTables)[k];
-  __syncthreads();
   const int lane = threadIdx.x & 31;
   const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= *P.desc_rows) return;                   // grid sized for the host's upper bound
@@ -1341,7 +1340,7 @@ __global__ void __launch_bounds__(256, ETL_CELLS_CTAS) k_cells(DecodeParams P) {
       }
       case ETL_K_NUMERIC: code = parse_numeric_sync(mask, tv, len, P.heap, hpos, o); break;
       case ETL_K_JSON:
-        if (json_valid_sync(mask, tv, len, sh.json_tables)) { o.tag = ETL_CELL_JSON; o.val = soff; o.aux = len; } else code = ETL_E_JSON;
+        if (json_valid_sync(mask, tv, len, kJsonTables)) { o.tag = ETL_CELL_JSON; o.val = soff; o.aux = len; } else code = ETL_E_JSON;
         break;
       case ETL_K_TIMESTAMPTZ:
         if (!fast_timestamptz(tv, len, o)) { CellOut t; t.tag = 0; t.val = 0; t.aux = 0; code = parse_text_cell(kind, tv, len, soff, P.heap, hpos, t); o = t; }
