@@ -9,8 +9,9 @@ A "step" is one pass of the decode hot path over the staged synthetic stream:
   e2e    — the same call through the C ABI with HOST (pinned) buffers: H2D of the stream and its
            anchor index, the kernels, and the D2H of every result plane are inside the timed region
 Workload (default c5): BASELINE.json configs[4], "10 GiB synthetic pgoutput buffer, mixed ops +
-TOASTed text"; the whole buffer is decoded at every N (strong scaling), rank r owning the r-th
-contiguous byte range.  Inputs are far larger than L2 (126 MB), so no flush is needed between steps.
+TOASTed text"; every GPU decodes a full-size (10 GiB) byte-range shard of one longer stream (weak scaling:
+rank r owns segments r*64 .. r*64+63), the shard seams are stitched by one all-gather of 48-byte summaries.
+Inputs are far larger than L2 (126 MB), so no flush is needed between steps.
 """
 from __future__ import annotations
 
@@ -38,7 +39,7 @@ def parse_args():
     ap.add_argument("--workload", default="c5", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the BASELINE.json size of the workload")
     ap.add_argument("--stride", type=int, default=2048, help="anchor stride of the staged stream")
-    ap.add_argument("--cpu-sample-gib", type=float, default=1.0, help="bounded sample for the CPU baseline")
+    ap.add_argument("--cpu-sample-gib", type=float, default=10.0, help="bounded sample for the CPU baseline")
     ap.add_argument("--gen-threads", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -85,7 +86,7 @@ class ClockSampler:
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.002)
 
     def __enter__(self):
         if self._nv:

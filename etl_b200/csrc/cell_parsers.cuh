@@ -756,11 +756,11 @@ __device__ __forceinline__ bool json_valid_sync(unsigned mask, const uint8_t* s,
   uint32_t st = JT_VALUE, depth = 0, ctx = 0 /*0 top, 1 object, 2 array*/, aux = 0, hexn = 0;
   bool key = false, low_sur = false;
   uint64_t lo = 0, hi = 0;                            // container stack, bit d = 1: level d is an object
-  uint64_t word = 0;
+  uint64_t word = 0, next = n ? ldu64(s) : 0ull;      // one word ahead: the load overlaps the 8 DFA steps before it
   uint32_t i = 0;
   while (__any_sync(mask, i < n && st != JT_BAD)) {
     if (i < n && st != JT_BAD) {
-      if ((i & 7u) == 0) word = ldu64(s + i);
+      if ((i & 7u) == 0) { word = next; if (i + 8u < n) next = ldu64(s + i + 8u); }
       const uint32_t c = (uint32_t)(word >> ((i & 7u) * 8u)) & 0xFFu;
       i++;
       if (st - JT_ESC <= 3u) {                        // inside an escape: rare

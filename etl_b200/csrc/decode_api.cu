@@ -320,6 +320,13 @@ int etl_dec_create(int device_id, etl_dec_ctx** out) {
   for (auto& e : ctx->ev) cudaEventCreate(&e);
   for (auto& e : ctx->evk) cudaEventCreate(&e);
   if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ETL_ERR_CUDA; }
+  {  // batch planes come from the stream-ordered pool: keep freed blocks for the next batch instead of returning them to the OS
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming); cudaEventCreate(&ctx->ev_l0); cudaEventCreate(&ctx->ev_l1);
   cudaHostAlloc((void**)&ctx->h_total, sizeof(Summ), cudaHostAllocDefault);
   cudaHostAlloc((void**)&ctx->h_scalars, 16 * sizeof(unsigned long long), cudaHostAllocDefault);
@@ -456,6 +463,32 @@ void etl_dec_batch_free(etl_dec_batch* b) {
   delete b;
 }
 
+// Where the structure-blind UTF-8 pass (k_utf8_dead, HBM-bound) runs relative to the latency-bound passes.
+// 0: side stream from the start of the index pass; 1: side stream from the start of the tuple passes
+// (the index + record passes keep the memory system to themselves); 2: main stream after the tuple passes.
+// ETL_DEAD_MODE / ETL_DEAD_CTAS are tuning knobs for measurement, not part of the ABI.
+static int dead_mode() {
+  static const int m = getenv("ETL_DEAD_SERIAL") ? 2 : (getenv("ETL_DEAD_MODE") ? atoi(getenv("ETL_DEAD_MODE")) : 0);
+  return m;
+}
+static int dead_ctas(int dflt) {
+  static const int c = getenv("ETL_DEAD_CTAS") ? atoi(getenv("ETL_DEAD_CTAS")) : 0;
+  return c > 0 ? c : dflt;
+}
+static cudaError_t launch_dead_side(etl_dec_ctx* ctx, cudaStream_t st) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  cudaError_t e;
+  if ((e = cudaEventRecord(ctx->ev_in, st)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(ctx->side, ctx->ev_in, 0)) != cudaSuccess) return e;
+  if ((e = cudaEventRecord(ctx->ev_l0, ctx->side)) != cudaSuccess) return e;
+  k_utf8_dead<<<sms * dead_ctas(3), 256, 0, ctx->side>>>(ctx->P);
+  if ((e = cudaEventRecord(ctx->ev_l1, ctx->side)) != cudaSuccess) return e;
+  ctx->launches += 1;
+  ctx->lines_launched = true;
+  return cudaSuccess;
+}
+
 int etl_dec_decode_begin(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t flags, etl_dec_seam* seam_out) {
   if (!ctx || !in) return ETL_ERR_INVALID_ARG;
   ctx->pending = false;
@@ -588,18 +621,7 @@ int etl_dec_decode_begin(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t fla
     k_act_count<<<act_blocks, kActThreads, 0, st>>>(P);
     k_act_scan<<<1, kActThreads, 0, st>>>(P, act_blocks);
     k_act_scatter<<<act_blocks, kActThreads, 0, st>>>(P);
-    if (!getenv("ETL_DEAD_SERIAL")) {  // structure-blind UTF-8 pass over the dead segments, on the side stream underneath everything that follows
-      int sms = 148;
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-      CK(cudaEventRecord(ctx->ev_in, st));
-      CK(cudaStreamWaitEvent(ctx->side, ctx->ev_in, 0));
-      CK(cudaEventRecord(ctx->ev_l0, ctx->side));
-      static const int dead_ctas = getenv("ETL_DEAD_CTAS") ? atoi(getenv("ETL_DEAD_CTAS")) : 3;   // per SM (tuning knob)
-      k_utf8_dead<<<sms * dead_ctas, 256, 0, ctx->side>>>(P);
-      CK(cudaEventRecord(ctx->ev_l1, ctx->side));
-      ctx->launches += 1;
-      ctx->lines_launched = true;
-    }
+    if (dead_mode() == 0) CK(launch_dead_side(ctx, st));   // underneath everything that follows
     k_index<<<P.n_groups, P.tiles_per_group * P.segs_per_tile, 0, st>>>(P);
     k_scan<<<1, 512, 0, st>>>(P);
     k_tile_prefix<<<(P.n_tiles + 255) / 256, 256, 0, st>>>(P);
@@ -713,6 +735,7 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
       P.n_records = nr;
       k_frames<<<(P.n_anchors + 255) / 256, 256, 0, st>>>(P);
       cudaEventRecord(ctx->evk[0], st);
+      if (dead_mode() == 1 && !ctx->lines_launched) CK(launch_dead_side(ctx, st));   // underneath the tuple passes only
       if (nr) {
         k_bin_scan<<<1, 1024, 0, st>>>(P);
         k_perm<<<(uint32_t)((nr + 255) / 256), 256, 0, st>>>(P);
@@ -727,11 +750,11 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
         cudaEventRecord(ctx->ev_l0, st);
-        k_utf8_dead<<<sms * (getenv("ETL_DEAD_CTAS") ? atoi(getenv("ETL_DEAD_CTAS")) : 6), 256, 0, st>>>(P);
+        k_utf8_dead<<<sms * dead_ctas(6), 256, 0, st>>>(P);
         cudaEventRecord(ctx->ev_l1, st);
         ctx->launches += 1;
       }
-      if (nr) k_long_verdict<<<64, 256, 0, st>>>(P);
+      if (nr) k_long_verdict<<<592, 256, 0, st>>>(P);
       ctx->launches += nr ? 7 : 1;
       CK(cudaGetLastError());
     }

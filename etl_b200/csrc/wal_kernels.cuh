@@ -485,11 +485,22 @@ __device__ __forceinline__ bool has_high_bits(const uint8_t* s, uint32_t n) {
   const uint64_t* w = reinterpret_cast<const uint64_t*>(a & ~uintptr_t(7));
   const uint32_t lead = (uint32_t)(a & 7u);
   const uint32_t nw = (lead + n + 7u) >> 3;          // words touched
-  uint64_t acc = w[0] & (~0ull << (8u * lead));
-  if (nw == 1) { const uint32_t tail = lead + n; if (tail < 8u) acc &= (1ull << (8u * tail)) - 1ull; return (acc & 0x8080808080808080ull) != 0; }
-  for (uint32_t i = 1; i + 1 < nw; i++) acc |= w[i];
   const uint32_t tail = (lead + n) & 7u;
-  acc |= tail ? (w[nw - 1] & ((1ull << (8u * tail)) - 1ull)) : w[nw - 1];
+  // every load is independent of the others: issue them in groups of four so that a 60-byte cell costs two
+  // memory round trips instead of eight (a load-OR-load chain was the longest stall of k_cells)
+  const uint64_t first = w[0], last = w[nw - 1];
+  uint64_t acc = 0;
+  for (uint32_t i = 1; i + 1 < nw; i += 4) {
+    const uint64_t a0 = w[i];
+    const uint64_t a1 = i + 2 < nw ? w[i + 1] : 0ull;
+    const uint64_t a2 = i + 3 < nw ? w[i + 2] : 0ull;
+    const uint64_t a3 = i + 4 < nw ? w[i + 3] : 0ull;
+    acc |= a0 | a1 | a2 | a3;
+  }
+  const uint64_t lo_mask = ~0ull << (8u * lead);
+  const uint64_t hi_mask = tail ? (1ull << (8u * tail)) - 1ull : ~0ull;
+  if (nw == 1) acc = first & lo_mask & hi_mask;
+  else acc |= (first & lo_mask) | (last & hi_mask);
   return (acc & 0x8080808080808080ull) != 0;
 }
 __device__ __forceinline__ bool utf8_valid_fast(const uint8_t* s, uint32_t n) {
@@ -1242,7 +1253,7 @@ __device__ __forceinline__ void desc_origin(const DecodeParams& P, uint32_t row,
 // (event.rs:972), the per-kind parser, the cell plane and the heap.  No walker state: the registers go to
 // the parsers.
 #ifndef ETL_CELLS_CTAS
-#define ETL_CELLS_CTAS 6
+#define ETL_CELLS_CTAS 5
 #endif
 __global__ void __launch_bounds__(256, ETL_CELLS_CTAS) k_cells(DecodeParams P) {
   const int lane = threadIdx.x & 31;
