@@ -468,7 +468,7 @@ void etl_dec_batch_free(etl_dec_batch* b) {
 // (the index + record passes keep the memory system to themselves); 2: main stream after the tuple passes.
 // ETL_DEAD_MODE / ETL_DEAD_CTAS are tuning knobs for measurement, not part of the ABI.
 static int dead_mode() {
-  static const int m = getenv("ETL_DEAD_SERIAL") ? 2 : (getenv("ETL_DEAD_MODE") ? atoi(getenv("ETL_DEAD_MODE")) : 0);
+  static const int m = getenv("ETL_DEAD_SERIAL") ? 2 : (getenv("ETL_DEAD_MODE") ? atoi(getenv("ETL_DEAD_MODE")) : 1);
   return m;
 }
 static int dead_ctas(int dflt) {
