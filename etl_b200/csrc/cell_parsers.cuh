@@ -670,6 +670,57 @@ __device__ __forceinline__ bool fast_timestamp(const uint8_t* s, uint32_t n, Cel
   return true;
 }
 
+// "YYYY-MM-DD" exactly (what the pinned session's DateStyle ISO produces), years 0001-9999; else the exact path
+__device__ __forceinline__ bool fast_date(const uint8_t* s, uint32_t n, CellOut& o) {
+  if (n != 10) return false;
+  const uint64_t a = ldu64(s);
+  const uint32_t b = (uint32_t)ldu64(s + 8) & 0xFFFFu;
+  if (((a >> 32) & 0xFFu) != '-' || ((a >> 56) & 0xFFu) != '-') return false;
+  const uint64_t da = (a & 0x00FFFF00FFFFFFFFull) | 0x3000003000000000ull;
+  const uint64_t db = (uint64_t)b | 0x3030303030300000ull;
+  if (!swar_all_digits(da) || !swar_all_digits(db)) return false;
+  const uint32_t y = ((uint32_t)(a & 0xF)) * 1000 + ((uint32_t)(a >> 8) & 0xF) * 100 + ((uint32_t)(a >> 16) & 0xF) * 10 + ((uint32_t)(a >> 24) & 0xF);
+  const uint32_t mo = ((uint32_t)(a >> 40) & 0xF) * 10 + ((uint32_t)(a >> 48) & 0xF);
+  const uint32_t d = (b & 0xF) * 10 + ((b >> 8) & 0xF);
+  if (y < 1 || mo < 1 || mo > 12 || d < 1) return false;
+  const uint32_t dim = (mo == 2) ? (((y % 4 == 0 && y % 100 != 0) || y % 400 == 0) ? 29u : 28u)
+                                 : ((mo == 4 || mo == 6 || mo == 9 || mo == 11) ? 30u : 31u);
+  if (d > dim) return false;
+  o.tag = ETL_CELL_DATE; o.val = (uint64_t)days_from_civil((int64_t)y, (int64_t)mo, (int64_t)d); o.aux = 0;
+  return true;
+}
+// 8 hex characters (memory order) → 4 bytes (memory order); *ok cleared on any non-hex character
+__device__ __forceinline__ uint32_t swar_hex8(uint64_t x, bool* ok) {
+  const uint64_t HI = 0x8080808080808080ull, ONES = 0x0101010101010101ull;
+  if (x & HI) { *ok = false; return 0; }
+  const uint64_t lo = x | 0x2020202020202020ull;
+  const uint64_t digit = ((x + 0x50ull * ONES) & HI) & ~((x + 0x46ull * ONES) & HI);      // x >= '0' and not x > '9'
+  const uint64_t alpha = ((lo + 0x1Full * ONES) & HI) & ~((lo + 0x19ull * ONES) & HI);    // lo >= 'a' and not lo > 'f'
+  if ((digit | alpha) != HI) { *ok = false; return 0; }
+  const uint64_t nib = (x & 0x0F0F0F0F0F0F0F0Full) + (alpha >> 7) * 9ull;
+  const uint64_t pairs = ((nib << 4) | (nib >> 8)) & 0x00FF00FF00FF00FFull;
+  return __byte_perm((uint32_t)pairs, (uint32_t)(pairs >> 32), 0x6420);
+}
+// the hyphenated 36-character spelling (uuid text output); everything else (braces, urn:, simple) → exact path
+__device__ __forceinline__ bool fast_uuid(const uint8_t* s, uint32_t n, uint8_t* heap, uint64_t hpos, CellOut& o) {
+  if (n != 36) return false;
+  const uint64_t g0 = ldu64(s), g1 = ldu64(s + 8), g2 = ldu64(s + 16), g3 = ldu64(s + 24);
+  const uint32_t g4 = (uint32_t)ldu64(s + 32);
+  // '-' at 8, 13, 18, 23
+  if ((g1 & 0xFFu) != '-' || ((g1 >> 40) & 0xFFu) != '-' || ((g2 >> 16) & 0xFFu) != '-' || ((g2 >> 56) & 0xFFu) != '-') return false;
+  bool ok = true;
+  const uint32_t o0 = swar_hex8(g0, &ok);                                                                    // chars 0-7
+  const uint32_t o1 = swar_hex8(((g1 >> 8) & 0xFFFFFFFFull) | ((((g1 >> 48) | (g2 << 16)) & 0xFFFFFFFFull) << 32), &ok);   // 9-12, 14-17
+  const uint32_t o2 = swar_hex8(((g2 >> 24) & 0xFFFFFFFFull) | ((g3 & 0xFFFFFFFFull) << 32), &ok);               // 19-22, 24-27
+  const uint32_t o3 = swar_hex8((g3 >> 32) | ((uint64_t)g4 << 32), &ok);                                       // 28-35
+  if (!ok) return false;
+  uint64_t* dst = reinterpret_cast<uint64_t*>(heap + hpos);      // heap reservations are 8-byte aligned
+  dst[0] = (uint64_t)o0 | ((uint64_t)o1 << 32);
+  dst[1] = (uint64_t)o2 | ((uint64_t)o3 << 32);
+  o.tag = ETL_CELL_UUID; o.val = hpos; o.aux = 16;
+  return true;
+}
+
 // numeric: [+-]digits[.digits] (what Postgres emits) with warp-synchronous loops; everything else
 // (NaN, Infinity, exponents, '_' separators, whitespace) goes to parse_numeric.
 __device__ __forceinline__ uint32_t parse_numeric_sync(unsigned mask, const uint8_t* s, uint32_t n, uint8_t* heap, uint64_t hpos, CellOut& o) {

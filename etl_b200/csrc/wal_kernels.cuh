@@ -1359,6 +1359,15 @@ __global__ void __launch_bounds__(256, ETL_CELLS_CTAS) k_cells(DecodeParams P) {
       case ETL_K_TIMESTAMP:
         if (!fast_timestamp(tv, len, o)) { CellOut t; t.tag = 0; t.val = 0; t.aux = 0; code = parse_text_cell(kind, tv, len, soff, P.heap, hpos, t); o = t; }
         break;
+      case ETL_K_DATE:
+        if (!fast_date(tv, len, o)) { CellOut t; t.tag = 0; t.val = 0; t.aux = 0; code = parse_text_cell(kind, tv, len, soff, P.heap, hpos, t); o = t; }
+        break;
+      case ETL_K_UUID:
+        if (!fast_uuid(tv, len, P.heap, hpos, o)) { CellOut t; t.tag = 0; t.val = 0; t.aux = 0; code = parse_text_cell(kind, tv, len, soff, P.heap, hpos, t); o = t; }
+        break;
+      case ETL_K_BOOL:                                  // bool.rs: exactly "t" / "f"
+        if (len == 1 && (tv[0] == 't' || tv[0] == 'f')) { o.tag = ETL_CELL_BOOL; o.val = tv[0] == 't'; } else code = ETL_E_BOOL;
+        break;
       default: {
         CellOut t; t.tag = 0; t.val = 0; t.aux = 0;
         if (kind & ETL_K_ARRAY) {
