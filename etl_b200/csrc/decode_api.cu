@@ -598,7 +598,7 @@ int etl_dec_decode_begin(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t fla
     CK(cudaStreamSynchronize(st));  // sbb is a local
     P.schema_by_batch = ctx->d_schema_by_batch.p;
   }
-  P.tile_prefix = ctx->d_tile_prefix.p; P.tile_counter = (unsigned int*)(ctx->d_scalars.p + 6);
+  P.tile_prefix = ctx->d_tile_prefix.p;
   const size_t line_words = (in->len + 4095) / 4096 + 1;
   CK(ctx->d_line_bad.ensure(line_words)); CK(ctx->d_dead.ensure(P.n_anchors + 1));
   P.line_bad = ctx->d_line_bad.p; P.dead = ctx->d_dead.p;

@@ -230,14 +230,12 @@ __device__ __noinline__ uint32_t parse_float(const uint8_t* s, uint32_t n, bool 
   // ---- first 19 significant digits
   uint64_t w = 0;
   uint32_t taken = 0, sig = 0;   // sig = significant digits seen (after leading zeros)
-  bool dropped_nonzero = false;
   for (uint32_t k = 0; k < n_int + n_frac; k++) {
     const uint32_t c = (k < n_int) ? s[int0 + k] : s[frac0 + (k - n_int)];
     const uint32_t dgt = c - '0';
     if (sig == 0 && dgt == 0) continue;
     sig++;
-    if (taken < 19) { w = w * 10 + dgt; taken++; }
-    else if (dgt) dropped_nonzero = true;
+    if (taken < 19) { w = w * 10 + dgt; taken++; }   // digits past 19: sig > taken sends the value to the w / w+1 check below
   }
   if (sig == 0) { o.val = sign; return 0; }                 // ±0
   const int64_t q = exp_number - (int64_t)n_frac + (int64_t)(sig - taken);
@@ -266,7 +264,6 @@ __device__ __noinline__ uint32_t parse_float(const uint8_t* s, uint32_t n, bool 
       am = dec_to_binary(d, F);
     }
   }
-  (void)dropped_nonzero;
   o.val = sign | ((uint64_t)am.pow2 << F.mant_bits) | am.mant;
   return 0;
 }

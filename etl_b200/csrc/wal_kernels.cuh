@@ -31,11 +31,6 @@
 
 namespace etl {
 
-#ifndef ETL_TILE_BYTES
-#define ETL_TILE_BYTES 32768
-#endif
-constexpr int kTileBytes = ETL_TILE_BYTES;       // nominal tile = kTileBytes of stream (frames that START inside it)
-constexpr int kTileCap = ETL_TILE_BYTES + 4096;        // shared-memory window; bytes past it are read from global
 #ifndef ETL_WALK_THREADS
 #define ETL_WALK_THREADS 128
 #endif
@@ -109,7 +104,6 @@ struct DecodeParams {
   Summ* group_prefix;        // exclusive prefix per group (pass B)
   Summ* total;               // [0] = fold of everything (shard seam summary)
   Summ* tile_prefix;         // exclusive prefix per tile (pass B2), carry not included
-  unsigned int* tile_counter;  // dynamic tile scheduler of the emit pass
   // global grouping of the DML records by frame shape (k_frames counts, k_bin_scan lays out, k_perm fills)
   uint32_t* bin_count; uint32_t* bin_cursor; uint32_t n_bins; uint32_t* perm; unsigned int* perm_len;
   uint32_t* bin_start; uint32_t* bin_row_base; uint32_t n_batch_schemas;
@@ -503,18 +497,6 @@ __device__ __forceinline__ bool has_high_bits(const uint8_t* s, uint32_t n) {
   else acc |= (first & lo_mask) | (last & hi_mask);
   return (acc & 0x8080808080808080ull) != 0;
 }
-__device__ __forceinline__ bool utf8_valid_fast(const uint8_t* s, uint32_t n) {
-  uint32_t hi = 0;
-  uint32_t i = 0;
-  for (; i + 8 <= n; i += 8) { uint64_t x = ld64u(s + i); hi |= (uint32_t)(x >> 32) | (uint32_t)x; }
-  if (i < n) {
-    uint64_t x = ld64u(s + i);
-    x &= (1ull << (8 * (n - i))) - 1ull;  // 1..7 valid bytes
-    hi |= (uint32_t)(x >> 32) | (uint32_t)x;
-  }
-  if (!(hi & 0x80808080u)) return true;
-  return utf8_valid(s, n);
-}
 
 // text.rs:28-173 dispatch for one text cell (bytes already UTF-8 validated). `soff` = absolute
 // stream offset of the value bytes.
@@ -761,16 +743,6 @@ __global__ void __launch_bounds__(256) k_long_verdict(DecodeParams P) {
 // out of line: k_walk's registers are the scarce resource
 __device__ __noinline__ bool utf8_medium_bad(const uint8_t* cell, uint32_t len) { return utf8_range_bad(cell, len, 0, len, 0, 1); }
 
-__device__ __forceinline__ uint32_t warp_incl_sum(uint32_t v, int lane) {
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += u; }
-  return v;
-}
-__device__ __forceinline__ int32_t warp_incl_max(int32_t v, int lane) {
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) { int32_t u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v = max(v, u); }
-  return v;
-}
 
 // ================================================================================================
 // Shape bins.  A warp of k_walk is fastest when its 32 records have the same frame shape (table
@@ -1005,9 +977,6 @@ __global__ void __launch_bounds__(256) k_frames(DecodeParams P) {
 
 // ================================================================================================
 // pass C2: tuples.  Thread per DML record (event.rs:376-919 + text.rs:28-173).
-#ifndef ETL_WALK_CTAS
-#define ETL_WALK_CTAS 4
-#endif
 #ifndef ETL_WALK_PREFETCH
 #define ETL_WALK_PREFETCH 1
 #endif
