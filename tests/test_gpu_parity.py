@@ -382,3 +382,84 @@ def _raw_text_insert(rel_id: int, key: bytes, payload: bytes) -> bytes:
     body = b"I" + struct.pack(">I", rel_id) + b"N" + struct.pack(">H", 2)
     body += b"t" + struct.pack(">I", len(key)) + key + b"t" + struct.pack(">I", len(payload)) + payload
     return body
+
+
+# ---------------------------------------------------------------------------------------------
+# seeded fuzz over every scalar decode class: canonical spellings and mutations of them
+# ---------------------------------------------------------------------------------------------
+FUZZ_KINDS = [  # (type oid, canonical spellings, alphabet used for mutations)
+    (21, ["0", "-32768", "32767", "+7", "12"], "0123456789+- _x"),
+    (23, ["0", "-2147483648", "2147483647", "+15", "000123"], "0123456789+- _.e"),
+    (20, ["0", "-9223372036854775808", "9223372036854775807", "18446744073709551615", "42"], "0123456789+- "),
+    (26, ["0", "4294967295", "4294967296", "-1", "16384"], "0123456789+-"),
+    (16, ["t", "f", "true", "T", ""], "tfTF01 "),
+    (1700, ["0", "-0.00", "123.456", "NaN", "Infinity", "-Infinity", "1e10", "0.000000001", "99999999999999999999.0001", "1_000", ".5", "5.", "+1.5E-3"],
+     "0123456789.+-eE_NaInfity "),
+    (1082, ["2024-02-29", "0001-01-01", "9999-12-31", "2023-02-29", "2024-1-5", " 2024-01-05", "2024-01-05 ", "+2024-01-05", "10000-01-01", "-0001-01-01"],
+     "0123456789-+ /"),
+    (1083, ["00:00:00", "23:59:59.999999", "12:34:56.1", "24:00:00", "12:34", "12:34:60", "1:2:3", "12:34:56.1234567891"], "0123456789:. "),
+    (1114, ["2024-02-29 12:34:56", "2024-02-29 12:34:56.789", "2024-02-29T12:34:56", "2024-02-29 24:00:00", "2024-02-30 00:00:00",
+            "1-1-1 1:1:1", "2024-02-29  12:34:56", "2024-02-29 12:34:56.", "2024-02-29 12:34:60"], "0123456789-:. T"),
+    (1184, ["2024-02-29 12:34:56+00", "2024-02-29 12:34:56.789-07", "2024-02-29 12:34:56+05:30", "2024-02-29 12:34:56+0530", "2024-02-29 12:34:56Z",
+            "2024-02-29 12:34:56 +00", "2024-02-29 12:34:56+24", "2024-02-29 12:34:56+5", "2024-02-29 12:34:56+05:3", "2024-02-29 12:34:56.123456789+00:00:00"],
+     "0123456789-:. +Zz"),
+    (2950, ["a0eebc99-9c0b-4ef8-bb6d-6bb9bd380a11", "A0EEBC99-9C0B-4EF8-BB6D-6BB9BD380A11", "a0eebc999c0b4ef8bb6d6bb9bd380a11",
+            "{a0eebc99-9c0b-4ef8-bb6d-6bb9bd380a11}", "urn:uuid:a0eebc99-9c0b-4ef8-bb6d-6bb9bd380a11", "a0eebc99-9c0b-4ef8-bb6d-6bb9bd380a1"],
+     "0123456789abcdefABCDEFg-{}"),
+    (17, ["\\x", "\\x00ff", "\\xDEADbeef", "\\x0", "abc", "\\\\000", "\\x+f", ""], "\\x0123456789abcdefABCDEFg+ "),
+    (3802, ['{"a": 1}', "[1, 2.5, -3e2]", '"s"', "null", " true ", '{"a": {"b": [null, false]}}', '"\\u00e9"', '"\\ud83d\\ude00"', "01", "{", '{"a" 1}'],
+     '{}[]":, 0123456789.-+eEtruefalsn\\ud8'),
+    (25, ["", "plain", "with space", "unicode é ✓ 🤔", "x" * 300], "abc é✓"),
+    (701, ["0", "-1.5", "1e308", "1e309", "NaN", "-inf", "4.9e-324", "0.1", "1.7976931348623157e308", "2.2250738585072011e-308"], "0123456789.+-eEnaif"),
+    (700, ["0", "-1.5", "3.4028235e38", "3.4028236e38", "1e-45", "0.1", "16777217"], "0123456789.+-eE"),
+]
+
+
+@pytest.mark.parametrize("oid", [k[0] for k in FUZZ_KINDS])
+def test_scalar_fuzz_parity(gpu, oracle_mod, oid):
+    """Per decode class: the canonical spellings above and ~300 seeded mutations of them (insert / delete /
+    replace from a class-specific alphabet).  Values the oracle accepts go into one stream (every typed value
+    compared); values it rejects are decoded one per stream (error kind and position compared)."""
+    _, seeds, alphabet = next(k for k in FUZZ_KINDS if k[0] == oid)
+    rng = np.random.default_rng(oid)
+    cases = list(seeds)
+    for _ in range(300):
+        s = list(seeds[int(rng.integers(0, len(seeds)))])
+        for _ in range(int(rng.integers(1, 3))):
+            op = int(rng.integers(0, 3))
+            p = int(rng.integers(0, len(s) + 1))
+            ch = alphabet[int(rng.integers(0, len(alphabet)))]
+            if op == 0:
+                s.insert(p, ch)
+            elif op == 1 and s:
+                del s[min(p, len(s) - 1)]
+            elif s:
+                s[min(p, len(s) - 1)] = ch
+        cases.append("".join(s))
+    cases = list(dict.fromkeys(cases))
+    cols = [sc.col("id", sc.INT8, 1), sc.col("v", oid, None, True)]
+    rel = pg.relation(95, "public", "fuzz", "d", sc.rel_cols(cols, {"id"}))
+    valid = [c for c in cases if oracle_mod.parse_cell(oid, c.encode())[0] == 0]
+    invalid = [c for c in cases if c not in valid]
+    assert valid, oid
+    w = pg.StreamWriter()
+    tx = sc.Tx(w)
+    tx.begin()
+    w.emit(rel)
+    for i, c in enumerate(valid):
+        w.emit(pg.insert(95, [str(i), c]))
+    tx.commit()
+    stream = w.bytes()
+    got, want = both(gpu, oracle_mod, {95: cols}, stream)
+    assert want.first_error[0] is None
+    assert_planes_equal(got, want, stream)
+    for c in invalid[:120]:
+        w = pg.StreamWriter()
+        tx = sc.Tx(w)
+        tx.begin()
+        w.emit(rel)
+        w.emit(pg.insert(95, ["1", c]))
+        tx.commit()
+        got, want = both(gpu, oracle_mod, {95: cols}, w.bytes())
+        assert want.first_error[0] is not None, (oid, c)
+        assert got.first_error == want.first_error, (oid, c, got.first_error, want.first_error)
