@@ -187,6 +187,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("ETL_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
@@ -320,10 +321,12 @@ def main():
         pipeline_ms = float(km[3])                                          # index + records passes incl. the join with the side stream
         emit_avg = ktime[dominant]
         achieved = kbytes[dominant] / (emit_avg * 1e-3) / 1e9
-        traffic = None
+        traffic, alone_us = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(f"{w.name}/{dominant}")
+                tj = json.load(f)
+            traffic = tj.get(f"{w.name}/{dominant}")
+            alone_us = tj.get(f"{w.name}/{dominant}/serialised_us") if args.scale == 1.0 else None
         except Exception:
             pass
         line = {
@@ -339,6 +342,10 @@ def main():
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": kbytes[dominant], "avg_launch_ms": emit_avg,
+                         "alone_under_ncu": ({"ms": alone_us / 1e3, "achieved": kbytes[dominant] / (alone_us * 1e-6) / 1e9,
+                                              "frac": kbytes[dominant] / (alone_us * 1e-6) / 1e9 / peak,
+                                              "source": "profiles/traffic.json (ncu launch list of this command: kernels serialised, not sharing HBM)"}
+                                             if alone_us else None),
                          "kernels_ms": kern,
                          "pipeline": {"algorithmic_bytes": algo_bytes, "ms": pipeline_ms,
                                       "achieved": algo_bytes / (pipeline_ms * 1e-3) / 1e9,

@@ -2,7 +2,7 @@
 """One-line digest of a bench.py JSON line. Usage: bench_line.py file.json"""
 import json
 import sys
-d = json.load(open(sys.argv[1]))
+d = json.loads([l for l in open(sys.argv[1]) if l.startswith("{")][-1])
 r = d["roofline"]
 print(d["config"]["workload"].split(":")[0], f"N={d['n_gpus']}", round(d["value"], 1), "GB/s", round(d["events_per_s"] / 1e6, 1), "Mev/s", round(d["ms_per_step"], 3), "ms",
       "pipeline_frac", round(r["pipeline"]["frac"], 3), "e2e", round(d.get("e2e", {}).get("value", 0), 1),

@@ -52,6 +52,7 @@ with open(os.path.join(P, f"{rnd}_launches_bench_c5.txt"), "w") as f:
         f.write(f"{k:28s} {int(n):3d} {a['gpu__time_duration.sum'] / n:10.1f} {100 * a['gpu__time_duration.sum'] / tot:6.1f}% "
                 f"{a['dram__bytes_read.sum'] / n / 1e6:11.1f} {a['dram__bytes_write.sum'] / n / 1e6:11.1f}\n")
         traffic[f"c5/{k}"] = int((a["dram__bytes_read.sum"] + a["dram__bytes_write.sum"]) / n)
+        traffic[f"c5/{k}/serialised_us"] = round(a["gpu__time_duration.sum"] / n, 1)
     f.write(f"\nsum of per-launch averages: {sum(a['gpu__time_duration.sum'] / (a['n'] or 1) for a in agg.values()) / 1e3:.3f} ms per decode\n")
 json.dump({"_source": f"profiles/{rnd}_launches_bench_c5.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, c5 at 10 GiB)", **traffic},
           open(os.path.join(P, "traffic.json"), "w"), indent=1)
