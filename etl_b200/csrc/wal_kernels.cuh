@@ -1,24 +1,27 @@
-// wal_kernels.cuh — sm_100a kernels of the batched pgoutput decode path.
+// wal_kernels.cuh — sm_100a kernels of the batched pgoutput decode path (launch order):
 //
-//   k_index   (pass A)  one thread per anchor segment walks the 'd'+len32 frame chain from global
-//                       memory (only frame heads are touched), classifies frames and reduces a
-//                       per-tile summary {records, cells, heap bytes, stream-state transformer}.
-//   k_scan    (pass B)  single-block exclusive scan of the per-group summaries (the state
-//                       transformer is associative, so commit_lsn / tx_ordinal become a scan).
-//   k_frames  (pass C1) one thread per anchor segment replays its frames with the segment's exclusive
-//                       prefix (record index, cell base, stream state) and writes the record plane —
-//                       the apply loop's per-message state machine, serial inside 2 KiB, parallel across.
-//   k_walk    (pass C2) one thread per DML record; each CTA first groups its 256 records by frame
-//                       shape (schema, op, old-image kind) so a warp walks structurally identical
-//                       tuples in lockstep: cell i of every lane is the same column → the same parser.
-//   k_act_*   (pass A0) compact the list of segments that contain a frame start (TOAST-heavy streams
-//                       leave most segments empty).
-//   k_utf8_dead         structure-blind UTF-8 pass over the segments WITHOUT a frame start (the inside of
-//                       TOAST-sized values) at HBM speed: one bit per 128-byte line, "some position in
-//                       this line breaks the position-local rule".  Needs no frame structure, so it runs
-//                       on a second stream underneath the latency-bound passes.
-//   k_long_verdict      after both streams join: the interior verdict of every long text cell that
-//                       k_walk listed, read from the line bitmap.
+//   k_act_count/scan/scatter  list the anchor segments that contain a frame start (`act`) and those that do
+//                       not (`dead`): TOAST-heavy streams leave most segments empty.
+//   k_index   (pass A)  one thread per live segment walks the 'd'+len32 frame chain from global memory (only
+//                       frame heads are touched), classifies frames and reduces a per-tile summary
+//                       {records, cells, descriptor slots, stream-state transformer}.
+//   k_scan, k_tile_prefix (pass B)  exclusive scans of the summaries (the state transformer is associative,
+//                       so commit_lsn / tx_ordinal become a scan).
+//   k_utf8_dead (side stream)  structure-blind UTF-8 pass over the dead segments (the inside of TOAST-sized
+//                       values) at HBM speed: one bit per 128-byte line, "some position in this line breaks
+//                       the position-local rule".
+//   k_frames  (pass C1) one thread per live segment replays its frames with the segment's exclusive prefix
+//                       (record index, cell base, stream state) and writes the record plane — the apply
+//                       loop's per-message state machine, serial inside 2 KiB, parallel across; counts the
+//                       frame shapes.
+//   k_bin_scan, k_perm  counting sort of the DML records by frame shape (schema version, op, old-image kind).
+//   k_walk    (pass C2a) one thread per DML record in shape order: hops the TupleData cell headers and writes
+//                       one 16-byte descriptor per wire cell, row-major by (warp chunk, slot).
+//   k_cells   (pass C2b) one warp per descriptor row = 32 cells of one column: UTF-8, per-kind parser, cell
+//                       plane + heap.
+//   k_copy    (pass C2c) unchanged-TOAST cells of updates take the old image's decoded cell.
+//   k_long_verdict      after both streams join: the interior verdict of every long text cell that k_cells
+//                       listed, read from the line bitmap.
 //
 // Reference semantics: apply.rs:1687-2248 (state machine), event.rs:376-979 (tuples → rows),
 // text.rs:28-173 (cells).  HBM-bound integer/byte work — no tensor cores.
