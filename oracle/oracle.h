@@ -78,6 +78,16 @@ uint32_t orc_parse_cell(uint32_t type_oid, const uint8_t* text, uint32_t len, ui
                         uint32_t* heap_len);
 /* type oid → ETL_K_* exactly as text.rs:28-173 + utils.rs:7-16 dispatch */
 uint32_t orc_kind_for_oid(uint32_t type_oid);
+
+/* COPY-text row (table_row.rs:25-165; SURVEY §8f N1 groundwork).  Cells of kind string/json carry offsets
+ * into `text_out` (the unescaped field values); numeric/bytea/uuid/array offsets into `heap_out`.
+ * Returns 0 or an error code: an ETL_E_* cell error, or one of the two row-level errors below. */
+#define ORC_E_COPY_NOT_TERMINATED 101u   /* "Row data not properly terminated" (ConversionError) */
+#define ORC_E_COPY_COLUMN_COUNT 102u     /* "Column count mismatch between schema and row" (ConversionError) */
+uint32_t orc_parse_copy_row(const uint32_t* type_oids, uint32_t n_cols, const uint8_t* row, uint64_t len,
+                            uint8_t* tags, uint64_t* vals, uint32_t* auxs, uint32_t* n_values,
+                            uint8_t* text_out, uint64_t text_cap, uint64_t* text_len,
+                            uint8_t* heap_out, uint64_t heap_cap, uint64_t* heap_len, uint32_t* err_col);
 uint32_t orc_error_kind(uint32_t code);
 
 #ifdef __cplusplus

@@ -18,7 +18,7 @@ _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("oracle_cells.c", "oracle_stream.c", "oracle.h",
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_cells.c", "oracle_stream.c", "oracle_copy.c", "oracle.h",
                                               "oracle_internal.h", "../include/etl_decode.h")]
     if force or not os.path.exists(_LIB_PATH) or any(
             os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs):
@@ -237,3 +237,29 @@ def parse_cell(type_oid: int, text: bytes):
 def kind_for_oid(type_oid: int) -> int:
     """ETL_K_* decode class the reference's `Type` dispatch gives this oid (oracle_cells.c)."""
     return int(lib().orc_kind_for_oid(type_oid))
+
+
+E_COPY_NOT_TERMINATED, E_COPY_COLUMN_COUNT = 101, 102
+
+
+def parse_copy_row(type_oids: Sequence[int], row: bytes):
+    """table_row.rs:25-165 for one COPY-text row → (err_code, err_col, cells) with cells as
+    [(tag, val, aux)], plus the unescaped text plane and the heap the cells point into."""
+    L = lib()
+    if not getattr(L, "_copy_bound", False):
+        L.orc_parse_copy_row.restype = C.c_uint32
+        L.orc_parse_copy_row.argtypes = [C.POINTER(C.c_uint32), C.c_uint32, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint8),
+                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8),
+                                         C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint64),
+                                         C.POINTER(C.c_uint32)]
+        L._copy_bound = True
+    n = len(type_oids)
+    oids = (C.c_uint32 * max(n, 1))(*type_oids)
+    tags, vals, auxs = (C.c_uint8 * max(n, 1))(), (C.c_uint64 * max(n, 1))(), (C.c_uint32 * max(n, 1))()
+    nv, ecol = C.c_uint32(), C.c_uint32()
+    tcap, hcap = len(row) + 16, 16 * len(row) + 1024
+    text, heap = (C.c_uint8 * tcap)(), (C.c_uint8 * hcap)()
+    tl, hl = C.c_uint64(), C.c_uint64()
+    e = L.orc_parse_copy_row(oids, n, row, len(row), tags, vals, auxs, C.byref(nv), text, tcap, C.byref(tl), heap, hcap, C.byref(hl), C.byref(ecol))
+    cells = [(tags[i], vals[i], auxs[i]) for i in range(nv.value)]
+    return e, (None if ecol.value == 0xFFFFFFFF else ecol.value), cells, bytes(text[:tl.value]), bytes(heap[:min(hl.value, hcap)])
