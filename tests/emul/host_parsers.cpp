@@ -26,54 +26,23 @@ static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
   return out;
 }
 
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+
 #include "cell_parsers.cuh"
 #include "float_parse.cuh"
+#include "array_parse.cuh"
 
 using namespace etl;
 
-// the exact path: the same dispatch as parse_text_cell_impl (wal_kernels.cuh)
+// the exact path: parse_text_cell_impl itself (array_parse.cuh); arrays through parse_array_any with a private heap region
 static uint32_t exact(uint32_t kind, const uint8_t* s, uint32_t n, uint64_t soff, HeapCursor& hc, CellOut& o) {
-  o.aux = 0;
-  int64_t iv;
-  uint32_t e;
-  switch (kind) {
-    case ETL_K_STRING: o.tag = ETL_CELL_STRING; o.val = soff; o.aux = n; return 0;
-    case ETL_K_I32: e = parse_int(s, n, true, 2147483647ull, 2147483648ull, &iv); o.tag = ETL_CELL_I32; o.val = (uint64_t)iv; return e;
-    case ETL_K_I64: e = parse_int(s, n, true, 9223372036854775807ull, 9223372036854775808ull, &iv); o.tag = ETL_CELL_I64; o.val = (uint64_t)iv; return e;
-    case ETL_K_I16: e = parse_int(s, n, true, 32767ull, 32768ull, &iv); o.tag = ETL_CELL_I16; o.val = (uint64_t)iv; return e;
-    case ETL_K_U32: e = parse_int(s, n, false, 4294967295ull, 0ull, &iv); o.tag = ETL_CELL_U32; o.val = (uint64_t)iv; return e;
-    case ETL_K_BOOL:
-      if (n == 1 && (s[0] == 't' || s[0] == 'f')) { o.tag = ETL_CELL_BOOL; o.val = s[0] == 't'; return 0; }
-      return ETL_E_BOOL;
-    case ETL_K_NUMERIC: return parse_numeric(s, n, hc, o);
-    case ETL_K_TIMESTAMPTZ:
-      if (parse_timestamptz_fmt(s, n, true, o)) return 0;
-      if (parse_timestamptz_fmt(s, n, false, o)) return 0;
-      return ETL_E_DATETIME;
-    case ETL_K_JSON:
-      if (!json_valid(s, n)) return ETL_E_JSON;
-      o.tag = ETL_CELL_JSON; o.val = soff; o.aux = n; return 0;
-    case ETL_K_DATE: {
-      Cur c{s, n}; int64_t days;
-      if (!parse_date_part(c, &days) || c.n != 0) return ETL_E_DATETIME;
-      o.tag = ETL_CELL_DATE; o.val = (uint64_t)days; return 0;
-    }
-    case ETL_K_TIME: {
-      Cur c{s, n}; int64_t secs; uint32_t ns;
-      if (!parse_time_part(c, &secs, &ns) || c.n != 0) return ETL_E_DATETIME;
-      o.tag = ETL_CELL_TIME; o.val = (uint64_t)secs; o.aux = ns; return 0;
-    }
-    case ETL_K_TIMESTAMP: {
-      Cur c{s, n}; int64_t days, secs; uint32_t ns;
-      if (!parse_ts_prefix(c, &days, &secs, &ns) || c.n != 0) return ETL_E_DATETIME;
-      o.tag = ETL_CELL_TIMESTAMP; o.val = (uint64_t)(days * 86400 + secs); o.aux = ns; return 0;
-    }
-    case ETL_K_UUID: return parse_uuid(s, n, hc, o);
-    case ETL_K_BYTES: return parse_bytea(s, n, hc, o);
-    case ETL_K_F32: return parse_float(s, n, true, o);
-    case ETL_K_F64: return parse_float(s, n, false, o);
-    default: return ETL_E_MALFORMED_FRAME;
+  if (kind & ETL_K_ARRAY) {
+    static thread_local unsigned long long arr_top;
+    arr_top = 0;
+    const uint32_t e = parse_array_any(ArrHeap{hc.heap, &arr_top, 0, 1ull << 16}, kind, s, n, o);
+    return e == 0xFFFFFFFEu ? 0xFFFFFFFEu : e;
   }
+  return parse_text_cell_impl(kind, s, n, soff, hc, o);
 }
 
 extern "C" uint32_t emu_parse_cell(uint32_t kind, const uint8_t* text, uint32_t n, int fast, uint8_t* tag, uint64_t* val,

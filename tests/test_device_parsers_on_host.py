@@ -125,3 +125,38 @@ def test_device_parsers_match_oracle_on_host(emu, oracle_mod, oid):
             got = emu(kind, text, fast)
             assert got == want, (oid, text, "fast" if fast else "exact", got, want)
     assert n_ok > N_PER_KIND // 20, (oid, n_ok)
+
+
+from test_gpu_parity import ARRAY_COLS  # noqa: E402
+
+
+@pytest.mark.parametrize("oid", [k[0] for k in ARRAY_COLS])
+def test_device_array_parser_matches_oracle_on_host(emu, oracle_mod, oid):
+    """text.rs:184-249 + element dispatch: the device splitter (array_parse.cuh) against the oracle on mutated
+    array literals — quoting, escapes, NULL spellings, empty elements, element parse errors."""
+    _, valid, invalid = next(k for k in ARRAY_COLS if k[0] == oid)
+    kind = oracle_mod.kind_for_oid(oid)
+    if not kind & 0x20:
+        pytest.skip("not an array decode class in the oracle")
+    seeds = list(valid) + list(invalid) + ["{}", "{NULL}", '{"a,b",c}', '{"\\"q\\"",\\\\}', "{ 1 , 2 }"]
+    alphabet = '{}",\\ NULnul0123456789.-+:eabtfx'
+    rng = random.Random(oid * 104729)
+    n_ok = 0
+    n = max(2000, N_PER_KIND // 4)
+    for _ in range(n):
+        s = list(rng.choice(seeds))
+        for _ in range(rng.randint(0, 3)):
+            op, p, ch = rng.randint(0, 2), rng.randint(0, len(s)), rng.choice(alphabet)
+            if op == 0:
+                s.insert(p, ch)
+            elif s and op == 1:
+                del s[min(p, len(s) - 1)]
+            elif s:
+                s[min(p, len(s) - 1)] = ch
+        text = "".join(s).encode()
+        e, tag, val, aux, heap = oracle_mod.parse_cell(oid, text)
+        want = (e, None) if e else (0, decode_cell(tag, val, aux, text, heap))
+        n_ok += e == 0
+        got = emu(kind, text, 1)
+        assert got == want, (oid, text, got, want)
+    assert n_ok > n // 20, (oid, n_ok)
