@@ -43,7 +43,8 @@ class Planes(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("n_cells", C.c_uint64), ("heap_bytes", C.c_uint64),
                 ("rec_off", C.c_void_p), ("rec_kind", C.c_void_p), ("rec_flags", C.c_void_p), ("rec_rel", C.c_void_p),
                 ("rec_schema", C.c_void_p), ("rec_start_lsn", C.c_void_p), ("rec_commit_lsn", C.c_void_p),
-                ("rec_tx_ordinal", C.c_void_p), ("rec_cell_base", C.c_void_p), ("cell_tag", C.c_void_p),
+                ("rec_tx_ordinal", C.c_void_p), ("rec_cell_base", C.c_void_p), ("rec_tuple_bytes", C.c_void_p),
+                ("rec_heap_hint", C.c_void_p), ("cell_tag", C.c_void_p),
                 ("cell_val", C.c_void_p), ("cell_aux", C.c_void_p), ("heap", C.c_void_p)]
 
 
@@ -52,7 +53,8 @@ class Summary(C.Structure):
                 ("update_bytes", C.c_uint64), ("delete_bytes", C.c_uint64), ("n_events", C.c_uint64),
                 ("n_schemas", C.c_uint32), ("gpu_launches", C.c_uint32), ("kernel_ms", C.c_float),
                 ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("index_ms", C.c_float),
-                ("emit_ms", C.c_float), ("frames_ms", C.c_float), ("walk_ms", C.c_float), ("spans_ms", C.c_float), ("cells_ms", C.c_float), ("_pad1", C.c_float), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("span_bytes", C.c_uint64)]
+                ("emit_ms", C.c_float), ("frames_ms", C.c_float), ("walk_ms", C.c_float), ("spans_ms", C.c_float), ("cells_ms", C.c_float), ("_pad1", C.c_float), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("span_bytes", C.c_uint64),
+                ("record_index_base", C.c_uint64), ("abi_version", C.c_uint32), ("_pad2", C.c_uint32)]
 
 
 class SchemaInfo(C.Structure):
@@ -67,7 +69,8 @@ EXPORTS = [
     "etl_stage_append_framed", "etl_stage_view", "etl_dec_create", "etl_dec_set_stream", "etl_dec_destroy",
     "etl_dec_last_error", "etl_dec_put_table_schema", "etl_dec_reset_relations", "etl_dec_decode",
     "etl_dec_decode_begin", "etl_dec_decode_finish", "etl_dec_batch_free", "etl_dec_batch_planes",
-    "etl_dec_batch_summary", "etl_dec_batch_schema",
+    "etl_dec_batch_summary", "etl_dec_batch_schema", "etl_dec_decode_sharded", "etl_dec_comm_unique_id", "etl_dec_comm_init",
+    "etl_dec_kind_for_type_oid", "etl_dec_mem_info",
 ]
 
 _lib = None
@@ -116,6 +119,12 @@ def load(build: bool = True):
     L.etl_dec_batch_planes.argtypes = [vp, C.c_int, C.POINTER(Planes)]
     L.etl_dec_batch_summary.argtypes = [vp, C.POINTER(Summary)]
     L.etl_dec_batch_schema.argtypes = [vp, C.c_uint32, C.POINTER(SchemaInfo)]
+    L.etl_dec_decode_sharded.argtypes = [vp, C.POINTER(DecInput), C.c_uint32, C.POINTER(vp)]
+    L.etl_dec_comm_unique_id.argtypes = [vp, C.c_uint32]
+    L.etl_dec_comm_init.argtypes = [vp, vp, C.c_uint32, C.c_int, C.c_int]
+    L.etl_dec_kind_for_type_oid.argtypes = [C.c_uint32]
+    L.etl_dec_kind_for_type_oid.restype = C.c_uint32
+    L.etl_dec_mem_info.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     _lib = L
     return L
 

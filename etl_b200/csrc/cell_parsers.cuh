@@ -290,7 +290,7 @@ __device__ __noinline__ uint32_t parse_numeric(const uint8_t* s, uint32_t n, Hea
   if (c.s[0] == '+') { explicit_sign = true; c.s++; c.n--; }
   else if (c.s[0] == '-') { neg = true; explicit_sign = true; c.s++; c.n--; }
   etl_numeric_hdr hdr;
-  hdr.kind = 0; hdr.sign = 0; hdr.weight = 0; hdr.scale = 0; hdr._pad = 0;
+  hdr.kind = 0; hdr.sign = 0; hdr.weight = 0; hdr.scale = 0; hdr.pushed_groups = 0;
   const uint8_t* p = c.s;
   uint32_t rem = c.n;
   if (!(rem > 0 && (is_digit(p[0]) || p[0] == '.'))) {
@@ -385,9 +385,10 @@ __device__ __noinline__ uint32_t parse_numeric(const uint8_t* s, uint32_t n, Hea
     hdr.sign = neg ? 1 : 0;
     hdr.weight = (int16_t)fw;
     nd = last_nz;
+    hdr.pushed_groups = (uint16_t)min(ndig, 0xFFFFu);   // groups pushed before the zero strips (Vec capacity, size hints)
   }
   *reinterpret_cast<etl_numeric_hdr*>(hc.heap + off) = hdr;
-  o.tag = ETL_CELL_NUMERIC; o.val = off; o.aux = nd;
+  o.tag = ETL_CELL_NUMERIC | ((uint32_t)hdr.pushed_groups << 16); o.val = off; o.aux = nd;
   return 0;
 }
 // heap bytes reserved for a numeric cell of n text bytes (upper bound on 8 + 2*ndigits, 8-aligned)
@@ -777,7 +778,7 @@ __device__ __forceinline__ uint32_t parse_numeric_sync(unsigned mask, const uint
   }
   if (simple) {
     etl_numeric_hdr hdr;
-    hdr.kind = 0; hdr.sign = 0; hdr.weight = 0; hdr.scale = (uint16_t)nfrac; hdr._pad = 0;
+    hdr.kind = 0; hdr.sign = 0; hdr.weight = 0; hdr.scale = (uint16_t)nfrac; hdr.pushed_groups = 0;
     uint32_t nd = 0;
     code = 0;
     if (nfrac > 16383u) code = ETL_E_NUMERIC;
@@ -785,9 +786,10 @@ __device__ __forceinline__ uint32_t parse_numeric_sync(unsigned mask, const uint
       const int64_t fw = weight - (int64_t)lead;
       if (fw < -32768 || fw > 32767) code = ETL_E_NUMERIC;
       hdr.sign = neg ? 1 : 0; hdr.weight = (int16_t)fw; nd = last_nz;
+      hdr.pushed_groups = (uint16_t)ndig;            // n ≤ 4096 here
     }
     *reinterpret_cast<etl_numeric_hdr*>(hc.heap + off) = hdr;
-    o.tag = ETL_CELL_NUMERIC; o.val = off; o.aux = nd;
+    o.tag = ETL_CELL_NUMERIC | ((uint32_t)hdr.pushed_groups << 16); o.val = off; o.aux = nd;
   }
   if (code == 0xFFFFFFFFu) {                          // own copies: `o` must not have its address taken (see k_walk)
     HeapCursor h2{heap, hpos};

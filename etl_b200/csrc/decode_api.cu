@@ -4,8 +4,17 @@
 // path): staging, schema catalogue, Relation → ReplicationMask / IdentityMask
 // (apply.rs:2012-2089, event.rs:325-369, etl-postgres/src/types/schema.rs:288-323,406-438,527-535),
 // buffer management and kernel orchestration.  Every per-row / per-cell operation of the hot path
-// runs in the sm_100a kernels of wal_kernels.cuh; there is no CPU decode fallback.
+// runs in the sm_100a kernels of wal_kernels.cuh / rows_kernel.cuh; there is no CPU decode fallback.
+//
+// One decode = one host synchronisation, at the end.  The planes are sized from what the previous
+// batches needed per staged byte; k_scan compares the real totals with the reservation on the device and,
+// when they do not fit, every later kernel returns at once and the host re-runs the record and tuple passes
+// with exact sizes (the first batch of a context takes the exact path: index pass, sync, then the rest).
+// Multi-GPU: the shard seam summaries are all-gathered by NCCL on the decode stream and folded on the
+// device (k_seam_fold) — nothing returns to the host between the index pass and the record pass.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the entry points are resolved at run time (etl_dec_comm_*)
 
 #include <algorithm>
 #include <cstdio>
@@ -16,6 +25,7 @@
 #include <vector>
 
 #include "etl_decode.h"
+#include "oid_classes.h"
 #include "wal_kernels.cuh"
 
 using namespace etl;
@@ -41,51 +51,6 @@ struct RelVersion {  // ReplicatedTableSchema (schema.rs:651-900)
   std::vector<int32_t> index;
 };
 
-// text.rs:28-173 + utils.rs:7-16: type oid → decode class
-uint32_t kind_for_oid(uint32_t oid) {
-  switch (oid) {
-    case 16: return ETL_K_BOOL;
-    case 1000: return ETL_K_ARRAY | ETL_K_BOOL;
-    case 18: case 1042: case 1043: case 19: case 25: case 790: return ETL_K_STRING;
-    case 1002: case 1014: case 1015: case 1003: case 1009: case 791: return ETL_K_ARRAY | ETL_K_STRING;
-    case 21: return ETL_K_I16;
-    case 1005: return ETL_K_ARRAY | ETL_K_I16;
-    case 23: return ETL_K_I32;
-    case 1007: return ETL_K_ARRAY | ETL_K_I32;
-    case 20: return ETL_K_I64;
-    case 1016: return ETL_K_ARRAY | ETL_K_I64;
-    case 700: return ETL_K_F32;
-    case 1021: return ETL_K_ARRAY | ETL_K_F32;
-    case 701: return ETL_K_F64;
-    case 1022: return ETL_K_ARRAY | ETL_K_F64;
-    case 1700: return ETL_K_NUMERIC;
-    case 1231: return ETL_K_ARRAY | ETL_K_NUMERIC;
-    case 17: return ETL_K_BYTES;
-    case 1001: return ETL_K_ARRAY | ETL_K_BYTES;
-    case 1082: return ETL_K_DATE;
-    case 1182: return ETL_K_ARRAY | ETL_K_DATE;
-    case 1083: return ETL_K_TIME;
-    case 1183: return ETL_K_ARRAY | ETL_K_TIME;
-    case 1114: return ETL_K_TIMESTAMP;
-    case 1115: return ETL_K_ARRAY | ETL_K_TIMESTAMP;
-    case 1184: return ETL_K_TIMESTAMPTZ;
-    case 1185: return ETL_K_ARRAY | ETL_K_TIMESTAMPTZ;
-    case 2950: return ETL_K_UUID;
-    case 2951: return ETL_K_ARRAY | ETL_K_UUID;
-    case 114: case 3802: return ETL_K_JSON;
-    case 199: case 3807: return ETL_K_ARRAY | ETL_K_JSON;
-    case 26: return ETL_K_U32;
-    case 1028: return ETL_K_ARRAY | ETL_K_U32;
-    default: break;
-  }
-  static const uint32_t other_arrays[] = {
-      143, 271, 629, 651, 719, 775, 1006, 1008, 1010, 1011, 1012, 1013, 1017, 1018, 1019, 1020, 1027, 1034, 1040,
-      1041, 1187, 1263, 1270, 1561, 1563, 2201, 2207, 2208, 2209, 2210, 2211, 2949, 3221, 3643, 3644, 3645, 3735,
-      3770, 3905, 3907, 3909, 3911, 3913, 3927, 4073, 4090, 4097, 4192, 5039, 6150, 6151, 6152, 6153, 6155, 6157};
-  for (uint32_t a : other_arrays)
-    if (a == oid) return ETL_K_ARRAY | ETL_K_STRING;
-  return ETL_K_STRING;
-}
 bool kind_supported_on_device(uint32_t k) {
   if (k & ETL_K_ARRAY) k &= ~(uint32_t)ETL_K_ARRAY;   // arrays: element kinds below
   switch (k) {
@@ -136,21 +101,61 @@ bool utf8_ok(const uint8_t* s, size_t n) {
   return true;
 }
 
-template <typename T>
-struct DevBuf {  // growable device scratch
-  T* p = nullptr;
-  size_t cap = 0;
-  cudaError_t ensure(size_t n) {
-    if (n <= cap) return cudaSuccess;
+// growable device scratch; every instance registers itself with its context so that destroy releases all of them
+struct DevBufBase {
+  void* p = nullptr;
+  size_t cap_bytes = 0;
+  cudaError_t ensure_bytes(size_t n) {
+    if (n <= cap_bytes) return cudaSuccess;
     if (p) cudaFree(p);
-    p = nullptr; cap = 0;
+    p = nullptr; cap_bytes = 0;
     size_t want = std::max<size_t>(n + n / 4, 256);
-    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
-    if (e == cudaSuccess) cap = want;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap_bytes = want;
     return e;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  void release() { if (p) cudaFree(p); p = nullptr; cap_bytes = 0; }
 };
+template <typename T>
+struct DevBuf : DevBufBase {
+  explicit DevBuf(std::vector<DevBufBase*>& reg) { reg.push_back(this); }
+  T* ptr() const { return static_cast<T*>(p); }
+  cudaError_t ensure(size_t n) { return ensure_bytes(n * sizeof(T)); }
+};
+
+// ---- NCCL, resolved at run time: the library already loaded into the process (PyTorch bundles its own) is
+// preferred, the system libnccl.so.2 otherwise.  Linking -lnccl would pull a second copy into a torch process.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi& nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return api;
+  api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+  api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+  api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+  api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GetErrorString;
+  return api;
+}
+
+constexpr size_t kScalarWords = 16;
+// device scalar block: 16 words followed by the DevCarry
+//  [0] first_error key  [1..3] insert/update/delete bytes  [4] events  [5] heap_top  [7] long_count  [9] heap_overflow
+//  [10] arr_top  [11] perm_len  [12] n_act (k_act_scan)  [13] abort flag (k_scan)
+constexpr size_t kScalarBlockBytes = kScalarWords * 8 + sizeof(DevCarry);
 
 }  // namespace
 
@@ -163,6 +168,7 @@ struct etl_stager {
   std::vector<uint64_t> relations;
   size_t n_real_anchors = 0;   // anchors.size() before etl_stage_view padded the tail with `len`
   bool padded = false;
+  uint64_t n_frames = 0;
 };
 
 struct etl_dec_batch {
@@ -185,37 +191,44 @@ struct etl_dec_ctx {
   std::string last_error;
   std::map<uint32_t, StoredTable> tables;
   std::map<uint32_t, RelVersion> current;  // SharedTableCache Ready state (table_cache.rs:36-130)
-  // scratch
-  DevBuf<uint8_t> d_stream;
-  DevBuf<uint64_t> d_anchors;
-  DevBuf<uint32_t> d_seg_frames, d_act, d_act_blk;
-  DevBuf<Summ> d_tile_summ, d_group_summ, d_group_prefix, d_total, d_tile_prefix, d_seg_summ;
-  DevBuf<uint32_t> d_schema_by_batch;
-  DevBuf<DevSchema> d_schemas;
-  DevBuf<uint8_t> d_col_kind, d_col_flags;
-  DevBuf<uint32_t> d_line_bad, d_dead, d_bin_count, d_bin_cursor, d_perm, d_bin_start, d_bin_row_base, d_row_chunk;
-  DevBuf<CellDesc> d_desc;
-  DevBuf<CopyPair> d_copies;
-  DevBuf<LongCell> d_long;
-  DevBuf<unsigned long long> d_scalars;  // [0] first_error key, [1..4] metrics
-  DevBuf<uint64_t> d_rel_err_off;
-  DevBuf<uint32_t> d_rel_err_code, d_rel_err_seq;
+  // scratch (all registered in `bufs`)
+  std::vector<DevBufBase*> bufs;
+  DevBuf<uint8_t> d_stream{bufs};
+  DevBuf<uint64_t> d_anchors{bufs};
+  DevBuf<uint32_t> d_seg_frames{bufs}, d_act{bufs}, d_act_blk{bufs};
+  DevBuf<Summ> d_tile_summ{bufs}, d_group_summ{bufs}, d_group_prefix{bufs}, d_total{bufs}, d_tile_prefix{bufs}, d_seg_summ{bufs};
+  DevBuf<uint8_t> d_tables{bufs};          // DevSchema[] | schema_by_batch[] | col_kind[] | col_flags[] | relation errors
+  DevBuf<uint32_t> d_line_bad{bufs}, d_dead{bufs}, d_bin_count{bufs}, d_bin_cursor{bufs}, d_perm{bufs}, d_rec_flen{bufs};
+  DevBuf<LongCell> d_long{bufs};
+  DevBuf<uint8_t> d_scalars{bufs};         // kScalarBlockBytes
+  DevBuf<SeamBlock> d_seam{bufs};          // [0] this rank's block, [1 .. 1+n_ranks) the gathered blocks
+  DevBuf<uint8_t> d_rel_x{bufs};           // relation-update exchange: send slot | n_ranks receive slots
   void* h_result = nullptr; size_t h_result_cap = 0;  // pinned result staging, grow-only
+  uint8_t* h_up = nullptr; size_t h_up_cap = 0;       // pinned staging of the small per-batch uploads
+  uint8_t* h_rel_x = nullptr; size_t h_rel_x_cap = 0; // pinned staging of the relation-update exchange
   uint64_t pending_h2d_bytes = 0;
   Summ* h_total = nullptr;               // pinned
-  unsigned long long* h_scalars = nullptr;  // pinned
+  unsigned long long* h_scalars = nullptr;  // pinned, kScalarWords + DevCarry
   cudaEvent_t ev[6]{};
   cudaEvent_t evk[3]{};
-  cudaStream_t side = nullptr;           // k_utf8_lines runs here, underneath the index / records passes
+  cudaStream_t side = nullptr;           // k_utf8_dead runs here, underneath the tuple pass
   cudaEvent_t ev_in = nullptr, ev_l0 = nullptr, ev_l1 = nullptr;
-  // pending two-phase decode
+  // decode in flight
   bool pending = false;
   DecodeParams P{};
   std::vector<RelVersion> pending_schemas;
+  std::vector<std::pair<uint64_t, RelVersion>> pending_installs;   // (frame offset, version) of this batch's Relation frames: committed by finish
+  std::vector<RelVersion> foreign_installs;                        // versions announced by the other shards (sharded decode)
   uint32_t pending_flags = 0;
-  float pending_h2d_ms = 0, pending_index_ms = 0;
   uint32_t launches = 0;
-  const uint8_t* pending_host_buf = nullptr;
+  bool tables_valid = false;             // d_tables matches `current` and no Relation frame since
+  size_t n_layouts = 1;
+  // what earlier batches needed per staged byte (sizing of the next one)
+  double rec_per_byte = 0, cells_per_byte = 0;
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  int rank = 0, n_ranks = 1;
+  size_t rel_slot = 64 << 10;            // bytes per rank in the relation-update exchange (grows on demand)
 };
 
 #define CK(call)                                                                         \
@@ -226,10 +239,19 @@ struct etl_dec_ctx {
       return ETL_ERR_CUDA;                                                               \
     }                                                                                    \
   } while (0)
+#define CKN(call)                                                                        \
+  do {                                                                                   \
+    ncclResult_t _r = (call);                                                            \
+    if (_r != ncclSuccess) {                                                             \
+      ctx->last_error = std::string(#call) + ": " + nccl_api().GetErrorString(_r);       \
+      return ETL_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
 
 extern "C" {
 
 uint32_t etl_dec_abi_version(void) { return ETL_DECODE_ABI_VERSION; }
+uint32_t etl_dec_kind_for_type_oid(uint32_t type_oid) { return etl_oid_decode_class(type_oid); }
 
 // ------------------------------------------------------------------------------------------------ stager
 int etl_stage_create(uint64_t capacity_bytes, uint32_t anchor_stride, etl_stager** out) {
@@ -237,13 +259,16 @@ int etl_stage_create(uint64_t capacity_bytes, uint32_t anchor_stride, etl_stager
   etl_stager* s = new etl_stager();
   s->stride = anchor_stride;
   s->cap = capacity_bytes;
-  // pinned when a CUDA device is usable, plain memory otherwise (the stager itself needs no GPU)
-  if (cudaHostAlloc((void**)&s->buf, capacity_bytes ? capacity_bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+  // pinned when a CUDA device is usable, plain memory otherwise (the stager itself needs no GPU); 64 bytes of
+  // zero padding follow the staged bytes (the kernels read whole aligned words around a cell)
+  const uint64_t alloc = capacity_bytes + 64;
+  if (cudaHostAlloc((void**)&s->buf, alloc, cudaHostAllocDefault) != cudaSuccess) {
     cudaGetLastError();
-    s->buf = (uint8_t*)malloc(capacity_bytes ? capacity_bytes : 1);
+    s->buf = (uint8_t*)malloc(alloc);
     if (!s->buf) { delete s; return ETL_ERR_ALLOC; }
     s->cap |= (1ull << 63);  // tag: malloc'ed
   }
+  memset(s->buf + capacity_bytes, 0, 64);
   *out = s;
   return ETL_OK;
 }
@@ -252,13 +277,14 @@ void etl_stage_destroy(etl_stager* s) {
   if (s->cap >> 63) free(s->buf); else cudaFreeHost(s->buf);
   delete s;
 }
-void etl_stage_reset(etl_stager* s) { s->len = 0; s->anchors.clear(); s->relations.clear(); s->padded = false; s->n_real_anchors = 0; }
+void etl_stage_reset(etl_stager* s) { s->len = 0; s->anchors.clear(); s->relations.clear(); s->padded = false; s->n_real_anchors = 0; s->n_frames = 0; }
 
 static inline void stage_note_frame(etl_stager* s, uint64_t off, const uint8_t* body, uint32_t body_len) {
   // anchors[k] = first frame starting at or after k*stride
   if (s->padded) { s->anchors.resize(s->n_real_anchors); s->padded = false; }
   while ((uint64_t)s->anchors.size() * s->stride <= off) s->anchors.push_back(off);
   if (body_len >= 26 && body[0] == 'w' && body[25] == 'R') s->relations.push_back(off);
+  s->n_frames++;
 }
 int etl_stage_append(etl_stager* s, const uint8_t* body, uint32_t body_len) {
   uint64_t cap = s->cap & ~(1ull << 63);
@@ -275,18 +301,24 @@ int etl_stage_append(etl_stager* s, const uint8_t* body, uint32_t body_len) {
 int etl_stage_append_framed(etl_stager* s, const uint8_t* framed, uint64_t len) {
   uint64_t cap = s->cap & ~(1ull << 63);
   if (s->len + len > cap) return ETL_ERR_ALLOC;
-  uint64_t base = s->len;
-  memcpy(s->buf + base, framed, len);
+  // validate the whole chain before anything is committed: a broken chain leaves the stager untouched
   uint64_t pos = 0;
   while (pos + 5 <= len) {
     if (framed[pos] != 'd') break;
     uint32_t fl = rd32(framed + pos + 1);
     if (fl < 4 || pos + 1ull + fl > len) break;
+    pos += 1ull + fl;
+  }
+  if (pos != len) return ETL_ERR_INVALID_ARG;
+  uint64_t base = s->len;
+  memcpy(s->buf + base, framed, len);
+  for (pos = 0; pos < len;) {
+    uint32_t fl = rd32(framed + pos + 1);
     stage_note_frame(s, base + pos, framed + pos + 5, fl - 4);
     pos += 1ull + fl;
   }
   s->len += len;
-  return pos == len ? ETL_OK : ETL_ERR_INVALID_ARG;
+  return ETL_OK;
 }
 int etl_stage_view(const etl_stager* cs, etl_dec_input* out) {
   etl_stager* s = const_cast<etl_stager*>(cs);
@@ -307,6 +339,23 @@ int etl_stage_view(const etl_stager* cs, etl_dec_input* out) {
 }
 
 // ------------------------------------------------------------------------------------------------ ctx
+static void ctx_release(etl_dec_ctx* ctx) {
+  for (DevBufBase* b : ctx->bufs) b->release();
+  if (ctx->h_result) cudaFreeHost(ctx->h_result);
+  if (ctx->h_up) cudaFreeHost(ctx->h_up);
+  if (ctx->h_rel_x) cudaFreeHost(ctx->h_rel_x);
+  if (ctx->h_total) cudaFreeHost(ctx->h_total);
+  if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+  for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : ctx->evk) if (e) cudaEventDestroy(e);
+  if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
+  if (ctx->ev_l0) cudaEventDestroy(ctx->ev_l0);
+  if (ctx->ev_l1) cudaEventDestroy(ctx->ev_l1);
+  if (ctx->side) cudaStreamDestroy(ctx->side);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->comm && nccl_api().ok) nccl_api().CommDestroy(ctx->comm);
+  delete ctx;
+}
 int etl_dec_create(int device_id, etl_dec_ctx** out) {
   if (!out) return ETL_ERR_INVALID_ARG;
   int n = 0;
@@ -314,22 +363,20 @@ int etl_dec_create(int device_id, etl_dec_ctx** out) {
   if (device_id < 0 || device_id >= n) return ETL_ERR_INVALID_ARG;
   etl_dec_ctx* ctx = new etl_dec_ctx();
   ctx->device = device_id;
-  if (cudaSetDevice(device_id) != cudaSuccess) { delete ctx; return ETL_ERR_CUDA; }
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ETL_ERR_CUDA; }
-  ctx->own_stream = true;
-  for (auto& e : ctx->ev) cudaEventCreate(&e);
-  for (auto& e : ctx->evk) cudaEventCreate(&e);
-  if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ETL_ERR_CUDA; }
-  {  // batch planes come from the stream-ordered pool: keep freed blocks for the next batch instead of returning them to the OS
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
-      unsigned long long keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-  }
-  cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming); cudaEventCreate(&ctx->ev_l0); cudaEventCreate(&ctx->ev_l1);
-  cudaHostAlloc((void**)&ctx->h_total, sizeof(Summ), cudaHostAllocDefault);
-  cudaHostAlloc((void**)&ctx->h_scalars, 16 * sizeof(unsigned long long), cudaHostAllocDefault);
+  bool ok = cudaSetDevice(device_id) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ctx->own_stream = ok;
+  ok = ok && cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) == cudaSuccess;
+  for (auto& e : ctx->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+  for (auto& e : ctx->evk) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreate(&ctx->ev_l0) == cudaSuccess && cudaEventCreate(&ctx->ev_l1) == cudaSuccess;
+  ok = ok && cudaHostAlloc((void**)&ctx->h_total, sizeof(Summ), cudaHostAllocDefault) == cudaSuccess;
+  ok = ok && cudaHostAlloc((void**)&ctx->h_scalars, kScalarBlockBytes, cudaHostAllocDefault) == cudaSuccess;
+  ok = ok && ctx->d_scalars.ensure(kScalarBlockBytes) == cudaSuccess && ctx->d_total.ensure(1) == cudaSuccess;
+  if (ok) ok = cudaFuncSetAttribute(k_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmemBytes) == cudaSuccess;
+  if (!ok) { cudaGetLastError(); ctx_release(ctx); return ETL_ERR_CUDA; }
+  // batch planes come from the stream-ordered pool: keep freed blocks for the next batch instead of returning them to the OS
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
     uint64_t thr = UINT64_MAX;
@@ -349,23 +396,32 @@ void etl_dec_destroy(etl_dec_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  ctx->d_stream.release(); ctx->d_anchors.release(); ctx->d_seg_frames.release(); ctx->d_tile_summ.release();
-  ctx->d_group_summ.release(); ctx->d_group_prefix.release(); ctx->d_tile_prefix.release(); ctx->d_line_bad.release(); ctx->d_seg_summ.release(); ctx->d_schema_by_batch.release(); ctx->d_total.release(); ctx->d_schemas.release();
-  ctx->d_col_kind.release(); ctx->d_col_flags.release(); ctx->d_scalars.release(); ctx->d_rel_err_off.release();
-  ctx->d_rel_err_code.release(); ctx->d_rel_err_seq.release();
-  if (ctx->h_result) cudaFreeHost(ctx->h_result);
-  if (ctx->h_total) cudaFreeHost(ctx->h_total);
-  if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
-  for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
-  for (auto& e : ctx->evk) if (e) cudaEventDestroy(e);
-  if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
-  if (ctx->ev_l0) cudaEventDestroy(ctx->ev_l0);
-  if (ctx->ev_l1) cudaEventDestroy(ctx->ev_l1);
-  if (ctx->side) cudaStreamDestroy(ctx->side);
-  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
-  delete ctx;
+  cudaStreamSynchronize(ctx->side);
+  ctx_release(ctx);
 }
 const char* etl_dec_last_error(const etl_dec_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null ctx"; }
+
+// ---- communicator over the GPUs of one box (one process per GPU): NCCL inside the library
+int etl_dec_comm_unique_id(uint8_t* out, uint32_t cap) {
+  if (!out || cap < sizeof(ncclUniqueId)) return ETL_ERR_INVALID_ARG;
+  if (!nccl_api().ok) return ETL_ERR_INTERNAL;
+  ncclUniqueId id;
+  if (nccl_api().GetUniqueId(&id) != ncclSuccess) return ETL_ERR_CUDA;
+  memset(out, 0, cap);
+  memcpy(out, &id, sizeof id);
+  return ETL_OK;
+}
+int etl_dec_comm_init(etl_dec_ctx* ctx, const uint8_t* unique_id, uint32_t id_bytes, int rank, int n_ranks) {
+  if (!ctx || !unique_id || id_bytes < sizeof(ncclUniqueId) || n_ranks < 1 || rank < 0 || rank >= n_ranks) return ETL_ERR_INVALID_ARG;
+  if (!nccl_api().ok) { ctx->last_error = "libnccl.so.2 could not be loaded"; return ETL_ERR_INTERNAL; }
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->comm) { nccl_api().CommDestroy(ctx->comm); ctx->comm = nullptr; }
+  ncclUniqueId id;
+  memcpy(&id, unique_id, sizeof id);
+  CKN(nccl_api().CommInitRank(&ctx->comm, n_ranks, id, rank));
+  ctx->rank = rank; ctx->n_ranks = n_ranks;
+  return ETL_OK;
+}
 
 int etl_dec_put_table_schema(etl_dec_ctx* ctx, uint32_t table_id, uint64_t snapshot_id, const etl_column_schema* cols,
                              uint32_t n_cols) {
@@ -385,6 +441,7 @@ int etl_dec_put_table_schema(etl_dec_ctx* ctx, uint32_t table_id, uint64_t snaps
 int etl_dec_reset_relations(etl_dec_ctx* ctx) {
   if (!ctx) return ETL_ERR_INVALID_ARG;
   ctx->current.clear();
+  ctx->tables_valid = false;
   return ETL_OK;
 }
 
@@ -443,7 +500,7 @@ static uint32_t build_relation(etl_dec_ctx* ctx, const uint8_t* frame, uint64_t 
   out->kind.clear(); out->flags.clear(); out->index.clear();
   for (size_t k = 0; k < t.cols.size(); k++) {
     if (!repl[k]) continue;
-    out->kind.push_back((uint8_t)kind_for_oid(t.cols[k].type_oid));
+    out->kind.push_back((uint8_t)etl_oid_decode_class(t.cols[k].type_oid));
     out->flags.push_back((uint8_t)((t.cols[k].nullable ? 1 : 0) | (ident[k] ? 2 : 0)));
     out->index.push_back((int32_t)k);
     if (ident[k]) out->n_ident++;
@@ -464,48 +521,126 @@ void etl_dec_batch_free(etl_dec_batch* b) {
 }
 
 // Where the structure-blind UTF-8 pass (k_utf8_dead, HBM-bound) runs relative to the latency-bound passes.
-// 0: side stream from the start of the index pass; 1: side stream from the start of the tuple passes
-// (the index + record passes keep the memory system to themselves); 2: main stream after the tuple passes.
+// 1: side stream from the start of the tuple pass (default); 2: main stream after the tuple pass.
 // ETL_DEAD_MODE / ETL_DEAD_CTAS are tuning knobs for measurement, not part of the ABI.
 static int dead_mode() {
-  static const int m = getenv("ETL_DEAD_SERIAL") ? 2 : (getenv("ETL_DEAD_MODE") ? atoi(getenv("ETL_DEAD_MODE")) : 1);
+  static const int m = getenv("ETL_DEAD_MODE") ? atoi(getenv("ETL_DEAD_MODE")) : 1;
   return m;
 }
 static int dead_ctas(int dflt) {
   static const int c = getenv("ETL_DEAD_CTAS") ? atoi(getenv("ETL_DEAD_CTAS")) : 0;
   return c > 0 ? c : dflt;
 }
+static int sm_count(etl_dec_ctx* ctx) {
+  static int sms = 0;
+  if (!sms) { sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device); }
+  return sms;
+}
 static cudaError_t launch_dead_side(etl_dec_ctx* ctx, cudaStream_t st) {
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
   cudaError_t e;
   if ((e = cudaEventRecord(ctx->ev_in, st)) != cudaSuccess) return e;
   if ((e = cudaStreamWaitEvent(ctx->side, ctx->ev_in, 0)) != cudaSuccess) return e;
   if ((e = cudaEventRecord(ctx->ev_l0, ctx->side)) != cudaSuccess) return e;
-  k_utf8_dead<<<sms * dead_ctas(3), 256, 0, ctx->side>>>(ctx->P);
+  k_utf8_dead<<<sm_count(ctx) * dead_ctas(3), 256, 0, ctx->side>>>(ctx->P);
   if ((e = cudaEventRecord(ctx->ev_l1, ctx->side)) != cudaSuccess) return e;
   ctx->launches += 1;
   ctx->lines_launched = true;
   return cudaSuccess;
 }
 
-int etl_dec_decode_begin(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t flags, etl_dec_seam* seam_out) {
-  if (!ctx || !in) return ETL_ERR_INVALID_ARG;
+static int ensure_pinned(etl_dec_ctx* ctx, uint8_t** p, size_t* cap, size_t want) {
+  if (*cap >= want) return ETL_OK;
+  if (*p) cudaFreeHost(*p);
+  *p = nullptr; *cap = 0;
+  size_t n = want + want / 2 + 4096;
+  CK(cudaHostAlloc((void**)p, n, cudaHostAllocDefault));
+  *cap = n;
+  return ETL_OK;
+}
+
+// ---- relation-update exchange: a Relation frame in shard r changes the decode state of every
+// shard after it.  Each rank contributes the raw Relation frames of its byte range; every rank builds the
+// versions announced by the ranks before it (they apply from its first byte) and — at the end of the batch —
+// installs all of them, in stream order, as the state the next batch starts from (apply.rs:2079 note_ready,
+// table_cache.rs:36-130).  One all-gather of `rel_slot` bytes per rank; the slot grows when a shard needs more.
+static int exchange_relations(etl_dec_ctx* ctx, const etl_dec_input* in, std::vector<std::vector<uint8_t>>* frames_by_rank) {
+  frames_by_rank->assign(ctx->n_ranks, {});
+  cudaStream_t st = ctx->stream;
+  for (;;) {
+    const size_t slot = ctx->rel_slot;
+    CK(ctx->d_rel_x.ensure(slot * (1 + (size_t)ctx->n_ranks)));
+    if (int rc = ensure_pinned(ctx, &ctx->h_rel_x, &ctx->h_rel_x_cap, slot * (1 + (size_t)ctx->n_ranks))) return rc;
+    // slot: u64 payload bytes needed | u64 frames | frames back to back
+    uint8_t* s = ctx->h_rel_x;
+    uint64_t need = 16, nf = 0;
+    for (uint64_t i = 0; i < in->n_relations; i++) {
+      const uint64_t off = in->relation_offsets[i];
+      if (off + 5 > in->len) continue;
+      const uint64_t fl = 1ull + rd32(in->host_buf + off + 1);
+      if (off + fl > in->len) continue;
+      if (need + fl <= slot) memcpy(s + need, in->host_buf + off, fl);
+      need += fl; nf++;
+    }
+    memcpy(s, &need, 8); memcpy(s + 8, &nf, 8);
+    CK(cudaMemcpyAsync(ctx->d_rel_x.ptr(), s, std::min<uint64_t>(need, slot), cudaMemcpyHostToDevice, st));
+    CKN(nccl_api().AllGather(ctx->d_rel_x.ptr(), ctx->d_rel_x.ptr() + slot, slot, ncclUint8, ctx->comm, st));
+    CK(cudaMemcpyAsync(ctx->h_rel_x + slot, ctx->d_rel_x.ptr() + slot, slot * ctx->n_ranks, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint64_t max_need = 0;
+    for (int r = 0; r < ctx->n_ranks; r++) { uint64_t v; memcpy(&v, ctx->h_rel_x + slot * (1 + r), 8); max_need = std::max(max_need, v); }
+    if (max_need > slot) { ctx->rel_slot = (size_t)(max_need * 2); continue; }   // every rank sees the same sizes: all retry together
+    for (int r = 0; r < ctx->n_ranks; r++) {
+      const uint8_t* q = ctx->h_rel_x + slot * (1 + r);
+      uint64_t v; memcpy(&v, q, 8);
+      (*frames_by_rank)[r].assign(q + 16, q + v);
+    }
+    return ETL_OK;
+  }
+}
+
+// ---------------------------------------------------------------- phase 0: everything known before a kernel runs
+static int prepare(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t flags, bool sharded) {
   ctx->pending = false;
   const uint32_t stride = in->anchor_stride;
   if (stride < 256 || stride > 32768 || (stride & (stride - 1))) { ctx->last_error = "anchor_stride must be a power of two in [256, 32768]"; return ETL_ERR_INVALID_ARG; }
   if (in->len && (!in->host_buf && !in->dev_buf)) { ctx->last_error = "no input buffer"; return ETL_ERR_INVALID_ARG; }
   if (in->dev_buf && (reinterpret_cast<uintptr_t>(in->dev_buf) & 15u)) { ctx->last_error = "dev_buf must be 16-byte aligned"; return ETL_ERR_INVALID_ARG; }
+  if (in->len >= (1ull << 40)) { ctx->last_error = "a staged batch is limited to 1 TiB"; return ETL_ERR_INVALID_ARG; }
   const uint64_t n_anchors_expected = in->len ? (in->len + stride - 1) / stride : 0;
   if (in->n_anchors != n_anchors_expected || (in->n_anchors && !in->anchors && !in->dev_anchors)) { ctx->last_error = "anchors: expected ceil(len/stride) entries"; return ETL_ERR_INVALID_ARG; }
   if (in->n_relations && (!in->relation_offsets || !in->host_buf)) { ctx->last_error = "relation_offsets require host_buf"; return ETL_ERR_INVALID_ARG; }
+  if (sharded && (!ctx->comm || ctx->n_ranks < 2)) { ctx->last_error = "sharded decode needs etl_dec_comm_init with n_ranks >= 2"; return ETL_ERR_INVALID_ARG; }
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   ctx->launches = 0;
+  ctx->pending_flags = flags;
+  ctx->pending_installs.clear();
+  ctx->foreign_installs.clear();
 
-  // ---- schema versions of this batch: carried-in (ascending table id) then Relation frames in order
+  // ---- schema versions of this batch: carried-in (ascending table id), versions announced by earlier shards,
+  // then this range's Relation frames in order
   std::vector<RelVersion> vers;
-  for (auto& kv : ctx->current) { RelVersion v = kv.second; v.effective_off = 0; vers.push_back(std::move(v)); }
+  std::map<uint32_t, RelVersion> base = ctx->current;
+  if (sharded) {
+    std::vector<std::vector<uint8_t>> frames;
+    if (int rc = exchange_relations(ctx, in, &frames)) return rc;
+    for (int r = 0; r < ctx->n_ranks; r++) {
+      if (r == ctx->rank) continue;
+      const std::vector<uint8_t>& fb = frames[r];
+      for (size_t pos = 0; pos + 5 <= fb.size();) {
+        const size_t fl = 1 + (size_t)rd32(fb.data() + pos + 1);
+        RelVersion v; uint32_t seq = 0;
+        if (build_relation(ctx, fb.data() + pos, fb.size() - pos, 0, &v, &seq) == 0) {
+          if (r < ctx->rank) base[v.table_id] = v;               // applies from this shard's first byte
+          ctx->foreign_installs.push_back(std::move(v));         // and is part of the state after the batch
+          if (r > ctx->rank) ctx->foreign_installs.back().effective_off = 1;   // marker: after this shard
+        }
+        pos += fl;
+      }
+    }
+  }
+  const bool reuse_tables = ctx->tables_valid && in->n_relations == 0 && !sharded;
+  for (auto& kv : base) { RelVersion v = kv.second; v.effective_off = 0; vers.push_back(std::move(v)); }
   std::vector<uint64_t> rel_err_off; std::vector<uint32_t> rel_err_code, rel_err_seq;
   for (uint64_t i = 0; i < in->n_relations; i++) {
     uint64_t off = in->relation_offsets[i];
@@ -513,38 +648,23 @@ int etl_dec_decode_begin(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t fla
     RelVersion v; uint32_t seq = 0;
     uint32_t code = build_relation(ctx, in->host_buf + off, in->len - off, off, &v, &seq);
     if (code) { rel_err_off.push_back(off); rel_err_code.push_back(code); rel_err_seq.push_back(seq); continue; }
-    ctx->current[v.table_id] = v;  // note_ready apply.rs:2079
+    ctx->pending_installs.emplace_back(off, v);   // note_ready (apply.rs:2079) happens in finish, for the valid prefix only
     vers.push_back(std::move(v));
   }
   for (const RelVersion& v : vers)
     for (uint8_t k : v.kind)
       if (!kind_supported_on_device(k)) {
         char msg[160];
-        snprintf(msg, sizeof msg, "table %u: column decode class 0x%x (array types) has no device parser yet; refusing to decode", v.table_id, k);
+        snprintf(msg, sizeof msg, "table %u: column decode class 0x%x has no device parser; refusing to decode", v.table_id, k);
         ctx->last_error = msg;
         return ETL_ERR_INVALID_ARG;
       }
-  // device tables sorted by (table_id, effective_off)
-  std::vector<uint32_t> order(vers.size());
-  for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
-  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-    if (vers[a].table_id != vers[b].table_id) return vers[a].table_id < vers[b].table_id;
-    return vers[a].effective_off < vers[b].effective_off;
-  });
-  std::vector<DevSchema> ds; std::vector<uint8_t> ck, cf;
-  for (uint32_t oi : order) {
-    const RelVersion& v = vers[oi];
-    DevSchema d{};
-    d.table_id = v.table_id; d.n_cols = (uint32_t)v.kind.size(); d.n_ident = v.n_ident; d.col_base = (uint32_t)ck.size();
-    d.effective_off = v.effective_off; d.batch_index = oi; d.has_heap = 0;
-    for (uint8_t k : v.kind) if (kind_has_heap(k)) d.has_heap = 1;
-    ck.insert(ck.end(), v.kind.begin(), v.kind.end());
-    cf.insert(cf.end(), v.flags.begin(), v.flags.end());
-    ds.push_back(d);
-  }
 
   // ---- geometry
   DecodeParams& P = ctx->P;
+  const void* keep_tables[6] = {P.schemas, P.schema_by_batch, P.col_kind, P.col_flags, P.rel_error_off, P.rel_error_code};
+  const void* keep_seq = P.rel_error_seq;
+  const uint32_t keep_counts[3] = {P.n_schemas, P.n_batch_schemas, P.n_bins};
   memset(&P, 0, sizeof P);
   P.len = in->len;
   P.n_anchors = (uint32_t)in->n_anchors;
@@ -556,84 +676,449 @@ int etl_dec_decode_begin(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t fla
 
   // ---- uploads
   CK(cudaEventRecord(ctx->ev[0], st));
-  ctx->pending_h2d_bytes = (in->dev_buf ? 0 : in->len) + (in->dev_anchors ? 0 : (in->n_anchors + 1) * 8) +
-                           ds.size() * sizeof(DevSchema) + ck.size() * 2 + rel_err_off.size() * 16 + 5 * 8;
+  ctx->pending_h2d_bytes = (in->dev_buf ? 0 : in->len) + (in->dev_anchors ? 0 : (in->n_anchors + 1) * 8) + kScalarBlockBytes;
   if (in->dev_buf) P.buf = in->dev_buf;
   else {
     CK(ctx->d_stream.ensure(in->len + 64));
-    if (in->len) CK(cudaMemcpyAsync(ctx->d_stream.p, in->host_buf, in->len, cudaMemcpyHostToDevice, st));
-    P.buf = ctx->d_stream.p;
+    if (in->len) CK(cudaMemcpyAsync(ctx->d_stream.ptr(), in->host_buf, in->len, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->d_stream.ptr() + in->len, 0, 64, st));
+    P.buf = ctx->d_stream.ptr();
   }
   if (in->dev_anchors) P.anchors = in->dev_anchors;
   else {
     CK(ctx->d_anchors.ensure(in->n_anchors + 1));
-    if (in->n_anchors) CK(cudaMemcpyAsync(ctx->d_anchors.p, in->anchors, in->n_anchors * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_anchors.p + in->n_anchors, &in->len, 8, cudaMemcpyHostToDevice, st));
-    P.anchors = ctx->d_anchors.p;
+    if (in->n_anchors) CK(cudaMemcpyAsync(ctx->d_anchors.ptr(), in->anchors, in->n_anchors * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_anchors.ptr() + in->n_anchors, &in->len, 8, cudaMemcpyHostToDevice, st));
+    P.anchors = ctx->d_anchors.ptr();
   }
-  CK(ctx->d_schemas.ensure(ds.size() + 1)); CK(ctx->d_col_kind.ensure(ck.size() + 1)); CK(ctx->d_col_flags.ensure(cf.size() + 1));
-  if (!ds.empty()) CK(cudaMemcpyAsync(ctx->d_schemas.p, ds.data(), ds.size() * sizeof(DevSchema), cudaMemcpyHostToDevice, st));
-  if (!ck.empty()) {
-    CK(cudaMemcpyAsync(ctx->d_col_kind.p, ck.data(), ck.size(), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_col_flags.p, cf.data(), cf.size(), cudaMemcpyHostToDevice, st));
-  }
-  P.schemas = ctx->d_schemas.p; P.n_schemas = (uint32_t)ds.size(); P.col_kind = ctx->d_col_kind.p; P.col_flags = ctx->d_col_flags.p;
-  CK(ctx->d_rel_err_off.ensure(rel_err_off.size() + 1)); CK(ctx->d_rel_err_code.ensure(rel_err_off.size() + 1)); CK(ctx->d_rel_err_seq.ensure(rel_err_off.size() + 1));
-  if (!rel_err_off.empty()) {
-    CK(cudaMemcpyAsync(ctx->d_rel_err_off.p, rel_err_off.data(), rel_err_off.size() * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_rel_err_code.p, rel_err_code.data(), rel_err_code.size() * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_rel_err_seq.p, rel_err_seq.data(), rel_err_seq.size() * 4, cudaMemcpyHostToDevice, st));
-  }
-  P.rel_error_off = ctx->d_rel_err_off.p; P.rel_error_code = ctx->d_rel_err_code.p; P.rel_error_seq = ctx->d_rel_err_seq.p;
-  P.n_rel_errors = (uint32_t)rel_err_off.size();
-  CK(ctx->d_seg_frames.ensure(P.n_anchors + 1)); CK(ctx->d_tile_summ.ensure(P.n_tiles + 1));
-  CK(ctx->d_group_summ.ensure(P.n_groups + 1)); CK(ctx->d_group_prefix.ensure(P.n_groups + 1)); CK(ctx->d_total.ensure(1));
-  CK(ctx->d_scalars.ensure(16)); CK(ctx->d_tile_prefix.ensure(P.n_tiles + 1));
-  CK(ctx->d_seg_summ.ensure(P.n_anchors + 1)); P.seg_summ = ctx->d_seg_summ.p;
-  {
+  if (reuse_tables) {
+    P.schemas = (const DevSchema*)keep_tables[0]; P.schema_by_batch = (const uint32_t*)keep_tables[1];
+    P.col_kind = (const uint8_t*)keep_tables[2]; P.col_flags = (const uint8_t*)keep_tables[3];
+    P.rel_error_off = (const uint64_t*)keep_tables[4]; P.rel_error_code = (const uint32_t*)keep_tables[5]; P.rel_error_seq = (const uint32_t*)keep_seq;
+    P.n_schemas = keep_counts[0]; P.n_batch_schemas = keep_counts[1]; P.n_bins = keep_counts[2];
+    P.n_rel_errors = 0;
+  } else {
+    // device tables sorted by (table_id, effective_off); versions with identical columns share a layout (shape bins)
+    std::vector<uint32_t> order(vers.size());
+    for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+      if (vers[a].table_id != vers[b].table_id) return vers[a].table_id < vers[b].table_id;
+      return vers[a].effective_off < vers[b].effective_off;
+    });
+    std::map<std::pair<std::vector<uint8_t>, std::vector<uint8_t>>, uint32_t> layouts;
+    std::vector<DevSchema> ds; std::vector<uint8_t> ck, cf;
+    for (uint32_t oi : order) {
+      const RelVersion& v = vers[oi];
+      DevSchema d{};
+      d.table_id = v.table_id; d.n_cols = (uint32_t)v.kind.size(); d.n_ident = v.n_ident; d.col_base = (uint32_t)ck.size();
+      d.effective_off = v.effective_off; d.batch_index = oi; d.has_heap = 0;
+      for (uint8_t k : v.kind) if (kind_has_heap(k)) d.has_heap = 1;
+      auto key = std::make_pair(v.kind, v.flags);
+      auto it = layouts.find(key);
+      if (it == layouts.end()) it = layouts.emplace(std::move(key), (uint32_t)layouts.size()).first;
+      d.layout = it->second;
+      ck.insert(ck.end(), v.kind.begin(), v.kind.end());
+      cf.insert(cf.end(), v.flags.begin(), v.flags.end());
+      ds.push_back(d);
+    }
+    ctx->n_layouts = std::max<size_t>(1, layouts.size());
     std::vector<uint32_t> sbb(ds.size() + 1, 0);
     for (uint32_t i = 0; i < ds.size(); i++) sbb[ds[i].batch_index] = i;
-    CK(ctx->d_schema_by_batch.ensure(sbb.size()));
-    CK(cudaMemcpyAsync(ctx->d_schema_by_batch.p, sbb.data(), sbb.size() * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));  // sbb is a local
-    P.schema_by_batch = ctx->d_schema_by_batch.p;
+    auto al16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t o_ds = 0, o_sbb = al16(o_ds + (ds.size() + 1) * sizeof(DevSchema)), o_ck = al16(o_sbb + sbb.size() * 4),
+                 o_cf = al16(o_ck + ck.size() + 1), o_eo = al16(o_cf + cf.size() + 1), o_ec = al16(o_eo + (rel_err_off.size() + 1) * 8),
+                 o_es = al16(o_ec + (rel_err_off.size() + 1) * 4), total = al16(o_es + (rel_err_off.size() + 1) * 4);
+    if (int rc = ensure_pinned(ctx, &ctx->h_up, &ctx->h_up_cap, total)) return rc;
+    CK(ctx->d_tables.ensure(total));
+    uint8_t* h = ctx->h_up;
+    if (!ds.empty()) memcpy(h + o_ds, ds.data(), ds.size() * sizeof(DevSchema));
+    memcpy(h + o_sbb, sbb.data(), sbb.size() * 4);
+    if (!ck.empty()) { memcpy(h + o_ck, ck.data(), ck.size()); memcpy(h + o_cf, cf.data(), cf.size()); }
+    if (!rel_err_off.empty()) {
+      memcpy(h + o_eo, rel_err_off.data(), rel_err_off.size() * 8);
+      memcpy(h + o_ec, rel_err_code.data(), rel_err_code.size() * 4);
+      memcpy(h + o_es, rel_err_seq.data(), rel_err_seq.size() * 4);
+    }
+    CK(cudaMemcpyAsync(ctx->d_tables.ptr(), h, total, cudaMemcpyHostToDevice, st));   // h_up is not reused before the final sync
+    ctx->pending_h2d_bytes += total;
+    uint8_t* d = ctx->d_tables.ptr();
+    P.schemas = (const DevSchema*)(d + o_ds); P.schema_by_batch = (const uint32_t*)(d + o_sbb);
+    P.col_kind = d + o_ck; P.col_flags = d + o_cf;
+    P.rel_error_off = (const uint64_t*)(d + o_eo); P.rel_error_code = (const uint32_t*)(d + o_ec); P.rel_error_seq = (const uint32_t*)(d + o_es);
+    P.n_schemas = (uint32_t)ds.size(); P.n_rel_errors = (uint32_t)rel_err_off.size();
+    P.n_batch_schemas = (uint32_t)vers.size();
+    P.n_bins = (uint32_t)std::min<size_t>(kMaxBins, 16 * ctx->n_layouts);
+    ctx->tables_valid = in->n_relations == 0 && !sharded;   // built from `current` alone: valid until a Relation arrives
   }
-  P.tile_prefix = ctx->d_tile_prefix.p;
+  CK(ctx->d_seg_frames.ensure(P.n_anchors + 1)); CK(ctx->d_tile_summ.ensure(P.n_tiles + 1));
+  CK(ctx->d_group_summ.ensure(P.n_groups + 1)); CK(ctx->d_group_prefix.ensure(P.n_groups + 1));
+  CK(ctx->d_tile_prefix.ensure(P.n_tiles + 1)); CK(ctx->d_seg_summ.ensure(P.n_anchors + 1));
+  P.seg_summ = ctx->d_seg_summ.ptr(); P.tile_prefix = ctx->d_tile_prefix.ptr();
   const size_t line_words = (in->len + 4095) / 4096 + 1;
   CK(ctx->d_line_bad.ensure(line_words)); CK(ctx->d_dead.ensure(P.n_anchors + 1));
-  P.line_bad = ctx->d_line_bad.p; P.dead = ctx->d_dead.p;
+  P.line_bad = ctx->d_line_bad.ptr(); P.dead = ctx->d_dead.ptr();
   P.long_cap = P.n_anchors + 16;                      // a listed cell covers at least one whole segment
   CK(ctx->d_long.ensure(P.long_cap));
-  P.long_cells = ctx->d_long.p; P.long_count = (unsigned int*)(ctx->d_scalars.p + 7);
-  CK(cudaMemsetAsync(P.line_bad, 0, line_words * 4, st));
-  P.seg_frames = ctx->d_seg_frames.p; P.tile_summ = ctx->d_tile_summ.p; P.group_summ = ctx->d_group_summ.p;
-  P.group_prefix = ctx->d_group_prefix.p; P.total = ctx->d_total.p;
-  P.first_error = ctx->d_scalars.p; P.metrics = ctx->d_scalars.p + 1;
+  unsigned long long* sc = reinterpret_cast<unsigned long long*>(ctx->d_scalars.ptr());
+  P.long_cells = ctx->d_long.ptr(); P.long_count = (unsigned int*)(sc + 7);
+  P.seg_frames = ctx->d_seg_frames.ptr(); P.tile_summ = ctx->d_tile_summ.ptr(); P.group_summ = ctx->d_group_summ.ptr();
+  P.group_prefix = ctx->d_group_prefix.ptr(); P.total = ctx->d_total.ptr();
+  P.first_error = sc; P.metrics = sc + 1;
+  P.heap_top = sc + 5; P.heap_overflow = (unsigned int*)(sc + 9); P.arr_top = sc + 10;
+  P.perm_len = (unsigned int*)(sc + 11); P.n_act = (unsigned int*)(sc + 12); P.abort_flag = (unsigned int*)(sc + 13);
+  P.dc = reinterpret_cast<const DevCarry*>(sc + kScalarWords); P.dc_out = reinterpret_cast<DevCarry*>(sc + kScalarWords);
   const uint32_t act_blocks = (P.n_anchors + kActThreads - 1) / kActThreads;
   CK(ctx->d_act.ensure(P.n_anchors + 1)); CK(ctx->d_act_blk.ensure(act_blocks + 1));
-  P.act = ctx->d_act.p; P.act_blk = ctx->d_act_blk.p; P.n_act = (unsigned int*)(ctx->d_scalars.p + 12);   // [12] survives decode_finish's reset of [0..10]
-  CK(cudaEventRecord(ctx->ev[1], st));
-
+  P.act = ctx->d_act.ptr(); P.act_blk = ctx->d_act_blk.ptr();
+  CK(ctx->d_bin_count.ensure(kMaxBins)); CK(ctx->d_bin_cursor.ensure(kMaxBins));
+  P.bin_count = ctx->d_bin_count.ptr(); P.bin_cursor = ctx->d_bin_cursor.ptr();
+  P.rank = (uint32_t)ctx->rank; P.n_ranks = sharded ? (uint32_t)ctx->n_ranks : 1u;
+  if (sharded) {
+    CK(ctx->d_seam.ensure(1 + (size_t)ctx->n_ranks));
+    P.seam_send = ctx->d_seam.ptr(); P.seam_all = ctx->d_seam.ptr() + 1;
+  }
+  CK(cudaMemsetAsync(P.line_bad, 0, line_words * 4, st));
+  ctx->pending_schemas = std::move(vers);
   ctx->lines_launched = false;
+  return ETL_OK;
+}
 
-  // ---- pass A + B
+// scalars [lo, hi) ← initial values (+ the carry block when `with_carry`)
+static int upload_scalars(etl_dec_ctx* ctx, size_t lo, size_t hi, const DevCarry* carry) {
+  unsigned long long* h = ctx->h_scalars;
+  for (size_t i = lo; i < hi; i++) h[i] = 0;
+  if (lo == 0) h[0] = ~0ull;
+  size_t bytes = (hi - lo) * 8;
+  if (carry) { memcpy(h + kScalarWords, carry, sizeof *carry); bytes = (kScalarWords - lo) * 8 + sizeof *carry; }
+  CK(cudaMemcpyAsync(ctx->d_scalars.ptr() + lo * 8, h + lo, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return ETL_OK;
+}
+
+// ---------------------------------------------------------------- pass A + B
+static int launch_index(etl_dec_ctx* ctx) {
+  DecodeParams& P = ctx->P;
+  cudaStream_t st = ctx->stream;
+  CK(cudaEventRecord(ctx->ev[1], st));
   if (P.n_groups) {
+    const uint32_t act_blocks = (P.n_anchors + kActThreads - 1) / kActThreads;
     k_act_count<<<act_blocks, kActThreads, 0, st>>>(P);
     k_act_scan<<<1, kActThreads, 0, st>>>(P, act_blocks);
     k_act_scatter<<<act_blocks, kActThreads, 0, st>>>(P);
-    if (dead_mode() == 0) CK(launch_dead_side(ctx, st));   // underneath everything that follows
     k_index<<<P.n_groups, P.tiles_per_group * P.segs_per_tile, 0, st>>>(P);
     k_scan<<<1, 512, 0, st>>>(P);
     k_tile_prefix<<<(P.n_tiles + 255) / 256, 256, 0, st>>>(P);
     ctx->launches += 6;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(ctx->h_total, P.total, sizeof(Summ), cudaMemcpyDeviceToHost, st));
-  } else *ctx->h_total = summ_identity();
+  } else {
+    CK(cudaMemsetAsync(P.total, 0, sizeof(Summ), st));
+    if (P.seam_send) CK(cudaMemsetAsync(P.seam_send, 0, sizeof(SeamBlock), st));
+  }
   CK(cudaEventRecord(ctx->ev[2], st));
-  CK(cudaStreamSynchronize(st));
-  cudaEventElapsedTime(&ctx->pending_h2d_ms, ctx->ev[0], ctx->ev[1]);
-  cudaEventElapsedTime(&ctx->pending_index_ms, ctx->ev[1], ctx->ev[2]);
+  return ETL_OK;
+}
 
+struct PlaneLayout { uint64_t rec_off, kind, flags, rel, schema, start, commit, ord, cbase, tb, hint, tag, val, aux, heap, total; };
+static PlaneLayout plane_layout(uint64_t nr, uint64_t nc, uint64_t nh) {
+  PlaneLayout L;
+  uint64_t cur = 0;
+  auto take = [&](uint64_t bytes) { uint64_t o = cur; cur += (bytes + 255) & ~255ull; return o; };
+  L.rec_off = take(nr * 8); L.kind = take(nr); L.flags = take(nr); L.rel = take(nr * 4); L.schema = take(nr * 4);
+  L.start = take(nr * 8); L.commit = take(nr * 8); L.ord = take(nr * 8); L.cbase = take((nr + 1) * 8);
+  L.tb = take(nr * 4); L.hint = take(nr * 4);
+  L.tag = take(nc); L.val = take(nc * 8); L.aux = take(nc * 4); L.heap = take(nh);
+  L.total = cur ? cur : 256;
+  return L;
+}
+static void fill_planes(etl_dec_planes& pl, uint8_t* bs, const PlaneLayout& L, uint64_t nr, uint64_t nc, uint64_t nh) {
+  pl.n_records = nr; pl.n_cells = nc; pl.heap_bytes = nh;
+  pl.rec_off = (uint64_t*)(bs + L.rec_off); pl.rec_kind = bs + L.kind; pl.rec_flags = bs + L.flags;
+  pl.rec_rel = (uint32_t*)(bs + L.rel); pl.rec_schema = (int32_t*)(bs + L.schema); pl.rec_start_lsn = (uint64_t*)(bs + L.start);
+  pl.rec_commit_lsn = (uint64_t*)(bs + L.commit); pl.rec_tx_ordinal = (uint64_t*)(bs + L.ord); pl.rec_cell_base = (uint64_t*)(bs + L.cbase);
+  pl.rec_tuple_bytes = (uint32_t*)(bs + L.tb); pl.rec_heap_hint = (uint32_t*)(bs + L.hint);
+  pl.cell_tag = bs + L.tag; pl.cell_val = (uint64_t*)(bs + L.val); pl.cell_aux = (uint32_t*)(bs + L.aux); pl.heap = bs + L.heap;
+}
+
+// ---------------------------------------------------------------- pass C into planes of capacity (cap_r, cap_c)
+static int launch_emit(etl_dec_ctx* ctx, etl_dec_batch* b, uint64_t cap_r, uint64_t cap_c, uint64_t array_heap, PlaneLayout* Lout, uint64_t* scalar_heap_out) {
+  DecodeParams& P = ctx->P;
+  cudaStream_t st = ctx->stream;
+  bool any_heap = false, any_array = false;
+  for (const RelVersion& v : b->schemas) for (uint8_t k : v.kind) { any_heap = any_heap || kind_has_heap(k); any_array = any_array || (k & ETL_K_ARRAY); }
+  // upper bound on Σ cell_heap_bound: numeric ≤ n/2+19, bytea ≤ n/2+7, uuid = 16 per decoded text cell.
+  // Arrays reserve 16 + 44·n_elems + 1.5·len per cell: first guess 3·len, retried ×4 on overflow (≤ 48·len).
+  uint64_t nh = any_heap ? (P.len / 2 + 24 * cap_c + 256) : 0;
+  nh = (nh + 15) & ~15ull;
+  *scalar_heap_out = nh;
+  if (any_array) nh += array_heap ? array_heap : 3 * P.len + 4096;
+  const PlaneLayout L = plane_layout(cap_r, cap_c, nh);
+  *Lout = L;
+  b->block_bytes = L.total;
+  CK(cudaMallocAsync(&b->dev_block, b->block_bytes, st));
+  fill_planes(b->dev, (uint8_t*)b->dev_block, L, cap_r, cap_c, nh);
+  P.rec_off = (uint64_t*)b->dev.rec_off; P.rec_kind = (uint8_t*)b->dev.rec_kind; P.rec_flags = (uint8_t*)b->dev.rec_flags;
+  P.rec_rel = (uint32_t*)b->dev.rec_rel; P.rec_schema = (int32_t*)b->dev.rec_schema; P.rec_start_lsn = (uint64_t*)b->dev.rec_start_lsn;
+  P.rec_commit_lsn = (uint64_t*)b->dev.rec_commit_lsn; P.rec_tx_ordinal = (uint64_t*)b->dev.rec_tx_ordinal;
+  P.rec_cell_base = (uint64_t*)b->dev.rec_cell_base; P.rec_tuple_bytes = (uint32_t*)b->dev.rec_tuple_bytes; P.rec_heap_hint = (uint32_t*)b->dev.rec_heap_hint;
+  P.cell_tag = (uint8_t*)b->dev.cell_tag; P.cell_val = (uint64_t*)b->dev.cell_val;
+  P.cell_aux = (uint32_t*)b->dev.cell_aux; P.heap = (uint8_t*)b->dev.heap;
+  P.heap_cap = nh; P.arr_base = *scalar_heap_out;
+  P.cap_records = cap_r; P.cap_cells = cap_c;
+  const size_t perm_cap = cap_r + 32ull * P.n_bins + 256;
+  CK(ctx->d_perm.ensure(perm_cap)); CK(ctx->d_rec_flen.ensure(cap_r + 1));
+  P.perm = ctx->d_perm.ptr(); P.rec_flen = ctx->d_rec_flen.ptr();
+  return ETL_OK;
+}
+static int launch_emit_kernels(etl_dec_ctx* ctx) {
+  DecodeParams& P = ctx->P;
+  cudaStream_t st = ctx->stream;
+  const uint64_t cap_r = P.cap_records;
+  const size_t perm_cap = cap_r + 32ull * P.n_bins + 256;
+  CK(cudaEventRecord(ctx->ev[3], st));
+  CK(cudaMemsetAsync(P.bin_count, 0, P.n_bins * 4, st));
+  CK(cudaMemsetAsync(P.perm, 0xFF, perm_cap * 4, st));
+  if (P.n_tiles) {
+    k_frames<<<(P.n_anchors + 255) / 256, 256, 0, st>>>(P);
+    cudaEventRecord(ctx->evk[0], st);
+    if (dead_mode() == 1 && !ctx->lines_launched) CK(launch_dead_side(ctx, st));   // underneath the tuple pass
+    if (cap_r) {
+      k_bin_scan<<<1, 1024, 0, st>>>(P);
+      k_perm<<<(uint32_t)((cap_r + 255) / 256), 256, 0, st>>>(P);
+      cudaEventRecord(ctx->evk[2], st);
+      const uint32_t chunks = (uint32_t)((perm_cap + kRowsThreads - 1) / kRowsThreads);
+      k_rows<<<((chunks + 63u) / 64u) * 64u, kRowsThreads, kRowsSmemBytes, st>>>(P);
+      ctx->launches += 3;
+    } else cudaEventRecord(ctx->evk[2], st);
+    cudaEventRecord(ctx->evk[1], st);
+    if (ctx->lines_launched) CK(cudaStreamWaitEvent(st, ctx->ev_l1, 0));   // join: the bitmap is complete
+    else {                                            // ETL_DEAD_MODE=2: the same pass on the main stream (tuning knob)
+      cudaEventRecord(ctx->ev_l0, st);
+      k_utf8_dead<<<sm_count(ctx) * dead_ctas(6), 256, 0, st>>>(P);
+      cudaEventRecord(ctx->ev_l1, st);
+      ctx->launches += 1;
+    }
+    if (cap_r) { k_long_verdict<<<592, 256, 0, st>>>(P); ctx->launches += 1; }
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+  } else { cudaEventRecord(ctx->evk[0], st); cudaEventRecord(ctx->evk[2], st); cudaEventRecord(ctx->evk[1], st); cudaEventRecord(ctx->ev_l0, st); cudaEventRecord(ctx->ev_l1, st); }
+  CK(cudaEventRecord(ctx->ev[4], st));
+  CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars.ptr(), kScalarWords * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ctx->h_total, P.total, sizeof(Summ), cudaMemcpyDeviceToHost, st));
+  return ETL_OK;
+}
+
+static Summ carry_of(const etl_stream_state* cin) {
+  Summ carry = summ_identity();
+  if (cin) {
+    if (cin->in_tx) { carry.flags = S_HAS_B; carry.lsn = cin->final_lsn; }
+    carry.ord = cin->next_tx_ordinal;
+  }
+  return carry;
+}
+
+// one decode, common to every entry point.  mode 0: one-shot (optimistic sizing); 1: after decode_begin (totals known)
+static int run_decode(etl_dec_ctx* ctx, const etl_stream_state* carry_in, uint64_t record_index_base, bool sharded, bool totals_known,
+                      etl_dec_batch** out) {
+  cudaStream_t st = ctx->stream;
+  DecodeParams& P = ctx->P;
+  etl_dec_batch* b = new etl_dec_batch();
+  b->ctx = ctx;
+  b->schemas = ctx->pending_schemas;
+  auto fail = [&](int rc) { if (b->dev_block) cudaFreeAsync(b->dev_block, st); delete b; return rc; };
+#define CKB(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->last_error = std::string(#call) + ": " + cudaGetErrorString(_e); return fail(ETL_ERR_CUDA); } } while (0)
+  const Summ host_carry = carry_of(carry_in);
+  P.host_carry = host_carry;
+  DevCarry dc; dc.carry = host_carry; dc.record_index_base = record_index_base;
+
+  uint64_t cap_r, cap_c;
+  bool exact = totals_known;
+  if (!totals_known) {
+    if (int rc = upload_scalars(ctx, 0, kScalarWords, &dc)) return fail(rc);
+    // optimistic sizes from what earlier batches needed per byte; the first batch has no history: exact path
+    if (ctx->rec_per_byte > 0) {
+      cap_r = (uint64_t)(P.len * ctx->rec_per_byte * 1.08) + 4096;
+      cap_c = (uint64_t)(P.len * ctx->cells_per_byte * 1.08) + 16384;
+    } else { cap_r = cap_c = 0; exact = true; }
+    P.cap_records = exact ? ~0ull : cap_r; P.cap_cells = exact ? ~0ull : cap_c;   // k_scan decides with these
+    P.rec_cell_base = nullptr;
+  } else {
+    if (int rc = upload_scalars(ctx, 0, 12, nullptr)) return fail(rc);           // [12] n_act survives from decode_begin
+    ctx->h_scalars[13] = 0;
+    CKB(cudaMemcpyAsync(ctx->d_scalars.ptr() + 13 * 8, ctx->h_scalars + 13, 8, cudaMemcpyHostToDevice, st));
+    memcpy(ctx->h_scalars + kScalarWords, &dc, sizeof dc);
+    CKB(cudaMemcpyAsync(ctx->d_scalars.ptr() + kScalarWords * 8, ctx->h_scalars + kScalarWords, sizeof dc, cudaMemcpyHostToDevice, st));
+  }
+  PlaneLayout L{};
+  uint64_t scalar_heap = 0, array_heap = 0, heap_used = 0;
+  if (!totals_known && !exact) {
+    // planes first (k_scan writes the tail of rec_cell_base), then the whole pipeline without a host round trip
+    if (int rc = launch_emit(ctx, b, cap_r, cap_c, 0, &L, &scalar_heap)) return fail(rc);
+    if (int rc = launch_index(ctx)) return fail(rc);
+  } else if (!totals_known) {
+    if (int rc = launch_index(ctx)) return fail(rc);
+    CKB(cudaMemcpyAsync(ctx->h_total, P.total, sizeof(Summ), cudaMemcpyDeviceToHost, st));
+    CKB(cudaStreamSynchronize(st));
+  }
+  if (sharded) {
+    if (nccl_api().AllGather(P.seam_send, (void*)P.seam_all, sizeof(SeamBlock), ncclUint8, ctx->comm, st) != ncclSuccess) { ctx->last_error = "ncclAllGather(seam) failed"; return fail(ETL_ERR_CUDA); }
+    k_seam_fold<<<1, 32, 0, st>>>(P);
+    ctx->launches += 2;
+  }
+  for (int attempt = 0;; attempt++) {
+    if (exact) {
+      const Summ T = *ctx->h_total;
+      if (b->dev_block) { CKB(cudaFreeAsync(b->dev_block, st)); b->dev_block = nullptr; }
+      if (int rc = launch_emit(ctx, b, T.n_rec, T.n_cells, array_heap, &L, &scalar_heap)) return fail(rc);
+      CKB(cudaMemcpyAsync((void*)(b->dev.rec_cell_base + T.n_rec), &ctx->h_total->n_cells, 8, cudaMemcpyHostToDevice, st));
+      if (attempt > 0 || totals_known) {              // a re-run of pass C: fresh scalars, the carry block stays
+        if (int rc = upload_scalars(ctx, 0, 12, nullptr)) return fail(rc);
+        ctx->h_scalars[13] = 0;
+        CKB(cudaMemcpyAsync(ctx->d_scalars.ptr() + 13 * 8, ctx->h_scalars + 13, 8, cudaMemcpyHostToDevice, st));
+      }
+    }
+    if (int rc = launch_emit_kernels(ctx)) return fail(rc);
+    CKB(cudaStreamSynchronize(st));
+    const Summ T = *ctx->h_total;
+    if (ctx->h_scalars[13]) {                         // did not fit the optimistic planes: exact sizes, pass C again
+      exact = true;
+      ctx->lines_launched = false;
+      CKB(cudaMemsetAsync(P.line_bad, 0, ((P.len + 4095) / 4096 + 1) * 4, st));
+      continue;
+    }
+    heap_used = P.heap_cap;
+    if (P.heap_cap) heap_used = std::min<uint64_t>(P.heap_cap, ctx->h_scalars[10] ? scalar_heap + ctx->h_scalars[10] : ctx->h_scalars[5]);
+    if (ctx->h_scalars[9]) {                          // an array reservation did not fit: larger array region, pass C again
+      if (attempt >= 4) { ctx->last_error = "array heap reservation overflow after retries"; return fail(ETL_ERR_CUDA); }
+      array_heap = (P.heap_cap - scalar_heap) * 4;
+      exact = true;
+      ctx->lines_launched = false;
+      CKB(cudaMemsetAsync(P.line_bad, 0, ((P.len + 4095) / 4096 + 1) * 4, st));
+      continue;
+    }
+    // the planes describe exactly the batch
+    b->dev.n_records = T.n_rec; b->dev.n_cells = T.n_cells; b->dev.heap_bytes = heap_used;
+    break;
+  }
+  const Summ T = *ctx->h_total;
+  if (P.len) { ctx->rec_per_byte = std::max(ctx->rec_per_byte * 0.97, (double)T.n_rec / P.len); ctx->cells_per_byte = std::max(ctx->cells_per_byte * 0.97, (double)T.n_cells / P.len); }
+
+  uint64_t d2h_bytes = kScalarWords * 8 + sizeof(Summ);
+  if (ctx->pending_flags & ETL_DECODE_RESULTS_TO_HOST) {
+    // compact host image: planes laid out for the exact counts; one copy per plane, one synchronisation
+    const uint64_t nr = T.n_rec, nc = T.n_cells;
+    const PlaneLayout H = plane_layout(nr, nc, heap_used);
+    if (ctx->h_result_cap < H.total) {
+      if (ctx->h_result) cudaFreeHost(ctx->h_result);
+      ctx->h_result = nullptr; ctx->h_result_cap = 0;
+      size_t want = H.total + H.total / 8;
+      CKB(cudaHostAlloc(&ctx->h_result, want, cudaHostAllocDefault));
+      ctx->h_result_cap = want;
+    }
+    b->host_block = ctx->h_result;
+    uint8_t* hb = (uint8_t*)b->host_block;
+    const uint8_t* db = (const uint8_t*)b->dev_block;
+    CKB(cudaEventRecord(ctx->ev[4], st));
+    if (L.rec_off == H.rec_off && L.heap + heap_used <= H.total && L.tag == H.tag && L.heap == H.heap) {
+      CKB(cudaMemcpyAsync(hb, db, H.heap + heap_used, cudaMemcpyDeviceToHost, st));
+      d2h_bytes += H.heap + heap_used;
+    } else {
+      auto cp = [&](uint64_t ho, uint64_t dof, uint64_t bytes) { if (bytes) cudaMemcpyAsync(hb + ho, db + dof, bytes, cudaMemcpyDeviceToHost, st); d2h_bytes += bytes; };
+      cp(H.rec_off, L.rec_off, nr * 8); cp(H.kind, L.kind, nr); cp(H.flags, L.flags, nr); cp(H.rel, L.rel, nr * 4); cp(H.schema, L.schema, nr * 4);
+      cp(H.start, L.start, nr * 8); cp(H.commit, L.commit, nr * 8); cp(H.ord, L.ord, nr * 8); cp(H.cbase, L.cbase, (nr + 1) * 8);
+      cp(H.tb, L.tb, nr * 4); cp(H.hint, L.hint, nr * 4); cp(H.tag, L.tag, nc); cp(H.val, L.val, nc * 8); cp(H.aux, L.aux, nc * 4); cp(H.heap, L.heap, heap_used);
+      CKB(cudaGetLastError());
+    }
+    fill_planes(b->host, hb, H, nr, nc, heap_used);
+    b->has_host = true;
+    CKB(cudaEventRecord(ctx->ev[5], st));
+    CKB(cudaStreamSynchronize(st));
+  } else { CKB(cudaEventRecord(ctx->ev[5], st)); CKB(cudaEventSynchronize(ctx->ev[5])); }
+
+  // ---- summary
+  etl_dec_summary& S = b->summary;
+  memset(&S, 0, sizeof S);
+  float h2d_ms = 0, index_ms = 0, emit_ms = 0, d2h_ms = 0;
+  cudaEventElapsedTime(&h2d_ms, ctx->ev[0], ctx->ev[1]);
+  cudaEventElapsedTime(&index_ms, ctx->ev[1], ctx->ev[2]);
+  cudaEventElapsedTime(&emit_ms, ctx->ev[3], ctx->ev[4]);
+  cudaEventElapsedTime(&d2h_ms, ctx->ev[4], ctx->ev[5]);
+  if (ctx->pending_flags & ETL_DECODE_RESULTS_TO_HOST) { float whole = 0; cudaEventElapsedTime(&whole, ctx->ev[3], ctx->ev[5]); emit_ms = whole - d2h_ms; }
+  S.kernel_ms = index_ms + emit_ms;
+  S.index_ms = index_ms; S.emit_ms = emit_ms;
+  if (P.n_tiles) {
+    cudaEventElapsedTime(&S.frames_ms, ctx->ev[3], ctx->evk[0]);
+    cudaEventElapsedTime(&S.walk_ms, ctx->evk[0], ctx->evk[2]);    // k_bin_scan + k_perm
+    cudaEventElapsedTime(&S.cells_ms, ctx->evk[2], ctx->evk[1]);   // k_rows
+    cudaEventElapsedTime(&S.spans_ms, ctx->ev_l0, ctx->ev_l1);     // k_utf8_dead, concurrent with k_rows
+  }
+  S.h2d_ms = h2d_ms; S.d2h_ms = d2h_ms;
+  S.h2d_bytes = ctx->pending_h2d_bytes;
+  // bytes k_utf8_dead streamed: the dead segments (h_scalars[12] = live segment count, left by k_act_scan)
+  S.span_bytes = P.n_tiles ? std::min<uint64_t>(P.len, (uint64_t)(P.n_anchors - (uint32_t)ctx->h_scalars[12]) * P.anchor_stride) : 0;
+  S.d2h_bytes = d2h_bytes;
+  S.gpu_launches = ctx->launches;
+  S.n_schemas = (uint32_t)b->schemas.size();
+  unsigned long long key = ctx->h_scalars[0];
+  uint64_t err_off = ~0ull;
+  if (key == ~0ull) { S.first_error.record_index = UINT64_MAX; }
+  else {
+    S.first_error.record_index = key >> 24;  // global index
+    S.first_error.seq = (uint32_t)((key >> 6) & 0x3FFFFu);
+    S.first_error.code = (uint32_t)(key & 63u);
+    S.first_error.kind = error_kind_of(S.first_error.code);
+  }
+  S.insert_bytes = ctx->h_scalars[1]; S.update_bytes = ctx->h_scalars[2]; S.delete_bytes = ctx->h_scalars[3]; S.n_events = ctx->h_scalars[4];
+  // carry-out: this shard's end state (sharded: relative to the folded carry, read back only when asked for below)
+  Summ endst = fold(host_carry, T);
+  if (sharded) {                                       // the stream state after the LAST shard = fold over all seams
+    std::vector<SeamBlock> all(ctx->n_ranks);
+    CKB(cudaMemcpy(all.data(), P.seam_all, sizeof(SeamBlock) * ctx->n_ranks, cudaMemcpyDeviceToHost));
+    endst = host_carry;
+    uint64_t base = 0;
+    for (int r = 0; r < ctx->n_ranks; r++) { if (r < ctx->rank) base += all[r].total.n_rec; endst = fold(endst, all[r].total); }
+    S.record_index_base = base;
+  } else S.record_index_base = record_index_base;
+  S.carry_out.in_tx = ((endst.flags & S_HAS_B) && !(endst.flags & S_CLOSED)) ? 1 : 0;
+  S.carry_out.final_lsn = endst.lsn;
+  S.carry_out.next_tx_ordinal = endst.ord;
+  S.abi_version = ETL_DECODE_ABI_VERSION;
+
+  // ---- note_ready (apply.rs:2079): the Relation frames of the valid prefix become the state of the next batch.
+  // After a data error the reference has bailed out before caching anything that follows it.
+  if (key != ~0ull) {
+    const uint64_t local = S.first_error.record_index - S.record_index_base;
+    if (local < T.n_rec) CKB(cudaMemcpy(&err_off, b->dev.rec_off + local, 8, cudaMemcpyDeviceToHost));
+  }
+  bool changed = false;
+  for (const RelVersion& v : ctx->foreign_installs) if (v.effective_off == 0) { ctx->current[v.table_id] = v; ctx->current[v.table_id].effective_off = 0; changed = true; }
+  for (auto& pr : ctx->pending_installs) if (pr.first < err_off) { ctx->current[pr.second.table_id] = pr.second; changed = true; }
+  if (key == ~0ull) for (const RelVersion& v : ctx->foreign_installs) if (v.effective_off == 1) { ctx->current[v.table_id] = v; ctx->current[v.table_id].effective_off = 0; changed = true; }
+  if (changed) ctx->tables_valid = false;
+  ctx->pending_installs.clear(); ctx->foreign_installs.clear();
+  *out = b;
+  return ETL_OK;
+#undef CKB
+}
+
+int etl_dec_decode(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t flags, etl_dec_batch** out) {
+  if (!ctx || !in || !out) return ETL_ERR_INVALID_ARG;
+  if (int rc = prepare(ctx, in, flags, false)) return rc;
+  return run_decode(ctx, &in->carry_in, 0, false, false, out);
+}
+int etl_dec_decode_sharded(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t flags, etl_dec_batch** out) {
+  if (!ctx || !in || !out) return ETL_ERR_INVALID_ARG;
+  if (int rc = prepare(ctx, in, flags, true)) return rc;
+  return run_decode(ctx, &in->carry_in, 0, true, false, out);
+}
+
+int etl_dec_decode_begin(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t flags, etl_dec_seam* seam_out) {
+  if (!ctx || !in) return ETL_ERR_INVALID_ARG;
+  if (int rc = prepare(ctx, in, flags, false)) return rc;
+  DecodeParams& P = ctx->P;
+  P.cap_records = ~0ull; P.cap_cells = ~0ull; P.rec_cell_base = nullptr;
+  if (int rc = upload_scalars(ctx, 0, kScalarWords, nullptr)) return rc;
+  if (int rc = launch_index(ctx)) return rc;
+  CK(cudaMemcpyAsync(ctx->h_total, P.total, sizeof(Summ), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   const Summ& T = *ctx->h_total;
   if (seam_out) {
     memset(seam_out, 0, sizeof *seam_out);
@@ -642,9 +1127,6 @@ int etl_dec_decode_begin(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t fla
     seam_out->has_begin = (T.flags & S_HAS_B) ? 1 : 0; seam_out->closed = (T.flags & S_CLOSED) ? 1 : 0;
   }
   ctx->pending = true;
-  ctx->pending_schemas = std::move(vers);
-  ctx->pending_flags = flags;
-  ctx->pending_host_buf = in->host_buf;
   return ETL_OK;
 }
 
@@ -653,185 +1135,7 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
   if (!ctx || !out || !ctx->pending) { if (ctx) ctx->last_error = "decode_finish without decode_begin"; return ETL_ERR_INVALID_ARG; }
   ctx->pending = false;
   CK(cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
-  DecodeParams& P = ctx->P;
-  const Summ T = *ctx->h_total;
-  etl_dec_batch* b = new etl_dec_batch();
-  b->ctx = ctx;
-  b->schemas = std::move(ctx->pending_schemas);
-
-  // ---- one device block for all planes
-  bool any_heap = false, any_array = false;
-  for (const RelVersion& v : b->schemas) for (uint8_t k : v.kind) { any_heap = any_heap || kind_has_heap(k); any_array = any_array || (k & ETL_K_ARRAY); }
-  // upper bound on Σ cell_heap_bound: numeric ≤ n/2+19, bytea ≤ n/2+7, uuid = 16 per decoded text cell.
-  // Arrays reserve 16 + 44·n_elems + 1.5·len per cell: first guess 3·len, retried ×4 on overflow (≤ 48·len).
-  const uint64_t nr = T.n_rec, nc = T.n_cells;
-  uint64_t nh = any_heap ? (P.len / 2 + 24 * T.n_cells + 256) : 0;
-  nh = (nh + 15) & ~15ull;
-  const uint64_t scalar_heap = nh;
-  if (any_array) nh += 3 * P.len + 4096;
-  auto al = [](uint64_t x) { return (x + 255) & ~255ull; };
-  uint64_t f_rec_off, f_kind, f_flags, f_rel, f_schema, f_start, f_commit, f_ord, f_cbase, f_tag, f_val, f_aux, f_heap;
-  auto fill = [&](etl_dec_planes& pl, uint8_t* bs) {
-    pl.n_records = nr; pl.n_cells = nc; pl.heap_bytes = nh;
-    pl.rec_off = (uint64_t*)(bs + f_rec_off); pl.rec_kind = bs + f_kind; pl.rec_flags = bs + f_flags;
-    pl.rec_rel = (uint32_t*)(bs + f_rel); pl.rec_schema = (int32_t*)(bs + f_schema); pl.rec_start_lsn = (uint64_t*)(bs + f_start);
-    pl.rec_commit_lsn = (uint64_t*)(bs + f_commit); pl.rec_tx_ordinal = (uint64_t*)(bs + f_ord); pl.rec_cell_base = (uint64_t*)(bs + f_cbase);
-    pl.cell_tag = bs + f_tag; pl.cell_val = (uint64_t*)(bs + f_val); pl.cell_aux = (uint32_t*)(bs + f_aux); pl.heap = bs + f_heap;
-  };
-  P.record_index_base = record_index_base;
-  Summ carry = summ_identity();
-  etl_stream_state cin{};
-  if (carry_in) cin = *carry_in;
-  if (cin.in_tx) { carry.flags = S_HAS_B; carry.lsn = cin.final_lsn; }
-  carry.ord = cin.next_tx_ordinal;
-  P.carry = carry;
-  uint64_t heap_used = 0;
-  for (int attempt = 0;; attempt++) {
-    uint64_t cur = 0;
-    auto take = [&](uint64_t bytes) { uint64_t o = cur; cur += al(bytes); return o; };
-    f_rec_off = take(nr * 8); f_kind = take(nr); f_flags = take(nr); f_rel = take(nr * 4); f_schema = take(nr * 4);
-    f_start = take(nr * 8); f_commit = take(nr * 8); f_ord = take(nr * 8); f_cbase = take((nr + 1) * 8);
-    f_tag = take(nc); f_val = take(nc * 8); f_aux = take(nc * 4); f_heap = take(nh);
-    b->block_bytes = cur ? cur : 256;
-    CK(cudaMallocAsync(&b->dev_block, b->block_bytes, st));
-    fill(b->dev, (uint8_t*)b->dev_block);
-    P.rec_off = (uint64_t*)b->dev.rec_off; P.rec_kind = (uint8_t*)b->dev.rec_kind; P.rec_flags = (uint8_t*)b->dev.rec_flags;
-    P.rec_rel = (uint32_t*)b->dev.rec_rel; P.rec_schema = (int32_t*)b->dev.rec_schema; P.rec_start_lsn = (uint64_t*)b->dev.rec_start_lsn;
-    P.rec_commit_lsn = (uint64_t*)b->dev.rec_commit_lsn; P.rec_tx_ordinal = (uint64_t*)b->dev.rec_tx_ordinal;
-    P.rec_cell_base = (uint64_t*)b->dev.rec_cell_base; P.cell_tag = (uint8_t*)b->dev.cell_tag; P.cell_val = (uint64_t*)b->dev.cell_val;
-    P.cell_aux = (uint32_t*)b->dev.cell_aux; P.heap = (uint8_t*)b->dev.heap;
-    P.heap_top = ctx->d_scalars.p + 5; P.heap_cap = nh;
-    P.heap_overflow = (unsigned int*)(ctx->d_scalars.p + 9);
-    P.arr_top = ctx->d_scalars.p + 10; P.arr_base = scalar_heap;
-
-    // ---- pass C
-    ctx->h_scalars[0] = ~0ull;
-    for (int i = 1; i < 12; i++) ctx->h_scalars[i] = 0;
-    CK(cudaMemcpyAsync(ctx->d_scalars.p, ctx->h_scalars, 12 * 8, cudaMemcpyHostToDevice, st));
-    P.n_bins = (uint32_t)std::min<size_t>(kMaxBins, std::max<size_t>(16, 16 * b->schemas.size()));
-    const size_t perm_cap = nr + 32ull * P.n_bins + 256;
-    CK(ctx->d_bin_count.ensure(kMaxBins)); CK(ctx->d_bin_cursor.ensure(kMaxBins)); CK(ctx->d_perm.ensure(perm_cap));
-    P.bin_count = ctx->d_bin_count.p; P.bin_cursor = ctx->d_bin_cursor.p; P.perm = ctx->d_perm.p;
-    P.perm_len = (unsigned int*)(ctx->d_scalars.p + 11);
-    CK(ctx->d_bin_start.ensure(kMaxBins)); CK(ctx->d_bin_row_base.ensure(kMaxBins));
-    P.bin_start = ctx->d_bin_start.p; P.bin_row_base = ctx->d_bin_row_base.p; P.n_batch_schemas = (uint32_t)b->schemas.size();
-    // descriptor rows: Σ over bins ceil(count/32)·slots(bin) ≤ slots/32 + Σ slots(bin) ≤ slots/32 + 32·Σ n_cols
-    uint64_t sum_cols = 0, max_cols = 0;
-    for (const RelVersion& v : b->schemas) { sum_cols += v.kind.size(); max_cols = std::max<uint64_t>(max_cols, v.kind.size()); }
-    uint64_t rows_cap = T.slots / 32 + 32 * sum_cols + 64;
-    if (16 * b->schemas.size() > (size_t)kMaxBins) rows_cap = ((uint64_t)nr * 2 * max_cols) / 32 + 64ull * kMaxBins / 16 * max_cols + 64;   // clamped bins take the widest schema
-    if (rows_cap >= (1ull << 31)) { ctx->last_error = "batch too large for the descriptor plane"; delete b; return ETL_ERR_INVALID_ARG; }
-    P.desc_row_cap = (uint32_t)rows_cap;
-    CK(ctx->d_desc.ensure(rows_cap * 32)); CK(ctx->d_row_chunk.ensure(rows_cap));
-    P.desc = ctx->d_desc.p; P.row_chunk = ctx->d_row_chunk.p; P.desc_rows = (unsigned int*)(ctx->d_scalars.p + 13);
-    P.copy_cap = (uint32_t)std::min<uint64_t>(nc / 2 + 16, 0xFFFFFFFFull);
-    CK(ctx->d_copies.ensure(P.copy_cap));
-    P.copies = ctx->d_copies.p; P.copy_count = (unsigned int*)(ctx->d_scalars.p + 8);
-    CK(cudaMemsetAsync(P.bin_count, 0, P.n_bins * 4, st));
-    CK(cudaMemsetAsync(P.perm, 0xFF, perm_cap * 4, st));
-    CK(cudaEventRecord(ctx->ev[3], st));
-    if (P.n_tiles) {
-      P.n_records = nr;
-      k_frames<<<(P.n_anchors + 255) / 256, 256, 0, st>>>(P);
-      cudaEventRecord(ctx->evk[0], st);
-      if (dead_mode() == 1 && !ctx->lines_launched) CK(launch_dead_side(ctx, st));   // underneath the tuple passes only
-      if (nr) {
-        k_bin_scan<<<1, 1024, 0, st>>>(P);
-        k_perm<<<(uint32_t)((nr + 255) / 256), 256, 0, st>>>(P);
-        k_walk<<<(uint32_t)((nr + 32ull * P.n_bins + kWalkThreads - 1) / kWalkThreads) + 64u, kWalkThreads, 0, st>>>(P);
-        cudaEventRecord(ctx->evk[2], st);
-        k_cells<<<(uint32_t)((rows_cap * 32 + 255) / 256), 256, 0, st>>>(P);
-        k_copy<<<128, 256, 0, st>>>(P);
-      } else cudaEventRecord(ctx->evk[2], st);
-      cudaEventRecord(ctx->evk[1], st);
-      if (ctx->lines_launched) CK(cudaStreamWaitEvent(st, ctx->ev_l1, 0));   // join: the bitmap is complete
-      else {                                          // ETL_DEAD_SERIAL: the same pass on the main stream (tuning knob)
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-        cudaEventRecord(ctx->ev_l0, st);
-        k_utf8_dead<<<sms * dead_ctas(6), 256, 0, st>>>(P);
-        cudaEventRecord(ctx->ev_l1, st);
-        ctx->launches += 1;
-      }
-      if (nr) k_long_verdict<<<592, 256, 0, st>>>(P);
-      ctx->launches += nr ? 7 : 1;
-      CK(cudaGetLastError());
-    }
-    CK(cudaMemcpyAsync((void*)(b->dev.rec_cell_base + nr), &ctx->h_total->n_cells, 8, cudaMemcpyHostToDevice, st));
-    CK(cudaEventRecord(ctx->ev[4], st));
-    CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars.p, 13 * 8, cudaMemcpyDeviceToHost, st));
-    heap_used = nh;
-    if (!nh) break;
-    CK(cudaStreamSynchronize(st));
-    heap_used = std::min<uint64_t>(nh, ctx->h_scalars[10] ? scalar_heap + ctx->h_scalars[10] : ctx->h_scalars[5]);
-    if (!ctx->h_scalars[9]) break;
-    if (attempt >= 3) { ctx->last_error = "array heap reservation overflow after retries"; cudaFreeAsync(b->dev_block, st); delete b; return ETL_ERR_CUDA; }
-    CK(cudaFreeAsync(b->dev_block, st));
-    b->dev_block = nullptr;
-    nh = scalar_heap + (nh - scalar_heap) * 4;
-  }
-  const uint64_t copy_bytes = f_heap + heap_used;
-  b->dev.heap_bytes = heap_used;
-  if (ctx->pending_flags & ETL_DECODE_RESULTS_TO_HOST) {
-    if (ctx->h_result_cap < b->block_bytes) {
-      if (ctx->h_result) cudaFreeHost(ctx->h_result);
-      ctx->h_result = nullptr; ctx->h_result_cap = 0;
-      size_t want = b->block_bytes + b->block_bytes / 8;
-      CK(cudaHostAlloc(&ctx->h_result, want, cudaHostAllocDefault));
-      ctx->h_result_cap = want;
-    }
-    b->host_block = ctx->h_result;
-    CK(cudaMemcpyAsync(b->host_block, b->dev_block, copy_bytes, cudaMemcpyDeviceToHost, st));
-    fill(b->host, (uint8_t*)b->host_block);
-    b->host.heap_bytes = heap_used;
-    b->has_host = true;
-  }
-  CK(cudaEventRecord(ctx->ev[5], st));
-  CK(cudaStreamSynchronize(st));
-
-  // ---- summary
-  etl_dec_summary& S = b->summary;
-  memset(&S, 0, sizeof S);
-  float emit_ms = 0, d2h_ms = 0;
-  cudaEventElapsedTime(&emit_ms, ctx->ev[3], ctx->ev[4]);
-  cudaEventElapsedTime(&d2h_ms, ctx->ev[4], ctx->ev[5]);
-  S.kernel_ms = ctx->pending_index_ms + emit_ms;
-  S.index_ms = ctx->pending_index_ms; S.emit_ms = emit_ms;
-  if (P.n_tiles) {
-    cudaEventElapsedTime(&S.frames_ms, ctx->ev[3], ctx->evk[0]);
-    cudaEventElapsedTime(&S.walk_ms, ctx->evk[0], ctx->evk[2]);    // k_bin_scan + k_perm + k_walk (structure)
-    cudaEventElapsedTime(&S.cells_ms, ctx->evk[2], ctx->evk[1]);   // k_cells + k_copy
-    cudaEventElapsedTime(&S.spans_ms, ctx->ev_l0, ctx->ev_l1);   // concurrent with index / records
-  }
-  S.h2d_ms = ctx->pending_h2d_ms; S.d2h_ms = d2h_ms;
-  S.h2d_bytes = ctx->pending_h2d_bytes;
-  // bytes k_utf8_dead streamed: the dead segments (h_scalars[12] = live segment count, left by k_act_scan)
-  S.span_bytes = P.n_tiles ? std::min<uint64_t>(P.len, (uint64_t)(P.n_anchors - (uint32_t)ctx->h_scalars[12]) * P.anchor_stride) : 0;
-  S.d2h_bytes = 5 * 8 + sizeof(Summ) + ((ctx->pending_flags & ETL_DECODE_RESULTS_TO_HOST) ? copy_bytes : 0);
-  S.gpu_launches = ctx->launches;
-  S.n_schemas = (uint32_t)b->schemas.size();
-  unsigned long long key = ctx->h_scalars[0];
-  if (key == ~0ull) { S.first_error.record_index = UINT64_MAX; }
-  else {
-    S.first_error.record_index = (key >> 24) - 0;  // global index
-    S.first_error.seq = (uint32_t)((key >> 6) & 0x3FFFFu);
-    S.first_error.code = (uint32_t)(key & 63u);
-    S.first_error.kind = error_kind_of(S.first_error.code);
-  }
-  S.insert_bytes = ctx->h_scalars[1]; S.update_bytes = ctx->h_scalars[2]; S.delete_bytes = ctx->h_scalars[3]; S.n_events = ctx->h_scalars[4];
-  Summ endst = fold(carry, T);
-  S.carry_out.in_tx = ((endst.flags & S_HAS_B) && !(endst.flags & S_CLOSED)) ? 1 : 0;
-  S.carry_out.final_lsn = endst.lsn;
-  S.carry_out.next_tx_ordinal = endst.ord;
-  *out = b;
-  return ETL_OK;
-}
-
-int etl_dec_decode(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t flags, etl_dec_batch** out) {
-  int rc = etl_dec_decode_begin(ctx, in, flags, nullptr);
-  if (rc) return rc;
-  return etl_dec_decode_finish(ctx, &in->carry_in, 0, out);
+  return run_decode(ctx, carry_in, record_index_base, false, true, out);
 }
 
 int etl_dec_batch_planes(const etl_dec_batch* b, int host, etl_dec_planes* out) {
@@ -851,6 +1155,15 @@ int etl_dec_batch_schema(const etl_dec_batch* b, uint32_t i, etl_dec_schema_info
   out->table_id = v.table_id; out->n_cols = (uint32_t)v.kind.size(); out->n_identity = v.n_ident; out->_pad = 0;
   out->snapshot_id = v.snapshot_id; out->effective_off = v.effective_off;
   out->col_kind = v.kind.data(); out->col_flags = v.flags.data(); out->col_index = v.index.data();
+  return ETL_OK;
+}
+int etl_dec_mem_info(etl_dec_ctx* ctx, uint64_t* free_bytes, uint64_t* total_bytes) {
+  if (!ctx) return ETL_ERR_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  size_t f = 0, t = 0;
+  CK(cudaMemGetInfo(&f, &t));
+  if (free_bytes) *free_bytes = f;
+  if (total_bytes) *total_bytes = t;
   return ETL_OK;
 }
 

@@ -4,7 +4,7 @@
 //                       not (`dead`): TOAST-heavy streams leave most segments empty.
 //   k_index   (pass A)  one thread per live segment walks the 'd'+len32 frame chain from global memory (only
 //                       frame heads are touched), classifies frames and reduces a per-tile summary
-//                       {records, cells, descriptor slots, stream-state transformer}.
+//                       {records, cells, stream-state transformer}.
 //   k_scan, k_tile_prefix (pass B)  exclusive scans of the summaries (the state transformer is associative,
 //                       so commit_lsn / tx_ordinal become a scan).
 //   k_utf8_dead (side stream)  structure-blind UTF-8 pass over the dead segments (the inside of TOAST-sized
@@ -15,11 +15,9 @@
 //                       loop's per-message state machine, serial inside 2 KiB, parallel across; counts the
 //                       frame shapes.
 //   k_bin_scan, k_perm  counting sort of the DML records by frame shape (schema version, op, old-image kind).
-//   k_walk    (pass C2a) one thread per DML record in shape order: hops the TupleData cell headers and writes
-//                       one 16-byte descriptor per wire cell, row-major by (warp chunk, slot).
-//   k_cells   (pass C2b) one warp per descriptor row = 32 cells of one column: UTF-8, per-kind parser, cell
-//                       plane + heap.
-//   k_copy    (pass C2c) unchanged-TOAST cells of updates take the old image's decoded cell.
+//   k_rows    (pass C2, rows_kernel.cuh) one thread per DML record in shape order, one warp per 32 records of
+//                       one shape: frames staged into shared memory by bulk async copies, tuples walked in
+//                       lockstep, one parser per column for the whole warp; cell plane + heap.
 //   k_long_verdict      after both streams join: the interior verdict of every long text cell that k_cells
 //                       listed, read from the line bitmap.
 //
@@ -34,18 +32,9 @@
 
 namespace etl {
 
-#ifndef ETL_WALK_THREADS
-#define ETL_WALK_THREADS 128
-#endif
-constexpr int kWalkThreads = ETL_WALK_THREADS;
 constexpr int kIndexThreads = 256;
 constexpr int kMaxBins = 4096;         // 16 frame shapes x 256 schema versions (more versions share the last bins)
 
-// One wire cell of a DML tuple, as k_walk hands it to k_cells.  Rows of 32 descriptors = one slot (wire cell
-// index) of the 32 records a k_walk warp steps through, so a k_cells warp gets 32 cells of the same column.
-struct CellDesc { uint64_t a, b; };   // a = stream offset (40) | len[0:24) << 40;  b = dest cell (40) | kind << 40 | len[24:32) << 48
-struct CopyPair { uint64_t dest, src; };   // unchanged TOAST resolved from the old image: cell[dest] = cell[src] after k_cells
-constexpr uint32_t DK_EMPTY = 0xFFu;
 struct LongCell { uint32_t rec_local, seq; uint64_t l0, l1; };   // lines [l0, l1) of the stream are interior to the cell
 
 // ---- stream-state transformer (apply.rs:600-626, 1927-2006) + counters; associative under fold()
@@ -53,18 +42,16 @@ struct Summ {
   uint64_t lsn;      // final_lsn of the last Begin (valid if HAS_B)
   uint64_t ord;      // HAS_B: next ordinal after the span; else number of ordinal consumers in the span
   uint64_t n_cells;
-  uint64_t slots;    // descriptor slots k_walk will fill (wire cells of the DML tuples, by frame shape)
   uint32_t n_rec;
   uint32_t flags;    // 1 HAS_B, 2 CLOSED (a Commit follows the last Begin / any Commit if no Begin)
 };
 constexpr uint32_t S_HAS_B = 1, S_CLOSED = 2;
 
-__host__ __device__ __forceinline__ Summ summ_identity() { return Summ{0, 0, 0, 0, 0, 0}; }
+__host__ __device__ __forceinline__ Summ summ_identity() { return Summ{0, 0, 0, 0, 0}; }
 __host__ __device__ __forceinline__ Summ fold(const Summ& a, const Summ& b) {
   Summ r;
   r.n_rec = a.n_rec + b.n_rec;
   r.n_cells = a.n_cells + b.n_cells;
-  r.slots = a.slots + b.slots;
   if (b.flags & S_HAS_B) { r.flags = b.flags; r.lsn = b.lsn; r.ord = b.ord; }
   else {
     r.flags = (a.flags & S_HAS_B) | ((b.flags & S_CLOSED) ? S_CLOSED : (a.flags & S_CLOSED));
@@ -82,7 +69,18 @@ struct DevSchema {
   uint64_t effective_off; // stream offset from which this version applies
   uint32_t batch_index;   // index reported in rec_schema
   uint32_t has_heap;      // any numeric / bytea / uuid / array column
+  uint32_t layout;        // versions with identical (kind, flags) columns share a layout: the shape bins are keyed by it
+  uint32_t _pad;
 };
+
+// carry-in of the shard, resident on the device (single GPU: uploaded with the batch scalars; multi-GPU: written
+// by k_seam_fold from the all-gathered seam summaries — no host round trip between the index and record passes)
+struct DevCarry {
+  Summ carry;                  // stream state at the shard's first record
+  uint64_t record_index_base;  // global index of the shard's first record
+};
+// what one rank contributes to the seam all-gather (64 bytes)
+struct SeamBlock { Summ total; uint64_t _pad[4]; };
 
 
 struct DecodeParams {
@@ -109,20 +107,25 @@ struct DecodeParams {
   Summ* tile_prefix;         // exclusive prefix per tile (pass B2), carry not included
   // global grouping of the DML records by frame shape (k_frames counts, k_bin_scan lays out, k_perm fills)
   uint32_t* bin_count; uint32_t* bin_cursor; uint32_t n_bins; uint32_t* perm; unsigned int* perm_len;
-  uint32_t* bin_start; uint32_t* bin_row_base; uint32_t n_batch_schemas;
-  CellDesc* desc; uint32_t* row_chunk; unsigned int* desc_rows; uint32_t desc_row_cap;   // descriptor rows (32 cells each)
-  CopyPair* copies; unsigned int* copy_count; uint32_t copy_cap;
+  uint32_t n_batch_schemas;
+  uint32_t* rec_flen;               // CopyData length + 1 of every record's frame (k_frames → k_rows: sizes the staged window)
+  unsigned int* abort_flag;         // set by k_scan when the batch does not fit the planes the host reserved
+  uint64_t cap_records, cap_cells;  // capacity of the record / cell planes
   uint32_t* line_bad;               // k_utf8_dead: bit l set = line l (128 bytes) holds a UTF-8 rule violation (zeroed per batch)
   uint32_t* dead;                   // segments without a frame start (ascending); n_dead = n_anchors - *n_act
   struct LongCell* long_cells; unsigned int* long_count; uint32_t long_cap;   // text cells spanning whole dead segments
-  // carry-in (known when pass C runs)
-  Summ carry;
-  uint64_t record_index_base;  // global index of this shard's first record (multi-GPU)
-  uint64_t n_records;          // records of this shard (known after pass B)
+  // carry-in (device resident; valid when pass C runs)
+  const DevCarry* dc;
+  SeamBlock* seam_send;        // this rank's block (k_scan writes it); NULL on a single GPU
+  const SeamBlock* seam_all;   // n_ranks blocks after the all-gather
+  DevCarry* dc_out;            // = dc, writable (k_seam_fold)
+  uint32_t rank, n_ranks;
+  Summ host_carry;             // carry-in of the whole (unsharded) stream
   const uint32_t* schema_by_batch;  // batch schema index → position in `schemas`
   // outputs
   uint64_t* rec_off; uint8_t* rec_kind; uint8_t* rec_flags; uint32_t* rec_rel; int32_t* rec_schema;
   uint64_t* rec_start_lsn; uint64_t* rec_commit_lsn; uint64_t* rec_tx_ordinal; uint64_t* rec_cell_base;
+  uint32_t* rec_tuple_bytes; uint32_t* rec_heap_hint;
   uint8_t* cell_tag; uint64_t* cell_val; uint32_t* cell_aux;
   uint8_t* heap;
   uint32_t* act;                    // compacted list of the segments that contain a frame start (ascending)
@@ -227,15 +230,6 @@ __device__ __forceinline__ uint32_t frame_out_cells(const FrameHead& h, const De
     default: return 0;
   }
 }
-// wire-cell slots reserved for a DML frame: by shape only (a full-width key tuple has n_cols entries)
-__device__ __forceinline__ uint32_t shape_slots(uint32_t shape /*op << 2 | old flags*/, uint32_t n_cols) {
-  return ((shape >> 2) == 1u && (shape & 3u)) ? 2u * n_cols : n_cols;   // only an update with an old image has two tuples
-}
-__device__ __forceinline__ uint32_t frame_slots(const FrameHead& h, const DevSchema* s) {
-  if (!s || (h.kind != 'I' && h.kind != 'U' && h.kind != 'D')) return 0;
-  const uint32_t oldf = h.old_tag == 'O' ? 1u : (h.old_tag == 'K' ? 2u : 0u);
-  return shape_slots((h.kind == 'I' ? 0u : (h.kind == 'U' ? 4u : 8u)) | oldf, s->n_cols);
-}
 __device__ __forceinline__ Summ frame_state_elem(const FrameHead& h, const uint8_t* p) {
   Summ e = summ_identity();
   e.n_rec = 1;
@@ -319,7 +313,8 @@ __device__ __forceinline__ const uint8_t* cstr_end(const uint8_t* q, const uint8
 // unchanged in the compacted index space.
 constexpr int kActThreads = 1024;
 __device__ __forceinline__ bool seg_live(const DecodeParams& P, uint32_t seg) {
-  return seg < P.n_anchors && P.anchors[seg] < P.anchors[seg + 1];
+  // anchors are caller data: clamp to the stream, a non-ascending pair is an empty segment
+  return seg < P.n_anchors && P.anchors[seg] < min(P.anchors[seg + 1], P.len);
 }
 __global__ void __launch_bounds__(kActThreads) k_act_count(DecodeParams P) {
   const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
@@ -381,7 +376,7 @@ __global__ void __launch_bounds__(kIndexThreads) k_index(DecodeParams P) {
   if (j < G.n_act) {
     const uint32_t seg = P.act[j];
     uint64_t pos = P.anchors[seg];
-    const uint64_t stop = P.anchors[seg + 1];
+    const uint64_t stop = min(P.anchors[seg + 1], P.len);
     while (pos < stop) {
       const uint8_t* p = P.buf + pos;
       FrameHead h = read_head(p, P.len - pos);
@@ -390,7 +385,6 @@ __global__ void __launch_bounds__(kIndexThreads) k_index(DecodeParams P) {
         const DevSchema* s = nullptr;
         if (h.kind == 'I' || h.kind == 'U' || h.kind == 'D') s = find_schema(P, h.rel, pos);
         e.n_cells = frame_out_cells(h, s);
-        e.slots = frame_slots(h, s);
       }
       acc = fold(acc, e);
       nframes++;
@@ -456,7 +450,27 @@ __global__ void __launch_bounds__(512) k_scan(DecodeParams P) {
     P.group_prefix[i] = run;
     run = fold(run, P.group_summ[i]);
   }
-  if (threadIdx.x == blockDim.x - 1) P.total[0] = sh[blockDim.x - 1];
+  if (threadIdx.x == blockDim.x - 1) {
+    const Summ T = sh[blockDim.x - 1];
+    P.total[0] = T;
+    // the host sized the planes from the previous batches: when this one does not fit, every later kernel returns
+    // at once and the host re-runs pass C with exact sizes (P.total stays valid)
+    const bool fits = (uint64_t)T.n_rec <= P.cap_records && T.n_cells <= P.cap_cells;
+    *P.abort_flag = fits ? 0u : 1u;
+    if (fits) P.rec_cell_base[T.n_rec] = T.n_cells;
+    if (P.seam_send) { SeamBlock b; b.total = T; b._pad[0] = b._pad[1] = b._pad[2] = b._pad[3] = 0; *P.seam_send = b; }
+  }
+}
+
+// multi-GPU: fold the seam summaries of the ranks before this one into the carry-in and the record-index base
+// (apply.rs:600-626: the state transformer is associative, so a shard's effect on the stream state is its Summ)
+__global__ void k_seam_fold(DecodeParams P) {
+  if (threadIdx.x || blockIdx.x) return;
+  Summ c = P.host_carry;
+  uint64_t base = 0;
+  for (uint32_t r = 0; r < P.rank; r++) { c = fold(c, P.seam_all[r].total); base += P.seam_all[r].total.n_rec; }
+  DevCarry d; d.carry = c; d.record_index_base = base;
+  *P.dc_out = d;
 }
 
 // ================================================================================================
@@ -605,71 +619,62 @@ __device__ __forceinline__ bool lines_any_bad(const uint32_t* bm, uint64_t l0, u
   return false;
 }
 __global__ void __launch_bounds__(256) k_long_verdict(DecodeParams P) {
+  if (*P.abort_flag) return;
   const uint32_t n = min(*P.long_count, P.long_cap);
   for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
     const LongCell c = P.long_cells[e];
-    if (lines_any_bad(P.line_bad, c.l0, c.l1)) report_error(P, P.record_index_base + c.rec_local, c.seq, ETL_E_UTF8);
+    if (lines_any_bad(P.line_bad, c.l0, c.l1)) report_error(P, P.dc->record_index_base + c.rec_local, c.seq, ETL_E_UTF8);
   }
 }
-// out of line: k_walk's registers are the scarce resource
+// out of line: cold (an oversize cell just below the warp-cooperative threshold)
 __device__ __noinline__ bool utf8_medium_bad(const uint8_t* cell, uint32_t len) { return utf8_range_bad(cell, len, 0, len, 0, 1); }
 
 
 // ================================================================================================
-// Shape bins.  A warp of k_walk is fastest when its 32 records have the same frame shape (table
-// version, operation, old-image kind): wire cell i is then the same column for every lane and one parser
-// runs for all of them.  Output positions are fixed by the scan, so records can be walked in any order:
-// k_frames histograms the shapes, k_bin_scan lays the bins out (each padded to a whole warp), k_perm
-// writes the record indices bin by bin, and k_walk thread t walks record perm[t].
-__device__ __forceinline__ uint32_t walk_bin(const DecodeParams& P, int32_t schema, uint32_t kind, uint32_t rflags) {
-  const uint32_t b = ((uint32_t)schema << 4) | (kind == 'I' ? 0u : (kind == 'U' ? 4u : 8u)) | (rflags & 3u);
+// Shape bins.  A warp of k_rows is fastest when its 32 records have the same frame shape (column layout,
+// operation, old-image kind): wire cell i is then the same column for every lane and one parser runs for
+// all of them.  Output positions are fixed by the scan, so records can be walked in any order: k_frames
+// histograms the shapes, k_bin_scan lays the bins out (each padded to a whole warp), k_perm writes the
+// record indices bin by bin, and k_rows thread t walks record perm[t].  Schema versions with identical
+// columns share a layout (a table whose Relation is re-sent keeps its bins); a batch with more layouts
+// than bins shares the last 16 bins, whose warps then hold mixed shapes (k_rows handles that per lane).
+__device__ __forceinline__ uint32_t walk_bin(const DecodeParams& P, uint32_t layout, uint32_t kind, uint32_t rflags) {
+  const uint32_t b = (layout << 4) | (kind == 'I' ? 0u : (kind == 'U' ? 4u : 8u)) | (rflags & 3u);
   return b < P.n_bins ? b : P.n_bins - 16u + (b & 15u);
 }
-// wire-cell slots per record of a bin (clamped bins hold several schema versions: take the widest)
-__device__ __forceinline__ uint32_t bin_slots(const DecodeParams& P, uint32_t bin) {
-  const uint32_t si = bin >> 4;
-  uint32_t n_cols = 0;
-  if (si < P.n_batch_schemas) n_cols = P.schemas[P.schema_by_batch[si]].n_cols;
-  if (bin + 16u >= P.n_bins) for (uint32_t j = si + 1; j < P.n_batch_schemas; j++) n_cols = max(n_cols, P.schemas[P.schema_by_batch[j]].n_cols);
-  return shape_slots(bin & 15u, n_cols);
-}
 __global__ void __launch_bounds__(1024) k_bin_scan(DecodeParams P) {
-  __shared__ uint32_t sh[1024], shr[1024];
+  __shared__ uint32_t sh[1024];
+  if (*P.abort_flag) return;
   const uint32_t per = (P.n_bins + 1023u) / 1024u;
   const uint32_t lo = threadIdx.x * per, hi = min(lo + per, P.n_bins);
-  uint32_t acc = 0, accr = 0;
-  for (uint32_t i = lo; i < hi; i++) {
-    const uint32_t pc = (P.bin_count[i] + 31u) & ~31u;
-    acc += pc;
-    if (pc) accr += (pc >> 5) * bin_slots(P, i);
-  }
-  sh[threadIdx.x] = acc; shr[threadIdx.x] = accr;
+  uint32_t acc = 0;
+  for (uint32_t i = lo; i < hi; i++) acc += (P.bin_count[i] + 31u) & ~31u;
+  sh[threadIdx.x] = acc;
   __syncthreads();
   for (uint32_t d = 1; d < 1024; d <<= 1) {
-    uint32_t v = sh[threadIdx.x], vr = shr[threadIdx.x];
-    if (threadIdx.x >= d) { v += sh[threadIdx.x - d]; vr += shr[threadIdx.x - d]; }
+    uint32_t v = sh[threadIdx.x];
+    if (threadIdx.x >= d) v += sh[threadIdx.x - d];
     __syncthreads();
-    sh[threadIdx.x] = v; shr[threadIdx.x] = vr;
+    sh[threadIdx.x] = v;
     __syncthreads();
   }
-  uint32_t run = threadIdx.x ? sh[threadIdx.x - 1] : 0u, runr = threadIdx.x ? shr[threadIdx.x - 1] : 0u;
+  uint32_t run = threadIdx.x ? sh[threadIdx.x - 1] : 0u;
   for (uint32_t i = lo; i < hi; i++) {
-    const uint32_t pc = (P.bin_count[i] + 31u) & ~31u;
-    P.bin_cursor[i] = run; P.bin_start[i] = run; P.bin_row_base[i] = runr;
-    run += pc;
-    if (pc) runr += (pc >> 5) * bin_slots(P, i);
+    P.bin_cursor[i] = run;
+    run += (P.bin_count[i] + 31u) & ~31u;
   }
-  if (threadIdx.x == 1023) { *P.perm_len = sh[1023]; *P.desc_rows = shr[1023]; }
+  if (threadIdx.x == 1023) *P.perm_len = sh[1023];
 }
 __global__ void __launch_bounds__(256) k_perm(DecodeParams P) {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   bool dml = false;
   uint32_t bin = 0;
-  if (r < P.n_records) {
+  if (*P.abort_flag) return;
+  if (r < P.total[0].n_rec) {
     const uint32_t kind = P.rec_kind[r];
     const int32_t sc = P.rec_schema[r];
-    if ((kind == 'I' || kind == 'U' || kind == 'D') && sc >= 0) { dml = true; bin = walk_bin(P, sc, kind, P.rec_flags[r]); }
+    if ((kind == 'I' || kind == 'U' || kind == 'D') && sc >= 0) { dml = true; bin = walk_bin(P, P.schemas[P.schema_by_batch[sc]].layout, kind, P.rec_flags[r]); }
   }
   const unsigned vm = __ballot_sync(0xffffffffu, dml);
   if (dml) {                                          // one atomic per bin per warp
@@ -688,7 +693,7 @@ __global__ void __launch_bounds__(256) k_perm(DecodeParams P) {
 // for ~2 KiB of stream per thread.
 __global__ void __launch_bounds__(256) k_frames(DecodeParams P) {
   const ActGeom G = act_geom(P);
-  if (blockIdx.x * blockDim.x >= G.n_act) return;   // grid sized for the all-live case
+  if (blockIdx.x * blockDim.x >= G.n_act || *P.abort_flag) return;   // grid sized for the all-live case
   __shared__ uint32_t hist[kMaxBins];               // frame shapes of the CTA's DML records
   for (uint32_t i = threadIdx.x; i < P.n_bins; i += blockDim.x) hist[i] = 0;
   __syncthreads();
@@ -704,28 +709,28 @@ __global__ void __launch_bounds__(256) k_frames(DecodeParams P) {
     for (int d = 1; d < 32; d <<= 1) {
       Summ up;
       up.lsn = __shfl_up_sync(0xffffffffu, inc.lsn, d); up.ord = __shfl_up_sync(0xffffffffu, inc.ord, d);
-      up.n_cells = __shfl_up_sync(0xffffffffu, inc.n_cells, d); up.slots = 0;
+      up.n_cells = __shfl_up_sync(0xffffffffu, inc.n_cells, d);
       up.n_rec = __shfl_up_sync(0xffffffffu, inc.n_rec, d); up.flags = __shfl_up_sync(0xffffffffu, inc.flags, d);
       if (lane >= d) inc = fold(up, inc);
     }
     Summ ex;
     ex.lsn = __shfl_up_sync(0xffffffffu, inc.lsn, 1); ex.ord = __shfl_up_sync(0xffffffffu, inc.ord, 1);
-    ex.n_cells = __shfl_up_sync(0xffffffffu, inc.n_cells, 1); ex.slots = 0;
+    ex.n_cells = __shfl_up_sync(0xffffffffu, inc.n_cells, 1);
     ex.n_rec = __shfl_up_sync(0xffffffffu, inc.n_rec, 1); ex.flags = __shfl_up_sync(0xffffffffu, inc.flags, 1);
     if (lane == 0) ex = summ_identity();
     const uint32_t tile = j / 32u;
     const Summ tp = tile < G.n_tiles ? P.tile_prefix[tile] : summ_identity();
-    st = fold(fold(P.carry, tp), ex);
+    st = fold(fold(P.dc->carry, tp), ex);
   }
   if (j < G.n_act) {
     const uint32_t seg = P.act[j];
     uint64_t pos = P.anchors[seg];
-    const uint64_t stop = P.anchors[seg + 1];
+    const uint64_t stop = min(P.anchors[seg + 1], P.len);
     while (pos < stop) {
       const uint8_t* fp = P.buf + pos;
       const FrameHead h = read_head(fp, P.len - pos);
       const uint64_t ridx = st.n_rec;
-      const uint64_t gidx = P.record_index_base + ridx;
+      const uint64_t gidx = P.dc->record_index_base + ridx;
       const uint64_t my_cell0 = st.n_cells;
       const bool in_tx = (st.flags & S_HAS_B) && !(st.flags & S_CLOSED);
       const DevSchema* s = nullptr;
@@ -828,11 +833,12 @@ __global__ void __launch_bounds__(256) k_frames(DecodeParams P) {
       // a record k_walk must not touch keeps schema = -1 only when it failed before conversion
       if (h.kind == 'I' || h.kind == 'U' || h.kind == 'D') {
         if (!ok) rschema = -1;
-        else if (rschema >= 0) atomicAdd(&hist[walk_bin(P, rschema, h.kind, rflags)], 1u);
+        else if (rschema >= 0) atomicAdd(&hist[walk_bin(P, s->layout, h.kind, rflags)], 1u);
       }
       P.rec_off[ridx] = pos; P.rec_kind[ridx] = (uint8_t)h.kind; P.rec_flags[ridx] = (uint8_t)rflags;
       P.rec_rel[ridx] = rrel; P.rec_schema[ridx] = rschema; P.rec_start_lsn[ridx] = start_lsn;
       P.rec_commit_lsn[ridx] = commit_lsn; P.rec_tx_ordinal[ridx] = ordinal; P.rec_cell_base[ridx] = my_cell0;
+      P.rec_flen[ridx] = 1u + h.flen; P.rec_tuple_bytes[ridx] = 0; P.rec_heap_hint[ridx] = 0;   // k_rows fills the DML records
       if (ok && (rflags & ETL_RF_EVENT)) events++;
       st = fold(st, e);
       pos += 1ull + h.flen;
@@ -847,394 +853,27 @@ __global__ void __launch_bounds__(256) k_frames(DecodeParams P) {
 }
 
 // ================================================================================================
-// pass C2: tuples.  Thread per DML record (event.rs:376-919 + text.rs:28-173).
-#ifndef ETL_WALK_PREFETCH
-#define ETL_WALK_PREFETCH 1
-#endif
-// Walker state, packed: k_walk is bound by live registers (a spilled field costs an LSU wavefront per
-// access, and the first ncu pass showed 60 % of all warp instructions were local loads/stores).
-struct Wk {
-  const uint8_t* base;   // frame start (global)
-  uint32_t pos, end;     // frame-relative: next byte to read / frame end
-  uint32_t col_base;
-  uint32_t nc_ni;        // n_cols | n_ident << 16   (both ≤ 32767: int16 on the wire)
-  uint64_t cell0;        // first output cell of the record
-  uint32_t rec_local;
-  uint32_t rem_wire;     // remaining | wire_i << 16
-  uint32_t cmap_kout;    // cmap | k_out << 16
-  uint32_t keyi_nold;    // key_i | n_old << 16
-  uint32_t bits;         // stage[0:3) kind[3:5) old[5:7) dense[7] partial[8] emit[9]
-  uint32_t tb;           // Σ text lengths (calculate_tuple_bytes event.rs:260-270)
-};
-enum : uint32_t { W_OLD_HDR = 0, W_OLD_CELLS = 1, W_NEW_HDR = 2, W_NEW_CELLS = 3, W_DONE = 4 };
-enum : uint32_t { WK_I = 1, WK_U = 2, WK_D = 3, WO_FULL = 1, WO_KEY = 2, WB_DENSE = 1u << 7, WB_PARTIAL = 1u << 8,
-                  WB_EMIT = 1u << 9 };   // emit clears after the first data error: structure-only walk (a malformed
-                                         // frame, i.e. a parser error in the reference, outranks every conversion error)
-struct TextCell { uint32_t voff, len, kind, dest; };   // voff frame-relative, dest relative to cell0
-#define W_SET_STAGE(s_) (w.bits = (w.bits & ~7u) | (s_))
-#define W_DATA_ERROR(seq_, code_) do { report_error(P, P.record_index_base + w.rec_local, (seq_), (code_)); w.bits &= ~WB_EMIT; } while (0)
-#define W_MALFORMED() do { report_error(P, P.record_index_base + w.rec_local, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); W_SET_STAGE(W_DONE); } while (0)
-
-// one step: a tuple header or ONE wire cell.  Returns 0 when no wire cell was consumed (header, end of a
-// tuple, malformed), 1 when one was consumed and needs no parsing, 2 when it is a text cell (tc filled).
-__device__ __forceinline__ uint32_t wk_step(const DecodeParams& P, Wk& w, TextCell& tc) {
-  const uint32_t stage = w.bits & 7u, kind = (w.bits >> 3) & 3u, old = (w.bits >> 5) & 3u;
-  const bool emit = (w.bits & WB_EMIT) != 0;
-  const uint32_t n_cols = w.nc_ni & 0xFFFFu, n_ident = w.nc_ni >> 16;
-  uint32_t ret = 0;
-  do {
-    if (stage == W_OLD_HDR || stage == W_NEW_HDR) {
-      const bool is_new = stage == W_NEW_HDR;
-      if ((uint64_t)w.pos + (is_new ? 3u : 2u) > w.end) { W_MALFORMED(); break; }
-      uint32_t hdr = (uint32_t)ld64u(w.base + w.pos);
-      if (is_new) {
-        if ((hdr & 0xFFu) != 'N') { W_MALFORMED(); break; }
-        hdr >>= 8; w.pos++;
-      }
-      int32_t nci = (int32_t)(int16_t)(((hdr & 0xFFu) << 8) | ((hdr >> 8) & 0xFFu));
-      const uint32_t nc = nci < 0 ? 0u : (uint32_t)nci;
-      w.pos += 2;
-      w.rem_wire = nc; w.cmap_kout = 0;
-      if (!is_new) {
-        if (old == WO_KEY) {                        // normalize_key_tuple_to_row event.rs:879-919
-          w.keyi_nold = (w.keyi_nold & 0xFFFFu) | (n_ident << 16);
-          const bool dense = nc == n_ident;
-          if (dense) w.bits |= WB_DENSE;
-          if (emit) {
-            if (n_ident == 0) W_DATA_ERROR(SEQ_OLD_SHAPE, ETL_E_KEY_NO_COLUMNS);
-            else if (!dense && nc != n_cols) W_DATA_ERROR(SEQ_OLD_SHAPE, ETL_E_KEY_SHAPE);
-          }
-        } else {                                    // convert_tuple_to_row event.rs:550-583
-          w.keyi_nold = (w.keyi_nold & 0xFFFFu) | (n_cols << 16);
-          if (emit && nc != n_cols) W_DATA_ERROR(SEQ_OLD_SHAPE, ETL_E_FIELD_COUNT);
-        }
-        W_SET_STAGE(W_OLD_CELLS);
-      } else {
-        if (emit && nc != n_cols) W_DATA_ERROR(SEQ_NEW_SHAPE, ETL_E_FIELD_COUNT);
-        W_SET_STAGE(W_NEW_CELLS);
-      }
-      break;
-    }
-    if ((w.rem_wire & 0xFFFFu) == 0) {
-      W_SET_STAGE((stage == W_OLD_CELLS && kind != WK_D) ? W_NEW_HDR : W_DONE);
-      break;
-    }
-    if (w.pos >= w.end) { W_MALFORMED(); break; }
-    const uint64_t x = ld64u(w.base + w.pos);
-    const uint32_t tag = (uint32_t)(x & 0xFFu);
-    const uint32_t len = bswap32((uint32_t)(x >> 8));
-    const uint32_t voff = w.pos + 5u;
-    if (tag == 't' || tag == 'b') {
-      if ((uint64_t)w.pos + 5 > w.end || (int32_t)len < 0 || (uint64_t)len > (uint64_t)(w.end - w.pos - 5)) { W_MALFORMED(); break; }
-      w.tb += len;
-      w.pos += 5u + len;
-    } else if (tag == 'n' || tag == 'u') w.pos += 1;
-    else { W_MALFORMED(); break; }
-    const uint32_t i = w.rem_wire >> 16;
-    w.rem_wire += 0x10000u - 1u;                    // wire_i++, remaining--
-    ret = 1;
-    if (!emit) break;                               // structure-only after a data error
-    const bool is_new = stage == W_NEW_CELLS;
-    const uint8_t* flags = P.col_flags + w.col_base;
-    uint32_t col = i, dest;
-    if (!is_new && old == WO_KEY) {
-      if (w.bits & WB_DENSE) {
-        uint32_t cmap = w.cmap_kout & 0xFFFFu;
-        while (cmap < n_cols && !(flags[cmap] & 2)) cmap++;
-        col = cmap++;
-        w.cmap_kout = (w.cmap_kout & 0xFFFF0000u) | cmap;
-      } else if (!(flags[i] & 2)) break;            // full-width key: non-identity entries are not decoded
-      dest = w.cmap_kout >> 16;
-      w.cmap_kout += 0x10000u;
-    } else dest = (is_new ? (w.keyi_nold >> 16) : 0u) + i;
-    const uint32_t seq = is_new ? seq_new_cell(i) : seq_old_cell(i);
-    const bool upd_key = is_new && kind == WK_U && old == WO_KEY;
-    const bool need_flags = tag != 't' || upd_key;
-    const uint32_t cflags = need_flags ? (uint32_t)flags[col] : 0u;
-    const bool resolver_key = upd_key && (cflags & 2);
-    if (tag == 't') {
-      if (resolver_key) w.keyi_nold++;
-      tc.voff = voff; tc.len = len; tc.kind = P.col_kind[w.col_base + col]; tc.dest = dest;
-      return 2;
-    }
-    if (tag == 'n') {                               // convert_tuple_data_to_cell event.rs:941-957
-      if (resolver_key) w.keyi_nold++;
-      if (cflags & 1) put_cell(P, w.cell0 + dest, ETL_CELL_NULL, 0, 0);
-      else W_DATA_ERROR(seq, ETL_E_NOT_NULL);
-      break;
-    }
-    if (tag == 'u') {                               // event.rs:958-970 + OldRowResolver :722-762
-      if (is_new && kind == WK_U) {
-        uint64_t src = ~0ull;
-        if (old == WO_FULL) src = w.cell0 + i;
-        else if (resolver_key) { src = w.cell0 + (w.keyi_nold & 0xFFFFu); w.keyi_nold++; }
-        if (src != ~0ull) {                           // the old cell is produced by k_cells: copied by k_copy afterwards
-          const uint32_t at = atomicAdd(P.copy_count, 1u);
-          if (at < P.copy_cap) { CopyPair cp; cp.dest = w.cell0 + dest; cp.src = src; P.copies[at] = cp; }
-        } else { put_cell(P, w.cell0 + dest, ETL_CELL_MISSING, 0, 0); w.bits |= WB_PARTIAL; }
-      } else W_DATA_ERROR(seq, (!is_new && old == WO_KEY) ? ETL_E_KEY_MISSING_VALUE : ETL_E_FULL_ROW_MISSING);
-      break;
-    }
-    if (resolver_key) w.keyi_nold++;
-    W_DATA_ERROR(seq, ETL_E_BINARY_FORMAT);         // 'b'
-  } while (0);
-  return ret;
+// size hints (types/table_row.rs:250-345): heap bytes a decoded cell owns.  String / Bytes: the Vec's capacity =
+// its length (to_owned, with_capacity).  Numeric: the digit vector is pushed group by group onto Vec::new()
+// (numeric.rs:441-448), so its capacity follows RawVec's amortised growth 0 → 4 → 8 → 16 …; the parsers leave the
+// number of pushed groups in bits [16,32) of CellOut.tag.  Json / Array payloads are estimated by whoever builds
+// the serde_json::Value / ArrayCell (the shim has to run that parser anyway) and are NOT part of rec_heap_hint.
+__device__ __forceinline__ uint32_t vec_cap_after_pushes(uint32_t n) { return n == 0 ? 0u : (n <= 4u ? 4u : 1u << (32 - __clz(n - 1u))); }
+__device__ __forceinline__ uint32_t cell_heap_hint(uint32_t tag32, uint32_t aux) {
+  const uint32_t tag = tag32 & 0xFFu;
+  if (tag == ETL_CELL_STRING || tag == ETL_CELL_BYTES) return aux;
+  if (tag == ETL_CELL_NUMERIC) return 2u * vec_cap_after_pushes(tag32 >> 16);
+  return 0u;
+}
+// a cloned cell (unchanged TOAST taken from the old image, event.rs:958-970): Clone allocates exactly len
+__device__ __forceinline__ uint32_t cell_clone_hint(uint32_t tag, uint32_t aux) {
+  if (tag == ETL_CELL_STRING || tag == ETL_CELL_BYTES) return aux;
+  if (tag == ETL_CELL_NUMERIC) return 2u * aux;
+  return 0u;
 }
 
-__device__ __forceinline__ CellDesc desc_make(uint64_t soff, uint32_t len, uint64_t dest, uint32_t kind) {
-  CellDesc d;
-  d.a = soff | ((uint64_t)(len & 0xFFFFFFu) << 40);
-  d.b = dest | ((uint64_t)kind << 40) | ((uint64_t)(len >> 24) << 48);
-  return d;
-}
-
-// pass C2a: structure.  Thread t walks record perm[t] one wire cell per step and writes one descriptor per
-// step into row (row0 + slot); the 32 lanes of a warp hold records of one shape bin, so a row is one column.
-__global__ void __launch_bounds__(kWalkThreads) k_walk(DecodeParams P) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t n_perm = *P.perm_len;
-  // chunk of the binned order for this CTA.  Bins are contiguous and differ in cost per record (an update
-  // with a full old image walks twice the cells of an insert): consecutive CTAs take chunks 1/64 of the
-  // order apart so that every SM gets the same mix.  The grid is sized for the worst-case padding.
-  const uint32_t n_chunks = (n_perm + blockDim.x - 1) / blockDim.x, cols = (n_chunks + 63u) / 64u;
-  const uint32_t chunk = (blockIdx.x & 63u) * cols + (blockIdx.x >> 6);
-  if ((blockIdx.x >> 6) >= cols || chunk >= n_chunks) return;
-  const uint32_t t = chunk * blockDim.x + threadIdx.x;
-  const uint32_t my_rec = t < n_perm ? P.perm[t] : 0xFFFFFFFFu;   // 0xFFFFFFFF = bin padding
-  Wk w;
-  w.bits = W_DONE; w.tb = 0; w.rec_local = 0; w.base = nullptr; w.pos = 0; w.end = 0; w.col_base = 0; w.nc_ni = 0; w.cell0 = 0;
-  w.rem_wire = 0; w.cmap_kout = 0; w.keyi_nold = 0;
-  uint32_t bin = 0;
-  if (my_rec != 0xFFFFFFFFu) {
-    const uint64_t rr = my_rec;
-    const uint8_t* fp = P.buf + P.rec_off[rr];
-    const int32_t sc = P.rec_schema[rr];
-    const DevSchema& s = P.schemas[P.schema_by_batch[sc]];
-#if ETL_WALK_PREFETCH
-    // the walk is a dependent chain through the frame: put its first lines in flight together
-    if (fp + 128 < P.buf + P.len) asm volatile("prefetch.global.L2 [%0];" ::"l"(fp + 128));
-    if (fp + 256 < P.buf + P.len) asm volatile("prefetch.global.L2 [%0];" ::"l"(fp + 256));
-#endif
-    w.base = fp; w.end = 1u + bswap32((uint32_t)(ld64u(fp) >> 8));
-    w.col_base = s.col_base; w.nc_ni = s.n_cols | (s.n_ident << 16);
-    w.cell0 = P.rec_cell_base[rr]; w.rec_local = (uint32_t)rr;
-    const uint32_t k = P.rec_kind[rr], rf = P.rec_flags[rr];
-    bin = walk_bin(P, sc, k, rf);
-    const uint32_t kc = k == 'I' ? WK_I : (k == 'U' ? WK_U : WK_D);
-    const uint32_t oc = (rf & ETL_RF_OLD_FULL) ? WO_FULL : ((rf & ETL_RF_OLD_KEY) ? WO_KEY : 0u);
-    const bool old_first = kc != WK_I && oc;        // old image first; else the 'N' marker, then the new tuple
-    w.pos = old_first ? 36u : 35u;
-    w.bits = (old_first ? W_OLD_HDR : W_NEW_HDR) | (kc << 3) | (oc << 5) | WB_EMIT;
-  }
-  // the warp's descriptor rows: all valid lanes are in the same bin
-  const unsigned vm = __ballot_sync(0xffffffffu, my_rec != 0xFFFFFFFFu);
-  if (vm == 0) return;
-  bin = __shfl_sync(0xffffffffu, bin, __ffs(vm) - 1);
-  const uint32_t bound = bin_slots(P, bin);
-  const uint32_t row0 = P.bin_row_base[bin] + ((t >> 5) - (P.bin_start[bin] >> 5)) * bound;
-  uint32_t slot = 0;
-  // warp-synchronous stepping: all lanes take one step (header or cell) per iteration; a finished lane
-  // pads its remaining slots with empty descriptors
-  for (;;) {
-    const bool act = (w.bits & 7u) != W_DONE;
-    if (!__any_sync(0xffffffffu, act || slot < bound)) break;
-    TextCell tc;
-    tc.voff = 0; tc.len = 0; tc.kind = 0; tc.dest = 0;
-    const uint32_t got = act ? wk_step(P, w, tc) : (slot < bound ? 1u : 0u);
-    if (got) {
-      if (slot < bound) {
-        CellDesc d;
-        if (got == 2) d = desc_make((uint64_t)(w.base - P.buf) + tc.voff, tc.len, w.cell0 + tc.dest, tc.kind);
-        else d = desc_make(0, 0, 0, DK_EMPTY);
-        const uint32_t row = row0 + slot;
-        reinterpret_cast<uint4*>(P.desc)[(uint64_t)row * 32u + lane] = make_uint4((uint32_t)d.a, (uint32_t)(d.a >> 32), (uint32_t)d.b, (uint32_t)(d.b >> 32));
-        if (lane == 0) P.row_chunk[row] = t >> 5;
-      } else if (got == 2) {
-        // cannot happen for a well-formed shape (the reserved slots cover n_cols wire cells per tuple); a tuple
-        // that is longer than its schema already raised a field-count error and emits nothing
-      }
-      slot++;
-    }
-  }
-  // ---- per-record epilogue: Partial flag; tuple-byte metrics (one atomic per warp and op kind)
-  if (w.bits & WB_PARTIAL) P.rec_flags[w.rec_local] |= ETL_RF_NEW_PARTIAL;
-  const uint32_t wkind = (w.bits >> 3) & 3u;
-  uint32_t tbi = wkind == WK_I ? w.tb : 0u, tbu = wkind == WK_U ? w.tb : 0u, tbd = wkind == WK_D ? w.tb : 0u;
-  unsigned long long si = tbi, su = tbu, sd = tbd;
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) { si += __shfl_down_sync(0xffffffffu, si, d); su += __shfl_down_sync(0xffffffffu, su, d); sd += __shfl_down_sync(0xffffffffu, sd, d); }
-  if (lane == 0) { if (si) atomicAdd(&P.metrics[0], si); if (su) atomicAdd(&P.metrics[1], su); if (sd) atomicAdd(&P.metrics[2], sd); }
-}
-#undef W_DATA_ERROR
-#undef W_MALFORMED
-#undef W_SET_STAGE
-
-// (record, evaluation step) of the cell in lane `lane` of descriptor row `row`: needed only when the cell
-// fails or is a long cell, so it is recomputed from the frame instead of travelling in every descriptor.
-// (inlined: a reference to the kernel parameter struct from an out-of-line function makes every thread copy
-// the whole struct to local memory at kernel entry)
-__device__ __forceinline__ void desc_origin(const DecodeParams& P, uint32_t row, uint32_t lane, uint32_t* rec_out, uint32_t* seq_out) {
-  const uint32_t wchunk = P.row_chunk[row];
-  const uint32_t rec = P.perm[(uint64_t)wchunk * 32u + lane];
-  const uint32_t kind = P.rec_kind[rec], rf = P.rec_flags[rec];
-  const uint32_t bin = walk_bin(P, P.rec_schema[rec], kind, rf);
-  const uint32_t slot = row - (P.bin_row_base[bin] + (wchunk - (P.bin_start[bin] >> 5)) * bin_slots(P, bin));
-  uint32_t n_old_wire = 0;
-  if (kind != 'I' && (rf & 3u)) {                     // old image present: its wire count sits right after the tag
-    const uint8_t* fp = P.buf + P.rec_off[rec];
-    const int32_t nc = (int32_t)(int16_t)(((uint32_t)fp[36] << 8) | fp[37]);
-    n_old_wire = nc < 0 ? 0u : (uint32_t)nc;
-  }
-  *rec_out = rec;
-  *seq_out = slot < n_old_wire ? seq_old_cell(slot) : seq_new_cell(slot - n_old_wire);
-}
-
-// pass C2b: cells.  One warp per descriptor row (text.rs:28-173 on 32 cells of one column): UTF-8
-// (event.rs:972), the per-kind parser, the cell plane and the heap.  No walker state: the registers go to
-// the parsers.
-#ifndef ETL_CELLS_CTAS
-#define ETL_CELLS_CTAS 5
-#endif
-__global__ void __launch_bounds__(256, ETL_CELLS_CTAS) k_cells(DecodeParams P) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (row >= *P.desc_rows) return;                   // grid sized for the host's upper bound
-  const uint4 raw = reinterpret_cast<const uint4*>(P.desc)[(uint64_t)row * 32u + lane];
-  const uint64_t da = ((uint64_t)raw.y << 32) | raw.x, db = ((uint64_t)raw.w << 32) | raw.z;
-  const uint32_t kind = (uint32_t)(db >> 40) & 0xFFu;
-  const bool is_text = kind != DK_EMPTY;
-  const uint64_t soff = da & ((1ull << 40) - 1ull), dest = db & ((1ull << 40) - 1ull);
-  const uint32_t len = (uint32_t)(da >> 40) | ((uint32_t)(db >> 48) & 0xFFu) << 24;
-  const uint8_t* tv = P.buf + soff;
-  CellOut o;
-  o.tag = 0; o.val = 0; o.aux = 0;
-  uint32_t code = 0;
-  bool need_slow = false;                            // small cell with non-ASCII bytes: validated by the whole warp below
-  uint32_t r0_hi = 0, r1_lo = 0, r1_hi = 0;          // long cell: byte ranges [0, r0_hi) and [r1_lo, r1_hi) validated by the whole warp
-  if (is_text) {
-    if (kind == ETL_K_STRING) { o.tag = ETL_CELL_STRING; o.val = soff; o.aux = len; }
-    if (len >= (uint32_t)kCoopLen) {
-      // whole segments inside the cell hold no frame start: k_utf8_dead covers them, the rest is done here
-      const uint64_t cb = soff + len;
-      const uint64_t S0 = (soff + 3ull + P.anchor_stride - 1ull) & ~(uint64_t)(P.anchor_stride - 1u), S1 = cb & ~(uint64_t)(P.anchor_stride - 1u);
-      r0_hi = len;
-      if (S0 < S1) {
-        const uint32_t at = atomicAdd(P.long_count, 1u);
-        if (at < P.long_cap) {
-          LongCell lc;
-          desc_origin(P, row, lane, &lc.rec_local, &lc.seq);
-          lc.l0 = S0 >> 7; lc.l1 = S1 >> 7;
-          P.long_cells[at] = lc;
-          r0_hi = (uint32_t)(S0 - soff); r1_lo = (uint32_t)(S1 - soff); r1_hi = len;
-        }
-      }
-    } else if (len >= (uint32_t)kWideLen) { if (utf8_medium_bad(tv, len)) code = ETL_E_UTF8; }
-    else need_slow = has_high_bits(tv, len);
-  }
-  __syncwarp();
-  // position-local UTF-8 rule, one byte position per lane (a lane-serial walk of a 60-byte cell would
-  // hold the other 31 lanes for ~1000 issue slots; this costs ~60 for the whole warp)
-  for (unsigned sm = __ballot_sync(0xffffffffu, need_slow); sm; sm &= sm - 1) {
-    const int src = __ffs(sm) - 1;
-    const uint8_t* cp = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(tv), src));
-    const uint32_t cn = __shfl_sync(0xffffffffu, len, src);
-    bool bad = false;
-    for (uint32_t i = lane; i <= cn; i += 32) {        // position cn = a virtual ASCII terminator (catches a truncated tail)
-      const uint32_t b = i < cn ? cp[i] : 0u, p1 = i >= 1 ? cp[i - 1] : 0u, p2 = i >= 2 ? cp[i - 2] : 0u, p3 = i >= 3 ? cp[i - 3] : 0u;
-      if ((b | p1 | p2 | p3) >= 0x80u) bad |= utf8_step_bad(b, p1, p2, p3);
-    }
-    bad = __any_sync(0xffffffffu, bad);
-    if (lane == src && bad) code = ETL_E_UTF8;
-  }
-  for (int round = 0; round < 2; round++) {
-    const uint32_t my_lo = round ? r1_lo : 0u, my_hi = round ? r1_hi : r0_hi;
-    for (unsigned sm = __ballot_sync(0xffffffffu, my_hi > my_lo); sm; sm &= sm - 1) {
-      const int src = __ffs(sm) - 1;
-      const uint8_t* cp = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(tv), src));
-      const uint32_t cn = __shfl_sync(0xffffffffu, len, src), lo = __shfl_sync(0xffffffffu, my_lo, src), hi = __shfl_sync(0xffffffffu, my_hi, src);
-      const bool bad = __any_sync(0xffffffffu, utf8_range_bad(cp, cn, lo, hi, (uint32_t)lane, 32u));
-      if (lane == src && bad) code = ETL_E_UTF8;
-    }
-  }
-  const bool do_parse = is_text && !code && kind != ETL_K_STRING;
-  const unsigned pm = __ballot_sync(0xffffffffu, do_parse);
-  if (do_parse) {
-    const unsigned mask = __match_any_sync(pm, kind);
-    uint64_t hpos = 0;
-    const bool heap_kind = kind == ETL_K_NUMERIC || kind == ETL_K_BYTES || kind == ETL_K_UUID;  // uniform over `mask`
-    if (heap_kind) {                                 // warp-aggregated bump allocation
-      const uint32_t hb = cell_heap_bound(kind, len);
-      const unsigned below = mask & ((1u << lane) - 1u);
-      uint32_t mine_off = 0, total = 0;
-      for (unsigned mm = mask; mm; mm &= mm - 1) {   // lanes of `mask` run this loop together
-        const int src = __ffs(mm) - 1;
-        const uint32_t v = __shfl_sync(mask, hb, src);
-        if ((below >> src) & 1u) mine_off += v;
-        total += v;
-      }
-      unsigned long long base = 0;
-      const int leader = __ffs(mask) - 1;
-      if (lane == leader) base = atomicAdd(P.heap_top, (unsigned long long)total);
-      base = __shfl_sync(mask, base, leader);
-      hpos = base + mine_off;
-    }
-    // out-of-line parsers get their own CellOut so that `o` never has its address taken
-    int64_t iv = 0;
-    switch (kind) {
-      case ETL_K_I32: case ETL_K_I64: case ETL_K_I16: case ETL_K_U32: {   // one copy of the parser, limits by kind
-        const uint64_t pos_limit = kind == ETL_K_I32 ? 2147483647ull : (kind == ETL_K_I64 ? 9223372036854775807ull : (kind == ETL_K_I16 ? 32767ull : 4294967295ull));
-        const uint64_t neg_limit = kind == ETL_K_U32 ? 0ull : pos_limit + 1ull;
-        code = parse_int_sync(mask, tv, len, kind != ETL_K_U32, pos_limit, neg_limit, &iv);
-        o.tag = kind == ETL_K_I32 ? ETL_CELL_I32 : (kind == ETL_K_I64 ? ETL_CELL_I64 : (kind == ETL_K_I16 ? ETL_CELL_I16 : ETL_CELL_U32));
-        o.val = (uint64_t)iv;
-        break;
-      }
-      case ETL_K_NUMERIC: code = parse_numeric_sync(mask, tv, len, P.heap, hpos, o); break;
-      case ETL_K_JSON:
-        if (json_valid_sync(mask, tv, len, kJsonTables)) { o.tag = ETL_CELL_JSON; o.val = soff; o.aux = len; } else code = ETL_E_JSON;
-        break;
-      case ETL_K_TIMESTAMPTZ:
-        if (!fast_timestamptz(tv, len, o)) { CellOut t; t.tag = 0; t.val = 0; t.aux = 0; code = parse_text_cell(kind, tv, len, soff, P.heap, hpos, t); o = t; }
-        break;
-      case ETL_K_TIMESTAMP:
-        if (!fast_timestamp(tv, len, o)) { CellOut t; t.tag = 0; t.val = 0; t.aux = 0; code = parse_text_cell(kind, tv, len, soff, P.heap, hpos, t); o = t; }
-        break;
-      case ETL_K_DATE:
-        if (!fast_date(tv, len, o)) { CellOut t; t.tag = 0; t.val = 0; t.aux = 0; code = parse_text_cell(kind, tv, len, soff, P.heap, hpos, t); o = t; }
-        break;
-      case ETL_K_UUID:
-        if (!fast_uuid(tv, len, P.heap, hpos, o)) { CellOut t; t.tag = 0; t.val = 0; t.aux = 0; code = parse_text_cell(kind, tv, len, soff, P.heap, hpos, t); o = t; }
-        break;
-      case ETL_K_BOOL:                                  // bool.rs: exactly "t" / "f"
-        if (len == 1 && (tv[0] == 't' || tv[0] == 'f')) { o.tag = ETL_CELL_BOOL; o.val = tv[0] == 't'; } else code = ETL_E_BOOL;
-        break;
-      default: {
-        CellOut t; t.tag = 0; t.val = 0; t.aux = 0;
-        if (kind & ETL_K_ARRAY) {
-          code = parse_array_any(ArrHeap{P.heap, P.arr_top, P.arr_base, P.heap_cap}, kind, tv, len, t);
-          if (code == 0xFFFFFFFEu) { atomicExch(P.heap_overflow, 1u); code = 0; t.tag = ETL_CELL_NULL; }
-        } else code = parse_text_cell(kind, tv, len, soff, P.heap, hpos, t);
-        o = t;
-        break;
-      }
-    }
-  }
-  if (is_text) {
-    if (code) {
-      uint32_t rec, seq;
-      desc_origin(P, row, (uint32_t)lane, &rec, &seq);
-      report_error(P, P.record_index_base + rec, seq, code);
-    } else put_cell(P, dest, o.tag, o.val, o.aux);
-  }
-}
-
-// pass C2c: unchanged-TOAST cells of updates take the value k_cells produced for the old image
-__global__ void __launch_bounds__(256) k_copy(DecodeParams P) {
-  const uint32_t n = min(*P.copy_count, P.copy_cap);
-  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    const CopyPair c = P.copies[e];
-    put_cell(P, c.dest, P.cell_tag[c.src], P.cell_val[c.src], P.cell_aux[c.src]);
-  }
-}
+}  // namespace etl
+#include "rows_kernel.cuh"
+namespace etl {
 
 }  // namespace etl

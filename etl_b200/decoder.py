@@ -52,6 +52,8 @@ class DecodedBatch:
     rec_commit_lsn: np.ndarray
     rec_tx_ordinal: np.ndarray
     rec_cell_base: np.ndarray
+    rec_tuple_bytes: np.ndarray
+    rec_heap_hint: np.ndarray
     cell_tag: np.ndarray
     cell_val: np.ndarray
     cell_aux: np.ndarray
@@ -72,6 +74,7 @@ class DecodedBatch:
     emit_ms: float = 0.0
     h2d_bytes: int = 0
     d2h_bytes: int = 0
+    record_index_base: int = 0
 
 
 def _make_columns(cols: Sequence[dict]):
@@ -188,6 +191,28 @@ class Decoder:
         self._check(rc)
         return BatchHandle(self, h)
 
+    # -- multi-GPU: the library owns the NCCL communicator and the seam / relation-update exchange ------------
+    def comm_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        self._check(self._l.etl_dec_comm_unique_id(C.cast(buf, C.c_void_p), 128))
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, rank: int, n_ranks: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self._l.etl_dec_comm_init(self._ctx, C.cast(buf, C.c_void_p), 128, rank, n_ranks))
+
+    def decode_sharded(self, inp: abi.DecInput, to_host: bool = True) -> "BatchHandle":
+        """This rank's byte range of one stream: relation-update exchange, index pass, seam all-gather and fold on
+        the device, record + tuple passes (etl_dec_decode_sharded)."""
+        h = C.c_void_p()
+        self._check(self._l.etl_dec_decode_sharded(self._ctx, C.byref(inp), abi.RESULTS_TO_HOST if to_host else 0, C.byref(h)))
+        return BatchHandle(self, h)
+
+    def mem_info(self):
+        f, t = C.c_uint64(), C.c_uint64()
+        self._check(self._l.etl_dec_mem_info(self._ctx, C.byref(f), C.byref(t)))
+        return int(f.value), int(t.value)
+
     def decode_begin(self, inp: abi.DecInput, to_host: bool = True) -> abi.Seam:
         seam = abi.Seam()
         self._check(self._l.etl_dec_decode_begin(self._ctx, C.byref(inp), abi.RESULTS_TO_HOST if to_host else 0, C.byref(seam)))
@@ -270,14 +295,15 @@ class BatchHandle:
         p, s = self.planes(True), self.summary()
         n, m = p.n_records, p.n_cells
         fe = s.first_error
-        nbytes = n * (8 + 1 + 1 + 4 + 4 + 8 + 8 + 8 + 8) + 8 + m * 13 + p.heap_bytes
+        nbytes = n * (8 + 1 + 1 + 4 + 4 + 8 + 8 + 8 + 8 + 4 + 4) + 8 + m * 13 + p.heap_bytes
         return DecodedBatch(
             n_records=int(n), n_cells=int(m),
             rec_off=_np_from(p.rec_off, n, np.uint64), rec_kind=_np_from(p.rec_kind, n, np.uint8),
             rec_flags=_np_from(p.rec_flags, n, np.uint8), rec_rel=_np_from(p.rec_rel, n, np.uint32),
             rec_schema=_np_from(p.rec_schema, n, np.int32), rec_start_lsn=_np_from(p.rec_start_lsn, n, np.uint64),
             rec_commit_lsn=_np_from(p.rec_commit_lsn, n, np.uint64), rec_tx_ordinal=_np_from(p.rec_tx_ordinal, n, np.uint64),
-            rec_cell_base=_np_from(p.rec_cell_base, n + 1, np.uint64), cell_tag=_np_from(p.cell_tag, m, np.uint8),
+            rec_cell_base=_np_from(p.rec_cell_base, n + 1, np.uint64), rec_tuple_bytes=_np_from(p.rec_tuple_bytes, n, np.uint32),
+            rec_heap_hint=_np_from(p.rec_heap_hint, n, np.uint32), cell_tag=_np_from(p.cell_tag, m, np.uint8),
             cell_val=_np_from(p.cell_val, m, np.uint64), cell_aux=_np_from(p.cell_aux, m, np.uint32),
             heap=_np_from(p.heap, p.heap_bytes, np.uint8),
             first_error=(None if fe.record_index == 2**64 - 1 else int(fe.record_index), int(fe.seq), int(fe.code), int(fe.kind)),
@@ -285,4 +311,5 @@ class BatchHandle:
             insert_bytes=int(s.insert_bytes), update_bytes=int(s.update_bytes), delete_bytes=int(s.delete_bytes),
             n_events=int(s.n_events), schemas=self.schemas(), kernel_ms=float(s.kernel_ms), h2d_ms=float(s.h2d_ms),
             d2h_ms=float(s.d2h_ms), gpu_launches=int(s.gpu_launches), result_bytes=int(nbytes),
-            index_ms=float(s.index_ms), emit_ms=float(s.emit_ms), h2d_bytes=int(s.h2d_bytes), d2h_bytes=int(s.d2h_bytes))
+            index_ms=float(s.index_ms), emit_ms=float(s.emit_ms), h2d_bytes=int(s.h2d_bytes), d2h_bytes=int(s.d2h_bytes),
+            record_index_base=int(s.record_index_base))

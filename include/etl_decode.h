@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define ETL_DECODE_ABI_VERSION 1u
+#define ETL_DECODE_ABI_VERSION 2u
 
 /* ---------------------------------------------------------------- status codes */
 typedef enum etl_status {
@@ -113,7 +113,9 @@ typedef struct etl_numeric_hdr {
   uint8_t sign;   /* 0 positive, 1 negative */
   int16_t weight;
   uint16_t scale;
-  uint16_t _pad;
+  uint16_t pushed_groups; /* base-10000 groups the reference pushes onto its digit Vec before stripping zero groups
+                             (numeric.rs:441-448; 0 for canonical zero and the specials, saturates at 65535): the
+                             Vec's capacity — and with it the row's size hint — follows from this count */
 } etl_numeric_hdr;
 
 /* array heap entry: header followed by n_elems etl_array_elem (8-byte aligned). Element payloads
@@ -218,10 +220,15 @@ int etl_stage_append_framed(etl_stager*, const uint8_t* framed, uint64_t len);
 
 typedef struct etl_dec_input {
   const uint8_t* host_buf;       /* framed stream in host memory (pinned if from the stager) */
-  const uint8_t* dev_buf;        /* optional: same bytes already resident in HBM, 16-byte aligned (NULL → library copies) */
+  const uint8_t* dev_buf;        /* optional: same bytes already resident in HBM (NULL → library copies). PRECONDITION:
+                                    16-byte aligned and followed by at least 64 readable bytes after `len` — the
+                                    kernels read whole aligned words / 16-byte copy granules around a cell. The
+                                    library's own copy of host_buf is padded for you. */
   uint64_t len;
   const uint64_t* anchors;       /* host array, n_anchors entries, see etl_stager */
-  const uint64_t* dev_anchors;   /* optional: n_anchors + 1 entries resident in HBM, last entry = len */
+  const uint64_t* dev_anchors;   /* optional: n_anchors + 1 entries resident in HBM, last entry = len. Anchors are
+                                    not trusted: the kernels clamp them to `len` and treat a non-ascending pair as an
+                                    empty segment; an anchor that is not a frame start yields ETL_E_MALFORMED_FRAME. */
   uint64_t n_anchors;
   uint32_t anchor_stride;
   uint32_t _pad;
@@ -235,6 +242,9 @@ int etl_stage_view(const etl_stager*, etl_dec_input* out);
 typedef struct etl_dec_ctx etl_dec_ctx;
 typedef struct etl_dec_batch etl_dec_batch;
 
+/* One context = one apply loop on one GPU (the harness and the shim run one process / thread per GPU).  SURVEY §8b
+ * sketched `etl_dec_create(const int* device_ids, int n_dev, …)`; with one owner per device the multi-GPU form is
+ * etl_dec_create + etl_dec_comm_init(rank, n_ranks) below, which gives the context its NCCL communicator. */
 int etl_dec_create(int device_id, etl_dec_ctx** out);
 /* run on the caller's CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream);
  * default: a private stream created by etl_dec_create */
@@ -248,6 +258,24 @@ int etl_dec_put_table_schema(etl_dec_ctx*, uint32_t table_id, uint64_t snapshot_
                              const etl_column_schema* cols, uint32_t n_cols);
 /* forget replicated-schema state (new connection: Postgres re-sends Relation messages) */
 int etl_dec_reset_relations(etl_dec_ctx*);
+/* ETL_K_* decode class of a type oid, exactly as text.rs:28-173 dispatches (utils.rs:7-16 for unknown oids) */
+uint32_t etl_dec_kind_for_type_oid(uint32_t type_oid);
+/* free / total device memory as the CUDA runtime reports it (leak checks) */
+int etl_dec_mem_info(etl_dec_ctx*, uint64_t* free_bytes, uint64_t* total_bytes);
+
+/* ---------------------------------------------------------------- multi-GPU
+ * The staged stream shards by byte range at record starts, one range per GPU of a box; the library owns the
+ * exchange: an NCCL communicator over the ranks (libnccl.so.2 is resolved at run time — the copy already loaded
+ * into the process if there is one).  etl_dec_decode_sharded runs
+ *   relation-update exchange (the Relation frames of every range, one all-gather; apply.rs:2012-2089,
+ *   table_cache.rs:36-130) → index pass → ncclAllGather of the 64-byte seam summaries ON THE DECODE STREAM →
+ *   device-side fold of the ranks before this one into the carry-in (apply.rs:600-626) → record + tuple passes
+ * with no host round trip between the index and the record pass.  `carry_in` of the input is the state before the
+ * FIRST shard (pass the same value on every rank); summary.carry_out is the state after the LAST shard and
+ * summary.record_index_base the global index of this rank's first record.  Output order = rank order. */
+#define ETL_COMM_ID_BYTES 128u
+int etl_dec_comm_unique_id(uint8_t* out, uint32_t cap);   /* rank 0; broadcast the bytes to the other ranks */
+int etl_dec_comm_init(etl_dec_ctx*, const uint8_t* unique_id, uint32_t id_bytes, int rank, int n_ranks);
 
 /* flags for etl_dec_decode */
 enum {
@@ -269,7 +297,8 @@ typedef struct etl_dec_seam {
 } etl_dec_seam;
 
 int etl_dec_decode(etl_dec_ctx*, const etl_dec_input*, uint32_t flags, etl_dec_batch** out);
-/* multi-GPU two-phase form */
+int etl_dec_decode_sharded(etl_dec_ctx*, const etl_dec_input*, uint32_t flags, etl_dec_batch** out);
+/* two-phase form: the caller exchanges the seam summaries itself (tests; hosts without NCCL) */
 int etl_dec_decode_begin(etl_dec_ctx*, const etl_dec_input*, uint32_t flags, etl_dec_seam* seam_out);
 int etl_dec_decode_finish(etl_dec_ctx*, const etl_stream_state* carry_in, uint64_t record_index_base,
                           etl_dec_batch** out);
@@ -292,6 +321,13 @@ typedef struct etl_dec_planes {
   const uint64_t* rec_commit_lsn;
   const uint64_t* rec_tx_ordinal;
   const uint64_t* rec_cell_base;
+  const uint32_t* rec_tuple_bytes; /* DML: Σ text lengths of the frame's tuples = the ETL_ROW_SIZE_BYTES histogram sample
+                                      (calculate_tuple_bytes, event.rs:260-270, :388, :462, :507); 0 for other records */
+  const uint32_t* rec_heap_hint;   /* DML: Σ estimate_cell_allocated_bytes (types/table_row.rs:295-345) over the String,
+                                      Bytes and Numeric cells of the event's rows — the part of Event::size_hint
+                                      (types/event.rs:288-312) that depends on the data; the struct sizes and Vec<Cell>
+                                      capacities follow from rec_kind / rec_flags / the schema. Json and Array payloads
+                                      are estimated by whoever builds the serde_json::Value / ArrayCell. */
   /* cell plane */
   const uint8_t* cell_tag;
   const uint64_t* cell_val;
@@ -314,12 +350,15 @@ typedef struct etl_dec_summary {
   float index_ms;         /* pass A+B: k_act_* + k_index + k_scan + k_tile_prefix */
   float emit_ms;          /* pass C: k_frames … k_long_verdict, incl. the join with the side stream */
   float frames_ms;        /* k_frames */
-  float walk_ms;          /* k_bin_scan + k_perm + k_walk (tuple structure → cell descriptors) */
+  float walk_ms;          /* k_bin_scan + k_perm (shape bins) */
   float spans_ms;         /* k_utf8_dead (structure-blind UTF-8 pass over segments without a frame start; side stream) */
-  float cells_ms;         /* k_cells + k_copy (UTF-8, per-kind parsers, cell plane) */
+  float cells_ms;         /* k_rows (tuples → rows: staging, walk, UTF-8, per-kind parsers, cell plane) */
   float _pad1;
   uint64_t h2d_bytes, d2h_bytes; /* bytes copied host→device / device→host for this batch */
   uint64_t span_bytes;    /* bytes streamed by k_utf8_dead (its algorithmic bytes) */
+  uint64_t record_index_base; /* global index of this batch's first record (sharded decode: Σ records of the ranks before) */
+  uint32_t abi_version;
+  uint32_t _pad2;
 } etl_dec_summary;
 
 int etl_dec_batch_planes(const etl_dec_batch*, int host, etl_dec_planes* out);

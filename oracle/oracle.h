@@ -46,6 +46,8 @@ typedef struct orc_batch {
   uint64_t* rec_commit_lsn;
   uint64_t* rec_tx_ordinal;
   uint64_t* rec_cell_base; /* n_records + 1 */
+  uint32_t* rec_tuple_bytes; /* DML: Σ text lengths of the frame's tuples (ETL_ROW_SIZE_BYTES sample), else 0 */
+  uint32_t* rec_heap_hint;   /* DML: Σ heap bytes of the String / Bytes / Numeric cells (size hints), else 0 */
   uint8_t* cell_tag;
   uint64_t* cell_val;
   uint32_t* cell_aux;

@@ -370,6 +370,7 @@ static uint32_t parse_numeric(const uint8_t* s, uint64_t n, orc_heap* heap, orc_
       memmove(digits, digits + lead, nd * sizeof(int16_t));
       hdr.sign = (uint8_t)neg;
       hdr.weight = (int16_t)final_weight;
+      hdr.pushed_groups = (uint16_t)(ndig > 65535 ? 65535 : ndig);   /* base_10000_digits.push per group, numeric.rs:441-448 */
     } else {
       nd = 0; hdr.sign = 0; hdr.weight = 0;                  /* canonical zero keeps scale */
     }

@@ -97,6 +97,7 @@ static void ensure_records(orc_batch* b, uint64_t n) {
   GROW(rec_off, uint64_t, 0); GROW(rec_kind, uint8_t, 0); GROW(rec_flags, uint8_t, 0);
   GROW(rec_rel, uint32_t, 0); GROW(rec_schema, int32_t, 0); GROW(rec_start_lsn, uint64_t, 0);
   GROW(rec_commit_lsn, uint64_t, 0); GROW(rec_tx_ordinal, uint64_t, 0); GROW(rec_cell_base, uint64_t, 1);
+  GROW(rec_tuple_bytes, uint32_t, 0); GROW(rec_heap_hint, uint32_t, 0);
   b->cap_records = c;
 }
 static void ensure_cells(orc_batch* b, uint64_t n) {
@@ -128,6 +129,7 @@ void orc_batch_free(orc_batch* b) {
   if (!b) return;
   free(b->rec_off); free(b->rec_kind); free(b->rec_flags); free(b->rec_rel); free(b->rec_schema);
   free(b->rec_start_lsn); free(b->rec_commit_lsn); free(b->rec_tx_ordinal); free(b->rec_cell_base);
+  free(b->rec_tuple_bytes); free(b->rec_heap_hint);
   free(b->cell_tag); free(b->cell_val); free(b->cell_aux); free(b->heap);
   for (uint32_t i = 0; i < b->n_schemas; i++) { free(b->schemas[i].col_kind); free(b->schemas[i].col_flags); free(b->schemas[i].col_index); }
   free(b->schemas);
@@ -184,6 +186,24 @@ typedef struct derr { uint32_t code, seq; } derr;
 #define SEQ_NEW_SHAPE 0x20000u
 #define SEQ_NEW_CELL(i) (0x20001u + (uint32_t)(i))
 
+/* Heap bytes owned by a decoded cell — estimate_cell_allocated_bytes, types/table_row.rs:295-345 — for the
+ * variants whose final Rust value this path builds: String / Bytes = the buffer's capacity (= length: to_owned,
+ * Vec::with_capacity hex.rs:21); Numeric = capacity of the digit Vec, which numeric.rs:441-448 grows by push from
+ * Vec::new() (RawVec amortised growth 0 → 4 → 8 → 16 …, capacity survives the zero strips), × size_of::<i16>().
+ * A value cloned from the old image (event.rs:958-970) allocates exactly its length.  Json / Array: the estimate
+ * walks the serde_json::Value / ArrayCell, which only the materialising side builds — not counted here. */
+static uint32_t vec_cap_after_pushes(uint32_t n) { uint32_t c = 4; if (!n) return 0; while (c < n) c <<= 1; return c; }
+static uint32_t cell_heap_hint(const orc_cell* c, const orc_heap* heap, int cloned) {
+  if (c->tag == ETL_CELL_STRING || c->tag == ETL_CELL_BYTES) return c->aux;
+  if (c->tag == ETL_CELL_NUMERIC) {
+    if (cloned) return 2u * c->aux;
+    etl_numeric_hdr h; memcpy(&h, heap->data + c->val, sizeof h);
+    return 2u * vec_cap_after_pushes(h.pushed_groups);
+  }
+  return 0;
+}
+static __thread uint64_t g_hint;   /* accumulates over the cells of the record being converted */
+
 /* convert_tuple_data_to_cell event.rs:934-979. returns 0 ok/present, 1 missing, or sets *e */
 static int convert_cell(const uint8_t* buf, const wcell* w, uint8_t kind, uint8_t nullable,
                         const orc_cell* old_value, orc_heap* heap, orc_cell* out, uint32_t* ecode) {
@@ -192,11 +212,12 @@ static int convert_cell(const uint8_t* buf, const wcell* w, uint8_t kind, uint8_
       if (nullable) { out->tag = ETL_CELL_NULL; out->val = 0; out->aux = 0; return 0; }
       *ecode = ETL_E_NOT_NULL; return -1;
     case 'u':
-      if (old_value) { *out = *old_value; return 0; }
+      if (old_value) { *out = *old_value; g_hint += cell_heap_hint(out, heap, 1); return 0; }
       return 1;
     case 't':
       if (!orc_utf8_valid(buf + w->off, w->len)) { *ecode = ETL_E_UTF8; return -1; }
       *ecode = orc_parse_text(kind, buf + w->off, w->len, w->off, heap, out);
+      if (!*ecode) g_hint += cell_heap_hint(out, heap, 0);
       return *ecode ? -1 : 0;
     default: /* 'b' */
       *ecode = ETL_E_BINARY_FORMAT; return -1;
@@ -326,6 +347,7 @@ int orc_decode(orc_ctx* c, const uint8_t* buf, uint64_t len, const etl_stream_st
     b->rec_off[rec] = pos; b->rec_kind[rec] = 0; b->rec_flags[rec] = 0; b->rec_rel[rec] = 0;
     b->rec_schema[rec] = -1; b->rec_start_lsn[rec] = 0; b->rec_commit_lsn[rec] = 0;
     b->rec_tx_ordinal[rec] = 0; b->rec_cell_base[rec] = b->n_cells;
+    b->rec_tuple_bytes[rec] = 0; b->rec_heap_hint[rec] = 0;
     err.code = 0; err.seq = 0;
     wtuple t_old = {0, NULL}, t_new = {0, NULL};
     /* ---- CopyData framing written by the stager */
@@ -489,10 +511,13 @@ int orc_decode(orc_ctx* c, const uint8_t* buf, uint64_t len, const etl_stream_st
         b->rec_flags[rec] |= ETL_RF_EVENT;
         if (s->n_cols + 1 > cell_cap) { cell_cap = s->n_cols + 64; oldc = (orc_cell*)realloc(oldc, cell_cap * sizeof(orc_cell)); newc = (orc_cell*)realloc(newc, cell_cap * sizeof(orc_cell)); }
         uint32_t n_old = 0;
+        g_hint = 0;
+        b->rec_tuple_bytes[rec] = (uint32_t)(tuple_bytes(&t_new) + tuple_bytes(&t_old));   /* ETL_ROW_SIZE_BYTES sample event.rs:388,462,507 */
         if (tag == 'I') {                                  /* event.rs:376-393 */
           b->insert_bytes += tuple_bytes(&t_new);
           if (convert_full_row(buf, s, &t_new, &heap, newc, &err, 0) < 0) goto fail;
           for (uint32_t i = 0; i < s->n_cols; i++) push_cell(b, &newc[i]);
+          b->rec_heap_hint[rec] = (uint32_t)g_hint;
           break;
         }
         /* old image first (event.rs:429-450 / :499-520) */
@@ -524,6 +549,7 @@ int orc_decode(orc_ctx* c, const uint8_t* buf, uint64_t len, const etl_stream_st
         }
         for (uint32_t i = 0; i < n_old; i++) push_cell(b, &oldc[i]);
         if (tag == 'U') for (uint32_t i = 0; i < s->n_cols; i++) push_cell(b, &newc[i]);
+        b->rec_heap_hint[rec] = (uint32_t)g_hint;
         break;
       }
       case 'T': {                                          /* apply.rs:2206-2248 */

@@ -55,7 +55,8 @@ class OrcBatch(C.Structure):
                 ("rec_flags", C.POINTER(C.c_uint8)), ("rec_rel", C.POINTER(C.c_uint32)),
                 ("rec_schema", C.POINTER(C.c_int32)), ("rec_start_lsn", C.POINTER(C.c_uint64)),
                 ("rec_commit_lsn", C.POINTER(C.c_uint64)), ("rec_tx_ordinal", C.POINTER(C.c_uint64)),
-                ("rec_cell_base", C.POINTER(C.c_uint64)), ("cell_tag", C.POINTER(C.c_uint8)),
+                ("rec_cell_base", C.POINTER(C.c_uint64)), ("rec_tuple_bytes", C.POINTER(C.c_uint32)),
+                ("rec_heap_hint", C.POINTER(C.c_uint32)), ("cell_tag", C.POINTER(C.c_uint8)),
                 ("cell_val", C.POINTER(C.c_uint64)), ("cell_aux", C.POINTER(C.c_uint32)),
                 ("heap", C.POINTER(C.c_uint8)), ("first_error", FirstError),
                 ("carry_out", StreamState), ("insert_bytes", C.c_uint64),
@@ -124,6 +125,8 @@ class Planes:
     rec_commit_lsn: np.ndarray
     rec_tx_ordinal: np.ndarray
     rec_cell_base: np.ndarray
+    rec_tuple_bytes: np.ndarray
+    rec_heap_hint: np.ndarray
     cell_tag: np.ndarray
     cell_val: np.ndarray
     cell_aux: np.ndarray
@@ -210,7 +213,8 @@ class Oracle:
                 rec_flags=_arr(b.rec_flags, n, np.uint8), rec_rel=_arr(b.rec_rel, n, np.uint32),
                 rec_schema=_arr(b.rec_schema, n, np.int32), rec_start_lsn=_arr(b.rec_start_lsn, n, np.uint64),
                 rec_commit_lsn=_arr(b.rec_commit_lsn, n, np.uint64), rec_tx_ordinal=_arr(b.rec_tx_ordinal, n, np.uint64),
-                rec_cell_base=_arr(b.rec_cell_base, n + 1, np.uint64), cell_tag=_arr(b.cell_tag, m, np.uint8),
+                rec_cell_base=_arr(b.rec_cell_base, n + 1, np.uint64), rec_tuple_bytes=_arr(b.rec_tuple_bytes, n, np.uint32),
+                rec_heap_hint=_arr(b.rec_heap_hint, n, np.uint32), cell_tag=_arr(b.cell_tag, m, np.uint8),
                 cell_val=_arr(b.cell_val, m, np.uint64), cell_aux=_arr(b.cell_aux, m, np.uint32),
                 heap=_arr(b.heap, b.heap_bytes, np.uint8),
                 first_error=(None if fe.record_index == 2**64 - 1 else int(fe.record_index), int(fe.seq), int(fe.code), int(fe.kind)),

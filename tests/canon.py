@@ -24,8 +24,8 @@ def _i64(v: int) -> int:
     return v - (1 << 64) if v >= (1 << 63) else v
 
 
-def numeric_from_heap(heap: bytes, off: int, nd: int):
-    kind, sign, weight, scale, _ = struct.unpack_from("<BBhHH", heap, off)
+def numeric_from_heap(heap: bytes, off: int, nd: int, with_pushed: bool = False):
+    kind, sign, weight, scale, pushed = struct.unpack_from("<BBhHH", heap, off)
     if kind == 1:
         return ("numeric", "NaN")
     if kind == 2:
@@ -33,10 +33,12 @@ def numeric_from_heap(heap: bytes, off: int, nd: int):
     if kind == 3:
         return ("numeric", "-Infinity")
     digits = list(struct.unpack_from("<%dh" % nd, heap, off + 8)) if nd else []
+    if with_pushed:                                    # groups pushed before the zero strips (the digit Vec's capacity)
+        return ("numeric", "-" if sign else "+", weight, scale, digits, pushed)
     return ("numeric", "-" if sign else "+", weight, scale, digits)
 
 
-def decode_cell(tag: int, val: int, aux: int, stream: bytes, heap: bytes, in_array: bool = False) -> Any:
+def decode_cell(tag: int, val: int, aux: int, stream: bytes, heap: bytes, in_array: bool = False, strict: bool = False) -> Any:
     if tag == CELL_NULL:
         return None
     if tag == CELL_MISSING:
@@ -58,7 +60,7 @@ def decode_cell(tag: int, val: int, aux: int, stream: bytes, heap: bytes, in_arr
         src = heap if in_array else stream
         return ("json", bytes(src[val:val + aux]))
     if tag == CELL_NUMERIC:
-        return numeric_from_heap(heap, val, aux)
+        return numeric_from_heap(heap, val, aux, with_pushed=strict and not in_array)
     if tag == CELL_DATE:
         return ("date", _i64(val))
     if tag == CELL_TIME:
@@ -135,7 +137,7 @@ def planes_to_events(p, stream: bytes, limit: Optional[int] = None) -> List[dict
 
 
 _REC_FIELDS = ["rec_off", "rec_kind", "rec_flags", "rec_rel", "rec_schema", "rec_start_lsn",
-               "rec_commit_lsn", "rec_tx_ordinal"]
+               "rec_commit_lsn", "rec_tx_ordinal", "rec_tuple_bytes", "rec_heap_hint"]
 _VAR_TAGS = (CELL_NUMERIC, CELL_UUID, CELL_BYTES, CELL_ARRAY)
 
 
@@ -173,8 +175,8 @@ def assert_planes_equal(got, want, stream: bytes, check_heap_contents: bool = Tr
         gh, wh = got.heap.tobytes(), want.heap.tobytes()
         for i in np.nonzero(~fixed)[0]:
             i = int(i)
-            a = decode_cell(int(gt[i]), int(gv[i]), int(ga[i]), stream, gh)
-            b = decode_cell(int(wt[i]), int(wv[i]), int(wa[i]), stream, wh)
+            a = decode_cell(int(gt[i]), int(gv[i]), int(ga[i]), stream, gh, strict=True)
+            b = decode_cell(int(wt[i]), int(wv[i]), int(wa[i]), stream, wh, strict=True)
             if a != b:
                 raise AssertionError(f"var cell {i} (tag {wt[i]}) differs: got {a} want {b}")
     # schema versions (the host installs every Relation of the batch up front; after a data error

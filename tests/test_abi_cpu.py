@@ -20,19 +20,31 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(abi.EXPORTS), declared ^ set(abi.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.etl_dec_abi_version() == 1
+    assert lib.etl_dec_abi_version() == 2
 
 
-def test_struct_layouts_match_header_sizes():
-    # sizes the C compiler gives (x86-64 SysV): guards against silent ABI drift in the bindings
-    assert C.sizeof(abi.ColumnSchema) == 32
-    assert C.sizeof(abi.StreamState) == 24
-    assert C.sizeof(abi.FirstError) == 24
-    assert C.sizeof(abi.DecInput) == 96
-    assert C.sizeof(abi.Seam) == 48
-    assert C.sizeof(abi.Planes) == 128
-    assert C.sizeof(abi.Summary) == 152
-    assert C.sizeof(abi.SchemaInfo) == 56
+def test_struct_layouts_match_header_sizes(tmp_path):
+    """sizeof / field offsets the C compiler gives for include/etl_decode.h vs the ctypes mirror (guards against
+    silent ABI drift in the bindings)."""
+    import subprocess
+    pairs = [("etl_column_schema", abi.ColumnSchema), ("etl_stream_state", abi.StreamState), ("etl_first_error", abi.FirstError),
+             ("etl_dec_input", abi.DecInput), ("etl_dec_seam", abi.Seam), ("etl_dec_planes", abi.Planes),
+             ("etl_dec_summary", abi.Summary), ("etl_dec_schema_info", abi.SchemaInfo)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "etl_decode.h"', 'int main(void) {']
+    for cname, ct in pairs:
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi_sizes.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi_sizes"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, ct in pairs:
+        assert int(got[cname]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(ct, fname).offset, f"{cname}.{fname}"
 
 
 @pytest.mark.parametrize("stride", [256, 2048, 32768])
