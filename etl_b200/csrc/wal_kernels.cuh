@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(512) k_scan(DecodeParams P) {
     // at once and the host re-runs pass C with exact sizes (P.total stays valid)
     const bool fits = (uint64_t)T.n_rec <= P.cap_records && T.n_cells <= P.cap_cells;
     *P.abort_flag = fits ? 0u : 1u;
-    if (fits) P.rec_cell_base[T.n_rec] = T.n_cells;
+    if (fits && P.rec_cell_base) P.rec_cell_base[T.n_rec] = T.n_cells;   // exact path: the planes do not exist yet, the host writes the tail
     if (P.seam_send) { SeamBlock b; b.total = T; b._pad[0] = b._pad[1] = b._pad[2] = b._pad[3] = 0; *P.seam_send = b; }
   }
 }

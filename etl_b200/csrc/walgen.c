@@ -51,6 +51,8 @@ typedef struct wg_cfg {
   uint32_t toast_unchanged_pct;/* per 10000 of updates leave WG_TOAST_TEXT columns 'u' */
   uint32_t keepalive_every;    /* a keepalive frame every N DML messages (0 = none) */
   uint32_t schema_bump_ppm;    /* per million DML: re-send the Relation with a flipped replica identity */
+  uint32_t relations_once;     /* 1: ONE stream — only segment 0 carries the Relation messages (segments > 0 continue the connection) */
+  uint32_t _pad1;
 } wg_cfg;
 
 typedef struct wg_stats {
@@ -254,6 +256,7 @@ uint64_t wg_generate_segment(const wg_cfg* cfg, uint64_t seg, uint8_t* out, uint
   uint8_t sent[4096]; uint8_t ident[4096];
   memset(sent, 0, sizeof sent);
   for (uint32_t i = 0; i < cfg->n_tables && i < 4096; i++) ident[i] = cfg->tables[i].replident;
+  if (cfg->relations_once && seg > 0) memset(sent, 1, sizeof sent);
   uint64_t row_id = seg * 1000000007ULL + 1;
   uint64_t dml = 0;
   int done = 0;

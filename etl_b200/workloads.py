@@ -41,7 +41,8 @@ class _Cfg(C.Structure):
                 ("pct_update", C.c_uint32), ("pct_delete", C.c_uint32), ("pct_key_change", C.c_uint32),
                 ("tx_mean", C.c_uint32), ("tx_fixed", C.c_uint32), ("null_pct", C.c_uint32),
                 ("nonascii_pct", C.c_uint32), ("toast_row_pct", C.c_uint32), ("toast_unchanged_pct", C.c_uint32),
-                ("keepalive_every", C.c_uint32), ("schema_bump_ppm", C.c_uint32)]
+                ("keepalive_every", C.c_uint32), ("schema_bump_ppm", C.c_uint32), ("relations_once", C.c_uint32),
+                ("_pad1", C.c_uint32)]
 
 
 class _Stats(C.Structure):
@@ -103,6 +104,7 @@ class Workload:
     toast_unchanged_pct: int = 0
     keepalive_every: int = 0
     schema_bump_ppm: int = 0
+    relations_once: bool = False      # ONE stream: only segment 0 carries the Relation messages
     description: str = ""
     _keep: list = field(default_factory=list, repr=False)
 
@@ -136,6 +138,7 @@ class Workload:
         cfg.null_pct, cfg.nonascii_pct = self.null_pct, self.nonascii_pct
         cfg.toast_row_pct, cfg.toast_unchanged_pct = self.toast_row_pct, self.toast_unchanged_pct
         cfg.keepalive_every, cfg.schema_bump_ppm = self.keepalive_every, self.schema_bump_ppm
+        cfg.relations_once = int(self.relations_once)
         return cfg
 
     def segment_capacity(self) -> int:
@@ -205,7 +208,37 @@ def _c4_tables(seed: int) -> List[TableSpec]:
     return tabs
 
 
-def make(name: str, scale: float = 1.0, n_segments: Optional[int] = None) -> Workload:
+def relation_preamble(stream: np.ndarray, n_tables: int) -> np.ndarray:
+    """Prefix of a stream up to the first Commit after every table's Relation message has been seen: decoding it
+    gives a fresh decoder the replicated-schema state the rest of a `relations_once` stream relies on."""
+    pos, seen, n = 0, 0, int(stream.nbytes)
+    while pos + 5 <= n:
+        fl = int.from_bytes(stream[pos + 1:pos + 5].tobytes(), "big")
+        tag = int(stream[pos + 30]) if stream[pos + 5] == ord("w") else 0
+        pos += 1 + fl
+        if tag == ord("R"):
+            seen += 1
+        elif tag == ord("C") and seen >= n_tables:
+            return stream[:pos]
+    return stream
+
+
+def mid_transaction_cut(stream: np.ndarray, target: int) -> int:
+    """Offset of the first frame at or after `target` that is a DML record preceded by a DML record — a cut there
+    falls inside a transaction (bench.py --scaling strong puts the shard seams at such offsets)."""
+    pos, prev, n = 0, 0, int(stream.nbytes)
+    dml = (ord("I"), ord("U"), ord("D"))
+    while pos + 5 <= n:
+        fl = int.from_bytes(stream[pos + 1:pos + 5].tobytes(), "big")
+        tag = int(stream[pos + 30]) if stream[pos + 5] == ord("w") else 0
+        if pos >= target and tag in dml and prev in dml:
+            return pos
+        prev = tag
+        pos += 1 + fl
+    return 0
+
+
+def make(name: str, scale: float = 1.0, n_segments: Optional[int] = None, one_stream: bool = False) -> Workload:
     """name ∈ {c1, c2, c3, c4, c5}.  `scale` multiplies the message count / byte size of the named
     configuration (1.0 = the BASELINE.json size)."""
     name = name.lower()
@@ -243,6 +276,6 @@ def make(name: str, scale: float = 1.0, n_segments: Optional[int] = None) -> Wor
         return Workload("c5", [TableSpec(16384, "docs_default", "d", cols_d), TableSpec(16385, "docs_full", "f", cols_f)],
                         0xE7100005, bytes_per_segment=max(1 << 16, total // segs), n_segments=segs, mix=(5000, 3500, 1500),
                         pct_key_change=1000, tx_mean=20, null_pct=500, nonascii_pct=200, toast_row_pct=500,
-                        toast_unchanged_pct=6000, keepalive_every=4096,
+                        toast_unchanged_pct=6000, keepalive_every=4096, relations_once=one_stream,
                         description="10 GiB synthetic pgoutput buffer, mixed ops + TOASTed text")
     raise ValueError(f"unknown workload {name}")

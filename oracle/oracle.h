@@ -92,6 +92,11 @@ uint32_t orc_parse_copy_row(const uint32_t* type_oids, uint32_t n_cols, const ui
                             uint8_t* heap_out, uint64_t heap_cap, uint64_t* heap_len, uint32_t* err_col);
 uint32_t orc_error_kind(uint32_t code);
 
+/* canonical 256-bit digest of records [0, n_valid) of a decoded batch (oracle_digest.c): var-width payloads are
+ * dereferenced, so two decodes of the same stream compare equal whatever their heap placement */
+void orc_planes_digest(const etl_dec_planes* p, uint64_t n_valid, uint64_t out[4]);
+void orc_batch_digest(const orc_batch* b, uint64_t out[4]);
+
 #ifdef __cplusplus
 }
 #endif

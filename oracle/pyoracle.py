@@ -18,7 +18,7 @@ _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("oracle_cells.c", "oracle_stream.c", "oracle_copy.c", "oracle.h",
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_cells.c", "oracle_stream.c", "oracle_copy.c", "oracle_digest.c", "oracle.h",
                                               "oracle_internal.h", "../include/etl_decode.h")]
     if force or not os.path.exists(_LIB_PATH) or any(
             os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs):
@@ -89,6 +89,10 @@ def lib():
         L.orc_kind_for_oid.restype = C.c_uint32
         L.orc_error_kind.argtypes = [C.c_uint32]
         L.orc_error_kind.restype = C.c_uint32
+        L.orc_planes_digest.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.orc_planes_digest.restype = None
+        L.orc_batch_digest.argtypes = [C.POINTER(OrcBatch), C.POINTER(C.c_uint64)]
+        L.orc_batch_digest.restype = None
         _lib = L
     return _lib
 
@@ -193,6 +197,17 @@ class Oracle:
         self._l.orc_decode(self._ctx, ptr, n, C.byref(st), C.byref(b))
         return b
 
+    def digest(self, buf, carry_in: Optional[tuple] = None):
+        """Decode and return (canonical digest hex, n_records, first_error record or None) without copying planes out."""
+        b = self.decode_raw(buf, carry_in)
+        try:
+            out = (C.c_uint64 * 4)()
+            self._l.orc_batch_digest(C.byref(b), out)
+            fe = b.first_error.record_index
+            return "".join("%016x" % v for v in out), int(b.n_records), (None if fe == 2**64 - 1 else int(fe))
+        finally:
+            self.free(b)
+
     def free(self, b: OrcBatch):
         self._l.orc_batch_free(C.byref(b))
 
@@ -223,6 +238,13 @@ class Oracle:
                 n_events=int(b.n_events), schemas=schemas)
         finally:
             self.free(b)
+
+
+def planes_digest(planes_struct, n_valid: int) -> str:
+    """Canonical digest of an etl_dec_planes struct (ctypes, host pointers) — the checker side of the parity leg."""
+    out = (C.c_uint64 * 4)()
+    lib().orc_planes_digest(C.byref(planes_struct), n_valid, out)
+    return "".join("%016x" % v for v in out)
 
 
 def parse_cell(type_oid: int, text: bytes):
