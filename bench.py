@@ -335,6 +335,12 @@ def gpu_parity(dec_factory, w, arrays, preamble_needed, threads):
     t0 = time.perf_counter()
     _, recs, want = cpu_decode_segments(w, arrays, threads, pre, digests=True)
     dec = dec_factory()
+    if pre is not None:                               # the same starting state as the oracle workers: the stream's Relation preamble
+        from etl_b200 import decoder as _d
+        pst = _d.Stager(max(pre.nbytes, 1), 2048)
+        pst.append_framed(pre)
+        dec.decode_input(pst.view(), to_host=True).free()
+        pst.close()
     bad = []
     for i, a in enumerate(arrays):
         if not w.relations_once:

@@ -71,6 +71,8 @@ EXPORTS = [
     "etl_dec_decode_begin", "etl_dec_decode_finish", "etl_dec_batch_free", "etl_dec_batch_planes",
     "etl_dec_batch_summary", "etl_dec_batch_schema", "etl_dec_decode_sharded", "etl_dec_comm_unique_id", "etl_dec_comm_init",
     "etl_dec_kind_for_type_oid", "etl_dec_mem_info",
+    "etl_shim_materialise", "etl_shim_event_count", "etl_shim_size_hint", "etl_shim_total_size_hint", "etl_shim_owned_bytes",
+    "etl_shim_json_text", "etl_shim_event_list_free",
 ]
 
 _lib = None
@@ -125,6 +127,16 @@ def load(build: bool = True):
     L.etl_dec_kind_for_type_oid.argtypes = [C.c_uint32]
     L.etl_dec_kind_for_type_oid.restype = C.c_uint32
     L.etl_dec_mem_info.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.etl_shim_materialise.argtypes = [vp, vp, vp, C.POINTER(vp)]
+    for f in ("etl_shim_event_count", "etl_shim_total_size_hint", "etl_shim_owned_bytes"):
+        getattr(L, f).argtypes = [vp]
+        getattr(L, f).restype = C.c_uint64
+    L.etl_shim_size_hint.argtypes = [vp, C.c_uint64]
+    L.etl_shim_size_hint.restype = C.c_uint64
+    L.etl_shim_json_text.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_char_p, C.c_uint64]
+    L.etl_shim_json_text.restype = C.c_int64
+    L.etl_shim_event_list_free.argtypes = [vp]
+    L.etl_shim_event_list_free.restype = None
     _lib = L
     return L
 

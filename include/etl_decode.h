@@ -378,6 +378,29 @@ typedef struct etl_dec_schema_info {
 } etl_dec_schema_info;
 int etl_dec_batch_schema(const etl_dec_batch*, uint32_t index, etl_dec_schema_info* out);
 
+/* ---------------------------------------------------------------- shim stand-in (host only, no GPU work)
+ * What the Rust shim does with the planes (replaces nothing in the reference — it is the glue that
+ * rebuilds the reference's own types): materialise the AoS Vec<Event> handed to add_event_to_batch (apply.rs:433-439)
+ * — one owned copy per String / Bytes / Numeric, a serde_json-style tree per Json cell, ArrayCells — and compute
+ * Event::size_hint (types/event.rs:288-312, types/table_row.rs:250-345) per event.  C++ here because the image has no
+ * Rust toolchain; the Rust struct sizes are parameters (pass std::mem::size_of values; NULL = x86-64 estimates). */
+typedef struct etl_rust_layout {
+  uint32_t size_of_cell, size_of_table_row, size_of_partial_table_row;
+  uint32_t size_of_begin_event, size_of_commit_event, size_of_insert_event, size_of_update_event, size_of_delete_event,
+           size_of_truncate_event, size_of_replicated_table_schema, size_of_relation_event;
+  uint32_t size_of_json_value, size_of_usize;
+} etl_rust_layout;
+typedef struct etl_event_list etl_event_list;
+/* batch must have been decoded with ETL_DECODE_RESULTS_TO_HOST; host_stream = the staged bytes (string / json spans) */
+int etl_shim_materialise(const etl_dec_batch*, const uint8_t* host_stream, const etl_rust_layout*, etl_event_list** out);
+uint64_t etl_shim_event_count(const etl_event_list*);
+uint64_t etl_shim_size_hint(const etl_event_list*, uint64_t event_index);  /* Event::size_hint */
+uint64_t etl_shim_total_size_hint(const etl_event_list*);                  /* what events_batch_bytes would hold */
+uint64_t etl_shim_owned_bytes(const etl_event_list*);                      /* bytes copied into owned buffers */
+/* serde_json::to_string of the Json cell at `new_row_cell` of an insert/update event (tests); returns its length */
+int64_t etl_shim_json_text(const etl_event_list*, uint64_t event_index, uint32_t new_row_cell, char* buf, uint64_t cap);
+void etl_shim_event_list_free(etl_event_list*);
+
 #ifdef __cplusplus
 }
 #endif

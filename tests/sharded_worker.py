@@ -1,0 +1,55 @@
+"""Worker of tests/test_gpu_sharded.py: one process per GPU (torchrun).  Every rank builds the SAME deterministic
+stream, takes its byte range, runs etl_dec_decode_sharded (NCCL inside the library) and saves its planes."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    out_dir, name, scale = sys.argv[1], sys.argv[2], float(sys.argv[3])
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    import torch
+    import torch.distributed as dist
+    from etl_b200 import decoder, workloads as wl
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    w = wl.make(name, scale, n_segments=1)
+    if int(os.environ.get("ETL_TEST_BUMP", "0")):
+        w.schema_bump_ppm = int(os.environ["ETL_TEST_BUMP"])
+    stream, _ = w.generate()
+    cuts = np.load(os.path.join(out_dir, "cuts.npy")).tolist()
+    shard = stream[cuts[rank]:cuts[rank + 1]]
+    dec = decoder.Decoder(rank)
+    for tid, cols in w.table_schemas().items():
+        dec.put_table_schema(tid, cols)
+    uid = [dec.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    dec.comm_init(uid[0], rank, world)
+    st = decoder.Stager(max(shard.nbytes, 1), 2048)
+    st.append_framed(shard)
+    for rep in range(2):                                # second pass: optimistic sizing + carried relation state
+        if rep:
+            dec.reset_relations()
+        with dec.decode_sharded(st.view(), to_host=True) as bh:
+            p = bh.to_host()
+    fields = {k: getattr(p, k) for k in ("rec_off", "rec_kind", "rec_flags", "rec_rel", "rec_schema", "rec_start_lsn", "rec_commit_lsn",
+                                         "rec_tx_ordinal", "rec_cell_base", "rec_tuple_bytes", "rec_heap_hint", "cell_tag", "cell_val",
+                                         "cell_aux", "heap")}
+    fe = p.first_error
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **fields,
+             meta=np.array([p.n_records, p.n_cells, -1 if fe[0] is None else fe[0], fe[1], fe[2], fe[3], p.carry_out[0], p.carry_out[1],
+                            p.carry_out[2], p.insert_bytes, p.update_bytes, p.delete_bytes, p.n_events, p.record_index_base], dtype=np.int64),
+             schema_tables=np.array([s.table_id for s in p.schemas], dtype=np.int64),
+             schema_offs=np.array([s.effective_off for s in p.schemas], dtype=np.int64),
+             schema_ident=np.array([s.n_identity for s in p.schemas], dtype=np.int64))
+    dec.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_exports_every_declared_symbol():
     lib = abi.load()
     header = open(os.path.join(ROOT, "include", "etl_decode.h")).read()
-    declared = set(re.findall(r"\b(etl_(?:dec|stage)_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(etl_(?:dec|stage|shim)_[a-z_0-9]+)\s*\(", header))
     assert declared == set(abi.EXPORTS), declared ^ set(abi.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name

@@ -156,12 +156,34 @@ def test_big_cells_and_oversize_frames(gpu, oracle_mod):
     assert_planes_equal(got, want, bad)
 
 
-def test_two_phase_shards_with_seam_fold(gpu, oracle_mod):
-    """The multi-GPU protocol on one device: every shard runs decode_begin (index + scan → seam
-    summary), the summaries are folded exactly as after the all-gather, decode_finish gets the carry.
-    Cuts are in the middle of transactions; the concatenated result must equal the oracle's."""
+def _two_phase(gpu, tables, raw, cuts):
+    """The multi-GPU protocol on one device: every range runs decode_begin (index + scan → seam summary), the
+    summaries are folded exactly as after an all-gather, decode_finish gets the carry and the global record base."""
     from etl_b200 import sharding
     from etl_b200.decoder import Stager
+    dec = gpu.Decoder(0)
+    for tid, cols in tables.items():
+        dec.put_table_schema(tid, cols)
+    parts, state, base = [], (0, 0, 0), 0
+    for k in range(len(cuts) - 1):
+        shard = raw[cuts[k]:cuts[k + 1]]
+        st = Stager(len(shard), 2048)
+        st.append_framed(shard)
+        seam = dec.decode_begin(st.view(), to_host=True)
+        words = sharding.seam_to_words(seam)
+        with dec.decode_finish(state, base) as bh:
+            parts.append(bh.to_host())
+        state = sharding.fold_state(state, words)
+        base += int(words[0])
+        st.close()
+    dec.close()
+    return parts, base
+
+
+def test_two_phase_shards_with_seam_fold(gpu, oracle_mod):
+    """Cuts are in the middle of transactions; the stitched result must equal the oracle's decode of the whole
+    stream on EVERY plane."""
+    from shard_util import mid_tx_cuts, stitch
     w = wl.make("c2", 0.02, n_segments=1)
     stream, _ = w.generate()
     raw = stream.tobytes()
@@ -169,37 +191,35 @@ def test_two_phase_shards_with_seam_fold(gpu, oracle_mod):
     for tid, cols in w.table_schemas().items():
         orc.put_table_schema(tid, cols)
     full = orc.decode(raw)
-    kinds = [chr(k) for k in full.rec_kind]
-    cuts_rec = [next(i for i in range(full.n_records * f // 3, full.n_records) if kinds[i] in "IUD" and kinds[i - 1] in "IUD") for f in (1, 2)]
-    cuts = [0] + [int(full.rec_off[i]) for i in cuts_rec] + [len(raw)]
-    dec = gpu.Decoder(0)
-    for tid, cols in w.table_schemas().items():
-        dec.put_table_schema(tid, cols)
-    seams, parts = [], []
-    state, base = (0, 0, 0), 0
-    for k in range(3):
-        shard = raw[cuts[k]:cuts[k + 1]]
-        st = Stager(len(shard), 2048)
-        st.append_framed(shard)
-        inp = st.view()
-        seam = dec.decode_begin(inp, to_host=True)
-        words = sharding.seam_to_words(seam)
-        with dec.decode_finish(state, base) as bh:
-            parts.append(bh.to_host())
-        seams.append(words)
-        state = sharding.fold_state(state, words)
-        base += int(words[0])
-        st.close()
-    dec.close()
+    cuts = mid_tx_cuts(full, 3) + [len(raw)]
+    parts, base = _two_phase(gpu, w.table_schemas(), raw, cuts)
     assert base == full.n_records
     assert all(p.first_error[0] is None for p in parts)
-    ordinals = np.concatenate([p.rec_tx_ordinal for p in parts])
-    commits = np.concatenate([p.rec_commit_lsn for p in parts])
-    assert np.array_equal(ordinals, full.rec_tx_ordinal) and np.array_equal(commits, full.rec_commit_lsn)
-    assert np.array_equal(np.concatenate([p.cell_val for p in parts])[~np.isin(np.concatenate([p.cell_tag for p in parts]), (2, 15))],
-                          full.cell_val[~np.isin(full.cell_tag, (2, 15))])
-    assert parts[-1].carry_out == full.carry_out
-    # a data error in a later shard reports its GLOBAL record index
+    assert_planes_equal(stitch(parts, cuts), full, raw)
+
+
+def test_two_phase_error_in_later_shard_reports_global_index(gpu, oracle_mod):
+    """A data error in the third range carries its GLOBAL record index (record_index_base > 0 in report_error and
+    k_long_verdict), and is the index the oracle reports for the whole stream."""
+    from shard_util import mid_tx_cuts
+    w = wl.make("c2", 0.02, n_segments=1)
+    stream, _ = w.generate()
+    orc = oracle_mod.Oracle()
+    for tid, cols in w.table_schemas().items():
+        orc.put_table_schema(tid, cols)
+    full = orc.decode(stream.tobytes())
+    cuts = mid_tx_cuts(full, 3)
+    s = bytearray(stream.tobytes())
+    victim = next(i for i in range(full.n_records * 5 // 6, full.n_records) if chr(full.rec_kind[i]) == "I")
+    off = int(full.rec_off[victim])
+    assert off > cuts[2] and s[off + 38:off + 39] == b"t"
+    s[off + 43] = ord("x")                              # first cell (int4) of an insert: not a digit any more
+    raw = bytes(s)
+    want = orc.decode(raw)
+    assert want.first_error[0] == victim
+    parts, _ = _two_phase(gpu, w.table_schemas(), raw, cuts + [len(raw)])
+    assert parts[0].first_error[0] is None and parts[1].first_error[0] is None
+    assert parts[2].first_error == want.first_error
 
 
 FLOAT_CASES = ["0", "-0", "1", "3.15", "-2.818", "inf", "-Infinity", "NaN", "-nan", "3.4028235e38", "-3.4028235e38",
