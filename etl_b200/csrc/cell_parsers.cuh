@@ -736,13 +736,19 @@ __device__ __forceinline__ uint32_t parse_numeric_sync(unsigned mask, const uint
   while (__any_sync(mask, simple && i < n)) {
     if (simple && i < n) {
       const uint32_t k = min(8u, n - i);
-      uint64_t x = ldu64(s + i);
-      for (uint32_t j = 0; j < k; j++, x >>= 8) {
-        const uint32_t ch = (uint32_t)x & 0xFFu;
-        if (is_digit(ch)) { if (ndot) nfrac++; else nint++; }
-        else if (ch == '.') ndot++;
-        else simple = false;
-      }
+      const uint64_t x = ldu64(s + i);
+      // per-byte classes, 8 bytes at a time: 0x80 in a byte of `dig` / `dot` = that byte is a digit / a '.'
+      const uint64_t HI = 0x8080808080808080ull, L7 = 0x7F7F7F7F7F7F7F7Full;
+      const uint64_t vm = k < 8u ? ((1ull << (8u * k)) - 1ull) & HI : HI;
+      const uint64_t t = x ^ 0x3030303030303030ull;                       // digits → 0..9
+      const uint64_t dig = ~(((t & L7) + 0x7676767676767676ull) | t) & vm;
+      const uint64_t u = x ^ 0x2E2E2E2E2E2E2E2Eull;                       // '.' → 0
+      const uint64_t dot = ~(((u & L7) + L7) | u) & vm;
+      if ((dig | dot) != vm) simple = false;
+      const uint64_t before = dot ? ((dot & (0ull - dot)) - 1ull) : ~0ull;   // bytes below the first '.' of this word
+      const uint32_t nd_all = (uint32_t)__popcll(dig), nd_before = (uint32_t)__popcll(dig & before);
+      if (ndot) nfrac += nd_all; else { nint += nd_before; nfrac += nd_all - nd_before; }
+      ndot += (uint32_t)__popcll(dot);
       i += k;
     }
   }
@@ -803,65 +809,64 @@ __device__ __forceinline__ uint32_t parse_numeric_sync(unsigned mask, const uint
 // serde_json acceptance, table-driven so that every lane executes the same instructions per byte
 // (a switch over the state serialises the warp: the first version spent ~225 warp instructions per
 // byte step on it).  Tables: tools/gen_json_tables.py (fuzzed against the oracle in
-// tests/test_json_tables.py); T points at the CTA's shared-memory copy of kJsonTables.
-// Every iteration consumes exactly one byte, so `i` stays uniform over the lanes of `mask`.
-__device__ __forceinline__ bool json_valid_sync(unsigned mask, const uint8_t* s, uint32_t n, const uint8_t* T) {
-  uint32_t st = JT_VALUE, depth = 0, ctx = 0 /*0 top, 1 object, 2 array*/, aux = 0, hexn = 0;
+// tests/test_json_tables.py); T2 = kJsonT2 (state << 8 | byte → next | action << 5), in shared memory.
+// One load per byte (the class lookup is folded into the table), eight bytes between two warp votes, and the
+// container stack is a 128-bit shift register (bit 0 = innermost level, 1 = object) so that brackets and commas
+// are handled by predicated straight-line code: with 32 documents in flight some lane sits on a structural
+// byte at almost every step, and a divergent action block was a third of this function's issue slots (ncu, C3).
+__device__ __forceinline__ bool json_valid_sync(unsigned mask, const uint8_t* s, uint32_t n, const uint8_t* T2) {
+  uint32_t st = JT_VALUE, depth = 0, aux = 0, hexn = 0;
   bool key = false, low_sur = false;
-  uint64_t lo = 0, hi = 0;                            // container stack, bit d = 1: level d is an object
-  uint64_t word = 0, next = n ? ldu64(s) : 0ull;      // one word ahead: the load overlaps the 8 DFA steps before it
+  uint64_t lo = 0, hi = 0;
+  uint64_t next = n ? ldu64(s) : 0ull;                // one word ahead: the load overlaps the 8 DFA steps before it
   uint32_t i = 0;
-  while (__any_sync(mask, i < n && st != JT_BAD)) {
-    if (i < n && st != JT_BAD) {
-      if ((i & 7u) == 0) { word = next; if (i + 8u < n) next = ldu64(s + i + 8u); }
-      const uint32_t c = (uint32_t)(word >> ((i & 7u) * 8u)) & 0xFFu;
-      i++;
-      if (st - JT_ESC <= 3u) {                        // inside an escape: rare
-        if (st == JT_ESC) {
-          if (c == 'u') { st = JT_HEX; hexn = 4; aux = 0; }
-          else if (c == '"' || c == '\\' || c == '/' || c == 'b' || c == 'f' || c == 'n' || c == 'r' || c == 't') st = low_sur ? JT_BAD : JT_STR;
-          else st = JT_BAD;
-        } else if (st == JT_HEX) {
-          const int h = hexval(c);
-          if (h < 0) st = JT_BAD;
-          else {
-            aux = aux * 16u + (uint32_t)h;
-            if (--hexn == 0) {
-              if (low_sur) { st = (aux >= 0xDC00u && aux <= 0xDFFFu) ? JT_STR : JT_BAD; low_sur = false; }
-              else if (aux >= 0xDC00u && aux <= 0xDFFFu) st = JT_BAD;
-              else if (aux >= 0xD800u && aux <= 0xDBFFu) st = JT_SUR_BS;
-              else st = JT_STR;
+  while (__any_sync(mask, i < n && st != JT_BAD)) {   // i is a multiple of 8 for every lane that is still running
+    const uint64_t word = next;
+    if (i + 8u < n) next = ldu64(s + i + 8u);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (i < n && st != JT_BAD) {
+        const uint32_t c = (uint32_t)(word >> (8 * k)) & 0xFFu;
+        i++;
+        if (st - JT_ESC <= 3u) {                      // inside an escape: rare
+          if (st == JT_ESC) {
+            if (c == 'u') { st = JT_HEX; hexn = 4; aux = 0; }
+            else if (c == '"' || c == '\\' || c == '/' || c == 'b' || c == 'f' || c == 'n' || c == 'r' || c == 't') st = low_sur ? JT_BAD : JT_STR;
+            else st = JT_BAD;
+          } else if (st == JT_HEX) {
+            const int h = hexval(c);
+            if (h < 0) st = JT_BAD;
+            else {
+              aux = aux * 16u + (uint32_t)h;
+              if (--hexn == 0) {
+                if (low_sur) { st = (aux >= 0xDC00u && aux <= 0xDFFFu) ? JT_STR : JT_BAD; low_sur = false; }
+                else if (aux >= 0xDC00u && aux <= 0xDFFFu) st = JT_BAD;
+                else if (aux >= 0xD800u && aux <= 0xDBFFu) st = JT_SUR_BS;
+                else st = JT_STR;
+              }
             }
+          } else if (st == JT_SUR_BS) st = (c == '\\') ? JT_SUR_U : JT_BAD;
+          else { if (c == 'u') { st = JT_HEX; hexn = 4; aux = 0; low_sur = true; } else st = JT_BAD; }
+        } else {
+          const uint32_t e = T2[(st << 8) | c];
+          uint32_t nst = e & 31u;
+          const uint32_t act = e >> 5;
+          const bool top_obj = (lo & 1ull) != 0ull;
+          if ((act - JA_PUSH_OBJ) < 2u) {             // '{' '[': serde_json's recursion limit is 128 levels
+            nst = depth < 127u ? nst : (uint32_t)JT_BAD;
+            hi = (hi << 1) | (lo >> 63); lo = (lo << 1) | (act == JA_PUSH_OBJ ? 1ull : 0ull);
+            depth++;
           }
-        } else if (st == JT_SUR_BS) st = (c == '\\') ? JT_SUR_U : JT_BAD;
-        else { if (c == 'u') { st = JT_HEX; hexn = 4; aux = 0; low_sur = true; } else st = JT_BAD; }
-      } else {
-        const uint32_t e = T[256u + st * (uint32_t)kJsonClasses + T[c]];
-        uint32_t nst = e & 31u;
-        const uint32_t act = e >> 5;
-        if (act) {                                    // brackets, commas, opening quotes
-          if (act <= JA_PUSH_ARR) {
-            if (depth >= 127u) nst = JT_BAD;
-            else {
-              const uint64_t bit = act == JA_PUSH_OBJ ? 1ull : 0ull;
-              if (depth < 64u) lo = (lo & ~(1ull << depth)) | (bit << depth);
-              else hi = (hi & ~(1ull << (depth - 64u))) | (bit << (depth - 64u));
-              depth++;
-              ctx = act == JA_PUSH_OBJ ? 1u : 2u;
-            }
-          } else if (act <= JA_POP_ARR) {
-            if (ctx != (act == JA_POP_OBJ ? 1u : 2u)) nst = JT_BAD;
-            else {
-              depth--;
-              const uint32_t p = depth - 1u;          // parent level (unused when depth == 0)
-              const uint64_t bits = p < 64u ? lo : hi;
-              ctx = depth == 0 ? 0u : (((bits >> (p & 63u)) & 1ull) ? 1u : 2u);
-            }
-          } else if (act == JA_COMMA) nst = ctx == 0 ? JT_BAD : (ctx == 1 ? JT_KEY : JT_VALUE);
-          else { key = act == JA_KEYSTR; low_sur = false; }
+          if ((act - JA_POP_OBJ) < 2u) {              // '}' ']' must close the innermost container of its kind
+            nst = (depth > 0u && top_obj == (act == JA_POP_OBJ)) ? nst : (uint32_t)JT_BAD;
+            lo = (lo >> 1) | (hi << 63); hi >>= 1;
+            depth--;
+          }
+          if (act == JA_COMMA) nst = depth == 0u ? (uint32_t)JT_BAD : (top_obj ? (uint32_t)JT_KEY : (uint32_t)JT_VALUE);
+          if (act >= JA_KEYSTR) { key = act == JA_KEYSTR; low_sur = false; }
+          if (nst == JT_STR_END) nst = key ? JT_COLON : JT_AFTER;
+          st = nst;
         }
-        if (nst == JT_STR_END) nst = key ? JT_COLON : JT_AFTER;
-        st = nst;
       }
     }
   }

@@ -757,7 +757,7 @@ static int prepare(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t flags, bo
   const size_t line_words = (in->len + 4095) / 4096 + 1;
   CK(ctx->d_line_bad.ensure(line_words)); CK(ctx->d_dead.ensure(P.n_anchors + 1));
   P.line_bad = ctx->d_line_bad.ptr(); P.dead = ctx->d_dead.ptr();
-  P.long_cap = P.n_anchors + 16;                      // a listed cell covers at least one whole segment
+  P.long_cap = (uint32_t)(in->len / 512) + 16;        // every listed cell is at least kCoopLen (512) bytes long
   CK(ctx->d_long.ensure(P.long_cap));
   unsigned long long* sc = reinterpret_cast<unsigned long long*>(ctx->d_scalars.ptr());
   P.long_cells = ctx->d_long.ptr(); P.long_count = (unsigned int*)(sc + 7);
@@ -896,7 +896,7 @@ static int launch_emit_kernels(etl_dec_ctx* ctx) {
       cudaEventRecord(ctx->ev_l1, st);
       ctx->launches += 1;
     }
-    if (cap_r) { k_long_verdict<<<592, 256, 0, st>>>(P); ctx->launches += 1; }
+    if (cap_r) { k_long_cells<<<sm_count(ctx) * 8, 256, 0, st>>>(P); ctx->launches += 1; }
     ctx->launches += 1;
     CK(cudaGetLastError());
   } else { cudaEventRecord(ctx->evk[0], st); cudaEventRecord(ctx->evk[2], st); cudaEventRecord(ctx->evk[1], st); cudaEventRecord(ctx->ev_l0, st); cudaEventRecord(ctx->ev_l1, st); }

@@ -15,20 +15,26 @@
 namespace etl {
 
 #ifndef ETL_ROWS_WIN
-#define ETL_ROWS_WIN 512                 // bytes of one record's frame staged per pass (multiple of 16)
+#define ETL_ROWS_WIN 480                 // bytes of one record's frame staged per pass (multiple of 16)
 #endif
 #ifndef ETL_ROWS_CTAS
-#define ETL_ROWS_CTAS 3
+#define ETL_ROWS_CTAS 3                  // resident CTAs per SM the register budget is set for
 #endif
-constexpr uint32_t kRowsWarps = 4;
+#ifndef ETL_ROWS_WARPS
+#define ETL_ROWS_WARPS 4
+#endif
+constexpr uint32_t kRowsWarps = ETL_ROWS_WARPS;
 constexpr uint32_t kRowsThreads = kRowsWarps * 32;
 constexpr uint32_t kRowsWin = ETL_ROWS_WIN;
 constexpr uint32_t kRowsSlot = kRowsWin + 16;                      // slot stride: 16-byte aligned, skews the banks
-constexpr uint32_t kRowsJsonBytes = (256 + 32 * kJsonClasses + 127) & ~127u;
-constexpr uint32_t kRowsBarOff = kRowsJsonBytes;                   // kRowsWarps mbarriers (8 bytes each)
-constexpr uint32_t kRowsSlotsOff = kRowsBarOff + 128;
+constexpr uint32_t kRowsJsonBytes = 32 * 256;                      // kJsonT2, brought in by one bulk copy per CTA
+constexpr uint32_t kRowsBarOff = kRowsJsonBytes;                   // [0] the CTA's table barrier, [1 ..] one mbarrier per warp
+constexpr uint32_t kRowsColsOff = kRowsBarOff + 128;               // per warp: 256 column kinds + 256 column flags of its schema
+constexpr uint32_t kRowsColsCached = 256;
+constexpr uint32_t kRowsSlotsOff = kRowsColsOff + kRowsWarps * 2 * kRowsColsCached;
 constexpr uint32_t kRowsSmemBytes = kRowsSlotsOff + kRowsWarps * 32 * kRowsSlot + 64;   // + tail padding for word reads
 constexpr uint32_t kRowsMaxInWin = kRowsWin - 24;                  // a text cell up to this long always fits a fresh window
+static_assert(kRowsWarps <= 15 && kRowsWin % 16 == 0, "k_rows geometry");
 
 // ---- mbarrier / bulk-copy primitives (PTX ISA 8.x; SASS: SYNCS.*, UBLKCP)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -56,6 +62,56 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// text.rs:28-173 for the lanes of `mask` (same decode class): the warp-synchronous fast paths for the spellings
+// Postgres emits, the exact out-of-line parsers for everything else.  `soff` = where a zero-copy span (json) points;
+// `hpos` = this lane's reservation in the scalar heap.  Shared by k_rows (WAL tuples) and k_copy_rows (COPY rows).
+struct CellHeaps { uint8_t* heap; unsigned long long* arr_top; uint64_t arr_base, heap_cap; unsigned int* heap_overflow; };
+__device__ __forceinline__ uint32_t parse_cell_sync(unsigned mask, uint32_t kind, const uint8_t* tv, uint32_t len, uint64_t soff,
+                                                    const CellHeaps H, uint64_t hpos, const uint8_t* JT, CellOut& o) {
+  uint32_t code = 0;
+  int64_t iv = 0;
+  // out-of-line parsers get their own CellOut so that `o` never has its address taken
+  switch (kind) {
+    case ETL_K_I32: case ETL_K_I64: case ETL_K_I16: case ETL_K_U32: {   // one copy of the parser, limits by kind
+      const uint64_t pos_limit = kind == ETL_K_I32 ? 2147483647ull : (kind == ETL_K_I64 ? 9223372036854775807ull : (kind == ETL_K_I16 ? 32767ull : 4294967295ull));
+      const uint64_t neg_limit = kind == ETL_K_U32 ? 0ull : pos_limit + 1ull;
+      code = parse_int_sync(mask, tv, len, kind != ETL_K_U32, pos_limit, neg_limit, &iv);
+      o.tag = kind == ETL_K_I32 ? ETL_CELL_I32 : (kind == ETL_K_I64 ? ETL_CELL_I64 : (kind == ETL_K_I16 ? ETL_CELL_I16 : ETL_CELL_U32));
+      o.val = (uint64_t)iv;
+      break;
+    }
+    case ETL_K_NUMERIC: code = parse_numeric_sync(mask, tv, len, H.heap, hpos, o); break;
+    case ETL_K_JSON:
+      if (json_valid_sync(mask, tv, len, JT)) { o.tag = ETL_CELL_JSON; o.val = soff; o.aux = len; } else code = ETL_E_JSON;
+      break;
+    case ETL_K_TIMESTAMPTZ:
+      if (!fast_timestamptz(tv, len, o)) { CellOut tt; tt.tag = 0; tt.val = 0; tt.aux = 0; code = parse_text_cell(kind, tv, len, soff, H.heap, hpos, tt); o = tt; }
+      break;
+    case ETL_K_TIMESTAMP:
+      if (!fast_timestamp(tv, len, o)) { CellOut tt; tt.tag = 0; tt.val = 0; tt.aux = 0; code = parse_text_cell(kind, tv, len, soff, H.heap, hpos, tt); o = tt; }
+      break;
+    case ETL_K_DATE:
+      if (!fast_date(tv, len, o)) { CellOut tt; tt.tag = 0; tt.val = 0; tt.aux = 0; code = parse_text_cell(kind, tv, len, soff, H.heap, hpos, tt); o = tt; }
+      break;
+    case ETL_K_UUID:
+      if (!fast_uuid(tv, len, H.heap, hpos, o)) { CellOut tt; tt.tag = 0; tt.val = 0; tt.aux = 0; code = parse_text_cell(kind, tv, len, soff, H.heap, hpos, tt); o = tt; }
+      break;
+    case ETL_K_BOOL:                                  // bool.rs: exactly "t" / "f"
+      if (len == 1 && (tv[0] == 't' || tv[0] == 'f')) { o.tag = ETL_CELL_BOOL; o.val = tv[0] == 't'; } else code = ETL_E_BOOL;
+      break;
+    default: {
+      CellOut tt; tt.tag = 0; tt.val = 0; tt.aux = 0;
+      if (kind & ETL_K_ARRAY) {
+        code = parse_array_any(ArrHeap{H.heap, H.arr_top, H.arr_base, H.heap_cap}, kind, tv, len, tt);
+        if (code == 0xFFFFFFFEu) { atomicExch(H.heap_overflow, 1u); code = 0; tt.tag = ETL_CELL_NULL; }
+      } else code = parse_text_cell(kind, tv, len, soff, H.heap, hpos, tt);
+      o = tt;
+      break;
+    }
+  }
+  return code;
 }
 
 // Walker state of one record.
@@ -112,7 +168,7 @@ __device__ __forceinline__ bool rk_peek(const Wk& w, const RowWin& W, uint64_t* 
 
 // One step: a tuple header or ONE wire cell (event.rs:550-919).  Returns 0 when no wire cell was consumed
 // (header, end of a tuple, malformed), 1 when one was consumed and needs no parsing, 2 when it is a text cell.
-__device__ __forceinline__ uint32_t rk_step(const DecodeParams& P, Wk& w, TextCell& tc, const uint64_t x) {
+__device__ __forceinline__ uint32_t rk_step(const DecodeParams& P, Wk& w, TextCell& tc, const uint64_t x, const uint8_t* kinds, const uint8_t* flags) {
   const uint32_t stage = w.bits & 7u, kind = (w.bits >> 3) & 3u, old = (w.bits >> 5) & 3u;
   const bool emit = (w.bits & WB_EMIT) != 0;
   const uint32_t n_cols = w.nc_ni & 0xFFFFu, n_ident = w.nc_ni >> 16;
@@ -169,7 +225,6 @@ __device__ __forceinline__ uint32_t rk_step(const DecodeParams& P, Wk& w, TextCe
     ret = 1;
     if (!emit) break;                               // structure-only after a data error
     const bool is_new = stage == W_NEW_CELLS;
-    const uint8_t* flags = P.col_flags + w.col_base;
     uint32_t col = i, dest;
     if (!is_new && old == WO_KEY) {
       if (w.bits & WB_DENSE) {
@@ -188,7 +243,7 @@ __device__ __forceinline__ uint32_t rk_step(const DecodeParams& P, Wk& w, TextCe
     const bool resolver_key = upd_key && (cflags & 2);
     if (tag == 't') {
       if (resolver_key) w.keyi_nold++;
-      tc.voff = voff; tc.len = len; tc.kind = P.col_kind[w.col_base + col]; tc.dest = dest; tc.seq = seq;
+      tc.voff = voff; tc.len = len; tc.kind = kinds[col]; tc.dest = dest; tc.seq = seq;
       return 2;
     }
     if (tag == 'n') {                               // convert_tuple_data_to_cell event.rs:941-957
@@ -229,16 +284,18 @@ __global__ void __launch_bounds__(kRowsThreads, ETL_ROWS_CTAS) k_rows(DecodePara
   const uint32_t n_chunks = (n_perm + blockDim.x - 1) / blockDim.x, cols = (n_chunks + 63u) / 64u;
   const uint32_t chunk = (blockIdx.x & 63u) * cols + (blockIdx.x >> 6);
   if ((blockIdx.x >> 6) >= cols || chunk >= n_chunks) return;
-  // CTA set-up: the JSON acceptor's tables and one mbarrier per warp
-  for (uint32_t i = threadIdx.x; i < (256u + 32u * kJsonClasses) / 4u; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(smem)[i] = reinterpret_cast<const uint32_t*>(kJsonTables)[i];
+  // CTA set-up: one mbarrier per warp, and the JSON acceptor's table by one bulk copy (waited for after the record loads)
+  const uint32_t tbar = smem_u32(smem + kRowsBarOff);
   if (threadIdx.x == 0) {
-    for (uint32_t k = 0; k < kRowsWarps; k++) mbar_init(smem_u32(smem + kRowsBarOff + 8u * k), 32u);
+    mbar_init(tbar, 1u);
+    for (uint32_t k = 0; k < kRowsWarps; k++) mbar_init(smem_u32(smem + kRowsBarOff + 8u + 8u * k), 32u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_arrive_expect_tx(tbar, kRowsJsonBytes);
+    bulk_g2s(smem_u32(smem), kJsonT2, kRowsJsonBytes, tbar);
   }
   __syncthreads();
   const uint8_t* JT = smem;
-  const uint32_t bar = smem_u32(smem + kRowsBarOff + 8u * wid);
+  const uint32_t bar = smem_u32(smem + kRowsBarOff + 8u + 8u * wid);
   uint8_t* const slot = smem + kRowsSlotsOff + ((uint32_t)wid * 32u + (uint32_t)lane) * kRowsSlot;
   const uint32_t slot_s = smem_u32(slot);
   uint32_t parity = 0;
@@ -264,7 +321,25 @@ __global__ void __launch_bounds__(kRowsThreads, ETL_ROWS_CTAS) k_rows(DecodePara
     w.pos = old_first ? 36u : 35u;
     w.bits = (old_first ? W_OLD_HDR : W_NEW_HDR) | (kc << 3) | (oc << 5) | WB_EMIT;
   }
-  if (__ballot_sync(0xffffffffu, my_rec != 0xFFFFFFFFu) == 0) return;
+  const unsigned valid = __ballot_sync(0xffffffffu, my_rec != 0xFFFFFFFFu);
+  if (valid == 0) return;
+  // the warp's column kinds / flags: one schema per warp in a shape bin → a shared-memory copy (every step reads them);
+  // warps of a clamped bin (mixed schemas) and very wide tables read them from global memory
+  const uint8_t* kinds = P.col_kind + w.col_base;
+  const uint8_t* flags = P.col_flags + w.col_base;
+  {
+    const int first = __ffs(valid) - 1;
+    const uint32_t cb0 = __shfl_sync(0xffffffffu, w.col_base, first), nn0 = __shfl_sync(0xffffffffu, w.nc_ni, first);
+    const bool same = __all_sync(0xffffffffu, my_rec == 0xFFFFFFFFu || (w.col_base == cb0 && w.nc_ni == nn0));
+    const uint32_t nc0 = nn0 & 0xFFFFu;
+    if (same && nc0 <= kRowsColsCached) {
+      uint8_t* ck = smem + kRowsColsOff + (uint32_t)wid * 2u * kRowsColsCached;
+      for (uint32_t i = (uint32_t)lane; i < nc0; i += 32u) { ck[i] = P.col_kind[cb0 + i]; ck[kRowsColsCached + i] = P.col_flags[cb0 + i]; }
+      __syncwarp();
+      kinds = ck; flags = ck + kRowsColsCached;
+    }
+  }
+  mbar_wait(tbar, 0u);                                // kJsonT2 has landed
   RowWin W;
   W.win = slot; W.delta = 0x7FFFFFFF; W.w1 = 0;     // empty window: the first peek stages
   for (;;) {
@@ -292,7 +367,7 @@ __global__ void __launch_bounds__(kRowsThreads, ETL_ROWS_CTAS) k_rows(DecodePara
     }
     TextCell tc;
     tc.voff = 0; tc.len = 0; tc.kind = 0; tc.dest = 0; tc.seq = 0;
-    const uint32_t got = act ? rk_step(P, w, tc, hdr) : 0u;
+    const uint32_t got = act ? rk_step(P, w, tc, hdr, kinds, flags) : 0u;
     const bool is_text = got == 2u;
     if (!__any_sync(0xffffffffu, is_text)) continue;
     // ---- the text cells of this step: UTF-8 (event.rs:972), the per-kind parser, the cell plane and the heap
@@ -309,19 +384,21 @@ __global__ void __launch_bounds__(kRowsThreads, ETL_ROWS_CTAS) k_rows(DecodePara
       if (kind == ETL_K_STRING) { o.tag = ETL_CELL_STRING; o.val = soff; o.aux = len; }
       if (in_win) need_slow = has_high_bits(tv, len);
       else if (len >= (uint32_t)kCoopLen) {
-        // whole segments inside the cell hold no frame start: k_utf8_dead covers them, the rest is done here
+        // a long cell is read from global memory.  A text column (the TOAST case) needs nothing but its UTF-8 verdict:
+        // listed for k_long_cells, which runs after the join with enough warps to hide the latency.  Other kinds must
+        // be validated before they are parsed: whole warp, here.
+        const bool defer = kind == ETL_K_STRING;
         const uint64_t cb = soff + len;
         const uint64_t S0 = (soff + 3ull + P.anchor_stride - 1ull) & ~(uint64_t)(P.anchor_stride - 1u), S1 = cb & ~(uint64_t)(P.anchor_stride - 1u);
-        r0_hi = len;
-        if (S0 < S1) {
+        r0_hi = defer ? 0u : len;
+        if (defer || S0 < S1) {
           const uint32_t at = atomicAdd(P.long_count, 1u);
           if (at < P.long_cap) {
             LongCell lc;
-            lc.rec_local = w.rec_local; lc.seq = tc.seq;
-            lc.l0 = S0 >> 7; lc.l1 = S1 >> 7;
+            lc.rec_local = w.rec_local; lc.seq = tc.seq; lc.soff = soff; lc.len = len; lc.edges = defer ? 1u : 0u;
             P.long_cells[at] = lc;
-            r0_hi = (uint32_t)(S0 - soff); r1_lo = (uint32_t)(S1 - soff); r1_hi = len;
-          }
+            if (!defer) { r0_hi = (uint32_t)(S0 - soff); r1_lo = (uint32_t)(S1 - soff); r1_hi = len; }
+          } else r0_hi = len;                          // cannot happen (the list holds every cell of ≥ kCoopLen bytes)
         }
       } else if (utf8_medium_bad(tv, len)) code = ETL_E_UTF8;
     }
@@ -352,67 +429,26 @@ __global__ void __launch_bounds__(kRowsThreads, ETL_ROWS_CTAS) k_rows(DecodePara
     }
     const bool do_parse = is_text && !code && kind != ETL_K_STRING;
     const unsigned pm = __ballot_sync(0xffffffffu, do_parse);
+    // heap space of this step's numeric / bytea / uuid cells: one warp-wide exclusive scan, one atomic
+    uint64_t hpos = 0;
+    {
+      const bool heap_kind = do_parse && (kind == ETL_K_NUMERIC || kind == ETL_K_BYTES || kind == ETL_K_UUID);
+      if (__any_sync(0xffffffffu, heap_kind)) {
+        const uint32_t hb = heap_kind ? cell_heap_bound(kind, len) : 0u;
+        uint32_t inc = hb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t up = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += up; }
+        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+        unsigned long long hbase = 0;
+        if (lane == 0) hbase = atomicAdd(P.heap_top, (unsigned long long)total);
+        hbase = __shfl_sync(0xffffffffu, hbase, 0);
+        hpos = hbase + (inc - hb);
+      }
+    }
     if (do_parse) {
       // lanes of one shape bin hold the same column here; lanes of a clamped bin (more layouts than bins) may not
       const unsigned mask = __match_any_sync(pm, kind);
-      uint64_t hpos = 0;
-      const bool heap_kind = kind == ETL_K_NUMERIC || kind == ETL_K_BYTES || kind == ETL_K_UUID;  // uniform over `mask`
-      if (heap_kind) {                                 // warp-aggregated bump allocation
-        const uint32_t hb = cell_heap_bound(kind, len);
-        const unsigned below = mask & ((1u << lane) - 1u);
-        uint32_t mine_off = 0, total = 0;
-        for (unsigned mm = mask; mm; mm &= mm - 1) {   // lanes of `mask` run this loop together
-          const int src = __ffs(mm) - 1;
-          const uint32_t v = __shfl_sync(mask, hb, src);
-          if ((below >> src) & 1u) mine_off += v;
-          total += v;
-        }
-        unsigned long long hbase = 0;
-        const int leader = __ffs(mask) - 1;
-        if (lane == leader) hbase = atomicAdd(P.heap_top, (unsigned long long)total);
-        hbase = __shfl_sync(mask, hbase, leader);
-        hpos = hbase + mine_off;
-      }
-      // out-of-line parsers get their own CellOut so that `o` never has its address taken
-      int64_t iv = 0;
-      switch (kind) {
-        case ETL_K_I32: case ETL_K_I64: case ETL_K_I16: case ETL_K_U32: {   // one copy of the parser, limits by kind
-          const uint64_t pos_limit = kind == ETL_K_I32 ? 2147483647ull : (kind == ETL_K_I64 ? 9223372036854775807ull : (kind == ETL_K_I16 ? 32767ull : 4294967295ull));
-          const uint64_t neg_limit = kind == ETL_K_U32 ? 0ull : pos_limit + 1ull;
-          code = parse_int_sync(mask, tv, len, kind != ETL_K_U32, pos_limit, neg_limit, &iv);
-          o.tag = kind == ETL_K_I32 ? ETL_CELL_I32 : (kind == ETL_K_I64 ? ETL_CELL_I64 : (kind == ETL_K_I16 ? ETL_CELL_I16 : ETL_CELL_U32));
-          o.val = (uint64_t)iv;
-          break;
-        }
-        case ETL_K_NUMERIC: code = parse_numeric_sync(mask, tv, len, P.heap, hpos, o); break;
-        case ETL_K_JSON:
-          if (json_valid_sync(mask, tv, len, JT)) { o.tag = ETL_CELL_JSON; o.val = soff; o.aux = len; } else code = ETL_E_JSON;
-          break;
-        case ETL_K_TIMESTAMPTZ:
-          if (!fast_timestamptz(tv, len, o)) { CellOut tt; tt.tag = 0; tt.val = 0; tt.aux = 0; code = parse_text_cell(kind, tv, len, soff, P.heap, hpos, tt); o = tt; }
-          break;
-        case ETL_K_TIMESTAMP:
-          if (!fast_timestamp(tv, len, o)) { CellOut tt; tt.tag = 0; tt.val = 0; tt.aux = 0; code = parse_text_cell(kind, tv, len, soff, P.heap, hpos, tt); o = tt; }
-          break;
-        case ETL_K_DATE:
-          if (!fast_date(tv, len, o)) { CellOut tt; tt.tag = 0; tt.val = 0; tt.aux = 0; code = parse_text_cell(kind, tv, len, soff, P.heap, hpos, tt); o = tt; }
-          break;
-        case ETL_K_UUID:
-          if (!fast_uuid(tv, len, P.heap, hpos, o)) { CellOut tt; tt.tag = 0; tt.val = 0; tt.aux = 0; code = parse_text_cell(kind, tv, len, soff, P.heap, hpos, tt); o = tt; }
-          break;
-        case ETL_K_BOOL:                                  // bool.rs: exactly "t" / "f"
-          if (len == 1 && (tv[0] == 't' || tv[0] == 'f')) { o.tag = ETL_CELL_BOOL; o.val = tv[0] == 't'; } else code = ETL_E_BOOL;
-          break;
-        default: {
-          CellOut tt; tt.tag = 0; tt.val = 0; tt.aux = 0;
-          if (kind & ETL_K_ARRAY) {
-            code = parse_array_any(ArrHeap{P.heap, P.arr_top, P.arr_base, P.heap_cap}, kind, tv, len, tt);
-            if (code == 0xFFFFFFFEu) { atomicExch(P.heap_overflow, 1u); code = 0; tt.tag = ETL_CELL_NULL; }
-          } else code = parse_text_cell(kind, tv, len, soff, P.heap, hpos, tt);
-          o = tt;
-          break;
-        }
-      }
+      code = parse_cell_sync(mask, kind, tv, len, soff, CellHeaps{P.heap, P.arr_top, P.arr_base, P.heap_cap, P.heap_overflow}, hpos, JT, o);
     }
     if (is_text) {
       if (code) { report_error(P, P.dc->record_index_base + w.rec_local, tc.seq, code); w.bits &= ~WB_EMIT; }

@@ -35,7 +35,7 @@ namespace etl {
 constexpr int kIndexThreads = 256;
 constexpr int kMaxBins = 4096;         // 16 frame shapes x 256 schema versions (more versions share the last bins)
 
-struct LongCell { uint32_t rec_local, seq; uint64_t l0, l1; };   // lines [l0, l1) of the stream are interior to the cell
+struct LongCell { uint32_t rec_local, seq; uint64_t soff; uint32_t len, edges; };   // a text cell of ≥ kCoopLen bytes; edges: its head and tail are still to be validated
 
 // ---- stream-state transformer (apply.rs:600-626, 1927-2006) + counters; associative under fold()
 struct Summ {
@@ -618,12 +618,26 @@ __device__ __forceinline__ bool lines_any_bad(const uint32_t* bm, uint64_t l0, u
   }
   return false;
 }
-__global__ void __launch_bounds__(256) k_long_verdict(DecodeParams P) {
+// One warp per listed long cell, after the dead-segment pass has joined: the part of the cell that covers whole
+// dead segments is judged from the line bitmap; head and tail (up to a segment each) are validated here when k_rows
+// deferred them (text columns) — four 16-byte loads in flight per lane, enough warps to hide the latency.
+__global__ void __launch_bounds__(256) k_long_cells(DecodeParams P) {
   if (*P.abort_flag) return;
   const uint32_t n = min(*P.long_count, P.long_cap);
-  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+  const uint32_t lane = threadIdx.x & 31u, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n; e += nwarps) {
     const LongCell c = P.long_cells[e];
-    if (lines_any_bad(P.line_bad, c.l0, c.l1)) report_error(P, P.dc->record_index_base + c.rec_local, c.seq, ETL_E_UTF8);
+    const uint64_t cb = c.soff + c.len;
+    const uint64_t S0 = (c.soff + 3ull + P.anchor_stride - 1ull) & ~(uint64_t)(P.anchor_stride - 1u), S1 = cb & ~(uint64_t)(P.anchor_stride - 1u);
+    bool bad = false;
+    if (S0 < S1) {
+      if (lane == 0) bad = lines_any_bad(P.line_bad, S0 >> 7, S1 >> 7);
+      if (c.edges) {
+        bad |= utf8_range_bad(P.buf + c.soff, c.len, 0u, (uint32_t)(S0 - c.soff), lane, 32u);
+        bad |= utf8_range_bad(P.buf + c.soff, c.len, (uint32_t)(S1 - c.soff), c.len, lane, 32u);
+      }
+    } else if (c.edges) bad = utf8_range_bad(P.buf + c.soff, c.len, 0u, c.len, lane, 32u);
+    if (__any_sync(0xffffffffu, bad) && lane == 0) report_error(P, P.dc->record_index_base + c.rec_local, c.seq, ETL_E_UTF8);
   }
 }
 // out of line: cold (an oversize cell just below the warp-cooperative threshold)

@@ -17,6 +17,8 @@ template <typename T> static inline T min(T a, T b) { return a < b ? a : b; }
 template <typename T> static inline T max(T a, T b) { return a > b ? a : b; }
 static inline bool __any_sync(unsigned, bool p) { return p; }
 static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
+static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
+#define __align__(n) __attribute__((aligned(n)))
 static inline uint64_t __umul64hi(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31u)); }
 static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
@@ -73,7 +75,7 @@ extern "C" uint32_t emu_parse_cell(uint32_t kind, const uint8_t* text, uint32_t 
       }
       case ETL_K_NUMERIC: code = parse_numeric_sync(mask, s, n, heap, 0, o); break;
       case ETL_K_JSON:
-        if (json_valid_sync(mask, s, n, kJsonTables)) { o.tag = ETL_CELL_JSON; o.val = 0; o.aux = n; } else code = ETL_E_JSON;
+        if (json_valid_sync(mask, s, n, kJsonT2)) { o.tag = ETL_CELL_JSON; o.val = 0; o.aux = n; } else code = ETL_E_JSON;
         break;
       case ETL_K_TIMESTAMPTZ: if (!fast_timestamptz(s, n, o)) code = exact(kind, s, n, 0, hc, o); break;
       case ETL_K_TIMESTAMP: if (!fast_timestamp(s, n, o)) code = exact(kind, s, n, 0, hc, o); break;

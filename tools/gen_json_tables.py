@@ -242,6 +242,11 @@ def emit(path: str):
         f.write("enum : uint32_t { JA_NONE = 0, JA_PUSH_OBJ, JA_PUSH_ARR, JA_POP_OBJ, JA_POP_ARR, JA_COMMA, JA_KEYSTR, JA_VALSTR };\n")
         f.write("// [0,256): class of each byte; [256, 256 + 32*kJsonClasses): next state | action << 5\n")
         f.write("__device__ const uint8_t kJsonTables[256 + 32 * kJsonClasses] = {\n    " + rows(CLS + TRANS, 32) + "};\n")
+        # the same transitions with the class lookup folded in: one load per byte instead of two dependent ones.
+        # 32 states x 256 bytes; k_rows brings it into shared memory with one bulk copy per CTA.
+        t2 = [TRANS[st * NCLS + CLS[b]] for st in range(32) for b in range(256)]
+        f.write("// [state << 8 | byte]: next state | action << 5 (class lookup folded in)\n")
+        f.write("__device__ __align__(16) const uint8_t kJsonT2[32 * 256] = {\n    " + rows(t2, 64) + "};\n")
         f.write("}  // namespace etl\n")
 
 
