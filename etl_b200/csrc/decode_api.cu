@@ -521,7 +521,8 @@ void etl_dec_batch_free(etl_dec_batch* b) {
 }
 
 // Where the structure-blind UTF-8 pass (k_utf8_dead, HBM-bound) runs relative to the latency-bound passes.
-// 1: side stream from the start of the tuple pass (default); 2: main stream after the tuple pass.
+// 0: side stream from the start of the index pass; 1: side stream from the start of the tuple pass (default);
+// 2: main stream after the tuple pass.
 // ETL_DEAD_MODE / ETL_DEAD_CTAS are tuning knobs for measurement, not part of the ABI.
 static int dead_mode() {
   static const int m = getenv("ETL_DEAD_MODE") ? atoi(getenv("ETL_DEAD_MODE")) : 1;
@@ -804,6 +805,7 @@ static int launch_index(etl_dec_ctx* ctx) {
     k_act_count<<<act_blocks, kActThreads, 0, st>>>(P);
     k_act_scan<<<1, kActThreads, 0, st>>>(P, act_blocks);
     k_act_scatter<<<act_blocks, kActThreads, 0, st>>>(P);
+    if (dead_mode() == 0) CK(launch_dead_side(ctx, st));   // underneath everything that follows (needs only the dead-segment list)
     k_index<<<P.n_groups, P.tiles_per_group * P.segs_per_tile, 0, st>>>(P);
     k_scan<<<1, 512, 0, st>>>(P);
     k_tile_prefix<<<(P.n_tiles + 255) / 256, 256, 0, st>>>(P);
