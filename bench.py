@@ -441,6 +441,78 @@ def batch_leg(torch, dev, name, scale, calls, stride):
     return out
 
 
+def copy_leg(torch, dev, n_rows, steps):
+    """Initial-sync COPY rows: a 10-column int4 + text table (the C2 shape) as COPY text, decoded by
+    etl_dec_copy_decode with the buffer resident in HBM; rows/s next to the 1-thread CPU port and parity by digest.
+    The reference's own figure for its copy phase (87 738 rows/s end to end, etl-benchmarks/README.md:302-308) includes
+    the network read and the destination write — context only."""
+    from etl_b200 import abi, decoder
+    from oracle import pyoracle
+    rng = np.random.default_rng(0xC0B7)
+    ints = rng.integers(-2**31, 2**31, size=(n_rows, 5))
+    lens = np.minimum(256, np.maximum(1, np.exp(np.log(16) + 0.8 * rng.standard_normal((n_rows, 5))).astype(np.int64)))
+    alnum = np.frombuffer(b"abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789      ", dtype=np.uint8)
+    pool = alnum[rng.integers(0, len(alnum), size=1 << 20)].tobytes()
+    starts = rng.integers(0, (1 << 20) - 256, size=(n_rows, 5))
+    nulls = rng.integers(0, 20, size=(n_rows, 9)) == 0
+    rows = []
+    for r in range(n_rows):
+        f = [str(ints[r, 0])]
+        for c in range(1, 5):
+            f.append("\\N" if nulls[r, c - 1] else str(ints[r, c]))
+        for c in range(5):
+            f.append("\\N" if nulls[r, 4 + c] else pool[starts[r, c]:starts[r, c] + lens[r, c]].decode())
+        rows.append("\t".join(f))
+    blob = ("\n".join(rows) + "\n").encode()
+    buf = np.frombuffer(blob, dtype=np.uint8)
+    offs = np.zeros(n_rows + 1, dtype=np.uint64)
+    offs[1:] = np.flatnonzero(buf == 10) + 1
+    oids = [23] * 5 + [25] * 5
+    cols = [dict(name=f"c{i}", type_oid=o, pk=1 if i == 0 else None, nullable=i != 0) for i, o in enumerate(oids)]
+    dec = decoder.Decoder(dev.index, stream=torch.cuda.current_stream().cuda_stream)
+    dec.put_table_schema(9, cols)
+    d_buf = torch.zeros(buf.nbytes + 64, dtype=torch.uint8, device=dev)
+    d_buf[:buf.nbytes].copy_(torch.from_numpy(buf.copy()))
+    d_off = torch.from_numpy(offs.view(np.int64).copy()).to(dev)
+    lib = abi.load()
+
+    def once(to_host):
+        inp = abi.CopyInput()
+        inp.dev_buf, inp.dev_row_offsets, inp.len, inp.n_rows = d_buf.data_ptr(), d_off.data_ptr(), buf.nbytes, n_rows
+        inp.row_offsets = offs.ctypes.data
+        h = C.c_void_p()
+        rc = lib.etl_dec_copy_decode(dec._ctx, 9, C.byref(inp), abi.RESULTS_TO_HOST if to_host else 0, C.byref(h))
+        if rc:
+            raise RuntimeError(lib.etl_dec_last_error(dec._ctx).decode())
+        return decoder.BatchHandle(dec, h)
+
+    for _ in range(3):
+        once(False).free()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        once(False).free()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    bh = once(True)
+    p, s = bh.planes(True), bh.summary()
+    m = int(p.n_cells)
+    got = pyoracle.copy_planes_digest(decoder._np_from(p.cell_tag, m, np.uint8), decoder._np_from(p.cell_val, m, np.uint64),
+                                      decoder._np_from(p.cell_aux, m, np.uint32), n_rows, len(oids), buf, decoder._np_from(p.heap, p.heap_bytes, np.uint8))
+    clean = s.first_error.record_index == NO_ERROR
+    bh.free()
+    dec.close()
+    t0 = time.perf_counter()
+    want, err = pyoracle.copy_rows_digest(oids, buf, offs)
+    cpu_s = time.perf_counter() - t0
+    return {"table": "10 columns (5 x int4, 5 x text, 5 % NULL), COPY text", "rows": n_rows, "bytes": int(buf.nbytes), "ms_per_step": ms,
+            "rows_per_s": n_rows / (ms * 1e-3), "GBps": buf.nbytes / (ms * 1e-3) / 1e9,
+            "cpu_port_1thread_rows_per_s": n_rows / cpu_s, "parity": "bit-exact (every cell, strings by content)" if (clean and err is None and got == want) else "MISMATCH",
+            "reference_context": "87 738 rows/s end to end on other hardware (etl-benchmarks/README.md:302-308), incl. network and destination"}
+
+
 def measure_workload(torch, dev, name, scale, steps, warmup, stride, threads, cpu_budget_s=6.0):
     """One of the other BASELINE configs on one GPU: value, e2e, roofline, 1-thread CPU port, parity at size."""
     from etl_b200 import decoder, workloads as wl
@@ -626,7 +698,11 @@ def main():
                 batches[name] = batch_leg(torch, dev, name, min(1.0, args.extras_scale) * (1.0 if name == "c2" else 0.1), args.batch_calls, args.stride)
             except Exception as e:  # noqa: BLE001
                 batches[name] = {"error": f"{type(e).__name__}: {e}"}
-        extras = {"parity": parity, "workloads": workloads, "batch_8MiB": batches}
+        try:
+            copy = copy_leg(torch, dev, int(1_000_000 * min(1.0, args.extras_scale)), args.steps)
+        except Exception as e:  # noqa: BLE001
+            copy = {"error": f"{type(e).__name__}: {e}"}
+        extras = {"parity": parity, "workloads": workloads, "batch_8MiB": batches, "copy_rows": copy}
 
     if rank == 0:
         line = {

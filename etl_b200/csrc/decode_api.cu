@@ -153,7 +153,7 @@ NcclApi& nccl_api() {
 
 constexpr size_t kScalarWords = 16;
 // device scalar block: 16 words followed by the DevCarry
-//  [0] first_error key  [1..3] insert/update/delete bytes  [4] events  [5] heap_top  [7] long_count  [9] heap_overflow
+//  [0] first_error key  [1..3] insert/update/delete bytes  [4] events  [5] heap_top  [7] long_count  [8] copy_count  [9] heap_overflow
 //  [10] arr_top  [11] perm_len  [12] n_act (k_act_scan)  [13] abort flag (k_scan)
 constexpr size_t kScalarBlockBytes = kScalarWords * 8 + sizeof(DevCarry);
 
@@ -375,6 +375,7 @@ int etl_dec_create(int device_id, etl_dec_ctx** out) {
   ok = ok && cudaHostAlloc((void**)&ctx->h_scalars, kScalarBlockBytes, cudaHostAllocDefault) == cudaSuccess;
   ok = ok && ctx->d_scalars.ensure(kScalarBlockBytes) == cudaSuccess && ctx->d_total.ensure(1) == cudaSuccess;
   if (ok) ok = cudaFuncSetAttribute(k_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmemBytes) == cudaSuccess;
+  if (ok) ok = cudaFuncSetAttribute(k_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeavySmemBytes) == cudaSuccess;
   if (!ok) { cudaGetLastError(); ctx_release(ctx); return ETL_ERR_CUDA; }
   // batch planes come from the stream-ordered pool: keep freed blocks for the next batch instead of returning them to the OS
   cudaMemPool_t pool;
@@ -767,6 +768,7 @@ static int prepare(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t flags, bo
   P.first_error = sc; P.metrics = sc + 1;
   P.heap_top = sc + 5; P.heap_overflow = (unsigned int*)(sc + 9); P.arr_top = sc + 10;
   P.perm_len = (unsigned int*)(sc + 11); P.n_act = (unsigned int*)(sc + 12); P.abort_flag = (unsigned int*)(sc + 13);
+  P.copy_count = (unsigned int*)(sc + 8);
   P.dc = reinterpret_cast<const DevCarry*>(sc + kScalarWords); P.dc_out = reinterpret_cast<DevCarry*>(sc + kScalarWords);
   const uint32_t act_blocks = (P.n_anchors + kActThreads - 1) / kActThreads;
   CK(ctx->d_act.ensure(P.n_anchors + 1)); CK(ctx->d_act_blk.ensure(act_blocks + 1));
@@ -888,7 +890,9 @@ static int launch_emit_kernels(etl_dec_ctx* ctx) {
       cudaEventRecord(ctx->evk[2], st);
       const uint32_t chunks = (uint32_t)((perm_cap + kRowsThreads - 1) / kRowsThreads);
       k_rows<<<((chunks + 63u) / 64u) * 64u, kRowsThreads, kRowsSmemBytes, st>>>(P);
-      ctx->launches += 3;
+      k_heavy<<<std::min<uint32_t>((uint32_t)((P.cap_cells + kHeavyTile - 1) / kHeavyTile) + 1u, (uint32_t)sm_count(ctx) * 3u), kHeavyThreads, kHeavySmemBytes, st>>>(P);
+      k_fix<<<sm_count(ctx) * 2, 256, 0, st>>>(P);
+      ctx->launches += 5;
     } else cudaEventRecord(ctx->evk[2], st);
     cudaEventRecord(ctx->evk[1], st);
     if (ctx->lines_launched) CK(cudaStreamWaitEvent(st, ctx->ev_l1, 0));   // join: the bitmap is complete
@@ -1138,6 +1142,147 @@ int etl_dec_decode_finish(etl_dec_ctx* ctx, const etl_stream_state* carry_in, ui
   ctx->pending = false;
   CK(cudaSetDevice(ctx->device));
   return run_decode(ctx, carry_in, record_index_base, false, true, out);
+}
+
+// ---------------------------------------------------------------- COPY rows (table_row.rs:25-165 for a buffer of rows)
+int etl_dec_copy_decode(etl_dec_ctx* ctx, uint32_t table_id, const etl_copy_input* in, uint32_t flags, etl_dec_batch** out) {
+  if (!ctx || !in || !out) return ETL_ERR_INVALID_ARG;
+  if (in->len && !in->host_buf && !in->dev_buf) { ctx->last_error = "no input buffer"; return ETL_ERR_INVALID_ARG; }
+  if (in->dev_buf && (reinterpret_cast<uintptr_t>(in->dev_buf) & 15u)) { ctx->last_error = "dev_buf must be 16-byte aligned"; return ETL_ERR_INVALID_ARG; }
+  if (in->n_rows && !in->row_offsets && !in->dev_row_offsets) { ctx->last_error = "row_offsets missing"; return ETL_ERR_INVALID_ARG; }
+  if (in->n_rows >= (1ull << 32)) { ctx->last_error = "a COPY batch is limited to 2^32 rows"; return ETL_ERR_INVALID_ARG; }
+  auto it = ctx->tables.find(table_id);
+  if (it == ctx->tables.end()) { ctx->last_error = "table schema not stored"; return ETL_ERR_INVALID_ARG; }
+  const StoredTable& t = it->second;
+  const uint32_t n_cols = (uint32_t)t.cols.size();
+  std::vector<uint8_t> kinds(n_cols);
+  bool any_heap = false, any_array = false;
+  for (uint32_t i = 0; i < n_cols; i++) {
+    const uint32_t k = etl_oid_decode_class(t.cols[i].type_oid);
+    if (!kind_supported_on_device(k)) { ctx->last_error = "column decode class has no device parser"; return ETL_ERR_INVALID_ARG; }
+    kinds[i] = (uint8_t)k;
+    any_heap = any_heap || kind_has_heap(k); any_array = any_array || (k & ETL_K_ARRAY);
+  }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  ctx->launches = 0;
+  ctx->tables_valid = false;                          // d_tables is reused for the column classes
+  etl_dec_batch* b = new etl_dec_batch();
+  b->ctx = ctx;
+  auto fail = [&](int rc) { if (b->dev_block) cudaFreeAsync(b->dev_block, st); delete b; return rc; };
+#define CKB(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->last_error = std::string(#call) + ": " + cudaGetErrorString(_e); return fail(ETL_ERR_CUDA); } } while (0)
+  DecodeParams& P = ctx->P;
+  memset(&P, 0, sizeof P);
+  P.len = in->len; P.anchor_stride = 2048; P.copy_cols = n_cols;
+  CKB(cudaEventRecord(ctx->ev[0], st));
+  uint64_t h2d = 0;
+  if (in->dev_buf) P.buf = in->dev_buf;
+  else {
+    CKB(ctx->d_stream.ensure(in->len + 64));
+    if (in->len) CKB(cudaMemcpyAsync(ctx->d_stream.ptr(), in->host_buf, in->len, cudaMemcpyHostToDevice, st));
+    CKB(cudaMemsetAsync(ctx->d_stream.ptr() + in->len, 0, 64, st));
+    P.buf = ctx->d_stream.ptr(); h2d += in->len;
+  }
+  const uint64_t nr = in->n_rows, nc = nr * n_cols;
+  // planes: rec_off (row offsets) + cells + heap (unescaped text ≤ len, scalar payloads, arrays)
+  uint64_t nh = in->len + 64 + (any_heap ? in->len / 2 + 24 * nc + 256 : 0);
+  nh = (nh + 15) & ~15ull;
+  const uint64_t scalar_heap = nh;
+  uint64_t array_heap = any_array ? 3 * in->len + 4096 : 0;
+  for (int attempt = 0;; attempt++) {
+    const uint64_t heap_total = scalar_heap + array_heap;
+    const PlaneLayout L = plane_layout(nr, nc, heap_total);
+    if (b->dev_block) { CKB(cudaFreeAsync(b->dev_block, st)); b->dev_block = nullptr; }
+    b->block_bytes = L.total;
+    CKB(cudaMallocAsync(&b->dev_block, b->block_bytes, st));
+    fill_planes(b->dev, (uint8_t*)b->dev_block, L, nr, nc, heap_total);
+    uint64_t* d_rows = (uint64_t*)b->dev.rec_cell_base;             // the (n_rows + 1)-entry plane holds the row offsets
+    if (in->dev_row_offsets) CKB(cudaMemcpyAsync(d_rows, in->dev_row_offsets, (nr + 1) * 8, cudaMemcpyDeviceToDevice, st));
+    else if (nr) { CKB(cudaMemcpyAsync(d_rows, in->row_offsets, (nr + 1) * 8, cudaMemcpyHostToDevice, st)); h2d += (nr + 1) * 8; }
+    else CKB(cudaMemsetAsync(d_rows, 0, 8, st));
+    b->dev.rec_off = d_rows;
+    b->dev.rec_kind = nullptr; b->dev.rec_flags = nullptr; b->dev.rec_rel = nullptr; b->dev.rec_schema = nullptr; b->dev.rec_start_lsn = nullptr;
+    b->dev.rec_commit_lsn = nullptr; b->dev.rec_tx_ordinal = nullptr; b->dev.rec_tuple_bytes = nullptr; b->dev.rec_heap_hint = nullptr;
+    P.rec_off = d_rows; P.rec_cell_base = d_rows;
+    P.cell_tag = (uint8_t*)b->dev.cell_tag; P.cell_val = (uint64_t*)b->dev.cell_val; P.cell_aux = (uint32_t*)b->dev.cell_aux; P.heap = (uint8_t*)b->dev.heap;
+    P.heap_cap = heap_total; P.arr_base = scalar_heap;
+    CKB(ctx->d_tables.ensure(n_cols + 16));
+    if (int rc = ensure_pinned(ctx, &ctx->h_up, &ctx->h_up_cap, n_cols + 16)) return fail(rc);
+    memcpy(ctx->h_up, kinds.data(), n_cols);
+    if (n_cols) CKB(cudaMemcpyAsync(ctx->d_tables.ptr(), ctx->h_up, n_cols, cudaMemcpyHostToDevice, st));
+    P.col_kind = ctx->d_tables.ptr(); P.col_flags = ctx->d_tables.ptr();
+    unsigned long long* sc = reinterpret_cast<unsigned long long*>(ctx->d_scalars.ptr());
+    P.first_error = sc; P.metrics = sc + 1; P.heap_top = sc + 5; P.long_count = (unsigned int*)(sc + 7); P.copy_count = (unsigned int*)(sc + 8);
+    P.heap_overflow = (unsigned int*)(sc + 9); P.arr_top = sc + 10; P.perm_len = (unsigned int*)(sc + 11); P.n_act = (unsigned int*)(sc + 12);
+    P.abort_flag = (unsigned int*)(sc + 13);
+    P.dc = reinterpret_cast<const DevCarry*>(sc + kScalarWords); P.dc_out = reinterpret_cast<DevCarry*>(sc + kScalarWords);
+    P.total = ctx->d_total.ptr();
+    DevCarry dc; dc.carry = summ_identity(); dc.record_index_base = 0;
+    if (int rc = upload_scalars(ctx, 0, kScalarWords, &dc)) return fail(rc);
+    Summ T = summ_identity(); T.n_rec = (uint32_t)nr; T.n_cells = nc;
+    *ctx->h_total = T;
+    CKB(cudaMemcpyAsync(P.total, ctx->h_total, sizeof(Summ), cudaMemcpyHostToDevice, st));
+    P.cap_records = nr; P.cap_cells = nc;
+    CKB(cudaEventRecord(ctx->ev[1], st));
+    if (nr) {
+      k_copy_rows<<<(uint32_t)((nr + kRowsThreads - 1) / kRowsThreads), kRowsThreads, kRowsSmemBytes, st>>>(P);
+      k_heavy<<<std::min<uint32_t>((uint32_t)((nc + kHeavyTile - 1) / kHeavyTile) + 1u, (uint32_t)sm_count(ctx) * 3u), kHeavyThreads, kHeavySmemBytes, st>>>(P);
+      ctx->launches += 2;
+      CKB(cudaGetLastError());
+    }
+    CKB(cudaEventRecord(ctx->ev[4], st));
+    CKB(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars.ptr(), kScalarWords * 8, cudaMemcpyDeviceToHost, st));
+    CKB(cudaStreamSynchronize(st));
+    if (!ctx->h_scalars[9]) break;
+    if (attempt >= 4) { ctx->last_error = "array heap reservation overflow after retries"; return fail(ETL_ERR_CUDA); }
+    array_heap *= 4;
+  }
+  const uint64_t heap_used = std::min<uint64_t>(P.heap_cap, ctx->h_scalars[10] ? scalar_heap + ctx->h_scalars[10] : ctx->h_scalars[5]);
+  b->dev.heap_bytes = heap_used;
+  uint64_t d2h = kScalarWords * 8;
+  if (flags & ETL_DECODE_RESULTS_TO_HOST) {
+    const PlaneLayout H = plane_layout(nr, nc, heap_used);
+    if (ctx->h_result_cap < H.total) {
+      if (ctx->h_result) cudaFreeHost(ctx->h_result);
+      ctx->h_result = nullptr; ctx->h_result_cap = 0;
+      size_t want = H.total + H.total / 8;
+      CKB(cudaHostAlloc(&ctx->h_result, want, cudaHostAllocDefault));
+      ctx->h_result_cap = want;
+    }
+    uint8_t* hb = (uint8_t*)ctx->h_result;
+    fill_planes(b->host, hb, H, nr, nc, heap_used);
+    b->host.rec_off = b->host.rec_cell_base;
+    b->host.rec_kind = nullptr; b->host.rec_flags = nullptr; b->host.rec_rel = nullptr; b->host.rec_schema = nullptr; b->host.rec_start_lsn = nullptr;
+    b->host.rec_commit_lsn = nullptr; b->host.rec_tx_ordinal = nullptr; b->host.rec_tuple_bytes = nullptr; b->host.rec_heap_hint = nullptr;
+    CKB(cudaMemcpyAsync((void*)b->host.rec_cell_base, b->dev.rec_cell_base, (nr + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (nc) {
+      CKB(cudaMemcpyAsync((void*)b->host.cell_tag, b->dev.cell_tag, nc, cudaMemcpyDeviceToHost, st));
+      CKB(cudaMemcpyAsync((void*)b->host.cell_val, b->dev.cell_val, nc * 8, cudaMemcpyDeviceToHost, st));
+      CKB(cudaMemcpyAsync((void*)b->host.cell_aux, b->dev.cell_aux, nc * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (heap_used) CKB(cudaMemcpyAsync((void*)b->host.heap, b->dev.heap, heap_used, cudaMemcpyDeviceToHost, st));
+    d2h += (nr + 1) * 8 + nc * 13 + heap_used;
+    b->host_block = hb; b->has_host = true;
+  }
+  CKB(cudaEventRecord(ctx->ev[5], st));
+  CKB(cudaStreamSynchronize(st));
+  etl_dec_summary& S = b->summary;
+  memset(&S, 0, sizeof S);
+  cudaEventElapsedTime(&S.h2d_ms, ctx->ev[0], ctx->ev[1]);
+  cudaEventElapsedTime(&S.emit_ms, ctx->ev[1], ctx->ev[4]);
+  cudaEventElapsedTime(&S.d2h_ms, ctx->ev[4], ctx->ev[5]);
+  S.kernel_ms = S.emit_ms; S.cells_ms = S.emit_ms;
+  S.h2d_bytes = h2d; S.d2h_bytes = d2h; S.gpu_launches = ctx->launches; S.abi_version = ETL_DECODE_ABI_VERSION;
+  const unsigned long long key = ctx->h_scalars[0];
+  if (key == ~0ull) S.first_error.record_index = UINT64_MAX;
+  else {
+    S.first_error.record_index = key >> 24; S.first_error.seq = (uint32_t)((key >> 6) & 0x3FFFFu);
+    S.first_error.code = (uint32_t)(key & 63u); S.first_error.kind = error_kind_of(S.first_error.code);
+  }
+  S.n_events = nr;
+  *out = b;
+  return ETL_OK;
+#undef CKB
 }
 
 int etl_dec_batch_planes(const etl_dec_batch* b, int host, etl_dec_planes* out) {

@@ -7,6 +7,14 @@
 //            the whole warp on bytes that sit in shared memory.  The cell-header hop chain and the value bytes
 //            are read from HBM exactly once (by the copy engine); there is no descriptor round trip, and an
 //            unchanged-TOAST cell takes the value the same lane decoded for the old image a few steps earlier.
+//            k_rows itself parses the LIGHT decode classes (text, bool, integers, date / timestamp(tz), uuid in the
+//            spellings Postgres emits): ~100 registers, no stack, 20+ warps per SM.  Every other cell (json, numeric,
+//            floats, bytea, time, arrays, and any spelling the fast paths decline) is left in the cell plane as a
+//            PENDING placeholder {kind, record, frame offset, length}.
+//   k_heavy  second pass over the cell plane: a CTA takes a tile of 4096 cells, gathers the pending ones per decode
+//            class in shared memory and parses them 32 at a time (one class per warp row, so the warp-synchronous
+//            parsers run full width), each lane's bytes staged from global memory with all its 16-byte loads in flight.
+//   k_fix    resolves unchanged-TOAST cells whose source was still pending when k_rows met them.
 //
 // Reference semantics: event.rs:376-979 (tuples → rows), text.rs:28-173 (cells), event.rs:260-270 (tuple bytes),
 // types/table_row.rs + types/event.rs:288-312 (size hints).
@@ -15,10 +23,10 @@
 namespace etl {
 
 #ifndef ETL_ROWS_WIN
-#define ETL_ROWS_WIN 480                 // bytes of one record's frame staged per pass (multiple of 16)
+#define ETL_ROWS_WIN 304                 // bytes of one record's frame staged per pass (multiple of 16)
 #endif
 #ifndef ETL_ROWS_CTAS
-#define ETL_ROWS_CTAS 3                  // resident CTAs per SM the register budget is set for
+#define ETL_ROWS_CTAS 5                  // resident CTAs per SM the register budget is set for
 #endif
 #ifndef ETL_ROWS_WARPS
 #define ETL_ROWS_WARPS 4
@@ -27,8 +35,7 @@ constexpr uint32_t kRowsWarps = ETL_ROWS_WARPS;
 constexpr uint32_t kRowsThreads = kRowsWarps * 32;
 constexpr uint32_t kRowsWin = ETL_ROWS_WIN;
 constexpr uint32_t kRowsSlot = kRowsWin + 16;                      // slot stride: 16-byte aligned, skews the banks
-constexpr uint32_t kRowsJsonBytes = 32 * 256;                      // kJsonT2, brought in by one bulk copy per CTA
-constexpr uint32_t kRowsBarOff = kRowsJsonBytes;                   // [0] the CTA's table barrier, [1 ..] one mbarrier per warp
+constexpr uint32_t kRowsBarOff = 0;                                // one mbarrier per warp
 constexpr uint32_t kRowsColsOff = kRowsBarOff + 128;               // per warp: 256 column kinds + 256 column flags of its schema
 constexpr uint32_t kRowsColsCached = 256;
 constexpr uint32_t kRowsSlotsOff = kRowsColsOff + kRowsWarps * 2 * kRowsColsCached;
@@ -64,52 +71,53 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// text.rs:28-173 for the lanes of `mask` (same decode class): the warp-synchronous fast paths for the spellings
-// Postgres emits, the exact out-of-line parsers for everything else.  `soff` = where a zero-copy span (json) points;
-// `hpos` = this lane's reservation in the scalar heap.  Shared by k_rows (WAL tuples) and k_copy_rows (COPY rows).
-struct CellHeaps { uint8_t* heap; unsigned long long* arr_top; uint64_t arr_base, heap_cap; unsigned int* heap_overflow; };
-__device__ __forceinline__ uint32_t parse_cell_sync(unsigned mask, uint32_t kind, const uint8_t* tv, uint32_t len, uint64_t soff,
-                                                    const CellHeaps H, uint64_t hpos, const uint8_t* JT, CellOut& o) {
-  uint32_t code = 0;
-  int64_t iv = 0;
-  // out-of-line parsers get their own CellOut so that `o` never has its address taken
+// Cells k_rows leaves for k_heavy: tag = ETL_CELL_PENDING | decode class (ETL_K_*, 6 bits), val = record << 32 | offset
+// of the value bytes inside the record's frame, aux = length.  ETL_CELL_PENDING_COPY: an unchanged-TOAST cell whose
+// source (val = its cell index, aux = record) was itself pending.  Internal: no placeholder survives a decode.
+constexpr uint32_t ETL_CELL_PENDING = 0x80u, ETL_CELL_PENDING_MASK = 0xC0u, ETL_CELL_PENDING_COPY = 0xF0u;
+__device__ __forceinline__ bool kind_is_light(uint32_t kind) {
+  return kind == ETL_K_STRING || kind == ETL_K_BOOL || (kind - ETL_K_I16) <= (ETL_K_I64 - ETL_K_I16) || kind == ETL_K_DATE ||
+         kind == ETL_K_TIMESTAMP || kind == ETL_K_TIMESTAMPTZ || kind == ETL_K_UUID;
+}
+// text.rs:28-173, the light classes, for the lanes of `mask` (same class): warp-synchronous / SWAR fast paths for the
+// spellings Postgres emits.  Returns 0 (o filled), an error code, or 0xFFFFFFFF = "not this spelling": the cell is
+// left to k_heavy's exact parsers.  `hpos` = this lane's 16 bytes in the heap (uuid).
+__device__ __forceinline__ uint32_t parse_light_sync(unsigned mask, uint32_t kind, const uint8_t* tv, uint32_t len, uint8_t* heap, uint64_t hpos, CellOut& o) {
   switch (kind) {
     case ETL_K_I32: case ETL_K_I64: case ETL_K_I16: case ETL_K_U32: {   // one copy of the parser, limits by kind
       const uint64_t pos_limit = kind == ETL_K_I32 ? 2147483647ull : (kind == ETL_K_I64 ? 9223372036854775807ull : (kind == ETL_K_I16 ? 32767ull : 4294967295ull));
       const uint64_t neg_limit = kind == ETL_K_U32 ? 0ull : pos_limit + 1ull;
-      code = parse_int_sync(mask, tv, len, kind != ETL_K_U32, pos_limit, neg_limit, &iv);
+      int64_t iv = 0;
+      const uint32_t code = parse_int_sync(mask, tv, len, kind != ETL_K_U32, pos_limit, neg_limit, &iv);
       o.tag = kind == ETL_K_I32 ? ETL_CELL_I32 : (kind == ETL_K_I64 ? ETL_CELL_I64 : (kind == ETL_K_I16 ? ETL_CELL_I16 : ETL_CELL_U32));
       o.val = (uint64_t)iv;
-      break;
+      return code;
     }
-    case ETL_K_NUMERIC: code = parse_numeric_sync(mask, tv, len, H.heap, hpos, o); break;
-    case ETL_K_JSON:
-      if (json_valid_sync(mask, tv, len, JT)) { o.tag = ETL_CELL_JSON; o.val = soff; o.aux = len; } else code = ETL_E_JSON;
-      break;
-    case ETL_K_TIMESTAMPTZ:
-      if (!fast_timestamptz(tv, len, o)) { CellOut tt; tt.tag = 0; tt.val = 0; tt.aux = 0; code = parse_text_cell(kind, tv, len, soff, H.heap, hpos, tt); o = tt; }
-      break;
-    case ETL_K_TIMESTAMP:
-      if (!fast_timestamp(tv, len, o)) { CellOut tt; tt.tag = 0; tt.val = 0; tt.aux = 0; code = parse_text_cell(kind, tv, len, soff, H.heap, hpos, tt); o = tt; }
-      break;
-    case ETL_K_DATE:
-      if (!fast_date(tv, len, o)) { CellOut tt; tt.tag = 0; tt.val = 0; tt.aux = 0; code = parse_text_cell(kind, tv, len, soff, H.heap, hpos, tt); o = tt; }
-      break;
-    case ETL_K_UUID:
-      if (!fast_uuid(tv, len, H.heap, hpos, o)) { CellOut tt; tt.tag = 0; tt.val = 0; tt.aux = 0; code = parse_text_cell(kind, tv, len, soff, H.heap, hpos, tt); o = tt; }
-      break;
+    case ETL_K_TIMESTAMPTZ: return fast_timestamptz(tv, len, o) ? 0u : 0xFFFFFFFFu;
+    case ETL_K_TIMESTAMP: return fast_timestamp(tv, len, o) ? 0u : 0xFFFFFFFFu;
+    case ETL_K_DATE: return fast_date(tv, len, o) ? 0u : 0xFFFFFFFFu;
+    case ETL_K_UUID: return fast_uuid(tv, len, heap, hpos, o) ? 0u : 0xFFFFFFFFu;
     case ETL_K_BOOL:                                  // bool.rs: exactly "t" / "f"
-      if (len == 1 && (tv[0] == 't' || tv[0] == 'f')) { o.tag = ETL_CELL_BOOL; o.val = tv[0] == 't'; } else code = ETL_E_BOOL;
-      break;
-    default: {
-      CellOut tt; tt.tag = 0; tt.val = 0; tt.aux = 0;
-      if (kind & ETL_K_ARRAY) {
-        code = parse_array_any(ArrHeap{H.heap, H.arr_top, H.arr_base, H.heap_cap}, kind, tv, len, tt);
-        if (code == 0xFFFFFFFEu) { atomicExch(H.heap_overflow, 1u); code = 0; tt.tag = ETL_CELL_NULL; }
-      } else code = parse_text_cell(kind, tv, len, soff, H.heap, hpos, tt);
-      o = tt;
-      break;
-    }
+      if (len == 1 && (tv[0] == 't' || tv[0] == 'f')) { o.tag = ETL_CELL_BOOL; o.val = tv[0] == 't'; return 0u; }
+      return ETL_E_BOOL;
+    default: return 0xFFFFFFFFu;
+  }
+}
+// ... and every class, exactly, for k_heavy (the exact parsers are out of line; json / numeric have warp-synchronous paths)
+struct CellHeaps { uint8_t* heap; unsigned long long* arr_top; uint64_t arr_base, heap_cap; unsigned int* heap_overflow; };
+__device__ __forceinline__ uint32_t parse_heavy_sync(unsigned mask, uint32_t kind, const uint8_t* tv, uint32_t len, uint64_t soff,
+                                                     const CellHeaps H, uint64_t hpos, const uint8_t* JT, CellOut& o) {
+  uint32_t code = 0;
+  if (kind == ETL_K_JSON) {
+    if (json_valid_sync(mask, tv, len, JT)) { o.tag = ETL_CELL_JSON; o.val = soff; o.aux = len; } else code = ETL_E_JSON;
+  } else if (kind == ETL_K_NUMERIC) code = parse_numeric_sync(mask, tv, len, H.heap, hpos, o);
+  else {
+    CellOut tt; tt.tag = 0; tt.val = 0; tt.aux = 0;     // out-of-line parsers get their own CellOut so that `o` never has its address taken
+    if (kind & ETL_K_ARRAY) {
+      code = parse_array_any(ArrHeap{H.heap, H.arr_top, H.arr_base, H.heap_cap}, kind, tv, len, tt);
+      if (code == 0xFFFFFFFEu) { atomicExch(H.heap_overflow, 1u); code = 0; tt.tag = ETL_CELL_NULL; }
+    } else code = parse_text_cell(kind, tv, len, soff, H.heap, hpos, tt);
+    o = tt;
   }
   return code;
 }
@@ -260,8 +268,13 @@ __device__ __forceinline__ uint32_t rk_step(const DecodeParams& P, Wk& w, TextCe
         if (src != ~0ull) {                         // this lane decoded the old image earlier in the same walk
           const uint32_t stag = P.cell_tag[src];
           const uint32_t saux = P.cell_aux[src];
-          put_cell(P, w.cell0 + dest, stag, P.cell_val[src], saux);
-          w.hint += cell_clone_hint(stag, saux);    // the clone owns its own heap buffer (Cell::clone)
+          if ((stag & ETL_CELL_PENDING_MASK) == ETL_CELL_PENDING) {     // the old cell waits for k_heavy: k_fix copies it afterwards
+            put_cell(P, w.cell0 + dest, ETL_CELL_PENDING_COPY, src, w.rec_local);
+            atomicAdd(P.copy_count, 1u);
+          } else {
+            put_cell(P, w.cell0 + dest, stag, P.cell_val[src], saux);
+            w.hint += cell_clone_hint(stag, saux);  // the clone owns its own heap buffer (Cell::clone)
+          }
         } else { put_cell(P, w.cell0 + dest, ETL_CELL_MISSING, 0, 0); w.bits |= WB_PARTIAL; }
       } else W_DATA_ERROR(seq, (!is_new && old == WO_KEY) ? ETL_E_KEY_MISSING_VALUE : ETL_E_FULL_ROW_MISSING);
       break;
@@ -284,18 +297,13 @@ __global__ void __launch_bounds__(kRowsThreads, ETL_ROWS_CTAS) k_rows(DecodePara
   const uint32_t n_chunks = (n_perm + blockDim.x - 1) / blockDim.x, cols = (n_chunks + 63u) / 64u;
   const uint32_t chunk = (blockIdx.x & 63u) * cols + (blockIdx.x >> 6);
   if ((blockIdx.x >> 6) >= cols || chunk >= n_chunks) return;
-  // CTA set-up: one mbarrier per warp, and the JSON acceptor's table by one bulk copy (waited for after the record loads)
-  const uint32_t tbar = smem_u32(smem + kRowsBarOff);
+  // CTA set-up: one mbarrier per warp
   if (threadIdx.x == 0) {
-    mbar_init(tbar, 1u);
-    for (uint32_t k = 0; k < kRowsWarps; k++) mbar_init(smem_u32(smem + kRowsBarOff + 8u + 8u * k), 32u);
+    for (uint32_t k = 0; k < kRowsWarps; k++) mbar_init(smem_u32(smem + kRowsBarOff + 8u * k), 32u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_arrive_expect_tx(tbar, kRowsJsonBytes);
-    bulk_g2s(smem_u32(smem), kJsonT2, kRowsJsonBytes, tbar);
   }
   __syncthreads();
-  const uint8_t* JT = smem;
-  const uint32_t bar = smem_u32(smem + kRowsBarOff + 8u + 8u * wid);
+  const uint32_t bar = smem_u32(smem + kRowsBarOff + 8u * wid);
   uint8_t* const slot = smem + kRowsSlotsOff + ((uint32_t)wid * 32u + (uint32_t)lane) * kRowsSlot;
   const uint32_t slot_s = smem_u32(slot);
   uint32_t parity = 0;
@@ -339,7 +347,6 @@ __global__ void __launch_bounds__(kRowsThreads, ETL_ROWS_CTAS) k_rows(DecodePara
       kinds = ck; flags = ck + kRowsColsCached;
     }
   }
-  mbar_wait(tbar, 0u);                                // kJsonT2 has landed
   RowWin W;
   W.win = slot; W.delta = 0x7FFFFFFF; W.w1 = 0;     // empty window: the first peek stages
   for (;;) {
@@ -427,31 +434,31 @@ __global__ void __launch_bounds__(kRowsThreads, ETL_ROWS_CTAS) k_rows(DecodePara
         if (lane == src && bad) code = ETL_E_UTF8;
       }
     }
-    const bool do_parse = is_text && !code && kind != ETL_K_STRING;
+    const bool light = kind_is_light(kind);
+    const bool do_parse = is_text && !code && kind != ETL_K_STRING && light;
     const unsigned pm = __ballot_sync(0xffffffffu, do_parse);
-    // heap space of this step's numeric / bytea / uuid cells: one warp-wide exclusive scan, one atomic
+    // heap space of this step's uuid cells: one warp-wide exclusive scan, one atomic
     uint64_t hpos = 0;
     {
-      const bool heap_kind = do_parse && (kind == ETL_K_NUMERIC || kind == ETL_K_BYTES || kind == ETL_K_UUID);
-      if (__any_sync(0xffffffffu, heap_kind)) {
-        const uint32_t hb = heap_kind ? cell_heap_bound(kind, len) : 0u;
-        uint32_t inc = hb;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t up = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += up; }
-        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+      const bool heap_kind = do_parse && kind == ETL_K_UUID;
+      const unsigned hm = __ballot_sync(0xffffffffu, heap_kind);
+      if (hm) {
         unsigned long long hbase = 0;
-        if (lane == 0) hbase = atomicAdd(P.heap_top, (unsigned long long)total);
+        if (lane == 0) hbase = atomicAdd(P.heap_top, 16ull * (unsigned long long)__popc(hm));
         hbase = __shfl_sync(0xffffffffu, hbase, 0);
-        hpos = hbase + (inc - hb);
+        hpos = hbase + 16ull * (unsigned long long)__popc(hm & ((1u << lane) - 1u));
       }
     }
+    bool defer = is_text && !code && !light;
     if (do_parse) {
       // lanes of one shape bin hold the same column here; lanes of a clamped bin (more layouts than bins) may not
       const unsigned mask = __match_any_sync(pm, kind);
-      code = parse_cell_sync(mask, kind, tv, len, soff, CellHeaps{P.heap, P.arr_top, P.arr_base, P.heap_cap, P.heap_overflow}, hpos, JT, o);
+      code = parse_light_sync(mask, kind, tv, len, P.heap, hpos, o);
+      if (code == 0xFFFFFFFFu) { code = 0; defer = true; }     // not a spelling the fast paths take: k_heavy's exact parser decides
     }
     if (is_text) {
       if (code) { report_error(P, P.dc->record_index_base + w.rec_local, tc.seq, code); w.bits &= ~WB_EMIT; }
+      else if (defer) put_cell(P, w.cell0 + tc.dest, ETL_CELL_PENDING | kind, ((uint64_t)w.rec_local << 32) | tc.voff, len);
       else { put_cell(P, w.cell0 + tc.dest, o.tag, o.val, o.aux); w.hint += cell_heap_hint(o.tag, o.aux); }
     }
   }
@@ -471,5 +478,154 @@ __global__ void __launch_bounds__(kRowsThreads, ETL_ROWS_CTAS) k_rows(DecodePara
 #undef W_DATA_ERROR
 #undef W_MALFORMED
 #undef W_SET_STAGE
+
+// ================================================================================================
+// pass C3: the pending cells.
+constexpr uint32_t kHeavyThreads = 256, kHeavyWarps = kHeavyThreads / 32, kHeavyTile = 4096, kHeavyStage = 128, kHeavySlot = kHeavyStage + 32;
+constexpr uint32_t kHeavyListOff = 32 * 256;                                     // after kJsonT2
+constexpr uint32_t kHeavyCntOff = kHeavyListOff + 3 * kHeavyTile * 2;
+constexpr uint32_t kHeavySlotsOff = kHeavyCntOff + 64;
+constexpr uint32_t kHeavySmemBytes = kHeavySlotsOff + kHeavyWarps * 32 * kHeavySlot + 64;
+// (record, evaluation step) → the error key of a cell, recomputed from the planes: only a failing cell pays for it
+__device__ __noinline__ uint32_t seq_of_cell(const DecodeParams P, uint32_t rec, uint64_t cell) {
+  const uint32_t out_idx = (uint32_t)(cell - P.rec_cell_base[rec]);
+  const uint32_t rf = P.rec_flags[rec];
+  const DevSchema sc = P.schemas[P.schema_by_batch[P.rec_schema[rec]]];
+  const uint32_t n_old = (rf & ETL_RF_OLD_FULL) ? sc.n_cols : ((rf & ETL_RF_OLD_KEY) ? sc.n_ident : 0u);
+  if (out_idx >= n_old) return seq_new_cell(out_idx - n_old);
+  if (rf & ETL_RF_OLD_FULL) return seq_old_cell(out_idx);
+  const uint8_t* fp = P.buf + P.rec_off[rec];              // key tuple: dense (one entry per identity column) or full width
+  const int32_t nc = (int32_t)(int16_t)(((uint32_t)fp[36] << 8) | fp[37]);
+  if ((uint32_t)(nc < 0 ? 0 : nc) == sc.n_ident) return seq_old_cell(out_idx);
+  uint32_t k = 0;
+  for (uint32_t i = 0; i < sc.n_cols; i++) if (P.col_flags[sc.col_base + i] & 2) { if (k == out_idx) return seq_old_cell(i); k++; }
+  return seq_old_cell(out_idx);
+}
+__global__ void __launch_bounds__(kHeavyThreads, 3) k_heavy(DecodeParams P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  if (*P.abort_flag) return;
+  const uint64_t n_cells = P.total[0].n_cells;
+  const uint32_t n_tiles = (uint32_t)((n_cells + kHeavyTile - 1) / kHeavyTile);
+  if (blockIdx.x >= n_tiles) return;
+  const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+  for (uint32_t i = threadIdx.x; i < 32u * 256u / 16u; i += blockDim.x)       // the JSON acceptor's table
+    reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(kJsonT2)[i];
+  uint16_t* const lists = reinterpret_cast<uint16_t*>(smem + kHeavyListOff);
+  uint32_t* const cnt = reinterpret_cast<uint32_t*>(smem + kHeavyCntOff);
+  uint8_t* const slot = smem + kHeavySlotsOff + (wid * 32u + lane) * kHeavySlot;
+  const CellHeaps H{P.heap, P.arr_top, P.arr_base, P.heap_cap, P.heap_overflow};
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint64_t c0 = (uint64_t)tile * kHeavyTile;
+    if (threadIdx.x < 3) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    {   // gather: 16 tags per thread (one 16-byte load: the cell planes are 256-byte aligned and the tile is a multiple of 16)
+      const uint64_t t0 = c0 + (uint64_t)threadIdx.x * 16u;
+      uint4 tg = make_uint4(0, 0, 0, 0);
+      if (t0 < n_cells) tg = *reinterpret_cast<const uint4*>(P.cell_tag + t0);     // the planes are padded to 256 bytes: the tail reads stay inside
+      const uint32_t wv[4] = {tg.x, tg.y, tg.z, tg.w};
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        const uint32_t t = (wv[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+        if ((t & ETL_CELL_PENDING_MASK) == ETL_CELL_PENDING && t0 + k < n_cells) {
+          const uint32_t kind = t & 0x3Fu;
+          const uint32_t cls = kind == ETL_K_JSON ? 0u : (kind == ETL_K_NUMERIC ? 1u : 2u);
+          const uint32_t at = atomicAdd(&cnt[cls], 1u);
+          lists[cls * kHeavyTile + at] = (uint16_t)(threadIdx.x * 16u + k);
+        }
+      }
+    }
+    __syncthreads();
+    for (uint32_t cls = 0; cls < 3; cls++) {
+      const uint32_t n = cnt[cls];
+      for (uint32_t base = wid * 32u; base < n; base += kHeavyWarps * 32u) {
+        const bool have = base + lane < n;
+        const uint64_t cell = c0 + (have ? lists[cls * kHeavyTile + base + lane] : 0u);
+        uint32_t kind = 0, len = 0, rec = 0;
+        uint64_t soff = 0;
+        const uint8_t* tv = P.buf;
+        if (have) {
+          kind = P.cell_tag[cell] & 0x3Fu;
+          const uint64_t v = P.cell_val[cell];
+          len = P.cell_aux[cell];
+          if (P.copy_cols) {                                // COPY rows: val locates the text itself (bit 63: an unescaped copy in the heap)
+            rec = (uint32_t)(cell / P.copy_cols);
+            soff = v;
+            tv = ((v >> 63) ? P.heap : P.buf) + (v & ~(1ull << 63));
+          } else {
+            rec = (uint32_t)(v >> 32);
+            soff = P.rec_off[rec] + (uint32_t)v;
+            tv = P.buf + soff;
+          }
+          if (len <= kHeavyStage) {                         // stage the value: every 16-byte load of the lane in flight at once
+            const uintptr_t a0 = reinterpret_cast<uintptr_t>(tv) & ~uintptr_t(15);
+            const uint32_t nch = (uint32_t)((reinterpret_cast<uintptr_t>(tv) + len + 15u - a0) >> 4);        // ≤ 9
+            const uint4* gp = reinterpret_cast<const uint4*>(a0);
+            uint4 ch[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) ch[k] = (uint32_t)k < nch ? gp[k] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int k = 0; k < 9; k++) if ((uint32_t)k < nch) reinterpret_cast<uint4*>(slot)[k] = ch[k];
+            tv = slot + (uint32_t)(reinterpret_cast<uintptr_t>(tv) - a0);
+          }
+        }
+        __syncwarp();
+        // heap space of this row's numeric / bytea / uuid cells
+        uint64_t hpos = 0;
+        {
+          const bool heap_kind = have && (kind == ETL_K_NUMERIC || kind == ETL_K_BYTES || kind == ETL_K_UUID);
+          if (__any_sync(0xffffffffu, heap_kind)) {
+            const uint32_t hb = heap_kind ? cell_heap_bound(kind, len) : 0u;
+            uint32_t inc = hb;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t up = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (uint32_t)d) inc += up; }
+            const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+            unsigned long long hbase = 0;
+            if (lane == 0) hbase = atomicAdd(P.heap_top, (unsigned long long)total);
+            hbase = __shfl_sync(0xffffffffu, hbase, 0);
+            hpos = hbase + (inc - hb);
+          }
+        }
+        const unsigned hm = __ballot_sync(0xffffffffu, have);
+        if (have) {
+          const unsigned mask = cls == 2u ? __match_any_sync(hm, kind) : hm;      // the json / numeric lists hold one class each
+          CellOut o;
+          o.tag = 0; o.val = 0; o.aux = 0;
+          const uint32_t code = parse_heavy_sync(mask, kind, tv, len, soff, H, hpos, smem, o);
+          if (code) report_error(P, P.dc->record_index_base + rec, P.copy_cols ? 1u + (uint32_t)(cell % P.copy_cols) : seq_of_cell(P, rec, cell), code);
+          else {
+            put_cell(P, cell, o.tag, o.val, o.aux);
+            const uint32_t h = P.copy_cols ? 0u : cell_heap_hint(o.tag, o.aux);
+            if (h) atomicAdd(&P.rec_heap_hint[rec], h);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// pass C4: unchanged-TOAST cells whose source was pending in k_rows take the parsed value now (event.rs:958-970: a clone)
+__global__ void __launch_bounds__(256) k_fix(DecodeParams P) {
+  if (*P.abort_flag || *P.copy_count == 0u) return;
+  const uint64_t n_cells = P.total[0].n_cells;
+  for (uint64_t t0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16u; t0 < n_cells; t0 += (uint64_t)gridDim.x * blockDim.x * 16u) {
+    const uint4 tg = *reinterpret_cast<const uint4*>(P.cell_tag + t0);
+    const uint32_t wv[4] = {tg.x, tg.y, tg.z, tg.w};
+    if (!(((tg.x | tg.y | tg.z | tg.w) & 0x80808080u))) continue;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const uint32_t t = (wv[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+      if (t == ETL_CELL_PENDING_COPY && t0 + k < n_cells) {
+        const uint64_t src = P.cell_val[t0 + k];
+        const uint32_t rec = P.cell_aux[t0 + k];
+        const uint32_t stag = P.cell_tag[src], saux = P.cell_aux[src];
+        put_cell(P, t0 + k, stag, P.cell_val[src], saux);
+        const uint32_t h = cell_clone_hint(stag, saux);
+        if (h) atomicAdd(&P.rec_heap_hint[rec], h);
+      }
+    }
+  }
+}
 
 }  // namespace etl

@@ -110,6 +110,8 @@ struct DecodeParams {
   uint32_t n_batch_schemas;
   uint32_t* rec_flen;               // CopyData length + 1 of every record's frame (k_frames → k_rows: sizes the staged window)
   unsigned int* abort_flag;         // set by k_scan when the batch does not fit the planes the host reserved
+  unsigned int* copy_count;         // unchanged-TOAST cells left for k_fix
+  uint32_t copy_cols;               // COPY-row decode (copy_kernel.cuh): columns per row; 0 on the replication path
   uint64_t cap_records, cap_cells;  // capacity of the record / cell planes
   uint32_t* line_bad;               // k_utf8_dead: bit l set = line l (128 bytes) holds a UTF-8 rule violation (zeroed per batch)
   uint32_t* dead;                   // segments without a frame start (ascending); n_dead = n_anchors - *n_act
@@ -579,31 +581,32 @@ __global__ void __launch_bounds__(256) k_utf8_dead(DecodeParams P) {
     const uint64_t s0 = (uint64_t)P.dead[d] * P.anchor_stride;
     const uint64_t s1 = s0 + P.anchor_stride < P.len ? s0 + P.anchor_stride : P.len;
     for (uint64_t base = s0; base < s1; base += 2048ull) {
+      // every lane owns 64 contiguous bytes (half a 128-byte line): four 16-byte loads in flight, and the three
+      // bytes before its first chunk come from one 4-byte load that hits L1 — no shuffles (round 1 paid three
+      // __shfl per 16 bytes; they were a third of this kernel's stall samples)
+      const uint64_t off = base + (uint64_t)lane * 64ull;
       uint4 x[4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const uint64_t off = base + (uint64_t)(k * 32 + (int)lane) * 16ull;
-        x[k] = off < s1 ? *reinterpret_cast<const uint4*>(P.buf + off) : make_uint4(0, 0, 0, 0);   // +64 bytes of padding are readable
-      }
-      uint32_t word = 0;
-      uint32_t carry = base >= 4 ? *reinterpret_cast<const uint32_t*>(P.buf + base - 4) : 0u;   // last word before the pass
+      for (int k = 0; k < 4; k++)
+        x[k] = off + 16ull * k < s1 ? *reinterpret_cast<const uint4*>(P.buf + off + 16ull * k) : make_uint4(0, 0, 0, 0);   // +64 bytes of padding are readable
+      uint32_t pw = (off >= 4 && off < s1) ? *reinterpret_cast<const uint32_t*>(P.buf + off - 4) : 0u;   // last word before the lane's bytes
+      bool bad = false;
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        uint32_t pw = __shfl_up_sync(0xffffffffu, x[k].w, 1);      // the previous 16 bytes' last word
-        if (lane == 0) pw = carry;
-        carry = __shfl_sync(0xffffffffu, x[k].w, 31);
         const uint32_t h = x[k].x | x[k].y | x[k].z | x[k].w;
-        bool bad = false;
         if ((h & 0x80808080u) | (pw & 0x80808000u)) {             // high bits here or in the three bytes before
-          const uint64_t off = base + (uint64_t)(k * 32 + (int)lane) * 16ull;
-          if (off < s1) bad = !utf8_chunk_valid_at(P.buf, P.len, off, off + 16ull < P.len ? off + 16ull : P.len);
+          const uint64_t o = off + 16ull * k;
+          if (o < s1) bad |= !utf8_chunk_valid_at(P.buf, P.len, o, o + 16ull < P.len ? o + 16ull : P.len);
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, bad);
-#pragma unroll
-        for (int m = 0; m < 4; m++) if ((bal >> (8 * m)) & 0xFFu) word |= 1u << (k * 4 + m);
+        pw = x[k].w;
       }
+      // two lanes per 128-byte line, 16 lines per pass: bit m of `word` = line m holds a violation
+      unsigned bal = __ballot_sync(0xffffffffu, bad);
+      bal = (bal | (bal >> 1)) & 0x55555555u;
+      bal = (bal | (bal >> 1)) & 0x33333333u; bal = (bal | (bal >> 2)) & 0x0F0F0F0Fu;
+      bal = (bal | (bal >> 4)) & 0x00FF00FFu; bal = (bal | (bal >> 8)) & 0x0000FFFFu;
       // base is a multiple of min(stride, 2048): the (at most 16) bits of this pass stay inside one word
-      if (word && lane == 0) atomicOr(&P.line_bad[(base >> 7) >> 5], word << ((base >> 7) & 31u));
+      if (bal && lane == 0) atomicOr(&P.line_bad[(base >> 7) >> 5], bal << ((base >> 7) & 31u));
     }
   }
 }
@@ -888,6 +891,7 @@ __device__ __forceinline__ uint32_t cell_clone_hint(uint32_t tag, uint32_t aux) 
 
 }  // namespace etl
 #include "rows_kernel.cuh"
+#include "copy_kernel.cuh"
 namespace etl {
 
 }  // namespace etl

@@ -77,6 +77,22 @@ class DecodedBatch:
     record_index_base: int = 0
 
 
+@dataclass
+class CopyBatch:
+    """Decoded COPY rows: row-major cells (cell r * n_cols + c).  A string / json cell is a span of `stream`
+    (val = offset) unless bit 63 of val is set: then the low bits are an offset into `heap` (the field was unescaped)."""
+    n_rows: int
+    n_cols: int
+    stream: np.ndarray
+    cell_tag: np.ndarray
+    cell_val: np.ndarray
+    cell_aux: np.ndarray
+    heap: np.ndarray
+    first_error: tuple   # (row | None, step (0 = the row's UTF-8 check, 1 + column otherwise), code, kind)
+    kernel_ms: float = 0.0
+    gpu_launches: int = 0
+
+
 def _make_columns(cols: Sequence[dict]):
     arr = (abi.ColumnSchema * max(1, len(cols)))()
     keep = []
@@ -207,6 +223,39 @@ class Decoder:
         h = C.c_void_p()
         self._check(self._l.etl_dec_decode_sharded(self._ctx, C.byref(inp), abi.RESULTS_TO_HOST if to_host else 0, C.byref(h)))
         return BatchHandle(self, h)
+
+    # -- initial-sync COPY rows (etl_dec_copy_decode; table_row.rs:25-165 for a whole buffer of rows) --------------
+    def copy_decode(self, table_id: int, rows, row_offsets=None) -> "CopyBatch":
+        """`rows`: bytes / uint8 array of COPY-text rows back to back (each with its LF), or a list of row chunks.
+        Returns the decoded cells (host copies)."""
+        if isinstance(rows, (list, tuple)):
+            offs = np.zeros(len(rows) + 1, dtype=np.uint64)
+            offs[1:] = np.cumsum([len(r) for r in rows])
+            buf = np.frombuffer(b"".join(bytes(r) for r in rows), dtype=np.uint8)
+        else:
+            buf = rows if isinstance(rows, np.ndarray) else np.frombuffer(bytes(rows), dtype=np.uint8)
+            offs = np.asarray(row_offsets, dtype=np.uint64)
+        padded = np.zeros(buf.nbytes + 64, dtype=np.uint8)            # the kernels read whole aligned words around a value
+        padded[:buf.nbytes] = buf
+        inp = abi.CopyInput()
+        inp.host_buf = padded.ctypes.data
+        inp.len = buf.nbytes
+        inp.row_offsets = offs.ctypes.data
+        inp.n_rows = len(offs) - 1
+        h = C.c_void_p()
+        self._check(self._l.etl_dec_copy_decode(self._ctx, table_id, C.byref(inp), abi.RESULTS_TO_HOST, C.byref(h)))
+        bh = BatchHandle(self, h)
+        try:
+            p, s = bh.planes(True), bh.summary()
+            m = int(p.n_cells)
+            fe = s.first_error
+            return CopyBatch(n_rows=int(p.n_records), n_cols=(m // int(p.n_records)) if p.n_records else 0, stream=buf,
+                             cell_tag=_np_from(p.cell_tag, m, np.uint8), cell_val=_np_from(p.cell_val, m, np.uint64),
+                             cell_aux=_np_from(p.cell_aux, m, np.uint32), heap=_np_from(p.heap, p.heap_bytes, np.uint8),
+                             first_error=(None if fe.record_index == 2**64 - 1 else int(fe.record_index), int(fe.seq), int(fe.code), int(fe.kind)),
+                             kernel_ms=float(s.kernel_ms), gpu_launches=int(s.gpu_launches))
+        finally:
+            bh.free()
 
     def mem_info(self):
         f, t = C.c_uint64(), C.c_uint64()

@@ -172,6 +172,8 @@ typedef enum etl_error_code {
   ETL_E_UNKNOWN_COLUMNS = 22,   /* CorruptedTableSchema "Received columns during replication that are not in the stored table schema" error.rs:960-975 */
   ETL_E_MISSING_TABLE_SCHEMA = 23,/* MissingTableSchema  stored TableSchema absent for a Relation (apply.rs:2062-2072) */
   ETL_E_MALFORMED_FRAME = 24,   /* SourceError: truncated frame / unknown tag (postgres-replication parse error) */
+  ETL_E_COPY_NOT_TERMINATED = 25, /* ConversionError "Row data not properly terminated"                  table_row.rs:88-92 */
+  ETL_E_COPY_COLUMN_COUNT = 26,  /* ConversionError "Column count mismatch between schema and row"     table_row.rs:103-113,150-160 */
   ETL_E__COUNT
 } etl_error_code;
 
@@ -377,6 +379,28 @@ typedef struct etl_dec_schema_info {
   const int32_t* col_index; /* index into the stored TableSchema's column list */
 } etl_dec_schema_info;
 int etl_dec_batch_schema(const etl_dec_batch*, uint32_t index, etl_dec_schema_info* out);
+
+/* ---------------------------------------------------------------- initial-sync COPY rows
+ * Replaces parse_table_row_from_postgres_copy_bytes (crates/etl/src/conversions/table_row.rs:25-165) applied row by
+ * row by TableCopyStream::poll_next (crates/etl/src/replication/stream.rs:75-101) for a whole buffer of rows.
+ * `buf` holds the COPY-text rows back to back exactly as the CopyData bodies arrive (each ends with its LF);
+ * row_offsets has n_rows + 1 ascending entries (row r = [row_offsets[r], row_offsets[r+1])).  Same device-buffer
+ * precondition as etl_dec_input.dev_buf (16-byte aligned, 64 readable bytes after len).  The table's columns are those
+ * of etl_dec_put_table_schema, in order.  Result: an etl_dec_batch whose planes hold n_records = n_rows,
+ * n_cells = n_rows * n_cols (row-major: cell r * n_cols + c), rec_off = the row offsets, rec_kind..rec_heap_hint NULL;
+ * a string / json cell is a span of `buf` (val = offset) unless the field needed unescaping: then bit 63 of val is
+ * set and the low bits are a heap offset.  first_error: record_index = row, seq = 0 for the row's UTF-8 check,
+ * 1 + column otherwise; rows before it are valid. */
+#define ETL_COPY_VAL_IN_HEAP (1ull << 63)
+typedef struct etl_copy_input {
+  const uint8_t* host_buf;
+  const uint8_t* dev_buf;          /* optional, resident copy */
+  uint64_t len;
+  const uint64_t* row_offsets;     /* host, n_rows + 1 entries */
+  const uint64_t* dev_row_offsets; /* optional, resident copy */
+  uint64_t n_rows;
+} etl_copy_input;
+int etl_dec_copy_decode(etl_dec_ctx*, uint32_t table_id, const etl_copy_input*, uint32_t flags, etl_dec_batch** out);
 
 /* ---------------------------------------------------------------- shim stand-in (host only, no GPU work)
  * What the Rust shim does with the planes (replaces nothing in the reference — it is the glue that

@@ -96,6 +96,11 @@ uint32_t orc_error_kind(uint32_t code);
  * dereferenced, so two decodes of the same stream compare equal whatever their heap placement */
 void orc_planes_digest(const etl_dec_planes* p, uint64_t n_valid, uint64_t out[4]);
 void orc_batch_digest(const orc_batch* b, uint64_t out[4]);
+/* COPY rows: digest of device planes / of the oracle's own row-by-row parse (strings by content) */
+void orc_copy_planes_digest(const uint8_t* tags, const uint64_t* vals, const uint32_t* auxs, uint64_t n_valid_rows, uint32_t n_cols,
+                            const uint8_t* stream, const uint8_t* heap, uint64_t out[4]);
+void orc_copy_rows_digest(const uint32_t* type_oids, uint32_t n_cols, const uint8_t* buf, const uint64_t* row_off, uint64_t n_rows,
+                          uint64_t out[4], uint64_t* err_row, uint32_t* err_col, uint32_t* err_code);
 
 #ifdef __cplusplus
 }

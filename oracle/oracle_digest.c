@@ -5,6 +5,7 @@
  * var-width payloads (numeric / uuid / bytes / arrays) dereferenced from the heap so that heap placement does
  * not matter; string and json cells are (stream offset, length) spans of the same staged stream.
  * Four independent 64-bit multiplicative hashes (256 bits) over the canonical byte sequence. */
+#include <stdlib.h>
 #include <string.h>
 
 #include "oracle.h"
@@ -72,4 +73,50 @@ void orc_batch_digest(const orc_batch* b, uint64_t out[4]) {
   p.cell_tag = b->cell_tag; p.cell_val = b->cell_val; p.cell_aux = b->cell_aux; p.heap = b->heap;
   const uint64_t nv = b->first_error.record_index == UINT64_MAX ? b->n_records : b->first_error.record_index;
   orc_planes_digest(&p, nv, out);
+}
+
+/* ---- COPY rows: canonical digest of decoded rows, strings by CONTENT (the device keeps a field
+ * that needs no unescaping as a span of the staged stream and copies the others into its heap; the oracle keeps
+ * every unescaped field in its own text buffer). */
+static void dg_copy_cell(dg* d, uint32_t tag, uint64_t val, uint32_t aux, const uint8_t* text_src, const uint8_t* heap) {
+  if (tag == ETL_CELL_STRING || tag == ETL_CELL_JSON) { dg_u64(d, tag); dg_bytes(d, text_src + val, aux); }
+  else dg_cell(d, tag, val, aux, heap, 1);   /* in_array = 1: pushed_groups is not part of a COPY row's contract */
+}
+/* device planes: n_valid_rows x n_cols cells; string / json val = offset into `stream`, or bit 63 set = offset into `heap` */
+void orc_copy_planes_digest(const uint8_t* tags, const uint64_t* vals, const uint32_t* auxs, uint64_t n_valid_rows, uint32_t n_cols,
+                            const uint8_t* stream, const uint8_t* heap, uint64_t out[4]) {
+  dg d; for (int i = 0; i < 4; i++) d.h[i] = K[i] ^ (uint64_t)(i + 11);
+  dg_u64(&d, n_valid_rows); dg_u64(&d, n_cols);
+  for (uint64_t c = 0; c < n_valid_rows * n_cols; c++) {
+    const uint64_t v = vals[c];
+    const int in_heap = (int)(v >> 63);
+    dg_copy_cell(&d, tags[c], v & ~(1ull << 63), auxs[c], (tags[c] == ETL_CELL_STRING || tags[c] == ETL_CELL_JSON) && !in_heap ? stream : heap, heap);
+  }
+  for (int i = 0; i < 4; i++) out[i] = d.h[i];
+}
+/* oracle side: parse rows [0, n_rows) given by row_off (n_rows + 1 offsets into buf) one by one with orc_parse_copy_row
+ * (table_row.rs:25-165), stop at the first failing row; digest of the rows before it. */
+void orc_copy_rows_digest(const uint32_t* type_oids, uint32_t n_cols, const uint8_t* buf, const uint64_t* row_off, uint64_t n_rows,
+                          uint64_t out[4], uint64_t* err_row, uint32_t* err_col, uint32_t* err_code) {
+  dg d; for (int i = 0; i < 4; i++) d.h[i] = K[i] ^ (uint64_t)(i + 11);
+  *err_row = UINT64_MAX; *err_col = 0xFFFFFFFFu; *err_code = 0;
+  uint64_t cap = 1 << 16;
+  uint8_t* tags = 0; uint64_t* vals = 0; uint32_t* auxs = 0; uint8_t* text = 0; uint8_t* heap = 0;
+  tags = (uint8_t*)malloc(n_cols + 1); vals = (uint64_t*)malloc((n_cols + 1) * 8); auxs = (uint32_t*)malloc((n_cols + 1) * 4);
+  text = (uint8_t*)malloc(cap); heap = (uint8_t*)malloc(cap * 24);
+  /* first pass: find the first failing row so that the row count is hashed first (as the device side does) */
+  uint64_t n_ok = n_rows;
+  for (int pass = 0; pass < 2; pass++) {
+    if (pass == 1) { dg_u64(&d, n_ok); dg_u64(&d, n_cols); }
+    for (uint64_t r = 0; r < (pass ? n_ok : n_rows); r++) {
+      const uint64_t len = row_off[r + 1] - row_off[r];
+      if (len + 64 > cap) { cap = (len + 64) * 2; text = (uint8_t*)realloc(text, cap); heap = (uint8_t*)realloc(heap, cap * 24); }
+      uint32_t nv = 0, ec = 0; uint64_t tl = 0, hl = 0;
+      const uint32_t e = orc_parse_copy_row(type_oids, n_cols, buf + row_off[r], len, tags, vals, auxs, &nv, text, cap, &tl, heap, cap * 24, &hl, &ec);
+      if (e) { if (!pass) { n_ok = r; *err_row = r; *err_col = ec; *err_code = e; } break; }
+      if (pass) for (uint32_t c = 0; c < n_cols; c++) dg_copy_cell(&d, tags[c], vals[c], auxs[c], text, heap);
+    }
+  }
+  free(tags); free(vals); free(auxs); free(text); free(heap);
+  for (int i = 0; i < 4; i++) out[i] = d.h[i];
 }

@@ -247,6 +247,33 @@ def planes_digest(planes_struct, n_valid: int) -> str:
     return "".join("%016x" % v for v in out)
 
 
+def copy_rows_digest(type_oids: Sequence[int], buf: np.ndarray, row_off: np.ndarray):
+    """Oracle decode of COPY rows, row by row (table_row.rs:25-165): (digest of the rows before the first failing one,
+    first error (row, col, code) or None)."""
+    L = lib()
+    oids = (C.c_uint32 * max(len(type_oids), 1))(*type_oids)
+    out = (C.c_uint64 * 4)()
+    er, ec, ee = C.c_uint64(), C.c_uint32(), C.c_uint32()
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    row_off = np.ascontiguousarray(row_off, dtype=np.uint64)
+    L.orc_copy_rows_digest.restype = None
+    L.orc_copy_rows_digest(oids, C.c_uint32(len(type_oids)), C.c_void_p(buf.ctypes.data), C.c_void_p(row_off.ctypes.data), C.c_uint64(len(row_off) - 1), out,
+                           C.byref(er), C.byref(ec), C.byref(ee))
+    err = None if er.value == 2**64 - 1 else (int(er.value), int(ec.value), int(ee.value))
+    return "".join("%016x" % v for v in out), err
+
+
+def copy_planes_digest(tags: np.ndarray, vals: np.ndarray, auxs: np.ndarray, n_valid_rows: int, n_cols: int, stream: np.ndarray, heap: np.ndarray) -> str:
+    L = lib()
+    out = (C.c_uint64 * 4)()
+    heap = np.ascontiguousarray(heap if heap.nbytes else np.zeros(8, np.uint8))
+    stream = np.ascontiguousarray(stream if stream.nbytes else np.zeros(8, np.uint8))
+    L.orc_copy_planes_digest.restype = None
+    L.orc_copy_planes_digest(C.c_void_p(tags.ctypes.data), C.c_void_p(vals.ctypes.data), C.c_void_p(auxs.ctypes.data), C.c_uint64(n_valid_rows),
+                             C.c_uint32(n_cols), C.c_void_p(stream.ctypes.data), C.c_void_p(heap.ctypes.data), out)
+    return "".join("%016x" % v for v in out)
+
+
 def parse_cell(type_oid: int, text: bytes):
     """text.rs:28 for one value → (err_code, tag, val, aux, heap bytes)."""
     L = lib()

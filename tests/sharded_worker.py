@@ -36,6 +36,23 @@ def main():
             dec.reset_relations()
         with dec.decode_sharded(st.view(), to_host=True) as bh:
             p = bh.to_host()
+        print(f"[rank {rank}] rep {rep}: records {p.n_records} first_error {p.first_error} base {p.record_index_base} carry_out {p.carry_out}", flush=True)
+    if os.environ.get("ETL_TEST_DIAG"):                 # the same range through the two-phase entry points, carry taken from the library's own answer
+        from etl_b200 import sharding
+        seam = dec.decode_begin(st.view(), to_host=True)
+        words = torch.from_numpy(sharding.seam_to_words(seam).view(np.int64).copy()).cuda()
+        allw = [torch.zeros_like(words) for _ in range(world)]
+        dist.all_gather(allw, words)
+        allw = np.stack([w_.cpu().numpy().view(np.uint64) for w_ in allw])
+        state, base = sharding.carry_for_rank(allw, rank)
+        with dec.decode_finish(state, base) as bh:
+            q = bh.to_host()
+        print(f"[rank {rank}] two-phase: records {q.n_records} first_error {q.first_error} carry {state} base {base}", flush=True)
+        for f in ("rec_kind", "rec_flags", "rec_schema", "rec_commit_lsn", "rec_tx_ordinal", "rec_cell_base", "cell_tag", "cell_aux"):
+            a_, b_ = getattr(p, f), getattr(q, f)
+            n_ = min(len(a_), len(b_))
+            d_ = np.nonzero(a_[:n_] != b_[:n_])[0]
+            print(f"[rank {rank}] {f}: len {len(a_)} vs {len(b_)}, first diff {d_[:3]}", flush=True)
     fields = {k: getattr(p, k) for k in ("rec_off", "rec_kind", "rec_flags", "rec_rel", "rec_schema", "rec_start_lsn", "rec_commit_lsn",
                                          "rec_tx_ordinal", "rec_cell_base", "rec_tuple_bytes", "rec_heap_hint", "cell_tag", "cell_val",
                                          "cell_aux", "heap")}
