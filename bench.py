@@ -38,6 +38,7 @@ sys.path.insert(0, ROOT)
 
 GIB = 1 << 30
 NO_ERROR = 2**64 - 1
+DATA_ERRORS = []      # first_error of any timed / warm-up decode: a clean synthetic stream must not produce one
 
 
 def parse_args():
@@ -260,7 +261,8 @@ def decode_once(dec, st, resident, sharded, carry=None):
     bh = dec.decode_sharded(inp, to_host=not resident) if sharded else dec.decode_input(inp, to_host=not resident)
     s = bh.summary()
     if s.first_error.record_index != NO_ERROR:
-        raise RuntimeError(f"decode reported a data error at record {s.first_error.record_index} code {s.first_error.code}")
+        # never raise between collectives (the other ranks would wait for this one for ever): remember it, fail the line later
+        DATA_ERRORS.append((int(s.first_error.record_index), int(s.first_error.seq), int(s.first_error.code)))
     return bh, s
 
 
@@ -646,10 +648,16 @@ def main():
         e2e = {"ms_per_step": e2e_ms / args.steps, "h2d": elast["h2d"], "d2h": elast["d2h"]}
 
     # ---- totals over ranks
-    tot = torch.tensor([nbytes, frames, last["n_records"], last["n_cells"], e2e["h2d"] if e2e else 0, e2e["d2h"] if e2e else 0],
+    tot = torch.tensor([nbytes, frames, last["n_records"], last["n_cells"], e2e["h2d"] if e2e else 0, e2e["d2h"] if e2e else 0, len(DATA_ERRORS)],
                        dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if tot[6].item() > 0:
+        if DATA_ERRORS:
+            print(f"rank {rank}: decode reported data errors on a clean stream: {DATA_ERRORS[:3]}", file=sys.stderr, flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        sys.exit(3)
     total_bytes, total_frames = float(tot[0].item()), float(tot[1].item())
     n_anchors = st.n_anchors
     dec.close()

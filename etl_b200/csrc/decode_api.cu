@@ -886,7 +886,7 @@ static int launch_emit_kernels(etl_dec_ctx* ctx) {
     if (dead_mode() == 1 && !ctx->lines_launched) CK(launch_dead_side(ctx, st));   // underneath the tuple pass
     if (cap_r) {
       k_bin_scan<<<1, 1024, 0, st>>>(P);
-      k_perm<<<(uint32_t)((cap_r + 255) / 256), 256, 0, st>>>(P);
+      k_perm<<<(uint32_t)((cap_r + kPermThreads - 1) / kPermThreads), kPermThreads, 0, st>>>(P);
       cudaEventRecord(ctx->evk[2], st);
       const uint32_t chunks = (uint32_t)((perm_cap + kRowsThreads - 1) / kRowsThreads);
       k_rows<<<((chunks + 63u) / 64u) * 64u, kRowsThreads, kRowsSmemBytes, st>>>(P);

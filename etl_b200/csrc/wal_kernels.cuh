@@ -682,26 +682,39 @@ __global__ void __launch_bounds__(1024) k_bin_scan(DecodeParams P) {
   }
   if (threadIdx.x == 1023) *P.perm_len = sh[1023];
 }
-__global__ void __launch_bounds__(256) k_perm(DecodeParams P) {
+// k_perm: CTA-local counting first (shared-memory histogram), then ONE global atomic per occupied bin per CTA.
+// (Round 1 issued one global atomic per bin per WARP: a single-table stream has ~8 occupied bins, so 75 k warps
+// queued on 8 addresses — 0.2 ms on C5 for what is a 10 MB permutation.)
+constexpr int kPermThreads = 1024;
+__global__ void __launch_bounds__(kPermThreads) k_perm(DecodeParams P) {
+  __shared__ uint32_t hist[kMaxBins];                 // count of the CTA's records per bin, then the CTA's base in the bin
+  if (*P.abort_flag) return;
+  const uint64_t n_rec = P.total[0].n_rec;
+  if ((uint64_t)blockIdx.x * blockDim.x >= n_rec) return;
+  for (uint32_t i = threadIdx.x; i < P.n_bins; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   bool dml = false;
-  uint32_t bin = 0;
-  if (*P.abort_flag) return;
-  if (r < P.total[0].n_rec) {
+  uint32_t bin = 0, local = 0;
+  if (r < n_rec) {
     const uint32_t kind = P.rec_kind[r];
     const int32_t sc = P.rec_schema[r];
     if ((kind == 'I' || kind == 'U' || kind == 'D') && sc >= 0) { dml = true; bin = walk_bin(P, P.schemas[P.schema_by_batch[sc]].layout, kind, P.rec_flags[r]); }
   }
   const unsigned vm = __ballot_sync(0xffffffffu, dml);
-  if (dml) {                                          // one atomic per bin per warp
+  if (dml) {                                          // one shared-memory atomic per bin per warp
     const unsigned mask = __match_any_sync(vm, bin);
     const int leader = __ffs(mask) - 1;
     uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(&P.bin_cursor[bin], (uint32_t)__popc(mask));
+    if (lane == leader) base = atomicAdd(&hist[bin], (uint32_t)__popc(mask));
     base = __shfl_sync(mask, base, leader);
-    P.perm[base + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)r;
+    local = base + __popc(mask & ((1u << lane) - 1u));
   }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < P.n_bins; i += blockDim.x) { const uint32_t c = hist[i]; if (c) hist[i] = atomicAdd(&P.bin_cursor[i], c); }
+  __syncthreads();
+  if (dml) P.perm[hist[bin] + local] = (uint32_t)r;
 }
 
 // ================================================================================================
