@@ -585,6 +585,10 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs CUDA devices (the decode path has no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # the decode chain runs on torch's CURRENT stream (the CUDA events below see only that one): a high-priority stream,
+    # so that the library's low-priority side pass yields thread slots to it
+    main_stream = torch.cuda.Stream(device=dev, priority=-1)
+    torch.cuda.set_stream(main_stream)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world

@@ -14,6 +14,7 @@
 // device (k_seam_fold) — nothing returns to the host between the index pass and the record pass.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <link.h>
 #include <nccl.h>   // types and prototypes only: the entry points are resolved at run time (etl_dec_comm_*)
 
 #include <algorithm>
@@ -138,9 +139,18 @@ NcclApi& nccl_api() {
   static bool tried = false;
   if (tried) return api;
   tried = true;
-  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
-  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  // the copy the process already holds (PyTorch's bundled NCCL, a host application's, …): found by walking the loaded
+  // objects, re-opened by its exact path; only when there is none is the system library loaded.  RTLD_LOCAL: a second
+  // NCCL must never interpose its symbols on the first.
+  std::string loaded;
+  dl_iterate_phdr([](struct dl_phdr_info* info, size_t, void* out) -> int {
+    if (info->dlpi_name && strstr(info->dlpi_name, "libnccl.so")) { *static_cast<std::string*>(out) = info->dlpi_name; return 1; }
+    return 0;
+  }, &loaded);
+  void* h = nullptr;
+  if (!loaded.empty()) h = dlopen(loaded.c_str(), RTLD_NOW | RTLD_NOLOAD | RTLD_LOCAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
   if (!h) return api;
   api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
   api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
@@ -227,6 +237,8 @@ struct etl_dec_ctx {
   double rec_per_byte = 0, cells_per_byte = 0;
   // multi-GPU
   ncclComm_t comm = nullptr;
+  etl_host_allgather_fn host_allgather = nullptr;   // exchange through the host instead of NCCL (etl_dec_comm_init_host)
+  void* host_user = nullptr;
   int rank = 0, n_ranks = 1;
   size_t rel_slot = 64 << 10;            // bytes per rank in the relation-update exchange (grows on demand)
 };
@@ -364,9 +376,13 @@ int etl_dec_create(int device_id, etl_dec_ctx** out) {
   etl_dec_ctx* ctx = new etl_dec_ctx();
   ctx->device = device_id;
   bool ok = cudaSetDevice(device_id) == cudaSuccess;
-  ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+  // the latency-bound chain runs at the highest priority, the HBM-bound side pass at the lowest: when both have CTAs
+  // pending the scheduler places the chain's first
+  int prio_lo = 0, prio_hi = 0;
+  ok = ok && cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
   ctx->own_stream = ok;
-  ok = ok && cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_lo) == cudaSuccess;
   for (auto& e : ctx->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
   for (auto& e : ctx->evk) ok = ok && cudaEventCreate(&e) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming) == cudaSuccess;
@@ -421,6 +437,29 @@ int etl_dec_comm_init(etl_dec_ctx* ctx, const uint8_t* unique_id, uint32_t id_by
   memcpy(&id, unique_id, sizeof id);
   CKN(nccl_api().CommInitRank(&ctx->comm, n_ranks, id, rank));
   ctx->rank = rank; ctx->n_ranks = n_ranks;
+  return ETL_OK;
+}
+
+int etl_dec_comm_init_host(etl_dec_ctx* ctx, int rank, int n_ranks, etl_host_allgather_fn fn, void* user) {
+  if (!ctx || !fn || n_ranks < 1 || rank < 0 || rank >= n_ranks) return ETL_ERR_INVALID_ARG;
+  if (ctx->comm && nccl_api().ok) { nccl_api().CommDestroy(ctx->comm); ctx->comm = nullptr; }
+  ctx->host_allgather = fn; ctx->host_user = user;
+  ctx->rank = rank; ctx->n_ranks = n_ranks;
+  return ETL_OK;
+}
+// all-gather of `bytes` per rank from d_send into d_recv (n_ranks blocks) on the decode stream: NCCL, or through the host
+static int ctx_allgather(etl_dec_ctx* ctx, const void* d_send, void* d_recv, size_t bytes) {
+  cudaStream_t st = ctx->stream;
+  if (!ctx->host_allgather) {
+    CKN(nccl_api().AllGather(d_send, d_recv, bytes, ncclUint8, ctx->comm, st));
+    return ETL_OK;
+  }
+  std::vector<uint8_t> hs(bytes), hr(bytes * (size_t)ctx->n_ranks);
+  CK(cudaMemcpyAsync(hs.data(), d_send, bytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (ctx->host_allgather(ctx->host_user, hs.data(), hr.data(), bytes) != 0) { ctx->last_error = "host all-gather callback failed"; return ETL_ERR_INTERNAL; }
+  CK(cudaMemcpyAsync(d_recv, hr.data(), hr.size(), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));                      // hr is a local
   return ETL_OK;
 }
 
@@ -524,14 +563,13 @@ void etl_dec_batch_free(etl_dec_batch* b) {
 // Where the structure-blind UTF-8 pass (k_utf8_dead, HBM-bound) runs relative to the latency-bound passes.
 // 0: side stream from the start of the index pass; 1: side stream from the start of the tuple pass (default);
 // 2: main stream after the tuple pass.
-// ETL_DEAD_MODE / ETL_DEAD_CTAS are tuning knobs for measurement, not part of the ABI.
+// ETL_DEAD_MODE is a tuning knob for measurement, not part of the ABI.
 static int dead_mode() {
   static const int m = getenv("ETL_DEAD_MODE") ? atoi(getenv("ETL_DEAD_MODE")) : 1;
   return m;
 }
-static int dead_ctas(int dflt) {
-  static const int c = getenv("ETL_DEAD_CTAS") ? atoi(getenv("ETL_DEAD_CTAS")) : 0;
-  return c > 0 ? c : dflt;
+static uint32_t dead_grid(const DecodeParams& P) {   // 8 warps per CTA, kDeadSegsPerWarp segments per warp; surplus CTAs return at once
+  return (uint32_t)((P.n_anchors + 8u * kDeadSegsPerWarp - 1u) / (8u * kDeadSegsPerWarp)) + 1u;
 }
 static int sm_count(etl_dec_ctx* ctx) {
   static int sms = 0;
@@ -543,7 +581,7 @@ static cudaError_t launch_dead_side(etl_dec_ctx* ctx, cudaStream_t st) {
   if ((e = cudaEventRecord(ctx->ev_in, st)) != cudaSuccess) return e;
   if ((e = cudaStreamWaitEvent(ctx->side, ctx->ev_in, 0)) != cudaSuccess) return e;
   if ((e = cudaEventRecord(ctx->ev_l0, ctx->side)) != cudaSuccess) return e;
-  k_utf8_dead<<<sm_count(ctx) * dead_ctas(3), 256, 0, ctx->side>>>(ctx->P);
+  k_utf8_dead<<<dead_grid(ctx->P), 256, 0, ctx->side>>>(ctx->P);
   if ((e = cudaEventRecord(ctx->ev_l1, ctx->side)) != cudaSuccess) return e;
   ctx->launches += 1;
   ctx->lines_launched = true;
@@ -585,7 +623,7 @@ static int exchange_relations(etl_dec_ctx* ctx, const etl_dec_input* in, std::ve
     }
     memcpy(s, &need, 8); memcpy(s + 8, &nf, 8);
     CK(cudaMemcpyAsync(ctx->d_rel_x.ptr(), s, std::min<uint64_t>(need, slot), cudaMemcpyHostToDevice, st));
-    CKN(nccl_api().AllGather(ctx->d_rel_x.ptr(), ctx->d_rel_x.ptr() + slot, slot, ncclUint8, ctx->comm, st));
+    if (int rc = ctx_allgather(ctx, ctx->d_rel_x.ptr(), ctx->d_rel_x.ptr() + slot, slot)) return rc;
     CK(cudaMemcpyAsync(ctx->h_rel_x + slot, ctx->d_rel_x.ptr() + slot, slot * ctx->n_ranks, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     uint64_t max_need = 0;
@@ -611,7 +649,7 @@ static int prepare(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t flags, bo
   const uint64_t n_anchors_expected = in->len ? (in->len + stride - 1) / stride : 0;
   if (in->n_anchors != n_anchors_expected || (in->n_anchors && !in->anchors && !in->dev_anchors)) { ctx->last_error = "anchors: expected ceil(len/stride) entries"; return ETL_ERR_INVALID_ARG; }
   if (in->n_relations && (!in->relation_offsets || !in->host_buf)) { ctx->last_error = "relation_offsets require host_buf"; return ETL_ERR_INVALID_ARG; }
-  if (sharded && (!ctx->comm || ctx->n_ranks < 2)) { ctx->last_error = "sharded decode needs etl_dec_comm_init with n_ranks >= 2"; return ETL_ERR_INVALID_ARG; }
+  if (sharded && !ctx->comm && !ctx->host_allgather) { ctx->last_error = "sharded decode needs etl_dec_comm_init / etl_dec_comm_init_host"; return ETL_ERR_INVALID_ARG; }
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   ctx->launches = 0;
@@ -880,6 +918,8 @@ static int launch_emit_kernels(etl_dec_ctx* ctx) {
   CK(cudaEventRecord(ctx->ev[3], st));
   CK(cudaMemsetAsync(P.bin_count, 0, P.n_bins * 4, st));
   CK(cudaMemsetAsync(P.perm, 0xFF, perm_cap * 4, st));
+  // k_heavy / k_fix read every cell tag: a record that failed leaves cells unwritten, and a stale tag must not look pending
+  if (P.cap_cells) CK(cudaMemsetAsync(P.cell_tag, 0, P.cap_cells, st));
   if (P.n_tiles) {
     k_frames<<<(P.n_anchors + 255) / 256, 256, 0, st>>>(P);
     cudaEventRecord(ctx->evk[0], st);
@@ -898,7 +938,7 @@ static int launch_emit_kernels(etl_dec_ctx* ctx) {
     if (ctx->lines_launched) CK(cudaStreamWaitEvent(st, ctx->ev_l1, 0));   // join: the bitmap is complete
     else {                                            // ETL_DEAD_MODE=2: the same pass on the main stream (tuning knob)
       cudaEventRecord(ctx->ev_l0, st);
-      k_utf8_dead<<<sm_count(ctx) * dead_ctas(6), 256, 0, st>>>(P);
+      k_utf8_dead<<<dead_grid(P), 256, 0, st>>>(P);
       cudaEventRecord(ctx->ev_l1, st);
       ctx->launches += 1;
     }
@@ -965,7 +1005,7 @@ static int run_decode(etl_dec_ctx* ctx, const etl_stream_state* carry_in, uint64
     CKB(cudaStreamSynchronize(st));
   }
   if (sharded) {
-    if (nccl_api().AllGather(P.seam_send, (void*)P.seam_all, sizeof(SeamBlock), ncclUint8, ctx->comm, st) != ncclSuccess) { ctx->last_error = "ncclAllGather(seam) failed"; return fail(ETL_ERR_CUDA); }
+    if (int rc = ctx_allgather(ctx, P.seam_send, (void*)P.seam_all, sizeof(SeamBlock))) return fail(rc);
     k_seam_fold<<<1, 32, 0, st>>>(P);
     ctx->launches += 2;
   }
@@ -1223,6 +1263,7 @@ int etl_dec_copy_decode(etl_dec_ctx* ctx, uint32_t table_id, const etl_copy_inpu
     *ctx->h_total = T;
     CKB(cudaMemcpyAsync(P.total, ctx->h_total, sizeof(Summ), cudaMemcpyHostToDevice, st));
     P.cap_records = nr; P.cap_cells = nc;
+    if (nc) CKB(cudaMemsetAsync(P.cell_tag, 0, nc, st));   // a row that failed leaves cells unwritten: k_heavy must not see stale tags
     CKB(cudaEventRecord(ctx->ev[1], st));
     if (nr) {
       k_copy_rows<<<(uint32_t)((nr + kRowsThreads - 1) / kRowsThreads), kRowsThreads, kRowsSmemBytes, st>>>(P);

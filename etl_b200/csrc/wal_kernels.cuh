@@ -471,6 +471,7 @@ __global__ void k_seam_fold(DecodeParams P) {
   Summ c = P.host_carry;
   uint64_t base = 0;
   for (uint32_t r = 0; r < P.rank; r++) { c = fold(c, P.seam_all[r].total); base += P.seam_all[r].total.n_rec; }
+  c.n_rec = 0; c.n_cells = 0;                          // the planes are this rank's own: only the stream state carries over
   DevCarry d; d.carry = c; d.record_index_base = base;
   *P.dc_out = d;
 }
@@ -573,11 +574,15 @@ __device__ __forceinline__ bool utf8_range_bad(const uint8_t* cell, uint32_t cel
 // three predecessors lie inside the cell.  A segment without a frame start lies inside one frame; the
 // segments that lie inside one text cell are what k_walk asks about.  One warp per dead segment, 2 KiB
 // (4 coalesced 16-byte loads per lane) per pass; the bitmap is written only where a violation is found.
+// Short-lived CTAs (a warp takes kDeadSegsPerWarp consecutive dead segments and retires): the pass runs on a low-priority
+// side stream underneath latency-bound kernels, and a persistent grid would sit on every SM's thread slots until it is
+// done — k_bin_scan / k_perm waited 1.6 ms for a slot behind it (round-2 sweep).  The grid is sized for "every segment dead".
+constexpr uint32_t kDeadSegsPerWarp = 4;
 __global__ void __launch_bounds__(256) k_utf8_dead(DecodeParams P) {
   const uint32_t n_dead = P.n_anchors - *P.n_act;
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; d < n_dead; d += nwarps) {
+  const uint32_t d0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kDeadSegsPerWarp;
+  for (uint32_t d = d0; d < min(d0 + kDeadSegsPerWarp, n_dead); d++) {
     const uint64_t s0 = (uint64_t)P.dead[d] * P.anchor_stride;
     const uint64_t s1 = s0 + P.anchor_stride < P.len ? s0 + P.anchor_stride : P.len;
     for (uint64_t base = s0; base < s1; base += 2048ull) {

@@ -217,6 +217,21 @@ class Decoder:
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         self._check(self._l.etl_dec_comm_init(self._ctx, C.cast(buf, C.c_void_p), 128, rank, n_ranks))
 
+    def comm_init_host(self, rank: int, n_ranks: int, allgather):
+        """Exchange through the host: `allgather(send: bytes) -> bytes` returns the n_ranks blocks in rank order
+        (e.g. torch.distributed with the gloo backend).  Same decode_sharded afterwards."""
+        def _cb(_user, send, recv, nbytes):
+            try:
+                out = allgather(C.string_at(send, nbytes))
+                if len(out) != nbytes * n_ranks:
+                    return 1
+                C.memmove(recv, out, len(out))
+                return 0
+            except Exception:  # noqa: BLE001 — reported through the status code
+                return 1
+        self._host_cb = abi.HOST_ALLGATHER_FN(_cb)      # keep the trampoline alive
+        self._check(self._l.etl_dec_comm_init_host(self._ctx, rank, n_ranks, self._host_cb, None))
+
     def decode_sharded(self, inp: abi.DecInput, to_host: bool = True) -> "BatchHandle":
         """This rank's byte range of one stream: relation-update exchange, index pass, seam all-gather and fold on
         the device, record + tuple passes (etl_dec_decode_sharded)."""

@@ -278,6 +278,10 @@ int etl_dec_mem_info(etl_dec_ctx*, uint64_t* free_bytes, uint64_t* total_bytes);
 #define ETL_COMM_ID_BYTES 128u
 int etl_dec_comm_unique_id(uint8_t* out, uint32_t cap);   /* rank 0; broadcast the bytes to the other ranks */
 int etl_dec_comm_init(etl_dec_ctx*, const uint8_t* unique_id, uint32_t id_bytes, int rank, int n_ranks);
+/* The same protocol with the two exchanges carried by the HOST (a box without NVLink/NCCL between the processes, tests
+ * on one GPU): `fn(user, send, recv, bytes)` must fill recv with the n_ranks blocks of `bytes` in rank order, return 0. */
+typedef int (*etl_host_allgather_fn)(void* user, const void* send, void* recv, uint64_t bytes);
+int etl_dec_comm_init_host(etl_dec_ctx*, int rank, int n_ranks, etl_host_allgather_fn fn, void* user);
 
 /* flags for etl_dec_decode */
 enum {

@@ -89,8 +89,9 @@ void orc_copy_planes_digest(const uint8_t* tags, const uint64_t* vals, const uin
   dg_u64(&d, n_valid_rows); dg_u64(&d, n_cols);
   for (uint64_t c = 0; c < n_valid_rows * n_cols; c++) {
     const uint64_t v = vals[c];
-    const int in_heap = (int)(v >> 63);
-    dg_copy_cell(&d, tags[c], v & ~(1ull << 63), auxs[c], (tags[c] == ETL_CELL_STRING || tags[c] == ETL_CELL_JSON) && !in_heap ? stream : heap, heap);
+    const int spanned = tags[c] == ETL_CELL_STRING || tags[c] == ETL_CELL_JSON;   /* only these carry the in-heap flag: bit 63 of an int cell is its sign */
+    const int in_heap = spanned && (v >> 63);
+    dg_copy_cell(&d, tags[c], spanned ? (v & ~(1ull << 63)) : v, auxs[c], in_heap ? heap : stream, heap);
   }
   for (int i = 0; i < 4; i++) out[i] = d.h[i];
 }

@@ -15,20 +15,33 @@ def main():
     import torch
     import torch.distributed as dist
     from etl_b200 import decoder, workloads as wl
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    host_mode = os.environ.get("ETL_TEST_HOST_EXCHANGE") == "1"    # every rank on GPU 0, the exchanges carried by gloo
+    dev_index = 0 if host_mode else rank
+    torch.cuda.set_device(dev_index)
+    if host_mode:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
     w = wl.make(name, scale, n_segments=1)
     if int(os.environ.get("ETL_TEST_BUMP", "0")):
         w.schema_bump_ppm = int(os.environ["ETL_TEST_BUMP"])
     stream, _ = w.generate()
     cuts = np.load(os.path.join(out_dir, "cuts.npy")).tolist()
     shard = stream[cuts[rank]:cuts[rank + 1]]
-    dec = decoder.Decoder(rank)
+    dec = decoder.Decoder(dev_index)
     for tid, cols in w.table_schemas().items():
         dec.put_table_schema(tid, cols)
-    uid = [dec.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(uid, src=0)
-    dec.comm_init(uid[0], rank, world)
+    if host_mode:
+        def allgather(send: bytes) -> bytes:
+            t = torch.frombuffer(bytearray(send), dtype=torch.uint8)
+            outs = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(outs, t)
+            return b"".join(o.numpy().tobytes() for o in outs)
+        dec.comm_init_host(rank, world, allgather)
+    else:
+        uid = [dec.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        dec.comm_init(uid[0], rank, world)
     st = decoder.Stager(max(shard.nbytes, 1), 2048)
     st.append_framed(shard)
     for rep in range(2):                                # second pass: optimistic sizing + carried relation state
@@ -40,7 +53,9 @@ def main():
     if os.environ.get("ETL_TEST_DIAG"):                 # the same range through the two-phase entry points, carry taken from the library's own answer
         from etl_b200 import sharding
         seam = dec.decode_begin(st.view(), to_host=True)
-        words = torch.from_numpy(sharding.seam_to_words(seam).view(np.int64).copy()).cuda()
+        words = torch.from_numpy(sharding.seam_to_words(seam).view(np.int64).copy())
+        if not host_mode:
+            words = words.cuda()
         allw = [torch.zeros_like(words) for _ in range(world)]
         dist.all_gather(allw, words)
         allw = np.stack([w_.cpu().numpy().view(np.uint64) for w_ in allw])

@@ -32,11 +32,14 @@ def _load_rank(path):
                            record_index_base=int(m[13]), schemas=schemas, **{k: z[k] for k in z.files if k not in ("meta", "schema_tables", "schema_offs", "schema_ident")})
 
 
-@pytest.mark.parametrize("name,scale,world", [("c2", 0.02, 2), ("c4", 0.002, 2), ("c4", 0.004, 4), ("c5", 0.004, 8)])
-def test_sharded_decode_matches_oracle(oracle_mod, tmp_path, name, scale, world):
+@pytest.mark.parametrize("name,scale,world,exchange", [("c2", 0.02, 2, "host"), ("c4", 0.002, 3, "host"), ("c5", 0.004, 4, "host"),
+                                                      ("c2", 0.02, 2, "nccl"), ("c4", 0.002, 2, "nccl"), ("c4", 0.004, 4, "nccl"), ("c5", 0.004, 8, "nccl")])
+def test_sharded_decode_matches_oracle(oracle_mod, tmp_path, name, scale, world, exchange):
     """ONE stream cut into `world` byte ranges inside transactions.  c4: 64 tables whose Relation messages all sit in
-    the first range, plus mid-stream schema bumps (replica identity flips) that later ranges must honour."""
-    if _gpus() < world:
+    the first range, plus mid-stream schema bumps (replica identity flips) that later ranges must honour.
+    exchange = "nccl": one process per GPU, the library's own communicator (needs `world` GPUs); "host": every rank
+    on GPU 0 with the two exchanges carried by gloo (etl_dec_comm_init_host) — the whole protocol on a one-GPU box."""
+    if _gpus() < (world if exchange == "nccl" else 1):
         pytest.skip(f"needs {world} GPUs")
     w = wl.make(name, scale, n_segments=1)
     if name == "c4":
@@ -50,7 +53,7 @@ def test_sharded_decode_matches_oracle(oracle_mod, tmp_path, name, scale, world)
     assert full.first_error[0] is None
     cuts = mid_tx_cuts(full, world) + [len(raw)]
     np.save(tmp_path / "cuts.npy", np.array(cuts, dtype=np.int64))
-    env = dict(os.environ, ETL_TEST_BUMP="3000" if name == "c4" else "0")
+    env = dict(os.environ, ETL_TEST_BUMP="3000" if name == "c4" else "0", ETL_TEST_HOST_EXCHANGE="1" if exchange == "host" else "0")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", "29611", os.path.join(ROOT, "tests", "sharded_worker.py"), str(tmp_path), name, str(scale)]
     r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240)
