@@ -297,7 +297,8 @@ def roofline_block(wname, nbytes, n_anchors, km, ms_per_step, last, scale):
     live = algo_bytes - span
     # bytes each kernel is responsible for: k_utf8_dead streams the segments without a frame start (the inside of
     # TOAST-sized values); k_rows every live byte (frames staged once) + the 13-byte cell it writes per output cell
-    kbytes = {"k_utf8_dead": span, "k_rows": live + 13 * int(last["n_cells"])}
+    fused_dead = span > 0 and float(km[4]) < 0.02       # the dead-segment pass runs inside k_rows (its warps stream the segments after their rows)
+    kbytes = {"k_utf8_dead": 0 if fused_dead else span, "k_rows": live + 13 * int(last["n_cells"]) + (span if fused_dead else 0)}
     ktime = {"k_utf8_dead": float(km[4]), "k_rows": float(km[3])}
     dominant = max(ktime, key=lambda k: ktime[k])
     achieved = kbytes[dominant] / max(ktime[dominant], 1e-9) / 1e6
@@ -310,7 +311,8 @@ def roofline_block(wname, nbytes, n_anchors, km, ms_per_step, last, scale):
     except Exception:
         pass
     kern = {"k_act*+k_index+k_scan+k_tile_prefix": float(km[0]), "k_frames": float(km[1]), "k_bin_scan+k_perm": float(km[2]),
-            "k_rows": float(km[3]), "k_utf8_dead (side stream, overlapped with k_rows)": float(km[4])}
+            "k_rows+k_heavy+k_fix" + (" (k_rows streams the dead segments too)" if fused_dead else ""): float(km[3]),
+            "k_utf8_dead (separate launch)": float(km[4])}
     return {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": kbytes[dominant],
             "avg_launch_ms": ktime[dominant],
@@ -319,8 +321,8 @@ def roofline_block(wname, nbytes, n_anchors, km, ms_per_step, last, scale):
                                  "source": "profiles/traffic.json (ncu launch list: kernels serialised, not sharing HBM)"} if alone_us else None),
             "kernels_ms": kern,
             "k_rows": {"algorithmic_bytes": kbytes["k_rows"], "ms": ktime["k_rows"], "frac": kbytes["k_rows"] / max(ktime["k_rows"], 1e-9) / 1e6 / peak},
-            "k_utf8_dead": {"algorithmic_bytes": span, "ms": ktime["k_utf8_dead"],
-                            "frac": (span / max(ktime["k_utf8_dead"], 1e-9) / 1e6 / peak) if span else None},
+            "k_utf8_dead": {"algorithmic_bytes": span, "ms": ktime["k_utf8_dead"], "fused_into_k_rows": fused_dead,
+                            "frac": (span / max(ktime["k_utf8_dead"], 1e-9) / 1e6 / peak) if (span and not fused_dead) else None},
             "pipeline": {"algorithmic_bytes": algo_bytes, "ms": ms_per_step,
                          "achieved": algo_bytes / (ms_per_step * 1e-3) / 1e9,
                          "frac": algo_bytes / (ms_per_step * 1e-3) / 1e9 / peak,

@@ -47,6 +47,11 @@ class CopyInput(C.Structure):
 HOST_ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64)
 
 
+class ArrowColumn(C.Structure):
+    _fields_ = [("arrow_type", C.c_uint32), ("_pad", C.c_uint32), ("validity", C.c_void_p), ("values", C.c_void_p),
+                ("offsets", C.c_void_p), ("data", C.c_void_p), ("data_bytes", C.c_uint64)]
+
+
 class Planes(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("n_cells", C.c_uint64), ("heap_bytes", C.c_uint64),
                 ("rec_off", C.c_void_p), ("rec_kind", C.c_void_p), ("rec_flags", C.c_void_p), ("rec_rel", C.c_void_p),
@@ -79,7 +84,8 @@ EXPORTS = [
     "etl_dec_decode_begin", "etl_dec_decode_finish", "etl_dec_batch_free", "etl_dec_batch_planes",
     "etl_dec_batch_summary", "etl_dec_batch_schema", "etl_dec_decode_sharded", "etl_dec_comm_unique_id", "etl_dec_comm_init", "etl_dec_comm_init_host",
     "etl_dec_kind_for_type_oid", "etl_dec_mem_info",
-    "etl_dec_copy_decode", "etl_shim_materialise", "etl_shim_event_count", "etl_shim_size_hint", "etl_shim_total_size_hint", "etl_shim_owned_bytes",
+    "etl_dec_copy_decode", "etl_dec_arrow_emit", "etl_dec_arrow_rows", "etl_dec_arrow_cols", "etl_dec_arrow_row_records",
+    "etl_dec_arrow_column", "etl_dec_arrow_free", "etl_dec_batch_device_stream", "etl_shim_materialise", "etl_shim_event_count", "etl_shim_size_hint", "etl_shim_total_size_hint", "etl_shim_owned_bytes",
     "etl_shim_json_text", "etl_shim_event_list_free",
 ]
 
@@ -137,6 +143,18 @@ def load(build: bool = True):
     L.etl_dec_kind_for_type_oid.restype = C.c_uint32
     L.etl_dec_mem_info.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.etl_dec_copy_decode.argtypes = [vp, C.c_uint32, C.POINTER(CopyInput), C.c_uint32, C.POINTER(vp)]
+    L.etl_dec_arrow_emit.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(vp)]
+    L.etl_dec_arrow_rows.argtypes = [vp]
+    L.etl_dec_arrow_rows.restype = C.c_uint64
+    L.etl_dec_arrow_cols.argtypes = [vp]
+    L.etl_dec_arrow_cols.restype = C.c_uint32
+    L.etl_dec_arrow_row_records.argtypes = [vp, C.c_int]
+    L.etl_dec_arrow_row_records.restype = C.c_void_p
+    L.etl_dec_arrow_column.argtypes = [vp, C.c_uint32, C.c_int, C.POINTER(ArrowColumn)]
+    L.etl_dec_arrow_free.argtypes = [vp]
+    L.etl_dec_arrow_free.restype = None
+    L.etl_dec_batch_device_stream.argtypes = [vp]
+    L.etl_dec_batch_device_stream.restype = C.c_void_p
     L.etl_shim_materialise.argtypes = [vp, vp, vp, C.POINTER(vp)]
     for f in ("etl_shim_event_count", "etl_shim_total_size_hint", "etl_shim_owned_bytes"):
         getattr(L, f).argtypes = [vp]

@@ -191,6 +191,7 @@ struct etl_dec_batch {
   size_t block_bytes = 0;
   etl_dec_summary summary{};
   std::vector<RelVersion> schemas;
+  const uint8_t* dev_stream = nullptr;   // the staged bytes the planes point into
 };
 
 struct etl_dec_ctx {
@@ -562,10 +563,10 @@ void etl_dec_batch_free(etl_dec_batch* b) {
 
 // Where the structure-blind UTF-8 pass (k_utf8_dead, HBM-bound) runs relative to the latency-bound passes.
 // 0: side stream from the start of the index pass; 1: side stream from the start of the tuple pass (default);
-// 2: main stream after the tuple pass.
+// 2: main stream after the tuple pass; 3 (default): inside k_rows — its warps stream the dead segments after their rows.
 // ETL_DEAD_MODE is a tuning knob for measurement, not part of the ABI.
 static int dead_mode() {
-  static const int m = getenv("ETL_DEAD_MODE") ? atoi(getenv("ETL_DEAD_MODE")) : 1;
+  static const int m = getenv("ETL_DEAD_MODE") ? atoi(getenv("ETL_DEAD_MODE")) : 3;
   return m;
 }
 static uint32_t dead_grid(const DecodeParams& P) {   // 8 warps per CTA, kDeadSegsPerWarp segments per warp; surplus CTAs return at once
@@ -924,6 +925,7 @@ static int launch_emit_kernels(etl_dec_ctx* ctx) {
     k_frames<<<(P.n_anchors + 255) / 256, 256, 0, st>>>(P);
     cudaEventRecord(ctx->evk[0], st);
     if (dead_mode() == 1 && !ctx->lines_launched) CK(launch_dead_side(ctx, st));   // underneath the tuple pass
+    P.dead_in_rows = (dead_mode() == 3 && cap_r) ? 1u : 0u;
     if (cap_r) {
       k_bin_scan<<<1, 1024, 0, st>>>(P);
       k_perm<<<(uint32_t)((cap_r + kPermThreads - 1) / kPermThreads), kPermThreads, 0, st>>>(P);
@@ -936,7 +938,8 @@ static int launch_emit_kernels(etl_dec_ctx* ctx) {
     } else cudaEventRecord(ctx->evk[2], st);
     cudaEventRecord(ctx->evk[1], st);
     if (ctx->lines_launched) CK(cudaStreamWaitEvent(st, ctx->ev_l1, 0));   // join: the bitmap is complete
-    else {                                            // ETL_DEAD_MODE=2: the same pass on the main stream (tuning knob)
+    else if (P.dead_in_rows) { cudaEventRecord(ctx->ev_l0, st); cudaEventRecord(ctx->ev_l1, st); }   // done by k_rows
+    else {                                            // ETL_DEAD_MODE=2 (or a batch without DML records): the same pass on the main stream
       cudaEventRecord(ctx->ev_l0, st);
       k_utf8_dead<<<dead_grid(P), 256, 0, st>>>(P);
       cudaEventRecord(ctx->ev_l1, st);
@@ -1140,10 +1143,12 @@ static int run_decode(etl_dec_ctx* ctx, const etl_stream_state* carry_in, uint64
   if (key == ~0ull) for (const RelVersion& v : ctx->foreign_installs) if (v.effective_off == 1) { ctx->current[v.table_id] = v; ctx->current[v.table_id].effective_off = 0; changed = true; }
   if (changed) ctx->tables_valid = false;
   ctx->pending_installs.clear(); ctx->foreign_installs.clear();
+  b->dev_stream = P.buf;
   *out = b;
   return ETL_OK;
 #undef CKB
 }
+const uint8_t* etl_dec_batch_device_stream(const etl_dec_batch* b) { return b ? b->dev_stream : nullptr; }
 
 int etl_dec_decode(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t flags, etl_dec_batch** out) {
   if (!ctx || !in || !out) return ETL_ERR_INVALID_ARG;
@@ -1321,6 +1326,7 @@ int etl_dec_copy_decode(etl_dec_ctx* ctx, uint32_t table_id, const etl_copy_inpu
     S.first_error.code = (uint32_t)(key & 63u); S.first_error.kind = error_kind_of(S.first_error.code);
   }
   S.n_events = nr;
+  b->dev_stream = P.buf;
   *out = b;
   return ETL_OK;
 #undef CKB

@@ -286,10 +286,8 @@ __device__ __forceinline__ uint32_t rk_step(const DecodeParams& P, Wk& w, TextCe
 }
 
 // pass C2: rows.  grid = chunks of kRowsThreads records of the binned order (+ padding), dynamic smem kRowsSmemBytes.
-__global__ void __launch_bounds__(kRowsThreads, ETL_ROWS_CTAS) k_rows(DecodeParams P) {
-  extern __shared__ __align__(128) uint8_t smem[];
+__device__ __forceinline__ void rows_body(const DecodeParams& P, uint8_t* smem) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (*P.abort_flag) return;
   const uint32_t n_perm = *P.perm_len;
   // chunk of the binned order for this CTA.  Bins are contiguous and differ in cost per record (an update
   // with a full old image walks twice the cells of an insert): consecutive CTAs take chunks 1/64 of the
@@ -474,6 +472,26 @@ __global__ void __launch_bounds__(kRowsThreads, ETL_ROWS_CTAS) k_rows(DecodePara
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) { si += __shfl_down_sync(0xffffffffu, si, d); su += __shfl_down_sync(0xffffffffu, su, d); sd += __shfl_down_sync(0xffffffffu, sd, d); }
   if (lane == 0) { if (si) atomicAdd(&P.metrics[0], si); if (su) atomicAdd(&P.metrics[1], su); if (sd) atomicAdd(&P.metrics[2], sd); }
+}
+// The kernel: the rows of this CTA's chunk, then — when the stream has segments without a frame start (TOAST-sized
+// values) and the host asked for it — this warp's share of the structure-blind UTF-8 pass.  The row work is bound by
+// instruction issue and shared-memory latency, the UTF-8 pass by HBM bandwidth: warps of one kernel that are in
+// different phases overlap the two without either waiting for thread slots held by the other's kernel (a separate
+// low-priority k_utf8_dead launch was starved by k_rows, which fills the register file: 3.1 ms instead of 1.5 ms).
+__global__ void __launch_bounds__(kRowsThreads, ETL_ROWS_CTAS) k_rows(DecodeParams P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  if (*P.abort_flag) return;
+  rows_body(P, smem);
+  if (P.dead_in_rows) {
+    const uint32_t n_dead = P.n_anchors - *P.n_act;
+    const uint32_t n_warps = gridDim.x * kRowsWarps, gw = blockIdx.x * kRowsWarps + (threadIdx.x >> 5);
+    const uint32_t q = (n_dead + n_warps - 1u) / n_warps;
+    // segment d of the compacted list goes to warp d % n_warps: consecutive warps stream consecutive segments
+    for (uint32_t k = 0; k < q; k++) {
+      const uint32_t d = k * n_warps + gw;
+      if (d < n_dead) utf8_dead_segment(P, d, threadIdx.x & 31u);
+    }
+  }
 }
 #undef W_DATA_ERROR
 #undef W_MALFORMED

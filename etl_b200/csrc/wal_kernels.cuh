@@ -112,6 +112,7 @@ struct DecodeParams {
   unsigned int* abort_flag;         // set by k_scan when the batch does not fit the planes the host reserved
   unsigned int* copy_count;         // unchanged-TOAST cells left for k_fix
   uint32_t copy_cols;               // COPY-row decode (copy_kernel.cuh): columns per row; 0 on the replication path
+  uint32_t dead_in_rows;            // 1: the warps of k_rows also stream the dead segments (no separate k_utf8_dead launch)
   uint64_t cap_records, cap_cells;  // capacity of the record / cell planes
   uint32_t* line_bad;               // k_utf8_dead: bit l set = line l (128 bytes) holds a UTF-8 rule violation (zeroed per batch)
   uint32_t* dead;                   // segments without a frame start (ascending); n_dead = n_anchors - *n_act
@@ -578,42 +579,44 @@ __device__ __forceinline__ bool utf8_range_bad(const uint8_t* cell, uint32_t cel
 // side stream underneath latency-bound kernels, and a persistent grid would sit on every SM's thread slots until it is
 // done — k_bin_scan / k_perm waited 1.6 ms for a slot behind it (round-2 sweep).  The grid is sized for "every segment dead".
 constexpr uint32_t kDeadSegsPerWarp = 4;
+// one dead segment (no frame starts inside it), by one warp
+__device__ __forceinline__ void utf8_dead_segment(const DecodeParams& P, uint32_t d, uint32_t lane) {
+  const uint64_t s0 = (uint64_t)P.dead[d] * P.anchor_stride;
+  const uint64_t s1 = s0 + P.anchor_stride < P.len ? s0 + P.anchor_stride : P.len;
+  for (uint64_t base = s0; base < s1; base += 2048ull) {
+    // every lane owns 64 contiguous bytes (half a 128-byte line): four 16-byte loads in flight, and the three
+    // bytes before its first chunk come from one 4-byte load that hits L1 — no shuffles (round 1 paid three
+    // __shfl per 16 bytes; they were a third of this kernel's stall samples)
+    const uint64_t off = base + (uint64_t)lane * 64ull;
+    uint4 x[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      x[k] = off + 16ull * k < s1 ? *reinterpret_cast<const uint4*>(P.buf + off + 16ull * k) : make_uint4(0, 0, 0, 0);   // +64 bytes of padding are readable
+    uint32_t pw = (off >= 4 && off < s1) ? *reinterpret_cast<const uint32_t*>(P.buf + off - 4) : 0u;   // last word before the lane's bytes
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t h = x[k].x | x[k].y | x[k].z | x[k].w;
+      if ((h & 0x80808080u) | (pw & 0x80808000u)) {             // high bits here or in the three bytes before
+        const uint64_t o = off + 16ull * k;
+        if (o < s1) bad |= !utf8_chunk_valid_at(P.buf, P.len, o, o + 16ull < P.len ? o + 16ull : P.len);
+      }
+      pw = x[k].w;
+    }
+    // two lanes per 128-byte line, 16 lines per pass: bit m of `word` = line m holds a violation
+    unsigned bal = __ballot_sync(0xffffffffu, bad);
+    bal = (bal | (bal >> 1)) & 0x55555555u;
+    bal = (bal | (bal >> 1)) & 0x33333333u; bal = (bal | (bal >> 2)) & 0x0F0F0F0Fu;
+    bal = (bal | (bal >> 4)) & 0x00FF00FFu; bal = (bal | (bal >> 8)) & 0x0000FFFFu;
+    // base is a multiple of min(stride, 2048): the (at most 16) bits of this pass stay inside one word
+    if (bal && lane == 0) atomicOr(&P.line_bad[(base >> 7) >> 5], bal << ((base >> 7) & 31u));
+  }
+}
 __global__ void __launch_bounds__(256) k_utf8_dead(DecodeParams P) {
   const uint32_t n_dead = P.n_anchors - *P.n_act;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t d0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kDeadSegsPerWarp;
-  for (uint32_t d = d0; d < min(d0 + kDeadSegsPerWarp, n_dead); d++) {
-    const uint64_t s0 = (uint64_t)P.dead[d] * P.anchor_stride;
-    const uint64_t s1 = s0 + P.anchor_stride < P.len ? s0 + P.anchor_stride : P.len;
-    for (uint64_t base = s0; base < s1; base += 2048ull) {
-      // every lane owns 64 contiguous bytes (half a 128-byte line): four 16-byte loads in flight, and the three
-      // bytes before its first chunk come from one 4-byte load that hits L1 — no shuffles (round 1 paid three
-      // __shfl per 16 bytes; they were a third of this kernel's stall samples)
-      const uint64_t off = base + (uint64_t)lane * 64ull;
-      uint4 x[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-        x[k] = off + 16ull * k < s1 ? *reinterpret_cast<const uint4*>(P.buf + off + 16ull * k) : make_uint4(0, 0, 0, 0);   // +64 bytes of padding are readable
-      uint32_t pw = (off >= 4 && off < s1) ? *reinterpret_cast<const uint32_t*>(P.buf + off - 4) : 0u;   // last word before the lane's bytes
-      bool bad = false;
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const uint32_t h = x[k].x | x[k].y | x[k].z | x[k].w;
-        if ((h & 0x80808080u) | (pw & 0x80808000u)) {             // high bits here or in the three bytes before
-          const uint64_t o = off + 16ull * k;
-          if (o < s1) bad |= !utf8_chunk_valid_at(P.buf, P.len, o, o + 16ull < P.len ? o + 16ull : P.len);
-        }
-        pw = x[k].w;
-      }
-      // two lanes per 128-byte line, 16 lines per pass: bit m of `word` = line m holds a violation
-      unsigned bal = __ballot_sync(0xffffffffu, bad);
-      bal = (bal | (bal >> 1)) & 0x55555555u;
-      bal = (bal | (bal >> 1)) & 0x33333333u; bal = (bal | (bal >> 2)) & 0x0F0F0F0Fu;
-      bal = (bal | (bal >> 4)) & 0x00FF00FFu; bal = (bal | (bal >> 8)) & 0x0000FFFFu;
-      // base is a multiple of min(stride, 2048): the (at most 16) bits of this pass stay inside one word
-      if (bal && lane == 0) atomicOr(&P.line_bad[(base >> 7) >> 5], bal << ((base >> 7) & 31u));
-    }
-  }
+  for (uint32_t d = d0; d < min(d0 + kDeadSegsPerWarp, n_dead); d++) utf8_dead_segment(P, d, lane);
 }
 // any flagged line in [l0, l1)?
 __device__ __forceinline__ bool lines_any_bad(const uint32_t* bm, uint64_t l0, uint64_t l1) {

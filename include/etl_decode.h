@@ -406,6 +406,49 @@ typedef struct etl_copy_input {
 } etl_copy_input;
 int etl_dec_copy_decode(etl_dec_ctx*, uint32_t table_id, const etl_copy_input*, uint32_t flags, etl_dec_batch** out);
 
+/* ---------------------------------------------------------------- columnar emitter
+ * The rows of ONE replicated-schema version of a decoded batch as Arrow-layout column buffers, built on the device.
+ * Replaces the per-row walk of the destinations' encoders (crates/etl-destinations/src/iceberg/encoding.rs:61-330:
+ * build_array_for_field and the cell_to_* converters; the DuckLake / BigQuery encoders walk the same Vec<TableRow>) for
+ * the column types whose Arrow value depends on the decoded cell alone.  Numeric / Json / Array columns (cell_to_string
+ * formatting in the reference) come back as ETL_ARROW_UNSUPPORTED and stay on the shim's row path.
+ * row_kinds: bit 0 inserts, bit 1 updates (new image, Full rows only), bit 2 deletes (old image, when Full); rows keep
+ * stream order and etl_dec_arrow_row_records gives the record index of each (for the CDC columns). */
+enum {
+  ETL_ARROW_UNSUPPORTED = 0,
+  ETL_ARROW_BOOLEAN = 1,        /* values bit-packed like the validity bitmap */
+  ETL_ARROW_INT32 = 2,          /* Cell::I16 | I32   (encoding.rs:200-206) */
+  ETL_ARROW_INT64 = 3,          /* Cell::I64 | U32   (:214-220) */
+  ETL_ARROW_FLOAT32 = 4,
+  ETL_ARROW_FLOAT64 = 5,
+  ETL_ARROW_UTF8 = 6,           /* int32 offsets[n_rows + 1] + data */
+  ETL_ARROW_LARGE_BINARY = 7,   /* int64 offsets[n_rows + 1] + data */
+  ETL_ARROW_DATE32 = 8,         /* days since 1970-01-01 (:257-262) */
+  ETL_ARROW_TIME64_US = 9,      /* microseconds since midnight (:270-275) */
+  ETL_ARROW_TIMESTAMP_US = 10,  /* naive, microseconds since the epoch (:284-289) */
+  ETL_ARROW_TIMESTAMPTZ_US = 11,/* UTC, microseconds since the epoch (:297-302) */
+  ETL_ARROW_UUID = 12,          /* FixedSizeBinary(16) */
+};
+typedef struct etl_arrow_column {
+  uint32_t arrow_type;
+  uint32_t _pad;
+  const uint8_t* validity;  /* bit i = row i is non-null (LSB first), ceil(n_rows / 8) bytes, zero padded to 64 */
+  const void* values;       /* fixed-width values, n_rows entries (Boolean: bit-packed); NULL for var-width columns */
+  const void* offsets;      /* var-width: n_rows + 1 offsets (int32 for UTF8, int64 for LARGE_BINARY) */
+  const uint8_t* data;      /* var-width: the bytes */
+  uint64_t data_bytes;
+} etl_arrow_column;
+typedef struct etl_arrow_batch etl_arrow_batch;
+int etl_dec_arrow_emit(const etl_dec_batch*, uint32_t schema_index, uint32_t row_kinds, int to_host, etl_arrow_batch** out);
+uint64_t etl_dec_arrow_rows(const etl_arrow_batch*);
+uint32_t etl_dec_arrow_cols(const etl_arrow_batch*);
+const uint64_t* etl_dec_arrow_row_records(const etl_arrow_batch*, int host);
+int etl_dec_arrow_column(const etl_arrow_batch*, uint32_t column, int host, etl_arrow_column* out);
+void etl_dec_arrow_free(etl_arrow_batch*);
+/* device address of the staged stream a batch was decoded from (string / json cells are offsets into it); valid until
+ * the next decode on the same context (library-owned copy) or as long as the caller's dev_buf lives */
+const uint8_t* etl_dec_batch_device_stream(const etl_dec_batch*);
+
 /* ---------------------------------------------------------------- shim stand-in (host only, no GPU work)
  * What the Rust shim does with the planes (replaces nothing in the reference — it is the glue that
  * rebuilds the reference's own types): materialise the AoS Vec<Event> handed to add_event_to_batch (apply.rs:433-439)
