@@ -730,6 +730,27 @@ __device__ __forceinline__ uint32_t parse_numeric_sync(unsigned mask, const uint
   uint32_t i0 = 0;
   bool neg = false;
   if (simple) { const uint32_t c0 = s[0]; if (c0 == '-') { neg = true; i0 = 1; } else if (c0 == '+') i0 = 1; }
+  uint32_t code = 0xFFFFFFFFu;   // sentinel: not handled by the fast path
+  // the specials as Postgres spells them (numeric.rs:256-278): NaN (unsigned), [+-]Infinity, [+-]inf — one lane with a
+  // NaN would otherwise send its whole row of 32 through the exact, lane-serial parser
+  if (simple && n - i0 >= 3u && n - i0 <= 8u) {
+    const uint32_t m = n - i0;
+    uint64_t wv = ldu64(s + i0);
+    if (m < 8u) wv &= (1ull << (8u * m)) - 1ull;
+    const uint64_t lw = wv | 0x2020202020202020ull;                       // ASCII letters → lower case (other bytes cannot become these words)
+    const uint64_t lmask = m < 8u ? (1ull << (8u * m)) - 1ull : ~0ull;
+    uint32_t kind = 0;
+    if (m == 3u && (lw & lmask) == 0x6E616Eull && i0 == 0u) kind = 1;                     // "nan"
+    else if ((m == 3u && (lw & lmask) == 0x666E69ull) || (m == 8u && lw == 0x7974696E69666E69ull)) kind = neg ? 3u : 2u;   // "inf" / "infinity"
+    if (kind) {
+      etl_numeric_hdr hdr;
+      hdr.kind = (uint8_t)kind; hdr.sign = 0; hdr.weight = 0; hdr.scale = 0; hdr.pushed_groups = 0;
+      const uint64_t off = hc.alloc(8);
+      *reinterpret_cast<etl_numeric_hdr*>(hc.heap + off) = hdr;
+      o.tag = ETL_CELL_NUMERIC; o.val = off; o.aux = 0;
+      code = 0; simple = false;
+    }
+  }
   // pass 1: shape
   uint32_t nint = 0, nfrac = 0, ndot = 0;
   uint32_t i = i0;
@@ -753,7 +774,6 @@ __device__ __forceinline__ uint32_t parse_numeric_sync(unsigned mask, const uint
     }
   }
   simple = simple && ndot <= 1 && (nint + nfrac) > 0;
-  uint32_t code = 0xFFFFFFFFu;   // sentinel: not handled by the fast path
   // numeric.rs:409-472 on the digit string D = int digits ++ frac digits
   const uint32_t ndec = nint + nfrac;
   const int64_t dweight = (int64_t)nint - 1;

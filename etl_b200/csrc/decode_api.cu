@@ -570,7 +570,8 @@ static int dead_mode() {
   return m;
 }
 static uint32_t dead_grid(const DecodeParams& P) {   // 8 warps per CTA, kDeadSegsPerWarp segments per warp; surplus CTAs return at once
-  return (uint32_t)((P.n_anchors + 8u * kDeadSegsPerWarp - 1u) / (8u * kDeadSegsPerWarp)) + 1u;
+  const uint64_t items = (uint64_t)P.n_anchors * (P.anchor_stride > 2048u ? P.anchor_stride / 2048u : 1u);
+  return (uint32_t)((items + 8u * kDeadSegsPerWarp - 1u) / (8u * kDeadSegsPerWarp)) + 1u;
 }
 static int sm_count(etl_dec_ctx* ctx) {
   static int sms = 0;

@@ -483,14 +483,11 @@ __global__ void __launch_bounds__(kRowsThreads, ETL_ROWS_CTAS) k_rows(DecodePara
   if (*P.abort_flag) return;
   rows_body(P, smem);
   if (P.dead_in_rows) {
-    const uint32_t n_dead = P.n_anchors - *P.n_act;
+    const uint32_t ppseg = dead_ppseg(P);
+    const uint32_t n_items = (P.n_anchors - *P.n_act) * ppseg;
     const uint32_t n_warps = gridDim.x * kRowsWarps, gw = blockIdx.x * kRowsWarps + (threadIdx.x >> 5);
-    const uint32_t q = (n_dead + n_warps - 1u) / n_warps;
-    // segment d of the compacted list goes to warp d % n_warps: consecutive warps stream consecutive segments
-    for (uint32_t k = 0; k < q; k++) {
-      const uint32_t d = k * n_warps + gw;
-      if (d < n_dead) utf8_dead_segment(P, d, threadIdx.x & 31u);
-    }
+    // item i goes to warp i % n_warps (consecutive warps stream consecutive 2 KiB); kDeadIlp items in flight per warp
+    for (uint32_t it = gw; it < n_items; it += (uint32_t)kDeadIlp * n_warps) utf8_dead_items(P, it, n_warps, n_items, ppseg, threadIdx.x & 31u);
   }
 }
 #undef W_DATA_ERROR

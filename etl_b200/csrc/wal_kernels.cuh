@@ -578,45 +578,62 @@ __device__ __forceinline__ bool utf8_range_bad(const uint8_t* cell, uint32_t cel
 // Short-lived CTAs (a warp takes kDeadSegsPerWarp consecutive dead segments and retires): the pass runs on a low-priority
 // side stream underneath latency-bound kernels, and a persistent grid would sit on every SM's thread slots until it is
 // done — k_bin_scan / k_perm waited 1.6 ms for a slot behind it (round-2 sweep).  The grid is sized for "every segment dead".
-constexpr uint32_t kDeadSegsPerWarp = 4;
-// one dead segment (no frame starts inside it), by one warp
-__device__ __forceinline__ void utf8_dead_segment(const DecodeParams& P, uint32_t d, uint32_t lane) {
-  const uint64_t s0 = (uint64_t)P.dead[d] * P.anchor_stride;
-  const uint64_t s1 = s0 + P.anchor_stride < P.len ? s0 + P.anchor_stride : P.len;
-  for (uint64_t base = s0; base < s1; base += 2048ull) {
-    // every lane owns 64 contiguous bytes (half a 128-byte line): four 16-byte loads in flight, and the three
-    // bytes before its first chunk come from one 4-byte load that hits L1 — no shuffles (round 1 paid three
-    // __shfl per 16 bytes; they were a third of this kernel's stall samples)
-    const uint64_t off = base + (uint64_t)lane * 64ull;
-    uint4 x[4];
+constexpr uint32_t kDeadSegsPerWarp = 4;      // = kDeadIlp: one call per warp
+// Work item i of the dead-segment pass = 2 KiB pass (i % ppseg) of dead segment (i / ppseg), ppseg = passes per segment.
+// A warp takes up to kDeadIlp items at once: every lane owns 64 contiguous bytes of each (half a 128-byte line), so
+// kDeadIlp x 4 16-byte loads are in flight per lane before the first byte is looked at; the three bytes before a lane's
+// first chunk come from one 4-byte load that hits L1 — no shuffles (round 1 paid three __shfl per 16 bytes).
+constexpr int kDeadIlp = 4;
+__device__ __forceinline__ void utf8_dead_items(const DecodeParams& P, uint32_t item0, uint32_t step, uint32_t n_items, uint32_t ppseg, uint32_t lane) {
+  uint4 x[kDeadIlp][4];
+  uint32_t pw[kDeadIlp];
+  uint64_t off[kDeadIlp], s1[kDeadIlp];
+#pragma unroll
+  for (int j = 0; j < kDeadIlp; j++) {
+    const uint32_t it = item0 + (uint32_t)j * step;
+    off[j] = 0; s1[j] = 0; pw[j] = 0;
+    if (it < n_items) {
+      const uint64_t seg0 = (uint64_t)P.dead[it / ppseg] * P.anchor_stride;
+      const uint64_t base = seg0 + (uint64_t)(it % ppseg) * 2048ull;
+      const uint64_t e = seg0 + P.anchor_stride < P.len ? seg0 + P.anchor_stride : P.len;
+      s1[j] = base < e ? e : 0;
+      off[j] = base + (uint64_t)lane * 64ull;
+    }
 #pragma unroll
     for (int k = 0; k < 4; k++)
-      x[k] = off + 16ull * k < s1 ? *reinterpret_cast<const uint4*>(P.buf + off + 16ull * k) : make_uint4(0, 0, 0, 0);   // +64 bytes of padding are readable
-    uint32_t pw = (off >= 4 && off < s1) ? *reinterpret_cast<const uint32_t*>(P.buf + off - 4) : 0u;   // last word before the lane's bytes
+      x[j][k] = off[j] + 16ull * k < s1[j] ? *reinterpret_cast<const uint4*>(P.buf + off[j] + 16ull * k) : make_uint4(0, 0, 0, 0);   // +64 bytes of padding are readable
+    if (off[j] >= 4 && off[j] < s1[j]) pw[j] = *reinterpret_cast<const uint32_t*>(P.buf + off[j] - 4);   // last word before the lane's bytes
+  }
+#pragma unroll
+  for (int j = 0; j < kDeadIlp; j++) {
     bool bad = false;
+    uint32_t prev = pw[j];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      const uint32_t h = x[k].x | x[k].y | x[k].z | x[k].w;
-      if ((h & 0x80808080u) | (pw & 0x80808000u)) {             // high bits here or in the three bytes before
-        const uint64_t o = off + 16ull * k;
-        if (o < s1) bad |= !utf8_chunk_valid_at(P.buf, P.len, o, o + 16ull < P.len ? o + 16ull : P.len);
+      const uint32_t h = x[j][k].x | x[j][k].y | x[j][k].z | x[j][k].w;
+      if ((h & 0x80808080u) | (prev & 0x80808000u)) {           // high bits here or in the three bytes before
+        const uint64_t o = off[j] + 16ull * k;
+        if (o < s1[j]) bad |= !utf8_chunk_valid_at(P.buf, P.len, o, o + 16ull < P.len ? o + 16ull : P.len);
       }
-      pw = x[k].w;
+      prev = x[j][k].w;
     }
-    // two lanes per 128-byte line, 16 lines per pass: bit m of `word` = line m holds a violation
+    // two lanes per 128-byte line, 16 lines per item: bit m = line m holds a violation
     unsigned bal = __ballot_sync(0xffffffffu, bad);
-    bal = (bal | (bal >> 1)) & 0x55555555u;
-    bal = (bal | (bal >> 1)) & 0x33333333u; bal = (bal | (bal >> 2)) & 0x0F0F0F0Fu;
-    bal = (bal | (bal >> 4)) & 0x00FF00FFu; bal = (bal | (bal >> 8)) & 0x0000FFFFu;
-    // base is a multiple of min(stride, 2048): the (at most 16) bits of this pass stay inside one word
-    if (bal && lane == 0) atomicOr(&P.line_bad[(base >> 7) >> 5], bal << ((base >> 7) & 31u));
+    if (bal) {
+      bal = (bal | (bal >> 1)) & 0x55555555u;
+      bal = (bal | (bal >> 1)) & 0x33333333u; bal = (bal | (bal >> 2)) & 0x0F0F0F0Fu;
+      bal = (bal | (bal >> 4)) & 0x00FF00FFu; bal = (bal | (bal >> 8)) & 0x0000FFFFu;
+      const uint64_t base = off[j] - (uint64_t)lane * 64ull;     // a multiple of min(stride, 2048): the bits stay inside one word
+      if (lane == 0) atomicOr(&P.line_bad[(base >> 7) >> 5], bal << ((base >> 7) & 31u));
+    }
   }
 }
+__device__ __forceinline__ uint32_t dead_ppseg(const DecodeParams& P) { return P.anchor_stride > 2048u ? P.anchor_stride / 2048u : 1u; }
 __global__ void __launch_bounds__(256) k_utf8_dead(DecodeParams P) {
-  const uint32_t n_dead = P.n_anchors - *P.n_act;
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t d0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kDeadSegsPerWarp;
-  for (uint32_t d = d0; d < min(d0 + kDeadSegsPerWarp, n_dead); d++) utf8_dead_segment(P, d, lane);
+  const uint32_t ppseg = dead_ppseg(P);
+  const uint32_t n_items = (P.n_anchors - *P.n_act) * ppseg;
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // warp w: items [w * kDeadSegsPerWarp, +kDeadSegsPerWarp)
+  if (w * kDeadSegsPerWarp < n_items) utf8_dead_items(P, w * kDeadSegsPerWarp, 1u, min(n_items, (w + 1u) * kDeadSegsPerWarp), ppseg, threadIdx.x & 31u);
 }
 // any flagged line in [l0, l1)?
 __device__ __forceinline__ bool lines_any_bad(const uint32_t* bm, uint64_t l0, uint64_t l1) {
@@ -643,9 +660,9 @@ __global__ void __launch_bounds__(256) k_long_cells(DecodeParams P) {
     bool bad = false;
     if (S0 < S1) {
       if (lane == 0) bad = lines_any_bad(P.line_bad, S0 >> 7, S1 >> 7);
-      if (c.edges) {
-        bad |= utf8_range_bad(P.buf + c.soff, c.len, 0u, (uint32_t)(S0 - c.soff), lane, 32u);
-        bad |= utf8_range_bad(P.buf + c.soff, c.len, (uint32_t)(S1 - c.soff), c.len, lane, 32u);
+      if (c.edges) {                                     // head on lanes 0-15, tail on lanes 16-31: one latency chain, not two
+        const bool tail = lane >= 16u;
+        bad |= utf8_range_bad(P.buf + c.soff, c.len, tail ? (uint32_t)(S1 - c.soff) : 0u, tail ? c.len : (uint32_t)(S0 - c.soff), lane & 15u, 16u);
       }
     } else if (c.edges) bad = utf8_range_bad(P.buf + c.soff, c.len, 0u, c.len, lane, 32u);
     if (__any_sync(0xffffffffu, bad) && lane == 0) report_error(P, P.dc->record_index_base + c.rec_local, c.seq, ETL_E_UTF8);
