@@ -563,10 +563,12 @@ void etl_dec_batch_free(etl_dec_batch* b) {
 
 // Where the structure-blind UTF-8 pass (k_utf8_dead, HBM-bound) runs relative to the latency-bound passes.
 // 0: side stream from the start of the index pass; 1: side stream from the start of the tuple pass (default);
-// 2: main stream after the tuple pass; 3 (default): inside k_rows — its warps stream the dead segments after their rows.
+// 2 (default): main stream after the tuple pass; 3: inside k_rows — its warps stream the dead segments after their rows.
+// Measured on C5 (10 GiB, round 2): 2 → 3.66 ms per decode, 0 → 3.96, 1 → 4.10, 3 → 4.24: k_rows fills the register file and
+// is bound by instruction issue, the UTF-8 pass needs every SM's warps to saturate HBM — sharing the SMs helps neither.
 // ETL_DEAD_MODE is a tuning knob for measurement, not part of the ABI.
 static int dead_mode() {
-  static const int m = getenv("ETL_DEAD_MODE") ? atoi(getenv("ETL_DEAD_MODE")) : 3;
+  static const int m = getenv("ETL_DEAD_MODE") ? atoi(getenv("ETL_DEAD_MODE")) : 2;
   return m;
 }
 static uint32_t dead_grid(const DecodeParams& P) {   // 8 warps per CTA, kDeadSegsPerWarp segments per warp; surplus CTAs return at once

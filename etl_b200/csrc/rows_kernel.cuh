@@ -476,8 +476,9 @@ __device__ __forceinline__ void rows_body(const DecodeParams& P, uint8_t* smem) 
 // The kernel: the rows of this CTA's chunk, then — when the stream has segments without a frame start (TOAST-sized
 // values) and the host asked for it — this warp's share of the structure-blind UTF-8 pass.  The row work is bound by
 // instruction issue and shared-memory latency, the UTF-8 pass by HBM bandwidth: warps of one kernel that are in
-// different phases overlap the two without either waiting for thread slots held by the other's kernel (a separate
-// low-priority k_utf8_dead launch was starved by k_rows, which fills the register file: 3.1 ms instead of 1.5 ms).
+// different phases overlap the two without either waiting for thread slots held by the other's kernel.  Measured (C5):
+// not faster than running k_utf8_dead after k_rows — 20 warps per SM cannot keep enough bytes in flight to saturate
+// HBM — so this is a tuning knob (ETL_DEAD_MODE=3), not the default.
 __global__ void __launch_bounds__(kRowsThreads, ETL_ROWS_CTAS) k_rows(DecodeParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   if (*P.abort_flag) return;

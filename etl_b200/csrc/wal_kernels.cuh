@@ -578,12 +578,12 @@ __device__ __forceinline__ bool utf8_range_bad(const uint8_t* cell, uint32_t cel
 // Short-lived CTAs (a warp takes kDeadSegsPerWarp consecutive dead segments and retires): the pass runs on a low-priority
 // side stream underneath latency-bound kernels, and a persistent grid would sit on every SM's thread slots until it is
 // done — k_bin_scan / k_perm waited 1.6 ms for a slot behind it (round-2 sweep).  The grid is sized for "every segment dead".
-constexpr uint32_t kDeadSegsPerWarp = 4;      // = kDeadIlp: one call per warp
+constexpr uint32_t kDeadSegsPerWarp = 4;
 // Work item i of the dead-segment pass = 2 KiB pass (i % ppseg) of dead segment (i / ppseg), ppseg = passes per segment.
 // A warp takes up to kDeadIlp items at once: every lane owns 64 contiguous bytes of each (half a 128-byte line), so
 // kDeadIlp x 4 16-byte loads are in flight per lane before the first byte is looked at; the three bytes before a lane's
 // first chunk come from one 4-byte load that hits L1 — no shuffles (round 1 paid three __shfl per 16 bytes).
-constexpr int kDeadIlp = 4;
+constexpr int kDeadIlp = 1;   // measured: 4 items (16 loads) per lane cost 102 registers and a quarter of the warps — 2.14 ms instead of 1.46 ms on C5
 __device__ __forceinline__ void utf8_dead_items(const DecodeParams& P, uint32_t item0, uint32_t step, uint32_t n_items, uint32_t ppseg, uint32_t lane) {
   uint4 x[kDeadIlp][4];
   uint32_t pw[kDeadIlp];
@@ -633,7 +633,8 @@ __global__ void __launch_bounds__(256) k_utf8_dead(DecodeParams P) {
   const uint32_t ppseg = dead_ppseg(P);
   const uint32_t n_items = (P.n_anchors - *P.n_act) * ppseg;
   const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // warp w: items [w * kDeadSegsPerWarp, +kDeadSegsPerWarp)
-  if (w * kDeadSegsPerWarp < n_items) utf8_dead_items(P, w * kDeadSegsPerWarp, 1u, min(n_items, (w + 1u) * kDeadSegsPerWarp), ppseg, threadIdx.x & 31u);
+  for (uint32_t it = w * kDeadSegsPerWarp; it < min(n_items, (w + 1u) * kDeadSegsPerWarp); it += (uint32_t)kDeadIlp)
+    utf8_dead_items(P, it, 1u, min(n_items, (w + 1u) * kDeadSegsPerWarp), ppseg, threadIdx.x & 31u);
 }
 // any flagged line in [l0, l1)?
 __device__ __forceinline__ bool lines_any_bad(const uint32_t* bm, uint64_t l0, uint64_t l1) {
