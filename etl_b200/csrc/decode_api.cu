@@ -122,6 +122,12 @@ struct DevBuf : DevBufBase {
   explicit DevBuf(std::vector<DevBufBase*>& reg) { reg.push_back(this); }
   T* ptr() const { return static_cast<T*>(p); }
   cudaError_t ensure(size_t n) { return ensure_bytes(n * sizeof(T)); }
+  // grow-only like ensure(); a new allocation starts out zeroed (look-back status words: epochs tell the launches apart)
+  cudaError_t ensure_zeroed(size_t n, cudaStream_t st) {
+    if (n * sizeof(T) <= cap_bytes) return cudaSuccess;
+    cudaError_t e = ensure(n);
+    return e == cudaSuccess ? cudaMemsetAsync(p, 0, cap_bytes, st) : e;
+  }
 };
 
 // ---- NCCL, resolved at run time: the library already loaded into the process (PyTorch bundles its own) is
@@ -164,7 +170,7 @@ NcclApi& nccl_api() {
 constexpr size_t kScalarWords = 16;
 // device scalar block: 16 words followed by the DevCarry
 //  [0] first_error key  [1..3] insert/update/delete bytes  [4] events  [5] heap_top  [7] long_count  [8] copy_count  [9] heap_overflow
-//  [10] arr_top  [11] perm_len  [12] n_act (k_act_scan)  [13] abort flag (k_scan)
+//  [10] arr_top  [11] perm_len  [12] n_act (k_act_scan)  [13] ABORT_* bits (k_chase, k_records)  [14] n_frames (k_chase)
 constexpr size_t kScalarBlockBytes = kScalarWords * 8 + sizeof(DevCarry);
 
 }  // namespace
@@ -206,8 +212,12 @@ struct etl_dec_ctx {
   std::vector<DevBufBase*> bufs;
   DevBuf<uint8_t> d_stream{bufs};
   DevBuf<uint64_t> d_anchors{bufs};
-  DevBuf<uint32_t> d_seg_frames{bufs}, d_act{bufs}, d_act_blk{bufs};
-  DevBuf<Summ> d_tile_summ{bufs}, d_group_summ{bufs}, d_group_prefix{bufs}, d_total{bufs}, d_tile_prefix{bufs}, d_seg_summ{bufs};
+  DevBuf<uint32_t> d_seg_rec_base{bufs}, d_act{bufs}, d_act_blk{bufs}, d_scan_status{bufs};
+  DevBuf<uint64_t> d_frame_off{bufs};      // frame offsets in stream order (k_chase → k_records)
+  DevBuf<unsigned long long> d_chase_status{bufs};
+  DevBuf<ScanSlot> d_scan_slots{bufs};
+  DevBuf<Summ> d_total{bufs};
+  uint32_t scan_epoch = 0;
   DevBuf<uint8_t> d_tables{bufs};          // DevSchema[] | schema_by_batch[] | col_kind[] | col_flags[] | relation errors
   DevBuf<uint32_t> d_line_bad{bufs}, d_dead{bufs}, d_bin_count{bufs}, d_bin_cursor{bufs}, d_perm{bufs}, d_rec_flen{bufs};
   DevBuf<LongCell> d_long{bufs};
@@ -713,10 +723,6 @@ static int prepare(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t flags, bo
   P.len = in->len;
   P.n_anchors = (uint32_t)in->n_anchors;
   P.anchor_stride = stride;
-  P.segs_per_tile = 32;  // one warp of anchor segments per tile
-  P.n_tiles = (P.n_anchors + P.segs_per_tile - 1) / P.segs_per_tile;
-  P.tiles_per_group = std::max<uint32_t>(1, kIndexThreads / P.segs_per_tile);
-  P.n_groups = (P.n_tiles + P.tiles_per_group - 1) / P.tiles_per_group;
 
   // ---- uploads
   CK(cudaEventRecord(ctx->ev[0], st));
@@ -794,10 +800,9 @@ static int prepare(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t flags, bo
     P.n_bins = (uint32_t)std::min<size_t>(kMaxBins, 16 * ctx->n_layouts);
     ctx->tables_valid = in->n_relations == 0 && !sharded;   // built from `current` alone: valid until a Relation arrives
   }
-  CK(ctx->d_seg_frames.ensure(P.n_anchors + 1)); CK(ctx->d_tile_summ.ensure(P.n_tiles + 1));
-  CK(ctx->d_group_summ.ensure(P.n_groups + 1)); CK(ctx->d_group_prefix.ensure(P.n_groups + 1));
-  CK(ctx->d_tile_prefix.ensure(P.n_tiles + 1)); CK(ctx->d_seg_summ.ensure(P.n_anchors + 1));
-  P.seg_summ = ctx->d_seg_summ.ptr(); P.tile_prefix = ctx->d_tile_prefix.ptr();
+  CK(ctx->d_seg_rec_base.ensure(P.n_anchors + 1));
+  CK(ctx->d_chase_status.ensure_zeroed((P.n_anchors + kChaseThreads - 1) / kChaseThreads + 1, st));
+  P.seg_rec_base = ctx->d_seg_rec_base.ptr(); P.chase_status = ctx->d_chase_status.ptr();
   const size_t line_words = (in->len + 4095) / 4096 + 1;
   CK(ctx->d_line_bad.ensure(line_words)); CK(ctx->d_dead.ensure(P.n_anchors + 1));
   P.line_bad = ctx->d_line_bad.ptr(); P.dead = ctx->d_dead.ptr();
@@ -805,11 +810,11 @@ static int prepare(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t flags, bo
   CK(ctx->d_long.ensure(P.long_cap));
   unsigned long long* sc = reinterpret_cast<unsigned long long*>(ctx->d_scalars.ptr());
   P.long_cells = ctx->d_long.ptr(); P.long_count = (unsigned int*)(sc + 7);
-  P.seg_frames = ctx->d_seg_frames.ptr(); P.tile_summ = ctx->d_tile_summ.ptr(); P.group_summ = ctx->d_group_summ.ptr();
-  P.group_prefix = ctx->d_group_prefix.ptr(); P.total = ctx->d_total.ptr();
+  P.total = ctx->d_total.ptr();
   P.first_error = sc; P.metrics = sc + 1;
   P.heap_top = sc + 5; P.heap_overflow = (unsigned int*)(sc + 9); P.arr_top = sc + 10;
   P.perm_len = (unsigned int*)(sc + 11); P.n_act = (unsigned int*)(sc + 12); P.abort_flag = (unsigned int*)(sc + 13);
+  P.n_frames = (unsigned int*)(sc + 14);
   P.copy_count = (unsigned int*)(sc + 8);
   P.dc = reinterpret_cast<const DevCarry*>(sc + kScalarWords); P.dc_out = reinterpret_cast<DevCarry*>(sc + kScalarWords);
   const uint32_t act_blocks = (P.n_anchors + kActThreads - 1) / kActThreads;
@@ -839,27 +844,76 @@ static int upload_scalars(etl_dec_ctx* ctx, size_t lo, size_t hi, const DevCarry
   return ETL_OK;
 }
 
-// ---------------------------------------------------------------- pass A + B
-static int launch_index(etl_dec_ctx* ctx) {
+// ---------------------------------------------------------------- pass A: live segments, frame offsets
+static uint32_t next_epoch(etl_dec_ctx* ctx) {
+  if (ctx->scan_epoch >= (1u << 30) - 2u) {          // the status words hold 30 bits of epoch: start over on zeroed words
+    if (ctx->d_chase_status.p) cudaMemsetAsync(ctx->d_chase_status.p, 0, ctx->d_chase_status.cap_bytes, ctx->stream);
+    if (ctx->d_scan_status.p) cudaMemsetAsync(ctx->d_scan_status.p, 0, ctx->d_scan_status.cap_bytes, ctx->stream);
+    ctx->scan_epoch = 0;
+  }
+  return ++ctx->scan_epoch;
+}
+// scratch of the record-parallel passes for up to `cap` frames
+static int ensure_record_scratch(etl_dec_ctx* ctx, uint64_t cap) {
+  DecodeParams& P = ctx->P;
+  const size_t nb = (size_t)((cap + kRecThreads - 1) / kRecThreads) + 1;
+  CK(ctx->d_frame_off.ensure(cap + 1));
+  CK(ctx->d_scan_status.ensure_zeroed(nb, ctx->stream));
+  CK(ctx->d_scan_slots.ensure(nb));
+  P.frame_off = ctx->d_frame_off.ptr(); P.frame_cap = cap;
+  P.scan_status = ctx->d_scan_status.ptr(); P.scan_slots = ctx->d_scan_slots.ptr();
+  return ETL_OK;
+}
+static void launch_chase(etl_dec_ctx* ctx, uint32_t mode) {
+  DecodeParams& P = ctx->P;
+  if (mode & 1u) P.scan_epoch = next_epoch(ctx);
+  k_chase<<<(P.n_anchors + kChaseThreads - 1) / kChaseThreads, kChaseThreads, 0, ctx->stream>>>(P, mode);
+  ctx->launches += 1;
+}
+// totals only (FULL = false) or the record plane (FULL = true); `n_max` bounds the number of frames
+static void launch_records(etl_dec_ctx* ctx, bool full, uint64_t n_max) {
+  DecodeParams& P = ctx->P;
+  P.scan_epoch = next_epoch(ctx);
+  const uint32_t grid = (uint32_t)std::max<uint64_t>(1, (n_max + kRecThreads - 1) / kRecThreads);
+  if (full) k_records<true><<<grid, kRecThreads, 0, ctx->stream>>>(P);
+  else k_records<false><<<grid, kRecThreads, 0, ctx->stream>>>(P);
+  ctx->launches += 1;
+}
+// Optimistic (exact = false): the offset scratch is sized by the caller; one launch counts, scans and writes.
+// Exact: count, read the count back, size the scratch, write.
+static int launch_index(etl_dec_ctx* ctx, bool exact) {
   DecodeParams& P = ctx->P;
   cudaStream_t st = ctx->stream;
   CK(cudaEventRecord(ctx->ev[1], st));
-  if (P.n_groups) {
+  if (P.n_anchors) {
     const uint32_t act_blocks = (P.n_anchors + kActThreads - 1) / kActThreads;
     k_act_count<<<act_blocks, kActThreads, 0, st>>>(P);
     k_act_scan<<<1, kActThreads, 0, st>>>(P, act_blocks);
     k_act_scatter<<<act_blocks, kActThreads, 0, st>>>(P);
+    ctx->launches += 3;
     if (dead_mode() == 0) CK(launch_dead_side(ctx, st));   // underneath everything that follows (needs only the dead-segment list)
-    k_index<<<P.n_groups, P.tiles_per_group * P.segs_per_tile, 0, st>>>(P);
-    k_scan<<<1, 512, 0, st>>>(P);
-    k_tile_prefix<<<(P.n_tiles + 255) / 256, 256, 0, st>>>(P);
-    ctx->launches += 6;
+    if (!exact) launch_chase(ctx, 3u);
+    else {
+      P.frame_cap = ~0ull;
+      launch_chase(ctx, 1u);
+      CK(cudaMemcpyAsync(ctx->h_scalars + 14, ctx->d_scalars.ptr() + 14 * 8, 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (int rc = ensure_record_scratch(ctx, (uint32_t)ctx->h_scalars[14])) return rc;
+      launch_chase(ctx, 2u);
+    }
     CK(cudaGetLastError());
-  } else {
-    CK(cudaMemsetAsync(P.total, 0, sizeof(Summ), st));
-    if (P.seam_send) CK(cudaMemsetAsync(P.seam_send, 0, sizeof(SeamBlock), st));
-  }
+  } else if (int rc = ensure_record_scratch(ctx, 0)) return rc;
   CK(cudaEventRecord(ctx->ev[2], st));
+  return ETL_OK;
+}
+// exact totals of the batch (P.total, the seam block) without planes: a SUMMARY pass with unlimited capacities
+static int launch_summary(etl_dec_ctx* ctx) {
+  DecodeParams& P = ctx->P;
+  const uint64_t keep_r = P.cap_records, keep_c = P.cap_cells;
+  P.cap_records = ~0ull; P.cap_cells = ~0ull;
+  launch_records(ctx, false, P.frame_cap);
+  P.cap_records = keep_r; P.cap_cells = keep_c;
+  CK(cudaGetLastError());
   return ETL_OK;
 }
 
@@ -924,8 +978,8 @@ static int launch_emit_kernels(etl_dec_ctx* ctx) {
   CK(cudaMemsetAsync(P.perm, 0xFF, perm_cap * 4, st));
   // k_heavy / k_fix read every cell tag: a record that failed leaves cells unwritten, and a stale tag must not look pending
   if (P.cap_cells) CK(cudaMemsetAsync(P.cell_tag, 0, P.cap_cells, st));
-  if (P.n_tiles) {
-    k_frames<<<(P.n_anchors + 255) / 256, 256, 0, st>>>(P);
+  if (P.n_anchors) {
+    launch_records(ctx, true, cap_r);
     cudaEventRecord(ctx->evk[0], st);
     if (dead_mode() == 1 && !ctx->lines_launched) CK(launch_dead_side(ctx, st));   // underneath the tuple pass
     P.dead_in_rows = (dead_mode() == 3 && cap_r) ? 1u : 0u;
@@ -949,9 +1003,8 @@ static int launch_emit_kernels(etl_dec_ctx* ctx) {
       ctx->launches += 1;
     }
     if (cap_r) { k_long_cells<<<sm_count(ctx) * 8, 256, 0, st>>>(P); ctx->launches += 1; }
-    ctx->launches += 1;
     CK(cudaGetLastError());
-  } else { cudaEventRecord(ctx->evk[0], st); cudaEventRecord(ctx->evk[2], st); cudaEventRecord(ctx->evk[1], st); cudaEventRecord(ctx->ev_l0, st); cudaEventRecord(ctx->ev_l1, st); }
+  } else { CK(cudaMemsetAsync(P.total, 0, sizeof(Summ), st)); cudaEventRecord(ctx->evk[0], st); cudaEventRecord(ctx->evk[2], st); cudaEventRecord(ctx->evk[1], st); cudaEventRecord(ctx->ev_l0, st); cudaEventRecord(ctx->ev_l1, st); }
   CK(cudaEventRecord(ctx->ev[4], st));
   CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars.ptr(), kScalarWords * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(ctx->h_total, P.total, sizeof(Summ), cudaMemcpyDeviceToHost, st));
@@ -969,7 +1022,7 @@ static Summ carry_of(const etl_stream_state* cin) {
 
 // one decode, common to every entry point.  mode 0: one-shot (optimistic sizing); 1: after decode_begin (totals known)
 static int run_decode(etl_dec_ctx* ctx, const etl_stream_state* carry_in, uint64_t record_index_base, bool sharded, bool totals_known,
-                      etl_dec_batch** out) {
+                      etl_dec_batch** out, bool force_exact = false) {
   cudaStream_t st = ctx->stream;
   DecodeParams& P = ctx->P;
   etl_dec_batch* b = new etl_dec_batch();
@@ -980,62 +1033,92 @@ static int run_decode(etl_dec_ctx* ctx, const etl_stream_state* carry_in, uint64
   const Summ host_carry = carry_of(carry_in);
   P.host_carry = host_carry;
   DevCarry dc; dc.carry = host_carry; dc.record_index_base = record_index_base;
+  auto reset_abort = [&]() -> cudaError_t {
+    ctx->h_scalars[13] = 0;
+    return cudaMemcpyAsync(ctx->d_scalars.ptr() + 13 * 8, ctx->h_scalars + 13, 8, cudaMemcpyHostToDevice, st);
+  };
 
-  uint64_t cap_r, cap_c;
+  uint64_t cap_r = 0, cap_c = 0;
   bool exact = totals_known;
   if (!totals_known) {
     if (int rc = upload_scalars(ctx, 0, kScalarWords, &dc)) return fail(rc);
     // optimistic sizes from what earlier batches needed per byte; the first batch has no history: exact path
-    if (ctx->rec_per_byte > 0) {
+    if (ctx->rec_per_byte > 0 && !force_exact) {
       cap_r = (uint64_t)(P.len * ctx->rec_per_byte * 1.08) + 4096;
       cap_c = (uint64_t)(P.len * ctx->cells_per_byte * 1.08) + 16384;
-    } else { cap_r = cap_c = 0; exact = true; }
-    P.cap_records = exact ? ~0ull : cap_r; P.cap_cells = exact ? ~0ull : cap_c;   // k_scan decides with these
+    } else exact = true;
+    P.cap_records = exact ? ~0ull : cap_r; P.cap_cells = exact ? ~0ull : cap_c;   // k_chase / k_records decide with these
     P.rec_cell_base = nullptr;
   } else {
-    if (int rc = upload_scalars(ctx, 0, 12, nullptr)) return fail(rc);           // [12] n_act survives from decode_begin
-    ctx->h_scalars[13] = 0;
-    CKB(cudaMemcpyAsync(ctx->d_scalars.ptr() + 13 * 8, ctx->h_scalars + 13, 8, cudaMemcpyHostToDevice, st));
+    if (int rc = upload_scalars(ctx, 0, 12, nullptr)) return fail(rc);           // [12] n_act, [14] n_frames survive from decode_begin
+    CKB(reset_abort());
     memcpy(ctx->h_scalars + kScalarWords, &dc, sizeof dc);
     CKB(cudaMemcpyAsync(ctx->d_scalars.ptr() + kScalarWords * 8, ctx->h_scalars + kScalarWords, sizeof dc, cudaMemcpyHostToDevice, st));
   }
   PlaneLayout L{};
   uint64_t scalar_heap = 0, array_heap = 0, heap_used = 0;
   if (!totals_known && !exact) {
-    // planes first (k_scan writes the tail of rec_cell_base), then the whole pipeline without a host round trip
+    // planes and offset scratch first, then the whole pipeline without a host round trip.  The scratch is cheap
+    // (8 bytes per frame): twice the expected count, so that only the planes can realistically be too small.
     if (int rc = launch_emit(ctx, b, cap_r, cap_c, 0, &L, &scalar_heap)) return fail(rc);
-    if (int rc = launch_index(ctx)) return fail(rc);
+    if (int rc = ensure_record_scratch(ctx, 2 * cap_r + 65536)) return fail(rc);
+    if (int rc = launch_index(ctx, false)) return fail(rc);
+    if (sharded) { if (int rc = launch_summary(ctx)) return fail(rc); }          // the seam block, before the exchange
   } else if (!totals_known) {
-    if (int rc = launch_index(ctx)) return fail(rc);
-    CKB(cudaMemcpyAsync(ctx->h_total, P.total, sizeof(Summ), cudaMemcpyDeviceToHost, st));
-    CKB(cudaStreamSynchronize(st));
+    if (int rc = launch_index(ctx, true)) return fail(rc);
+    if (int rc = launch_summary(ctx)) return fail(rc);
+    if (!sharded) {
+      CKB(cudaMemcpyAsync(ctx->h_total, P.total, sizeof(Summ), cudaMemcpyDeviceToHost, st));
+      CKB(cudaStreamSynchronize(st));
+    }
   }
   if (sharded) {
     if (int rc = ctx_allgather(ctx, P.seam_send, (void*)P.seam_all, sizeof(SeamBlock))) return fail(rc);
     k_seam_fold<<<1, 32, 0, st>>>(P);
     ctx->launches += 2;
+    if (exact && !totals_known) {
+      CKB(cudaMemcpyAsync(ctx->h_total, P.total, sizeof(Summ), cudaMemcpyDeviceToHost, st));
+      CKB(cudaStreamSynchronize(st));
+    }
   }
+  std::vector<SeamBlock> seams;                        // sharded: every rank's totals (read back after the first pass)
   for (int attempt = 0;; attempt++) {
     if (exact) {
       const Summ T = *ctx->h_total;
       if (b->dev_block) { CKB(cudaFreeAsync(b->dev_block, st)); b->dev_block = nullptr; }
       if (int rc = launch_emit(ctx, b, T.n_rec, T.n_cells, array_heap, &L, &scalar_heap)) return fail(rc);
-      CKB(cudaMemcpyAsync((void*)(b->dev.rec_cell_base + T.n_rec), &ctx->h_total->n_cells, 8, cudaMemcpyHostToDevice, st));
       if (attempt > 0 || totals_known) {              // a re-run of pass C: fresh scalars, the carry block stays
         if (int rc = upload_scalars(ctx, 0, 12, nullptr)) return fail(rc);
-        ctx->h_scalars[13] = 0;
-        CKB(cudaMemcpyAsync(ctx->d_scalars.ptr() + 13 * 8, ctx->h_scalars + 13, 8, cudaMemcpyHostToDevice, st));
+        CKB(reset_abort());
       }
     }
     if (int rc = launch_emit_kernels(ctx)) return fail(rc);
     CKB(cudaStreamSynchronize(st));
-    const Summ T = *ctx->h_total;
-    if (ctx->h_scalars[13]) {                         // did not fit the optimistic planes: exact sizes, pass C again
+    if (sharded && seams.empty()) {
+      seams.resize(ctx->n_ranks);
+      CKB(cudaMemcpy(seams.data(), P.seam_all, sizeof(SeamBlock) * ctx->n_ranks, cudaMemcpyDeviceToHost));
+    }
+    const uint32_t aborted = (uint32_t)ctx->h_scalars[13];
+    bool scratch_short = (aborted & ABORT_SCRATCH) != 0;
+    for (const SeamBlock& sb : seams) scratch_short = scratch_short || (sb.total.flags & 0x80000000u);   // some rank could not form its totals
+    if (scratch_short) {
+      // more frames than the offset scratch holds (2x what earlier batches needed): start over on the exact path.
+      // Sharded: every rank sees the same gathered blocks, so every rank takes this branch and the exchange is repeated.
+      if (force_exact) { ctx->last_error = "offset scratch overflow on the exact path"; return fail(ETL_ERR_CUDA); }
+      fail(0);
+      return run_decode(ctx, carry_in, record_index_base, sharded, false, out, true);
+    }
+    if (aborted) {                                     // did not fit the optimistic planes: exact sizes, pass C again
+      CKB(reset_abort());
+      if (int rc = launch_summary(ctx)) return fail(rc);
+      CKB(cudaMemcpyAsync(ctx->h_total, P.total, sizeof(Summ), cudaMemcpyDeviceToHost, st));
+      CKB(cudaStreamSynchronize(st));
       exact = true;
       ctx->lines_launched = false;
       CKB(cudaMemsetAsync(P.line_bad, 0, ((P.len + 4095) / 4096 + 1) * 4, st));
       continue;
     }
+    const Summ T = *ctx->h_total;
     heap_used = P.heap_cap;
     if (P.heap_cap) heap_used = std::min<uint64_t>(P.heap_cap, ctx->h_scalars[10] ? scalar_heap + ctx->h_scalars[10] : ctx->h_scalars[5]);
     if (ctx->h_scalars[9]) {                          // an array reservation did not fit: larger array region, pass C again
@@ -1096,7 +1179,7 @@ static int run_decode(etl_dec_ctx* ctx, const etl_stream_state* carry_in, uint64
   if (ctx->pending_flags & ETL_DECODE_RESULTS_TO_HOST) { float whole = 0; cudaEventElapsedTime(&whole, ctx->ev[3], ctx->ev[5]); emit_ms = whole - d2h_ms; }
   S.kernel_ms = index_ms + emit_ms;
   S.index_ms = index_ms; S.emit_ms = emit_ms;
-  if (P.n_tiles) {
+  if (P.n_anchors) {
     cudaEventElapsedTime(&S.frames_ms, ctx->ev[3], ctx->evk[0]);
     cudaEventElapsedTime(&S.walk_ms, ctx->evk[0], ctx->evk[2]);    // k_bin_scan + k_perm
     cudaEventElapsedTime(&S.cells_ms, ctx->evk[2], ctx->evk[1]);   // k_rows
@@ -1105,7 +1188,7 @@ static int run_decode(etl_dec_ctx* ctx, const etl_stream_state* carry_in, uint64
   S.h2d_ms = h2d_ms; S.d2h_ms = d2h_ms;
   S.h2d_bytes = ctx->pending_h2d_bytes;
   // bytes k_utf8_dead streamed: the dead segments (h_scalars[12] = live segment count, left by k_act_scan)
-  S.span_bytes = P.n_tiles ? std::min<uint64_t>(P.len, (uint64_t)(P.n_anchors - (uint32_t)ctx->h_scalars[12]) * P.anchor_stride) : 0;
+  S.span_bytes = P.n_anchors ? std::min<uint64_t>(P.len, (uint64_t)(P.n_anchors - (uint32_t)ctx->h_scalars[12]) * P.anchor_stride) : 0;
   S.d2h_bytes = d2h_bytes;
   S.gpu_launches = ctx->launches;
   S.n_schemas = (uint32_t)b->schemas.size();
@@ -1122,8 +1205,7 @@ static int run_decode(etl_dec_ctx* ctx, const etl_stream_state* carry_in, uint64
   // carry-out: this shard's end state (sharded: relative to the folded carry, read back only when asked for below)
   Summ endst = fold(host_carry, T);
   if (sharded) {                                       // the stream state after the LAST shard = fold over all seams
-    std::vector<SeamBlock> all(ctx->n_ranks);
-    CKB(cudaMemcpy(all.data(), P.seam_all, sizeof(SeamBlock) * ctx->n_ranks, cudaMemcpyDeviceToHost));
+    const std::vector<SeamBlock>& all = seams;
     endst = host_carry;
     uint64_t base = 0;
     for (int r = 0; r < ctx->n_ranks; r++) { if (r < ctx->rank) base += all[r].total.n_rec; endst = fold(endst, all[r].total); }
@@ -1170,7 +1252,8 @@ int etl_dec_decode_begin(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t fla
   DecodeParams& P = ctx->P;
   P.cap_records = ~0ull; P.cap_cells = ~0ull; P.rec_cell_base = nullptr;
   if (int rc = upload_scalars(ctx, 0, kScalarWords, nullptr)) return rc;
-  if (int rc = launch_index(ctx)) return rc;
+  if (int rc = launch_index(ctx, true)) return rc;
+  if (int rc = launch_summary(ctx)) return rc;
   CK(cudaMemcpyAsync(ctx->h_total, P.total, sizeof(Summ), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   const Summ& T = *ctx->h_total;

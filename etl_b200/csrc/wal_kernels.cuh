@@ -35,6 +35,7 @@ namespace etl {
 constexpr int kIndexThreads = 256;
 constexpr int kMaxBins = 4096;         // 16 frame shapes x 256 schema versions (more versions share the last bins)
 
+struct ScanSlot;
 struct LongCell { uint32_t rec_local, seq; uint64_t soff; uint32_t len, edges; };   // a text cell of ≥ kCoopLen bytes; edges: its head and tail are still to be validated
 
 // ---- stream-state transformer (apply.rs:600-626, 1927-2006) + counters; associative under fold()
@@ -89,27 +90,25 @@ struct DecodeParams {
   const uint64_t* anchors;   // n_anchors + 1 entries (last = len)
   uint32_t n_anchors;
   uint32_t anchor_stride;
-  uint32_t segs_per_tile;
-  uint32_t n_tiles;
-  uint32_t tiles_per_group;  // tiles folded per k_index CTA
-  uint32_t n_groups;
   const DevSchema* schemas;  // sorted by (table_id, effective_off)
   uint32_t n_schemas;
   const uint8_t* col_kind;
   const uint8_t* col_flags;  // bit0 nullable, bit1 identity
-  // pass A outputs
-  uint32_t* seg_frames;      // frames starting in each segment
-  Summ* seg_summ;            // per segment: summary (pass A) → exclusive prefix (pass B2), carry not included
-  Summ* tile_summ;           // per tile
-  Summ* group_summ;          // per group of tiles
-  Summ* group_prefix;        // exclusive prefix per group (pass B)
+  // pass A (k_chase): frame offsets in stream order + the scan state of the two single-pass scans
+  uint64_t* frame_off;       // offset of frame r (scratch of the context: k_records copies it into the rec_off plane)
+  uint64_t frame_cap;        // entries frame_off can hold
+  uint32_t* seg_rec_base;    // per live segment: index of its first frame
+  unsigned int* n_frames;    // frames (= records) of the batch
+  unsigned long long* chase_status;   // k_chase look-back words (zero-initialised once; epochs tell launches apart)
+  uint32_t* scan_status;     // k_records look-back words
+  struct ScanSlot* scan_slots;
+  uint32_t scan_epoch;       // changes with every launch of a scanning kernel
   Summ* total;               // [0] = fold of everything (shard seam summary)
-  Summ* tile_prefix;         // exclusive prefix per tile (pass B2), carry not included
   // global grouping of the DML records by frame shape (k_frames counts, k_bin_scan lays out, k_perm fills)
   uint32_t* bin_count; uint32_t* bin_cursor; uint32_t n_bins; uint32_t* perm; unsigned int* perm_len;
   uint32_t n_batch_schemas;
   uint32_t* rec_flen;               // CopyData length + 1 of every record's frame (k_frames → k_rows: sizes the staged window)
-  unsigned int* abort_flag;         // set by k_scan when the batch does not fit the planes the host reserved
+  unsigned int* abort_flag;         // ABORT_* bits: the batch does not fit the planes / scratch the host reserved (k_chase, k_records)
   unsigned int* copy_count;         // unchanged-TOAST cells left for k_fix
   uint32_t copy_cols;               // COPY-row decode (copy_kernel.cuh): columns per row; 0 on the replication path
   uint32_t dead_in_rows;            // 1: the warps of k_rows also stream the dead segments (no separate k_utf8_dead launch)
@@ -357,111 +356,94 @@ __global__ void __launch_bounds__(kActThreads) k_act_scatter(DecodeParams P) {
   if (live) P.act[live_rank] = seg;
   else if (seg < P.n_anchors) P.dead[seg - live_rank] = seg;
 }
-// compacted geometry, derived on the device
-struct ActGeom { uint32_t n_act, n_tiles, n_groups; };
-__device__ __forceinline__ ActGeom act_geom(const DecodeParams& P) {
-  ActGeom g;
-  g.n_act = *P.n_act;
-  g.n_tiles = (g.n_act + P.segs_per_tile - 1) / P.segs_per_tile;
-  g.n_groups = (g.n_tiles + P.tiles_per_group - 1) / P.tiles_per_group;
-  return g;
-}
-
 // ================================================================================================
-// pass A: index.  grid = n_groups, block = tiles_per_group * segs_per_tile threads.
-__global__ void __launch_bounds__(kIndexThreads) k_index(DecodeParams P) {
-  const uint32_t spt = P.segs_per_tile;
-  const ActGeom G = act_geom(P);
-  if (blockIdx.x >= G.n_groups) return;             // the grid is sized for a stream with every segment live
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  Summ acc = summ_identity();
-  uint32_t nframes = 0;
-  if (j < G.n_act) {
-    const uint32_t seg = P.act[j];
-    uint64_t pos = P.anchors[seg];
-    const uint64_t stop = min(P.anchors[seg + 1], P.len);
-    while (pos < stop) {
-      const uint8_t* p = P.buf + pos;
-      FrameHead h = read_head(p, P.len - pos);
-      Summ e = frame_state_elem(h, p);
-      if (!h.malformed) {
-        const DevSchema* s = nullptr;
-        if (h.kind == 'I' || h.kind == 'U' || h.kind == 'D') s = find_schema(P, h.rel, pos);
-        e.n_cells = frame_out_cells(h, s);
+// pass A: frame offsets.  One thread per live segment chases the 'd'+len32 chain of the frames that start in its
+// 2 KiB (ONE dependent 8-byte read per hop: nothing of a frame but its length field is looked at), the counts are
+// scanned in the same launch (decoupled look-back over the CTAs: a CTA publishes its count, then sums the
+// counts of its predecessors), and a second walk over the now cached length fields writes every frame's offset
+// into `frame_off` in stream order.  Everything after this pass is record-parallel: one thread per frame, coalesced.
+// (Round 1/2a walked the chain twice with the whole per-frame state machine inside the walk — k_index, k_frames:
+// 10 serial hops of ~5 µs each for a 2 KiB segment of 200-byte frames, 60 % of the time of an 8 MiB batch.)
+constexpr int kChaseThreads = 256;
+constexpr uint32_t ABORT_RECORDS = 1u, ABORT_SCRATCH = 2u, ABORT_CELLS = 4u;   // bits of *P.abort_flag
+// status word of the count scan: [0,2) state (1 = CTA count, 2 = inclusive prefix), [2,34) value, [34,64) launch epoch
+__device__ __forceinline__ unsigned long long chase_word(uint32_t epoch, uint32_t value, uint32_t state) {
+  return ((unsigned long long)epoch << 34) | ((unsigned long long)value << 2) | state;
+}
+// CopyData length of the frame at `pos` under read_head's rules: a chain that cannot continue runs to the end of the stream
+__device__ __forceinline__ uint32_t chase_flen(const uint8_t* buf, uint64_t pos, uint64_t len) {
+  const uint64_t avail = len - pos;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(buf + (pos & ~3ull));   // the stream is 16-byte aligned and padded
+  const uint32_t w0 = w[0], w1 = w[1];
+  const uint64_t v = (((uint64_t)w1 << 32) | w0) >> ((uint32_t)(pos & 3u) * 8u);   // bytes pos .. pos+4
+  if (avail < 5 || (uint32_t)(v & 0xFFu) != 'd') return (uint32_t)(avail > 0 ? avail - 1 : 0);
+  const uint32_t flen = __byte_perm((uint32_t)(v >> 8), 0, 0x0123);
+  if (flen < 4 || 1ull + flen > avail) return (uint32_t)(avail - 1);
+  return flen;
+}
+// mode bit 0: count + scan (writes seg_rec_base, n_frames, the abort bits); bit 1: write frame_off (needs seg_rec_base)
+__global__ void __launch_bounds__(kChaseThreads) k_chase(DecodeParams P, uint32_t mode) {
+  __shared__ uint32_t wsum[kChaseThreads / 32];
+  __shared__ uint32_t blk_prefix;
+  const uint32_t n_act = *P.n_act;
+  const uint32_t n_blocks = (n_act + kChaseThreads - 1) / kChaseThreads;
+  if (blockIdx.x >= n_blocks) return;                 // the grid is sized for a stream with every segment live
+  const uint32_t j = blockIdx.x * kChaseThreads + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+  const bool live = j < n_act;
+  uint64_t pos0 = 0, stop = 0;
+  if (live) { const uint32_t seg = P.act[j]; pos0 = P.anchors[seg]; stop = min(P.anchors[seg + 1], P.len); }
+  uint32_t base = 0;
+  if (mode & 1u) {
+    uint32_t count = 0;
+    for (uint64_t pos = pos0; pos < stop; count++) pos += 1ull + chase_flen(P.buf, pos, P.len);
+    uint32_t inc = count;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t up = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (uint32_t)d) inc += up; }
+    if (lane == 31u) wsum[wid] = inc;
+    __syncthreads();
+    uint32_t before = 0, blk_total = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < kChaseThreads / 32; k++) { const uint32_t c = wsum[k]; if (k < wid) before += c; blk_total += c; }
+    if (wid == 0) {
+      volatile unsigned long long* status = P.chase_status;
+      const uint32_t ep = P.scan_epoch;
+      if (lane == 0) status[blockIdx.x] = chase_word(ep, blk_total, blockIdx.x == 0 ? 2u : 1u);
+      uint32_t prefix = 0;
+      for (int hi = (int)blockIdx.x - 1; hi >= 0; hi -= 32) {
+        const int idx = hi - (int)lane;
+        unsigned long long sw = chase_word(ep, 0u, 2u);            // before the first CTA: an inclusive prefix of 0
+        if (idx >= 0) do { sw = status[idx]; } while ((uint32_t)(sw >> 34) != ep || (sw & 3ull) == 0ull);
+        const unsigned incl = __ballot_sync(0xffffffffu, (sw & 3ull) == 2ull);
+        const uint32_t last = incl ? (uint32_t)__ffs(incl) - 1u : 32u;   // nearest predecessor that already knows its inclusive prefix
+        uint32_t v = lane <= last ? (uint32_t)(sw >> 2) : 0u;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+        prefix += __shfl_sync(0xffffffffu, v, 0);
+        if (incl) break;
       }
-      acc = fold(acc, e);
-      nframes++;
-      pos += 1ull + h.flen;
+      if (lane == 0) {
+        blk_prefix = prefix;
+        const uint32_t total = prefix + blk_total;
+        if (blockIdx.x) status[blockIdx.x] = chase_word(ep, total, 2u);
+        if (blockIdx.x == n_blocks - 1u) {
+          *P.n_frames = total;
+          // sizes were guessed from earlier batches: record planes too small → pass C is re-run with exact sizes;
+          // offset scratch too small → nothing after this kernel can run
+          *P.abort_flag = ((uint64_t)total > P.cap_records ? ABORT_RECORDS : 0u) | ((uint64_t)total > P.frame_cap ? ABORT_SCRATCH : 0u);
+        }
+      }
     }
-    P.seg_frames[j] = nframes;
-    P.seg_summ[j] = acc;
-  }
-  // fold across the segments of each tile, then across the tiles of the group (ordered shuffles)
-  // generic ordered fold over the block through shared memory (blockDim <= 256)
-  __shared__ Summ sh[kIndexThreads];
-  sh[threadIdx.x] = acc;
-  __syncthreads();
-  // per-tile fold by the first lane of each tile
-  const uint32_t tile_in_block = threadIdx.x / spt;
-  if (threadIdx.x % spt == 0) {
-    Summ t = summ_identity();
-    for (uint32_t k = 0; k < spt && threadIdx.x + k < blockDim.x; k++) t = fold(t, sh[threadIdx.x + k]);
-    uint32_t tile = blockIdx.x * P.tiles_per_group + tile_in_block;
-    if (tile < G.n_tiles) P.tile_summ[tile] = t;
-    sh[threadIdx.x] = t;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    Summ g = summ_identity();
-    for (uint32_t k = 0; k < P.tiles_per_group; k++) g = fold(g, sh[k * spt]);
-    P.group_summ[blockIdx.x] = g;
-  }
-}
-
-// pass B2: per-tile exclusive prefix = group prefix ⊕ earlier tiles of the group (thread per tile)
-__global__ void __launch_bounds__(256) k_tile_prefix(DecodeParams P) {
-  const uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tile >= act_geom(P).n_tiles) return;
-  const uint32_t g = tile / P.tiles_per_group;
-  Summ pre = P.group_prefix[g];
-  for (uint32_t t = g * P.tiles_per_group; t < tile; t++) pre = fold(pre, P.tile_summ[t]);
-  P.tile_prefix[tile] = pre;
-
-}
-
-// ================================================================================================
-// pass B: exclusive scan of group summaries (single CTA; n_groups is len / (tiles_per_group*32 KiB))
-__global__ void __launch_bounds__(512) k_scan(DecodeParams P) {
-  __shared__ Summ sh[512];
-  const uint32_t n = act_geom(P).n_groups;
-  const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
-  const uint32_t lo = threadIdx.x * per, hi = min(lo + per, n);
-  Summ acc = summ_identity();
-  for (uint32_t i = lo; i < hi; i++) acc = fold(acc, P.group_summ[i]);
-  sh[threadIdx.x] = acc;
-  __syncthreads();
-  // Hillis-Steele inclusive scan over 1024 partials with the non-commutative fold
-  for (uint32_t d = 1; d < blockDim.x; d <<= 1) {
-    Summ v = sh[threadIdx.x];
-    if (threadIdx.x >= d) v = fold(sh[threadIdx.x - d], v);
     __syncthreads();
-    sh[threadIdx.x] = v;
-    __syncthreads();
-  }
-  Summ run = threadIdx.x ? sh[threadIdx.x - 1] : summ_identity();
-  for (uint32_t i = lo; i < hi; i++) {
-    P.group_prefix[i] = run;
-    run = fold(run, P.group_summ[i]);
-  }
-  if (threadIdx.x == blockDim.x - 1) {
-    const Summ T = sh[blockDim.x - 1];
-    P.total[0] = T;
-    // the host sized the planes from the previous batches: when this one does not fit, every later kernel returns
-    // at once and the host re-runs pass C with exact sizes (P.total stays valid)
-    const bool fits = (uint64_t)T.n_rec <= P.cap_records && T.n_cells <= P.cap_cells;
-    *P.abort_flag = fits ? 0u : 1u;
-    if (fits && P.rec_cell_base) P.rec_cell_base[T.n_rec] = T.n_cells;   // exact path: the planes do not exist yet, the host writes the tail
-    if (P.seam_send) { SeamBlock b; b.total = T; b._pad[0] = b._pad[1] = b._pad[2] = b._pad[3] = 0; *P.seam_send = b; }
+    base = blk_prefix + before + (inc - count);
+    if (live) P.seg_rec_base[j] = base;
+  } else if (live) base = P.seg_rec_base[j];
+  if ((mode & 2u) && live) {
+    uint64_t k = base;
+    for (uint64_t pos = pos0; pos < stop; k++) {
+      if (k < P.frame_cap) P.frame_off[k] = pos;
+      pos += 1ull + chase_flen(P.buf, pos, P.len);
+    }
   }
 }
 
@@ -744,169 +726,257 @@ __global__ void __launch_bounds__(kPermThreads) k_perm(DecodeParams P) {
 }
 
 // ================================================================================================
-// pass C1: records.  Thread per anchor segment; frames of a segment are replayed in order with the
-// running stream state (apply.rs:600-626, 1687-2248), exactly like the reference's apply loop but
-// for ~2 KiB of stream per thread.
-__global__ void __launch_bounds__(256) k_frames(DecodeParams P) {
-  const ActGeom G = act_geom(P);
-  if (blockIdx.x * blockDim.x >= G.n_act || *P.abort_flag) return;   // grid sized for the all-live case
-  __shared__ uint32_t hist[kMaxBins];               // frame shapes of the CTA's DML records
-  for (uint32_t i = threadIdx.x; i < P.n_bins; i += blockDim.x) hist[i] = 0;
-  __syncthreads();
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t events = 0;
-  // exclusive prefix of this segment: carry ⊕ tile prefix ⊕ earlier segments of the tile.  A tile is
-  // exactly one warp of segments (segs_per_tile == 32), so the last part is a warp shuffle scan.
-  Summ st;
+// pass B + C1: records.  One THREAD per frame (offsets from k_chase), 256 consecutive frames per CTA.  Every thread
+// reads its frame head and forms the frame's element of the stream-state transformer {records, cells, Begin / Commit
+// effect} (apply.rs:600-626, 1927-2006: associative, so commit_lsn / tx_ordinal / "inside a transaction" are a scan);
+// the CTA scans its 256 elements, publishes the aggregate and obtains its exclusive prefix from its predecessors in the
+// same launch (decoupled look-back with an ORDERED fold: the transformer does not commute).  With the prefix every
+// thread holds exactly the state the reference's apply loop has when it reaches that message (apply.rs:1687-2248),
+// and writes the record plane — consecutive records from consecutive lanes — plus the cells of Begin / Commit /
+// Truncate, and counts the frame shapes for k_perm.
+//   FULL = false: totals only (P.total, the seam block, the cells-overflow bit) — first batch (plane sizes unknown),
+//                 multi-GPU shards (the carry-in arrives through the seam exchange after this pass).
+constexpr int kRecThreads = 256;
+struct ScanSlot { Summ aggr; Summ incl; };
+#define SUMM_SHFL(dst, src, fn, arg)                                                                     \
+  do {                                                                                                    \
+    (dst).lsn = fn(0xffffffffu, (src).lsn, arg); (dst).ord = fn(0xffffffffu, (src).ord, arg);             \
+    (dst).n_cells = fn(0xffffffffu, (src).n_cells, arg); (dst).n_rec = fn(0xffffffffu, (src).n_rec, arg); \
+    (dst).flags = fn(0xffffffffu, (src).flags, arg);                                                      \
+  } while (0)
+__device__ __forceinline__ Summ ld_summ_cg(const Summ* p) {      // L2 (another CTA wrote it)
+  const uint4 a = __ldcg(reinterpret_cast<const uint4*>(p)), b = __ldcg(reinterpret_cast<const uint4*>(p) + 1);
+  Summ r;
+  r.lsn = ((uint64_t)a.y << 32) | a.x; r.ord = ((uint64_t)a.w << 32) | a.z; r.n_cells = ((uint64_t)b.y << 32) | b.x; r.n_rec = b.z; r.flags = b.w;
+  return r;
+}
+template <bool FULL>
+__global__ void __launch_bounds__(kRecThreads) k_records(DecodeParams P) {
+  __shared__ Summ wtot[kRecThreads / 32];
+  __shared__ Summ blk_excl_sh;
+  __shared__ uint32_t blk_fits_sh;
+  __shared__ uint32_t hist[FULL ? kMaxBins : 1];     // frame shapes of the CTA's DML records
   {
-    const int lane = threadIdx.x & 31;
-    Summ inc = j < G.n_act ? P.seg_summ[j] : summ_identity();
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      Summ up;
-      up.lsn = __shfl_up_sync(0xffffffffu, inc.lsn, d); up.ord = __shfl_up_sync(0xffffffffu, inc.ord, d);
-      up.n_cells = __shfl_up_sync(0xffffffffu, inc.n_cells, d);
-      up.n_rec = __shfl_up_sync(0xffffffffu, inc.n_rec, d); up.flags = __shfl_up_sync(0xffffffffu, inc.flags, d);
-      if (lane >= d) inc = fold(up, inc);
+    const uint32_t ab = *P.abort_flag;               // RECORDS / SCRATCH: set by k_chase, before this launch
+    if (ab & ABORT_SCRATCH) {                        // offsets are missing: no totals.  A shard says so in its seam block
+      if (!FULL && blockIdx.x == 0 && threadIdx.x == 0 && P.seam_send) {
+        SeamBlock sb; sb.total = summ_identity(); sb.total.flags = 0x80000000u; sb._pad[0] = sb._pad[1] = sb._pad[2] = sb._pad[3] = 0;
+        *P.seam_send = sb;
+      }
+      return;
     }
-    Summ ex;
-    ex.lsn = __shfl_up_sync(0xffffffffu, inc.lsn, 1); ex.ord = __shfl_up_sync(0xffffffffu, inc.ord, 1);
-    ex.n_cells = __shfl_up_sync(0xffffffffu, inc.n_cells, 1);
-    ex.n_rec = __shfl_up_sync(0xffffffffu, inc.n_rec, 1); ex.flags = __shfl_up_sync(0xffffffffu, inc.flags, 1);
-    if (lane == 0) ex = summ_identity();
-    const uint32_t tile = j / 32u;
-    const Summ tp = tile < G.n_tiles ? P.tile_prefix[tile] : summ_identity();
-    st = fold(fold(P.dc->carry, tp), ex);
+    if (FULL && (ab & ABORT_RECORDS)) return;
   }
-  if (j < G.n_act) {
-    const uint32_t seg = P.act[j];
-    uint64_t pos = P.anchors[seg];
-    const uint64_t stop = min(P.anchors[seg + 1], P.len);
-    while (pos < stop) {
-      const uint8_t* fp = P.buf + pos;
-      const FrameHead h = read_head(fp, P.len - pos);
-      const uint64_t ridx = st.n_rec;
-      const uint64_t gidx = P.dc->record_index_base + ridx;
-      const uint64_t my_cell0 = st.n_cells;
-      const bool in_tx = (st.flags & S_HAS_B) && !(st.flags & S_CLOSED);
-      const DevSchema* s = nullptr;
-      Summ e = frame_state_elem(h, fp);
-      if (!h.malformed) {
-        if (h.kind == 'I' || h.kind == 'U' || h.kind == 'D') s = find_schema(P, h.rel, pos);
-        e.n_cells = frame_out_cells(h, s);
-      }
-      uint64_t commit_lsn = 0, ordinal = 0, start_lsn = 0;
-      uint32_t rflags = 0;
-      int32_t rschema = -1;
-      uint32_t rrel = h.rel;
-      bool ok = true;
-      bool wellformed = !h.malformed;
-      if (wellformed && h.kind == 'O') wellformed = (h.flen >= 4 + 26 + 8) && cstr_end(fp + 39, fp + 1 + h.flen) != nullptr;
-      if (wellformed && h.kind == 'Y') {
-        const uint8_t* fe = fp + 1 + h.flen;
-        const uint8_t* q1 = (h.flen >= 4 + 26 + 4) ? cstr_end(fp + 35, fe) : nullptr;
-        wellformed = q1 != nullptr && cstr_end(q1, fe) != nullptr;
-      }
-      if (wellformed && (h.kind == 'I' || h.kind == 'U' || h.kind == 'D')) {
-        const uint32_t tt = fp[35];  // tuple marker (mlen >= 5 is guaranteed by read_head)
-        if (h.kind == 'I') wellformed = tt == 'N';
-        else if (h.kind == 'U') wellformed = tt == 'N' || tt == 'O' || tt == 'K';
-        else wellformed = tt == 'O' || tt == 'K';
-      }
-      if (!wellformed) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; }
-      else if (h.kind == 'k') { start_lsn = be64(fp + 6); rrel = fp[22]; }
-      else {
-        start_lsn = be64(fp + 6);                      // wal_start apply.rs:1700
-        const uint8_t* m = fp + 31;                    // message body after the tag
-        switch (h.kind) {
-          case 'B':                                    // apply.rs:1927-1943
-            commit_lsn = be64(m); ordinal = 0; rflags = ETL_RF_EVENT;
-            put_cell(P, my_cell0, ETL_CELL_I64, be64(m + 8), 0);
-            put_cell(P, my_cell0 + 1, ETL_CELL_U32, be32(m + 16), 0);
-            break;
-          case 'C': {                                  // apply.rs:1946-2006
-            if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; break; }
-            const uint64_t cl = be64(m + 1);
-            if (cl != st.lsn) { report_error(P, gidx, SEQ_STATE, ETL_E_COMMIT_LSN); ok = false; break; }
-            commit_lsn = cl; ordinal = st.ord; rflags = ETL_RF_EVENT;
-            put_cell(P, my_cell0, ETL_CELL_I32, (uint64_t)(int64_t)(int8_t)m[0], 0);
-            put_cell(P, my_cell0 + 1, ETL_CELL_I64, be64(m + 9), 0);
-            put_cell(P, my_cell0 + 2, ETL_CELL_I64, be64(m + 17), 0);
-            break;
-          }
-          case 'R':                                    // apply.rs:2012-2089 (masks are built on the host)
-            for (uint32_t k = 0; k < P.n_rel_errors; k++)
-              if (P.rel_error_off[k] == pos) { report_error(P, gidx, P.rel_error_seq[k], P.rel_error_code[k]); ok = false; }
-            if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; break; }
-            commit_lsn = st.lsn; ordinal = st.ord; rflags = ETL_RF_EVENT;
-            { const DevSchema* rs = find_schema(P, h.rel, pos); if (rs && rs->effective_off == pos) rschema = (int32_t)rs->batch_index; }
-            break;
-          case 'I': case 'U': case 'D': {              // apply.rs:2092-2203
-            // the tuple structure is validated by k_walk (a malformed frame outranks state errors)
-            if (!in_tx) report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE);
-            commit_lsn = st.lsn; ordinal = st.ord;
-            if (!s) {                                  // no schema to walk with: structure check only
-              unsigned long long ignored;
-              if (!dml_structure_ok(h, fp, &ignored)) report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME);
-              report_error(P, gidx, SEQ_TABLE, ETL_E_MISSING_TABLE_STATE); ok = false; break;
-            }
-            rschema = (int32_t)s->batch_index; rflags = ETL_RF_EVENT;
-            if (h.old_tag == 'O') rflags |= ETL_RF_OLD_FULL; else if (h.old_tag == 'K') rflags |= ETL_RF_OLD_KEY;
-            break;
-          }
-          case 'T': {                                  // apply.rs:2206-2248
-            if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; break; }
-            commit_lsn = st.lsn; ordinal = st.ord;
-            put_cell(P, my_cell0, ETL_CELL_I32, (uint64_t)(int64_t)(int8_t)m[4], 0);
-            for (uint32_t i = 0; i < h.rel; i++) {
-              const uint32_t rid = be32(m + 5 + 4 * i);
-              const DevSchema* ts = find_schema(P, rid, pos);
-              if (!ts) { report_error(P, gidx, SEQ_TABLE, ETL_E_MISSING_TABLE_STATE); ok = false; break; }
-              put_cell(P, my_cell0 + 1 + i, ETL_CELL_U32, rid, ts->batch_index);
-            }
-            if (h.rel > 0) rflags = ETL_RF_EVENT;
-            break;
-          }
-          case 'M': {                                  // apply.rs:1808-1924
-            const uint8_t* end = fp + 1 + h.flen;
-            const uint8_t* q = m + 9;
-            const char* ddl = "supabase_etl_ddl";
-            bool is_ddl = true; uint32_t k = 0; bool term = false;
-            if (q > end) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; break; }
-            for (; q + k < end; k++) { uint32_t ch = q[k]; if (!ch) { term = true; break; } if (k >= 16 || ch != (uint32_t)(uint8_t)ddl[k]) is_ddl = false; }
-            if (!term || !utf8_valid(q, k)) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; break; }
-            is_ddl = is_ddl && k == 16;
-            const uint8_t* cq = q + k + 1;
-            if (cq + 4 > end) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; break; }
-            const int32_t cl = (int32_t)be32(cq);
-            if (cl < 0 || (uint64_t)cl > (uint64_t)(end - cq - 4)) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; break; }
-            if (is_ddl) { rflags |= ETL_RF_DDL_MESSAGE; if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; } }
-            break;
-          }
-          default: break;                              // Origin / Type: structure only
-        }
-      }
-      // a record k_walk must not touch keeps schema = -1 only when it failed before conversion
-      if (h.kind == 'I' || h.kind == 'U' || h.kind == 'D') {
-        if (!ok) rschema = -1;
-        else if (rschema >= 0) atomicAdd(&hist[walk_bin(P, s->layout, h.kind, rflags)], 1u);
-      }
-      P.rec_off[ridx] = pos; P.rec_kind[ridx] = (uint8_t)h.kind; P.rec_flags[ridx] = (uint8_t)rflags;
-      P.rec_rel[ridx] = rrel; P.rec_schema[ridx] = rschema; P.rec_start_lsn[ridx] = start_lsn;
-      P.rec_commit_lsn[ridx] = commit_lsn; P.rec_tx_ordinal[ridx] = ordinal; P.rec_cell_base[ridx] = my_cell0;
-      P.rec_flen[ridx] = 1u + h.flen; P.rec_tuple_bytes[ridx] = 0; P.rec_heap_hint[ridx] = 0;   // k_rows fills the DML records
-      if (ok && (rflags & ETL_RF_EVENT)) events++;
-      st = fold(st, e);
-      pos += 1ull + h.flen;
+  const uint32_t n_rec = *P.n_frames;
+  const uint32_t n_blocks = (n_rec + kRecThreads - 1) / kRecThreads;
+  if (n_rec == 0) {                                  // a batch without frames: the totals are the identity
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      P.total[0] = summ_identity();
+      if (FULL && P.rec_cell_base) P.rec_cell_base[0] = 0;
+      if (P.seam_send) { SeamBlock sb; sb.total = summ_identity(); sb._pad[0] = sb._pad[1] = sb._pad[2] = sb._pad[3] = 0; *P.seam_send = sb; }
     }
+    return;
+  }
+  if (blockIdx.x >= n_blocks) return;                // the grid is sized for the capacity of the planes
+  if (FULL) { for (uint32_t i = threadIdx.x; i < P.n_bins; i += blockDim.x) hist[i] = 0; }
+  const uint32_t r = blockIdx.x * kRecThreads + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+  const bool live = r < n_rec;
+  const uint64_t pos = live ? P.frame_off[r] : 0ull;
+  const uint8_t* fp = P.buf + pos;
+  FrameHead h;
+  h.kind = 0; h.rel = 0; h.old_tag = 0; h.malformed = true; h.flen = 4;
+  const DevSchema* s = nullptr;
+  Summ e = summ_identity();
+  if (live) {
+    h = read_head(fp, P.len - pos);
+    e = frame_state_elem(h, fp);
+    if (!h.malformed) {
+      if (h.kind == 'I' || h.kind == 'U' || h.kind == 'D') s = find_schema(P, h.rel, pos);
+      e.n_cells = frame_out_cells(h, s);
+    }
+  }
+  // ---- scan of the CTA's elements: inclusive inside each warp, then across the warps
+  Summ inc = e;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    Summ up;
+    SUMM_SHFL(up, inc, __shfl_up_sync, d);
+    if (lane >= (uint32_t)d) inc = fold(up, inc);
+  }
+  Summ ex;
+  SUMM_SHFL(ex, inc, __shfl_up_sync, 1);
+  if (lane == 0) ex = summ_identity();
+  if (lane == 31u) wtot[wid] = inc;
+  __syncthreads();
+  Summ wpre = summ_identity(), aggr = summ_identity();
+#pragma unroll
+  for (uint32_t k = 0; k < kRecThreads / 32; k++) { const Summ t = wtot[k]; if (k < wid) wpre = fold(wpre, t); aggr = fold(aggr, t); }
+  // ---- exclusive prefix of the CTA (carry not included): look back over the predecessors, 32 at a time
+  if (wid == 0) {
+    volatile uint32_t* status = P.scan_status;
+    const uint32_t ep = P.scan_epoch << 2;
+    ScanSlot* const slots = P.scan_slots;
+    if (lane == 0) {
+      if (blockIdx.x == 0) slots[0].incl = aggr; else slots[blockIdx.x].aggr = aggr;
+      __threadfence();
+      status[blockIdx.x] = ep | (blockIdx.x == 0 ? 2u : 1u);
+    }
+    Summ prefix = summ_identity();                   // fold of the predecessors examined so far (the nearest ones)
+    for (int hi = (int)blockIdx.x - 1; hi >= 0; hi -= 32) {
+      const int idx = hi - (int)lane;
+      uint32_t sw = ep | 2u;                          // before the first CTA: an inclusive prefix equal to the identity
+      if (idx >= 0) do { sw = status[idx]; } while ((sw & ~3u) != ep || (sw & 3u) == 0u);
+      __threadfence();
+      const unsigned incl = __ballot_sync(0xffffffffu, (sw & 3u) == 2u);
+      const uint32_t last = incl ? (uint32_t)__ffs(incl) - 1u : 32u;
+      Summ v = summ_identity();
+      if (idx >= 0 && lane <= last) v = ld_summ_cg((sw & 3u) == 2u ? &slots[idx].incl : &slots[idx].aggr);
+      // ordered: lane 0 is the nearest predecessor, so the fold runs from the highest lane down
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        Summ older;
+        SUMM_SHFL(older, v, __shfl_down_sync, d);
+        if (lane + (uint32_t)d < 32u) v = fold(older, v);
+      }
+      Summ window;
+      SUMM_SHFL(window, v, __shfl_sync, 0);
+      prefix = fold(window, prefix);
+      if (incl) break;
+    }
+    if (lane == 0) {
+      const Summ incl_total = fold(prefix, aggr);
+      if (blockIdx.x) { slots[blockIdx.x].incl = incl_total; __threadfence(); status[blockIdx.x] = ep | 2u; }
+      blk_excl_sh = prefix;
+      const bool fits = incl_total.n_cells <= P.cap_cells;     // prefixes grow: every CTA after the first overflow sees it too
+      blk_fits_sh = fits ? 1u : 0u;
+      if (!fits) atomicOr(P.abort_flag, ABORT_CELLS);
+      if (blockIdx.x == n_blocks - 1u) {
+        P.total[0] = incl_total;
+        if (FULL && fits && P.rec_cell_base) P.rec_cell_base[incl_total.n_rec] = incl_total.n_cells;
+        if (P.seam_send) { SeamBlock sb; sb.total = incl_total; sb._pad[0] = sb._pad[1] = sb._pad[2] = sb._pad[3] = 0; *P.seam_send = sb; }
+      }
+    }
+  }
+  if (!FULL) return;
+  __syncthreads();
+  uint32_t events = 0;
+  if (live && blk_fits_sh) {
+    const Summ st = fold(fold(P.dc->carry, blk_excl_sh), fold(wpre, ex));
+    const uint64_t ridx = st.n_rec;
+    const uint64_t gidx = P.dc->record_index_base + ridx;
+    const uint64_t my_cell0 = st.n_cells;
+    const bool in_tx = (st.flags & S_HAS_B) && !(st.flags & S_CLOSED);
+    uint64_t commit_lsn = 0, ordinal = 0, start_lsn = 0;
+    uint32_t rflags = 0;
+    int32_t rschema = -1;
+    uint32_t rrel = h.rel;
+    bool ok = true;
+    bool wellformed = !h.malformed;
+    if (wellformed && h.kind == 'O') wellformed = (h.flen >= 4 + 26 + 8) && cstr_end(fp + 39, fp + 1 + h.flen) != nullptr;
+    if (wellformed && h.kind == 'Y') {
+      const uint8_t* fe = fp + 1 + h.flen;
+      const uint8_t* q1 = (h.flen >= 4 + 26 + 4) ? cstr_end(fp + 35, fe) : nullptr;
+      wellformed = q1 != nullptr && cstr_end(q1, fe) != nullptr;
+    }
+    if (wellformed && (h.kind == 'I' || h.kind == 'U' || h.kind == 'D')) {
+      const uint32_t tt = fp[35];  // tuple marker (mlen >= 5 is guaranteed by read_head)
+      if (h.kind == 'I') wellformed = tt == 'N';
+      else if (h.kind == 'U') wellformed = tt == 'N' || tt == 'O' || tt == 'K';
+      else wellformed = tt == 'O' || tt == 'K';
+    }
+    if (!wellformed) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; }
+    else if (h.kind == 'k') { start_lsn = be64(fp + 6); rrel = fp[22]; }
+    else {
+      start_lsn = be64(fp + 6);                      // wal_start apply.rs:1700
+      const uint8_t* m = fp + 31;                    // message body after the tag
+      switch (h.kind) {
+        case 'B':                                    // apply.rs:1927-1943
+          commit_lsn = be64(m); ordinal = 0; rflags = ETL_RF_EVENT;
+          put_cell(P, my_cell0, ETL_CELL_I64, be64(m + 8), 0);
+          put_cell(P, my_cell0 + 1, ETL_CELL_U32, be32(m + 16), 0);
+          break;
+        case 'C': {                                  // apply.rs:1946-2006
+          if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; break; }
+          const uint64_t cl = be64(m + 1);
+          if (cl != st.lsn) { report_error(P, gidx, SEQ_STATE, ETL_E_COMMIT_LSN); ok = false; break; }
+          commit_lsn = cl; ordinal = st.ord; rflags = ETL_RF_EVENT;
+          put_cell(P, my_cell0, ETL_CELL_I32, (uint64_t)(int64_t)(int8_t)m[0], 0);
+          put_cell(P, my_cell0 + 1, ETL_CELL_I64, be64(m + 9), 0);
+          put_cell(P, my_cell0 + 2, ETL_CELL_I64, be64(m + 17), 0);
+          break;
+        }
+        case 'R':                                    // apply.rs:2012-2089 (masks are built on the host)
+          for (uint32_t k = 0; k < P.n_rel_errors; k++)
+            if (P.rel_error_off[k] == pos) { report_error(P, gidx, P.rel_error_seq[k], P.rel_error_code[k]); ok = false; }
+          if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; break; }
+          commit_lsn = st.lsn; ordinal = st.ord; rflags = ETL_RF_EVENT;
+          { const DevSchema* rs = find_schema(P, h.rel, pos); if (rs && rs->effective_off == pos) rschema = (int32_t)rs->batch_index; }
+          break;
+        case 'I': case 'U': case 'D': {              // apply.rs:2092-2203
+          // the tuple structure is validated by k_walk (a malformed frame outranks state errors)
+          if (!in_tx) report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE);
+          commit_lsn = st.lsn; ordinal = st.ord;
+          if (!s) {                                  // no schema to walk with: structure check only
+            unsigned long long ignored;
+            if (!dml_structure_ok(h, fp, &ignored)) report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME);
+            report_error(P, gidx, SEQ_TABLE, ETL_E_MISSING_TABLE_STATE); ok = false; break;
+          }
+          rschema = (int32_t)s->batch_index; rflags = ETL_RF_EVENT;
+          if (h.old_tag == 'O') rflags |= ETL_RF_OLD_FULL; else if (h.old_tag == 'K') rflags |= ETL_RF_OLD_KEY;
+          break;
+        }
+        case 'T': {                                  // apply.rs:2206-2248
+          if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; break; }
+          commit_lsn = st.lsn; ordinal = st.ord;
+          put_cell(P, my_cell0, ETL_CELL_I32, (uint64_t)(int64_t)(int8_t)m[4], 0);
+          for (uint32_t i = 0; i < h.rel; i++) {
+            const uint32_t rid = be32(m + 5 + 4 * i);
+            const DevSchema* ts = find_schema(P, rid, pos);
+            if (!ts) { report_error(P, gidx, SEQ_TABLE, ETL_E_MISSING_TABLE_STATE); ok = false; break; }
+            put_cell(P, my_cell0 + 1 + i, ETL_CELL_U32, rid, ts->batch_index);
+          }
+          if (h.rel > 0) rflags = ETL_RF_EVENT;
+          break;
+        }
+        case 'M': {                                  // apply.rs:1808-1924
+          const uint8_t* end = fp + 1 + h.flen;
+          const uint8_t* q = m + 9;
+          const char* ddl = "supabase_etl_ddl";
+          bool is_ddl = true; uint32_t k = 0; bool term = false;
+          if (q > end) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; break; }
+          for (; q + k < end; k++) { uint32_t ch = q[k]; if (!ch) { term = true; break; } if (k >= 16 || ch != (uint32_t)(uint8_t)ddl[k]) is_ddl = false; }
+          if (!term || !utf8_valid(q, k)) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; break; }
+          is_ddl = is_ddl && k == 16;
+          const uint8_t* cq = q + k + 1;
+          if (cq + 4 > end) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; break; }
+          const int32_t cl = (int32_t)be32(cq);
+          if (cl < 0 || (uint64_t)cl > (uint64_t)(end - cq - 4)) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; break; }
+          if (is_ddl) { rflags |= ETL_RF_DDL_MESSAGE; if (!in_tx) { report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE); ok = false; } }
+          break;
+        }
+        default: break;                              // Origin / Type: structure only
+      }
+    }
+    // a record k_walk must not touch keeps schema = -1 only when it failed before conversion
+    if (h.kind == 'I' || h.kind == 'U' || h.kind == 'D') {
+      if (!ok) rschema = -1;
+      else if (rschema >= 0) atomicAdd(&hist[walk_bin(P, s->layout, h.kind, rflags)], 1u);
+    }
+    P.rec_off[ridx] = pos; P.rec_kind[ridx] = (uint8_t)h.kind; P.rec_flags[ridx] = (uint8_t)rflags;
+    P.rec_rel[ridx] = rrel; P.rec_schema[ridx] = rschema; P.rec_start_lsn[ridx] = start_lsn;
+    P.rec_commit_lsn[ridx] = commit_lsn; P.rec_tx_ordinal[ridx] = ordinal; P.rec_cell_base[ridx] = my_cell0;
+    P.rec_flen[ridx] = 1u + h.flen; P.rec_tuple_bytes[ridx] = 0; P.rec_heap_hint[ridx] = 0;   // k_rows fills the DML records
+    if (ok && (rflags & ETL_RF_EVENT)) events++;
   }
   // events: warp reduce, one atomic per warp
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) events += __shfl_down_sync(0xffffffffu, events, d);
-  if ((threadIdx.x & 31) == 0 && events) atomicAdd(&P.metrics[3], (unsigned long long)events);
+  if (lane == 0 && events) atomicAdd(&P.metrics[3], (unsigned long long)events);
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < P.n_bins; i += blockDim.x) if (hist[i]) atomicAdd(&P.bin_count[i], hist[i]);
 }
+#undef SUMM_SHFL
 
 // ================================================================================================
 // size hints (types/table_row.rs:250-345): heap bytes a decoded cell owns.  String / Bytes: the Vec's capacity =
