@@ -7,7 +7,7 @@
 // runs in the sm_100a kernels of wal_kernels.cuh / rows_kernel.cuh; there is no CPU decode fallback.
 //
 // One decode = one host synchronisation, at the end.  The planes are sized from what the previous
-// batches needed per staged byte; k_scan compares the real totals with the reservation on the device and,
+// batches needed per staged byte; k_chase / k_records compare the real totals with the reservation on the device and,
 // when they do not fit, every later kernel returns at once and the host re-runs the record and tuple passes
 // with exact sizes (the first batch of a context takes the exact path: index pass, sync, then the rest).
 // Multi-GPU: the shard seam summaries are all-gathered by NCCL on the decode stream and folded on the
@@ -185,6 +185,7 @@ struct etl_stager {
   size_t n_real_anchors = 0;   // anchors.size() before etl_stage_view padded the tail with `len`
   bool padded = false;
   uint64_t n_frames = 0;
+  uint32_t max_frame = 0;    // longest frame ('d' + length field + body), saturating
 };
 
 struct etl_dec_batch {
@@ -218,6 +219,8 @@ struct etl_dec_ctx {
   DevBuf<ScanSlot> d_scan_slots{bufs};
   DevBuf<Summ> d_total{bufs};
   uint32_t scan_epoch = 0;
+  uint32_t max_frame_hint = 0;            // etl_dec_input.max_frame_len of the batch in flight (0 = unknown)
+  bool long_skipped = false;              // the long-value passes were left out of the last launch_emit_kernels
   DevBuf<uint8_t> d_tables{bufs};          // DevSchema[] | schema_by_batch[] | col_kind[] | col_flags[] | relation errors
   DevBuf<uint32_t> d_line_bad{bufs}, d_dead{bufs}, d_bin_count{bufs}, d_bin_cursor{bufs}, d_perm{bufs}, d_rec_flen{bufs};
   DevBuf<LongCell> d_long{bufs};
@@ -231,7 +234,7 @@ struct etl_dec_ctx {
   Summ* h_total = nullptr;               // pinned
   unsigned long long* h_scalars = nullptr;  // pinned, kScalarWords + DevCarry
   cudaEvent_t ev[6]{};
-  cudaEvent_t evk[3]{};
+  cudaEvent_t evk[4]{};
   cudaStream_t side = nullptr;           // k_utf8_dead runs here, underneath the tuple pass
   cudaEvent_t ev_in = nullptr, ev_l0 = nullptr, ev_l1 = nullptr;
   // decode in flight
@@ -300,7 +303,7 @@ void etl_stage_destroy(etl_stager* s) {
   if (s->cap >> 63) free(s->buf); else cudaFreeHost(s->buf);
   delete s;
 }
-void etl_stage_reset(etl_stager* s) { s->len = 0; s->anchors.clear(); s->relations.clear(); s->padded = false; s->n_real_anchors = 0; s->n_frames = 0; }
+void etl_stage_reset(etl_stager* s) { s->len = 0; s->anchors.clear(); s->relations.clear(); s->padded = false; s->n_real_anchors = 0; s->n_frames = 0; s->max_frame = 0; }
 
 static inline void stage_note_frame(etl_stager* s, uint64_t off, const uint8_t* body, uint32_t body_len) {
   // anchors[k] = first frame starting at or after k*stride
@@ -308,6 +311,7 @@ static inline void stage_note_frame(etl_stager* s, uint64_t off, const uint8_t* 
   while ((uint64_t)s->anchors.size() * s->stride <= off) s->anchors.push_back(off);
   if (body_len >= 26 && body[0] == 'w' && body[25] == 'R') s->relations.push_back(off);
   s->n_frames++;
+  s->max_frame = std::max<uint32_t>(s->max_frame, (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, 5ull + body_len));
 }
 int etl_stage_append(etl_stager* s, const uint8_t* body, uint32_t body_len) {
   uint64_t cap = s->cap & ~(1ull << 63);
@@ -356,6 +360,7 @@ int etl_stage_view(const etl_stager* cs, etl_dec_input* out) {
   out->anchors = s->anchors.data();
   out->n_anchors = s->anchors.size();
   out->anchor_stride = s->stride;
+  out->max_frame_len = s->max_frame;
   out->relation_offsets = s->relations.data();
   out->n_relations = s->relations.size();
   return ETL_OK;
@@ -581,6 +586,12 @@ static int dead_mode() {
   static const int m = getenv("ETL_DEAD_MODE") ? atoi(getenv("ETL_DEAD_MODE")) : 2;
   return m;
 }
+// No frame of the batch can hold a text value of kCoopLen bytes (the stager's max_frame_len says so): k_rows lists no
+// long cell, and the passes that exist for them — the structure-blind UTF-8 pass over dead segments, k_long_cells, the
+// line bitmap — are left out.  The hint is not trusted: should k_rows list a long cell after all, run_decode runs them.
+static bool long_passes_skippable(const etl_dec_ctx* ctx) {
+  return ctx->max_frame_hint && ctx->max_frame_hint < (uint32_t)kCoopLen && dead_mode() == 2;
+}
 static uint32_t dead_grid(const DecodeParams& P) {   // 8 warps per CTA, kDeadSegsPerWarp segments per warp; surplus CTAs return at once
   const uint64_t items = (uint64_t)P.n_anchors * (P.anchor_stride > 2048u ? P.anchor_stride / 2048u : 1u);
   return (uint32_t)((items + 8u * kDeadSegsPerWarp - 1u) / (8u * kDeadSegsPerWarp)) + 1u;
@@ -723,6 +734,7 @@ static int prepare(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t flags, bo
   P.len = in->len;
   P.n_anchors = (uint32_t)in->n_anchors;
   P.anchor_stride = stride;
+  ctx->max_frame_hint = in->max_frame_len;
 
   // ---- uploads
   CK(cudaEventRecord(ctx->ev[0], st));
@@ -827,7 +839,7 @@ static int prepare(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t flags, bo
     CK(ctx->d_seam.ensure(1 + (size_t)ctx->n_ranks));
     P.seam_send = ctx->d_seam.ptr(); P.seam_all = ctx->d_seam.ptr() + 1;
   }
-  CK(cudaMemsetAsync(P.line_bad, 0, line_words * 4, st));
+  if (!long_passes_skippable(ctx)) CK(cudaMemsetAsync(P.line_bad, 0, line_words * 4, st));
   ctx->pending_schemas = std::move(vers);
   ctx->lines_launched = false;
   return ETL_OK;
@@ -875,8 +887,8 @@ static void launch_records(etl_dec_ctx* ctx, bool full, uint64_t n_max) {
   DecodeParams& P = ctx->P;
   P.scan_epoch = next_epoch(ctx);
   const uint32_t grid = (uint32_t)std::max<uint64_t>(1, (n_max + kRecThreads - 1) / kRecThreads);
-  if (full) k_records<true><<<grid, kRecThreads, 0, ctx->stream>>>(P);
-  else k_records<false><<<grid, kRecThreads, 0, ctx->stream>>>(P);
+  if (full) k_records<true><<<grid, kRecCtaThreads, 0, ctx->stream>>>(P);
+  else k_records<false><<<grid, kRecCtaThreads, 0, ctx->stream>>>(P);
   ctx->launches += 1;
 }
 // Optimistic (exact = false): the offset scratch is sized by the caller; one launch counts, scans and writes.
@@ -886,11 +898,14 @@ static int launch_index(etl_dec_ctx* ctx, bool exact) {
   cudaStream_t st = ctx->stream;
   CK(cudaEventRecord(ctx->ev[1], st));
   if (P.n_anchors) {
-    const uint32_t act_blocks = (P.n_anchors + kActThreads - 1) / kActThreads;
-    k_act_count<<<act_blocks, kActThreads, 0, st>>>(P);
-    k_act_scan<<<1, kActThreads, 0, st>>>(P, act_blocks);
-    k_act_scatter<<<act_blocks, kActThreads, 0, st>>>(P);
-    ctx->launches += 3;
+    if (P.n_anchors <= kActSmallSegs) { k_act_small<<<1, kActThreads, 0, st>>>(P); ctx->launches += 1; }
+    else {
+      const uint32_t act_blocks = (P.n_anchors + kActThreads - 1) / kActThreads;
+      k_act_count<<<act_blocks, kActThreads, 0, st>>>(P);
+      k_act_scan<<<1, kActThreads, 0, st>>>(P, act_blocks);
+      k_act_scatter<<<act_blocks, kActThreads, 0, st>>>(P);
+      ctx->launches += 3;
+    }
     if (dead_mode() == 0) CK(launch_dead_side(ctx, st));   // underneath everything that follows (needs only the dead-segment list)
     if (!exact) launch_chase(ctx, 3u);
     else {
@@ -978,6 +993,7 @@ static int launch_emit_kernels(etl_dec_ctx* ctx) {
   CK(cudaMemsetAsync(P.perm, 0xFF, perm_cap * 4, st));
   // k_heavy / k_fix read every cell tag: a record that failed leaves cells unwritten, and a stale tag must not look pending
   if (P.cap_cells) CK(cudaMemsetAsync(P.cell_tag, 0, P.cap_cells, st));
+  ctx->long_skipped = long_passes_skippable(ctx);
   if (P.n_anchors) {
     launch_records(ctx, true, cap_r);
     cudaEventRecord(ctx->evk[0], st);
@@ -996,15 +1012,17 @@ static int launch_emit_kernels(etl_dec_ctx* ctx) {
     cudaEventRecord(ctx->evk[1], st);
     if (ctx->lines_launched) CK(cudaStreamWaitEvent(st, ctx->ev_l1, 0));   // join: the bitmap is complete
     else if (P.dead_in_rows) { cudaEventRecord(ctx->ev_l0, st); cudaEventRecord(ctx->ev_l1, st); }   // done by k_rows
+    else if (ctx->long_skipped) { cudaEventRecord(ctx->ev_l0, st); cudaEventRecord(ctx->ev_l1, st); }
     else {                                            // ETL_DEAD_MODE=2 (or a batch without DML records): the same pass on the main stream
       cudaEventRecord(ctx->ev_l0, st);
       k_utf8_dead<<<dead_grid(P), 256, 0, st>>>(P);
       cudaEventRecord(ctx->ev_l1, st);
       ctx->launches += 1;
     }
-    if (cap_r) { k_long_cells<<<sm_count(ctx) * 8, 256, 0, st>>>(P); ctx->launches += 1; }
+    cudaEventRecord(ctx->evk[3], st);
+    if (cap_r && !ctx->long_skipped) { k_long_cells<<<sm_count(ctx) * 8, 256, 0, st>>>(P); ctx->launches += 1; }
     CK(cudaGetLastError());
-  } else { CK(cudaMemsetAsync(P.total, 0, sizeof(Summ), st)); cudaEventRecord(ctx->evk[0], st); cudaEventRecord(ctx->evk[2], st); cudaEventRecord(ctx->evk[1], st); cudaEventRecord(ctx->ev_l0, st); cudaEventRecord(ctx->ev_l1, st); }
+  } else { CK(cudaMemsetAsync(P.total, 0, sizeof(Summ), st)); cudaEventRecord(ctx->evk[0], st); cudaEventRecord(ctx->evk[2], st); cudaEventRecord(ctx->evk[1], st); cudaEventRecord(ctx->evk[3], st); cudaEventRecord(ctx->ev_l0, st); cudaEventRecord(ctx->ev_l1, st); }
   CK(cudaEventRecord(ctx->ev[4], st));
   CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars.ptr(), kScalarWords * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(ctx->h_total, P.total, sizeof(Summ), cudaMemcpyDeviceToHost, st));
@@ -1098,6 +1116,17 @@ static int run_decode(etl_dec_ctx* ctx, const etl_stream_state* carry_in, uint64
       seams.resize(ctx->n_ranks);
       CKB(cudaMemcpy(seams.data(), P.seam_all, sizeof(SeamBlock) * ctx->n_ranks, cudaMemcpyDeviceToHost));
     }
+    if (ctx->long_skipped && ctx->h_scalars[7] && !ctx->h_scalars[13]) {
+      // the frame-length hint was wrong: long values exist.  Run the passes that were left out, read the scalars again.
+      ctx->long_skipped = false;
+      CKB(cudaMemsetAsync(P.line_bad, 0, ((P.len + 4095) / 4096 + 1) * 4, st));
+      k_utf8_dead<<<dead_grid(P), 256, 0, st>>>(P);
+      k_long_cells<<<sm_count(ctx) * 8, 256, 0, st>>>(P);
+      ctx->launches += 2;
+      CKB(cudaGetLastError());
+      CKB(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars.ptr(), kScalarWords * 8, cudaMemcpyDeviceToHost, st));
+      CKB(cudaStreamSynchronize(st));
+    }
     const uint32_t aborted = (uint32_t)ctx->h_scalars[13];
     bool scratch_short = (aborted & ABORT_SCRATCH) != 0;
     for (const SeamBlock& sb : seams) scratch_short = scratch_short || (sb.total.flags & 0x80000000u);   // some rank could not form its totals
@@ -1183,7 +1212,8 @@ static int run_decode(etl_dec_ctx* ctx, const etl_stream_state* carry_in, uint64
     cudaEventElapsedTime(&S.frames_ms, ctx->ev[3], ctx->evk[0]);
     cudaEventElapsedTime(&S.walk_ms, ctx->evk[0], ctx->evk[2]);    // k_bin_scan + k_perm
     cudaEventElapsedTime(&S.cells_ms, ctx->evk[2], ctx->evk[1]);   // k_rows
-    cudaEventElapsedTime(&S.spans_ms, ctx->ev_l0, ctx->ev_l1);     // k_utf8_dead, concurrent with k_rows
+    cudaEventElapsedTime(&S.spans_ms, ctx->ev_l0, ctx->ev_l1);     // k_utf8_dead
+    cudaEventElapsedTime(&S.long_ms, ctx->evk[3], ctx->ev[4]);     // k_long_cells
   }
   S.h2d_ms = h2d_ms; S.d2h_ms = d2h_ms;
   S.h2d_bytes = ctx->pending_h2d_bytes;

@@ -2,24 +2,19 @@
 //
 //   k_act_count/scan/scatter  list the anchor segments that contain a frame start (`act`) and those that do
 //                       not (`dead`): TOAST-heavy streams leave most segments empty.
-//   k_index   (pass A)  one thread per live segment walks the 'd'+len32 frame chain from global memory (only
-//                       frame heads are touched), classifies frames and reduces a per-tile summary
-//                       {records, cells, stream-state transformer}.
-//   k_scan, k_tile_prefix (pass B)  exclusive scans of the summaries (the state transformer is associative,
-//                       so commit_lsn / tx_ordinal become a scan).
-//   k_utf8_dead (side stream)  structure-blind UTF-8 pass over the dead segments (the inside of TOAST-sized
-//                       values) at HBM speed: one bit per 128-byte line, "some position in this line breaks
-//                       the position-local rule".
-//   k_frames  (pass C1) one thread per live segment replays its frames with the segment's exclusive prefix
-//                       (record index, cell base, stream state) and writes the record plane — the apply
-//                       loop's per-message state machine, serial inside 2 KiB, parallel across; counts the
-//                       frame shapes.
-//   k_bin_scan, k_perm  counting sort of the DML records by frame shape (schema version, op, old-image kind).
-//   k_rows    (pass C2, rows_kernel.cuh) one thread per DML record in shape order, one warp per 32 records of
-//                       one shape: frames staged into shared memory by bulk async copies, tuples walked in
-//                       lockstep, one parser per column for the whole warp; cell plane + heap.
-//   k_long_verdict      after both streams join: the interior verdict of every long text cell that k_cells
-//                       listed, read from the line bitmap.
+//   k_chase   (pass A)  one thread per live segment chases the 'd'+len32 frame chain (only the length fields are
+//                       read), the frame counts are scanned in the same launch and every frame's offset is written
+//                       in stream order: everything after this pass is record-parallel.
+//   k_records (pass B + C1)  one thread per frame: head → element of the stream-state transformer {records, cells,
+//                       Begin / Commit effect}; CTA scan + decoupled look-back give every frame the state the apply
+//                       loop has when it reaches it (the transformer is associative, so commit_lsn / tx_ordinal are
+//                       a scan); writes the record plane, coalesced, and counts the frame shapes.  A totals-only
+//                       variant runs first when the plane sizes or the carry-in are not known yet.
+//   k_utf8_dead         structure-blind UTF-8 pass over the dead segments (the inside of TOAST-sized values) at HBM
+//                       speed: one bit per 128-byte line, "some position in this line breaks the position-local rule".
+//   k_bin_scan, k_perm  counting sort of the DML records by frame shape (column layout, op, old-image kind).
+//   k_rows, k_heavy, k_fix (pass C2, rows_kernel.cuh)  tuples → rows.
+//   k_long_cells        the verdict of every long text cell: interior from the line bitmap, edges validated here.
 //
 // Reference semantics: apply.rs:1687-2248 (state machine), event.rs:376-979 (tuples → rows),
 // text.rs:28-173 (cells).  HBM-bound integer/byte work — no tensor cores.
@@ -104,10 +99,10 @@ struct DecodeParams {
   struct ScanSlot* scan_slots;
   uint32_t scan_epoch;       // changes with every launch of a scanning kernel
   Summ* total;               // [0] = fold of everything (shard seam summary)
-  // global grouping of the DML records by frame shape (k_frames counts, k_bin_scan lays out, k_perm fills)
+  // global grouping of the DML records by frame shape (k_records counts, k_bin_scan lays out, k_perm fills)
   uint32_t* bin_count; uint32_t* bin_cursor; uint32_t n_bins; uint32_t* perm; unsigned int* perm_len;
   uint32_t n_batch_schemas;
-  uint32_t* rec_flen;               // CopyData length + 1 of every record's frame (k_frames → k_rows: sizes the staged window)
+  uint32_t* rec_flen;               // CopyData length + 1 of every record's frame (k_records → k_rows: sizes the staged window)
   unsigned int* abort_flag;         // ABORT_* bits: the batch does not fit the planes / scratch the host reserved (k_chase, k_records)
   unsigned int* copy_count;         // unchanged-TOAST cells left for k_fix
   uint32_t copy_cols;               // COPY-row decode (copy_kernel.cuh): columns per row; 0 on the replication path
@@ -118,7 +113,7 @@ struct DecodeParams {
   struct LongCell* long_cells; unsigned int* long_count; uint32_t long_cap;   // text cells spanning whole dead segments
   // carry-in (device resident; valid when pass C runs)
   const DevCarry* dc;
-  SeamBlock* seam_send;        // this rank's block (k_scan writes it); NULL on a single GPU
+  SeamBlock* seam_send;        // this rank's block (k_records writes it); NULL on a single GPU
   const SeamBlock* seam_all;   // n_ranks blocks after the all-gather
   DevCarry* dc_out;            // = dc, writable (k_seam_fold)
   uint32_t rank, n_ranks;
@@ -220,6 +215,66 @@ __device__ __forceinline__ FrameHead read_head(const uint8_t* p, uint64_t avail)
   return h;
 }
 
+// The first 36 bytes of a frame as little-endian words aligned to the frame start: ten aligned 4-byte loads and nine
+// funnel shifts instead of ~25 byte loads with their shifts and ORs (the byte loads were 12 % of k_records'
+// instructions).  The stream is padded, so the loads may run past a short frame.
+struct HeadW { uint32_t a[9]; };
+__device__ __forceinline__ HeadW load_head_words(const uint8_t* p) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~uintptr_t(3));
+  const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
+  uint32_t x[10];
+#pragma unroll
+  for (int k = 0; k < 10; k++) x[k] = w[k];
+  HeadW H;
+#pragma unroll
+  for (int k = 0; k < 9; k++) H.a[k] = __funnelshift_r(x[k], x[k + 1], sh);
+  return H;
+}
+template <int I> __device__ __forceinline__ uint32_t hw_u8(const HeadW& H) { return (H.a[I >> 2] >> (8 * (I & 3))) & 0xFFu; }
+template <int I> __device__ __forceinline__ uint32_t hw_be32(const HeadW& H) {
+  static_assert(I + 4 <= 36, "inside the loaded head");
+  const uint32_t v = (I & 3) ? __funnelshift_r(H.a[I >> 2], H.a[(I >> 2) + ((I & 3) ? 1 : 0)], 8 * (I & 3)) : H.a[I >> 2];
+  return __byte_perm(v, 0, 0x0123);
+}
+template <int I> __device__ __forceinline__ uint64_t hw_be64(const HeadW& H) { return ((uint64_t)hw_be32<I>(H) << 32) | hw_be32<I + 4>(H); }
+// read_head on the loaded words (same rules, same order)
+__device__ __forceinline__ FrameHead read_head_w(const HeadW& H, uint64_t avail) {
+  FrameHead h;
+  h.kind = 0; h.rel = 0; h.old_tag = 0; h.malformed = true; h.flen = 4;
+  if (avail < 5 || hw_u8<0>(H) != 'd') { h.flen = (uint32_t)(avail > 0 ? avail - 1 : 0); return h; }
+  const uint32_t flen = hw_be32<1>(H);
+  if (flen < 4 || 1ull + flen > avail) { h.flen = (uint32_t)(avail - 1); return h; }  // chain ends here
+  h.flen = flen;
+  const uint32_t blen = flen - 4;
+  if (blen < 1) return h;
+  const uint32_t t = hw_u8<5>(H);
+  if (t == 'k') { if (blen < 18) return h; h.kind = 'k'; h.malformed = false; return h; }
+  if (t != 'w' || blen < 26) return h;
+  const uint32_t tag = hw_u8<30>(H);
+  const uint32_t mlen = blen - 26;  // message bytes after the tag
+  h.kind = tag;
+  switch (tag) {
+    case 'B': if (mlen < 20) return h; break;
+    case 'C': if (mlen < 25) return h; break;
+    case 'R': case 'I': case 'U': case 'D':
+      if (mlen < 5) return h;
+      h.rel = hw_be32<31>(H);
+      if (tag == 'U' || tag == 'D') { const uint32_t tt = hw_u8<35>(H); if (tt == 'O' || tt == 'K') h.old_tag = tt; }
+      break;
+    case 'T': {
+      if (mlen < 5) return h;
+      const int32_t n = (int32_t)hw_be32<31>(H);
+      if (n > 0 && (uint64_t)n * 4 > (uint64_t)mlen - 5) return h;
+      h.rel = n > 0 ? (uint32_t)n : 0u;
+      break;
+    }
+    case 'O': case 'Y': case 'M': break;
+    default: return h;  // unknown tag
+  }
+  h.malformed = false;
+  return h;
+}
+
 // output cells of a frame (depends only on kind / old tag / schema — never on the tuple contents)
 __device__ __forceinline__ uint32_t frame_out_cells(const FrameHead& h, const DevSchema* s) {
   switch (h.kind) {
@@ -308,9 +363,9 @@ __device__ __forceinline__ const uint8_t* cstr_end(const uint8_t* q, const uint8
 }
 
 // ================================================================================================
-// pass A0: compaction.  A segment is a thread's unit of work in k_index / k_frames; a stream with large
+// pass A0: compaction.  A segment is a thread's unit of work in k_chase; a stream with large
 // values (TOAST) leaves most segments without a frame start, and a warp whose 32 segments hold three
-// live ones still issues every instruction (k_index ran at 2.9 active lanes on C5).  Listing the live
+// live ones still issues every instruction (the round-1 index pass ran at 2.9 active lanes on C5).  Listing the live
 // segments first packs them 32 to a warp.  Empty segments fold as the identity, so the scans are
 // unchanged in the compacted index space.
 constexpr int kActThreads = 1024;
@@ -356,6 +411,35 @@ __global__ void __launch_bounds__(kActThreads) k_act_scatter(DecodeParams P) {
   if (live) P.act[live_rank] = seg;
   else if (seg < P.n_anchors) P.dead[seg - live_rank] = seg;
 }
+// the three steps in one launch for a batch of up to kActSmallSegs segments (the reference's 8 MiB batch has 4096):
+// a small batch is bound by the number of dependent launches, not by their work
+constexpr uint32_t kActSmallPer = 8, kActSmallSegs = kActThreads * kActSmallPer;
+__global__ void __launch_bounds__(kActThreads) k_act_small(DecodeParams P) {
+  __shared__ uint32_t wsum[kActThreads / 32];
+  const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+  const uint32_t seg0 = threadIdx.x * kActSmallPer;
+  uint32_t livem = 0;
+#pragma unroll
+  for (uint32_t i = 0; i < kActSmallPer; i++) if (seg_live(P, seg0 + i)) livem |= 1u << i;
+  const uint32_t c = (uint32_t)__popc(livem);
+  uint32_t inc = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t up = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (uint32_t)d) inc += up; }
+  if (lane == 31u) wsum[wid] = inc;
+  __syncthreads();
+  uint32_t before = 0, total = 0;
+#pragma unroll
+  for (uint32_t k = 0; k < kActThreads / 32; k++) { const uint32_t v = wsum[k]; if (k < wid) before += v; total += v; }
+  uint32_t rank = before + inc - c;                   // live segments before seg0
+#pragma unroll
+  for (uint32_t i = 0; i < kActSmallPer; i++) {
+    const uint32_t seg = seg0 + i;
+    if ((livem >> i) & 1u) P.act[rank++] = seg;
+    else if (seg < P.n_anchors) P.dead[seg - rank] = seg;
+  }
+  if (threadIdx.x == 0) *P.n_act = total;
+}
+
 // ================================================================================================
 // pass A: frame offsets.  One thread per live segment chases the 'd'+len32 chain of the frames that start in its
 // 2 KiB (ONE dependent 8-byte read per hop: nothing of a frame but its length field is looked at), the counts are
@@ -365,6 +449,7 @@ __global__ void __launch_bounds__(kActThreads) k_act_scatter(DecodeParams P) {
 // (Round 1/2a walked the chain twice with the whole per-frame state machine inside the walk — k_index, k_frames:
 // 10 serial hops of ~5 µs each for a 2 KiB segment of 200-byte frames, 60 % of the time of an 8 MiB batch.)
 constexpr int kChaseThreads = 256;
+constexpr int kChaseKeep = 12;
 constexpr uint32_t ABORT_RECORDS = 1u, ABORT_SCRATCH = 2u, ABORT_CELLS = 4u;   // bits of *P.abort_flag
 // status word of the count scan: [0,2) state (1 = CTA count, 2 = inclusive prefix), [2,34) value, [34,64) launch epoch
 __device__ __forceinline__ unsigned long long chase_word(uint32_t epoch, uint32_t value, uint32_t state) {
@@ -394,9 +479,23 @@ __global__ void __launch_bounds__(kChaseThreads) k_chase(DecodeParams P, uint32_
   uint64_t pos0 = 0, stop = 0;
   if (live) { const uint32_t seg = P.act[j]; pos0 = P.anchors[seg]; stop = min(P.anchors[seg + 1], P.len); }
   uint32_t base = 0;
+  // the first kChaseKeep frame starts of the segment stay in registers (16-bit distances from the anchor: a segment is at
+  // most 32 KiB), so that segments of up to that many frames are not walked a second time for the write
+  uint32_t dd[kChaseKeep / 2];
+#pragma unroll
+  for (int k = 0; k < kChaseKeep / 2; k++) dd[k] = 0;
+  uint32_t count = 0, kept = 0;
+  uint64_t pos_keep = pos0;                           // position after the kept frames
   if (mode & 1u) {
-    uint32_t count = 0;
-    for (uint64_t pos = pos0; pos < stop; count++) pos += 1ull + chase_flen(P.buf, pos, P.len);
+#pragma unroll
+    for (int k = 0; k < kChaseKeep; k++)
+      if (pos_keep < stop && pos_keep - pos0 < 65536ull && kept == (uint32_t)k) {   // (anchors are caller data: a "segment" may be longer than a stride)
+        dd[k >> 1] |= (uint32_t)(pos_keep - pos0) << (16 * (k & 1));
+        kept++;
+        pos_keep += 1ull + chase_flen(P.buf, pos_keep, P.len);
+      }
+    count = kept;
+    for (uint64_t pos = pos_keep; pos < stop; count++) pos += 1ull + chase_flen(P.buf, pos, P.len);
     uint32_t inc = count;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const uint32_t up = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (uint32_t)d) inc += up; }
@@ -439,8 +538,15 @@ __global__ void __launch_bounds__(kChaseThreads) k_chase(DecodeParams P, uint32_
     if (live) P.seg_rec_base[j] = base;
   } else if (live) base = P.seg_rec_base[j];
   if ((mode & 2u) && live) {
-    uint64_t k = base;
-    for (uint64_t pos = pos0; pos < stop; k++) {
+    uint64_t k = base, pos = pos0;
+    if (mode & 1u) {
+#pragma unroll
+      for (int i = 0; i < kChaseKeep; i++)
+        if ((uint32_t)i < kept && k + i < P.frame_cap) P.frame_off[k + i] = pos0 + ((dd[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
+      k += kept;
+      pos = pos_keep;
+    }
+    for (; pos < stop; k++) {
       if (k < P.frame_cap) P.frame_off[k] = pos;
       pos += 1ull + chase_flen(P.buf, pos, P.len);
     }
@@ -618,16 +724,18 @@ __global__ void __launch_bounds__(256) k_utf8_dead(DecodeParams P) {
   for (uint32_t it = w * kDeadSegsPerWarp; it < min(n_items, (w + 1u) * kDeadSegsPerWarp); it += (uint32_t)kDeadIlp)
     utf8_dead_items(P, it, 1u, min(n_items, (w + 1u) * kDeadSegsPerWarp), ppseg, threadIdx.x & 31u);
 }
-// any flagged line in [l0, l1)?
-__device__ __forceinline__ bool lines_any_bad(const uint32_t* bm, uint64_t l0, uint64_t l1) {
+// any flagged line in [l0, l1)?  One bitmap word per lane and step (a 64 KiB value spans 16 words: a single lane
+// testing them one after the other was a chain of 16 dependent-by-branch loads per cell)
+__device__ __forceinline__ bool lines_any_bad(const uint32_t* bm, uint64_t l0, uint64_t l1, uint32_t lane) {
   const uint64_t w0 = l0 >> 5, w1 = (l1 - 1) >> 5;
-  for (uint64_t w = w0; w <= w1; w++) {
+  bool bad = false;
+  for (uint64_t w = w0 + lane; w <= w1; w += 32u) {
     uint32_t m = 0xFFFFFFFFu;
     if (w == w0) m &= 0xFFFFFFFFu << (l0 & 31);
     if (w == w1 && (l1 & 31)) m &= (1u << (l1 & 31)) - 1u;
-    if (bm[w] & m) return true;
+    bad = bad || (bm[w] & m) != 0u;
   }
-  return false;
+  return bad;
 }
 // One warp per listed long cell, after the dead-segment pass has joined: the part of the cell that covers whole
 // dead segments is judged from the line bitmap; head and tail (up to a segment each) are validated here when k_rows
@@ -642,7 +750,7 @@ __global__ void __launch_bounds__(256) k_long_cells(DecodeParams P) {
     const uint64_t S0 = (c.soff + 3ull + P.anchor_stride - 1ull) & ~(uint64_t)(P.anchor_stride - 1u), S1 = cb & ~(uint64_t)(P.anchor_stride - 1u);
     bool bad = false;
     if (S0 < S1) {
-      if (lane == 0) bad = lines_any_bad(P.line_bad, S0 >> 7, S1 >> 7);
+      bad = lines_any_bad(P.line_bad, S0 >> 7, S1 >> 7, lane);
       if (c.edges) {                                     // head on lanes 0-15, tail on lanes 16-31: one latency chain, not two
         const bool tail = lane >= 16u;
         bad |= utf8_range_bad(P.buf + c.soff, c.len, tail ? (uint32_t)(S1 - c.soff) : 0u, tail ? c.len : (uint32_t)(S0 - c.soff), lane & 15u, 16u);
@@ -658,7 +766,7 @@ __device__ __noinline__ bool utf8_medium_bad(const uint8_t* cell, uint32_t len) 
 // ================================================================================================
 // Shape bins.  A warp of k_rows is fastest when its 32 records have the same frame shape (column layout,
 // operation, old-image kind): wire cell i is then the same column for every lane and one parser runs for
-// all of them.  Output positions are fixed by the scan, so records can be walked in any order: k_frames
+// all of them.  Output positions are fixed by the scan, so records can be walked in any order: k_records
 // histograms the shapes, k_bin_scan lays the bins out (each padded to a whole warp), k_perm writes the
 // record indices bin by bin, and k_rows thread t walks record perm[t].  Schema versions with identical
 // columns share a layout (a table whose Relation is re-sent keeps its bins); a batch with more layouts
@@ -736,7 +844,8 @@ __global__ void __launch_bounds__(kPermThreads) k_perm(DecodeParams P) {
 // Truncate, and counts the frame shapes for k_perm.
 //   FULL = false: totals only (P.total, the seam block, the cells-overflow bit) — first batch (plane sizes unknown),
 //                 multi-GPU shards (the carry-in arrives through the seam exchange after this pass).
-constexpr int kRecThreads = 256;
+constexpr int kRecThreads = 256;                      // records per CTA, one thread each
+constexpr int kRecCtaThreads = kRecThreads + 32;      // + the look-back warp
 struct ScanSlot { Summ aggr; Summ incl; };
 #define SUMM_SHFL(dst, src, fn, arg)                                                                     \
   do {                                                                                                    \
@@ -751,10 +860,9 @@ __device__ __forceinline__ Summ ld_summ_cg(const Summ* p) {      // L2 (another 
   return r;
 }
 template <bool FULL>
-__global__ void __launch_bounds__(kRecThreads) k_records(DecodeParams P) {
+__global__ void __launch_bounds__(kRecCtaThreads) k_records(DecodeParams P) {
   __shared__ Summ wtot[kRecThreads / 32];
   __shared__ Summ blk_excl_sh;
-  __shared__ uint32_t blk_fits_sh;
   __shared__ uint32_t hist[FULL ? kMaxBins : 1];     // frame shapes of the CTA's DML records
   {
     const uint32_t ab = *P.abort_flag;               // RECORDS / SCRATCH: set by k_chase, before this launch
@@ -779,49 +887,24 @@ __global__ void __launch_bounds__(kRecThreads) k_records(DecodeParams P) {
   }
   if (blockIdx.x >= n_blocks) return;                // the grid is sized for the capacity of the planes
   if (FULL) { for (uint32_t i = threadIdx.x; i < P.n_bins; i += blockDim.x) hist[i] = 0; }
-  const uint32_t r = blockIdx.x * kRecThreads + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-  const bool live = r < n_rec;
-  const uint64_t pos = live ? P.frame_off[r] : 0ull;
-  const uint8_t* fp = P.buf + pos;
+  const bool lb_warp = wid == kRecThreads / 32;      // warp 8 holds no records: it looks back while the others read their heads
+  const uint32_t r = blockIdx.x * kRecThreads + threadIdx.x;
+  const bool live = !lb_warp && r < n_rec;
+  volatile uint32_t* const status = P.scan_status;
+  const uint32_t ep = P.scan_epoch << 2;
+  ScanSlot* const slots = P.scan_slots;
+  uint64_t pos = 0;
+  HeadW H;
+#pragma unroll
+  for (int k = 0; k < 9; k++) H.a[k] = 0;
   FrameHead h;
   h.kind = 0; h.rel = 0; h.old_tag = 0; h.malformed = true; h.flen = 4;
   const DevSchema* s = nullptr;
-  Summ e = summ_identity();
-  if (live) {
-    h = read_head(fp, P.len - pos);
-    e = frame_state_elem(h, fp);
-    if (!h.malformed) {
-      if (h.kind == 'I' || h.kind == 'U' || h.kind == 'D') s = find_schema(P, h.rel, pos);
-      e.n_cells = frame_out_cells(h, s);
-    }
-  }
-  // ---- scan of the CTA's elements: inclusive inside each warp, then across the warps
-  Summ inc = e;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    Summ up;
-    SUMM_SHFL(up, inc, __shfl_up_sync, d);
-    if (lane >= (uint32_t)d) inc = fold(up, inc);
-  }
-  Summ ex;
-  SUMM_SHFL(ex, inc, __shfl_up_sync, 1);
-  if (lane == 0) ex = summ_identity();
-  if (lane == 31u) wtot[wid] = inc;
-  __syncthreads();
-  Summ wpre = summ_identity(), aggr = summ_identity();
-#pragma unroll
-  for (uint32_t k = 0; k < kRecThreads / 32; k++) { const Summ t = wtot[k]; if (k < wid) wpre = fold(wpre, t); aggr = fold(aggr, t); }
-  // ---- exclusive prefix of the CTA (carry not included): look back over the predecessors, 32 at a time
-  if (wid == 0) {
-    volatile uint32_t* status = P.scan_status;
-    const uint32_t ep = P.scan_epoch << 2;
-    ScanSlot* const slots = P.scan_slots;
-    if (lane == 0) {
-      if (blockIdx.x == 0) slots[0].incl = aggr; else slots[blockIdx.x].aggr = aggr;
-      __threadfence();
-      status[blockIdx.x] = ep | (blockIdx.x == 0 ? 2u : 1u);
-    }
+  Summ ex = summ_identity(), wpre = summ_identity();
+  if (lb_warp) {
+    // ---- exclusive prefix of the CTA (carry not included): look back over the predecessors, 32 at a time.  Nothing
+    // here depends on this CTA's own records, so it overlaps their head reads; predecessors are usually done by then.
     Summ prefix = summ_identity();                   // fold of the predecessors examined so far (the nearest ones)
     for (int hi = (int)blockIdx.x - 1; hi >= 0; hi -= 32) {
       const int idx = hi - (int)lane;
@@ -844,24 +927,65 @@ __global__ void __launch_bounds__(kRecThreads) k_records(DecodeParams P) {
       prefix = fold(window, prefix);
       if (incl) break;
     }
+    if (lane == 0) blk_excl_sh = prefix;
+  } else {
+    Summ e = summ_identity();
+    if (live) {
+      pos = P.frame_off[r];
+      H = load_head_words(P.buf + pos);
+      h = read_head_w(H, P.len - pos);
+      e = frame_state_elem(h, P.buf + pos);
+      if (!h.malformed) {
+        if (h.kind == 'I' || h.kind == 'U' || h.kind == 'D') s = find_schema(P, h.rel, pos);
+        e.n_cells = frame_out_cells(h, s);
+      }
+    }
+    // ---- scan of the CTA's elements: inclusive inside each warp, then across the warps
+    Summ inc = e;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      Summ up;
+      SUMM_SHFL(up, inc, __shfl_up_sync, d);
+      if (lane >= (uint32_t)d) inc = fold(up, inc);
+    }
+    SUMM_SHFL(ex, inc, __shfl_up_sync, 1);
+    if (lane == 0) ex = summ_identity();
+    if (lane == 31u) wtot[wid] = inc;
+    asm volatile("bar.sync 1, %0;" ::"n"(kRecThreads) : "memory");      // the record warps only
+    if (threadIdx.x == 0) {                           // publish the aggregate at once: the successors wait for it
+      Summ aggr = wtot[0];
+#pragma unroll
+      for (uint32_t k = 1; k < kRecThreads / 32; k++) aggr = fold(aggr, wtot[k]);
+      if (blockIdx.x == 0) slots[0].incl = aggr; else slots[blockIdx.x].aggr = aggr;
+      __threadfence();
+      status[blockIdx.x] = ep | (blockIdx.x == 0 ? 2u : 1u);
+    }
+    for (uint32_t k = 0; k < wid; k++) wpre = fold(wpre, wtot[k]);
+  }
+  __syncthreads();                                    // the prefix is known
+  uint64_t blk_cells = blk_excl_sh.n_cells;
+#pragma unroll
+  for (uint32_t k = 0; k < kRecThreads / 32; k++) blk_cells += wtot[k].n_cells;
+  const bool blk_fits = blk_cells <= P.cap_cells;     // prefixes grow: every CTA after the first overflow sees it too
+  if (lb_warp) {
     if (lane == 0) {
-      const Summ incl_total = fold(prefix, aggr);
+      Summ aggr = wtot[0];
+#pragma unroll
+      for (uint32_t k = 1; k < kRecThreads / 32; k++) aggr = fold(aggr, wtot[k]);
+      const Summ incl_total = fold(blk_excl_sh, aggr);
       if (blockIdx.x) { slots[blockIdx.x].incl = incl_total; __threadfence(); status[blockIdx.x] = ep | 2u; }
-      blk_excl_sh = prefix;
-      const bool fits = incl_total.n_cells <= P.cap_cells;     // prefixes grow: every CTA after the first overflow sees it too
-      blk_fits_sh = fits ? 1u : 0u;
-      if (!fits) atomicOr(P.abort_flag, ABORT_CELLS);
+      if (!blk_fits) atomicOr(P.abort_flag, ABORT_CELLS);
       if (blockIdx.x == n_blocks - 1u) {
         P.total[0] = incl_total;
-        if (FULL && fits && P.rec_cell_base) P.rec_cell_base[incl_total.n_rec] = incl_total.n_cells;
+        if (FULL && blk_fits && P.rec_cell_base) P.rec_cell_base[incl_total.n_rec] = incl_total.n_cells;
         if (P.seam_send) { SeamBlock sb; sb.total = incl_total; sb._pad[0] = sb._pad[1] = sb._pad[2] = sb._pad[3] = 0; *P.seam_send = sb; }
       }
     }
   }
   if (!FULL) return;
-  __syncthreads();
   uint32_t events = 0;
-  if (live && blk_fits_sh) {
+  if (live && blk_fits) {
+    const uint8_t* const fp = P.buf + pos;
     const Summ st = fold(fold(P.dc->carry, blk_excl_sh), fold(wpre, ex));
     const uint64_t ridx = st.n_rec;
     const uint64_t gidx = P.dc->record_index_base + ridx;
@@ -880,15 +1004,15 @@ __global__ void __launch_bounds__(kRecThreads) k_records(DecodeParams P) {
       wellformed = q1 != nullptr && cstr_end(q1, fe) != nullptr;
     }
     if (wellformed && (h.kind == 'I' || h.kind == 'U' || h.kind == 'D')) {
-      const uint32_t tt = fp[35];  // tuple marker (mlen >= 5 is guaranteed by read_head)
+      const uint32_t tt = hw_u8<35>(H);  // tuple marker (mlen >= 5 is guaranteed by read_head)
       if (h.kind == 'I') wellformed = tt == 'N';
       else if (h.kind == 'U') wellformed = tt == 'N' || tt == 'O' || tt == 'K';
       else wellformed = tt == 'O' || tt == 'K';
     }
     if (!wellformed) { report_error(P, gidx, SEQ_MALFORMED, ETL_E_MALFORMED_FRAME); ok = false; }
-    else if (h.kind == 'k') { start_lsn = be64(fp + 6); rrel = fp[22]; }
+    else if (h.kind == 'k') { start_lsn = hw_be64<6>(H); rrel = hw_u8<22>(H); }
     else {
-      start_lsn = be64(fp + 6);                      // wal_start apply.rs:1700
+      start_lsn = hw_be64<6>(H);                     // wal_start apply.rs:1700
       const uint8_t* m = fp + 31;                    // message body after the tag
       switch (h.kind) {
         case 'B':                                    // apply.rs:1927-1943

@@ -289,13 +289,16 @@ class Decoder:
         self._check(self._l.etl_dec_decode_finish(self._ctx, C.byref(st), record_index_base, C.byref(h)))
         return BatchHandle(self, h)
 
-    def decode(self, stream, carry_in=None, anchor_stride: int = 2048) -> DecodedBatch:
-        """Stage `stream` (bytes / uint8 array of CopyData-framed messages) and decode it."""
+    def decode(self, stream, carry_in=None, anchor_stride: int = 2048, max_frame_len=None) -> DecodedBatch:
+        """Stage `stream` (bytes / uint8 array of CopyData-framed messages) and decode it.  `max_frame_len` overrides the
+        stager's frame-length hint (tests: 0 = unknown, or a deliberately wrong bound)."""
         n = stream.nbytes if isinstance(stream, np.ndarray) else len(stream)
         st = Stager(max(n, 1), anchor_stride)
         try:
             st.append_framed(stream)
             inp = st.view()
+            if max_frame_len is not None:
+                inp.max_frame_len = int(max_frame_len)
             self._carry(inp, carry_in)
             with self.decode_input(inp, to_host=True) as bh:
                 return bh.to_host()

@@ -233,7 +233,9 @@ typedef struct etl_dec_input {
                                     empty segment; an anchor that is not a frame start yields ETL_E_MALFORMED_FRAME. */
   uint64_t n_anchors;
   uint32_t anchor_stride;
-  uint32_t _pad;
+  uint32_t max_frame_len;        /* 0 = unknown; else an upper bound of the longest frame in bytes ('d' + length field +
+                                    body; the stager fills it).  A hint: when no frame can hold a 512-byte value the
+                                    passes that exist for long values are skipped (and run after all if it was wrong) */
   const uint64_t* relation_offsets; /* host array: frame offsets of every 'R' frame, ascending */
   uint64_t n_relations;
   etl_stream_state carry_in;
@@ -353,13 +355,13 @@ typedef struct etl_dec_summary {
   uint32_t gpu_launches;  /* kernels launched for this batch */
   float kernel_ms;        /* CUDA-event time of the kernel sequence (resident input → resident output) */
   float h2d_ms, d2h_ms;
-  float index_ms;         /* pass A+B: k_act_* + k_index + k_scan + k_tile_prefix */
-  float emit_ms;          /* pass C: k_frames … k_long_verdict, incl. the join with the side stream */
-  float frames_ms;        /* k_frames */
+  float index_ms;         /* pass A: k_act_* + k_chase (frame offsets) [+ the totals-only k_records pass] */
+  float emit_ms;          /* pass B+C: k_records … k_long_cells */
+  float frames_ms;        /* k_records (stream-state scan + record plane) */
   float walk_ms;          /* k_bin_scan + k_perm (shape bins) */
   float spans_ms;         /* k_utf8_dead (structure-blind UTF-8 pass over segments without a frame start; side stream) */
   float cells_ms;         /* k_rows (tuples → rows: staging, walk, UTF-8, per-kind parsers, cell plane) */
-  float _pad1;
+  float long_ms;          /* k_long_cells (verdicts of the long text cells: line bitmap + edges) */
   uint64_t h2d_bytes, d2h_bytes; /* bytes copied host→device / device→host for this batch */
   uint64_t span_bytes;    /* bytes streamed by k_utf8_dead (its algorithmic bytes) */
   uint64_t record_index_base; /* global index of this batch's first record (sharded decode: Σ records of the ranks before) */

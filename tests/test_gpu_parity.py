@@ -396,6 +396,43 @@ def test_long_cell_utf8_boundaries(gpu, oracle_mod):
             assert (want.first_error[0] is None) == (kind == "emoji"), (p, kind)
 
 
+def test_frame_length_hint_is_only_a_hint(gpu, oracle_mod):
+    """etl_dec_input.max_frame_len lets the decoder leave out the passes that exist for long values.  Three cases on a
+    stream WITH long values (C5: TOASTed text, one value poisoned with an invalid byte deep inside): the stager's own
+    (correct) hint, no hint, and a hint that wrongly promises short frames — the planes and the error must not change."""
+    w = wl.make("c5", 0.003, n_segments=1)
+    stream, _ = w.generate()
+    raw = bytearray(stream.tobytes())
+    tables = w.table_schemas()
+    orc0 = oracle_mod.Oracle()
+    for tid, cols in tables.items():
+        orc0.put_table_schema(tid, cols)
+    clean = orc0.decode(bytes(raw))
+    longs = np.flatnonzero((np.asarray(clean.cell_tag) == 2) & (np.asarray(clean.cell_aux) > 8192))   # String cells of TOAST size
+    assert len(longs) > 4
+    victim = int(longs[len(longs) // 2])
+    for poison in (False, True):
+        data = bytes(raw)
+        if poison:
+            b = bytearray(data)
+            b[int(clean.cell_val[victim]) + int(clean.cell_aux[victim]) // 2] = 0xFF     # deep inside the value: a dead segment
+            data = bytes(b)
+        orc = oracle_mod.Oracle()
+        for tid, cols in tables.items():
+            orc.put_table_schema(tid, cols)
+        want = orc.decode(data)
+        assert (want.first_error[0] is not None) == poison
+        for hint in (None, 0, 64):
+            dec = gpu.Decoder(0)
+            for tid, cols in tables.items():
+                dec.put_table_schema(tid, cols)
+            got = dec.decode(data, max_frame_len=hint)
+            dec.close()
+            assert got.first_error == want.first_error, (poison, hint, got.first_error, want.first_error)
+            if not poison:
+                assert_planes_equal(got, want, data)
+
+
 def _raw_text_insert(rel_id: int, key: bytes, payload: bytes) -> bytes:
     """Insert message whose second column carries arbitrary bytes (pg.insert encodes str as UTF-8)."""
     import struct
