@@ -220,7 +220,9 @@ struct etl_dec_ctx {
   DevBuf<Summ> d_total{bufs};
   uint32_t scan_epoch = 0;
   uint32_t max_frame_hint = 0;            // etl_dec_input.max_frame_len of the batch in flight (0 = unknown)
-  bool long_skipped = false;              // the long-value passes were left out of the last launch_emit_kernels
+  bool long_skipped = false;
+  // ETL_TRACE=1: host wall time per phase of a decode call, printed by etl_dec_destroy (a measurement aid, not ABI)
+  double tr[6] = {0, 0, 0, 0, 0, 0}; uint64_t tr_n = 0; double tr_t0 = 0;              // the long-value passes were left out of the last launch_emit_kernels
   DevBuf<uint8_t> d_tables{bufs};          // DevSchema[] | schema_by_batch[] | col_kind[] | col_flags[] | relation errors
   DevBuf<uint32_t> d_line_bad{bufs}, d_dead{bufs}, d_bin_count{bufs}, d_bin_cursor{bufs}, d_perm{bufs}, d_rec_flen{bufs};
   DevBuf<LongCell> d_long{bufs};
@@ -273,6 +275,10 @@ struct etl_dec_ctx {
       return ETL_ERR_CUDA;                                                               \
     }                                                                                    \
   } while (0)
+
+static bool trace_on() { static const bool on = getenv("ETL_TRACE") != nullptr; return on; }
+static double now_us() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; }
+#define TRACE_MARK(i) do { if (trace_on()) { const double _t = now_us(); ctx->tr[i] += _t - ctx->tr_t0; ctx->tr_t0 = _t; } } while (0)
 
 extern "C" {
 
@@ -430,6 +436,9 @@ void etl_dec_destroy(etl_dec_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->side);
+  if (trace_on() && ctx->tr_n)
+    fprintf(stderr, "[etl trace] %llu decodes, mean us: prepare %.1f | enqueue %.1f | wait %.1f | results+d2h %.1f | summary %.1f\n",
+            (unsigned long long)ctx->tr_n, ctx->tr[0] / ctx->tr_n, ctx->tr[1] / ctx->tr_n, ctx->tr[2] / ctx->tr_n, ctx->tr[3] / ctx->tr_n, ctx->tr[4] / ctx->tr_n);
   ctx_release(ctx);
 }
 const char* etl_dec_last_error(const etl_dec_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null ctx"; }
@@ -1111,7 +1120,9 @@ static int run_decode(etl_dec_ctx* ctx, const etl_stream_state* carry_in, uint64
       }
     }
     if (int rc = launch_emit_kernels(ctx)) return fail(rc);
+    TRACE_MARK(1);
     CKB(cudaStreamSynchronize(st));
+    TRACE_MARK(2);
     if (sharded && seams.empty()) {
       seams.resize(ctx->n_ranks);
       CKB(cudaMemcpy(seams.data(), P.seam_all, sizeof(SeamBlock) * ctx->n_ranks, cudaMemcpyDeviceToHost));
@@ -1197,6 +1208,7 @@ static int run_decode(etl_dec_ctx* ctx, const etl_stream_state* carry_in, uint64
     CKB(cudaStreamSynchronize(st));
   } else { CKB(cudaEventRecord(ctx->ev[5], st)); CKB(cudaEventSynchronize(ctx->ev[5])); }
 
+  TRACE_MARK(3);
   // ---- summary
   etl_dec_summary& S = b->summary;
   memset(&S, 0, sizeof S);
@@ -1260,6 +1272,7 @@ static int run_decode(etl_dec_ctx* ctx, const etl_stream_state* carry_in, uint64
   ctx->pending_installs.clear(); ctx->foreign_installs.clear();
   b->dev_stream = P.buf;
   *out = b;
+  TRACE_MARK(4);
   return ETL_OK;
 #undef CKB
 }
@@ -1267,7 +1280,9 @@ const uint8_t* etl_dec_batch_device_stream(const etl_dec_batch* b) { return b ? 
 
 int etl_dec_decode(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t flags, etl_dec_batch** out) {
   if (!ctx || !in || !out) return ETL_ERR_INVALID_ARG;
+  if (trace_on()) { ctx->tr_t0 = now_us(); ctx->tr_n++; }
   if (int rc = prepare(ctx, in, flags, false)) return rc;
+  TRACE_MARK(0);
   return run_decode(ctx, &in->carry_in, 0, false, false, out);
 }
 int etl_dec_decode_sharded(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t flags, etl_dec_batch** out) {
