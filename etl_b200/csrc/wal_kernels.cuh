@@ -661,67 +661,64 @@ __device__ __forceinline__ bool utf8_range_bad(const uint8_t* cell, uint32_t cel
 // Structure-blind UTF-8 pass.  The position-local rule (utf8_step_bad) needs only the three preceding
 // bytes, so the verdict for position i of a cell is the verdict for stream position a+i whenever the
 // three predecessors lie inside the cell.  A segment without a frame start lies inside one frame; the
-// segments that lie inside one text cell are what k_walk asks about.  One warp per dead segment, 2 KiB
+// segments that lie inside one text cell are what k_long_cells asks about.  One warp per dead segment, 2 KiB
 // (4 coalesced 16-byte loads per lane) per pass; the bitmap is written only where a violation is found.
 // Short-lived CTAs (a warp takes kDeadSegsPerWarp consecutive dead segments and retires): the pass runs on a low-priority
 // side stream underneath latency-bound kernels, and a persistent grid would sit on every SM's thread slots until it is
 // done — k_bin_scan / k_perm waited 1.6 ms for a slot behind it (round-2 sweep).  The grid is sized for "every segment dead".
 constexpr uint32_t kDeadSegsPerWarp = 4;
 // Work item i of the dead-segment pass = 2 KiB pass (i % ppseg) of dead segment (i / ppseg), ppseg = passes per segment.
-// A warp takes up to kDeadIlp items at once: every lane owns 64 contiguous bytes of each (half a 128-byte line), so
-// kDeadIlp x 4 16-byte loads are in flight per lane before the first byte is looked at; the three bytes before a lane's
-// first chunk come from one 4-byte load that hits L1 — no shuffles (round 1 paid three __shfl per 16 bytes).
-constexpr int kDeadIlp = 1;   // measured: 4 items (16 loads) per lane cost 102 registers and a quarter of the warps — 2.14 ms instead of 1.46 ms on C5
-__device__ __forceinline__ void utf8_dead_items(const DecodeParams& P, uint32_t item0, uint32_t step, uint32_t n_items, uint32_t ppseg, uint32_t lane) {
-  uint4 x[kDeadIlp][4];
-  uint32_t pw[kDeadIlp];
-  uint64_t off[kDeadIlp], s1[kDeadIlp];
+// The verdict of one lane's 64 bytes [off, off + 64) of a dead-segment item that ends at s1: x = the four 16-byte chunks,
+// pw = the word before them.  Sets the line bits of the item (two lanes per 128-byte line) — all lanes of the warp call it.
+__device__ __forceinline__ void utf8_dead_verdict(const DecodeParams& P, const uint4 (&x)[4], uint32_t pw, uint64_t off, uint64_t s1, uint32_t lane) {
+  bool bad = false;
+  uint32_t prev = pw;
 #pragma unroll
-  for (int j = 0; j < kDeadIlp; j++) {
-    const uint32_t it = item0 + (uint32_t)j * step;
-    off[j] = 0; s1[j] = 0; pw[j] = 0;
-    if (it < n_items) {
-      const uint64_t seg0 = (uint64_t)P.dead[it / ppseg] * P.anchor_stride;
-      const uint64_t base = seg0 + (uint64_t)(it % ppseg) * 2048ull;
-      const uint64_t e = seg0 + P.anchor_stride < P.len ? seg0 + P.anchor_stride : P.len;
-      s1[j] = base < e ? e : 0;
-      off[j] = base + (uint64_t)lane * 64ull;
+  for (int k = 0; k < 4; k++) {
+    const uint32_t h = x[k].x | x[k].y | x[k].z | x[k].w;
+    if ((h & 0x80808080u) | (prev & 0x80808000u)) {           // high bits here or in the three bytes before
+      const uint64_t o = off + 16ull * k;
+      if (o < s1) bad |= !utf8_chunk_valid_at(P.buf, P.len, o, o + 16ull < P.len ? o + 16ull : P.len);
     }
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-      x[j][k] = off[j] + 16ull * k < s1[j] ? *reinterpret_cast<const uint4*>(P.buf + off[j] + 16ull * k) : make_uint4(0, 0, 0, 0);   // +64 bytes of padding are readable
-    if (off[j] >= 4 && off[j] < s1[j]) pw[j] = *reinterpret_cast<const uint32_t*>(P.buf + off[j] - 4);   // last word before the lane's bytes
+    prev = x[k].w;
+  }
+  // two lanes per 128-byte line, 16 lines per item: bit m = line m holds a violation
+  unsigned bal = __ballot_sync(0xffffffffu, bad);
+  if (bal) {
+    bal = (bal | (bal >> 1)) & 0x55555555u;
+    bal = (bal | (bal >> 1)) & 0x33333333u; bal = (bal | (bal >> 2)) & 0x0F0F0F0Fu;
+    bal = (bal | (bal >> 4)) & 0x00FF00FFu; bal = (bal | (bal >> 8)) & 0x0000FFFFu;
+    const uint64_t base = off - (uint64_t)lane * 64ull;     // a multiple of min(stride, 2048): the bits stay inside one word
+    if (lane == 0) atomicOr(&P.line_bad[(base >> 7) >> 5], bal << ((base >> 7) & 31u));
+  }
+}
+// One item per warp step: every lane owns 64 contiguous bytes (half a 128-byte line), four 16-byte loads in flight before the
+// first byte is looked at; the three bytes before a lane's first chunk come from one 4-byte load that hits L1 — no shuffles
+// (round 1 paid three __shfl per 16 bytes).  Measured: 4 items (16 loads) per lane cost 102 registers and a quarter of the
+// warps — 2.14 ms instead of 1.46 ms on C5.
+__device__ __forceinline__ void utf8_dead_items(const DecodeParams& P, uint32_t it, uint32_t, uint32_t n_items, uint32_t ppseg, uint32_t lane) {
+  uint4 x[4];
+  uint32_t pw = 0;
+  uint64_t off = 0, s1 = 0;
+  if (it < n_items) {
+    const uint64_t seg0 = (uint64_t)P.dead[it / ppseg] * P.anchor_stride;
+    const uint64_t base = seg0 + (uint64_t)(it % ppseg) * 2048ull;
+    const uint64_t e = seg0 + P.anchor_stride < P.len ? seg0 + P.anchor_stride : P.len;
+    s1 = base < e ? e : 0;
+    off = base + (uint64_t)lane * 64ull;
   }
 #pragma unroll
-  for (int j = 0; j < kDeadIlp; j++) {
-    bool bad = false;
-    uint32_t prev = pw[j];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const uint32_t h = x[j][k].x | x[j][k].y | x[j][k].z | x[j][k].w;
-      if ((h & 0x80808080u) | (prev & 0x80808000u)) {           // high bits here or in the three bytes before
-        const uint64_t o = off[j] + 16ull * k;
-        if (o < s1[j]) bad |= !utf8_chunk_valid_at(P.buf, P.len, o, o + 16ull < P.len ? o + 16ull : P.len);
-      }
-      prev = x[j][k].w;
-    }
-    // two lanes per 128-byte line, 16 lines per item: bit m = line m holds a violation
-    unsigned bal = __ballot_sync(0xffffffffu, bad);
-    if (bal) {
-      bal = (bal | (bal >> 1)) & 0x55555555u;
-      bal = (bal | (bal >> 1)) & 0x33333333u; bal = (bal | (bal >> 2)) & 0x0F0F0F0Fu;
-      bal = (bal | (bal >> 4)) & 0x00FF00FFu; bal = (bal | (bal >> 8)) & 0x0000FFFFu;
-      const uint64_t base = off[j] - (uint64_t)lane * 64ull;     // a multiple of min(stride, 2048): the bits stay inside one word
-      if (lane == 0) atomicOr(&P.line_bad[(base >> 7) >> 5], bal << ((base >> 7) & 31u));
-    }
-  }
+  for (int k = 0; k < 4; k++)
+    x[k] = off + 16ull * k < s1 ? *reinterpret_cast<const uint4*>(P.buf + off + 16ull * k) : make_uint4(0, 0, 0, 0);   // +64 bytes of padding are readable
+  if (off >= 4 && off < s1) pw = *reinterpret_cast<const uint32_t*>(P.buf + off - 4);   // last word before the lane's bytes
+  utf8_dead_verdict(P, x, pw, off, s1, lane);
 }
 __device__ __forceinline__ uint32_t dead_ppseg(const DecodeParams& P) { return P.anchor_stride > 2048u ? P.anchor_stride / 2048u : 1u; }
 __global__ void __launch_bounds__(256) k_utf8_dead(DecodeParams P) {
   const uint32_t ppseg = dead_ppseg(P);
   const uint32_t n_items = (P.n_anchors - *P.n_act) * ppseg;
   const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // warp w: items [w * kDeadSegsPerWarp, +kDeadSegsPerWarp)
-  for (uint32_t it = w * kDeadSegsPerWarp; it < min(n_items, (w + 1u) * kDeadSegsPerWarp); it += (uint32_t)kDeadIlp)
+  for (uint32_t it = w * kDeadSegsPerWarp; it < min(n_items, (w + 1u) * kDeadSegsPerWarp); it++)
     utf8_dead_items(P, it, 1u, min(n_items, (w + 1u) * kDeadSegsPerWarp), ppseg, threadIdx.x & 31u);
 }
 // any flagged line in [l0, l1)?  One bitmap word per lane and step (a 64 KiB value spans 16 words: a single lane

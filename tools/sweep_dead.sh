@@ -1,9 +1,10 @@
 #!/bin/bash
-# where / how wide the structure-blind UTF-8 pass runs (ETL_DEAD_MODE, ETL_DEAD_CTAS), c5 at full size
-for mode in 3 2; do for ctas in 0; do
-  echo "== mode $mode ctas $ctas"
-  ETL_DEAD_MODE=$mode ETL_DEAD_CTAS=$ctas python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-extras 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read())
-print(round(d['value'],1),'GB/s', round(d['ms_per_step'],3),'ms', {k:round(v,3) for k,v in d['roofline']['kernels_ms'].items()})"
-done; done
+# Where the dead-segment UTF-8 pass runs (ETL_DEAD_MODE) x k_rows window (library variants built with ETL_LIB_SUFFIX /
+# ETL_NVCC_DEFS, see etl_b200/build.py).  Prints the per-kernel event times of the last decode.
+for cfg in ":2" ":4" "_b:4" "_b:2" ":0"; do
+  v=${cfg%%:*}; m=${cfg##*:}
+  for wl in "c5 0.5" "c2 1.0"; do
+    echo "== lib '${v}' ETL_DEAD_MODE=$m $wl"
+    ETL_LIB_SUFFIX=$v ETL_DEAD_MODE=$m timeout 120 python tools/run_decode.py $wl 6 2>&1 | tail -n 2
+  done
+done
