@@ -256,9 +256,9 @@ class Staged:
         self.d_stream = self.d_anchors = None
 
 
-def decode_once(dec, st, resident, sharded, carry=None):
+def decode_once(dec, st, resident, sharded, carry=None, timing=True):
     inp = st.view(resident, carry)
-    bh = dec.decode_sharded(inp, to_host=not resident) if sharded else dec.decode_input(inp, to_host=not resident)
+    bh = dec.decode_sharded(inp, to_host=not resident) if sharded else dec.decode_input(inp, to_host=not resident, timing=timing)
     s = bh.summary()
     if s.first_error.record_index != NO_ERROR:
         # never raise between collectives (the other ranks would wait for this one for ever): remember it, fail the line later
@@ -415,7 +415,7 @@ def batch_leg(torch, dev, name, scale, calls, stride):
             carry = None
             for st in staged:
                 t0 = time.perf_counter()
-                bh, s = decode_once(dec, st, resident, False, carry)
+                bh, s = decode_once(dec, st, resident, False, carry, timing=False)   # ETL_DECODE_NO_TIMING: what a production caller passes
                 if not resident:
                     bh.planes(True)
                 carry = (int(s.carry_out.in_tx), int(s.carry_out.final_lsn), int(s.carry_out.next_tx_ordinal))

@@ -170,3 +170,4 @@ def load(build: bool = True):
 
 
 RESULTS_TO_HOST = 0x1
+NO_TIMING = 0x4

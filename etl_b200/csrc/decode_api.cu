@@ -1001,7 +1001,6 @@ static int launch_emit_kernels(etl_dec_ctx* ctx) {
   const size_t perm_cap = cap_r + 32ull * P.n_bins + 256;
   CK(cudaEventRecord(ctx->ev[3], st));
   CK(cudaMemsetAsync(P.bin_count, 0, P.n_bins * 4, st));
-  CK(cudaMemsetAsync(P.perm, 0xFF, perm_cap * 4, st));
   // k_heavy / k_fix read every cell tag: a record that failed leaves cells unwritten, and a stale tag must not look pending
   if (P.cap_cells) CK(cudaMemsetAsync(P.cell_tag, 0, P.cap_cells, st));
   ctx->long_skipped = long_passes_skippable(ctx);
@@ -1208,27 +1207,29 @@ static int run_decode(etl_dec_ctx* ctx, const etl_stream_state* carry_in, uint64
     b->has_host = true;
     CKB(cudaEventRecord(ctx->ev[5], st));
     CKB(cudaStreamSynchronize(st));
-  } else { CKB(cudaEventRecord(ctx->ev[5], st)); CKB(cudaEventSynchronize(ctx->ev[5])); }
+  } else if (!(ctx->pending_flags & ETL_DECODE_NO_TIMING)) { CKB(cudaEventRecord(ctx->ev[5], st)); CKB(cudaEventSynchronize(ctx->ev[5])); }
 
   TRACE_MARK(3);
   // ---- summary
   etl_dec_summary& S = b->summary;
   memset(&S, 0, sizeof S);
   float h2d_ms = 0, index_ms = 0, emit_ms = 0, d2h_ms = 0;
-  cudaEventElapsedTime(&h2d_ms, ctx->ev[0], ctx->ev[1]);
-  cudaEventElapsedTime(&index_ms, ctx->ev[1], ctx->ev[2]);
-  cudaEventElapsedTime(&emit_ms, ctx->ev[3], ctx->ev[4]);
-  cudaEventElapsedTime(&d2h_ms, ctx->ev[4], ctx->ev[5]);
-  if (ctx->pending_flags & ETL_DECODE_RESULTS_TO_HOST) { float whole = 0; cudaEventElapsedTime(&whole, ctx->ev[3], ctx->ev[5]); emit_ms = whole - d2h_ms; }
+  if (!(ctx->pending_flags & ETL_DECODE_NO_TIMING)) {          // ten event queries: ~25 us of host time on an 8 MiB batch
+    cudaEventElapsedTime(&h2d_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&index_ms, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&emit_ms, ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&d2h_ms, ctx->ev[4], ctx->ev[5]);
+    if (ctx->pending_flags & ETL_DECODE_RESULTS_TO_HOST) { float whole = 0; cudaEventElapsedTime(&whole, ctx->ev[3], ctx->ev[5]); emit_ms = whole - d2h_ms; }
+    if (P.n_anchors) {
+      cudaEventElapsedTime(&S.frames_ms, ctx->ev[3], ctx->evk[0]);
+      cudaEventElapsedTime(&S.walk_ms, ctx->evk[0], ctx->evk[2]);    // k_bin_scan + k_perm
+      cudaEventElapsedTime(&S.cells_ms, ctx->evk[2], ctx->evk[1]);   // k_rows
+      cudaEventElapsedTime(&S.spans_ms, ctx->ev_l0, ctx->ev_l1);     // k_utf8_dead
+      cudaEventElapsedTime(&S.long_ms, ctx->evk[3], ctx->ev[4]);     // k_long_cells
+    }
+  }
   S.kernel_ms = index_ms + emit_ms;
   S.index_ms = index_ms; S.emit_ms = emit_ms;
-  if (P.n_anchors) {
-    cudaEventElapsedTime(&S.frames_ms, ctx->ev[3], ctx->evk[0]);
-    cudaEventElapsedTime(&S.walk_ms, ctx->evk[0], ctx->evk[2]);    // k_bin_scan + k_perm
-    cudaEventElapsedTime(&S.cells_ms, ctx->evk[2], ctx->evk[1]);   // k_rows
-    cudaEventElapsedTime(&S.spans_ms, ctx->ev_l0, ctx->ev_l1);     // k_utf8_dead
-    cudaEventElapsedTime(&S.long_ms, ctx->evk[3], ctx->ev[4]);     // k_long_cells
-  }
   S.h2d_ms = h2d_ms; S.d2h_ms = d2h_ms;
   S.h2d_bytes = ctx->pending_h2d_bytes;
   // bytes k_utf8_dead streamed: the dead segments (h_scalars[12] = live segment count, left by k_act_scan)

@@ -201,9 +201,10 @@ class Decoder:
         if carry_in:
             inp.carry_in.in_tx, inp.carry_in.final_lsn, inp.carry_in.next_tx_ordinal = int(carry_in[0]), carry_in[1], carry_in[2]
 
-    def decode_input(self, inp: abi.DecInput, to_host: bool = True) -> "BatchHandle":
+    def decode_input(self, inp: abi.DecInput, to_host: bool = True, timing: bool = True) -> "BatchHandle":
         h = C.c_void_p()
-        rc = self._l.etl_dec_decode(self._ctx, C.byref(inp), abi.RESULTS_TO_HOST if to_host else 0, C.byref(h))
+        flags = (abi.RESULTS_TO_HOST if to_host else 0) | (0 if timing else abi.NO_TIMING)
+        rc = self._l.etl_dec_decode(self._ctx, C.byref(inp), flags, C.byref(h))
         self._check(rc)
         return BatchHandle(self, h)
 

@@ -290,6 +290,8 @@ enum {
   ETL_DECODE_RESULTS_TO_HOST = 0x1, /* copy result planes to pinned host memory before returning */
   ETL_DECODE_SEAM_DEFER = 0x2,      /* multi-GPU shard: carry_in unknown, run only the local scan;
                                        caller exchanges etl_dec_seam and calls etl_dec_decode_finish */
+  ETL_DECODE_NO_TIMING = 0x4,       /* leave the *_ms fields of the summary at 0: the CUDA-event queries behind them cost
+                                       ~25 us of host time per call, which an 8 MiB batch notices */
 };
 
 /* per-shard seam summary exchanged with ONE all-gather across the GPUs of a box */

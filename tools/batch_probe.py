@@ -18,6 +18,7 @@ from etl_b200 import decoder, workloads as wl  # noqa: E402
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
 scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 calls = int(sys.argv[3]) if len(sys.argv) > 3 else 500
+timing = (sys.argv[4] != "notiming") if len(sys.argv) > 4 else True
 dev = torch.device("cuda", 0)
 torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=-1))
 w = wl.make(name, scale, n_segments=1)
@@ -44,7 +45,7 @@ while done < calls + 2 * len(staged):
         t0 = time.perf_counter()
         inp = st.view(True, carry)
         t1 = time.perf_counter()
-        bh = dec.decode_input(inp, to_host=False)
+        bh = dec.decode_input(inp, to_host=False, timing=timing)
         t2 = time.perf_counter()
         s = bh.summary()
         carry = (int(s.carry_out.in_tx), int(s.carry_out.final_lsn), int(s.carry_out.next_tx_ordinal))
