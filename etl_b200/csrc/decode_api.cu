@@ -587,8 +587,7 @@ void etl_dec_batch_free(etl_dec_batch* b) {
 
 // Where the structure-blind UTF-8 pass (k_utf8_dead, HBM-bound) runs relative to the latency-bound passes.
 // 0: side stream from the start of the index pass; 1: side stream from the start of the tuple pass (default);
-// 2 (default): main stream after the tuple pass; 3: inside k_rows — its warps stream the dead segments after their rows;
-// 4: like 0, but the copy-engine pipeline k_utf8_dead_tma (one 64-thread CTA per SM) instead of the LDG kernel.
+// 2 (default): main stream after the tuple pass; 3: inside k_rows — its warps stream the dead segments after their rows.
 // Measured on C5 (10 GiB, round 2): 2 → 3.66 ms per decode, 0 → 3.96, 1 → 4.10, 3 → 4.24: k_rows fills the register file and
 // is bound by instruction issue, the UTF-8 pass needs every SM's warps to saturate HBM — sharing the SMs helps neither.
 // ETL_DEAD_MODE is a tuning knob for measurement, not part of the ABI.
@@ -616,8 +615,7 @@ static cudaError_t launch_dead_side(etl_dec_ctx* ctx, cudaStream_t st) {
   if ((e = cudaEventRecord(ctx->ev_in, st)) != cudaSuccess) return e;
   if ((e = cudaStreamWaitEvent(ctx->side, ctx->ev_in, 0)) != cudaSuccess) return e;
   if ((e = cudaEventRecord(ctx->ev_l0, ctx->side)) != cudaSuccess) return e;
-  if (dead_mode() == 4) k_utf8_dead_tma<<<sm_count(ctx), kDeadTmaWarps * 32, kDeadTmaSmem, ctx->side>>>(ctx->P);
-  else k_utf8_dead<<<dead_grid(ctx->P), 256, 0, ctx->side>>>(ctx->P);
+  k_utf8_dead<<<dead_grid(ctx->P), 256, 0, ctx->side>>>(ctx->P);
   if ((e = cudaEventRecord(ctx->ev_l1, ctx->side)) != cudaSuccess) return e;
   ctx->launches += 1;
   ctx->lines_launched = true;
@@ -917,7 +915,7 @@ static int launch_index(etl_dec_ctx* ctx, bool exact) {
       k_act_scatter<<<act_blocks, kActThreads, 0, st>>>(P);
       ctx->launches += 3;
     }
-    if (dead_mode() == 0 || dead_mode() == 4) CK(launch_dead_side(ctx, st));   // underneath everything that follows (needs only the dead-segment list)
+    if (dead_mode() == 0) CK(launch_dead_side(ctx, st));   // underneath everything that follows (needs only the dead-segment list)
     if (!exact) launch_chase(ctx, 3u);
     else {
       P.frame_cap = ~0ull;

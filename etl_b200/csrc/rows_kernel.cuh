@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(kHeavyThreads, 3) k_heavy(DecodeParams P) {
   const CellHeaps H{P.heap, P.arr_top, P.arr_base, P.heap_cap, P.heap_overflow};
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint64_t c0 = (uint64_t)tile * kHeavyTile;
-    if (threadIdx.x < 3) cnt[threadIdx.x] = 0;
+    if (threadIdx.x < 4) cnt[threadIdx.x] = 0;           // [0..3) cells per class, [3] the next row to hand out
     __syncthreads();
     {   // gather: 16 tags per thread (one 16-byte load: the cell planes are 256-byte aligned and the tile is a multiple of 16)
       const uint64_t t0 = c0 + (uint64_t)threadIdx.x * 16u;
@@ -551,9 +551,18 @@ __global__ void __launch_bounds__(kHeavyThreads, 3) k_heavy(DecodeParams P) {
       }
     }
     __syncthreads();
-    for (uint32_t cls = 0; cls < 3; cls++) {
+    // rows of 32 cells of one class, taken by whichever warp is free (a json row costs many times a float row: a fixed
+    // row → warp assignment left warps waiting at the tile's barrier for a quarter of the kernel's samples)
+    const uint32_t rows0 = (cnt[0] + 31u) >> 5, rows1 = (cnt[1] + 31u) >> 5, rows2 = (cnt[2] + 31u) >> 5;
+    for (;;) {
+      uint32_t row = 0;
+      if (lane == 0) row = atomicAdd(&cnt[3], 1u);
+      row = __shfl_sync(0xffffffffu, row, 0);
+      if (row >= rows0 + rows1 + rows2) break;
+      const uint32_t cls = row < rows0 ? 0u : (row < rows0 + rows1 ? 1u : 2u);
       const uint32_t n = cnt[cls];
-      for (uint32_t base = wid * 32u; base < n; base += kHeavyWarps * 32u) {
+      {
+        const uint32_t base = (row - (cls == 0u ? 0u : (cls == 1u ? rows0 : rows0 + rows1))) * 32u;
         const bool have = base + lane < n;
         const uint64_t cell = c0 + (have ? lists[cls * kHeavyTile + base + lane] : 0u);
         uint32_t kind = 0, len = 0, rec = 0;
@@ -641,90 +650,6 @@ __global__ void __launch_bounds__(256) k_fix(DecodeParams P) {
         if (h) atomicAdd(&P.rec_heap_hint[rec], h);
       }
     }
-  }
-}
-
-// ================================================================================================
-// The dead-segment UTF-8 pass as a copy-engine pipeline (ETL_DEAD_MODE=4).  The LDG version needs every warp slot of
-// the SM to keep enough bytes in flight to saturate HBM, so it cannot share an SM with k_rows (which fills the register
-// file).  Here one small CTA per SM keeps kDeadStages items of 2 KiB in flight with 1-D bulk async copies into shared
-// memory: the bytes in flight no longer depend on resident warps or registers.  Two warps consume: a warp owns every
-// second stage, waits for the stage's mbarrier, checks its 64 bytes per lane out of shared memory (same rule, same line
-// bitmap as k_utf8_dead) and refills the stage with the next item of its slot.  Launched on the low-priority side stream
-// right after the live / dead segment lists exist, it streams underneath k_chase … k_rows.
-constexpr uint32_t kDeadTmaWarps = 2, kDeadStages = 20, kDeadStageBytes = 2048 + 16, kDeadPerWarp = kDeadStages / kDeadTmaWarps;
-constexpr uint32_t kDeadTmaMetaOff = 256, kDeadTmaHdrBytes = 1024;   // mbarriers | per-stage {base, nbytes} | stages
-constexpr uint32_t kDeadTmaSmem = kDeadTmaHdrBytes + kDeadStages * kDeadStageBytes;
-static_assert(kDeadStages * 8 <= kDeadTmaMetaOff && kDeadTmaMetaOff + kDeadStages * 16 <= kDeadTmaHdrBytes && kDeadStageBytes % 16 == 0 &&
-              kDeadStages % kDeadTmaWarps == 0, "dead-pass pipeline geometry");
-__global__ void __launch_bounds__(kDeadTmaWarps * 32, 16) k_utf8_dead_tma(DecodeParams P) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-  const uint32_t ppseg = dead_ppseg(P);
-  const uint32_t n_items = (P.n_anchors - *P.n_act) * ppseg;
-  if (threadIdx.x == 0) {
-    for (uint32_t s = 0; s < kDeadStages; s++) mbar_init(smem_u32(smem + 8u * s), 1u);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  const uint64_t n_slots = (uint64_t)gridDim.x * kDeadStages;    // slot = stage s of CTA b: s * gridDim + b (neighbouring SMs stream neighbouring items)
-  uint64_t* const meta = reinterpret_cast<uint64_t*>(smem + kDeadTmaMetaOff);   // [2 s] = stream offset of the item in stage s, [2 s + 1] = its bytes
-  // The stage holds stream bytes [base - 16, base + nbytes) at offset 0 (the 16 bytes before the item give the look-back
-  // word of lane 0; the first item of a stream has nothing before it).  `seg` = the item's dead-segment number, fetched a
-  // round earlier: the list lookup is a dependent global load that must not sit between two copies.
-  auto issue = [&](uint32_t s, uint64_t it, uint32_t seg) {
-    if (lane == 0) {
-      const uint32_t bar = smem_u32(smem + 8u * s);
-      const uint64_t seg0 = (uint64_t)seg * P.anchor_stride;
-      const uint64_t base = seg0 + (it % ppseg) * 2048ull;
-      const uint64_t e = seg0 + P.anchor_stride < P.len ? seg0 + P.anchor_stride : P.len;
-      const uint32_t nbytes = base < e ? (uint32_t)min((uint64_t)2048, e - base) : 0u;    // 0: the clamped tail of the last segment
-      meta[2u * s] = base; meta[2u * s + 1u] = nbytes;
-      if (nbytes) {
-        const uint32_t lead = base >= 16ull ? 16u : 0u;
-        const uint32_t bytes = lead + ((nbytes + 15u) & ~15u);                 // ≤ len + 15: the stream has 64 readable bytes of padding
-        mbar_arrive_expect_tx(bar, bytes);
-        bulk_g2s(smem_u32(smem + kDeadTmaHdrBytes + s * kDeadStageBytes + (16u - lead)), P.buf + base - lead, bytes, bar);
-      } else mbar_arrive(bar);
-    }
-  };
-  uint32_t nseg[kDeadPerWarp];                                    // segment number of the item each of this warp's stages takes next
-#pragma unroll
-  for (uint32_t k = 0; k < kDeadPerWarp; k++) {
-    const uint64_t it = (uint64_t)(wid + k * kDeadTmaWarps) * gridDim.x + blockIdx.x;
-    nseg[k] = it < n_items ? P.dead[it / ppseg] : 0u;
-  }
-#pragma unroll
-  for (uint32_t k = 0; k < kDeadPerWarp; k++) {
-    const uint32_t s = wid + k * kDeadTmaWarps;
-    const uint64_t it = (uint64_t)s * gridDim.x + blockIdx.x;
-    if (it < n_items) issue(s, it, nseg[k]);
-    nseg[k] = it + n_slots < n_items ? P.dead[(it + n_slots) / ppseg] : 0u;
-  }
-  for (uint32_t round = 0;; round++) {
-    bool any = false;
-#pragma unroll
-    for (uint32_t k = 0; k < kDeadPerWarp; k++) {
-      const uint32_t s = wid + k * kDeadTmaWarps;
-      const uint64_t it = (uint64_t)round * n_slots + (uint64_t)s * gridDim.x + blockIdx.x;
-      if (it >= n_items) continue;                               // nothing was issued into this stage
-      any = true;
-      mbar_wait(smem_u32(smem + 8u * s), round & 1u);
-      const uint64_t base = meta[2u * s];
-      const uint32_t nbytes = (uint32_t)meta[2u * s + 1u];
-      const uint8_t* st = smem + kDeadTmaHdrBytes + s * kDeadStageBytes + 16u;   // stream offset `base`
-      const uint32_t lo = lane * 64u;
-      uint4 x[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) x[j] = lo + 16u * j < nbytes ? *reinterpret_cast<const uint4*>(st + lo + 16u * j) : make_uint4(0, 0, 0, 0);
-      uint32_t pw = 0;
-      if (lo < nbytes && base + lo >= 4ull) pw = *reinterpret_cast<const uint32_t*>(st + lo - 4u);
-      utf8_dead_verdict(P, x, pw, base + lo, nbytes ? base + nbytes : 0ull, lane);
-      __syncwarp();                                              // every lane has read the stage and its meta: refill
-      if (it + n_slots < n_items) issue(s, it + n_slots, nseg[k]);
-      nseg[k] = it + 2ull * n_slots < n_items ? P.dead[(it + 2ull * n_slots) / ppseg] : 0u;
-    }
-    if (!any) break;
   }
 }
 

@@ -852,15 +852,6 @@ struct ScanSlot { Summ aggr; Summ incl; };
     (dst).n_cells = fn(0xffffffffu, (src).n_cells, arg); (dst).n_rec = fn(0xffffffffu, (src).n_rec, arg); \
     (dst).flags = fn(0xffffffffu, (src).flags, arg);                                                      \
   } while (0)
-constexpr int kLbPer = 4;                               // predecessors a look-back lane examines per window
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {   // earlier writes of this thread are visible before v is
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ Summ ld_summ_cg(const Summ* p) {      // L2 (another CTA wrote it)
   const uint4 a = __ldcg(reinterpret_cast<const uint4*>(p)), b = __ldcg(reinterpret_cast<const uint4*>(p) + 1);
   Summ r;
@@ -868,7 +859,7 @@ __device__ __forceinline__ Summ ld_summ_cg(const Summ* p) {      // L2 (another 
   return r;
 }
 template <bool FULL>
-__global__ void __launch_bounds__(kRecCtaThreads) k_records(DecodeParams P) {
+__global__ void __launch_bounds__(kRecCtaThreads, 4) k_records(DecodeParams P) {   // 4 CTAs per SM: at most 56 registers
   __shared__ Summ wtot[kRecThreads / 32];
   __shared__ Summ blk_excl_sh;
   __shared__ uint32_t hist[FULL ? kMaxBins : 1];     // frame shapes of the CTA's DML records
@@ -899,7 +890,7 @@ __global__ void __launch_bounds__(kRecCtaThreads) k_records(DecodeParams P) {
   const bool lb_warp = wid == kRecThreads / 32;      // warp 8 holds no records: it looks back while the others read their heads
   const uint32_t r = blockIdx.x * kRecThreads + threadIdx.x;
   const bool live = !lb_warp && r < n_rec;
-  uint32_t* const status = P.scan_status;
+  volatile uint32_t* const status = P.scan_status;
   const uint32_t ep = P.scan_epoch << 2;
   ScanSlot* const slots = P.scan_slots;
   uint64_t pos = 0;
@@ -914,35 +905,16 @@ __global__ void __launch_bounds__(kRecCtaThreads) k_records(DecodeParams P) {
     // ---- exclusive prefix of the CTA (carry not included): look back over the predecessors, 32 at a time.  Nothing
     // here depends on this CTA's own records, so it overlaps their head reads; predecessors are usually done by then.
     Summ prefix = summ_identity();                   // fold of the predecessors examined so far (the nearest ones)
-    for (int hi = (int)blockIdx.x - 1; hi >= 0; hi -= 32 * kLbPer) {
-      // a lane owns kLbPer consecutive predecessors (nearest first): their status words and summaries are fetched together,
-      // folded in the lane, and one warp reduction covers 128 CTAs — a batch of 8 MiB (160 CTAs, all resident at once, so
-      // nobody has an inclusive prefix yet) needs two windows instead of five
-      const int idx0 = hi - kLbPer * (int)lane;
-      uint32_t sw[kLbPer];
-      bool ready;
-      do {
-        ready = true;
-#pragma unroll
-        for (int j = 0; j < kLbPer; j++) {
-          sw[j] = ep | 2u;                            // before the first CTA: an inclusive prefix equal to the identity
-          if (idx0 - j >= 0) { sw[j] = ld_acquire_u32(status + (idx0 - j)); ready = ready && (sw[j] & ~3u) == ep && (sw[j] & 3u) != 0u; }
-        }
-      } while (!ready);
-      int jstop = kLbPer;                             // the lane's nearest predecessor that knows its inclusive prefix
-#pragma unroll
-      for (int j = kLbPer - 1; j >= 0; j--) if ((sw[j] & 3u) == 2u) jstop = j;
-      Summ pj[kLbPer];
-#pragma unroll
-      for (int j = 0; j < kLbPer; j++)
-        pj[j] = (idx0 - j >= 0 && j <= jstop) ? ld_summ_cg((sw[j] & 3u) == 2u ? &slots[idx0 - j].incl : &slots[idx0 - j].aggr) : summ_identity();
-      Summ v = pj[0];
-#pragma unroll
-      for (int j = 1; j < kLbPer; j++) if (j <= jstop) v = fold(pj[j], v);      // older ones fold in from the left
-      const unsigned incl = __ballot_sync(0xffffffffu, jstop < kLbPer);
+    for (int hi = (int)blockIdx.x - 1; hi >= 0; hi -= 32) {
+      const int idx = hi - (int)lane;
+      uint32_t sw = ep | 2u;                          // before the first CTA: an inclusive prefix equal to the identity
+      if (idx >= 0) do { sw = status[idx]; } while ((sw & ~3u) != ep || (sw & 3u) == 0u);
+      __threadfence();
+      const unsigned incl = __ballot_sync(0xffffffffu, (sw & 3u) == 2u);
       const uint32_t last = incl ? (uint32_t)__ffs(incl) - 1u : 32u;
-      if (lane > last) v = summ_identity();
-      // ordered: lane 0 holds the nearest predecessors, so the fold runs from the highest lane down
+      Summ v = summ_identity();
+      if (idx >= 0 && lane <= last) v = ld_summ_cg((sw & 3u) == 2u ? &slots[idx].incl : &slots[idx].aggr);
+      // ordered: lane 0 is the nearest predecessor, so the fold runs from the highest lane down
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         Summ older;
@@ -984,7 +956,8 @@ __global__ void __launch_bounds__(kRecCtaThreads) k_records(DecodeParams P) {
 #pragma unroll
       for (uint32_t k = 1; k < kRecThreads / 32; k++) aggr = fold(aggr, wtot[k]);
       if (blockIdx.x == 0) slots[0].incl = aggr; else slots[blockIdx.x].aggr = aggr;
-      st_release_u32(status + blockIdx.x, ep | (blockIdx.x == 0 ? 2u : 1u));
+      __threadfence();
+      status[blockIdx.x] = ep | (blockIdx.x == 0 ? 2u : 1u);
     }
     for (uint32_t k = 0; k < wid; k++) wpre = fold(wpre, wtot[k]);
   }
@@ -999,7 +972,7 @@ __global__ void __launch_bounds__(kRecCtaThreads) k_records(DecodeParams P) {
 #pragma unroll
       for (uint32_t k = 1; k < kRecThreads / 32; k++) aggr = fold(aggr, wtot[k]);
       const Summ incl_total = fold(blk_excl_sh, aggr);
-      if (blockIdx.x) { slots[blockIdx.x].incl = incl_total; st_release_u32(status + blockIdx.x, ep | 2u); }
+      if (blockIdx.x) { slots[blockIdx.x].incl = incl_total; __threadfence(); status[blockIdx.x] = ep | 2u; }
       if (!blk_fits) atomicOr(P.abort_flag, ABORT_CELLS);
       if (blockIdx.x == n_blocks - 1u) {
         P.total[0] = incl_total;
