@@ -170,7 +170,7 @@ NcclApi& nccl_api() {
 constexpr size_t kScalarWords = 16;
 // device scalar block: 16 words followed by the DevCarry
 //  [0] first_error key  [1..3] insert/update/delete bytes  [4] events  [5] heap_top  [7] long_count  [8] copy_count  [9] heap_overflow
-//  [10] arr_top  [11] perm_len  [12] n_act (k_act_scan)  [13] ABORT_* bits (k_chase, k_records)  [14] n_frames (k_chase)
+//  [10] arr_top  [11] perm_len  [12] n_act (k_act_scan)  [13] ABORT_* bits (k_chase, k_records)  [14] n_frames (k_chase)  [15] CTAs of k_chase that have published their state aggregate (shards)
 constexpr size_t kScalarBlockBytes = kScalarWords * 8 + sizeof(DevCarry);
 
 }  // namespace
@@ -217,6 +217,7 @@ struct etl_dec_ctx {
   DevBuf<uint64_t> d_frame_off{bufs};      // frame offsets in stream order (k_chase → k_records)
   DevBuf<unsigned long long> d_chase_status{bufs};
   DevBuf<ScanSlot> d_scan_slots{bufs};
+  DevBuf<Summ> d_chase_summ{bufs};
   DevBuf<Summ> d_total{bufs};
   uint32_t scan_epoch = 0;
   uint32_t max_frame_hint = 0;            // etl_dec_input.max_frame_len of the batch in flight (0 = unknown)
@@ -256,7 +257,8 @@ struct etl_dec_ctx {
   etl_host_allgather_fn host_allgather = nullptr;   // exchange through the host instead of NCCL (etl_dec_comm_init_host)
   void* host_user = nullptr;
   int rank = 0, n_ranks = 1;
-  size_t rel_slot = 64 << 10;            // bytes per rank in the relation-update exchange (grows on demand)
+  size_t rel_slot = 4 << 10;             // bytes per rank in the relation-update exchange (grows on demand)
+  uint8_t* h_seam = nullptr; size_t h_seam_cap = 0;   // pinned copy of the gathered seam blocks
 };
 
 #define CK(call)                                                                         \
@@ -378,6 +380,7 @@ static void ctx_release(etl_dec_ctx* ctx) {
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
   if (ctx->h_up) cudaFreeHost(ctx->h_up);
   if (ctx->h_rel_x) cudaFreeHost(ctx->h_rel_x);
+  if (ctx->h_seam) cudaFreeHost(ctx->h_seam);
   if (ctx->h_total) cudaFreeHost(ctx->h_total);
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -824,6 +827,7 @@ static int prepare(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t flags, bo
   CK(ctx->d_seg_rec_base.ensure(P.n_anchors + 1));
   CK(ctx->d_chase_status.ensure_zeroed((P.n_anchors + kChaseThreads - 1) / kChaseThreads + 1, st));
   P.seg_rec_base = ctx->d_seg_rec_base.ptr(); P.chase_status = ctx->d_chase_status.ptr();
+  if (sharded) { CK(ctx->d_chase_summ.ensure((P.n_anchors + kChaseThreads - 1) / kChaseThreads + 1)); P.chase_summ = ctx->d_chase_summ.ptr(); }
   const size_t line_words = (in->len + 4095) / 4096 + 1;
   CK(ctx->d_line_bad.ensure(line_words)); CK(ctx->d_dead.ensure(P.n_anchors + 1));
   P.line_bad = ctx->d_line_bad.ptr(); P.dead = ctx->d_dead.ptr();
@@ -835,7 +839,7 @@ static int prepare(etl_dec_ctx* ctx, const etl_dec_input* in, uint32_t flags, bo
   P.first_error = sc; P.metrics = sc + 1;
   P.heap_top = sc + 5; P.heap_overflow = (unsigned int*)(sc + 9); P.arr_top = sc + 10;
   P.perm_len = (unsigned int*)(sc + 11); P.n_act = (unsigned int*)(sc + 12); P.abort_flag = (unsigned int*)(sc + 13);
-  P.n_frames = (unsigned int*)(sc + 14);
+  P.n_frames = (unsigned int*)(sc + 14); P.chase_done = (unsigned int*)(sc + 15);
   P.copy_count = (unsigned int*)(sc + 8);
   P.dc = reinterpret_cast<const DevCarry*>(sc + kScalarWords); P.dc_out = reinterpret_cast<DevCarry*>(sc + kScalarWords);
   const uint32_t act_blocks = (P.n_anchors + kActThreads - 1) / kActThreads;
@@ -885,10 +889,13 @@ static int ensure_record_scratch(etl_dec_ctx* ctx, uint64_t cap) {
   P.scan_status = ctx->d_scan_status.ptr(); P.scan_slots = ctx->d_scan_slots.ptr();
   return ETL_OK;
 }
-static void launch_chase(etl_dec_ctx* ctx, uint32_t mode) {
+// seam: a shard on the optimistic path — the walk also folds the frames' effect on the stream state and writes the seam block
+static void launch_chase(etl_dec_ctx* ctx, uint32_t mode, bool seam = false) {
   DecodeParams& P = ctx->P;
   if (mode & 1u) P.scan_epoch = next_epoch(ctx);
-  k_chase<<<(P.n_anchors + kChaseThreads - 1) / kChaseThreads, kChaseThreads, 0, ctx->stream>>>(P, mode);
+  const uint32_t grid = (P.n_anchors + kChaseThreads - 1) / kChaseThreads;
+  if (seam) k_chase<true><<<grid, kChaseThreads, 0, ctx->stream>>>(P, mode);
+  else k_chase<false><<<grid, kChaseThreads, 0, ctx->stream>>>(P, mode);
   ctx->launches += 1;
 }
 // totals only (FULL = false) or the record plane (FULL = true); `n_max` bounds the number of frames
@@ -916,7 +923,7 @@ static int launch_index(etl_dec_ctx* ctx, bool exact) {
       ctx->launches += 3;
     }
     if (dead_mode() == 0) CK(launch_dead_side(ctx, st));   // underneath everything that follows (needs only the dead-segment list)
-    if (!exact) launch_chase(ctx, 3u);
+    if (!exact) launch_chase(ctx, 3u, P.seam_send != nullptr);
     else {
       P.frame_cap = ~0ull;
       launch_chase(ctx, 1u);
@@ -1034,6 +1041,10 @@ static int launch_emit_kernels(etl_dec_ctx* ctx) {
   CK(cudaEventRecord(ctx->ev[4], st));
   CK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars.ptr(), kScalarWords * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(ctx->h_total, P.total, sizeof(Summ), cudaMemcpyDeviceToHost, st));
+  if (P.seam_all && P.n_ranks > 1) {                  // every rank's totals: the host needs them for the carry-out (and the poison check)
+    if (int rc = ensure_pinned(ctx, &ctx->h_seam, &ctx->h_seam_cap, sizeof(SeamBlock) * P.n_ranks)) return rc;
+    CK(cudaMemcpyAsync(ctx->h_seam, P.seam_all, sizeof(SeamBlock) * P.n_ranks, cudaMemcpyDeviceToHost, st));
+  }
   return ETL_OK;
 }
 
@@ -1089,7 +1100,7 @@ static int run_decode(etl_dec_ctx* ctx, const etl_stream_state* carry_in, uint64
     if (int rc = launch_emit(ctx, b, cap_r, cap_c, 0, &L, &scalar_heap)) return fail(rc);
     if (int rc = ensure_record_scratch(ctx, 2 * cap_r + 65536)) return fail(rc);
     if (int rc = launch_index(ctx, false)) return fail(rc);
-    if (sharded) { if (int rc = launch_summary(ctx)) return fail(rc); }          // the seam block, before the exchange
+    if (sharded && !P.n_anchors) { if (int rc = launch_summary(ctx)) return fail(rc); }   // (an empty range: the identity seam; otherwise k_chase wrote the seam block)
   } else if (!totals_known) {
     if (int rc = launch_index(ctx, true)) return fail(rc);
     if (int rc = launch_summary(ctx)) return fail(rc);
@@ -1124,7 +1135,7 @@ static int run_decode(etl_dec_ctx* ctx, const etl_stream_state* carry_in, uint64
     TRACE_MARK(2);
     if (sharded && seams.empty()) {
       seams.resize(ctx->n_ranks);
-      CKB(cudaMemcpy(seams.data(), P.seam_all, sizeof(SeamBlock) * ctx->n_ranks, cudaMemcpyDeviceToHost));
+      memcpy(seams.data(), ctx->h_seam, sizeof(SeamBlock) * ctx->n_ranks);   // copied with the scalars, before the sync
     }
     if (ctx->long_skipped && ctx->h_scalars[7] && !ctx->h_scalars[13]) {
       // the frame-length hint was wrong: long values exist.  Run the passes that were left out, read the scalars again.

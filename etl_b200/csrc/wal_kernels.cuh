@@ -98,6 +98,8 @@ struct DecodeParams {
   uint32_t* scan_status;     // k_records look-back words
   struct ScanSlot* scan_slots;
   uint32_t scan_epoch;       // changes with every launch of a scanning kernel
+  Summ* chase_summ;          // multi-GPU: per-CTA state aggregates of k_chase (the seam block is their fold)
+  unsigned int* chase_done;  // ... and the count of CTAs that have published theirs
   Summ* total;               // [0] = fold of everything (shard seam summary)
   // global grouping of the DML records by frame shape (k_records counts, k_bin_scan lays out, k_perm fills)
   uint32_t* bin_count; uint32_t* bin_cursor; uint32_t n_bins; uint32_t* perm; unsigned int* perm_len;
@@ -448,6 +450,12 @@ __global__ void __launch_bounds__(kActThreads) k_act_small(DecodeParams P) {
 // into `frame_off` in stream order.  Everything after this pass is record-parallel: one thread per frame, coalesced.
 // (Round 1/2a walked the chain twice with the whole per-frame state machine inside the walk — k_index, k_frames:
 // 10 serial hops of ~5 µs each for a 2 KiB segment of 200-byte frames, 60 % of the time of an 8 MiB batch.)
+__device__ __forceinline__ Summ ld_summ_cg(const Summ* p) {      // L2 (another CTA wrote it)
+  const uint4 a = __ldcg(reinterpret_cast<const uint4*>(p)), b = __ldcg(reinterpret_cast<const uint4*>(p) + 1);
+  Summ r;
+  r.lsn = ((uint64_t)a.y << 32) | a.x; r.ord = ((uint64_t)a.w << 32) | a.z; r.n_cells = ((uint64_t)b.y << 32) | b.x; r.n_rec = b.z; r.flags = b.w;
+  return r;
+}
 constexpr int kChaseThreads = 256;
 constexpr int kChaseKeep = 12;
 constexpr uint32_t ABORT_RECORDS = 1u, ABORT_SCRATCH = 2u, ABORT_CELLS = 4u;   // bits of *P.abort_flag
@@ -467,11 +475,21 @@ __device__ __forceinline__ uint32_t chase_flen(const uint8_t* buf, uint64_t pos,
   return flen;
 }
 // mode bit 0: count + scan (writes seg_rec_base, n_frames, the abort bits); bit 1: write frame_off (needs seg_rec_base)
+// SEAM (a multi-GPU shard, counting): the walk also looks at every frame's head and folds its effect on the stream state
+// (Begin / Commit / ordinal consumers — no schema needed); the last CTA to finish folds the CTA aggregates in order and
+// writes the shard's seam block, so that the exchange can start without a separate totals pass over the frames.
+template <bool SEAM>
 __global__ void __launch_bounds__(kChaseThreads) k_chase(DecodeParams P, uint32_t mode) {
   __shared__ uint32_t wsum[kChaseThreads / 32];
   __shared__ uint32_t blk_prefix;
+  __shared__ Summ wagg[SEAM ? kChaseThreads / 32 : 1];
+  __shared__ uint32_t is_last;
   const uint32_t n_act = *P.n_act;
   const uint32_t n_blocks = (n_act + kChaseThreads - 1) / kChaseThreads;
+  if (SEAM && n_blocks == 0u && blockIdx.x == 0 && threadIdx.x == 0 && (mode & 1u) && P.seam_send) {   // no frame starts in this range
+    SeamBlock sb; sb.total = summ_identity(); sb._pad[0] = sb._pad[1] = sb._pad[2] = sb._pad[3] = 0;
+    *P.seam_send = sb;
+  }
   if (blockIdx.x >= n_blocks) return;                 // the grid is sized for a stream with every segment live
   const uint32_t j = blockIdx.x * kChaseThreads + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
@@ -486,16 +504,24 @@ __global__ void __launch_bounds__(kChaseThreads) k_chase(DecodeParams P, uint32_
   for (int k = 0; k < kChaseKeep / 2; k++) dd[k] = 0;
   uint32_t count = 0, kept = 0;
   uint64_t pos_keep = pos0;                           // position after the kept frames
+  Summ acc = summ_identity();                         // SEAM: fold of this segment's frames (n_cells stays 0: a shard's cells are its own)
+  auto flen_at = [&](uint64_t pos) -> uint32_t {
+    if (!SEAM) return chase_flen(P.buf, pos, P.len);
+    const HeadW H = load_head_words(P.buf + pos);
+    const FrameHead h = read_head_w(H, P.len - pos);
+    acc = fold(acc, frame_state_elem(h, P.buf + pos));
+    return h.flen;
+  };
   if (mode & 1u) {
 #pragma unroll
     for (int k = 0; k < kChaseKeep; k++)
       if (pos_keep < stop && pos_keep - pos0 < 65536ull && kept == (uint32_t)k) {   // (anchors are caller data: a "segment" may be longer than a stride)
         dd[k >> 1] |= (uint32_t)(pos_keep - pos0) << (16 * (k & 1));
         kept++;
-        pos_keep += 1ull + chase_flen(P.buf, pos_keep, P.len);
+        pos_keep += 1ull + flen_at(pos_keep);
       }
     count = kept;
-    for (uint64_t pos = pos_keep; pos < stop; count++) pos += 1ull + chase_flen(P.buf, pos, P.len);
+    for (uint64_t pos = pos_keep; pos < stop; count++) pos += 1ull + flen_at(pos);
     uint32_t inc = count;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const uint32_t up = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (uint32_t)d) inc += up; }
@@ -536,6 +562,48 @@ __global__ void __launch_bounds__(kChaseThreads) k_chase(DecodeParams P, uint32_
     __syncthreads();
     base = blk_prefix + before + (inc - count);
     if (live) P.seg_rec_base[j] = base;
+    if (SEAM) {
+      // ordered fold of the CTA's segments (thread order = stream order), published for the last CTA
+      Summ v = acc;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        Summ later;
+        later.lsn = __shfl_down_sync(0xffffffffu, v.lsn, d); later.ord = __shfl_down_sync(0xffffffffu, v.ord, d);
+        later.n_cells = 0; later.n_rec = __shfl_down_sync(0xffffffffu, v.n_rec, d); later.flags = __shfl_down_sync(0xffffffffu, v.flags, d);
+        if (lane + (uint32_t)d < 32u) v = fold(v, later);
+      }
+      if (lane == 0) wagg[wid] = v;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        Summ a = wagg[0];
+#pragma unroll
+        for (uint32_t k = 1; k < kChaseThreads / 32; k++) a = fold(a, wagg[k]);
+        P.chase_summ[blockIdx.x] = a;
+        __threadfence();
+        is_last = atomicAdd(P.chase_done, 1u) == n_blocks - 1u ? 1u : 0u;
+      }
+      __syncthreads();
+      if (is_last && wid == 0) {                      // every CTA has published its aggregate (and the frame count is final)
+        __threadfence();
+        Summ total = summ_identity();
+        for (uint32_t b0 = 0; b0 < n_blocks; b0 += 32u) {
+          Summ w = b0 + lane < n_blocks ? ld_summ_cg(&P.chase_summ[b0 + lane]) : summ_identity();
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            Summ later;
+            later.lsn = __shfl_down_sync(0xffffffffu, w.lsn, d); later.ord = __shfl_down_sync(0xffffffffu, w.ord, d);
+            later.n_cells = 0; later.n_rec = __shfl_down_sync(0xffffffffu, w.n_rec, d); later.flags = __shfl_down_sync(0xffffffffu, w.flags, d);
+            if (lane + (uint32_t)d < 32u) w = fold(w, later);
+          }
+          total = fold(total, w);                     // lane 0 holds the window's fold
+        }
+        if (lane == 0 && P.seam_send) {
+          SeamBlock sb; sb.total = total; sb._pad[0] = sb._pad[1] = sb._pad[2] = sb._pad[3] = 0;
+          if (*reinterpret_cast<volatile unsigned int*>(P.abort_flag) & ABORT_SCRATCH) sb.total.flags |= 0x80000000u;   // offsets missing: every rank starts over
+          *P.seam_send = sb;
+        }
+      }
+    }
   } else if (live) base = P.seg_rec_base[j];
   if ((mode & 2u) && live) {
     uint64_t k = base, pos = pos0;
@@ -852,12 +920,6 @@ struct ScanSlot { Summ aggr; Summ incl; };
     (dst).n_cells = fn(0xffffffffu, (src).n_cells, arg); (dst).n_rec = fn(0xffffffffu, (src).n_rec, arg); \
     (dst).flags = fn(0xffffffffu, (src).flags, arg);                                                      \
   } while (0)
-__device__ __forceinline__ Summ ld_summ_cg(const Summ* p) {      // L2 (another CTA wrote it)
-  const uint4 a = __ldcg(reinterpret_cast<const uint4*>(p)), b = __ldcg(reinterpret_cast<const uint4*>(p) + 1);
-  Summ r;
-  r.lsn = ((uint64_t)a.y << 32) | a.x; r.ord = ((uint64_t)a.w << 32) | a.z; r.n_cells = ((uint64_t)b.y << 32) | b.x; r.n_rec = b.z; r.flags = b.w;
-  return r;
-}
 template <bool FULL>
 __global__ void __launch_bounds__(kRecCtaThreads, 4) k_records(DecodeParams P) {   // 4 CTAs per SM: at most 56 registers
   __shared__ Summ wtot[kRecThreads / 32];
