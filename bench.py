@@ -41,6 +41,15 @@ NO_ERROR = 2**64 - 1
 DATA_ERRORS = []      # first_error of any timed / warm-up decode: a clean synthetic stream must not produce one
 
 
+_REAL_STDOUT = None
+
+
+def emit_line(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -218,7 +227,7 @@ def run_reference(args, rank, world):
             "config": {"workload": f"{w.name}: {w.description}", "scale": args.scale},
             "cpu_baseline": {"value": val, "unit": "GB/s", "cores": threads, "box_cores": box, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU side
@@ -596,15 +605,20 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries the ONE JSON line and nothing else: whatever native code writes to fd 1 (NCCL prints its version banner
+    # there) lands on stderr from here on, and the line goes to the saved descriptor
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
 
-    if world > 1 and "NCCL_DEBUG" not in os.environ:
-        # NCCL's init lines (incl. "nranks N") go to stderr; stdout carries the ONE JSON line
-        os.environ["NCCL_DEBUG"] = "INFO"
+    if world > 1:
+        # NCCL's init lines (incl. "nranks N") on stderr
+        os.environ["NCCL_DEBUG"] = os.environ.get("ETL_NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     from etl_b200 import decoder, workloads as wl
@@ -779,7 +793,7 @@ def main():
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         line.update(extras)
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 
