@@ -267,7 +267,7 @@ class Staged:
 
 def decode_once(dec, st, resident, sharded, carry=None, timing=True):
     inp = st.view(resident, carry)
-    bh = dec.decode_sharded(inp, to_host=not resident) if sharded else dec.decode_input(inp, to_host=not resident, timing=timing)
+    bh = dec.decode_sharded(inp, to_host=not resident, timing=timing) if sharded else dec.decode_input(inp, to_host=not resident, timing=timing)
     s = bh.summary()
     if s.first_error.record_index != NO_ERROR:
         # never raise between collectives (the other ranks would wait for this one for ever): remember it, fail the line later
@@ -276,6 +276,9 @@ def decode_once(dec, st, resident, sharded, carry=None, timing=True):
 
 
 def time_steps(torch, dist, dec, st, resident, sharded, steps, dev, world):
+    """K decode calls as a production caller makes them (ETL_DECODE_NO_TIMING: no per-kernel event queries on the host),
+    bracketed by barrier + synchronize and CUDA events, max over ranks.  The per-kernel breakdown comes from two more calls
+    with the summary timings on, after the timed region."""
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -283,8 +286,7 @@ def time_steps(torch, dist, dec, st, resident, sharded, steps, dev, world):
     rows, launches, last = [], 0, None
     e0.record()
     for _ in range(steps):
-        bh, s = decode_once(dec, st, resident, sharded)
-        rows.append((s.index_ms, s.frames_ms, s.walk_ms, s.cells_ms, s.spans_ms, s.kernel_ms, s.long_ms))
+        bh, s = decode_once(dec, st, resident, sharded, timing=False)
         launches += s.gpu_launches
         last = dict(h2d=int(s.h2d_bytes), d2h=int(s.d2h_bytes), span_bytes=int(s.span_bytes), n_records=int(bh.planes(False).n_records),
                     n_cells=int(bh.planes(False).n_cells))
@@ -295,6 +297,10 @@ def time_steps(torch, dist, dec, st, resident, sharded, steps, dev, world):
     if world > 1:
         dist.barrier()
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    for _ in range(2):                                   # every rank (the sharded call is collective)
+        bh, s = decode_once(dec, st, resident, sharded, timing=True)
+        rows.append((s.index_ms, s.frames_ms, s.walk_ms, s.cells_ms, s.spans_ms, s.kernel_ms, s.long_ms))
+        bh.free()
     return float(ms.item()), np.mean(np.array(rows, dtype=np.float64), axis=0), launches, last
 
 
@@ -773,6 +779,7 @@ def main():
                                         if n_gpus > 1 else "single GPU")),
                        "scaling_note": "efficiency = value_N / (N * value_1): total bytes are fixed under strong scaling, per-GPU bytes under weak",
                        "anchor_stride": args.stride, "l2_policy": "inputs (>=1.25 GiB per GPU) larger than the 126 MB L2",
+                       "timed_calls": "etl_dec_decode(_sharded) with ETL_DECODE_NO_TIMING; roofline.kernels_ms from two more calls with the summary timings on, outside the timed region",
                        "generate_s": round(gen_s, 2), "host_cores": {"box": box, "usable": usable}},
             "roofline": roofline_block(w.name, nbytes, n_anchors, km, ms_per_step, last, args.scale),
             "gpu_launches": launches,

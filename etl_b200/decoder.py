@@ -233,11 +233,12 @@ class Decoder:
         self._host_cb = abi.HOST_ALLGATHER_FN(_cb)      # keep the trampoline alive
         self._check(self._l.etl_dec_comm_init_host(self._ctx, rank, n_ranks, self._host_cb, None))
 
-    def decode_sharded(self, inp: abi.DecInput, to_host: bool = True) -> "BatchHandle":
+    def decode_sharded(self, inp: abi.DecInput, to_host: bool = True, timing: bool = True) -> "BatchHandle":
         """This rank's byte range of one stream: relation-update exchange, index pass, seam all-gather and fold on
         the device, record + tuple passes (etl_dec_decode_sharded)."""
         h = C.c_void_p()
-        self._check(self._l.etl_dec_decode_sharded(self._ctx, C.byref(inp), abi.RESULTS_TO_HOST if to_host else 0, C.byref(h)))
+        flags = (abi.RESULTS_TO_HOST if to_host else 0) | (0 if timing else abi.NO_TIMING)
+        self._check(self._l.etl_dec_decode_sharded(self._ctx, C.byref(inp), flags, C.byref(h)))
         return BatchHandle(self, h)
 
     # -- initial-sync COPY rows (etl_dec_copy_decode; table_row.rs:25-165 for a whole buffer of rows) --------------
