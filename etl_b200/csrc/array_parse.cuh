@@ -56,7 +56,7 @@ __device__ __forceinline__ uint32_t parse_text_cell_impl(uint32_t kind, const ui
   }
 }
 
-// out-of-line entry for k_walk's cold kinds: heap position by value, so the caller's state stays in registers
+// out-of-line entry for k_heavy's cold kinds: heap position by value, so the caller's state stays in registers
 __device__ __noinline__ uint32_t parse_text_cell(uint32_t kind, const uint8_t* s, uint32_t n, uint64_t soff, uint8_t* heap,
                                                  uint64_t hpos, CellOut& o) {
   HeapCursor hc{heap, hpos};

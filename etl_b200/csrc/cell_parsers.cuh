@@ -560,7 +560,7 @@ __device__ __forceinline__ uint32_t swar_parse8(uint64_t x) {
 __device__ __forceinline__ bool swar_all_digits(uint64_t x) {
   return (((x + 0x4646464646464646ull) | (x - 0x3030303030303030ull)) & 0x8080808080808080ull) == 0ull;
 }
-// a table in global memory: a local array would be re-materialised (18 stores) by every thread of k_cells
+// a table in global memory: a local array would be re-materialised (18 stores) by every thread of the cell kernels
 __device__ const uint64_t kPow10[9] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull};
 __device__ __forceinline__ uint64_t pow10_u64(uint32_t k) { return kPow10[k]; }  // k in 0..8
 
@@ -817,7 +817,7 @@ __device__ __forceinline__ uint32_t parse_numeric_sync(unsigned mask, const uint
     *reinterpret_cast<etl_numeric_hdr*>(hc.heap + off) = hdr;
     o.tag = ETL_CELL_NUMERIC | ((uint32_t)hdr.pushed_groups << 16); o.val = off; o.aux = nd;
   }
-  if (code == 0xFFFFFFFFu) {                          // own copies: `o` must not have its address taken (see k_walk)
+  if (code == 0xFFFFFFFFu) {                          // own copies: `o` must not have its address taken (see parse_heavy_sync)
     HeapCursor h2{heap, hpos};
     CellOut t; t.tag = 0; t.val = 0; t.aux = 0;
     code = parse_numeric(s, n, h2, t);

@@ -658,7 +658,7 @@ __device__ __forceinline__ bool has_high_bits(const uint8_t* s, uint32_t n) {
   const uint32_t nw = (lead + n + 7u) >> 3;          // words touched
   const uint32_t tail = (lead + n) & 7u;
   // every load is independent of the others: issue them in groups of four so that a 60-byte cell costs two
-  // memory round trips instead of eight (a load-OR-load chain was the longest stall of k_cells)
+  // memory round trips instead of eight (a load-OR-load chain was the longest stall of the round-1 cell kernel)
   const uint64_t first = w[0], last = w[nw - 1];
   uint64_t acc = 0;
   for (uint32_t i = 1; i + 1 < nw; i += 4) {
@@ -684,8 +684,8 @@ __device__ __forceinline__ void put_cell(const DecodeParams& P, uint64_t idx, ui
 }
 constexpr int kWideLen = 96;     // text cells at least this long are validated with 16-byte loads
 constexpr int kCoopLen = 512;    // ... these by the whole warp; the part that covers whole dead segments by k_utf8_dead
-// UTF-8 validation of bytes [lo, hi) of one text cell by `nthreads` cooperating threads (a warp, a
-// CTA, or a CTA of k_utf8_spans): 16-byte aligned chunks, 4 independent loads in flight per thread.
+// UTF-8 validation of bytes [lo, hi) of one text cell by `nthreads` cooperating threads (one thread, a warp,
+// or a half-warp of k_long_cells): 16-byte aligned chunks, 4 independent loads in flight per thread.
 // An all-ASCII chunk costs one load + one test; a chunk with high bits is checked with the
 // position-local rule over [clo, chi+3) so the following chunk never has to look back; the first 16
 // bytes of the range are always checked with look-back (a range may start in the middle of a cell).
@@ -1099,7 +1099,7 @@ __global__ void __launch_bounds__(kRecCtaThreads, 4) k_records(DecodeParams P) {
           { const DevSchema* rs = find_schema(P, h.rel, pos); if (rs && rs->effective_off == pos) rschema = (int32_t)rs->batch_index; }
           break;
         case 'I': case 'U': case 'D': {              // apply.rs:2092-2203
-          // the tuple structure is validated by k_walk (a malformed frame outranks state errors)
+          // the tuple structure is validated by k_rows (a malformed frame outranks state errors)
           if (!in_tx) report_error(P, gidx, SEQ_STATE, ETL_E_TX_STATE);
           commit_lsn = st.lsn; ordinal = st.ord;
           if (!s) {                                  // no schema to walk with: structure check only
@@ -1143,7 +1143,7 @@ __global__ void __launch_bounds__(kRecCtaThreads, 4) k_records(DecodeParams P) {
         default: break;                              // Origin / Type: structure only
       }
     }
-    // a record k_walk must not touch keeps schema = -1 only when it failed before conversion
+    // a record k_rows must not touch keeps schema = -1 only when it failed before conversion
     if (h.kind == 'I' || h.kind == 'U' || h.kind == 'D') {
       if (!ok) rschema = -1;
       else if (rschema >= 0) atomicAdd(&hist[walk_bin(P, s->layout, h.kind, rflags)], 1u);

@@ -4,7 +4,7 @@
 // fuzz them against the oracle with millions of spellings (tests/test_device_parsers_on_host.py).  It is not a
 // product path and nothing outside tests/ loads it: the product has no CPU fallback.
 //
-// emu_parse_cell mirrors what k_cells does for one cell (wal_kernels.cuh: UTF-8, then the per-kind fast path with
+// emu_parse_cell mirrors what k_rows / k_heavy do for one cell (rows_kernel.cuh: UTF-8, then the per-kind fast path with
 // the exact parser as fallback); with fast=0 it takes only the exact parsers (what parse_text_cell_impl does).
 #include <stdint.h>
 #include <string.h>
@@ -58,12 +58,12 @@ extern "C" uint32_t emu_parse_cell(uint32_t kind, const uint8_t* text, uint32_t 
   CellOut o; o.tag = 0; o.val = 0; o.aux = 0;
   HeapCursor hc{heap, 0};
   uint32_t code = 0;
-  if (!utf8_valid(s, n)) code = ETL_E_UTF8;      // event.rs:972 (k_cells: has_high_bits + the position-local rule)
+  if (!utf8_valid(s, n)) code = ETL_E_UTF8;      // event.rs:972 (k_rows: has_high_bits + the position-local rule)
   else if (!fast) code = exact(kind, s, n, 0, hc, o);
   else {
     const unsigned mask = 1u;
     int64_t iv = 0;
-    switch (kind) {                                // k_cells' switch
+    switch (kind) {                                // parse_light_sync / parse_heavy_sync
       case ETL_K_STRING: o.tag = ETL_CELL_STRING; o.val = 0; o.aux = n; break;
       case ETL_K_I32: case ETL_K_I64: case ETL_K_I16: case ETL_K_U32: {
         const uint64_t pos_limit = kind == ETL_K_I32 ? 2147483647ull : (kind == ETL_K_I64 ? 9223372036854775807ull : (kind == ETL_K_I16 ? 32767ull : 4294967295ull));

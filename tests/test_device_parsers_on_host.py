@@ -1,7 +1,7 @@
 """The DEVICE cell parsers, compiled for the host with one-lane stand-ins for the warp intrinsics
 (tests/emul/host_parsers.cpp — test infrastructure, not a product path), fuzzed against the oracle at a volume the
 GPU tests cannot afford: 100 000 spellings per decode class (ETL_HOST_FUZZ_N; 400 000 each was run once: 6.4 M, all equal), each through the exact path and through the fast
-path k_cells takes.  Same verdict, same error code, same typed value."""
+path k_rows / k_heavy take.  Same verdict, same error code, same typed value."""
 import ctypes as C
 import os
 import random

@@ -200,7 +200,7 @@ def test_two_phase_shards_with_seam_fold(gpu, oracle_mod):
 
 def test_two_phase_error_in_later_shard_reports_global_index(gpu, oracle_mod):
     """A data error in the third range carries its GLOBAL record index (record_index_base > 0 in report_error and
-    k_long_verdict), and is the index the oracle reports for the whole stream."""
+    k_long_cells), and is the index the oracle reports for the whole stream."""
     from shard_util import mid_tx_cuts
     w = wl.make("c2", 0.02, n_segments=1)
     stream, _ = w.generate()
