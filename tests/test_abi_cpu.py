@@ -82,6 +82,19 @@ def test_stager_append_bodies_equals_framed():
     assert st.host_array().tobytes() == raw
     v = st.view()
     assert v.n_relations == 1 and v.n_anchors == -(-len(raw) // 256)
+    # the frame-length hint: the longest frame, 'd' + length field + body (both ways of staging agree)
+    longest, pos = 0, 0
+    while pos < len(raw):
+        n = int.from_bytes(raw[pos + 1:pos + 5], "big")
+        longest = max(longest, 1 + n)
+        pos += 1 + n
+    assert v.max_frame_len == longest
+    st2 = Stager(1 << 16, 256)
+    st2.append_framed(raw)
+    assert st2.view().max_frame_len == longest
+    st2.reset()
+    assert st2.view().max_frame_len == 0
+    st2.close()
     st.close()
 
 
