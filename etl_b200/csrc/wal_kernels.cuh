@@ -911,7 +911,13 @@ __global__ void __launch_bounds__(kPermThreads) k_perm(DecodeParams P) {
 // Truncate, and counts the frame shapes for k_perm.
 //   FULL = false: totals only (P.total, the seam block, the cells-overflow bit) — first batch (plane sizes unknown),
 //                 multi-GPU shards (the carry-in arrives through the seam exchange after this pass).
-constexpr int kRecThreads = 256;                      // records per CTA, one thread each
+#ifndef ETL_REC_THREADS
+#define ETL_REC_THREADS 512
+#endif
+// Records per CTA, one thread each.  The look-back chain advances one window of 32 CTAs per L2 round trip (~1.5 us with
+// the fold): with 256 records per CTA that alone capped the pass at 5.5 records/ns on every workload (C2 / C4 / C5:
+// 0.164 / 0.185 / 0.158 ns per record, ncu: a third of the samples at the barrier behind the look-back warp).
+constexpr int kRecThreads = ETL_REC_THREADS;
 constexpr int kRecCtaThreads = kRecThreads + 32;      // + the look-back warp
 struct ScanSlot { Summ aggr; Summ incl; };
 #define SUMM_SHFL(dst, src, fn, arg)                                                                     \
@@ -921,7 +927,7 @@ struct ScanSlot { Summ aggr; Summ incl; };
     (dst).flags = fn(0xffffffffu, (src).flags, arg);                                                      \
   } while (0)
 template <bool FULL>
-__global__ void __launch_bounds__(kRecCtaThreads, 4) k_records(DecodeParams P) {   // 4 CTAs per SM: at most 56 registers
+__global__ void __launch_bounds__(kRecCtaThreads, kRecThreads >= 512 ? 2 : 4) k_records(DecodeParams P) {
   __shared__ Summ wtot[kRecThreads / 32];
   __shared__ Summ blk_excl_sh;
   __shared__ uint32_t hist[FULL ? kMaxBins : 1];     // frame shapes of the CTA's DML records
@@ -949,7 +955,7 @@ __global__ void __launch_bounds__(kRecCtaThreads, 4) k_records(DecodeParams P) {
   if (blockIdx.x >= n_blocks) return;                // the grid is sized for the capacity of the planes
   if (FULL) { for (uint32_t i = threadIdx.x; i < P.n_bins; i += blockDim.x) hist[i] = 0; }
   const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-  const bool lb_warp = wid == kRecThreads / 32;      // warp 8 holds no records: it looks back while the others read their heads
+  const bool lb_warp = wid == kRecThreads / 32;      // the last warp holds no records: it looks back while the others read their heads
   const uint32_t r = blockIdx.x * kRecThreads + threadIdx.x;
   const bool live = !lb_warp && r < n_rec;
   volatile uint32_t* const status = P.scan_status;
