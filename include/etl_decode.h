@@ -361,7 +361,7 @@ typedef struct etl_dec_summary {
   float emit_ms;          /* pass B+C: k_records … k_long_cells */
   float frames_ms;        /* k_records (stream-state scan + record plane) */
   float walk_ms;          /* k_bin_scan + k_perm (shape bins) */
-  float spans_ms;         /* k_utf8_dead (structure-blind UTF-8 pass over segments without a frame start; side stream) */
+  float spans_ms;         /* k_utf8_dead (structure-blind UTF-8 pass over segments without a frame start) */
   float cells_ms;         /* k_rows (tuples → rows: staging, walk, UTF-8, per-kind parsers, cell plane) */
   float long_ms;          /* k_long_cells (verdicts of the long text cells: line bitmap + edges) */
   uint64_t h2d_bytes, d2h_bytes; /* bytes copied host→device / device→host for this batch */
