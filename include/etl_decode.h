@@ -306,6 +306,9 @@ typedef struct etl_dec_seam {
   uint8_t _pad[6];
 } etl_dec_seam;
 
+/* Limits of one call: len < 1 TiB and fewer than 2^32 frames (record indices inside a batch are 32-bit: a 64 GiB
+ * stream of nothing but 23-byte keepalives is still below it); a longer stream is decoded in several calls chained
+ * through carry_in / carry_out, like the reference's batches. */
 int etl_dec_decode(etl_dec_ctx*, const etl_dec_input*, uint32_t flags, etl_dec_batch** out);
 int etl_dec_decode_sharded(etl_dec_ctx*, const etl_dec_input*, uint32_t flags, etl_dec_batch** out);
 /* two-phase form: the caller exchanges the seam summaries itself (tests; hosts without NCCL) */
